@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the B200-native build + traversal path on BASELINE.json's scaling config.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE config 3's stand-in — the reference's own NUMBER_OF_CLONES mechanism on the
+Stanford bunny: 30 clones = 1,078,411 spheres (the report's "Happy Buddha" count is 30 x 35,947), 3840x2160,
+4 spp, dataStructure = LBVH, one light, shadows off (= the reference's behaviour: trace_more is a stub).
+A step is one frame: jitter stream regeneration + ray generation + traversal + intersection + shading +
+quantisation of all 33,177,600 primary rays (+ the NCCL framebuffer gather when N>1).  The frame is FIXED and
+its scanline tiles are interleaved over the ranks, so scaling is strong.
+
+value  = rays/s with the scene and tree resident in HBM (device-side time, CUDA events, max over ranks).
+e2e    = the same frame through the C-ABI a reference user would call, per step: H2D of the sphere table,
+         rtds_build (LBVH), render, D2H of the RGB8 frame on rank 0.
+roofline = algorithmic bytes of the render kernel (32 B x slab tests + 16 B x sphere tests + 16 B per ray,
+         from the kernel's own counters) / its CUDA-event duration, against MEASURED_PEAKS.json's hbm_gbs.
+cpu_baseline = the UNMODIFIED reference (oracle/_ref, kind "reference"; else the oracle port) timed on one host
+         core on a bounded sample of the same frame's rows.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+W, H, SPP, CLONES = 3840, 2160, 4, 30
+TILE_ROWS = 8
+WORKLOAD = ("buddha-standin: bunny.obj x30 clones (NUMBER_OF_CLONES, main.cpp:61) = 1,078,411 spheres, "
+            "3840x2160, aa_samples 4, dataStructure LBVH, 1 light, shadows off (reference behaviour)")
+
+
+def bunny_vertices():
+    return np.fromfile(os.path.join(ROOT, "tests", "golden", "bunny_vertices.f32"), np.float32).reshape(-1, 3)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ------------------------------------------------------------------------------------------------------
+def sample_bands(n_bands, band_rows):
+    """Evenly spaced bands of rows over the frame (the image is sky above, bunny in the middle, ground below)."""
+    step = H // n_bands
+    return [(i * step + (step - band_rows) // 2, i * step + (step - band_rows) // 2 + band_rows) for i in range(n_bands)]
+
+
+class CpuArm:
+    """The reference's own CPU implementation: oracle/_ref (unmodified reference, kind 'reference') when it was
+    compiled, else the oracle port (kind 'port')."""
+
+    def __init__(self):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import conftest as T
+        self.T = T
+        self.rt = entry.load_rtds()
+        self.sph, self.mat = self.rt.scene_from_vertices(bunny_vertices(), CLONES)
+        ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_oracle.so")
+        self.kind = "reference" if os.path.exists(ref_so) else "port"
+        if self.kind == "reference":
+            self.ref = T.Ref()
+            self.ref.scene_from_spheres(self.sph, self.mat)
+            t0 = time.perf_counter()
+            self.total_nodes, self.build_s = self.ref.build(self.rt.LBVH)     # constructLBVHTree, as main.cpp:832
+            self.build_wall = time.perf_counter() - t0
+        else:
+            self.oracle = T.Oracle()
+            t0 = time.perf_counter()
+            rc, self.nodes, self.order, _ = self.oracle.build_bvh(self.sph, self.sph.shape[0] - 1)
+            self.build_s = self.build_wall = time.perf_counter() - t0
+            self.total_nodes = self.nodes.shape[0]
+
+    def render_bands(self, bands):
+        rays, secs = 0, 0.0
+        for (y0, y1) in bands:
+            if self.kind == "reference":
+                _, _, _, s = self.ref.render_rows(self.rt.LBVH, W, H, SPP, y0, y1)
+            else:
+                t0 = time.perf_counter()
+                self.oracle.render_rows(self.sph, self.mat, self.nodes, self.order, W, H, SPP, y0, y1, want_hit=False)
+                s = time.perf_counter() - t0
+            rays += (y1 - y0) * W * SPP
+            secs += s
+        return rays, secs
+
+
+def _child_render(arm, bands, conn):
+    rays, secs = arm.render_bands(bands)
+    conn.send((rays, secs))
+    conn.close()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    arm = CpuArm()
+    # bounded sample: 2 rows per band, as many bands as keep one step near ~8 s on `cores` processes
+    n_bands = max(cores, min(270, cores * 12))
+    bands = sample_bands(n_bands, 2)
+    chunks = [bands[i::cores] for i in range(cores)]
+    ctx = mp.get_context("fork")        # children share the built scene + tree copy-on-write
+
+    def one_step():
+        t0 = time.perf_counter()
+        procs, conns = [], []
+        for ch in chunks:
+            a, b = ctx.Pipe(False)
+            p = ctx.Process(target=_child_render, args=(arm, ch, b))
+            p.start()
+            procs.append(p)
+            conns.append(a)
+        res = [c.recv() for c in conns]
+        for p in procs:
+            p.join()
+        return sum(r[0] for r in res), time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        one_step()
+    rays, secs = 0, 0.0
+    for _ in range(args.steps):
+        r, s = one_step()
+        rays += r
+        secs += s
+    value = rays / secs / 1e6
+    sample = f"{n_bands} bands x 2 rows of the 3840x2160x4spp frame per step ({rays // max(args.steps, 1)} rays), {cores} processes"
+    line = {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "width": W, "height": H, "aa_samples": SPP, "n_prims": int(arm.sph.shape[0]),
+                       "accel": "LBVH (reference: constructLBVHTree)"},
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": arm.kind, "sample": sample,
+                             "build_s": arm.build_s, "build_ms_per_mprim": 1000 * arm.build_s / (arm.sph.shape[0] / 1e6)},
+            "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    rt = entry.load_rtds()
+    ctx = rt.Rtds(local_rank)              # raises if the CUDA library / GPU is missing: no fallback
+    sph, mat = rt.scene_from_vertices(bunny_vertices(), CLONES)
+    n = sph.shape[0]
+    sph_pin = torch.from_numpy(sph).pin_memory()
+    mat_pin = torch.from_numpy(mat).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # resident scene + tree
+    ctx.set_spheres(sph, mat)
+    build_stats = [ctx.build(rt.LBVH, mode=rt.MODE_TRUE) for _ in range(4)][1:]
+    build_ms = float(np.median([b["ms"] for b in build_stats]))
+
+    rows = rt.rows_for_rank(H, TILE_ROWS, rank, world)
+    max_rows = max(rt.rows_for_rank(H, TILE_ROWS, r, world) for r in range(world))
+    my_rows = torch.zeros((max_rows, W, 3), dtype=torch.uint8, device=dev)
+    gathered = [torch.zeros_like(my_rows) for _ in range(world)] if (world > 1 and rank == 0) else None
+    frame_host = torch.zeros((H, W, 3), dtype=torch.uint8).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    params = ctx.render_params(W, H, SPP, exact=False, rank=rank, world=world, tile_rows=TILE_ROWS)
+    row_index = [torch.from_numpy(rt.owned_rows(H, TILE_ROWS, r, world)).to(dev) for r in range(world)] if rank == 0 else None
+    frame_dev = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev) if rank == 0 else None
+
+    def step_resident():
+        st = ctx.render_device(rt.LBVH, params, my_rows.data_ptr())
+        if world > 1:
+            dist.gather(my_rows, gathered, dst=0)
+        return st
+
+    def assemble_and_download():
+        if rank != 0:
+            return
+        if world > 1:
+            for r in range(world):
+                frame_dev[row_index[r]] = gathered[r][: row_index[r].numel()]
+            frame_host.copy_(frame_dev, non_blocking=True)
+        else:
+            frame_host.copy_(my_rows[:H], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def step_e2e():
+        # what main.cpp does per run, through the C ABI with host buffers
+        ctx.lib.rtds_set_spheres(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), n)
+        ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+        st = step_resident()
+        assemble_and_download()
+        return st
+
+    def timed(step_fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        if sampler:
+            sampler.start()
+        per_step, stats = [], []
+        for _ in range(steps):
+            flush.fill_(1)                      # L2 flush between timed iterations (outside the event pair)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            stats.append(step_fn())
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            per_step.append(float(ms.item()))
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        return per_step, stats, clocks
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    per_step, stats, clocks = timed(step_resident, args.steps, args.warmup, sampler)
+    total_rays = W * H * SPP
+    ms_per_step = float(np.mean(per_step))
+    value = total_rays / (ms_per_step * 1e-3) / 1e6
+
+    e2e_steps, _, _ = timed(step_e2e, max(2, min(args.steps, 5)), 1)
+    e2e_ms = float(np.mean(e2e_steps))
+    e2e_value = total_rays / (e2e_ms * 1e-3) / 1e6
+
+    # counters (sum over ranks) and rank 0's kernel for the roofline
+    k_ms = float(np.mean([s["ms_kernel"] for s in stats]))
+    cnt = torch.tensor([stats[-1]["node_tests"], stats[-1]["prim_tests"], stats[-1]["primary_rays"], stats[-1]["node_visits"]],
+                       dtype=torch.float64, device=dev)
+    mine = cnt.clone()
+    if world > 1:
+        dist.all_reduce(cnt)
+    launches_per_step = stats[-1]["kernel_launches"]
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg_bytes = 32.0 * mine[0].item() + 16.0 * mine[1].item() + 16.0 * mine[2].item()   # this rank's launch
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "render_kernel_traffic.json")
+        if world == 1 and os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "width": W, "height": H, "aa_samples": SPP, "n_prims": int(n),
+                           "accel": "LBVH true mode (30-bit Morton, onesweep, Karras, atomic refit)", "traversal": "ordered, pruned (exact=0)",
+                           "partition": f"interleaved {TILE_ROWS}-row scanline tiles over {world} rank(s); NCCL gather of RGB8 rows" if world > 1 else "single GPU",
+                           "l2": "flushed between timed steps (256 MiB fill); per-frame inputs (531 MB jitter words + 90 MB tree) exceed L2"},
+                "rays_per_step": total_rays,
+                "per_ray": {"slab_tests": cnt[0].item() / total_rays, "sphere_tests": cnt[1].item() / total_rays,
+                            "node_visits": cnt[3].item() / total_rays,
+                            "algorithmic_bytes": (32.0 * cnt[0].item() + 16.0 * cnt[1].item()) / total_rays + 16.0},
+                "build": {"lbvh_ms": build_ms, "ms_per_mprim": build_ms / (n / 1e6), "n_prims": int(n),
+                          "kernel_launches": build_stats[-1]["kernel_launches"]},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "kernel": "render_kernel<1> (rank 0's launch)", "kernel_ms": k_ms,
+                             "peak_source": peak_src},
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(2 * n * 16) * world,
+                        "d2h_bytes_per_step": W * H * 3,
+                        "what": "per step: rtds_set_spheres (H2D from pinned) + rtds_build(LBVH) + render + gather + D2H of the RGB8 frame"},
+                "gpu_launches": int(launches_per_step * args.steps * world),
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                arm = CpuArm()
+                bands = sample_bands(60, 2)
+                rays, secs = arm.render_bands(bands)
+                line["cpu_baseline"] = {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": 1, "kind": arm.kind,
+                                        "sample": f"60 bands x 2 rows of the same frame ({rays} rays), 1 thread",
+                                        "build_s": arm.build_s, "build_ms_per_mprim": 1000 * arm.build_s / (n / 1e6)}
+            except Exception as ex:   # the baseline is a reported side number; never lose the bench line over it
+                line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 1, "kind": "unavailable", "sample": repr(ex)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

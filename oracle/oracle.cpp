@@ -1,0 +1,514 @@
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+//
+// oracle/oracle.cpp: CPU restatement ("port") of the reference's hot path, written from the reference's
+// behaviour, each function citing the reference file:line it follows (paths relative to
+// /root/reference/project/raytracer/).  It is the checker for the CUDA path: only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.  The product
+// (librtds.so) never links or calls it.
+//
+// Pinned: tests/test_oracle_vs_reference.py checks every function below against the compiled, unmodified
+// reference (oracle/_ref/libref_oracle.so, built from the sources where they lie) and against the golden
+// vectors the reference ships (output.ppm md5, node and test counts, Morton KATs) — see tests/golden/.
+//
+// Third-party arithmetic the reference's results depend on, and how it is restated here:
+//   * libstdc++ 13.3 std::partition / std::nth_element (call sites accelerators.h:302,313,511,522) decide the
+//     BVH's primitive order under ties.  The oracle calls the same library algorithms on compact records —
+//     the permutation they produce depends only on the comparison outcomes, not on the element type.
+//   * libstdc++ std::mt19937 + generate_canonical<double,53> (main.cpp:503-508): restated from the published
+//     MT19937 algorithm (Matsumoto & Nishimura 1998) and [rand.util.canonical].
+//   * glibc powf(x,25) (main.cpp:475): restated as an exact-product chain in double rounded once.
+// Build: oracle/Makefile -> oracle/liboracle.so   (g++ -O2 -ffp-contract=off: no FMA contraction, like the
+// reference's x86-64 baseline build).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+namespace {
+
+struct V3 { float x, y, z; };
+inline float comp(const V3& v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+
+struct Box { V3 mn, mx; };
+inline Box empty_box()  // BoxBoundries() accelerators.h:108-112
+{
+    const float M = std::numeric_limits<float>::max();
+    return Box{{M, M, M}, {-M, -M, -M}};
+}
+inline Box join(const Box& a, const Box& b)  // JoinBounds accelerators.h:201-214
+{
+    return Box{{std::min(a.mn.x, b.mn.x), std::min(a.mn.y, b.mn.y), std::min(a.mn.z, b.mn.z)},
+               {std::max(a.mx.x, b.mx.x), std::max(a.mx.y, b.mx.y), std::max(a.mx.z, b.mx.z)}};
+}
+inline int max_axis(const Box& b)  // GeMaximumAxis accelerators.h:190-199
+{
+    float ex = b.mx.x - b.mn.x, ey = b.mx.y - b.mn.y, ez = b.mx.z - b.mn.z;
+    if (ex > ey && ex > ez) return 0;
+    else if (ey > ez) return 1;
+    else return 2;
+}
+
+struct Prim { V3 c; float r; int id; Box box; };
+
+struct LinearNode {  // accelerators.h:231-240
+    float bmin[3], bmax[3];
+    int32_t offset;
+    uint16_t nPrimitives;
+    uint8_t axis, pad;
+};
+static_assert(sizeof(LinearNode) == 32, "LinearBVHNode is 32 bytes");
+
+Box prim_box(const float* s)  // main.cpp:686-688: centre -/+ radius in float
+{
+    return Box{{s[0] - s[3], s[1] - s[3], s[2] - s[3]}, {s[0] + s[3], s[1] + s[3], s[2] + s[3]}};
+}
+
+// ----------------------------------------------------------------------------------------------
+// constructBVHNew, accelerators.h:246-337, emitting the pre-order LinearBVHNode array directly.
+// Returns 0, or -6 when std::partition returns endIndex (the reference then recurses forever).
+// ----------------------------------------------------------------------------------------------
+struct MedianBuilder {
+    std::vector<Prim>& P;
+    std::vector<LinearNode>& out;
+    int max_depth = 0;
+    int status = 0;
+    MedianBuilder(std::vector<Prim>& p, std::vector<LinearNode>& o) : P(p), out(o) {}
+
+    void leaf(int my, int start)
+    {
+        out[my].offset = start; out[my].nPrimitives = 1; out[my].axis = 0; out[my].pad = 0;
+    }
+    int build(int start, int end, int depth)
+    {
+        if (status) return -1;
+        int my = (int)out.size();
+        out.push_back(LinearNode());
+        max_depth = std::max(max_depth, depth);
+        Box b = empty_box();
+        for (int i = start; i < end; ++i) b = join(b, P[i].box);  // :257-260
+        out[my].bmin[0] = b.mn.x; out[my].bmin[1] = b.mn.y; out[my].bmin[2] = b.mn.z;
+        out[my].bmax[0] = b.mx.x; out[my].bmax[1] = b.mx.y; out[my].bmax[2] = b.mx.z;
+        int n = end - start;
+        if (n <= 1) { leaf(my, start); return my; }  // :265-271
+        // centroidBounds is seeded with `bounds` (:275) and only grows by points inside it: == bounds
+        int dim = max_axis(b);
+        float lo = comp(b.mn, dim), hi = comp(b.mx, dim);
+        if (hi == lo) { status = -8; return my; }  // :286-293 zero-extent range (reference pushes wrong ids); unsupported
+        float pmid = (lo + hi) / 2;                // :298
+        Prim* first = &P[start];
+        Prim* last = &P[end - 1] + 1;
+        Prim* midp = std::partition(first, last, [dim, pmid](const Prim& p) { return comp(p.c, dim) < pmid; });  // :302-306
+        int mid = (int)(midp - &P[0]);
+        if (mid != start && mid != end) {          // :311-319
+            mid = (start + end) / 2;
+            std::nth_element(first, &P[mid], last, [dim](const Prim& a, const Prim& c) { return comp(a.c, dim) < comp(c.c, dim); });
+        }
+        if (start == mid) { leaf(my, start); return my; }  // :321-327 (the rest of the range is dropped)
+        if (mid == end) { status = -6; return my; }        // :329 recurses on the same range forever
+        build(start, mid, depth + 1);
+        int second = build(mid, end, depth + 1);
+        out[my].offset = second; out[my].nPrimitives = 0; out[my].axis = (uint8_t)dim; out[my].pad = 0;  // :333-334
+        return my;
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
+// Morton (accelerators.h:374-394)
+// ----------------------------------------------------------------------------------------------
+inline unsigned expandBits(unsigned v)
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+inline unsigned morton3D(float x, float y, float z)
+{
+    x = std::min(std::max(x * 1024.0f, 0.0f), 1023.0f);
+    y = std::min(std::max(y * 1024.0f, 0.0f), 1023.0f);
+    z = std::min(std::max(z * 1024.0f, 0.0f), 1023.0f);
+    unsigned xx = expandBits((unsigned)x), yy = expandBits((unsigned)y), zz = expandBits((unsigned)z);
+    return xx * 4 + yy * 2 + zz;
+}
+inline uint64_t spread21(uint64_t v)  // bit i -> bit 3i, one bit at a time (independent of the kernel's magic masks)
+{
+    uint64_t r = 0;
+    for (int i = 0; i < 21; ++i) r |= ((v >> i) & 1ull) << (3 * i);
+    return r;
+}
+inline uint64_t morton63(float x, float y, float z)
+{
+    x = std::min(std::max(x * 2097152.0f, 0.0f), 2097151.0f);
+    y = std::min(std::max(y * 2097152.0f, 0.0f), 2097151.0f);
+    z = std::min(std::max(z * 2097152.0f, 0.0f), 2097151.0f);
+    return spread21((uint64_t)x) * 4 + spread21((uint64_t)y) * 2 + spread21((uint64_t)z);
+}
+
+// Top-down LBVH over sorted keys: split where the highest differing bit of the (key, position) pair changes —
+// the tree Karras' parallel construction emits (NVIDIA "Thinking Parallel III", cited at accelerators.h:371,568;
+// findSplit :397-449 is the reference's 8-bit attempt at it).
+struct LbvhBuilder {
+    const std::vector<uint64_t>& K;  // sorted keys
+    const std::vector<Box>& LB;      // leaf boxes in sorted order
+    std::vector<LinearNode>& out;
+    int key_bits;
+    int max_depth = 0;
+    LbvhBuilder(const std::vector<uint64_t>& k, const std::vector<Box>& lb, std::vector<LinearNode>& o, int kb) : K(k), LB(lb), out(o), key_bits(kb) {}
+
+    // number of leading bits shared by elements i and j of the augmented key (key, position)
+    int common(int i, int j) const
+    {
+        if (K[i] != K[j]) return __builtin_clzll(K[i] ^ K[j]) - (64 - key_bits);
+        return key_bits + __builtin_clz((unsigned)(i ^ j));
+    }
+    Box build(int first, int last, int depth)
+    {
+        int my = (int)out.size();
+        out.push_back(LinearNode());
+        max_depth = std::max(max_depth, depth);
+        Box b;
+        if (first == last) {
+            b = LB[first];
+            out[my].offset = first; out[my].nPrimitives = 1; out[my].axis = 0; out[my].pad = 0;
+        } else {
+            int cp = common(first, last);
+            // last position in [first,last) that shares more than cp bits with `first`
+            int lo = first, hi = last;  // invariant: common(first,lo) > cp (or lo==first), common(first,hi) == cp
+            while (hi - lo > 1) {
+                int m = (lo + hi) / 2;
+                if (common(first, m) > cp) lo = m; else hi = m;
+            }
+            int split = lo;
+            Box l = build(first, split, depth + 1);
+            int second = (int)out.size();
+            Box r = build(split + 1, last, depth + 1);
+            b = join(l, r);
+            int axis = 0;
+            if (cp < key_bits) { int bit = key_bits - 1 - cp; axis = 2 - (bit % 3); }
+            // key_bits 30 and 63 are multiples of 3, so bit%3 is the same counted in the 32/64-bit container
+            out[my].offset = second; out[my].nPrimitives = 0; out[my].axis = (uint8_t)axis; out[my].pad = 0;
+        }
+        out[my].bmin[0] = b.mn.x; out[my].bmin[1] = b.mn.y; out[my].bmin[2] = b.mn.z;
+        out[my].bmax[0] = b.mx.x; out[my].bmax[1] = b.mx.y; out[my].bmax[2] = b.mx.z;
+        return b;
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
+// traversal + intersection
+// ----------------------------------------------------------------------------------------------
+// boundingBoxIntersection accelerators.h:588-626
+inline bool slab(const float o[3], const float d[3], const float* bmin, const float* bmax)
+{
+    float tmin = (bmin[0] - o[0]) / d[0];
+    float tmax = (bmax[0] - o[0]) / d[0];
+    if (tmin > tmax) std::swap(tmin, tmax);
+    float tymin = (bmin[1] - o[1]) / d[1];
+    float tymax = (bmax[1] - o[1]) / d[1];
+    if (tymin > tymax) std::swap(tymin, tymax);
+    if ((tmin > tymax) || (tymin > tmax)) return false;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    float tzmin = (bmin[2] - o[2]) / d[2];
+    float tzmax = (bmax[2] - o[2]) / d[2];
+    if (tzmin > tzmax) std::swap(tzmin, tzmax);
+    if ((tmin > tzmax) || (tzmin > tmax)) return false;
+    return true;
+}
+
+// Sphere::raySphereIntersect accelerators.h:79-92
+inline bool ray_sphere(const float o[3], const float d[3], const float* s /*cx,cy,cz,r*/, float& t0, float& t1)
+{
+    float lx = s[0] - o[0], ly = s[1] - o[1], lz = s[2] - o[2];
+    float tca = lx * d[0] + ly * d[1] + lz * d[2];
+    if (tca < 0) return false;
+    float d2 = (lx * lx + ly * ly + lz * lz) - tca * tca;
+    float radius2 = s[3] * s[3];
+    if (d2 > radius2) return false;
+    float thc = std::sqrt(radius2 - d2);
+    t0 = tca - thc;
+    t1 = tca + thc;
+    return true;
+}
+
+struct Scene {
+    const float* sph; const float* mat; int n;
+    const LinearNode* nodes; const int* prim_order; int n_nodes;
+    int tie_by_objid;
+};
+
+// boxIntersect accelerators.h:668-690 + candidate loop main.cpp:343-358 over a flattened tree.
+// tie_by_objid: candidates are visited in objId order instead of DFS order (equal-t ties only).
+void closest_bvh(const Scene& S, const float o[3], const float d[3], int& hit, float& tnear, long long* cand)
+{
+    hit = -1; tnear = INFINITY;
+    int best_key = 0;
+    int stack[128]; int sp = 0;
+    stack[sp++] = 0;
+    while (sp) {
+        int ni = stack[--sp];
+        const LinearNode& nd = S.nodes[ni];
+        if (!slab(o, d, nd.bmin, nd.bmax)) continue;
+        if (nd.nPrimitives) {
+            int leafpos = nd.offset, obj = S.prim_order[leafpos];
+            if (cand) ++*cand;
+            float t0 = INFINITY, t1 = INFINITY;
+            if (ray_sphere(o, d, S.sph + 4 * obj, t0, t1)) {
+                if (t0 < 0) t0 = t1;
+                int key = S.tie_by_objid ? obj : leafpos;
+                if (t0 < tnear || (t0 == tnear && hit >= 0 && key < best_key)) { tnear = t0; hit = obj; best_key = key; }
+            }
+        } else {
+            stack[sp++] = nd.offset;   // right child popped after the left subtree: DFS left -> right
+            stack[sp++] = ni + 1;
+        }
+    }
+}
+
+// main.cpp:376-386
+void closest_none(const Scene& S, const float o[3], const float d[3], int& hit, float& tnear)
+{
+    hit = -1; tnear = INFINITY;
+    for (int i = 0; i < S.n; ++i) {
+        float t0 = INFINITY, t1 = INFINITY;
+        if (ray_sphere(o, d, S.sph + 4 * i, t0, t1)) {
+            if (t0 < 0) t0 = t1;
+            if (t0 < tnear) { tnear = t0; hit = i; }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// shading (castRay's DIFFUSE_AND_GLOSSY branch, main.cpp:394-497)
+// ----------------------------------------------------------------------------------------------
+inline void normalize(float v[3])  // geometry.h:125-134: factor = 1 / sqrt(n) evaluated in double
+{
+    float n = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    if (n > 0) {
+        float factor = (float)(1 / std::sqrt((double)n));
+        v[0] *= factor; v[1] *= factor; v[2] *= factor;
+    }
+}
+inline float pow25(float xf)
+{
+    double x = xf, x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8;
+    return (float)(x16 * x8 * x);
+}
+struct Light { float c[3]; float radius; float le[3]; };
+
+void shade(const float o[3], const float d[3], float tnear, const float* sph, const float* mat, const Light* L, int nl, float rgb[3])
+{
+    float hp[3] = {o[0] + d[0] * tnear, o[1] + d[1] * tnear, o[2] + d[2] * tnear};   // :396
+    float N[3] = {hp[0] - sph[0], hp[1] - sph[1], hp[2] - sph[2]};                     // :398-399
+    normalize(N);
+    if (d[0] * N[0] + d[1] * N[1] + d[2] * N[2] > 0) { N[0] = -N[0]; N[1] = -N[1]; N[2] = -N[2]; }  // :406
+    float hc[3] = {0, 0, 0};                                                            // :449
+    const float diff[3] = {0.815f, 0.235f, 0.031f};  // getDiffuseColor((0.2,0.2)) -> first colour, accelerators.h:94-99
+    for (int i = 0; i < nl; ++i) {
+        float ld[3] = {L[i].c[0] - hp[0], L[i].c[1] - hp[1], L[i].c[2] - hp[2]};        // :463
+        normalize(ld);                                                                   // :466
+        float LdotN = std::max(0.f, ld[0] * N[0] + ld[1] * N[1] + ld[2] * N[2]);         // :467
+        float I[3] = {-ld[0], -ld[1], -ld[2]};
+        float s2 = 2 * (I[0] * N[0] + I[1] * N[1] + I[2] * N[2]);                        // reflect(), :218-221
+        float R[3] = {I[0] - N[0] * s2, I[1] - N[1] * s2, I[2] - N[2] * s2};
+        float sp = pow25(std::max(0.f, -(R[0] * d[0] + R[1] * d[1] + R[2] * d[2])));     // :475
+        for (int c = 0; c < 3; ++c) {
+            float amt = (L[i].le[c] * 1.0f) * LdotN;                                     // :473 (inShadow = 0)
+            float spec = L[i].le[c] * sp;
+            hc[c] += (amt * (diff[c] * 0.8f)) / 2.0f + spec * 0.5f;                      // :489
+            hc[c] += mat[c];                                                             // :490
+        }
+    }
+    rgb[0] = hc[0]; rgb[1] = hc[1]; rgb[2] = hc[2];
+}
+
+// ----------------------------------------------------------------------------------------------
+// MT19937 + generate_canonical<double,53> (main.cpp:503-508)
+// ----------------------------------------------------------------------------------------------
+struct MT {
+    uint32_t s[624]; int p;
+    explicit MT(uint32_t seed = 5489u)
+    {
+        s[0] = seed;
+        for (int i = 1; i < 624; ++i) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + (uint32_t)i;
+        p = 624;
+    }
+    void regen()
+    {
+        for (int i = 0; i < 624; ++i) {
+            uint32_t y = (s[i] & 0x80000000u) | (s[(i + 1) % 624] & 0x7fffffffu);
+            s[i] = s[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        p = 0;
+    }
+    uint32_t next()
+    {
+        if (p >= 624) regen();
+        uint32_t y = s[p++];
+        y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+        return y;
+    }
+    void discard(unsigned long long n) { while (n--) next(); }
+    double canonical()
+    {
+        double lo = (double)next(), hi = (double)next();
+        double r = (lo + hi * 4294967296.0) / 18446744073709551616.0;
+        if (r >= 1.0) r = std::nextafter(1.0, 0.0);
+        return r;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+// createScene_new's arithmetic (main.cpp:650-717) on already-parsed vertices. out: (nv*clones + 1) x 4.
+int orc_scene_from_vertices(const float* v, int nv, int clones, float* cxyz_r, float* rgb_mat)
+{
+    int id = 0;
+    for (int clone = 0; clone < clones; ++clone) {
+        float shift = clone * 20;                      // :652
+        for (int i = 0; i < nv; ++i, ++id) {
+            float cx = v[3 * i] * 100 + shift, cy = v[3 * i + 1] * 100 + shift, cz = v[3 * i + 2] * 100 + shift;  // :680
+            cy += -10; cz += -60;                      // :681-682
+            cxyz_r[4 * id] = cx; cxyz_r[4 * id + 1] = cy; cxyz_r[4 * id + 2] = cz;
+            cxyz_r[4 * id + 3] = (float)(0.01 * 5);    // :679
+            rgb_mat[4 * id] = 0.8f; rgb_mat[4 * id + 1] = 0.7f; rgb_mat[4 * id + 2] = 0.f; rgb_mat[4 * id + 3] = 0.f;  // :689
+        }
+    }
+    cxyz_r[4 * id] = 0.93591022f; cxyz_r[4 * id + 1] = -105.47120094f; cxyz_r[4 * id + 2] = -43.2363205f;  // :703
+    cxyz_r[4 * id + 3] = 100.f;
+    rgb_mat[4 * id] = 0; rgb_mat[4 * id + 1] = 0; rgb_mat[4 * id + 2] = 0; rgb_mat[4 * id + 3] = 0;
+    return id + 1;
+}
+
+// Median-split BVH over the first n_use of n spheres. nodes: capacity 2*n_use-1; prim_order: n_use.
+int orc_build_bvh(const float* cxyz_r, int n_use, LinearNode* nodes, int* prim_order, int* n_nodes, int* max_depth)
+{
+    std::vector<Prim> P(n_use);
+    for (int i = 0; i < n_use; ++i) {
+        P[i].c = V3{cxyz_r[4 * i], cxyz_r[4 * i + 1], cxyz_r[4 * i + 2]};
+        P[i].r = cxyz_r[4 * i + 3]; P[i].id = i; P[i].box = prim_box(cxyz_r + 4 * i);
+    }
+    std::vector<LinearNode> out;
+    out.reserve(2 * (size_t)n_use);
+    MedianBuilder B(P, out);
+    B.build(0, n_use, 0);
+    if (B.status) return B.status;
+    *n_nodes = (int)out.size();
+    if (max_depth) *max_depth = B.max_depth;
+    memcpy(nodes, out.data(), sizeof(LinearNode) * out.size());
+    for (int i = 0; i < n_use; ++i) prim_order[i] = P[i].id;
+    return 0;
+}
+
+void orc_morton30(const float* xyz, int n, uint32_t* codes)
+{
+    for (int i = 0; i < n; ++i) codes[i] = morton3D(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+}
+
+// LBVH as the reference intends it. bits 30|63; ref_norm: (c+30)/1000 (accelerators.h:577) else scene-normalised.
+int orc_build_lbvh(const float* cxyz_r, int n, int bits, int ref_norm, LinearNode* nodes, int* prim_order, uint64_t* keys_sorted,
+                   int* n_nodes, int* max_depth)
+{
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], cxyz_r[4 * i + a]); hi[a] = std::max(hi[a], cxyz_r[4 * i + a]); }
+    std::vector<std::pair<uint64_t, int>> kv(n);
+    for (int i = 0; i < n; ++i) {
+        float q[3];
+        for (int a = 0; a < 3; ++a) {
+            float c = cxyz_r[4 * i + a];
+            if (ref_norm) q[a] = (c + 30.0f) / 1000.0f;
+            else { float e = hi[a] - lo[a]; q[a] = e > 0.0f ? (c - lo[a]) / e : 0.0f; }
+        }
+        kv[i].first = bits == 30 ? (uint64_t)morton3D(q[0], q[1], q[2]) : morton63(q[0], q[1], q[2]);
+        kv[i].second = i;
+    }
+    std::stable_sort(kv.begin(), kv.end(), [](const std::pair<uint64_t, int>& a, const std::pair<uint64_t, int>& b) { return a.first < b.first; });
+    std::vector<uint64_t> K(n);
+    std::vector<Box> LB(n);
+    for (int i = 0; i < n; ++i) { K[i] = kv[i].first; prim_order[i] = kv[i].second; LB[i] = prim_box(cxyz_r + 4 * kv[i].second); if (keys_sorted) keys_sorted[i] = K[i]; }
+    std::vector<LinearNode> out;
+    out.reserve(2 * (size_t)n);
+    LbvhBuilder B(K, LB, out, bits);
+    B.build(0, n - 1, 0);
+    *n_nodes = (int)out.size();
+    if (max_depth) *max_depth = B.max_depth;
+    memcpy(nodes, out.data(), sizeof(LinearNode) * out.size());
+    return 0;
+}
+
+// Closest hits of arbitrary rays. nodes == NULL -> NONE brute force.
+void orc_trace(const float* cxyz_r, int n, const LinearNode* nodes, const int* prim_order, int n_nodes, int tie_by_objid,
+               const float* o, const float* d, int nrays, int* hit, float* t, long long* candidates)
+{
+    Scene S{cxyz_r, nullptr, n, nodes, prim_order, n_nodes, tie_by_objid};
+    long long cand = 0;
+    for (int r = 0; r < nrays; ++r) {
+        if (nodes) closest_bvh(S, o + 3 * r, d + 3 * r, hit[r], t[r], &cand);
+        else closest_none(S, o + 3 * r, d + 3 * r, hit[r], t[r]);
+    }
+    if (candidates) *candidates = cand;
+}
+
+void orc_jitter(double* out, int n, unsigned long long first)
+{
+    MT g;
+    g.discard(2 * first);
+    for (int i = 0; i < n; ++i) out[i] = g.canonical();
+}
+
+// render() rows [y0,y1) (main.cpp:541-566) + write_into_file's quantisation (main.cpp:521-523).
+// lights: m x {cx,cy,cz,radius,r,g,b}. nodes == NULL -> NONE. Optional outputs may be NULL.
+void orc_render_rows(const float* cxyz_r, const float* rgb_mat, int n, const LinearNode* nodes, const int* prim_order, int n_nodes,
+                     int tie_by_objid, const float* lights7, int m, int width, int height, int spp, int y0, int y1,
+                     uint8_t* rgb8, int* hit_out, float* accum, float* dirs)
+{
+    Scene S{cxyz_r, rgb_mat, n, nodes, prim_order, n_nodes, tie_by_objid};
+    std::vector<Light> L(m);
+    for (int i = 0; i < m; ++i) {
+        const float* l = lights7 + 7 * i;
+        L[i] = Light{{l[0], l[1], l[2]}, l[3], {l[4], l[5], l[6]}};
+    }
+    MT gen;
+    gen.discard(4ull * (unsigned long long)y0 * width * spp);
+    float invWidth = 1 / float(width), invHeight = 1 / float(height);         // :544
+    float fov = 30, aspectratio = width / float(height);                       // :545
+    float angle = (float)std::tan(3.141592653589793 * 0.5 * fov / 180.);       // :546
+    const float o[3] = {0, 0, 0};
+    size_t k = 0, kd = 0;
+    for (unsigned y = (unsigned)y0; y < (unsigned)y1; ++y) {
+        for (unsigned x = 0; x < (unsigned)width; ++x, ++k) {
+            float px[3] = {0, 0, 0};
+            int last = -1;
+            for (int s = 0; s < spp; ++s) {
+                float xx = (float)((2 * ((x + gen.canonical()) * invWidth) - 1) * angle * aspectratio);  // :554
+                float yy = (float)((1 - 2 * ((y + gen.canonical()) * invHeight)) * angle);               // :555
+                float d[3] = {xx, yy, -1};
+                normalize(d);
+                if (dirs) { dirs[kd++] = d[0]; dirs[kd++] = d[1]; dirs[kd++] = d[2]; }
+                int hit; float tnear;
+                if (nodes) closest_bvh(S, o, d, hit, tnear, nullptr); else closest_none(S, o, d, hit, tnear);
+                float c[3] = {0.6f, 0.8f, 1.0f};                                                          // :318
+                if (hit >= 0) shade(o, d, tnear, cxyz_r + 4 * hit, rgb_mat + 4 * hit, L.data(), m, c);
+                px[0] += c[0]; px[1] += c[1]; px[2] += c[2];
+                last = hit;
+            }
+            if (hit_out) hit_out[k] = last;
+            if (accum) { accum[3 * k] = px[0]; accum[3 * k + 1] = px[1]; accum[3 * k + 2] = px[2]; }
+            if (rgb8) {
+                float fs = (float)(uint32_t)spp;
+                rgb8[3 * k]     = (unsigned char)(std::min(float(1), px[0] / fs) * 255);
+                rgb8[3 * k + 1] = (unsigned char)(std::min(float(1), px[1] / fs) * 255);
+                rgb8[3 * k + 2] = (unsigned char)(std::min(float(1), px[2] / fs) * 255);
+            }
+        }
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+// api.cu — the C ABI of include/rtds.h: context, scene upload, build dispatch, exports, render/trace glue.
+// There is no CPU path in this library: every entry point that computes anything launches CUDA kernels,
+// and rtds_create fails when no sm_100 device is usable.
+#include "rtds_internal.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+static thread_local char g_err[1024] = "";
+
+void rtds_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int rtds_ensure_scratch(rtds_ctx* ctx, size_t bytes)
+{
+    if (ctx->scratch_bytes >= bytes) return RTDS_OK;
+    if (ctx->d_scratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_scratch); }
+    ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+    size_t want = bytes + bytes / 8 + 4096;
+    RTDS_CUDA(cudaMalloc(&ctx->d_scratch, want));
+    ctx->scratch_bytes = want;
+    return RTDS_OK;
+}
+
+template <typename T>
+static int ensure_buf(T** p, size_t* cap, size_t need)
+{
+    if (*cap >= need) return RTDS_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    RTDS_CUDA(cudaMalloc((void**)p, need));
+    *cap = need;
+    return RTDS_OK;
+}
+
+void rtds_free_bvh(DeviceBvh& b)
+{
+    if (b.nodes) cudaFree(b.nodes);
+    if (b.leaf_sph) cudaFree(b.leaf_sph);
+    if (b.prim_order) cudaFree(b.prim_order);
+    if (b.leaf_parent) cudaFree(b.leaf_parent);
+    b = DeviceBvh();
+}
+
+int rtds_alloc_bvh(DeviceBvh& b, int n_prims)
+{
+    rtds_free_bvh(b);
+    size_t ni = n_prims > 1 ? (size_t)(n_prims - 1) : 1;
+    RTDS_CUDA(cudaMalloc(&b.nodes, sizeof(Node64) * ni));
+    RTDS_CUDA(cudaMalloc(&b.leaf_sph, sizeof(float4) * (size_t)n_prims));
+    RTDS_CUDA(cudaMalloc(&b.prim_order, sizeof(int) * (size_t)n_prims));
+    RTDS_CUDA(cudaMalloc(&b.leaf_parent, sizeof(int) * (size_t)n_prims));
+    return RTDS_OK;
+}
+
+void rtds_free_kd(DeviceKd& k)
+{
+    if (k.nodes) cudaFree(k.nodes);
+    if (k.prim_idx) cudaFree(k.prim_idx);
+    k = DeviceKd();
+}
+
+int rtds_jitter_stream_impl(rtds_ctx* ctx, uint64_t first, int n, double* out);
+
+extern "C" {
+
+const char* rtds_last_error(void) { return g_err; }
+const char* rtds_version(void) { return "rtds-b200 0.1 (sm_100a)"; }
+
+int rtds_create(rtds_ctx** out, int device)
+{
+    if (!out) { rtds_set_error("rtds_create: out is NULL"); return RTDS_ERR_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        rtds_set_error("rtds_create: no CUDA device (%s); librtds has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+        return RTDS_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) { rtds_set_error("rtds_create: device %d of %d", device, count); return RTDS_ERR_INVALID; }
+    RTDS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RTDS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        rtds_set_error("rtds_create: device %d is sm_%d%d; this library holds sm_100a code only", device, prop.major, prop.minor);
+        return RTDS_ERR_NO_DEVICE;
+    }
+    rtds_ctx* c = new rtds_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    RTDS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    RTDS_CUDA(cudaEventCreate(&c->ev0)); RTDS_CUDA(cudaEventCreate(&c->ev1));
+    RTDS_CUDA(cudaEventCreate(&c->ev2)); RTDS_CUDA(cudaEventCreate(&c->ev3));
+    RTDS_CUDA(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8));
+    // main.cpp:775: Sphere light2(0, (0,3,30), 10, (1,1,1), 0, 0, emission (1,1,1))
+    c->n_lights = 1;
+    c->lights[0] = RtdsLight{{0.f, 3.f, 30.f}, 10.f, {1.f, 1.f, 1.f}};
+    *out = c;
+    return RTDS_OK;
+}
+
+int rtds_destroy(rtds_ctx* c)
+{
+    if (!c) return RTDS_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    rtds_free_bvh(c->bvh);
+    rtds_free_kd(c->kd);
+    void* bufs[] = {c->d_sph, c->d_mat, c->d_tris, c->d_keys_sorted, c->d_mt_snap, c->d_jitter, c->d_scratch,
+                    c->d_sort_ws, c->d_frame, c->d_hit, c->d_accum, c->d_counters};
+    for (void* b : bufs) if (b) cudaFree(b);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return RTDS_OK;
+}
+
+int rtds_set_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n)
+{
+    if (!c || !cxyz_r || n <= 0) { rtds_set_error("set_spheres: bad arguments"); return RTDS_ERR_INVALID; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->d_sph) cudaFree(c->d_sph);
+    if (c->d_mat) cudaFree(c->d_mat);
+    c->d_sph = nullptr; c->d_mat = nullptr; c->n = 0;
+    c->bvh.valid = false; c->kd.valid = false; c->bvh_acc = -1;
+    RTDS_CUDA(cudaMalloc(&c->d_sph, sizeof(float4) * (size_t)n));
+    RTDS_CUDA(cudaMalloc(&c->d_mat, sizeof(float4) * (size_t)n));
+    RTDS_CUDA(cudaMemcpyAsync(c->d_sph, cxyz_r, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    if (rgb_mat) {
+        RTDS_CUDA(cudaMemcpyAsync(c->d_mat, rgb_mat, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        std::vector<float> m((size_t)n * 4);
+        for (int i = 0; i < n; ++i) { m[4 * i] = 0.8f; m[4 * i + 1] = 0.7f; m[4 * i + 2] = 0.0f; m[4 * i + 3] = 0.f; }  // main.cpp:689
+        RTDS_CUDA(cudaMemcpyAsync(c->d_mat, m.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    c->n = n;
+    return RTDS_OK;
+}
+
+int rtds_set_triangles(rtds_ctx* c, const float*, const float*, int)
+{
+    (void)c;
+    rtds_set_error("set_triangles: not implemented in this round");
+    return RTDS_ERR_UNSUPPORTED;
+}
+
+int rtds_set_lights(rtds_ctx* c, const float* l, int m)
+{
+    if (!c || m < 0 || m > RTDS_MAX_LIGHTS || (m > 0 && !l)) { rtds_set_error("set_lights: 0..%d lights", RTDS_MAX_LIGHTS); return RTDS_ERR_INVALID; }
+    c->n_lights = m;
+    for (int i = 0; i < m; ++i) {
+        const float* p = l + 7 * i;
+        c->lights[i] = RtdsLight{{p[0], p[1], p[2]}, p[3], {p[4], p[5], p[6]}};
+    }
+    return RTDS_OK;
+}
+
+int rtds_build(rtds_ctx* c, int acc, const rtds_build_params* p, rtds_build_stats* st)
+{
+    if (!c) { rtds_set_error("build: ctx is NULL"); return RTDS_ERR_INVALID; }
+    if (c->n <= 0) { rtds_set_error("build: no scene"); return RTDS_ERR_NO_SCENE; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    if (st) memset(st, 0, sizeof *st);
+    const int mode = p ? p->mode : RTDS_MODE_COMPAT;
+    int rc;
+    switch (acc) {
+    case RTDS_BVH:
+        if (mode == RTDS_MODE_SAH) rc = rtds_build_sah(c, p, st);
+        else if (mode == RTDS_MODE_TRUE) rc = rtds_build_lbvh_true(c, p, st);
+        else rc = rtds_build_median(c, c->n, st);
+        break;
+    case RTDS_LBVH:
+        if (mode == RTDS_MODE_TRUE) rc = rtds_build_lbvh_true(c, p, st);
+        else if (mode == RTDS_MODE_SAH) rc = rtds_build_sah(c, p, st);
+        else {
+            // accelerators.h:583: constructLBVHNew(objects, codes, 0, size()-1): the last object is dropped
+            if (c->n < 2) { rtds_set_error("build: compat LBVH needs >= 2 objects (the reference drops the last one)"); return RTDS_ERR_INVALID; }
+            rc = rtds_build_median(c, c->n - 1, st);
+        }
+        break;
+    case RTDS_KDTREE:
+        rc = rtds_build_kd(c, p, st);
+        break;
+    default:  // NONE / UNIFORM_GRID: nothing to build (main.cpp:838-842)
+        if (st) { st->n_prims = c->n; }
+        return RTDS_OK;
+    }
+    if (rc == RTDS_OK && (acc == RTDS_BVH || acc == RTDS_LBVH)) { c->bvh_acc = acc; c->bvh_mode = mode; }
+    return rc;
+}
+
+int rtds_export_bvh(rtds_ctx* c, rtds_linear_bvh_node* nodes, int cap_nodes, int* n_nodes, int* prim_order, int cap_prims,
+                    int* n_prims)
+{
+    if (!c) { rtds_set_error("export_bvh: ctx is NULL"); return RTDS_ERR_INVALID; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    return rtds_bvh_preorder_export(c, nodes, cap_nodes, n_nodes, prim_order, cap_prims, n_prims);
+}
+
+int rtds_export_kd(rtds_ctx* c, rtds_kd_node* nodes, int cap_nodes, int* n_nodes, int* prim_indices, int cap_idx, int* n_idx,
+                   float* bounds6)
+{
+    if (!c) { rtds_set_error("export_kd: ctx is NULL"); return RTDS_ERR_INVALID; }
+    if (!c->kd.valid) { rtds_set_error("export_kd: no KD-tree has been built"); return RTDS_ERR_NOT_BUILT; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    if (n_nodes) *n_nodes = c->kd.n_nodes;
+    if (n_idx) *n_idx = c->kd.n_idx;
+    if ((nodes && cap_nodes < c->kd.n_nodes) || (prim_indices && cap_idx < c->kd.n_idx)) {
+        rtds_set_error("export_kd: need %d nodes / %d indices", c->kd.n_nodes, c->kd.n_idx);
+        return RTDS_ERR_CAPACITY;
+    }
+    if (nodes) RTDS_CUDA(cudaMemcpy(nodes, c->kd.nodes, sizeof(rtds_kd_node) * (size_t)c->kd.n_nodes, cudaMemcpyDeviceToHost));
+    if (prim_indices && c->kd.n_idx) RTDS_CUDA(cudaMemcpy(prim_indices, c->kd.prim_idx, sizeof(int) * (size_t)c->kd.n_idx, cudaMemcpyDeviceToHost));
+    if (bounds6) memcpy(bounds6, c->kd.bounds, sizeof(float) * 6);
+    return RTDS_OK;
+}
+
+int rtds_export_morton(rtds_ctx* c, uint64_t* keys, int* prim_ids, int cap, int* n)
+{
+    if (!c) { rtds_set_error("export_morton: ctx is NULL"); return RTDS_ERR_INVALID; }
+    if (!c->bvh.valid || c->bvh_mode != RTDS_MODE_TRUE || !c->d_keys_sorted) {
+        rtds_set_error("export_morton: the last build was not a TRUE-mode LBVH");
+        return RTDS_ERR_NOT_BUILT;
+    }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    if (n) *n = c->bvh.n_prims;
+    if (cap < c->bvh.n_prims) { rtds_set_error("export_morton: need %d", c->bvh.n_prims); return RTDS_ERR_CAPACITY; }
+    if (keys) RTDS_CUDA(cudaMemcpy(keys, c->d_keys_sorted, sizeof(uint64_t) * (size_t)c->bvh.n_prims, cudaMemcpyDeviceToHost));
+    if (prim_ids) RTDS_CUDA(cudaMemcpy(prim_ids, c->bvh.prim_order, sizeof(int) * (size_t)c->bvh.n_prims, cudaMemcpyDeviceToHost));
+    return RTDS_OK;
+}
+
+int rtds_trace(rtds_ctx* c, int acc, int exact, const float* o, const float* d, int nrays, int* hit, float* t,
+               rtds_render_stats* st)
+{
+    if (!c || !o || !d || !hit || !t || nrays < 0) { rtds_set_error("trace: bad arguments"); return RTDS_ERR_INVALID; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    return rtds_trace_impl(c, acc, exact, o, d, nrays, hit, t, st);
+}
+
+int rtds_rows_for_rank(int height, int tile_rows, int rank, int world)
+{
+    if (tile_rows <= 0) tile_rows = 8;
+    if (world <= 0) world = 1;
+    int tiles = (height + tile_rows - 1) / tile_rows, rows = 0;
+    for (int t = rank; t < tiles; t += world) rows += (t * tile_rows + tile_rows <= height) ? tile_rows : height - t * tile_rows;
+    return rows;
+}
+
+int rtds_render_device(rtds_ctx* c, int acc, const rtds_render_params* p, uint8_t* d_rgb_rows, rtds_render_stats* st)
+{
+    if (!c || !p || !d_rgb_rows) { rtds_set_error("render_device: bad arguments"); return RTDS_ERR_INVALID; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    RTDS_TRY(rtds_render_impl(c, acc, p, d_rgb_rows, nullptr, nullptr, st));
+    RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    return RTDS_OK;
+}
+
+int rtds_render(rtds_ctx* c, int acc, const rtds_render_params* p, uint8_t* rgb, int* hit_obj, float* accum,
+                rtds_render_stats* st)
+{
+    if (!c || !p || !rgb) { rtds_set_error("render: bad arguments"); return RTDS_ERR_INVALID; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    const int W = p->width, H = p->height;
+    if (W <= 0 || H <= 0) { rtds_set_error("render: width/height must be positive"); return RTDS_ERR_INVALID; }
+    const int world = p->world > 0 ? p->world : 1, tile_rows = p->tile_rows > 0 ? p->tile_rows : 8;
+    const int rows = rtds_rows_for_rank(H, tile_rows, p->rank, world);
+    const size_t px = (size_t)rows * W;
+    RTDS_TRY(ensure_buf(&c->d_frame, &c->frame_bytes, px * 3 + 16));
+    if (hit_obj) RTDS_TRY(ensure_buf(&c->d_hit, &c->hit_bytes, px * sizeof(int) + 16));
+    if (accum) RTDS_TRY(ensure_buf(&c->d_accum, &c->accum_bytes, px * 3 * sizeof(float) + 16));
+    RTDS_TRY(rtds_render_impl(c, acc, p, c->d_frame, hit_obj ? c->d_hit : nullptr, accum ? c->d_accum : nullptr, st));
+    // device -> host: local row tile j is global tile j*world + rank
+    cudaStream_t s = c->stream;
+    if (world == 1) {
+        RTDS_CUDA(cudaMemcpyAsync(rgb, c->d_frame, px * 3, cudaMemcpyDeviceToHost, s));
+        if (hit_obj) RTDS_CUDA(cudaMemcpyAsync(hit_obj, c->d_hit, px * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (accum) RTDS_CUDA(cudaMemcpyAsync(accum, c->d_accum, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    } else {
+        int lrow = 0;
+        for (int t = p->rank; t * tile_rows < H; t += world) {
+            int r0 = t * tile_rows, nr = (r0 + tile_rows <= H) ? tile_rows : H - r0;
+            size_t cnt = (size_t)nr * W;
+            RTDS_CUDA(cudaMemcpyAsync(rgb + (size_t)r0 * W * 3, c->d_frame + (size_t)lrow * W * 3, cnt * 3, cudaMemcpyDeviceToHost, s));
+            if (hit_obj) RTDS_CUDA(cudaMemcpyAsync(hit_obj + (size_t)r0 * W, c->d_hit + (size_t)lrow * W, cnt * sizeof(int), cudaMemcpyDeviceToHost, s));
+            if (accum) RTDS_CUDA(cudaMemcpyAsync(accum + (size_t)r0 * W * 3, c->d_accum + (size_t)lrow * W * 3, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+            lrow += nr;
+        }
+    }
+    RTDS_CUDA(cudaStreamSynchronize(s));
+    return RTDS_OK;
+}
+
+int rtds_jitter_stream(rtds_ctx* c, uint64_t first, int n, double* out)
+{
+    if (!c || !out || n < 0) { rtds_set_error("jitter_stream: bad arguments"); return RTDS_ERR_INVALID; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    return rtds_jitter_stream_impl(c, first, n, out);
+}
+
+int rtds_morton30(rtds_ctx* c, const float* xyz, int n, uint32_t* codes)
+{
+    if (!c || !xyz || !codes || n < 0) { rtds_set_error("morton30: bad arguments"); return RTDS_ERR_INVALID; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    return rtds_morton30_device(c, xyz, n, codes);
+}
+
+}  // extern "C"

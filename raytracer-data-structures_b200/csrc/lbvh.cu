@@ -1,0 +1,458 @@
+// lbvh.cu — the LBVH the reference intends (accelerators.h:371,568 cite NVIDIA's "Thinking Parallel III"):
+//   K1 scene/centroid bounds reduce      (JoinBounds / JoinBoxPopintBounds, accelerators.h:201-229)
+//   K2 30-bit / 63-bit Morton codes      (expandBits / morton3D, accelerators.h:374-394; 63-bit is an extension)
+//   K3 onesweep radix sort               (sort.cu)
+//   K4 Karras hierarchy emission         (the intended behaviour of findSplit, accelerators.h:397-449)
+//   K5 atomic bottom-up AABB refit       (node bounds = union of leaf boxBoundries, accelerators.h:257-260)
+// plus the pre-order flattening into the reference's LinearBVHNode layout (accelerators.h:231-240).
+#include "rtds_internal.cuh"
+#include <math.h>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// K1: bounds.  out[0..5] = centre min.xyz / max.xyz, out[6..11] = AABB (c -/+ r) min / max, as ordered uints.
+// ---------------------------------------------------------------------------------------------------
+__global__ void bounds_init_kernel(unsigned* out)
+{
+    int i = threadIdx.x;
+    if (i < 12) out[i] = ((i % 6) < 3) ? 0xffffffffu : 0u;
+}
+
+__global__ void __launch_bounds__(256) bounds_kernel(const float4* __restrict__ sph, int n, unsigned* __restrict__ out)
+{
+    float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float bmin[3] = {INFINITY, INFINITY, INFINITY}, bmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 s = ldg4(sph + i);
+        float c[3] = {s.x, s.y, s.z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            cmin[a] = fminf(cmin[a], c[a]);
+            cmax[a] = fmaxf(cmax[a], c[a]);
+            bmin[a] = fminf(bmin[a], c[a] - s.w);
+            bmax[a] = fmaxf(bmax[a], c[a] + s.w);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o; o >>= 1) {
+            cmin[a] = fminf(cmin[a], __shfl_xor_sync(0xffffffffu, cmin[a], o));
+            cmax[a] = fmaxf(cmax[a], __shfl_xor_sync(0xffffffffu, cmax[a], o));
+            bmin[a] = fminf(bmin[a], __shfl_xor_sync(0xffffffffu, bmin[a], o));
+            bmax[a] = fmaxf(bmax[a], __shfl_xor_sync(0xffffffffu, bmax[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&out[a], f2ord(cmin[a]));
+            atomicMax(&out[3 + a], f2ord(cmax[a]));
+            atomicMin(&out[6 + a], f2ord(bmin[a]));
+            atomicMax(&out[9 + a], f2ord(bmax[a]));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: Morton codes
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned expand_bits10(unsigned v)  // accelerators.h:374-381
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__device__ __forceinline__ unsigned morton30(float x, float y, float z)  // accelerators.h:385-394
+{
+    x = fminf(fmaxf(x * 1024.0f, 0.0f), 1023.0f);
+    y = fminf(fmaxf(y * 1024.0f, 0.0f), 1023.0f);
+    z = fminf(fmaxf(z * 1024.0f, 0.0f), 1023.0f);
+    unsigned xx = expand_bits10((unsigned)x);
+    unsigned yy = expand_bits10((unsigned)y);
+    unsigned zz = expand_bits10((unsigned)z);
+    return xx * 4 + yy * 2 + zz;
+}
+
+__device__ __forceinline__ unsigned long long expand_bits21(unsigned long long v)
+{
+    v &= 0x1fffffull;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long morton63(float x, float y, float z)
+{
+    x = fminf(fmaxf(x * 2097152.0f, 0.0f), 2097151.0f);
+    y = fminf(fmaxf(y * 2097152.0f, 0.0f), 2097151.0f);
+    z = fminf(fmaxf(z * 2097152.0f, 0.0f), 2097151.0f);
+    return expand_bits21((unsigned long long)x) * 4 + expand_bits21((unsigned long long)y) * 2 +
+           expand_bits21((unsigned long long)z);
+}
+
+// ref_norm: (centre + 30) / 1000 (accelerators.h:577); else (centre - cmin) / (cmax - cmin) per axis.
+template <typename K>
+__global__ void __launch_bounds__(256)
+morton_kernel(const float4* __restrict__ sph, int n, const unsigned* __restrict__ bounds_ord, int ref_norm,
+              K* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 s = ldg4(sph + i);
+    float x, y, z;
+    if (ref_norm) {
+        x = (s.x + 30.0f) / 1000.0f; y = (s.y + 30.0f) / 1000.0f; z = (s.z + 30.0f) / 1000.0f;
+    } else {
+        float lo[3] = {ord2f(bounds_ord[0]), ord2f(bounds_ord[1]), ord2f(bounds_ord[2])};
+        float hi[3] = {ord2f(bounds_ord[3]), ord2f(bounds_ord[4]), ord2f(bounds_ord[5])};
+        float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+        x = ex > 0.0f ? (s.x - lo[0]) / ex : 0.0f;
+        y = ey > 0.0f ? (s.y - lo[1]) / ey : 0.0f;
+        z = ez > 0.0f ? (s.z - lo[2]) / ez : 0.0f;
+    }
+    if (sizeof(K) == 4) keys[i] = (K)morton30(x, y, z);
+    else keys[i] = (K)morton63(x, y, z);
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void morton30_points_kernel(const float* __restrict__ xyz, int n, uint32_t* __restrict__ codes)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) codes[i] = morton30(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4: Karras hierarchy emission over the sorted keys.  Duplicate keys are disambiguated by position.
+// ---------------------------------------------------------------------------------------------------
+template <typename K>
+__device__ __forceinline__ int delta(const K* __restrict__ keys, int n, int i, K ki, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    K kj = keys[j];
+    if (ki == kj) return (int)(sizeof(K) * 8) + __clz(i ^ j);
+    return sizeof(K) == 4 ? __clz((unsigned)(ki ^ kj)) : __clzll((long long)(ki ^ kj));
+}
+
+template <typename K>
+__global__ void __launch_bounds__(256)
+karras_kernel(const K* __restrict__ keys, int n, Node64* __restrict__ nodes, int* __restrict__ leaf_parent)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    K ki = keys[i];
+    int d = (delta(keys, n, i, ki, i + 1) - delta(keys, n, i, ki, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, ki, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, ki, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, ki, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, ki, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, ki, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int left = (lo == gamma) ? ~gamma : gamma;
+    int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    nodes[i].left = left;
+    nodes[i].right = right;
+    // axis of the first differing Morton bit (bit 3k+2 = x, 3k+1 = y, 3k = z); equal keys -> 0
+    int axis = 0;
+    if (dnode < (int)(sizeof(K) * 8)) {
+        int b = (int)(sizeof(K) * 8) - 1 - dnode;
+        axis = 2 - (b % 3);
+    }
+    nodes[i].axis = axis;
+    if (i == 0) nodes[0].parent = -1;
+    if (left < 0) leaf_parent[~left] = i; else nodes[left].parent = i * 2;
+    if (right < 0) leaf_parent[~right] = i | 0x80000000; else nodes[right].parent = i * 2 + 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5: bottom-up refit.  One thread per leaf writes its box into its parent's child slot; the second
+// thread to arrive at an interior node (atomic counter) unions the two slots and carries on upward.
+// Node64::parent holds parent*2+side for interior nodes (side 1 = right child), -1 for the root.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_child_box(Node64* nd, int side, const float mn[3], const float mx[3])
+{
+    float* pmin = side ? nd->rmin : nd->lmin;
+    float* pmax = side ? nd->rmax : nd->lmax;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { __stcg(pmin + a, mn[a]); __stcg(pmax + a, mx[a]); }
+}
+
+__global__ void __launch_bounds__(256)
+refit_kernel(const float4* __restrict__ sph, const uint32_t* __restrict__ sorted_ids, int n, Node64* nodes,
+             const int* __restrict__ leaf_parent, float4* __restrict__ leaf_sph, int* __restrict__ prim_order,
+             unsigned* __restrict__ counters, float* __restrict__ root_box)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int prim = (int)sorted_ids[j];
+    float4 s = ldg4(sph + prim);
+    leaf_sph[j] = make_float4(s.x, s.y, s.z, s.w * s.w);
+    prim_order[j] = prim;
+    float mn[3] = {s.x - s.w, s.y - s.w, s.z - s.w};
+    float mx[3] = {s.x + s.w, s.y + s.w, s.z + s.w};
+    if (n == 1) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { root_box[a] = mn[a]; root_box[3 + a] = mx[a]; }
+        return;
+    }
+    int lp = leaf_parent[j];
+    int parent = lp & 0x7fffffff, side = (lp >> 31) & 1;
+    while (true) {
+        Node64* nd = nodes + parent;
+        store_child_box(nd, side, mn, mx);
+        __threadfence();
+        unsigned old = atomicAdd(&counters[parent], 1u);
+        if (old == 0) return;  // the sibling subtree is not finished: its last thread continues
+        __threadfence();
+        const float* omin = side ? nd->lmin : nd->rmin;
+        const float* omax = side ? nd->lmax : nd->rmax;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = fminf(mn[a], __ldcg(omin + a));
+            mx[a] = fmaxf(mx[a], __ldcg(omax + a));
+        }
+        int pe = __ldcg(&nd->parent);
+        if (pe < 0) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { root_box[a] = mn[a]; root_box[3 + a] = mx[a]; }
+            return;
+        }
+        parent = pe >> 1;
+        side = pe & 1;
+    }
+}
+
+// depth of the deepest leaf (root = depth 0): bounds the traversal stack
+__global__ void __launch_bounds__(256)
+depth_kernel(const Node64* __restrict__ nodes, const int* __restrict__ leaf_parent, int n, int* __restrict__ max_depth)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int depth = 0;
+    if (j < n && n > 1) {
+        int p = leaf_parent[j] & 0x7fffffff;
+        depth = 1;
+        while (true) {
+            int pe = nodes[p].parent;
+            if (pe < 0) break;
+            p = pe >> 1;
+            ++depth;
+        }
+    }
+    for (int o = 16; o; o >>= 1) depth = max(depth, __shfl_xor_sync(0xffffffffu, depth, o));
+    if ((threadIdx.x & 31) == 0 && depth > 0) atomicMax(max_depth, depth);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pre-order flattening (K9).  Leaf order is DFS order in every builder of this library, so a node whose
+// subtree starts at leaf f and that lies in the LEFT subtree of `lv` of its ancestors has pre-order index
+// 2*f + lv (f leaves and f - (#right turns) interior nodes precede it, plus its ancestors).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int first_leaf(const Node64* __restrict__ nodes, int ref)
+{
+    while (ref >= 0) ref = nodes[ref].left;
+    return ~ref;
+}
+
+__global__ void __launch_bounds__(256)
+preorder_kernel(const Node64* __restrict__ nodes, const int* __restrict__ leaf_parent, int n,
+                const float* __restrict__ root_box, rtds_linear_bvh_node* __restrict__ out)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int n_internal = n - 1;
+    if (t >= 2 * n - 1) return;
+    rtds_linear_bvh_node r;
+    if (n == 1) {
+        for (int a = 0; a < 3; ++a) { r.bmin[a] = root_box[a]; r.bmax[a] = root_box[3 + a]; }
+        r.offset = 0; r.nPrimitives = 1; r.axis = 0; r.pad = 0;
+        out[0] = r;
+        return;
+    }
+    int pe;          // parent*2+side of the node this thread handles
+    int f;           // first leaf of its subtree
+    bool leaf = t >= n_internal;
+    if (leaf) {
+        int j = t - n_internal;
+        int lp = leaf_parent[j];
+        pe = ((lp & 0x7fffffff) << 1) | ((lp >> 31) & 1);
+        f = j;
+        r.offset = j; r.nPrimitives = 1; r.axis = 0; r.pad = 0;
+    } else {
+        pe = nodes[t].parent;
+        f = first_leaf(nodes, t);
+        r.nPrimitives = 0; r.axis = (uint8_t)nodes[t].axis; r.pad = 0;
+    }
+    // own box: from the parent's child slot (root: root_box)
+    if (pe < 0) {
+        for (int a = 0; a < 3; ++a) { r.bmin[a] = root_box[a]; r.bmax[a] = root_box[3 + a]; }
+    } else {
+        const Node64* pn = nodes + (pe >> 1);
+        const float* mn = (pe & 1) ? pn->rmin : pn->lmin;
+        const float* mx = (pe & 1) ? pn->rmax : pn->lmax;
+        for (int a = 0; a < 3; ++a) { r.bmin[a] = mn[a]; r.bmax[a] = mx[a]; }
+    }
+    int lv = 0;
+    for (int q = pe; q >= 0; q = nodes[q >> 1].parent) lv += (q & 1) ? 0 : 1;
+    int my = 2 * f + lv;
+    if (!leaf) {
+        int fr = first_leaf(nodes, nodes[t].right);
+        r.offset = 2 * fr + lv;  // secondChildOffset: the right child is in the left subtree of the same ancestors
+    }
+    out[my] = r;
+}
+
+template <typename K>
+__global__ void widen_keys_kernel(const K* __restrict__ in, int n, uint64_t* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint64_t)in[i];
+}
+
+template <typename K>
+int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, int key_bits)
+{
+    const int n = ctx->n;
+    DeviceBvh& b = ctx->bvh;
+    int launches = 0;
+    // scratch: bounds[12] | counters[n] | max_depth | keys, keys_tmp | vals, vals_tmp
+    size_t off_bounds = 0;
+    size_t off_counters = 256;
+    size_t off_depth = off_counters + sizeof(unsigned) * (size_t)n;
+    off_depth = (off_depth + 255) & ~(size_t)255;
+    size_t off_keys = off_depth + 256;
+    size_t off_keys_tmp = off_keys + ((sizeof(K) * (size_t)n + 255) & ~(size_t)255);
+    size_t off_vals = off_keys_tmp + ((sizeof(K) * (size_t)n + 255) & ~(size_t)255);
+    size_t off_vals_tmp = off_vals + ((sizeof(uint32_t) * (size_t)n + 255) & ~(size_t)255);
+    size_t total = off_vals_tmp + ((sizeof(uint32_t) * (size_t)n + 255) & ~(size_t)255);
+    RTDS_TRY(rtds_ensure_scratch(ctx, total));
+    char* base = (char*)ctx->d_scratch;
+    unsigned* d_bounds = (unsigned*)(base + off_bounds);
+    unsigned* d_counters = (unsigned*)(base + off_counters);
+    int* d_depth = (int*)(base + off_depth);
+    K* d_keys = (K*)(base + off_keys);
+    K* d_keys_tmp = (K*)(base + off_keys_tmp);
+    uint32_t* d_vals = (uint32_t*)(base + off_vals);
+    uint32_t* d_vals_tmp = (uint32_t*)(base + off_vals_tmp);
+
+    RTDS_TRY(rtds_alloc_bvh(b, n));
+    if (ctx->n_keys < n) {
+        if (ctx->d_keys_sorted) cudaFree(ctx->d_keys_sorted);
+        ctx->d_keys_sorted = nullptr;
+        RTDS_CUDA(cudaMalloc(&ctx->d_keys_sorted, sizeof(uint64_t) * (size_t)n));
+    }
+    ctx->n_keys = n;
+
+    cudaStream_t s = ctx->stream;
+    RTDS_CUDA(cudaEventRecord(ctx->ev0, s));
+    const int T = 256;
+    const int G = (n + T - 1) / T;
+    bounds_init_kernel<<<1, 32, 0, s>>>(d_bounds);
+    bounds_kernel<<<min(G, ctx->sm_count * 8), T, 0, s>>>(ctx->d_sph, n, d_bounds);
+    morton_kernel<K><<<G, T, 0, s>>>(ctx->d_sph, n, d_bounds, p ? p->morton_ref_norm : 0, d_keys, d_vals);
+    launches += 3;
+    RTDS_TRY((sizeof(K) == 4)
+                 ? rtds_onesweep_sort_u32(ctx, (uint32_t*)d_keys, d_vals, (uint32_t*)d_keys_tmp, d_vals_tmp, n, key_bits, &launches)
+                 : rtds_onesweep_sort_u64(ctx, (uint64_t*)d_keys, d_vals, (uint64_t*)d_keys_tmp, d_vals_tmp, n, key_bits, &launches));
+    RTDS_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned) * (size_t)n + 0, s));
+    RTDS_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(int), s));
+    float* d_root_box = (float*)(d_bounds + 16);
+    if (n > 1) {
+        karras_kernel<K><<<(n - 1 + T - 1) / T, T, 0, s>>>(d_keys, n, b.nodes, b.leaf_parent);
+        launches += 1;
+    }
+    refit_kernel<<<G, T, 0, s>>>(ctx->d_sph, d_vals, n, b.nodes, b.leaf_parent, b.leaf_sph, b.prim_order, d_counters, d_root_box);
+    depth_kernel<<<G, T, 0, s>>>(b.nodes, b.leaf_parent, n, d_depth);
+    widen_keys_kernel<K><<<G, T, 0, s>>>(d_keys, n, ctx->d_keys_sorted);
+    launches += 3;
+    RTDS_CUDA(cudaEventRecord(ctx->ev1, s));
+    RTDS_CUDA(cudaGetLastError());
+    RTDS_CUDA(cudaMemcpyAsync(b.root_box, d_root_box, sizeof(float) * 6, cudaMemcpyDeviceToHost, s));
+    int depth = 0;
+    RTDS_CUDA(cudaMemcpyAsync(&depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, s));
+    RTDS_CUDA(cudaStreamSynchronize(s));
+    b.n_prims = n;
+    b.n_internal = n - 1;
+    b.root_ref = n > 1 ? 0 : ~0;
+    b.tie_by_objid = 1;
+    b.max_depth = depth;
+    b.valid = true;
+    float ms = 0;
+    RTDS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (st) {
+        st->n_prims = n;
+        st->total_nodes = 2 * n - 1;
+        st->alloc_nodes = 2 * n - 1;
+        st->max_depth = depth;
+        st->kernel_launches = launches;
+        st->ms = ms;
+    }
+    return RTDS_OK;
+}
+
+}  // namespace
+
+int rtds_build_lbvh_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st)
+{
+    int bits = (p && p->morton_bits) ? p->morton_bits : 30;
+    if (bits == 30) return build_true<uint32_t>(ctx, p, st, 30);
+    if (bits == 63) return build_true<uint64_t>(ctx, p, st, 63);
+    rtds_set_error("morton_bits must be 30 or 63 (got %d)", bits);
+    return RTDS_ERR_INVALID;
+}
+
+int rtds_morton30_device(rtds_ctx* ctx, const float* h_xyz, int n, uint32_t* h_codes)
+{
+    if (n <= 0) return RTDS_OK;
+    size_t bytes_in = sizeof(float) * 3 * (size_t)n, bytes_out = sizeof(uint32_t) * (size_t)n;
+    RTDS_TRY(rtds_ensure_scratch(ctx, bytes_in + bytes_out + 512));
+    float* d_in = (float*)ctx->d_scratch;
+    uint32_t* d_out = (uint32_t*)((char*)ctx->d_scratch + ((bytes_in + 255) & ~(size_t)255));
+    RTDS_CUDA(cudaMemcpyAsync(d_in, h_xyz, bytes_in, cudaMemcpyHostToDevice, ctx->stream));
+    morton30_points_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_in, n, d_out);
+    RTDS_CUDA(cudaGetLastError());
+    RTDS_CUDA(cudaMemcpyAsync(h_codes, d_out, bytes_out, cudaMemcpyDeviceToHost, ctx->stream));
+    RTDS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RTDS_OK;
+}
+
+int rtds_bvh_preorder_export(rtds_ctx* ctx, rtds_linear_bvh_node* h_nodes, int cap_nodes, int* n_nodes,
+                             int* h_prim_order, int cap_prims, int* n_prims)
+{
+    DeviceBvh& b = ctx->bvh;
+    if (!b.valid) { rtds_set_error("export_bvh: no BVH/LBVH has been built"); return RTDS_ERR_NOT_BUILT; }
+    const int n = b.n_prims, total = 2 * n - 1;
+    if (n_nodes) *n_nodes = total;
+    if (n_prims) *n_prims = n;
+    if ((h_nodes && cap_nodes < total) || (h_prim_order && cap_prims < n)) {
+        rtds_set_error("export_bvh: need %d nodes / %d prims", total, n);
+        return RTDS_ERR_CAPACITY;
+    }
+    if (h_nodes) {
+        size_t bytes = sizeof(rtds_linear_bvh_node) * (size_t)total;
+        RTDS_TRY(rtds_ensure_scratch(ctx, bytes + 256));
+        float* d_root = (float*)ctx->d_scratch;
+        rtds_linear_bvh_node* d_out = (rtds_linear_bvh_node*)((char*)ctx->d_scratch + 256);
+        RTDS_CUDA(cudaMemcpyAsync(d_root, b.root_box, sizeof(float) * 6, cudaMemcpyHostToDevice, ctx->stream));
+        preorder_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(b.nodes, b.leaf_parent, n, d_root, d_out);
+        RTDS_CUDA(cudaGetLastError());
+        RTDS_CUDA(cudaMemcpyAsync(h_nodes, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (h_prim_order)
+        RTDS_CUDA(cudaMemcpyAsync(h_prim_order, b.prim_order, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RTDS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RTDS_OK;
+}

@@ -1,0 +1,705 @@
+// render.cu — K10 (ray generation + traversal + ray/sphere test + shading + accumulate + 8-bit quantise)
+// and K11 (MT19937 jitter stream).
+//
+// Reference semantics reproduced here (all citations relative to /root/reference/project/raytracer/):
+//   render()            main.cpp:541-566   ray generation, per-pixel sample loop, accumulation order
+//   random_double()     main.cpp:503-508   std::mt19937 (seed 5489) + uniform_real_distribution<double>:
+//                                          generate_canonical<double,53> = (lo + hi*2^32) / 2^64
+//   castRay()           main.cpp:291-500   candidate loop (strict <, first candidate wins), Phong shading
+//   boxIntersect()      accelerators.h:668-690  collect every leaf whose ancestor chain passes the slab test
+//   boundingBoxIntersection() accelerators.h:588-626  slab test: 6 IEEE divides, no t-range test
+//   raySphereIntersect() accelerators.h:79-92  geometric solution
+//   Vec3::normalize()   geometry.h:125-134 factor = (float)(1.0 / sqrt((double)n))
+//   write_into_file()   main.cpp:516-528   (unsigned char)(min(1, c/aa) * 255)
+// The translation unit is compiled with -fmad=false -prec-div=true -prec-sqrt=true so that every float
+// operation rounds exactly like the reference's SSE2 code.
+#include "rtds_internal.cuh"
+#include <math.h>
+
+namespace {
+
+// ===================================================================================================
+// K11: MT19937
+// ===================================================================================================
+constexpr int MT_N = 624, MT_M = 397;
+constexpr int MT_SNAP_EVERY = 8;  // regenerations between stored state snapshots
+constexpr int MT_THREADS = 256;
+
+__device__ __forceinline__ uint32_t mt_twist(uint32_t u, uint32_t v)
+{
+    return (((u & 0x80000000u) | (v & 0x7fffffffu)) >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y)
+{
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+// One regeneration A -> B (624 words) by a block of >= 227 threads, three dependent phases.
+__device__ __forceinline__ void mt_regen(const uint32_t* __restrict__ A, uint32_t* __restrict__ B)
+{
+    const int t = threadIdx.x;
+    if (t < 227) B[t] = A[t + MT_M] ^ mt_twist(A[t], A[t + 1]);
+    __syncthreads();
+    if (t < 227) B[t + 227] = B[t] ^ mt_twist(A[t + 227], A[t + 228]);
+    __syncthreads();
+    if (t < 169) B[t + 454] = B[t + 227] ^ mt_twist(A[t + 454], A[t + 455]);
+    if (t == 169) B[623] = B[396] ^ mt_twist(A[623], B[0]);
+    __syncthreads();
+}
+
+// Sequential walk of the generator by ONE block: stores the state after every MT_SNAP_EVERY regenerations.
+// snap[k] = state after k*MT_SNAP_EVERY regenerations; k in [k0, k1). snap[0] is the seeded state.
+__global__ void __launch_bounds__(MT_THREADS) mt_snapshot_kernel(uint32_t* __restrict__ snap, int k0, int k1, uint32_t seed)
+{
+    __shared__ uint32_t S[2][MT_N];
+    const int t = threadIdx.x;
+    int cur = 0;
+    if (k0 == 0) {
+        if (t == 0) {
+            uint32_t x = seed;
+            S[0][0] = x;
+            for (int i = 1; i < MT_N; ++i) { x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i; S[0][i] = x; }
+        }
+        __syncthreads();
+        for (int i = t; i < MT_N; i += MT_THREADS) snap[i] = S[0][i];
+        k0 = 1;
+    } else {
+        for (int i = t; i < MT_N; i += MT_THREADS) S[0][i] = snap[(size_t)(k0 - 1) * MT_N + i];
+        __syncthreads();
+    }
+    for (int k = k0; k < k1; ++k) {
+        for (int r = 0; r < MT_SNAP_EVERY; ++r) { mt_regen(S[cur], S[cur ^ 1]); cur ^= 1; }
+        for (int i = t; i < MT_N; i += MT_THREADS) snap[(size_t)k * MT_N + i] = S[cur][i];
+    }
+}
+
+// Block b regenerates MT_SNAP_EVERY times from snapshot (s0 + b) and writes the tempered words.
+// out[0] is stream word (s0 * MT_SNAP_EVERY * 624).
+__global__ void __launch_bounds__(MT_THREADS) mt_expand_kernel(const uint32_t* __restrict__ snap, int s0,
+                                                               uint32_t* __restrict__ out, size_t n_words)
+{
+    __shared__ uint32_t S[2][MT_N];
+    const int t = threadIdx.x;
+    const uint32_t* src = snap + (size_t)(s0 + blockIdx.x) * MT_N;
+    for (int i = t; i < MT_N; i += MT_THREADS) S[0][i] = src[i];
+    __syncthreads();
+    int cur = 0;
+    size_t base = (size_t)blockIdx.x * MT_SNAP_EVERY * MT_N;
+    for (int r = 0; r < MT_SNAP_EVERY; ++r) {
+        mt_regen(S[cur], S[cur ^ 1]);
+        cur ^= 1;
+        for (int i = t; i < MT_N; i += MT_THREADS) {
+            size_t w = base + (size_t)r * MT_N + i;
+            if (w < n_words) out[w] = mt_temper(S[cur][i]);
+        }
+    }
+}
+
+// generate_canonical<double,53>(mt19937): two draws, (lo + hi*2^32)/2^64, clamped below 1.
+__device__ __forceinline__ double canonical53(uint32_t lo, uint32_t hi)
+{
+    double sum = __uint2double_rn(lo) + __uint2double_rn(hi) * 4294967296.0;
+    double r = sum / 18446744073709551616.0;
+    if (r >= 1.0) r = 0.99999999999999988897769753748434595763683319091796875;  // nextafter(1,0)
+    return r;
+}
+
+__global__ void jitter_doubles_kernel(const uint32_t* __restrict__ words, size_t first_double_rel, int n, double* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        size_t w = (first_double_rel + (size_t)i) * 2;
+        out[i] = canonical53(words[w], words[w + 1]);
+    }
+}
+
+// ===================================================================================================
+// ray / box / sphere primitives with the reference's exact operation order
+// ===================================================================================================
+struct Counters { unsigned node_tests, prim_tests, node_visits, rays; };
+
+// accelerators.h:588-626 (and :628-666 for the variant returning tMin/tMax)
+__device__ __forceinline__ bool slab_test(float ox, float oy, float oz, float dx, float dy, float dz, float bminx,
+                                          float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, float& tmin_o,
+                                          float& tmax_o)
+{
+    float tmin = (bminx - ox) / dx;
+    float tmax = (bmaxx - ox) / dx;
+    if (tmin > tmax) { float t = tmin; tmin = tmax; tmax = t; }
+    float tymin = (bminy - oy) / dy;
+    float tymax = (bmaxy - oy) / dy;
+    if (tymin > tymax) { float t = tymin; tymin = tymax; tymax = t; }
+    if ((tmin > tymax) || (tymin > tmax)) return false;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    float tzmin = (bminz - oz) / dz;
+    float tzmax = (bmaxz - oz) / dz;
+    if (tzmin > tzmax) { float t = tzmin; tzmin = tzmax; tzmax = t; }
+    if ((tmin > tzmax) || (tzmin > tmax)) return false;
+    if (tzmin > tmin) tmin = tzmin;
+    if (tzmax < tmax) tmax = tzmax;
+    tmin_o = tmin;
+    tmax_o = tmax;
+    return true;
+}
+
+// accelerators.h:79-92; s = {cx,cy,cz,r^2}
+__device__ __forceinline__ bool sphere_test(float ox, float oy, float oz, float dx, float dy, float dz, float4 s, float& t0,
+                                            float& t1)
+{
+    float lx = s.x - ox, ly = s.y - oy, lz = s.z - oz;
+    float tca = lx * dx + ly * dy + lz * dz;
+    if (tca < 0) return false;
+    float d2 = (lx * lx + ly * ly + lz * lz) - tca * tca;
+    if (d2 > s.w) return false;
+    float thc = sqrtf(s.w - d2);
+    t0 = tca - thc;
+    t1 = tca + thc;
+    return true;
+}
+
+// candidate update of main.cpp:350-355 / :379-384 with the reference's "first candidate wins" made
+// order-independent: `key` is the candidate's position in the reference's candidate order.
+__device__ __forceinline__ void candidate(float t0, float t1, int key, int leaf, float& tnear, int& best_key, int& best_leaf)
+{
+    if (t0 < 0) t0 = t1;
+    if (t0 < tnear || (t0 == tnear && best_leaf >= 0 && key < best_key)) {
+        tnear = t0; best_key = key; best_leaf = leaf;
+    }
+}
+
+struct BvhView {
+    const Node64* nodes;
+    const float4* leaf_sph;
+    const int*    prim_order;
+    int           root_ref;
+    int           tie_by_objid;
+    float         root_box[6];
+};
+
+constexpr int STACK_MAX = 64;
+
+// pruning margin for the ordered traversal: bounds the float error of raySphereIntersect's t0 against the
+// true entry distance for any sphere inside the root box (DESIGN.md "Ordered traversal is exact").
+__device__ __forceinline__ float prune_margin(const float rb[6], float ox, float oy, float oz)
+{
+    float ex = fmaxf(fabsf(rb[0] - ox), fabsf(rb[3] - ox));
+    float ey = fmaxf(fabsf(rb[1] - oy), fabsf(rb[4] - oy));
+    float ez = fmaxf(fabsf(rb[2] - oz), fabsf(rb[5] - oz));
+    float D = sqrtf(ex * ex + ey * ey + ez * ez);
+    return D * 0.00278f;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ void traverse_bvh(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
+                                             float& tnear, int& best_key, int& best_leaf, Counters& cnt)
+{
+    float tmn, tmx;
+    cnt.node_tests++;
+    if (!slab_test(ox, oy, oz, dx, dy, dz, B.root_box[0], B.root_box[1], B.root_box[2], B.root_box[3], B.root_box[4],
+                   B.root_box[5], tmn, tmx))
+        return;
+    if (B.root_ref < 0) {
+        float t0, t1;
+        cnt.prim_tests++;
+        if (sphere_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_sph), t0, t1))
+            candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order) : 0, 0, tnear, best_key, best_leaf);
+        return;
+    }
+    const float margin = EXACT ? 0.0f : prune_margin(B.root_box, ox, oy, oz);
+    int   stack[STACK_MAX];
+    float stack_t[EXACT ? 1 : STACK_MAX];
+    int sp = 0;
+    int node = 0;
+    while (true) {
+        const float4* q = reinterpret_cast<const float4*>(B.nodes + node);
+        float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+        int4 q3 = __ldg(reinterpret_cast<const int4*>(q + 3));
+        cnt.node_visits++;
+        cnt.node_tests += 2;
+        float tminL, tmaxL, tminR, tmaxR;
+        bool hitL = slab_test(ox, oy, oz, dx, dy, dz, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tminL, tmaxL);
+        bool hitR = slab_test(ox, oy, oz, dx, dy, dz, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tminR, tmaxR);
+        const int left = q3.x, right = q3.y;
+        if (!EXACT) {
+            // NaN-safe: a comparison with NaN is false and keeps the child
+            if (hitL && (tminL > tnear + margin || tmaxL < -margin)) hitL = false;
+            if (hitR && (tminR > tnear + margin || tmaxR < -margin)) hitR = false;
+        }
+        if (hitL && left < 0) {
+            int leaf = ~left;
+            float t0, t1;
+            cnt.prim_tests++;
+            if (sphere_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_sph + leaf), t0, t1))
+                candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
+            hitL = false;
+        }
+        if (hitR && right < 0) {
+            int leaf = ~right;
+            float t0, t1;
+            cnt.prim_tests++;
+            if (sphere_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_sph + leaf), t0, t1))
+                candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
+            hitR = false;
+        }
+        if (hitL && hitR) {
+            int nearc = left, farc = right;
+            float tfar = tminR;
+            if (!EXACT && tminR < tminL) { nearc = right; farc = left; tfar = tminL; }
+            if (sp < STACK_MAX) {
+                stack[sp] = farc;
+                if (!EXACT) stack_t[sp] = tfar;
+                ++sp;
+            }
+            node = nearc;
+            continue;
+        }
+        if (hitL) { node = left; continue; }
+        if (hitR) { node = right; continue; }
+        // pop
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (!EXACT && stack_t[sp] > tnear + margin) continue;
+            node = stack[sp];
+            found = true;
+            break;
+        }
+        if (!found) break;
+    }
+}
+
+// NONE: main.cpp:376-386, spheres staged through shared memory by the whole block (all threads must call).
+constexpr int NONE_CHUNK = 1024;
+__device__ __forceinline__ void brute_force_block(const float4* __restrict__ sph /*objId order {c,r}*/, int n, bool active,
+                                                  float ox, float oy, float oz, float dx, float dy, float dz, float& tnear,
+                                                  int& best, Counters& cnt, float4* sh)
+{
+    for (int base = 0; base < n; base += NONE_CHUNK) {
+        int m = min(NONE_CHUNK, n - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            float4 s = __ldg(sph + base + i);
+            sh[i] = make_float4(s.x, s.y, s.z, s.w * s.w);
+        }
+        __syncthreads();
+        if (active) {
+            for (int i = 0; i < m; ++i) {
+                float t0, t1;
+                if (sphere_test(ox, oy, oz, dx, dy, dz, sh[i], t0, t1)) {
+                    if (t0 < 0) t0 = t1;
+                    if (t0 < tnear) { tnear = t0; best = base + i; }
+                }
+            }
+            cnt.prim_tests += m;
+        }
+    }
+}
+
+// ===================================================================================================
+// shading: castRay's DIFFUSE_AND_GLOSSY branch (main.cpp:394-497)
+// ===================================================================================================
+struct ShadeParams {
+    int       n_lights;
+    RtdsLight lights[RTDS_MAX_LIGHTS];
+    float     bg[3];
+    float     bias;
+    int       max_depth;
+    int       shadows;
+};
+
+// geometry.h:125-134: n = x*x+y*y+z*z (float); factor = (float)(1 / sqrt((double)n))
+__device__ __forceinline__ void normalize3(float& x, float& y, float& z)
+{
+    float n = x * x + y * y + z * z;
+    if (n > 0) {
+        float factor = (float)(1.0 / sqrt((double)n));
+        x *= factor; y *= factor; z *= factor;
+    }
+}
+
+// powf(x, 25) for x in [0, ~1]: exact-product chain in double, one rounding to float. glibc's powf is
+// correctly rounded except in astronomically rare cases, and so is this.
+__device__ __forceinline__ float pow25f(float xf)
+{
+    double x = (double)xf;
+    double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8;
+    return (float)(x16 * x8 * x);
+}
+
+__device__ __forceinline__ void shade_diffuse(const ShadeParams& P, float ox, float oy, float oz, float dx, float dy,
+                                              float dz, float tnear, float cx, float cy, float cz, float sr, float sg,
+                                              float sb, float& r, float& g, float& b)
+{
+    // hitPoint = rayorig + raydir * tnear; nhit = normalize(hitPoint - centre); flip towards the ray
+    float hx = ox + dx * tnear, hy = oy + dy * tnear, hz = oz + dz * tnear;
+    float nx = hx - cx, ny = hy - cy, nz = hz - cz;
+    normalize3(nx, ny, nz);
+    if (dx * nx + dy * ny + dz * nz > 0) { nx = -nx; ny = -ny; nz = -nz; }
+    float hr = 0, hg = 0, hb = 0;
+    for (int i = 0; i < P.n_lights; ++i) {
+        const RtdsLight& L = P.lights[i];
+        float lx = L.c[0] - hx, ly = L.c[1] - hy, lz = L.c[2] - hz;
+        normalize3(lx, ly, lz);
+        float LdotN = fmaxf(0.f, lx * nx + ly * ny + lz * nz);
+        // lightAmt = (1 - inShadow) * emissionColor * LdotN      (inShadow = 0: trace_more is a stub)
+        float ar = (L.le[0] * 1.0f) * LdotN, ag = (L.le[1] * 1.0f) * LdotN, ab = (L.le[2] * 1.0f) * LdotN;
+        // reflect(-lightDir, N) = I - 2*dot(I,N)*N
+        float ix = -lx, iy = -ly, iz = -lz;
+        float s2 = 2 * (ix * nx + iy * ny + iz * nz);
+        float rx = ix - nx * s2, ry = iy - ny * s2, rz = iz - nz * s2;
+        float sp = pow25f(fmaxf(0.f, -(rx * dx + ry * dy + rz * dz)));
+        float spr = L.le[0] * sp, spg = L.le[1] * sp, spb = L.le[2] * sp;
+        // hitColor += lightAmt * (diffuse * 0.8) / 2 + specular * 0.5; diffuse = (0.815,0.235,0.031)
+        hr += (ar * (0.815f * 0.8f)) / 2.0f + spr * 0.5f;
+        hg += (ag * (0.235f * 0.8f)) / 2.0f + spg * 0.5f;
+        hb += (ab * (0.031f * 0.8f)) / 2.0f + spb * 0.5f;
+        hr += sr; hg += sg; hb += sb;
+    }
+    r = hr; g = hg; b = hb;
+}
+
+// ===================================================================================================
+// K10: the render kernel. One thread per pixel of this rank's rows, samples looped in order so the
+// per-pixel float accumulation matches main.cpp:553-560.
+// ===================================================================================================
+struct RenderArgs {
+    int   width, height, spp;
+    int   rank, world, tile_rows, local_rows;
+    float angle, aspect, inv_w, inv_h;
+    const uint32_t* jitter;      // word 0 = stream word jitter_base
+    uint64_t        jitter_rel;  // (4*first_sample - jitter_base): word offset of sample 0 of pixel 0
+    BvhView bvh;
+    const float4* sph;           // objId-indexed {c, r}
+    const float4* mat;           // objId-indexed {rgb, material}
+    int           n;             // primitive count for NONE
+    ShadeParams   shade;
+    uint8_t* out_rgb;            // local rows x width x 3
+    int*     out_hit;            // optional, local rows x width
+    float*   out_accum;          // optional, local rows x width x 3
+    unsigned long long* counters;
+};
+
+template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE*/>
+__global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
+{
+    __shared__ float4 sh_sph[MODE == 2 ? NONE_CHUNK : 1];
+    // block = 16 x 8 pixels; warp = 8 x 4 pixels
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int lrow = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const bool active = px < A.width && lrow < A.local_rows;
+    int py = 0;
+    if (active) {
+        int tile = lrow / A.tile_rows, within = lrow - tile * A.tile_rows;
+        py = (tile * A.world + A.rank) * A.tile_rows + within;
+    }
+    Counters cnt = {0, 0, 0, 0};
+    float acc_r = 0, acc_g = 0, acc_b = 0;
+    int last_hit = -1;
+    const size_t pix = (size_t)py * A.width + px;
+    for (int k = 0; k < A.spp; ++k) {
+        float dx = 0, dy = 0, dz = -1;
+        if (active) {
+            size_t w = A.jitter_rel + 4 * (pix * A.spp + k);
+            uint4 jw = __ldg(reinterpret_cast<const uint4*>(A.jitter + w));
+            double r1 = canonical53(jw.x, jw.y), r2 = canonical53(jw.z, jw.w);
+            // main.cpp:554-557
+            float xx = (float)((2 * (((double)(unsigned)px + r1) * (double)A.inv_w) - 1) * (double)A.angle * (double)A.aspect);
+            float yy = (float)((1 - 2 * (((double)(unsigned)py + r2) * (double)A.inv_h)) * (double)A.angle);
+            dx = xx; dy = yy; dz = -1;
+            normalize3(dx, dy, dz);
+            cnt.rays++;
+        }
+        float tnear = INFINITY;
+        int best_key = 0, best_leaf = -1, hit_obj = -1;
+        float cx = 0, cy = 0, cz = 0;
+        if (MODE == 2) {
+            brute_force_block(A.sph, A.n, active, 0.f, 0.f, 0.f, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
+            if (hit_obj >= 0) { float4 s = __ldg(A.sph + hit_obj); cx = s.x; cy = s.y; cz = s.z; }
+        } else if (active) {
+            traverse_bvh<MODE == 0>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+            if (best_leaf >= 0) {
+                hit_obj = __ldg(A.bvh.prim_order + best_leaf);
+                float4 s = __ldg(A.bvh.leaf_sph + best_leaf);
+                cx = s.x; cy = s.y; cz = s.z;
+            }
+        }
+        if (active) {
+            float r, g, b;
+            if (hit_obj < 0) { r = A.shade.bg[0]; g = A.shade.bg[1]; b = A.shade.bg[2]; }
+            else {
+                float4 m = __ldg(A.mat + hit_obj);
+                shade_diffuse(A.shade, 0.f, 0.f, 0.f, dx, dy, dz, tnear, cx, cy, cz, m.x, m.y, m.z, r, g, b);
+            }
+            acc_r += r; acc_g += g; acc_b += b;
+            last_hit = hit_obj;
+        }
+    }
+    if (active) {
+        size_t o = (size_t)lrow * A.width + px;
+        float fs = (float)(unsigned)A.spp;
+        A.out_rgb[3 * o]     = (unsigned char)(fminf(1.0f, acc_r / fs) * 255);
+        A.out_rgb[3 * o + 1] = (unsigned char)(fminf(1.0f, acc_g / fs) * 255);
+        A.out_rgb[3 * o + 2] = (unsigned char)(fminf(1.0f, acc_b / fs) * 255);
+        if (A.out_hit) A.out_hit[o] = last_hit;
+        if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
+    }
+    // counters: warp reduce, one atomic per warp per counter
+    unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned long long x = v[c];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(&A.counters[c], x);
+    }
+}
+
+// ===================================================================================================
+// parity probe: arbitrary rays
+// ===================================================================================================
+struct TraceArgs {
+    const float* o; const float* d; int nrays;
+    BvhView bvh;
+    const float4* sph; int n;
+    int* hit; float* t;
+    unsigned long long* counters;
+    int exact;
+};
+
+template <int MODE /*0 BVH, 2 NONE*/>
+__global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A)
+{
+    __shared__ float4 sh_sph[MODE == 2 ? NONE_CHUNK : 1];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool active = i < A.nrays;
+    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = -1;
+    if (active) {
+        ox = A.o[3 * i]; oy = A.o[3 * i + 1]; oz = A.o[3 * i + 2];
+        dx = A.d[3 * i]; dy = A.d[3 * i + 1]; dz = A.d[3 * i + 2];
+    }
+    Counters cnt = {0, 0, 0, 0};
+    float tnear = INFINITY;
+    int best_key = 0, best_leaf = -1, hit_obj = -1;
+    if (MODE == 2) {
+        brute_force_block(A.sph, A.n, active, ox, oy, oz, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
+    } else if (active) {
+        // the ordered traversal's pruning bound assumes a unit direction (as every ray castRay makes has)
+        float len2 = dx * dx + dy * dy + dz * dz;
+        bool unit = fabsf(len2 - 1.0f) < 1e-3f;
+        if (A.exact || !unit) traverse_bvh<true>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+        else traverse_bvh<false>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+        if (best_leaf >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf);
+    }
+    if (active) { A.hit[i] = hit_obj; A.t[i] = tnear; cnt.rays = 1; }
+    unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned long long x = v[c];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(&A.counters[c], x);
+    }
+}
+
+BvhView make_view(const DeviceBvh& b)
+{
+    BvhView v;
+    v.nodes = b.nodes; v.leaf_sph = b.leaf_sph; v.prim_order = b.prim_order;
+    v.root_ref = b.root_ref; v.tie_by_objid = b.tie_by_objid;
+    for (int i = 0; i < 6; ++i) v.root_box[i] = b.root_box[i];
+    return v;
+}
+
+int check_bvh(rtds_ctx* ctx, int acc)
+{
+    if (!ctx->bvh.valid || ctx->bvh_acc != acc) {
+        rtds_set_error("acc_type %d requested but the last BVH/LBVH build was acc_type %d (valid=%d): call rtds_build first",
+                       acc, ctx->bvh_acc, (int)ctx->bvh.valid);
+        return RTDS_ERR_NOT_BUILT;
+    }
+    if (ctx->bvh.max_depth >= STACK_MAX) {
+        rtds_set_error("tree depth %d exceeds the traversal stack (%d)", ctx->bvh.max_depth, STACK_MAX);
+        return RTDS_ERR_UNSUPPORTED;
+    }
+    return RTDS_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+int rtds_jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int* launches)
+{
+    if (n_words == 0) return RTDS_OK;
+    const uint64_t words_per_snap = (uint64_t)MT_SNAP_EVERY * MT_N;
+    const uint64_t s0 = first_word / words_per_snap;
+    const uint64_t s1 = (first_word + n_words - 1) / words_per_snap;  // last snapshot chunk needed (inclusive)
+    if (s1 + 2 >= (1ull << 31)) { rtds_set_error("jitter stream position too large"); return RTDS_ERR_INVALID; }
+    const int need_snaps = (int)(s1 + 1);
+    cudaStream_t s = ctx->stream;
+    if (ctx->n_snap < need_snaps) {
+        // grow geometrically; keep existing snapshots
+        int cap = need_snaps + need_snaps / 4 + 16;
+        uint32_t* nsnap = nullptr;
+        RTDS_CUDA(cudaMalloc(&nsnap, sizeof(uint32_t) * MT_N * (size_t)cap));
+        if (ctx->n_snap > 0)
+            RTDS_CUDA(cudaMemcpyAsync(nsnap, ctx->d_mt_snap, sizeof(uint32_t) * MT_N * (size_t)ctx->n_snap, cudaMemcpyDeviceToDevice, s));
+        mt_snapshot_kernel<<<1, MT_THREADS, 0, s>>>(nsnap, ctx->n_snap, cap, 5489u);
+        if (launches) *launches += 1;
+        RTDS_CUDA(cudaGetLastError());
+        RTDS_CUDA(cudaStreamSynchronize(s));
+        if (ctx->d_mt_snap) cudaFree(ctx->d_mt_snap);
+        ctx->d_mt_snap = nsnap;
+        ctx->n_snap = cap;
+    }
+    const int blocks = (int)(s1 - s0 + 1);
+    const size_t out_words = (size_t)blocks * words_per_snap;
+    if (ctx->jitter_cap_words < out_words) {
+        if (ctx->d_jitter) cudaFree(ctx->d_jitter);
+        ctx->d_jitter = nullptr; ctx->jitter_cap_words = 0;
+        RTDS_CUDA(cudaMalloc(&ctx->d_jitter, sizeof(uint32_t) * out_words));
+        ctx->jitter_cap_words = out_words;
+    }
+    mt_expand_kernel<<<blocks, MT_THREADS, 0, s>>>(ctx->d_mt_snap, (int)s0, ctx->d_jitter, out_words);
+    if (launches) *launches += 1;
+    RTDS_CUDA(cudaGetLastError());
+    ctx->jitter_first_word = s0 * words_per_snap;
+    ctx->jitter_n_words = out_words;
+    return RTDS_OK;
+}
+
+int rtds_jitter_stream_impl(rtds_ctx* ctx, uint64_t first, int n, double* out)
+{
+    if (n <= 0) return RTDS_OK;
+    RTDS_TRY(rtds_jitter_prepare(ctx, first * 2, (size_t)n * 2, nullptr));
+    RTDS_TRY(rtds_ensure_scratch(ctx, sizeof(double) * (size_t)n));
+    double* d_out = (double*)ctx->d_scratch;
+    jitter_doubles_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_jitter, (size_t)(first - ctx->jitter_first_word / 2), n, d_out);
+    RTDS_CUDA(cudaGetLastError());
+    RTDS_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RTDS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RTDS_OK;
+}
+
+int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_t* d_rgb_rows, int* d_hit, float* d_accum,
+                     rtds_render_stats* st)
+{
+    const int W = p->width, H = p->height, spp = p->aa_samples;
+    if (W <= 0 || H <= 0 || spp <= 0) { rtds_set_error("render: width/height/aa_samples must be positive"); return RTDS_ERR_INVALID; }
+    const int world = p->world > 0 ? p->world : 1, rank = p->rank;
+    if (rank < 0 || rank >= world) { rtds_set_error("render: rank %d outside world %d", rank, world); return RTDS_ERR_INVALID; }
+    const int tile_rows = p->tile_rows > 0 ? p->tile_rows : 8;
+    if (ctx->n <= 0) { rtds_set_error("render: no scene"); return RTDS_ERR_NO_SCENE; }
+    if (acc == RTDS_KDTREE) { rtds_set_error("render: KDTREE not implemented yet"); return RTDS_ERR_UNSUPPORTED; }
+    const bool brute = (acc != RTDS_BVH && acc != RTDS_LBVH);
+    if (!brute) RTDS_TRY(check_bvh(ctx, acc));
+
+    RenderArgs A;
+    A.width = W; A.height = H; A.spp = spp;
+    A.rank = rank; A.world = world; A.tile_rows = tile_rows;
+    A.local_rows = rtds_rows_for_rank(H, tile_rows, rank, world);
+    // main.cpp:544-546
+    const float fov = p->fov > 0 ? p->fov : 30.0f;
+    A.inv_w = 1 / float(W); A.inv_h = 1 / float(H);
+    A.aspect = W / float(H);
+    A.angle = (float)tan(3.141592653589793 * 0.5 * fov / 180.);
+    A.n = ctx->n; A.sph = ctx->d_sph; A.mat = ctx->d_mat;
+    if (!brute) A.bvh = make_view(ctx->bvh); else A.bvh = BvhView();
+    A.shade.n_lights = ctx->n_lights;
+    for (int i = 0; i < ctx->n_lights; ++i) A.shade.lights[i] = ctx->lights[i];
+    const bool bg0 = p->bg[0] == 0 && p->bg[1] == 0 && p->bg[2] == 0;
+    A.shade.bg[0] = bg0 ? 0.6f : p->bg[0]; A.shade.bg[1] = bg0 ? 0.8f : p->bg[1]; A.shade.bg[2] = bg0 ? 1.0f : p->bg[2];
+    A.shade.bias = p->bias > 0 ? p->bias : 1e-4f;
+    A.shade.max_depth = p->max_depth > 0 ? p->max_depth : 2;
+    A.shade.shadows = p->shadows;
+    if (p->shadows) { rtds_set_error("render: shadows not implemented yet"); return RTDS_ERR_UNSUPPORTED; }
+    A.out_rgb = d_rgb_rows; A.out_hit = d_hit; A.out_accum = d_accum;
+    A.counters = ctx->d_counters;
+
+    cudaStream_t s = ctx->stream;
+    int launches = 0;
+    RTDS_CUDA(cudaEventRecord(ctx->ev0, s));
+    const uint64_t first_word = 4ull * p->jitter_offset;
+    const size_t n_words = 4ull * (size_t)W * H * spp;
+    if (!(p->no_jitter_regen && ctx->d_jitter && ctx->jitter_first_word <= first_word &&
+          first_word + n_words <= ctx->jitter_first_word + ctx->jitter_n_words))
+        RTDS_TRY(rtds_jitter_prepare(ctx, first_word, n_words, &launches));
+    A.jitter = ctx->d_jitter;
+    A.jitter_rel = first_word - ctx->jitter_first_word;
+    RTDS_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 8, s));
+    if (A.local_rows > 0) {
+        dim3 grid((W + 15) / 16, (A.local_rows + 7) / 8), block(128);
+        RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
+        if (brute) render_kernel<2><<<grid, block, 0, s>>>(A);
+        else if (p->exact) render_kernel<0><<<grid, block, 0, s>>>(A);
+        else render_kernel<1><<<grid, block, 0, s>>>(A);
+        RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
+        launches += 1;
+        RTDS_CUDA(cudaGetLastError());
+    } else {
+        RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
+        RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
+    }
+    RTDS_CUDA(cudaEventRecord(ctx->ev1, s));
+    if (st) {
+        unsigned long long c[8];
+        RTDS_CUDA(cudaMemcpyAsync(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, s));
+        RTDS_CUDA(cudaStreamSynchronize(s));
+        memset(st, 0, sizeof *st);
+        st->node_tests = c[0]; st->prim_tests = c[1]; st->node_visits = c[2];
+        st->primary_rays = c[3]; st->rays = c[3];
+        RTDS_CUDA(cudaEventElapsedTime(&st->ms_kernel, ctx->ev2, ctx->ev3));
+        RTDS_CUDA(cudaEventElapsedTime(&st->ms_total, ctx->ev0, ctx->ev1));
+        st->kernel_launches = launches;
+        st->rows = A.local_rows;
+    }
+    return RTDS_OK;
+}
+
+int rtds_trace_impl(rtds_ctx* ctx, int acc, int exact, const float* h_o, const float* h_d, int nrays, int* h_hit, float* h_t,
+                    rtds_render_stats* st)
+{
+    if (nrays <= 0) return RTDS_OK;
+    if (ctx->n <= 0) { rtds_set_error("trace: no scene"); return RTDS_ERR_NO_SCENE; }
+    if (acc == RTDS_KDTREE) { rtds_set_error("trace: KDTREE not implemented yet"); return RTDS_ERR_UNSUPPORTED; }
+    const bool brute = (acc != RTDS_BVH && acc != RTDS_LBVH);
+    if (!brute) RTDS_TRY(check_bvh(ctx, acc));
+    size_t vec = (sizeof(float) * 3 * (size_t)nrays + 255) & ~(size_t)255;
+    size_t one = (sizeof(float) * (size_t)nrays + 255) & ~(size_t)255;
+    RTDS_TRY(rtds_ensure_scratch(ctx, 2 * vec + 2 * one));
+    char* base = (char*)ctx->d_scratch;
+    float* d_o = (float*)base; float* d_d = (float*)(base + vec);
+    int* d_hit = (int*)(base + 2 * vec); float* d_t = (float*)(base + 2 * vec + one);
+    cudaStream_t s = ctx->stream;
+    RTDS_CUDA(cudaMemcpyAsync(d_o, h_o, sizeof(float) * 3 * (size_t)nrays, cudaMemcpyHostToDevice, s));
+    RTDS_CUDA(cudaMemcpyAsync(d_d, h_d, sizeof(float) * 3 * (size_t)nrays, cudaMemcpyHostToDevice, s));
+    RTDS_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 8, s));
+    TraceArgs A;
+    A.o = d_o; A.d = d_d; A.nrays = nrays;
+    if (!brute) A.bvh = make_view(ctx->bvh); else A.bvh = BvhView();
+    A.sph = ctx->d_sph; A.n = ctx->n; A.hit = d_hit; A.t = d_t; A.counters = ctx->d_counters; A.exact = exact;
+    RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
+    if (brute) trace_kernel<2><<<(nrays + 127) / 128, 128, 0, s>>>(A);
+    else trace_kernel<0><<<(nrays + 127) / 128, 128, 0, s>>>(A);
+    RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
+    RTDS_CUDA(cudaGetLastError());
+    RTDS_CUDA(cudaMemcpyAsync(h_hit, d_hit, sizeof(int) * (size_t)nrays, cudaMemcpyDeviceToHost, s));
+    RTDS_CUDA(cudaMemcpyAsync(h_t, d_t, sizeof(float) * (size_t)nrays, cudaMemcpyDeviceToHost, s));
+    unsigned long long c[8];
+    RTDS_CUDA(cudaMemcpyAsync(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, s));
+    RTDS_CUDA(cudaStreamSynchronize(s));
+    if (st) {
+        memset(st, 0, sizeof *st);
+        st->node_tests = c[0]; st->prim_tests = c[1]; st->node_visits = c[2]; st->rays = c[3]; st->primary_rays = c[3];
+        RTDS_CUDA(cudaEventElapsedTime(&st->ms_kernel, ctx->ev2, ctx->ev3));
+        st->ms_total = st->ms_kernel;
+        st->kernel_launches = 1;
+    }
+    return RTDS_OK;
+}

@@ -1,0 +1,181 @@
+// rtds_internal.cuh — shared declarations of librtds.so (device layouts, context, helpers).
+// All device code in this library is compiled for sm_100a only, with -fmad=false (the reference is x86-64
+// SSE2 code without FMA contraction; see DESIGN.md "Exact float semantics").
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/rtds.h"
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+void rtds_set_error(const char* fmt, ...);
+
+#define RTDS_CUDA(call)                                                                            \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            rtds_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));  \
+            return RTDS_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+#define RTDS_TRY(call)                                                                             \
+    do {                                                                                           \
+        int s_ = (call);                                                                           \
+        if (s_ != RTDS_OK) return s_;                                                              \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// device layouts
+// ---------------------------------------------------------------------------------------------------
+
+// Traversal node: one 64-byte record per INTERIOR node holding both children's AABBs, so one visit is
+// four coalescable 16-byte loads and tests two boxes (accelerators.h:131-156 is a 160-byte pointer node).
+//   q0 = {lmin.x, lmin.y, lmin.z, lmax.x}   q1 = {lmax.y, lmax.z, rmin.x, rmin.y}
+//   q2 = {rmin.z, rmax.x, rmax.y, rmax.z}   q3 = {left, right, axis, parent} (ints)
+// Child reference: >= 0 interior node index, < 0 leaf: ~leafpos (position in leaf order).
+struct __align__(16) Node64 {
+    float lmin[3], lmax[3];
+    float rmin[3], rmax[3];
+    int   left, right;
+    int   axis;        // split axis of this node (exported as LinearBVHNode::axis)
+    int   parent;      // interior parent index, -1 for the root
+};
+static_assert(sizeof(Node64) == 64, "Node64 must be 64 bytes");
+
+struct DeviceBvh {
+    int      n_prims = 0;          // leaves
+    int      n_internal = 0;       // n_prims - 1 (0 when n_prims == 1)
+    int      root_ref = 0;         // 0 (interior node 0) or ~0 when the tree is a single leaf
+    Node64*  nodes = nullptr;      // [n_internal]
+    float4*  leaf_sph = nullptr;   // [n_prims] {cx,cy,cz,r^2} in leaf order (radius2 = r*r, accelerators.h:71)
+    int*     prim_order = nullptr; // [n_prims] leafpos -> objId
+    int*     leaf_parent = nullptr;// [n_prims] interior parent of each leaf (bit 31 set: right child)
+    float    root_box[6] = {0, 0, 0, 0, 0, 0};
+    int      tie_by_objid = 0;     // 1: equal-t candidates resolve to the lower objId (NONE order,
+                                   // main.cpp:376-386); 0: to the lower leaf position (DFS order of
+                                   // boxIntersect, accelerators.h:668-690)
+    int      max_depth = 0;
+    bool     valid = false;
+};
+
+struct DeviceKd {
+    int           n_nodes = 0;        // nextFreeNode
+    int           total_nodes = 0;    // totalKdNodes as the reference counts them
+    int           n_idx = 0;
+    rtds_kd_node* nodes = nullptr;
+    int*          prim_idx = nullptr;
+    float         bounds[6] = {0, 0, 0, 0, 0, 0};
+    bool          valid = false;
+};
+
+struct RtdsLight { float c[3]; float radius; float le[3]; };
+#define RTDS_MAX_LIGHTS 8
+
+struct rtds_ctx {
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t  ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    int          sm_count = 148;
+
+    // scene (objId-indexed)
+    int     n = 0;
+    float4* d_sph = nullptr;     // {cx,cy,cz,r}
+    float4* d_mat = nullptr;     // {r,g,b,(float)material}
+    int     n_lights = 0;
+    RtdsLight lights[RTDS_MAX_LIGHTS];
+
+    // triangles (extension)
+    int     n_tris = 0;
+    float*  d_tris = nullptr;
+
+    DeviceBvh bvh;               // last BVH/LBVH build
+    int       bvh_acc = -1;      // acc type that produced `bvh`
+    int       bvh_mode = 0;
+    DeviceKd  kd;
+
+    // sorted Morton keys of the last TRUE LBVH build (export / tests)
+    uint64_t* d_keys_sorted = nullptr;
+    int       n_keys = 0;
+
+    // jitter: MT19937 state snapshots (one per RTDS_MT_SNAP_EVERY regenerations) and the expanded words
+    uint32_t* d_mt_snap = nullptr;   // [n_snap][624]
+    int       n_snap = 0;
+    uint32_t* d_jitter = nullptr;    // tempered words
+    size_t    jitter_cap_words = 0;
+    uint64_t  jitter_first_word = 0; // stream index of d_jitter[0]
+    size_t    jitter_n_words = 0;
+
+    // scratch
+    void*   d_scratch = nullptr;
+    size_t  scratch_bytes = 0;
+    void*   d_sort_ws = nullptr;     // onesweep workspace (histograms, tile counters, look-back status)
+    size_t  sort_ws_bytes = 0;
+    uint8_t* d_frame = nullptr;      // rgb8 staging
+    size_t   frame_bytes = 0;
+    int*     d_hit = nullptr;  size_t hit_bytes = 0;
+    float*   d_accum = nullptr; size_t accum_bytes = 0;
+    unsigned long long* d_counters = nullptr;  // render counters [8]
+    uint8_t* h_pinned = nullptr;     // pinned host staging for D2H of frames
+    size_t   pinned_bytes = 0;
+};
+
+int rtds_ensure_scratch(rtds_ctx* ctx, size_t bytes);
+template <typename T> int rtds_realloc(T** p, size_t* cap_bytes, size_t need_bytes);
+
+// ---------------------------------------------------------------------------------------------------
+// builders / kernels (one translation unit each)
+// ---------------------------------------------------------------------------------------------------
+void rtds_free_bvh(DeviceBvh& b);
+int  rtds_alloc_bvh(DeviceBvh& b, int n_prims);
+
+// lbvh.cu — K1 bounds, K2 Morton, K4 Karras emission, K5 atomic refit
+int rtds_build_lbvh_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st);
+int rtds_morton30_device(rtds_ctx* ctx, const float* h_xyz, int n, uint32_t* h_codes);
+int rtds_bvh_preorder_export(rtds_ctx* ctx, rtds_linear_bvh_node* h_nodes, int cap_nodes, int* n_nodes,
+                             int* h_prim_order, int cap_prims, int* n_prims);
+
+// sort.cu — K3 onesweep LSD radix sort of (key, value) pairs; keys 32 or 64 bit
+int rtds_onesweep_sort_u32(rtds_ctx* ctx, uint32_t* d_keys, uint32_t* d_vals, uint32_t* d_keys_tmp,
+                           uint32_t* d_vals_tmp, int n, int key_bits, int* launches);
+int rtds_onesweep_sort_u64(rtds_ctx* ctx, uint64_t* d_keys, uint32_t* d_vals, uint64_t* d_keys_tmp,
+                           uint32_t* d_vals_tmp, int n, int key_bits, int* launches);
+
+// median.cu — K6 median-split BVH, bit-exact with constructBVHNew incl. libstdc++ partition/nth_element
+int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st);
+
+// sah.cu — K7 binned SAH BVH
+int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st);
+
+// kd.cu — K8 KD-tree SAH build
+int rtds_build_kd(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st);
+void rtds_free_kd(DeviceKd& k);
+
+// render.cu — K10 render/trace, K11 MT19937 jitter stream
+int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_t* d_rgb_rows, int* d_hit,
+                     float* d_accum, rtds_render_stats* st);
+int rtds_trace_impl(rtds_ctx* ctx, int acc, int exact, const float* h_o, const float* h_d, int nrays,
+                    int* h_hit, float* h_t, rtds_render_stats* st);
+int rtds_jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int* launches);
+
+// ---------------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// order-preserving float <-> uint mapping for atomicMin/atomicMax on floats
+__device__ __forceinline__ unsigned f2ord(float f)
+{
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+#endif

@@ -1,0 +1,105 @@
+"""GPU parity: jitter stream, traversal + ray/sphere test (rtds_trace), and the whole render path — against the
+oracle port, the golden vectors of the unmodified reference, and (size-independent) cross-mode properties."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import conftest as T
+
+rt = T.rtds_b200
+G = T.load_golden_json()
+pytestmark = pytest.mark.gpu
+
+
+def test_jitter_stream_bit_exact(gpu_ctx, oracle):
+    g = G["jitter"]
+    j = gpu_ctx.jitter_stream(0, 1000004)
+    assert [float(x).hex() for x in j[:8]] == g["first8_hex"]
+    assert [float(x).hex() for x in j[1000000:1000004]] == g["at_1000000_hex"]
+    assert hashlib.sha256(j[:1000000].tobytes()).hexdigest() == g["sha256_first_1e6"]
+    # a window far into the stream (4K x 4 spp needs 66.4M doubles), regenerated from snapshots
+    first = 66_000_000
+    assert np.array_equal(gpu_ctx.jitter_stream(first, 4096), oracle.jitter(4096, first))
+
+
+def _rays(n, seed, sph):
+    rng = np.random.default_rng(seed)
+    o = np.zeros((n, 3), np.float32)
+    tgt = sph[rng.integers(0, sph.shape[0], n), :3] + rng.normal(size=(n, 3)).astype(np.float32) * np.float32(0.05)
+    o[n // 2:] = rng.normal(size=(n - n // 2, 3)).astype(np.float32) * np.float32(20)   # second half: arbitrary origins
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return o, d.astype(np.float32)
+
+
+@pytest.mark.parametrize("bits", [30, 63])
+def test_trace_lbvh_true_matches_oracle_and_none(gpu_ctx, oracle, bits):
+    sph, mat = T.synthetic_scene(20000, 21)
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE, morton_bits=bits)
+    nodes, order = gpu_ctx.export_bvh()
+    o, d = _rays(20000, 22, sph)
+    h_o, t_o, cand = oracle.trace(sph, nodes, order, o, d, tie_by_objid=1)
+    for exact in (True, False):
+        h, t, st = gpu_ctx.trace(rt.LBVH, o, d, exact=exact)
+        assert np.array_equal(h, h_o), f"hit ids differ (exact={exact}): {np.count_nonzero(h != h_o)}"
+        assert t.tobytes() == t_o.tobytes()
+        if exact:
+            assert st["prim_tests"] == cand      # same candidate set as boxIntersect's collect-all traversal
+    hn, tn, _ = gpu_ctx.trace(rt.NONE, o, d)
+    hn_o, tn_o, _ = oracle.trace(sph, None, None, o, d)
+    assert np.array_equal(hn, hn_o) and tn.tobytes() == tn_o.tobytes()
+    assert (h_o >= 0).mean() > 0.3
+
+
+def test_render_none_default_config_is_byte_exact(gpu_ctx):
+    """dataStructure = NONE on the default config: the GPU frame equals the reference's PPM byte for byte."""
+    sph, mat = T.bunny_scene()
+    gpu_ctx.set_spheres(sph, mat)
+    rgb, hit, _, st = gpu_ctx.render(rt.NONE, 640, 480, 1, want_hit=True)
+    gold = np.load(T.GOLDEN + "/bunny_hits_640x480.npz")
+    assert np.array_equal(hit, gold["hit_none"])
+    assert T.ppm_md5(rgb) == G["default_config"]["NONE"]["ppm_md5"]
+    assert st["prim_tests"] == 640 * 480 * sph.shape[0]
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_render_lbvh_true_bunny_vs_oracle(gpu_ctx, oracle, exact):
+    sph, mat = T.bunny_scene()
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+    nodes, order = gpu_ctx.export_bvh()
+    rgb, hit, accum, st = gpu_ctx.render(rt.LBVH, 640, 480, 1, want_hit=True, want_accum=True, exact=exact)
+    rgb_o, hit_o, accum_o, _ = oracle.render_rows(sph, mat, nodes, order, 640, 480, 1, tie_by_objid=1, want_accum=True)
+    assert np.array_equal(hit, hit_o)
+    assert accum.tobytes() == accum_o.tobytes(), "float RGB sums differ from the CPU restatement"
+    assert np.array_equal(rgb, rgb_o)
+    # any valid BVH over the same leaf boxes yields the candidate set of the reference BVH path:
+    gold = np.load(T.GOLDEN + "/bunny_hits_640x480.npz")
+    diff = np.count_nonzero(hit != gold["hit_bvh"])
+    assert diff <= 3, f"{diff} pixels differ from the reference BVH path's hit ids"
+    assert st["primary_rays"] == 640 * 480
+
+
+def test_render_multisample_and_ranks(gpu_ctx, oracle):
+    """aa_samples = 4 accumulation order + interleaved scanline tiles: every rank's rows equal the 1-rank frame."""
+    sph, mat = T.synthetic_scene(3000, 31)
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+    nodes, order = gpu_ctx.export_bvh()
+    W, H, spp = 322, 203, 4          # ragged: not multiples of the 16x8 block or of tile_rows
+    full, hit, accum, _ = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True)
+    rgb_o, hit_o, accum_o, _ = oracle.render_rows(sph, mat, nodes, order, W, H, spp, tie_by_objid=1, want_accum=True)
+    assert accum.tobytes() == accum_o.tobytes() and np.array_equal(full, rgb_o) and np.array_equal(hit, hit_o)
+    for world in (2, 3, 8):
+        frame = np.zeros((H, W, 3), np.uint8)
+        rows_seen = 0
+        for rank in range(world):
+            part = np.zeros((H, W, 3), np.uint8)
+            _, _, _, st = gpu_ctx.render(rt.LBVH, W, H, spp, out=part, rank=rank, world=world)
+            rows = rt.owned_rows(H, 8, rank, world)
+            assert st["rows"] == rows.size == rt.rows_for_rank(H, 8, rank, world)
+            frame[rows] = part[rows]
+            rows_seen += rows.size
+        assert rows_seen == H and np.array_equal(frame, full)
