@@ -405,6 +405,19 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
 
 }  // namespace
 
+int rtds_bvh_compute_depth(rtds_ctx* ctx, DeviceBvh& b, int* depth_out)
+{
+    int* d_depth = nullptr;
+    RTDS_CUDA(cudaMalloc(&d_depth, sizeof(int)));
+    RTDS_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(int), ctx->stream));
+    depth_kernel<<<(b.n_prims + 255) / 256, 256, 0, ctx->stream>>>(b.nodes, b.leaf_parent, b.n_prims, d_depth);
+    RTDS_CUDA(cudaGetLastError());
+    RTDS_CUDA(cudaMemcpyAsync(depth_out, d_depth, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RTDS_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_depth);
+    return RTDS_OK;
+}
+
 int rtds_build_lbvh_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st)
 {
     int bits = (p && p->morton_bits) ? p->morton_bits : 30;
