@@ -194,6 +194,28 @@ __device__ __forceinline__ float prune_margin(const float rb[6], float ox, float
     return D * 0.00278f;
 }
 
+// Conservative slab test for INTERIOR boxes of the ordered traversal: t = (b - o) * (1/d) instead of six IEEE
+// divides, with the interval widened by more than the rounding difference between the two forms, so it accepts
+// every box the reference's test accepts (and a few more). Interior tests only steer the descent — whether a
+// sphere becomes a candidate is decided by the EXACT test on its own leaf box (a leaf box inside a node box
+// passes the reference's test only if the node box does: the per-axis intervals nest monotonically).
+// Valid for finite, non-tiny direction components (checked once per ray).
+constexpr float WIDE_EPS = 4.76837158e-7f;   // 2^-21 > 2^-24 (rcp) + 2^-24 (mul) + 2^-24 (the divide's own rounding)
+__device__ __forceinline__ bool slab_wide(float ox, float oy, float oz, float ix, float iy, float iz, float bminx, float bminy,
+                                          float bminz, float bmaxx, float bmaxy, float bmaxz, float& tmin_o, float& tmax_o)
+{
+    float x0 = (bminx - ox) * ix, x1 = (bmaxx - ox) * ix;
+    float y0 = (bminy - oy) * iy, y1 = (bmaxy - oy) * iy;
+    float z0 = (bminz - oz) * iz, z1 = (bmaxz - oz) * iz;
+    float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+    float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+    tmin = tmin - fabsf(tmin) * WIDE_EPS;
+    tmax = tmax + fabsf(tmax) * WIDE_EPS;
+    tmin_o = tmin;
+    tmax_o = tmax;
+    return tmin <= tmax;
+}
+
 template <bool EXACT>
 __device__ __forceinline__ void traverse_bvh(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
                                              float& tnear, int& best_key, int& best_leaf, Counters& cnt)
@@ -211,6 +233,10 @@ __device__ __forceinline__ void traverse_bvh(const BvhView& B, float ox, float o
         return;
     }
     const float margin = EXACT ? 0.0f : prune_margin(B.root_box, ox, oy, oz);
+    // reciprocal direction for the conservative interior test; rays with a zero / tiny / non-finite component
+    // take the exact divide-based test everywhere
+    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+    const bool wide_ok = !EXACT && fabsf(ix) < 1e30f && fabsf(iy) < 1e30f && fabsf(iz) < 1e30f;
     int   stack[STACK_MAX];
     float stack_t[EXACT ? 1 : STACK_MAX];
     int sp = 0;
@@ -221,10 +247,20 @@ __device__ __forceinline__ void traverse_bvh(const BvhView& B, float ox, float o
         int4 q3 = __ldg(reinterpret_cast<const int4*>(q + 3));
         cnt.node_visits++;
         cnt.node_tests += 2;
-        float tminL, tmaxL, tminR, tmaxR;
-        bool hitL = slab_test(ox, oy, oz, dx, dy, dz, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tminL, tmaxL);
-        bool hitR = slab_test(ox, oy, oz, dx, dy, dz, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tminR, tmaxR);
         const int left = q3.x, right = q3.y;
+        float tminL, tmaxL, tminR, tmaxR;
+        bool hitL, hitR;
+        if (!EXACT && wide_ok) {
+            // interior child: the conservative test is the answer; leaf child: it is a filter — a box the wide
+            // test rejects is rejected by the reference's test too, only survivors pay for the six divides
+            hitL = slab_wide(ox, oy, oz, ix, iy, iz, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tminL, tmaxL);
+            hitR = slab_wide(ox, oy, oz, ix, iy, iz, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tminR, tmaxR);
+            if (hitL && left < 0) hitL = slab_test(ox, oy, oz, dx, dy, dz, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tminL, tmaxL);
+            if (hitR && right < 0) hitR = slab_test(ox, oy, oz, dx, dy, dz, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tminR, tmaxR);
+        } else {
+            hitL = slab_test(ox, oy, oz, dx, dy, dz, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tminL, tmaxL);
+            hitR = slab_test(ox, oy, oz, dx, dy, dz, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tminR, tmaxR);
+        }
         if (!EXACT) {
             // NaN-safe: a comparison with NaN is false and keeps the child
             if (hitL && (tminL > tnear + margin || tmaxL < -margin)) hitL = false;
