@@ -46,14 +46,19 @@ void rtds_free_bvh(DeviceBvh& b)
     b = DeviceBvh();
 }
 
+// (Re)uses the arrays when they are large enough: cudaMalloc/cudaFree are device-wide synchronisation points and
+// cost milliseconds once peer access is enabled (NCCL), so a rebuild of the same scene must not touch them.
 int rtds_alloc_bvh(DeviceBvh& b, int n_prims)
 {
+    b.valid = false;
+    if (b.capacity >= n_prims && b.nodes) return RTDS_OK;
     rtds_free_bvh(b);
     size_t ni = n_prims > 1 ? (size_t)(n_prims - 1) : 1;
     RTDS_CUDA(cudaMalloc(&b.nodes, sizeof(Node64) * ni));
     RTDS_CUDA(cudaMalloc(&b.leaf_sph, sizeof(float4) * (size_t)n_prims));
     RTDS_CUDA(cudaMalloc(&b.prim_order, sizeof(int) * (size_t)n_prims));
     RTDS_CUDA(cudaMalloc(&b.leaf_parent, sizeof(int) * (size_t)n_prims));
+    b.capacity = n_prims;
     return RTDS_OK;
 }
 
@@ -125,12 +130,16 @@ int rtds_set_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int
     if (!c || !cxyz_r || n <= 0) { rtds_set_error("set_spheres: bad arguments"); return RTDS_ERR_INVALID; }
     RTDS_CUDA(cudaSetDevice(c->device));
     RTDS_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->d_sph) cudaFree(c->d_sph);
-    if (c->d_mat) cudaFree(c->d_mat);
-    c->d_sph = nullptr; c->d_mat = nullptr; c->n = 0;
+    c->n = 0;
     c->bvh.valid = false; c->kd.valid = false; c->bvh_acc = -1;
-    RTDS_CUDA(cudaMalloc(&c->d_sph, sizeof(float4) * (size_t)n));
-    RTDS_CUDA(cudaMalloc(&c->d_mat, sizeof(float4) * (size_t)n));
+    if (c->sph_capacity < n) {
+        if (c->d_sph) cudaFree(c->d_sph);
+        if (c->d_mat) cudaFree(c->d_mat);
+        c->d_sph = nullptr; c->d_mat = nullptr; c->sph_capacity = 0;
+        RTDS_CUDA(cudaMalloc(&c->d_sph, sizeof(float4) * (size_t)n));
+        RTDS_CUDA(cudaMalloc(&c->d_mat, sizeof(float4) * (size_t)n));
+        c->sph_capacity = n;
+    }
     RTDS_CUDA(cudaMemcpyAsync(c->d_sph, cxyz_r, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     if (rgb_mat) {
         RTDS_CUDA(cudaMemcpyAsync(c->d_mat, rgb_mat, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));

@@ -349,10 +349,11 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
     uint32_t* d_vals_tmp = (uint32_t*)(base + off_vals_tmp);
 
     RTDS_TRY(rtds_alloc_bvh(b, n));
-    if (ctx->n_keys < n) {
+    if (ctx->keys_capacity < n) {
         if (ctx->d_keys_sorted) cudaFree(ctx->d_keys_sorted);
         ctx->d_keys_sorted = nullptr;
         RTDS_CUDA(cudaMalloc(&ctx->d_keys_sorted, sizeof(uint64_t) * (size_t)n));
+        ctx->keys_capacity = n;
     }
     ctx->n_keys = n;
 
@@ -407,14 +408,12 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
 
 int rtds_bvh_compute_depth(rtds_ctx* ctx, DeviceBvh& b, int* depth_out)
 {
-    int* d_depth = nullptr;
-    RTDS_CUDA(cudaMalloc(&d_depth, sizeof(int)));
+    int* d_depth = (int*)(ctx->d_counters + 7);   // last slot of the context's counter block
     RTDS_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(int), ctx->stream));
     depth_kernel<<<(b.n_prims + 255) / 256, 256, 0, ctx->stream>>>(b.nodes, b.leaf_parent, b.n_prims, d_depth);
     RTDS_CUDA(cudaGetLastError());
     RTDS_CUDA(cudaMemcpyAsync(depth_out, d_depth, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     RTDS_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_depth);
     return RTDS_OK;
 }
 

@@ -77,18 +77,35 @@ __global__ void __launch_bounds__(MT_THREADS) mt_snapshot_kernel(uint32_t* __res
     }
 }
 
+// Which part of the stream a rank needs: the samples of the scanline tiles it owns (all of it when world == 1).
+struct JitterOwner {
+    unsigned long long first_word;   // stream word of sample 0 of pixel 0
+    unsigned long long row_words;    // 4 * width * spp
+    int tile_rows, rank, world, height;
+};
+
 // Block b regenerates MT_SNAP_EVERY times from snapshot (s0 + b) and writes the tempered words.
-// out[0] is stream word (s0 * MT_SNAP_EVERY * 624).
+// out[0] is stream word (s0 * MT_SNAP_EVERY * 624). Chunks that hold no sample of an owned row are skipped.
 __global__ void __launch_bounds__(MT_THREADS) mt_expand_kernel(const uint32_t* __restrict__ snap, int s0,
-                                                               uint32_t* __restrict__ out, size_t n_words)
+                                                               uint32_t* __restrict__ out, size_t n_words, const JitterOwner own)
 {
     __shared__ uint32_t S[2][MT_N];
     const int t = threadIdx.x;
+    const size_t base = (size_t)blockIdx.x * MT_SNAP_EVERY * MT_N;
+    if (own.world > 1) {
+        const unsigned long long wlo = (unsigned long long)(s0 + blockIdx.x) * MT_SNAP_EVERY * MT_N;
+        const unsigned long long whi = wlo + MT_SNAP_EVERY * MT_N - 1;
+        long long ylo = wlo > own.first_word ? (long long)((wlo - own.first_word) / own.row_words) : 0;
+        long long yhi = whi > own.first_word ? (long long)((whi - own.first_word) / own.row_words) : 0;
+        if (yhi >= own.height) yhi = own.height - 1;
+        bool mine = false;
+        for (long long tl = ylo / own.tile_rows; tl <= yhi / own.tile_rows; ++tl) mine |= (tl % own.world) == own.rank;
+        if (!mine) return;
+    }
     const uint32_t* src = snap + (size_t)(s0 + blockIdx.x) * MT_N;
     for (int i = t; i < MT_N; i += MT_THREADS) S[0][i] = src[i];
     __syncthreads();
     int cur = 0;
-    size_t base = (size_t)blockIdx.x * MT_SNAP_EVERY * MT_N;
     for (int r = 0; r < MT_SNAP_EVERY; ++r) {
         mt_regen(S[cur], S[cur ^ 1]);
         cur ^= 1;
@@ -570,7 +587,7 @@ int check_bvh(rtds_ctx* ctx, int acc)
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-int rtds_jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int* launches)
+static int jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int* launches, const JitterOwner& own)
 {
     if (n_words == 0) return RTDS_OK;
     const uint64_t words_per_snap = (uint64_t)MT_SNAP_EVERY * MT_N;
@@ -602,12 +619,18 @@ int rtds_jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int*
         RTDS_CUDA(cudaMalloc(&ctx->d_jitter, sizeof(uint32_t) * out_words));
         ctx->jitter_cap_words = out_words;
     }
-    mt_expand_kernel<<<blocks, MT_THREADS, 0, s>>>(ctx->d_mt_snap, (int)s0, ctx->d_jitter, out_words);
+    mt_expand_kernel<<<blocks, MT_THREADS, 0, s>>>(ctx->d_mt_snap, (int)s0, ctx->d_jitter, out_words, own);
     if (launches) *launches += 1;
     RTDS_CUDA(cudaGetLastError());
     ctx->jitter_first_word = s0 * words_per_snap;
     ctx->jitter_n_words = out_words;
     return RTDS_OK;
+}
+
+int rtds_jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int* launches)
+{
+    JitterOwner all{0, 1, 1, 0, 1, 1};
+    return jitter_prepare(ctx, first_word, n_words, launches, all);
 }
 
 int rtds_jitter_stream_impl(rtds_ctx* ctx, uint64_t first, int n, double* out)
@@ -665,7 +688,10 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     const size_t n_words = 4ull * (size_t)W * H * spp;
     if (!(p->no_jitter_regen && ctx->d_jitter && ctx->jitter_first_word <= first_word &&
           first_word + n_words <= ctx->jitter_first_word + ctx->jitter_n_words))
-        RTDS_TRY(rtds_jitter_prepare(ctx, first_word, n_words, &launches));
+    {
+        JitterOwner own{first_word, 4ull * (unsigned long long)W * spp, tile_rows, rank, world, H};
+        RTDS_TRY(jitter_prepare(ctx, first_word, n_words, &launches, own));
+    }
     A.jitter = ctx->d_jitter;
     A.jitter_rel = first_word - ctx->jitter_first_word;
     RTDS_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 8, s));

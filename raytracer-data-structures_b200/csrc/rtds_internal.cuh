@@ -49,6 +49,7 @@ struct __align__(16) Node64 {
 static_assert(sizeof(Node64) == 64, "Node64 must be 64 bytes");
 
 struct DeviceBvh {
+    int      capacity = 0;         // primitives the arrays below were allocated for
     int      n_prims = 0;          // leaves
     int      n_internal = 0;       // n_prims - 1 (0 when n_prims == 1)
     int      root_ref = 0;         // 0 (interior node 0) or ~0 when the tree is a single leaf
@@ -85,6 +86,7 @@ struct rtds_ctx {
 
     // scene (objId-indexed)
     int     n = 0;
+    int     sph_capacity = 0;
     float4* d_sph = nullptr;     // {cx,cy,cz,r}
     float4* d_mat = nullptr;     // {r,g,b,(float)material}
     int     n_lights = 0;
@@ -102,6 +104,7 @@ struct rtds_ctx {
     // sorted Morton keys of the last TRUE LBVH build (export / tests)
     uint64_t* d_keys_sorted = nullptr;
     int       n_keys = 0;
+    int       keys_capacity = 0;
 
     // jitter: MT19937 state snapshots (one per RTDS_MT_SNAP_EVERY regenerations) and the expanded words
     uint32_t* d_mt_snap = nullptr;   // [n_snap][624]

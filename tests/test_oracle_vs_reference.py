@@ -1,0 +1,46 @@
+"""CPU, build container only: the oracle port against the compiled UNMODIFIED reference on inputs the golden
+files do not cover (random synthetic scenes through ref_scene_from_spheres, arbitrary rays, 4 spp)."""
+import numpy as np
+import pytest
+
+import conftest as T
+
+rt = T.rtds_b200
+
+
+@pytest.mark.parametrize("n,seed,q", [(500, 1, 0.0), (3000, 2, 0.0), (2000, 3, 1.0), (64, 4, 0.5)])
+def test_port_tree_equals_reference_tree(ref, oracle, n, seed, q):
+    sph, mat = T.synthetic_scene(n, seed)
+    if q:
+        sph[:n, :3] = np.round(sph[:n, :3] / np.float32(q)) * np.float32(q)
+    ref.scene_from_spheres(sph, mat)
+    for acc, n_use in ((rt.BVH, sph.shape[0]), (rt.LBVH, sph.shape[0] - 1)):
+        total, _ = ref.build(acc)
+        nodes_r, objs_r, _ = ref.bvh_linear()
+        rc, nodes, order, _ = oracle.build_bvh(sph, n_use)
+        assert rc == 0 and total == nodes.shape[0]
+        assert np.array_equal(order, objs_r) and nodes.tobytes() == nodes_r.tobytes()
+
+
+def test_port_trace_and_render_equal_reference(ref, oracle):
+    sph, mat = T.synthetic_scene(4000, 7)
+    ref.scene_from_spheres(sph, mat)
+    ref.build(rt.BVH)
+    rc, nodes, order, _ = oracle.build_bvh(sph)
+    rng = np.random.default_rng(8)
+    d = rng.normal(size=(5000, 3)).astype(np.float32) * np.float32([0.15, 0.15, 0]) + np.float32([0, 0, -1])
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = np.zeros((1, 3), np.float32)
+    h_r, t_r, cand_r = ref.trace(rt.BVH, o, d)
+    h_o, t_o, cand_o = oracle.trace(sph, nodes, order, o, d)
+    assert np.array_equal(h_r, h_o) and t_r.tobytes() == t_o.tobytes() and cand_r == cand_o
+    h_rn, t_rn, _ = ref.trace(rt.NONE, o, d[:300])
+    h_on, t_on, _ = oracle.trace(sph, None, None, o, d[:300])
+    assert np.array_equal(h_rn, h_on) and t_rn.tobytes() == t_on.tobytes()
+    rgb_r, _, acc_r, _ = ref.render_rows(rt.BVH, 200, 150, 4, 40, 110, want_accum=True)
+    rgb_o, _, acc_o, _ = oracle.render_rows(sph, mat, nodes, order, 200, 150, 4, 40, 110, want_accum=True)
+    assert acc_r.tobytes() == acc_o.tobytes() and np.array_equal(rgb_r, rgb_o)
+
+
+def test_port_jitter_equals_libstdcxx(ref, oracle):
+    assert np.array_equal(ref.jitter(100000), oracle.jitter(100000))
