@@ -7,6 +7,7 @@
 // plus the pre-order flattening into the reference's LinearBVHNode layout (accelerators.h:231-240).
 #include "rtds_internal.cuh"
 #include <math.h>
+#include <string.h>
 
 namespace {
 
@@ -405,6 +406,25 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
 }
 
 }  // namespace
+
+// AABB of the scene: out12 = centre min/max (6), box min/max (6)
+int rtds_scene_bounds(rtds_ctx* ctx, float out12[12])
+{
+    RTDS_TRY(rtds_ensure_scratch(ctx, 4096));
+    unsigned* d_bounds = (unsigned*)((char*)ctx->d_scratch + ctx->scratch_bytes - 256);   // tail of the scratch area
+    bounds_init_kernel<<<1, 32, 0, ctx->stream>>>(d_bounds);
+    bounds_kernel<<<min((ctx->n + 255) / 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->d_sph, ctx->n, d_bounds);
+    RTDS_CUDA(cudaGetLastError());
+    unsigned h[12];
+    RTDS_CUDA(cudaMemcpyAsync(h, d_bounds, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    RTDS_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 12; ++i) {
+        unsigned u = h[i];
+        unsigned b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+        memcpy(&out12[i], &b, 4);
+    }
+    return RTDS_OK;
+}
 
 int rtds_bvh_compute_depth(rtds_ctx* ctx, DeviceBvh& b, int* depth_out)
 {

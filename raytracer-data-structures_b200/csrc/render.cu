@@ -354,6 +354,68 @@ __device__ __forceinline__ void brute_force_block(const float4* __restrict__ sph
 }
 
 // ===================================================================================================
+// kdtreeIntersect (accelerators.h:997-1086): any-hit, front-to-back, 64-entry todo stack
+// ===================================================================================================
+struct KdView {
+    const rtds_kd_node* nodes;
+    const int*          prim_idx;
+    const float4*       sph;       // objId-indexed {c, r} (kdtreeAllSceneObjects)
+    float               bounds[6];
+};
+
+__device__ __forceinline__ bool kd_any_hit(const KdView& K, float ox, float oy, float oz, float dx, float dy, float dz, Counters& cnt)
+{
+    float tMin, tMax;
+    cnt.node_tests++;
+    if (!slab_test(ox, oy, oz, dx, dy, dz, K.bounds[0], K.bounds[1], K.bounds[2], K.bounds[3], K.bounds[4], K.bounds[5], tMin, tMax))
+        return false;
+    const float o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
+    const float inv[3] = {1 / dx, 1 / dy, 1 / dz};
+    int   todo_node[64];
+    float todo_tmin[64], todo_tmax[64];
+    int todoPos = 0;
+    int node = 0;
+    while (true) {
+        const rtds_kd_node nd = K.nodes[node];
+        cnt.node_visits++;
+        if ((nd.w1 & 3u) == 3u) {
+            const int np = (int)nd.w2;
+            if (np == 1) {
+                float4 sp = __ldg(K.sph + (int)nd.w0);
+                float t0, t1;
+                cnt.prim_tests++;
+                if (sphere_test(ox, oy, oz, dx, dy, dz, make_float4(sp.x, sp.y, sp.z, sp.w * sp.w), t0, t1)) return true;
+            } else {
+                for (int i = 0; i < np; ++i) {
+                    int prim = __ldg(K.prim_idx + (int)nd.w0 + i);
+                    float4 sp = __ldg(K.sph + prim);
+                    float t0, t1;
+                    cnt.prim_tests++;
+                    if (sphere_test(ox, oy, oz, dx, dy, dz, make_float4(sp.x, sp.y, sp.z, sp.w * sp.w), t0, t1)) return true;
+                }
+            }
+            if (todoPos > 0) { --todoPos; node = todo_node[todoPos]; tMin = todo_tmin[todoPos]; tMax = todo_tmax[todoPos]; }
+            else break;
+        } else {
+            const int axis = (int)(nd.w1 & 3u);
+            const float split = __uint_as_float(nd.w0);
+            const float tPlane = (split - o[axis]) * inv[axis];
+            const bool belowFirst = (o[axis] < split) || (o[axis] == split && d[axis] <= 0);
+            const int below = node + 1, above = (int)(nd.w1 >> 2);
+            const int first = belowFirst ? below : above, second = belowFirst ? above : below;
+            if (tPlane > tMax || tPlane <= 0) node = first;
+            else if (tPlane < tMin) node = second;
+            else {
+                if (todoPos < 64) { todo_node[todoPos] = second; todo_tmin[todoPos] = tPlane; todo_tmax[todoPos] = tMax; ++todoPos; }
+                node = first;
+                tMax = tPlane;
+            }
+        }
+    }
+    return false;
+}
+
+// ===================================================================================================
 // shading: castRay's DIFFUSE_AND_GLOSSY branch (main.cpp:394-497)
 // ===================================================================================================
 struct ShadeParams {
@@ -427,6 +489,7 @@ struct RenderArgs {
     const uint32_t* jitter;      // word 0 = stream word jitter_base
     uint64_t        jitter_rel;  // (4*first_sample - jitter_base): word offset of sample 0 of pixel 0
     BvhView bvh;
+    KdView  kd;
     const float4* sph;           // objId-indexed {c, r}
     const float4* mat;           // objId-indexed {rgb, material}
     int           n;             // primitive count for NONE
@@ -437,7 +500,7 @@ struct RenderArgs {
     unsigned long long* counters;
 };
 
-template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE*/>
+template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE, 3 = KDTREE (any-hit, unshaded: main.cpp:362-372)*/>
 __global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
 {
     __shared__ float4 sh_sph[MODE == 2 ? NONE_CHUNK : 1];
@@ -474,6 +537,8 @@ __global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
         if (MODE == 2) {
             brute_force_block(A.sph, A.n, active, 0.f, 0.f, 0.f, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
             if (hit_obj >= 0) { float4 s = __ldg(A.sph + hit_obj); cx = s.x; cy = s.y; cz = s.z; }
+        } else if (MODE == 3) {
+            if (active) hit_obj = kd_any_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, cnt) ? 1 : -1;
         } else if (active) {
             traverse_bvh<MODE == 0>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
             if (best_leaf >= 0) {
@@ -485,6 +550,7 @@ __global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
         if (active) {
             float r, g, b;
             if (hit_obj < 0) { r = A.shade.bg[0]; g = A.shade.bg[1]; b = A.shade.bg[2]; }
+            else if (MODE == 3) { r = 0.f; g = 0.f; b = 0.f; }       // main.cpp:369: a KD hit is black
             else {
                 float4 m = __ldg(A.mat + hit_obj);
                 shade_diffuse(A.shade, 0.f, 0.f, 0.f, dx, dy, dz, tnear, cx, cy, cz, m.x, m.y, m.z, r, g, b);
@@ -518,13 +584,14 @@ __global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
 struct TraceArgs {
     const float* o; const float* d; int nrays;
     BvhView bvh;
+    KdView kd;
     const float4* sph; int n;
     int* hit; float* t;
     unsigned long long* counters;
     int exact;
 };
 
-template <int MODE /*0 BVH, 2 NONE*/>
+template <int MODE /*0 BVH, 2 NONE, 3 KDTREE*/>
 __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A)
 {
     __shared__ float4 sh_sph[MODE == 2 ? NONE_CHUNK : 1];
@@ -541,6 +608,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A)
     int best_key = 0, best_leaf = -1, hit_obj = -1;
     if (MODE == 2) {
         brute_force_block(A.sph, A.n, active, ox, oy, oz, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
+    } else if (MODE == 3) {
+        if (active) { hit_obj = kd_any_hit(A.kd, ox, oy, oz, dx, dy, dz, cnt) ? 1 : -1; tnear = 0.f; }
     } else if (active) {
         // the ordered traversal's pruning bound assumes a unit direction (as every ray castRay makes has)
         float len2 = dx * dx + dy * dy + dz * dz;
@@ -565,6 +634,14 @@ BvhView make_view(const DeviceBvh& b)
     v.nodes = b.nodes; v.leaf_sph = b.leaf_sph; v.prim_order = b.prim_order;
     v.root_ref = b.root_ref; v.tie_by_objid = b.tie_by_objid;
     for (int i = 0; i < 6; ++i) v.root_box[i] = b.root_box[i];
+    return v;
+}
+
+KdView make_kd_view(const rtds_ctx* ctx)
+{
+    KdView v;
+    v.nodes = ctx->kd.nodes; v.prim_idx = ctx->kd.prim_idx; v.sph = ctx->d_sph;
+    for (int i = 0; i < 6; ++i) v.bounds[i] = ctx->kd.bounds[i];
     return v;
 }
 
@@ -655,9 +732,10 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     if (rank < 0 || rank >= world) { rtds_set_error("render: rank %d outside world %d", rank, world); return RTDS_ERR_INVALID; }
     const int tile_rows = p->tile_rows > 0 ? p->tile_rows : 8;
     if (ctx->n <= 0) { rtds_set_error("render: no scene"); return RTDS_ERR_NO_SCENE; }
-    if (acc == RTDS_KDTREE) { rtds_set_error("render: KDTREE not implemented yet"); return RTDS_ERR_UNSUPPORTED; }
-    const bool brute = (acc != RTDS_BVH && acc != RTDS_LBVH);
-    if (!brute) RTDS_TRY(check_bvh(ctx, acc));
+    const bool kdt = acc == RTDS_KDTREE;
+    if (kdt && !ctx->kd.valid) { rtds_set_error("render: KDTREE requested but no KD-tree has been built"); return RTDS_ERR_NOT_BUILT; }
+    const bool brute = (acc != RTDS_BVH && acc != RTDS_LBVH && !kdt);
+    if (!brute && !kdt) RTDS_TRY(check_bvh(ctx, acc));
 
     RenderArgs A;
     A.width = W; A.height = H; A.spp = spp;
@@ -669,7 +747,8 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.aspect = W / float(H);
     A.angle = (float)tan(3.141592653589793 * 0.5 * fov / 180.);
     A.n = ctx->n; A.sph = ctx->d_sph; A.mat = ctx->d_mat;
-    if (!brute) A.bvh = make_view(ctx->bvh); else A.bvh = BvhView();
+    if (!brute && !kdt) A.bvh = make_view(ctx->bvh); else A.bvh = BvhView();
+    if (kdt) A.kd = make_kd_view(ctx); else A.kd = KdView();
     A.shade.n_lights = ctx->n_lights;
     for (int i = 0; i < ctx->n_lights; ++i) A.shade.lights[i] = ctx->lights[i];
     const bool bg0 = p->bg[0] == 0 && p->bg[1] == 0 && p->bg[2] == 0;
@@ -698,7 +777,8 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     if (A.local_rows > 0) {
         dim3 grid((W + 15) / 16, (A.local_rows + 7) / 8), block(128);
         RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
-        if (brute) render_kernel<2><<<grid, block, 0, s>>>(A);
+        if (kdt) render_kernel<3><<<grid, block, 0, s>>>(A);
+        else if (brute) render_kernel<2><<<grid, block, 0, s>>>(A);
         else if (p->exact) render_kernel<0><<<grid, block, 0, s>>>(A);
         else render_kernel<1><<<grid, block, 0, s>>>(A);
         RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
@@ -729,9 +809,10 @@ int rtds_trace_impl(rtds_ctx* ctx, int acc, int exact, const float* h_o, const f
 {
     if (nrays <= 0) return RTDS_OK;
     if (ctx->n <= 0) { rtds_set_error("trace: no scene"); return RTDS_ERR_NO_SCENE; }
-    if (acc == RTDS_KDTREE) { rtds_set_error("trace: KDTREE not implemented yet"); return RTDS_ERR_UNSUPPORTED; }
-    const bool brute = (acc != RTDS_BVH && acc != RTDS_LBVH);
-    if (!brute) RTDS_TRY(check_bvh(ctx, acc));
+    const bool kdt = acc == RTDS_KDTREE;
+    if (kdt && !ctx->kd.valid) { rtds_set_error("trace: KDTREE requested but no KD-tree has been built"); return RTDS_ERR_NOT_BUILT; }
+    const bool brute = (acc != RTDS_BVH && acc != RTDS_LBVH && !kdt);
+    if (!brute && !kdt) RTDS_TRY(check_bvh(ctx, acc));
     size_t vec = (sizeof(float) * 3 * (size_t)nrays + 255) & ~(size_t)255;
     size_t one = (sizeof(float) * (size_t)nrays + 255) & ~(size_t)255;
     RTDS_TRY(rtds_ensure_scratch(ctx, 2 * vec + 2 * one));
@@ -744,10 +825,12 @@ int rtds_trace_impl(rtds_ctx* ctx, int acc, int exact, const float* h_o, const f
     RTDS_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 8, s));
     TraceArgs A;
     A.o = d_o; A.d = d_d; A.nrays = nrays;
-    if (!brute) A.bvh = make_view(ctx->bvh); else A.bvh = BvhView();
+    if (!brute && !kdt) A.bvh = make_view(ctx->bvh); else A.bvh = BvhView();
+    if (kdt) A.kd = make_kd_view(ctx); else A.kd = KdView();
     A.sph = ctx->d_sph; A.n = ctx->n; A.hit = d_hit; A.t = d_t; A.counters = ctx->d_counters; A.exact = exact;
     RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
-    if (brute) trace_kernel<2><<<(nrays + 127) / 128, 128, 0, s>>>(A);
+    if (kdt) trace_kernel<3><<<(nrays + 127) / 128, 128, 0, s>>>(A);
+    else if (brute) trace_kernel<2><<<(nrays + 127) / 128, 128, 0, s>>>(A);
     else trace_kernel<0><<<(nrays + 127) / 128, 128, 0, s>>>(A);
     RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
     RTDS_CUDA(cudaGetLastError());

@@ -36,8 +36,29 @@ def quantised_scene(n, seed, q):
     return sph, mat
 
 
+def golden_kd(ref):
+    """KDTREE on the default config: the any-hit mask (pixel is black <=> kdtreeIntersect returned true)."""
+    sph, mat = T.bunny_scene()
+    ref.scene_from_spheres(sph, mat)
+    total, _ = ref.build(rt.KDTREE)
+    rgb, dirs, _, _ = ref.render_rows(rt.KDTREE, 640, 480, 1, want_dirs=True)
+    mask = (rgb.astype(np.int32).sum(-1) == 0)
+    h, _, _ = ref.trace(rt.KDTREE, np.zeros((1, 3), np.float32), dirs.reshape(-1, 3))
+    assert np.array_equal(h.reshape(480, 640) > 0, mask)
+    np.save(os.path.join(HERE, "bunny_kd_mask_640x480.npy"), np.packbits(mask))
+    return {"total_nodes": int(total), "hits": int(mask.sum()), "ppm_md5": T.ppm_md5(rgb)}
+
+
 def main():
     ref = T.Ref()
+    if len(sys.argv) > 1 and sys.argv[1] == "kd":
+        with open(os.path.join(HERE, "golden.json")) as f:
+            G = json.load(f)
+        G["kd"] = golden_kd(ref)
+        print(G["kd"])
+        with open(os.path.join(HERE, "golden.json"), "w") as f:
+            json.dump(G, f, indent=1, sort_keys=True)
+        return
     G = {}
     v = rt.parse_obj_vertices(os.path.join(T.REF_TREE, "models", "bunny.obj"))
     sph_ref, mat_ref = ref.scene_from_obj(rt.BUNNY, 1)
@@ -114,6 +135,7 @@ def main():
         G["trees"][name] = e
         print(name, e, flush=True)
 
+    G["kd"] = golden_kd(ref)
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(G, f, indent=1, sort_keys=True)
 
