@@ -300,27 +300,120 @@ inline float pow25(float xf)
 }
 struct Light { float c[3]; float radius; float le[3]; };
 
-void shade(const float o[3], const float d[3], float tnear, const float* sph, const float* mat, const Light* L, int nl, float rgb[3])
+// ----------------------------------------------------------------------------------------------
+// castRay in full (main.cpp:291-500): material branches, recursion to depth 2, and the shadow query.
+// The reference's trace_more (main.cpp:235-245) is a stub that returns false; with `shadows` the contract its
+// call site states (main.cpp:468-473) is evaluated instead: nearest hit of the shadow ray, in shadow iff
+// tNearShadow^2 < lightDistance2.  Shadows have no executable reference behaviour: PARITY UNPINNED for that flag.
+// ----------------------------------------------------------------------------------------------
+inline float clampf(float lo, float hi, float v) { return std::max(lo, std::min(hi, v)); }   // main.cpp:75-79
+
+void fresnel(const float I[3], const float N[3], float ior, float& kr)   // main.cpp:85-103
 {
-    float hp[3] = {o[0] + d[0] * tnear, o[1] + d[1] * tnear, o[2] + d[2] * tnear};   // :396
-    float N[3] = {hp[0] - sph[0], hp[1] - sph[1], hp[2] - sph[2]};                     // :398-399
+    float cosi = clampf(-1, 1, I[0] * N[0] + I[1] * N[1] + I[2] * N[2]);
+    float etai = 1, etat = ior;
+    if (cosi > 0) std::swap(etai, etat);
+    float sint = etai / etat * sqrtf(std::max(0.f, 1 - cosi * cosi));
+    if (sint >= 1) kr = 1;
+    else {
+        float cost = sqrtf(std::max(0.f, 1 - sint * sint));
+        cosi = fabsf(cosi);
+        float Rs = ((etat * cosi) - (etai * cost)) / ((etat * cosi) + (etai * cost));
+        float Rp = ((etai * cosi) - (etat * cost)) / ((etai * cosi) + (etat * cost));
+        kr = (Rs * Rs + Rp * Rp) / 2;
+    }
+}
+
+void refract(const float I[3], const float N[3], float ior, float out[3])   // main.cpp:223-233
+{
+    float cosi = clampf(-1, 1, I[0] * N[0] + I[1] * N[1] + I[2] * N[2]);
+    float etai = 1, etat = ior;
+    float n[3] = {N[0], N[1], N[2]};
+    if (cosi < 0) cosi = -cosi;
+    else { std::swap(etai, etat); n[0] = -N[0]; n[1] = -N[1]; n[2] = -N[2]; }
+    float eta = etai / etat;
+    float k = 1 - eta * eta * (1 - cosi * cosi);
+    if (k < 0) { out[0] = out[1] = out[2] = 0; return; }
+    float f = eta * cosi - sqrtf(k);
+    for (int c = 0; c < 3; ++c) out[c] = I[c] * eta + n[c] * f;
+}
+
+struct CastCtx {
+    const Scene* S; const Light* L; int nl; int shadows;
+    long long rays = 0, shadow_rays = 0, secondary_rays = 0;
+};
+
+void closest(const Scene& S, const float o[3], const float d[3], int& hit, float& tnear)
+{
+    if (S.nodes) closest_bvh(S, o, d, hit, tnear, nullptr); else closest_none(S, o, d, hit, tnear);
+}
+
+void cast_ray(CastCtx& C, const float o[3], const float d[3], int depth, float rgb[3], int* hit_out)
+{
+    const Scene& S = *C.S;
+    if (depth > 2) { rgb[0] = 0.6f; rgb[1] = 0.8f; rgb[2] = 1.0f; return; }                  // :311-313
+    int hit; float tnear;
+    closest(S, o, d, hit, tnear);
+    C.rays++;
+    if (hit_out) *hit_out = hit;
+    if (hit < 0) { rgb[0] = 0.6f; rgb[1] = 0.8f; rgb[2] = 1.0f; return; }                     // :318,394
+    const float* sph = S.sph + 4 * hit;
+    const float* mat = S.mat + 4 * hit;
+    float hp[3] = {o[0] + d[0] * tnear, o[1] + d[1] * tnear, o[2] + d[2] * tnear};
+    float N[3] = {hp[0] - sph[0], hp[1] - sph[1], hp[2] - sph[2]};
     normalize(N);
-    if (d[0] * N[0] + d[1] * N[1] + d[2] * N[2] > 0) { N[0] = -N[0]; N[1] = -N[1]; N[2] = -N[2]; }  // :406
-    float hc[3] = {0, 0, 0};                                                            // :449
-    const float diff[3] = {0.815f, 0.235f, 0.031f};  // getDiffuseColor((0.2,0.2)) -> first colour, accelerators.h:94-99
-    for (int i = 0; i < nl; ++i) {
-        float ld[3] = {L[i].c[0] - hp[0], L[i].c[1] - hp[1], L[i].c[2] - hp[2]};        // :463
-        normalize(ld);                                                                   // :466
-        float LdotN = std::max(0.f, ld[0] * N[0] + ld[1] * N[1] + ld[2] * N[2]);         // :467
+    if (d[0] * N[0] + d[1] * N[1] + d[2] * N[2] > 0) { N[0] = -N[0]; N[1] = -N[1]; N[2] = -N[2]; }
+    const float bias = 1e-4;                                                                  // :404
+    const int material = (int)mat[3];
+    if (material == 1) {                                                                      // REFLECTION_AND_REFRACTION :418-434
+        float rd[3];
+        refract(d, N, 3, rd);
+        normalize(rd);
+        float ro[3];
+        bool neg = rd[0] * N[0] + rd[1] * N[1] + rd[2] * N[2] < 0;
+        for (int c = 0; c < 3; ++c) ro[c] = neg ? hp[c] - N[c] * bias : hp[c] + N[c] * bias;
+        // the reflection ray of :428 is traced by the reference but its colour is never used; it has no effect
+        float refr[3];
+        if (depth + 1 <= 2) C.secondary_rays++;   // a deeper ray returns the sky untraced (:311)
+        cast_ray(C, ro, rd, depth + 1, refr, nullptr);
+        float kr;
+        fresnel(d, N, 2, kr);
+        for (int c = 0; c < 3; ++c) rgb[c] = refr[c] * (1 - kr);                              // :432
+        return;
+    }
+    if (material == 2) {                                                                      // REFLECTION :435-446
+        float kr;
+        fresnel(d, N, 2, kr);
+        rgb[0] = rgb[1] = rgb[2] = (1 - kr);                                                  // :445
+        return;
+    }
+    float hc[3] = {0, 0, 0};
+    const float diff[3] = {0.815f, 0.235f, 0.031f};
+    for (int i = 0; i < C.nl; ++i) {
+        const Light& Lt = C.L[i];
+        float ld[3] = {Lt.c[0] - hp[0], Lt.c[1] - hp[1], Lt.c[2] - hp[2]};
+        float dist2 = ld[0] * ld[0] + ld[1] * ld[1] + ld[2] * ld[2];                          // :465
+        normalize(ld);
+        float LdotN = std::max(0.f, ld[0] * N[0] + ld[1] * N[1] + ld[2] * N[2]);
+        int inShadow = 0;
+        if (C.shadows) {
+            bool front = d[0] * N[0] + d[1] * N[1] + d[2] * N[2] < 0;                         // :455-457
+            float so[3];
+            for (int c = 0; c < 3; ++c) so[c] = front ? hp[c] + N[c] * bias : hp[c] - N[c] * bias;
+            int sh; float ts;
+            closest(S, so, ld, sh, ts);
+            C.shadow_rays++; C.rays++;
+            inShadow = (sh >= 0 && ts * ts < dist2) ? 1 : 0;                                  // :471-472
+        }
         float I[3] = {-ld[0], -ld[1], -ld[2]};
-        float s2 = 2 * (I[0] * N[0] + I[1] * N[1] + I[2] * N[2]);                        // reflect(), :218-221
+        float s2 = 2 * (I[0] * N[0] + I[1] * N[1] + I[2] * N[2]);
         float R[3] = {I[0] - N[0] * s2, I[1] - N[1] * s2, I[2] - N[2] * s2};
-        float sp = pow25(std::max(0.f, -(R[0] * d[0] + R[1] * d[1] + R[2] * d[2])));     // :475
+        float sp = pow25(std::max(0.f, -(R[0] * d[0] + R[1] * d[1] + R[2] * d[2])));
         for (int c = 0; c < 3; ++c) {
-            float amt = (L[i].le[c] * 1.0f) * LdotN;                                     // :473 (inShadow = 0)
-            float spec = L[i].le[c] * sp;
-            hc[c] += (amt * (diff[c] * 0.8f)) / 2.0f + spec * 0.5f;                      // :489
-            hc[c] += mat[c];                                                             // :490
+            float amt = (Lt.le[c] * (float)(1 - inShadow)) * LdotN;                            // :473
+            float spec = Lt.le[c] * sp;
+            hc[c] += (amt * (diff[c] * 0.8f)) / 2.0f + spec * 0.5f;
+            hc[c] += mat[c];
         }
     }
     rgb[0] = hc[0]; rgb[1] = hc[1]; rgb[2] = hc[2];
@@ -465,9 +558,9 @@ void orc_jitter(double* out, int n, unsigned long long first)
 
 // render() rows [y0,y1) (main.cpp:541-566) + write_into_file's quantisation (main.cpp:521-523).
 // lights: m x {cx,cy,cz,radius,r,g,b}. nodes == NULL -> NONE. Optional outputs may be NULL.
-void orc_render_rows(const float* cxyz_r, const float* rgb_mat, int n, const LinearNode* nodes, const int* prim_order, int n_nodes,
-                     int tie_by_objid, const float* lights7, int m, int width, int height, int spp, int y0, int y1,
-                     uint8_t* rgb8, int* hit_out, float* accum, float* dirs)
+void orc_render_rows_ex(const float* cxyz_r, const float* rgb_mat, int n, const LinearNode* nodes, const int* prim_order, int n_nodes,
+                        int tie_by_objid, const float* lights7, int m, int width, int height, int spp, int y0, int y1,
+                        int shadows, uint8_t* rgb8, int* hit_out, float* accum, float* dirs, long long* ray_counts3)
 {
     Scene S{cxyz_r, rgb_mat, n, nodes, prim_order, n_nodes, tie_by_objid};
     std::vector<Light> L(m);
@@ -475,6 +568,8 @@ void orc_render_rows(const float* cxyz_r, const float* rgb_mat, int n, const Lin
         const float* l = lights7 + 7 * i;
         L[i] = Light{{l[0], l[1], l[2]}, l[3], {l[4], l[5], l[6]}};
     }
+    CastCtx CC;
+    CC.S = &S; CC.L = L.data(); CC.nl = m; CC.shadows = shadows;
     MT gen;
     gen.discard(4ull * (unsigned long long)y0 * width * spp);
     float invWidth = 1 / float(width), invHeight = 1 / float(height);         // :544
@@ -492,10 +587,9 @@ void orc_render_rows(const float* cxyz_r, const float* rgb_mat, int n, const Lin
                 float d[3] = {xx, yy, -1};
                 normalize(d);
                 if (dirs) { dirs[kd++] = d[0]; dirs[kd++] = d[1]; dirs[kd++] = d[2]; }
-                int hit; float tnear;
-                if (nodes) closest_bvh(S, o, d, hit, tnear, nullptr); else closest_none(S, o, d, hit, tnear);
-                float c[3] = {0.6f, 0.8f, 1.0f};                                                          // :318
-                if (hit >= 0) shade(o, d, tnear, cxyz_r + 4 * hit, rgb_mat + 4 * hit, L.data(), m, c);
+                int hit = -1;
+                float c[3];
+                cast_ray(CC, o, d, 1, c, &hit);                                                           // :558
                 px[0] += c[0]; px[1] += c[1]; px[2] += c[2];
                 last = hit;
             }
@@ -509,6 +603,15 @@ void orc_render_rows(const float* cxyz_r, const float* rgb_mat, int n, const Lin
             }
         }
     }
+    if (ray_counts3) { ray_counts3[0] = CC.rays; ray_counts3[1] = CC.shadow_rays; ray_counts3[2] = CC.secondary_rays; }
+}
+
+void orc_render_rows(const float* cxyz_r, const float* rgb_mat, int n, const LinearNode* nodes, const int* prim_order, int n_nodes,
+                     int tie_by_objid, const float* lights7, int m, int width, int height, int spp, int y0, int y1,
+                     uint8_t* rgb8, int* hit_out, float* accum, float* dirs)
+{
+    orc_render_rows_ex(cxyz_r, rgb_mat, n, nodes, prim_order, n_nodes, tie_by_objid, lights7, m, width, height, spp, y0, y1, 0,
+                       rgb8, hit_out, accum, dirs, nullptr);
 }
 
 }  // extern "C"

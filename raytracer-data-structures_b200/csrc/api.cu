@@ -71,6 +71,14 @@ void rtds_free_kd(DeviceKd& k)
 
 int rtds_jitter_stream_impl(rtds_ctx* ctx, uint64_t first, int n, double* out);
 
+// does any primitive carry a material other than DIFFUSE_AND_GLOSSY? (selects the full castRay kernel)
+__global__ void material_flag_kernel(const float4* __restrict__ mat, int n, int* flag)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool f = i < n && mat[i].w != 0.0f;
+    if (__any_sync(0xffffffffu, f) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 extern "C" {
 
 const char* rtds_last_error(void) { return g_err; }
@@ -141,8 +149,16 @@ int rtds_set_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int
         c->sph_capacity = n;
     }
     RTDS_CUDA(cudaMemcpyAsync(c->d_sph, cxyz_r, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    c->has_materials = false;
     if (rgb_mat) {
         RTDS_CUDA(cudaMemcpyAsync(c->d_mat, rgb_mat, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        int* d_flag = (int*)(c->d_counters + 6);
+        RTDS_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
+        material_flag_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_mat, n, d_flag);
+        int flag = 0;
+        RTDS_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        RTDS_CUDA(cudaStreamSynchronize(c->stream));
+        c->has_materials = flag != 0;
     } else {
         std::vector<float> m((size_t)n * 4);
         for (int i = 0; i < n; ++i) { m[4 * i] = 0.8f; m[4 * i + 1] = 0.7f; m[4 * i + 2] = 0.0f; m[4 * i + 3] = 0.f; }  // main.cpp:689

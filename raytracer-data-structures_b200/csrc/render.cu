@@ -579,6 +579,185 @@ __global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
 }
 
 // ===================================================================================================
+// K10b: castRay in full (main.cpp:291-500) — material branches, recursion to depth 2 unrolled into a loop, and the
+// shadow query whose contract main.cpp:468-473 states (trace_more itself is a stub: shadows are an extension).
+// Used when the scene holds non-diffuse materials or shadows are requested; the all-diffuse, shadow-free path
+// (everything the reference's own loader can produce) stays on render_kernel above.
+// ===================================================================================================
+__device__ __forceinline__ float clampf3(float lo, float hi, float v) { return fmaxf(lo, fminf(hi, v)); }   // main.cpp:75-79
+
+__device__ __forceinline__ float fresnel_kr(float ix, float iy, float iz, float nx, float ny, float nz, float ior)   // main.cpp:85-103
+{
+    float cosi = clampf3(-1.f, 1.f, ix * nx + iy * ny + iz * nz);
+    float etai = 1, etat = ior;
+    if (cosi > 0) { float t = etai; etai = etat; etat = t; }
+    float sint = etai / etat * sqrtf(fmaxf(0.f, 1 - cosi * cosi));
+    if (sint >= 1) return 1.f;
+    float cost = sqrtf(fmaxf(0.f, 1 - sint * sint));
+    cosi = fabsf(cosi);
+    float Rs = ((etat * cosi) - (etai * cost)) / ((etat * cosi) + (etai * cost));
+    float Rp = ((etai * cosi) - (etat * cost)) / ((etai * cosi) + (etat * cost));
+    return (Rs * Rs + Rp * Rp) / 2;
+}
+
+__device__ __forceinline__ void refract_dir(float ix, float iy, float iz, float nx, float ny, float nz, float ior, float& rx, float& ry,
+                                            float& rz)   // main.cpp:223-233
+{
+    float cosi = clampf3(-1.f, 1.f, ix * nx + iy * ny + iz * nz);
+    float etai = 1, etat = ior;
+    if (cosi < 0) cosi = -cosi;
+    else { float t = etai; etai = etat; etat = t; nx = -nx; ny = -ny; nz = -nz; }
+    float eta = etai / etat;
+    float k = 1 - eta * eta * (1 - cosi * cosi);
+    if (k < 0) { rx = ry = rz = 0.f; return; }
+    float f = eta * cosi - sqrtf(k);
+    rx = ix * eta + nx * f; ry = iy * eta + ny * f; rz = iz * eta + nz * f;
+}
+
+template <int MODE>
+__device__ __forceinline__ void closest_hit(const RenderArgs& A, float ox, float oy, float oz, float dx, float dy, float dz, float& tnear,
+                                            int& hit_obj, float& cx, float& cy, float& cz, Counters& cnt)
+{
+    tnear = INFINITY; hit_obj = -1;
+    if (MODE == 2) {   // main.cpp:376-386, straight from global memory (all lanes read the same address)
+        for (int i = 0; i < A.n; ++i) {
+            float4 s = __ldg(A.sph + i);
+            float t0, t1;
+            if (sphere_test(ox, oy, oz, dx, dy, dz, make_float4(s.x, s.y, s.z, s.w * s.w), t0, t1)) {
+                if (t0 < 0) t0 = t1;
+                if (t0 < tnear) { tnear = t0; hit_obj = i; cx = s.x; cy = s.y; cz = s.z; }
+            }
+        }
+        cnt.prim_tests += A.n;
+    } else {
+        int best_key = 0, best_leaf = -1;
+        float len2 = dx * dx + dy * dy + dz * dz;
+        if (MODE == 0 || !(fabsf(len2 - 1.0f) < 1e-3f)) traverse_bvh<true>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+        else traverse_bvh<false>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+        if (best_leaf >= 0) {
+            hit_obj = __ldg(A.bvh.prim_order + best_leaf);
+            float4 s = __ldg(A.bvh.leaf_sph + best_leaf);
+            cx = s.x; cy = s.y; cz = s.z;
+        }
+    }
+}
+
+template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE*/>
+__global__ void __launch_bounds__(128) render_full_kernel(const RenderArgs A)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int lrow = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const bool active = px < A.width && lrow < A.local_rows;
+    Counters cnt = {0, 0, 0, 0};
+    unsigned shadow_rays = 0, secondary_rays = 0;
+    if (active) {
+        const int tile = lrow / A.tile_rows, within = lrow - tile * A.tile_rows;
+        const int py = (tile * A.world + A.rank) * A.tile_rows + within;
+        float acc_r = 0, acc_g = 0, acc_b = 0;
+        int last_hit = -1;
+        const size_t pix = (size_t)py * A.width + px;
+        const float bias = A.shade.bias;
+        for (int k = 0; k < A.spp; ++k) {
+            size_t w = A.jitter_rel + 4 * (pix * A.spp + k);
+            uint4 jw = __ldg(reinterpret_cast<const uint4*>(A.jitter + w));
+            double r1 = canonical53(jw.x, jw.y), r2 = canonical53(jw.z, jw.w);
+            float dx = (float)((2 * (((double)(unsigned)px + r1) * (double)A.inv_w) - 1) * (double)A.angle * (double)A.aspect);
+            float dy = (float)((1 - 2 * (((double)(unsigned)py + r2) * (double)A.inv_h)) * (double)A.angle);
+            float dz = -1;
+            normalize3(dx, dy, dz);
+            float ox = 0, oy = 0, oz = 0;
+            float r = A.shade.bg[0], g = A.shade.bg[1], b = A.shade.bg[2];
+            float mult[2] = {1.f, 1.f};   // (1 - kr) of the REFLECTION_AND_REFRACTION hits on the way, outermost first
+            int nmult = 0;
+            for (int depth = 1;; ++depth) {
+                if (depth > A.shade.max_depth) break;                        // main.cpp:311-313: sky
+                float tnear, cx = 0, cy = 0, cz = 0;
+                int hit_obj;
+                closest_hit<MODE>(A, ox, oy, oz, dx, dy, dz, tnear, hit_obj, cx, cy, cz, cnt);
+                cnt.rays++;
+                if (depth == 1) last_hit = hit_obj;
+                if (hit_obj < 0) break;                                      // sky
+                const float4 m = __ldg(A.mat + hit_obj);
+                const int material = (int)m.w;
+                float hx = ox + dx * tnear, hy = oy + dy * tnear, hz = oz + dz * tnear;
+                float nx = hx - cx, ny = hy - cy, nz = hz - cz;
+                normalize3(nx, ny, nz);
+                if (dx * nx + dy * ny + dz * nz > 0) { nx = -nx; ny = -ny; nz = -nz; }
+                if (material == RTDS_REFLECTION_AND_REFRACTION) {            // main.cpp:418-434
+                    float rx, ry, rz;
+                    refract_dir(dx, dy, dz, nx, ny, nz, 3.f, rx, ry, rz);
+                    normalize3(rx, ry, rz);
+                    const bool neg = rx * nx + ry * ny + rz * nz < 0;
+                    const float kr = fresnel_kr(dx, dy, dz, nx, ny, nz, 2.f);
+                    if (nmult < 2) mult[nmult++] = 1 - kr;
+                    ox = neg ? hx - nx * bias : hx + nx * bias;
+                    oy = neg ? hy - ny * bias : hy + ny * bias;
+                    oz = neg ? hz - nz * bias : hz + nz * bias;
+                    dx = rx; dy = ry; dz = rz;
+                    if (depth + 1 <= A.shade.max_depth) secondary_rays++;   // a deeper ray returns the sky untraced
+                    // (the reflection ray of main.cpp:428 is traced by the reference but its colour is discarded)
+                    continue;
+                }
+                if (material == RTDS_REFLECTION) {                           // main.cpp:435-446
+                    const float kr = fresnel_kr(dx, dy, dz, nx, ny, nz, 2.f);
+                    r = g = b = 1 - kr;
+                    break;
+                }
+                float hr = 0, hg = 0, hb = 0;                                // main.cpp:447-494
+                for (int i = 0; i < A.shade.n_lights; ++i) {
+                    const RtdsLight& L = A.shade.lights[i];
+                    float lx = L.c[0] - hx, ly = L.c[1] - hy, lz = L.c[2] - hz;
+                    const float dist2 = lx * lx + ly * ly + lz * lz;
+                    normalize3(lx, ly, lz);
+                    const float LdotN = fmaxf(0.f, lx * nx + ly * ny + lz * nz);
+                    float lit = 1.0f;
+                    if (A.shade.shadows) {
+                        const bool front = dx * nx + dy * ny + dz * nz < 0;
+                        float sx = front ? hx + nx * bias : hx - nx * bias;
+                        float sy = front ? hy + ny * bias : hy - ny * bias;
+                        float sz = front ? hz + nz * bias : hz - nz * bias;
+                        float ts, ux, uy, uz;
+                        int sh;
+                        closest_hit<MODE>(A, sx, sy, sz, lx, ly, lz, ts, sh, ux, uy, uz, cnt);
+                        cnt.rays++;
+                        shadow_rays++;
+                        if (sh >= 0 && ts * ts < dist2) lit = 0.0f;           // main.cpp:471-472
+                    }
+                    const float ar = (L.le[0] * lit) * LdotN, ag = (L.le[1] * lit) * LdotN, ab = (L.le[2] * lit) * LdotN;
+                    const float ix = -lx, iy = -ly, iz = -lz;
+                    const float s2 = 2 * (ix * nx + iy * ny + iz * nz);
+                    const float qx = ix - nx * s2, qy = iy - ny * s2, qz = iz - nz * s2;
+                    const float sp = pow25f(fmaxf(0.f, -(qx * dx + qy * dy + qz * dz)));
+                    hr += (ar * (0.815f * 0.8f)) / 2.0f + (L.le[0] * sp) * 0.5f;
+                    hg += (ag * (0.235f * 0.8f)) / 2.0f + (L.le[1] * sp) * 0.5f;
+                    hb += (ab * (0.031f * 0.8f)) / 2.0f + (L.le[2] * sp) * 0.5f;
+                    hr += m.x; hg += m.y; hb += m.z;
+                }
+                r = hr; g = hg; b = hb;
+                break;
+            }
+            for (int i = nmult - 1; i >= 0; --i) { r = r * mult[i]; g = g * mult[i]; b = b * mult[i]; }   // main.cpp:432, innermost first
+            acc_r += r; acc_g += g; acc_b += b;
+        }
+        size_t o = (size_t)lrow * A.width + px;
+        float fs = (float)(unsigned)A.spp;
+        A.out_rgb[3 * o]     = (unsigned char)(fminf(1.0f, acc_r / fs) * 255);
+        A.out_rgb[3 * o + 1] = (unsigned char)(fminf(1.0f, acc_g / fs) * 255);
+        A.out_rgb[3 * o + 2] = (unsigned char)(fminf(1.0f, acc_b / fs) * 255);
+        if (A.out_hit) A.out_hit[o] = last_hit;
+        if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
+    }
+    unsigned v[6] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays, shadow_rays, secondary_rays};
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        unsigned long long x = v[c];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(&A.counters[c], x);
+    }
+}
+
+// ===================================================================================================
 // parity probe: arbitrary rays
 // ===================================================================================================
 struct TraceArgs {
@@ -756,7 +935,8 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.shade.bias = p->bias > 0 ? p->bias : 1e-4f;
     A.shade.max_depth = p->max_depth > 0 ? p->max_depth : 2;
     A.shade.shadows = p->shadows;
-    if (p->shadows) { rtds_set_error("render: shadows not implemented yet"); return RTDS_ERR_UNSUPPORTED; }
+    const bool full = p->shadows || ctx->has_materials;
+    if (full && kdt) { rtds_set_error("render: the KDTREE path is any-hit and unshaded (main.cpp:362-372); shadows/materials need BVH, LBVH or NONE"); return RTDS_ERR_UNSUPPORTED; }
     A.out_rgb = d_rgb_rows; A.out_hit = d_hit; A.out_accum = d_accum;
     A.counters = ctx->d_counters;
 
@@ -777,7 +957,12 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     if (A.local_rows > 0) {
         dim3 grid((W + 15) / 16, (A.local_rows + 7) / 8), block(128);
         RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
-        if (kdt) render_kernel<3><<<grid, block, 0, s>>>(A);
+        if (full) {
+            if (brute) render_full_kernel<2><<<grid, block, 0, s>>>(A);
+            else if (p->exact) render_full_kernel<0><<<grid, block, 0, s>>>(A);
+            else render_full_kernel<1><<<grid, block, 0, s>>>(A);
+        }
+        else if (kdt) render_kernel<3><<<grid, block, 0, s>>>(A);
         else if (brute) render_kernel<2><<<grid, block, 0, s>>>(A);
         else if (p->exact) render_kernel<0><<<grid, block, 0, s>>>(A);
         else render_kernel<1><<<grid, block, 0, s>>>(A);
@@ -795,7 +980,8 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
         RTDS_CUDA(cudaStreamSynchronize(s));
         memset(st, 0, sizeof *st);
         st->node_tests = c[0]; st->prim_tests = c[1]; st->node_visits = c[2];
-        st->primary_rays = c[3]; st->rays = c[3];
+        st->rays = c[3]; st->shadow_rays = c[4]; st->secondary_rays = c[5];
+        st->primary_rays = c[3] - c[4] - c[5];
         RTDS_CUDA(cudaEventElapsedTime(&st->ms_kernel, ctx->ev2, ctx->ev3));
         RTDS_CUDA(cudaEventElapsedTime(&st->ms_total, ctx->ev0, ctx->ev1));
         st->kernel_launches = launches;

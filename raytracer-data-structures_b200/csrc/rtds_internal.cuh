@@ -89,6 +89,7 @@ struct rtds_ctx {
     int     sph_capacity = 0;
     float4* d_sph = nullptr;     // {cx,cy,cz,r}
     float4* d_mat = nullptr;     // {r,g,b,(float)material}
+    bool    has_materials = false;   // any primitive with a non-DIFFUSE_AND_GLOSSY material
     int     n_lights = 0;
     RtdsLight lights[RTDS_MAX_LIGHTS];
 

@@ -127,7 +127,7 @@ class Oracle:
         return out
 
     def render_rows(self, sph, mat, nodes, order, width, height, spp, y0=0, y1=None, tie_by_objid=0, lights=None,
-                    want_hit=True, want_accum=False, want_dirs=False):
+                    want_hit=True, want_accum=False, want_dirs=False, shadows=0):
         y1 = height if y1 is None else y1
         sph = np.ascontiguousarray(sph, np.float32)
         mat = np.ascontiguousarray(mat, np.float32)
@@ -137,9 +137,12 @@ class Oracle:
         hit = np.zeros((rows, width), np.int32) if want_hit else None
         accum = np.zeros((rows, width, 3), np.float32) if want_accum else None
         dirs = np.zeros((rows, width, spp, 3), np.float32) if want_dirs else None
-        self.lib.orc_render_rows(self._p(sph), self._p(mat), sph.shape[0], self._p(nodes), self._p(order),
-                                 0 if nodes is None else nodes.shape[0], tie_by_objid, self._p(lights), lights.shape[0],
-                                 width, height, spp, y0, y1, self._p(rgb), self._p(hit), self._p(accum), self._p(dirs))
+        counts = np.zeros(3, np.int64)
+        self.lib.orc_render_rows_ex(self._p(sph), self._p(mat), sph.shape[0], self._p(nodes), self._p(order),
+                                    0 if nodes is None else nodes.shape[0], tie_by_objid, self._p(lights), lights.shape[0],
+                                    width, height, spp, y0, y1, int(shadows), self._p(rgb), self._p(hit), self._p(accum),
+                                    self._p(dirs), self._p(counts))
+        self.last_ray_counts = counts
         return rgb, hit, accum, dirs
 
 
@@ -286,6 +289,20 @@ def synthetic_scene(n, seed=1, ground=True, radius=0.05):
         sph[n] = np.asarray(rtds_b200.GROUND, np.float32)
     mat = np.zeros_like(sph)
     mat[:n, 0], mat[:n, 1] = 0.8, 0.7
+    return sph, mat
+
+
+def material_scene(n, seed, frac_rr=0.1, frac_refl=0.1, big=True):
+    """Synthetic scene with REFLECTION_AND_REFRACTION / REFLECTION spheres (unreachable through the reference's
+    loader, reachable through its castRay) — a few large ones so that secondary rays hit things."""
+    sph, mat = synthetic_scene(n, seed)
+    rng = np.random.default_rng(seed + 1000)
+    if big:
+        k = max(4, n // 100)
+        sph[:k, 3] = rng.uniform(0.5, 1.5, k).astype(np.float32)
+    u = rng.uniform(size=n)
+    mat[:n, 3] = np.where(u < frac_rr, 1.0, np.where(u < frac_rr + frac_refl, 2.0, 0.0)).astype(np.float32)
+    mat[:n, :3] = rng.uniform(0, 1, size=(n, 3)).astype(np.float32)
     return sph, mat
 
 

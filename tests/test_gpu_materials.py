@@ -1,0 +1,80 @@
+"""GPU parity for the rows SURVEY.md §8f marks "next": castRay's material branches (REFLECTION_AND_REFRACTION,
+REFLECTION, recursion depth) and the shadow query.  Oracle: the CPU restatement (pinned against the reference's own
+castRay for materials in tests/test_oracle_vs_reference.py; shadows have no executable reference behaviour —
+trace_more is a stub — PARITY UNPINNED for shadows, checked against the restatement of the contract of
+main.cpp:468-473 only)."""
+import os
+
+import numpy as np
+import pytest
+
+import conftest as T
+
+rt = T.rtds_b200
+pytestmark = pytest.mark.gpu
+LIGHTS3 = np.asarray([[0, 3, 30, 10, 1, 1, 1], [20, 30, -40, 1, 0.5, 0.4, 0.3], [-30, 5, -70, 1, 0.2, 0.3, 0.6]], np.float32)
+
+
+@pytest.mark.parametrize("acc,exact", [(rt.BVH, True), (rt.BVH, False), (rt.LBVH, False), (rt.NONE, False)])
+@pytest.mark.parametrize("shadows", [0, 1])
+def test_full_castray_matches_restatement(gpu_ctx, oracle, acc, exact, shadows):
+    n = 1500 if acc != rt.NONE else 400
+    sph, mat = T.material_scene(n, 11)
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.set_lights(LIGHTS3)
+    try:
+        if acc == rt.NONE:
+            nodes = order = None
+            tie = 0
+        else:
+            gpu_ctx.build(acc, mode=rt.MODE_TRUE if acc == rt.LBVH else rt.MODE_COMPAT)
+            nodes, order = gpu_ctx.export_bvh()
+            tie = 1 if acc == rt.LBVH else 0
+        W, H, spp = 240, 180, 2
+        rgb, hit, accum, st = gpu_ctx.render(acc, W, H, spp, want_hit=True, want_accum=True, exact=exact, shadows=shadows)
+        rgb_o, hit_o, accum_o, _ = oracle.render_rows(sph, mat, nodes, order, W, H, spp, tie_by_objid=tie, lights=LIGHTS3,
+                                                       want_accum=True, shadows=shadows)
+        rays, sh, sec = oracle.last_ray_counts
+        assert (st["rays"], st["shadow_rays"], st["secondary_rays"]) == (rays, sh, sec)
+        assert st["primary_rays"] == W * H * spp and sec > 10 and (sh > 1000 if shadows else sh == 0)
+        assert accum.tobytes() == accum_o.tobytes(), f"{np.count_nonzero((accum != accum_o).any(-1))} pixels differ"
+        assert np.array_equal(rgb, rgb_o)
+    finally:
+        gpu_ctx.set_lights(np.asarray([[0, 3, 30, 10, 1, 1, 1]], np.float32))
+
+
+def test_materials_vs_compiled_reference_castray(gpu_ctx):
+    """The reference's own castRay (materials set on Sphere::materialType) — within 1 LSB (glibc powf rounding)."""
+    if not os.path.exists(os.path.join(T.ROOT, "oracle", "_ref", "libref_oracle.so")):
+        pytest.skip("compiled reference not on this box")
+    ref = T.Ref()
+    sph, mat = T.material_scene(1500, 11)
+    ref.scene_from_spheres(sph, mat)
+    ref.lib.ref_set_lights(LIGHTS3.ctypes.data_as(T.C.c_void_p), 3)
+    ref.build(rt.BVH)
+    rgb_r, _, acc_r, _ = ref.render_rows(rt.BVH, 240, 180, 2, want_accum=True)
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.set_lights(LIGHTS3)
+    try:
+        gpu_ctx.build(rt.BVH)
+        rgb, _, accum, _ = gpu_ctx.render(rt.BVH, 240, 180, 2, want_accum=True)
+        assert np.allclose(accum, acc_r, rtol=3e-7, atol=1e-7)
+        assert np.abs(rgb.astype(int) - rgb_r.astype(int)).max() <= 1
+        assert np.count_nonzero(rgb != rgb_r) <= 3
+    finally:
+        gpu_ctx.set_lights(np.asarray([[0, 3, 30, 10, 1, 1, 1]], np.float32))
+
+
+def test_shadows_darken_only(gpu_ctx):
+    """Property at BASELINE config 2's size (1920x1080): shadows never brighten a pixel, sky pixels are unchanged,
+    and some bunny/ground pixels get darker."""
+    sph, mat = T.bunny_scene()
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+    a, hit, acc_a, st_a = gpu_ctx.render(rt.LBVH, 1920, 1080, 1, want_hit=True, want_accum=True)
+    b, _, acc_b, st_b = gpu_ctx.render(rt.LBVH, 1920, 1080, 1, want_accum=True, shadows=1)
+    assert np.all(acc_b <= acc_a)
+    assert np.array_equal(a[hit < 0], b[hit < 0])
+    assert np.count_nonzero((acc_b < acc_a).any(-1)) > 1000
+    assert st_b["shadow_rays"] == np.count_nonzero(hit >= 0) and st_b["rays"] == 1920 * 1080 + st_b["shadow_rays"]
+    print("1920x1080 LBVH: %.3f ms primary only, %.3f ms with shadows (%d shadow rays)" % (st_a["ms_kernel"], st_b["ms_kernel"], st_b["shadow_rays"]))
