@@ -160,7 +160,6 @@ def run_reference(args):
     ctx = mp.get_context("fork")        # children share the built scene + tree copy-on-write
 
     def one_step():
-        t0 = time.perf_counter()
         procs, conns = [], []
         for ch in chunks:
             a, b = ctx.Pipe(False)
@@ -171,7 +170,9 @@ def run_reference(args):
         res = [c.recv() for c in conns]
         for p in procs:
             p.join()
-        return sum(r[0] for r in res), time.perf_counter() - t0
+        # step time = the slowest process's time inside the reference's ray loop (the jitter generator's discard()
+        # to reach each band and the fork are harness overhead, not the reference's work)
+        return sum(r[0] for r in res), max(r[1] for r in res)
 
     for _ in range(args.warmup):
         one_step()

@@ -199,6 +199,79 @@ struct LbvhBuilder {
 };
 
 // ----------------------------------------------------------------------------------------------
+// Binned-SAH BVH (extension; the reference has no SAH BVH) — sequential statement of the definition in
+// raytracer-data-structures_b200/csrc/sah.cu. PARITY UNPINNED by the reference; this is the oracle for K7.
+// ----------------------------------------------------------------------------------------------
+struct SahBuilder {
+    const float* sph; std::vector<int>& order; std::vector<LinearNode>& out; int B; int max_depth = 0;
+    SahBuilder(const float* s, std::vector<int>& o, std::vector<LinearNode>& n, int b) : sph(s), order(o), out(n), B(b) {}
+    static float area(const Box& b)   // accelerators.h:122-125
+    {
+        float dx = b.mx.x - b.mn.x, dy = b.mx.y - b.mn.y, dz = b.mx.z - b.mn.z;
+        return 2 * (dx * dy + dx * dz + dy * dz);
+    }
+    Box build(int s, int e, int depth)
+    {
+        int my = (int)out.size();
+        out.push_back(LinearNode());
+        max_depth = std::max(max_depth, depth);
+        Box box;
+        if (e - s == 1) {
+            box = prim_box(sph + 4 * order[s]);
+            out[my].offset = s; out[my].nPrimitives = 1; out[my].axis = 0; out[my].pad = 0;
+        } else {
+            const float INF = INFINITY;
+            float cmn[3] = {INF, INF, INF}, cmx[3] = {-INF, -INF, -INF};
+            for (int p = s; p < e; ++p)
+                for (int a = 0; a < 3; ++a) { float c = sph[4 * order[p] + a]; cmn[a] = std::min(cmn[a], c); cmx[a] = std::max(cmx[a], c); }
+            float ex = cmx[0] - cmn[0], ey = cmx[1] - cmn[1], ez = cmx[2] - cmn[2];
+            int axis = (ex > ey && ex > ez) ? 0 : (ey > ez ? 1 : 2);
+            float lo = cmn[axis], hi = cmx[axis];
+            std::vector<int> bin(e - s);
+            std::vector<unsigned> cnt(B, 0);
+            std::vector<Box> bb(B, Box{{INF, INF, INF}, {-INF, -INF, -INF}});
+            for (int p = s; p < e; ++p) {
+                int b = 0;
+                if (hi > lo) { b = (int)((float)B * ((sph[4 * order[p] + axis] - lo) / (hi - lo))); if (b > B - 1) b = B - 1; }
+                bin[p - s] = b;
+                cnt[b]++;
+                bb[b] = join(bb[b], prim_box(sph + 4 * order[p]));
+            }
+            std::vector<Box> rb(B); std::vector<unsigned> rc(B, 0);
+            Box acc{{INF, INF, INF}, {-INF, -INF, -INF}}; unsigned n_acc = 0;
+            for (int b = B - 1; b >= 1; --b) { if (cnt[b]) acc = join(acc, bb[b]); n_acc += cnt[b]; rb[b] = acc; rc[b] = n_acc; }
+            Box lb{{INF, INF, INF}, {-INF, -INF, -INF}}; unsigned nL = 0;
+            float best = INF; int best_i = -1, best_nL = 0;
+            for (int i = 0; i < B - 1; ++i) {
+                if (cnt[i]) lb = join(lb, bb[i]);
+                nL += cnt[i];
+                unsigned nR = rc[i + 1];
+                if (nL == 0 || nR == 0) continue;
+                float cost = (float)nL * area(lb) + (float)nR * area(rb[i + 1]);
+                if (cost < best) { best = cost; best_i = i; best_nL = (int)nL; }
+            }
+            int mid;
+            if (best_i < 0) mid = s + (e - s) / 2;
+            else {
+                std::vector<int> L, R;
+                for (int p = s; p < e; ++p) (bin[p - s] <= best_i ? L : R).push_back(order[p]);
+                std::copy(L.begin(), L.end(), order.begin() + s);
+                std::copy(R.begin(), R.end(), order.begin() + s + L.size());
+                mid = s + best_nL;
+            }
+            Box l = build(s, mid, depth + 1);
+            int second = (int)out.size();
+            Box r = build(mid, e, depth + 1);
+            box = join(l, r);
+            out[my].offset = second; out[my].nPrimitives = 0; out[my].axis = (uint8_t)axis; out[my].pad = 0;
+        }
+        out[my].bmin[0] = box.mn.x; out[my].bmin[1] = box.mn.y; out[my].bmin[2] = box.mn.z;
+        out[my].bmax[0] = box.mx.x; out[my].bmax[1] = box.mx.y; out[my].bmax[2] = box.mx.z;
+        return box;
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
 // traversal + intersection
 // ----------------------------------------------------------------------------------------------
 // boundingBoxIntersection accelerators.h:588-626
@@ -496,6 +569,21 @@ int orc_build_bvh(const float* cxyz_r, int n_use, LinearNode* nodes, int* prim_o
     if (max_depth) *max_depth = B.max_depth;
     memcpy(nodes, out.data(), sizeof(LinearNode) * out.size());
     for (int i = 0; i < n_use; ++i) prim_order[i] = P[i].id;
+    return 0;
+}
+
+int orc_build_sah(const float* cxyz_r, int n, int bins, LinearNode* nodes, int* prim_order, int* n_nodes, int* max_depth)
+{
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::vector<LinearNode> out;
+    out.reserve(2 * (size_t)n);
+    SahBuilder B(cxyz_r, order, out, bins);
+    B.build(0, n, 0);
+    *n_nodes = (int)out.size();
+    if (max_depth) *max_depth = B.max_depth;
+    memcpy(nodes, out.data(), sizeof(LinearNode) * out.size());
+    for (int i = 0; i < n; ++i) prim_order[i] = order[i];
     return 0;
 }
 

@@ -426,6 +426,17 @@ int rtds_scene_bounds(rtds_ctx* ctx, float out12[12])
     return RTDS_OK;
 }
 
+// Bottom-up refit of a finished topology (nodes[].left/right/parent, leaf_parent[]) whose leaves hold the primitives
+// d_ids[leafpos]: fills every child-box slot, leaf_sph, prim_order and root_box. d_counters: n zeroed unsigneds.
+int rtds_bvh_refit(rtds_ctx* ctx, DeviceBvh& b, const uint32_t* d_ids, int n, unsigned* d_counters, float* d_root_box)
+{
+    RTDS_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned) * (size_t)n, ctx->stream));
+    refit_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_sph, d_ids, n, b.nodes, b.leaf_parent, b.leaf_sph, b.prim_order,
+                                                           d_counters, d_root_box);
+    RTDS_CUDA(cudaGetLastError());
+    return RTDS_OK;
+}
+
 int rtds_bvh_compute_depth(rtds_ctx* ctx, DeviceBvh& b, int* depth_out)
 {
     int* d_depth = (int*)(ctx->d_counters + 7);   // last slot of the context's counter block

@@ -1,7 +1,361 @@
-// sah.cu — K7 placeholder.
+// sah.cu — K7: binned-SAH BVH builder (extension: the reference's only BVH split is the object median,
+// accelerators.h:22,246-337; SAH exists there only in the KD-tree). Same output as the other builders: Node64
+// records, one primitive per leaf, leaves in DFS order, exportable as LinearBVHNode[] (accelerators.h:231-240).
+//
+// Deterministic definition (restated sequentially in oracle/oracle.cpp, orc_build_sah; trees are compared bit for bit):
+//   per node over the contiguous range [s,e) of the current order:
+//     cb   = min/max of the centres; axis = longest extent of cb (ties as GeMaximumAxis, accelerators.h:190-199)
+//     bin  = min(B-1, (int)(B * ((c[axis] - cb.min) / (cb.max - cb.min))))            B = 16 bins
+//     cost(i) = nL(i) * SA(union of bins 0..i) + nR(i) * SA(union of bins i+1..B-1)   SA as accelerators.h:122-125
+//     split = first i with minimal cost among those with nL > 0 and nR > 0;  left = bin <= i, STABLE partition
+//     no such i (all centres in one bin / zero extent): left = the first (e-s)/2 primitives of the range
+// Level-synchronous: bounds and bins are accumulated with exact, order-independent atomics (min/max on ordered
+// uints, integer adds), the stable partition is one global scan per level, boxes come from one atomic refit.
 #include "rtds_internal.cuh"
-int rtds_build_sah(rtds_ctx*, const rtds_build_params*, rtds_build_stats*)
+#include <math.h>
+#include <algorithm>
+
+int rtds_bvh_refit(rtds_ctx* ctx, DeviceBvh& b, const uint32_t* d_ids, int n, unsigned* d_counters, float* d_root_box);  // lbvh.cu
+int rtds_bvh_compute_depth(rtds_ctx* ctx, DeviceBvh& b, int* depth_out);
+
+namespace {
+
+constexpr int MAXB = 32;
+
+struct SahTask {
+    int s, e, parent_enc;     // range, parent*2+side (-1 root)
+    int node;                 // Node64 index
+    int axis, split_bin, nL;  // decision
+    int child_base;           // index of the first child task in the next level (or -1)
+    unsigned cb[6];           // centre bounds as ordered uints (min x,y,z, max x,y,z)
+};
+
+struct SahBins {              // per task
+    unsigned cnt[MAXB];
+    unsigned box[MAXB][6];    // ordered uints
+};
+
+__global__ void sah_reset(SahTask* tasks, SahBins* bins, int n_tasks, int B)
 {
-    rtds_set_error("SAH-binned BVH builder not implemented yet");
-    return RTDS_ERR_UNSUPPORTED;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    for (int a = 0; a < 3; ++a) { tasks[t].cb[a] = 0xffffffffu; tasks[t].cb[3 + a] = 0u; }
+    for (int b = 0; b < B; ++b) {
+        bins[t].cnt[b] = 0;
+        for (int a = 0; a < 3; ++a) { bins[t].box[b][a] = 0xffffffffu; bins[t].box[b][3 + a] = 0u; }
+    }
+}
+
+__global__ void sah_centre_bounds(const int* __restrict__ perm, const int* __restrict__ owner, int n, const float4* __restrict__ sph, SahTask* tasks)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int t = owner[p];
+    if (t < 0) return;
+    float4 c = __ldg(sph + perm[p]);
+    unsigned* cb = tasks[t].cb;
+    atomicMin(&cb[0], f2ord(c.x)); atomicMin(&cb[1], f2ord(c.y)); atomicMin(&cb[2], f2ord(c.z));
+    atomicMax(&cb[3], f2ord(c.x)); atomicMax(&cb[4], f2ord(c.y)); atomicMax(&cb[5], f2ord(c.z));
+}
+
+__device__ __forceinline__ int sah_axis(const unsigned cb[6], float& lo, float& hi)
+{
+    float mn[3] = {ord2f(cb[0]), ord2f(cb[1]), ord2f(cb[2])}, mx[3] = {ord2f(cb[3]), ord2f(cb[4]), ord2f(cb[5])};
+    float ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
+    int axis = (ex > ey && ex > ez) ? 0 : (ey > ez ? 1 : 2);
+    lo = mn[axis]; hi = mx[axis];
+    return axis;
+}
+
+__global__ void sah_binning(const int* __restrict__ perm, const int* __restrict__ owner, int n, const float4* __restrict__ sph,
+                            const SahTask* __restrict__ tasks, SahBins* bins, int* __restrict__ bin_of, int B)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int t = owner[p];
+    if (t < 0) return;
+    float4 c = __ldg(sph + perm[p]);
+    float lo, hi;
+    int axis = sah_axis(tasks[t].cb, lo, hi);
+    int b = 0;
+    if (hi > lo) {
+        float k = (axis == 0 ? c.x : (axis == 1 ? c.y : c.z));
+        b = (int)((float)B * ((k - lo) / (hi - lo)));
+        if (b > B - 1) b = B - 1;
+    }
+    bin_of[p] = b;
+    atomicAdd(&bins[t].cnt[b], 1u);
+    unsigned* bx = bins[t].box[b];
+    atomicMin(&bx[0], f2ord(c.x - c.w)); atomicMin(&bx[1], f2ord(c.y - c.w)); atomicMin(&bx[2], f2ord(c.z - c.w));
+    atomicMax(&bx[3], f2ord(c.x + c.w)); atomicMax(&bx[4], f2ord(c.y + c.w)); atomicMax(&bx[5], f2ord(c.z + c.w));
+}
+
+__device__ __forceinline__ float box_area(const float mn[3], const float mx[3])   // BoxBoundries::SurfaceArea, accelerators.h:122-125
+{
+    float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+    return 2 * (dx * dy + dx * dz + dy * dz);
+}
+
+// one thread per task: evaluate the B-1 split planes; has_child[2t], has_child[2t+1] = child is a task (size >= 2)
+__global__ void sah_decide(SahTask* tasks, const SahBins* __restrict__ bins, int n_tasks, int B, int node_base, int* __restrict__ child_flags)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    SahTask& T = tasks[t];
+    const SahBins& bn = bins[t];
+    float lo, hi;
+    T.axis = sah_axis(T.cb, lo, hi);
+    T.node = node_base + t;
+    const int m = T.e - T.s;
+    // suffix unions
+    float rmn[MAXB][3], rmx[MAXB][3];
+    unsigned rcnt[MAXB];
+    float amn[3] = {INFINITY, INFINITY, INFINITY}, amx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    unsigned acc = 0;
+    for (int b = B - 1; b >= 1; --b) {
+        if (bn.cnt[b]) for (int a = 0; a < 3; ++a) { amn[a] = fminf(amn[a], ord2f(bn.box[b][a])); amx[a] = fmaxf(amx[a], ord2f(bn.box[b][3 + a])); }
+        acc += bn.cnt[b];
+        for (int a = 0; a < 3; ++a) { rmn[b][a] = amn[a]; rmx[b][a] = amx[a]; }
+        rcnt[b] = acc;
+    }
+    float lmn[3] = {INFINITY, INFINITY, INFINITY}, lmx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    unsigned nL = 0;
+    float best = INFINITY;
+    int best_i = -1, best_nL = 0;
+    for (int i = 0; i < B - 1; ++i) {
+        if (bn.cnt[i]) for (int a = 0; a < 3; ++a) { lmn[a] = fminf(lmn[a], ord2f(bn.box[i][a])); lmx[a] = fmaxf(lmx[a], ord2f(bn.box[i][3 + a])); }
+        nL += bn.cnt[i];
+        unsigned nR = rcnt[i + 1];
+        if (nL == 0 || nR == 0) continue;
+        float cost = (float)nL * box_area(lmn, lmx) + (float)nR * box_area(rmn[i + 1], rmx[i + 1]);
+        if (cost < best) { best = cost; best_i = i; best_nL = (int)nL; }
+    }
+    if (best_i < 0) { T.split_bin = -1; T.nL = m / 2; }     // all centres in one bin: positional median of the range
+    else { T.split_bin = best_i; T.nL = best_nL; }
+    child_flags[2 * t] = T.nL >= 2 ? 1 : 0;
+    child_flags[2 * t + 1] = (m - T.nL) >= 2 ? 1 : 0;
+}
+
+__global__ void sah_left_flags(const int* __restrict__ owner, const int* __restrict__ bin_of, int n, const SahTask* __restrict__ tasks, int* __restrict__ flags)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int t = owner[p];
+    int f = 0;
+    if (t >= 0) {
+        const SahTask& T = tasks[t];
+        f = T.split_bin >= 0 ? (bin_of[p] <= T.split_bin) : ((p - T.s) < T.nL);
+    }
+    flags[p] = f;
+}
+
+// stable partition of every active range + creation of nodes / child tasks / leaf records
+__global__ void sah_scatter(const int* __restrict__ perm, const int* __restrict__ owner, const int* __restrict__ flags, const int* __restrict__ scan,
+                            int n, const SahTask* __restrict__ tasks, const int* __restrict__ child_scan, int* __restrict__ perm_next,
+                            int* __restrict__ owner_next, int* __restrict__ leaf_info)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int t = owner[p];
+    if (t < 0) { perm_next[p] = perm[p]; owner_next[p] = -1; return; }
+    const SahTask& T = tasks[t];
+    const int lefts_before = scan[p] - scan[T.s];
+    const bool left = flags[p] != 0;
+    const int dst = left ? T.s + lefts_before : T.s + T.nL + ((p - T.s) - lefts_before);
+    perm_next[dst] = perm[p];
+    const int m = T.e - T.s;
+    const int csize = left ? T.nL : m - T.nL;
+    if (csize >= 2) owner_next[dst] = child_scan[2 * t + (left ? 0 : 1)];
+    else { owner_next[dst] = -1; leaf_info[dst] = T.node * 2 + (left ? 0 : 1) + 2; }
+}
+
+__global__ void sah_make_children(const SahTask* __restrict__ tasks, int n_tasks, const int* __restrict__ child_flags, const int* __restrict__ child_scan,
+                                  SahTask* __restrict__ next, Node64* __restrict__ nodes, int next_node_base)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    const SahTask& T = tasks[t];
+    Node64& nd = nodes[T.node];
+    nd.axis = T.axis;
+    nd.parent = T.parent_enc;
+    if (T.parent_enc >= 0) { if (T.parent_enc & 1) nodes[T.parent_enc >> 1].right = T.node; else nodes[T.parent_enc >> 1].left = T.node; }
+    for (int side = 0; side < 2; ++side) {
+        if (!child_flags[2 * t + side]) continue;
+        SahTask c;
+        c.s = side ? T.s + T.nL : T.s;
+        c.e = side ? T.e : T.s + T.nL;
+        c.parent_enc = T.node * 2 + side;
+        c.node = next_node_base + child_scan[2 * t + side];
+        c.axis = 0; c.split_bin = -1; c.nL = 0; c.child_base = -1;
+        next[child_scan[2 * t + side]] = c;
+    }
+}
+
+__global__ void sah_finalize_leaves(const int* __restrict__ leaf_info, int n, Node64* nodes, int* __restrict__ leaf_parent)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int pe = leaf_info[p] - 2;
+    if (pe < 0) { leaf_parent[p] = 0; return; }
+    leaf_parent[p] = (pe >> 1) | ((pe & 1) ? 0x80000000 : 0);
+    if (pe & 1) nodes[pe >> 1].right = ~p; else nodes[pe >> 1].left = ~p;
+}
+
+__global__ void sah_init(int* perm, int* owner, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { perm[i] = i; owner[i] = n >= 2 ? 0 : -1; }
+}
+
+// ---- exclusive scan (same three-kernel scheme as kd.cu, kept local to this translation unit) ----
+constexpr int SC_BLOCK = 256, SC_ITEMS = 8, SC_TILE = SC_BLOCK * SC_ITEMS;
+__global__ void __launch_bounds__(SC_BLOCK) s_tile_sums(const int* __restrict__ in, int n, int* __restrict__ sums)
+{
+    __shared__ int ws[SC_BLOCK / 32];
+    long long base = (long long)blockIdx.x * SC_TILE;
+    int v = 0;
+    for (int i = threadIdx.x; i < SC_TILE; i += SC_BLOCK) { long long p = base + i; v += p < n ? in[p] : 0; }
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < SC_BLOCK / 32; ++w) t += ws[w]; sums[blockIdx.x] = t; }
+}
+__global__ void s_scan_sums(int* sums, int tiles, int* total)
+{
+    if (threadIdx.x == 0) { int run = 0; for (int i = 0; i < tiles; ++i) { int c = sums[i]; sums[i] = run; run += c; } *total = run; }
+}
+__global__ void __launch_bounds__(SC_BLOCK) s_apply(const int* __restrict__ in, int n, const int* __restrict__ sums, int* __restrict__ out)
+{
+    __shared__ int ws[SC_BLOCK / 32];
+    __shared__ int running;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = sums[blockIdx.x];
+    __syncthreads();
+    long long base = (long long)blockIdx.x * SC_TILE;
+    for (int it = 0; it < SC_ITEMS; ++it) {
+        long long p = base + it * SC_BLOCK + threadIdx.x;
+        int v = p < n ? in[p] : 0, x = v;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+        if (lane == 31) ws[warp] = x;
+        __syncthreads();
+        int woff = 0, chunk = 0;
+        for (int w = 0; w < SC_BLOCK / 32; ++w) { int c = ws[w]; woff += (w < warp) ? c : 0; chunk += c; }
+        const int start = running;
+        if (p < n) out[p] = start + woff + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) running = start + chunk;
+        __syncthreads();
+    }
+}
+
+template <typename T> T* carve(char*& p, size_t count)
+{
+    T* r = (T*)p;
+    p += (sizeof(T) * count + 255) & ~(size_t)255;
+    return r;
+}
+
+}  // namespace
+
+int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats* st)
+{
+    const int n = ctx->n;
+    const int B = (bp && bp->sah_bins > 1) ? std::min(bp->sah_bins, MAXB) : 16;
+    DeviceBvh& b = ctx->bvh;
+    RTDS_TRY(rtds_alloc_bvh(b, n));
+    const size_t max_tasks = (size_t)n / 2 + 2;
+    const int tiles = (int)(((size_t)std::max<size_t>(n, 2 * max_tasks) + SC_TILE - 1) / SC_TILE) + 1;
+    size_t bytes = 6 * (((size_t)n * 4 + 255) & ~(size_t)255) + 2 * ((sizeof(SahTask) * max_tasks + 255) & ~(size_t)255) +
+                   ((sizeof(SahBins) * max_tasks + 255) & ~(size_t)255) + 4 * ((8 * max_tasks + 255) & ~(size_t)255) + ((size_t)tiles * 4 + 255) +
+                   (((size_t)n * 4 + 255) & ~(size_t)255) + 4096;
+    RTDS_TRY(rtds_ensure_scratch(ctx, bytes));
+    char* p = (char*)ctx->d_scratch;
+    int* perm[2] = {carve<int>(p, n), carve<int>(p, n)};
+    int* owner[2] = {carve<int>(p, n), carve<int>(p, n)};
+    int* bin_of = carve<int>(p, n);
+    int* flags = carve<int>(p, n);
+    int* scan = carve<int>(p, n);
+    SahTask* tasks[2] = {carve<SahTask>(p, max_tasks), carve<SahTask>(p, max_tasks)};
+    SahBins* bins = carve<SahBins>(p, max_tasks);
+    int* child_flags = carve<int>(p, 2 * max_tasks);
+    int* child_scan = carve<int>(p, 2 * max_tasks);
+    int* sums = carve<int>(p, tiles);
+    int* d_small = carve<int>(p, 64);
+    cudaStream_t s = ctx->stream;
+    int launches = 0;
+    const int T = 256;
+    auto G = [&](long long m) { return (unsigned)((m + T - 1) / T); };
+    auto xscan = [&](const int* in, int* out, int m) -> int {
+        int tl = (m + SC_TILE - 1) / SC_TILE;
+        s_tile_sums<<<tl, SC_BLOCK, 0, s>>>(in, m, sums);
+        s_scan_sums<<<1, 32, 0, s>>>(sums, tl, d_small);
+        s_apply<<<tl, SC_BLOCK, 0, s>>>(in, m, sums, out);
+        launches += 3;
+        return RTDS_OK;
+    };
+    int* leaf_arr = carve<int>(p, n);   // scene position -> parent*2+side+2 once the position holds a finished leaf
+    RTDS_CUDA(cudaEventRecord(ctx->ev0, s));
+    RTDS_CUDA(cudaMemsetAsync(leaf_arr, 0, (size_t)n * 4, s));
+    sah_init<<<G(n), T, 0, s>>>(perm[0], owner[0], n);
+    ++launches;
+    int cur = 0, n_tasks = n >= 2 ? 1 : 0, node_base = 0, levels = 0;
+    if (n_tasks) {
+        SahTask root;
+        memset(&root, 0, sizeof root);
+        root.s = 0; root.e = n; root.parent_enc = -1; root.node = 0; root.split_bin = -1; root.child_base = -1;
+        RTDS_CUDA(cudaMemcpyAsync(tasks[0], &root, sizeof root, cudaMemcpyHostToDevice, s));
+    } else {
+        const int two = 1;   // single primitive: leaf_info = root leaf
+        RTDS_CUDA(cudaMemcpyAsync(leaf_arr, &two, sizeof two, cudaMemcpyHostToDevice, s));
+    }
+    while (n_tasks > 0) {
+        SahTask* tk = tasks[cur];
+        sah_reset<<<G(n_tasks), T, 0, s>>>(tk, bins, n_tasks, B);
+        sah_centre_bounds<<<G(n), T, 0, s>>>(perm[cur], owner[cur], n, ctx->d_sph, tk);
+        sah_binning<<<G(n), T, 0, s>>>(perm[cur], owner[cur], n, ctx->d_sph, tk, bins, bin_of, B);
+        sah_decide<<<G(n_tasks), T, 0, s>>>(tk, bins, n_tasks, B, node_base, child_flags);
+        launches += 4;
+        RTDS_TRY(xscan(child_flags, child_scan, 2 * n_tasks));
+        int next_tasks = 0;
+        RTDS_CUDA(cudaMemcpyAsync(&next_tasks, d_small, sizeof(int), cudaMemcpyDeviceToHost, s));
+        sah_left_flags<<<G(n), T, 0, s>>>(owner[cur], bin_of, n, tk, flags);
+        ++launches;
+        RTDS_TRY(xscan(flags, scan, n));
+        sah_scatter<<<G(n), T, 0, s>>>(perm[cur], owner[cur], flags, scan, n, tk, child_scan, perm[cur ^ 1], owner[cur ^ 1], leaf_arr);
+        RTDS_CUDA(cudaStreamSynchronize(s));
+        sah_make_children<<<G(n_tasks), T, 0, s>>>(tk, n_tasks, child_flags, child_scan, tasks[cur ^ 1], b.nodes, node_base + n_tasks);
+        launches += 2;
+        node_base += n_tasks;
+        n_tasks = next_tasks;
+        cur ^= 1;
+        ++levels;
+        if (levels > 4096) { rtds_set_error("sah build: runaway depth"); return RTDS_ERR_CUDA; }
+    }
+    sah_finalize_leaves<<<G(n), T, 0, s>>>(leaf_arr, n, b.nodes, b.leaf_parent);
+    ++launches;
+    unsigned* d_counters = (unsigned*)scan;
+    float* d_root = (float*)(d_small + 16);
+    RTDS_TRY(rtds_bvh_refit(ctx, b, (const uint32_t*)perm[cur], n, d_counters, d_root));
+    ++launches;
+    RTDS_CUDA(cudaGetLastError());
+    RTDS_CUDA(cudaMemcpyAsync(b.root_box, d_root, sizeof(float) * 6, cudaMemcpyDeviceToHost, s));
+    RTDS_CUDA(cudaStreamSynchronize(s));
+    b.n_prims = n;
+    b.n_internal = n - 1;
+    b.root_ref = n > 1 ? 0 : ~0;
+    b.tie_by_objid = 1;
+    int depth = 0;
+    RTDS_TRY(rtds_bvh_compute_depth(ctx, b, &depth));
+    ++launches;
+    RTDS_CUDA(cudaEventRecord(ctx->ev1, s));
+    RTDS_CUDA(cudaStreamSynchronize(s));
+    b.max_depth = depth;
+    b.valid = true;
+    float ms = 0;
+    RTDS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (st) {
+        st->n_prims = n; st->total_nodes = 2 * n - 1; st->alloc_nodes = 2 * n - 1; st->max_depth = depth;
+        st->kernel_launches = launches; st->ms = ms;
+    }
+    return RTDS_OK;
 }

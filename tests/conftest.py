@@ -101,6 +101,15 @@ class Oracle:
         assert rc == 0
         return nodes[:nn.value], order, keys, md.value
 
+    def build_sah(self, sph, bins=16):
+        sph = np.ascontiguousarray(sph, np.float32)
+        n = sph.shape[0]
+        nodes = np.zeros(2 * n - 1, LINEAR)
+        order = np.zeros(n, np.int32)
+        nn, md = C.c_int(), C.c_int()
+        self.lib.orc_build_sah(self._p(sph), n, bins, self._p(nodes), self._p(order), C.byref(nn), C.byref(md))
+        return nodes[:nn.value], order, md.value
+
     def morton30(self, xyz):
         xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
         codes = np.zeros(xyz.shape[0], np.uint32)
