@@ -193,6 +193,7 @@ struct BvhView {
     const Node64* nodes;
     const float4* leaf_sph;
     const int*    prim_order;
+    const int*    leaf_parent;
     int           root_ref;
     int           tie_by_objid;
     float         root_box[6];
@@ -324,6 +325,101 @@ __device__ __forceinline__ void traverse_bvh(const BvhView& B, float ox, float o
         }
         if (!found) break;
     }
+}
+
+// The ordered traversal (exact = 0), written "while-while": interior nodes and leaves are both stack items, so the
+// hot interior loop is branch-light (both children go through the conservative reciprocal test, no leaf special
+// case), and a leaf is only opened when it is popped with tmin still below the current hit: there the reference's
+// EXACT slab test is run on the leaf's box (re-read from its parent's record) and then the sphere test.
+// ZERO_O: the ray starts at the origin (every primary ray, main.cpp:558): t = b * (1/d), one multiply per plane.
+template <bool ZERO_O>
+__device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
+                                              float& tnear, int& best_key, int& best_leaf, Counters& cnt)
+{
+    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+    if (B.root_ref < 0 || !(fabsf(ix) < 1e30f && fabsf(iy) < 1e30f && fabsf(iz) < 1e30f)) {
+        // single-leaf tree, or a zero / tiny / non-finite direction component: the divide-based traversal
+        traverse_bvh<true>(B, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+        return;
+    }
+    float tmn, tmx;
+    cnt.node_tests++;
+    if (!slab_test(ox, oy, oz, dx, dy, dz, B.root_box[0], B.root_box[1], B.root_box[2], B.root_box[3], B.root_box[4],
+                   B.root_box[5], tmn, tmx))
+        return;
+    const float margin = prune_margin(B.root_box, ox, oy, oz);
+    const float neg_margin = -margin;
+    float tlim = tnear + margin;            // a subtree is opened only while its entry distance is <= tlim
+    int   stack[STACK_MAX];
+    float stack_t[STACK_MAX];
+    int sp = 0;
+    int node = 0;
+    unsigned visits = 0;
+    while (true) {
+        if (node >= 0) {
+            const float4* q = reinterpret_cast<const float4*>(B.nodes + node);
+            const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+            const int2 ch = __ldg(reinterpret_cast<const int2*>(q + 3));
+            ++visits;
+            float lx0, lx1, ly0, ly1, lz0, lz1, rx0, rx1, ry0, ry1, rz0, rz1;
+            if (ZERO_O) {
+                lx0 = q0.x * ix; ly0 = q0.y * iy; lz0 = q0.z * iz; lx1 = q0.w * ix; ly1 = q1.x * iy; lz1 = q1.y * iz;
+                rx0 = q1.z * ix; ry0 = q1.w * iy; rz0 = q2.x * iz; rx1 = q2.y * ix; ry1 = q2.z * iy; rz1 = q2.w * iz;
+            } else {
+                lx0 = (q0.x - ox) * ix; ly0 = (q0.y - oy) * iy; lz0 = (q0.z - oz) * iz;
+                lx1 = (q0.w - ox) * ix; ly1 = (q1.x - oy) * iy; lz1 = (q1.y - oz) * iz;
+                rx0 = (q1.z - ox) * ix; ry0 = (q1.w - oy) * iy; rz0 = (q2.x - oz) * iz;
+                rx1 = (q2.y - ox) * ix; ry1 = (q2.z - oy) * iy; rz1 = (q2.w - oz) * iz;
+            }
+            float tminL = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fminf(lz0, lz1));
+            float tmaxL = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fmaxf(lz0, lz1));
+            float tminR = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fminf(rz0, rz1));
+            float tmaxR = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1));
+            tminL = __fmaf_rn(-fabsf(tminL), WIDE_EPS, tminL); tmaxL = __fmaf_rn(fabsf(tmaxL), WIDE_EPS, tmaxL);
+            tminR = __fmaf_rn(-fabsf(tminR), WIDE_EPS, tminR); tmaxR = __fmaf_rn(fabsf(tmaxR), WIDE_EPS, tmaxR);
+            const bool hitL = tminL <= fminf(tmaxL, tlim) && tmaxL >= neg_margin;
+            const bool hitR = tminR <= fminf(tmaxR, tlim) && tmaxR >= neg_margin;
+            if (hitL && hitR) {
+                const bool rfirst = tminR < tminL;
+                stack[sp] = rfirst ? ch.x : ch.y;
+                stack_t[sp] = rfirst ? tminL : tminR;
+                sp = min(sp + 1, STACK_MAX - 1);
+                node = rfirst ? ch.y : ch.x;
+                continue;
+            }
+            if (hitL | hitR) { node = hitL ? ch.x : ch.y; continue; }
+        } else {
+            // leaf: exact test on its own box (in the parent's record), then the sphere
+            const int leaf = ~node;
+            const int lp = __ldg(B.leaf_parent + leaf);
+            const float4* q = reinterpret_cast<const float4*>(B.nodes + (lp & 0x7fffffff));
+            const float4 q1 = __ldg(q + 1);
+            float bx0, by0, bz0, bx1, by1, bz1;
+            if (lp < 0) { const float4 q2 = __ldg(q + 2); bx0 = q1.z; by0 = q1.w; bz0 = q2.x; bx1 = q2.y; by1 = q2.z; bz1 = q2.w; }
+            else { const float4 q0 = __ldg(q); bx0 = q0.x; by0 = q0.y; bz0 = q0.z; bx1 = q0.w; by1 = q1.x; bz1 = q1.y; }
+            float a, b2;
+            if (slab_test(ox, oy, oz, dx, dy, dz, bx0, by0, bz0, bx1, by1, bz1, a, b2)) {
+                float t0, t1;
+                cnt.prim_tests++;
+                if (sphere_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_sph + leaf), t0, t1)) {
+                    candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
+                    tlim = tnear + margin;
+                }
+            }
+        }
+        // pop
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (stack_t[sp] > tlim) continue;
+            node = stack[sp];
+            found = true;
+            break;
+        }
+        if (!found) break;
+    }
+    cnt.node_visits += visits;
+    cnt.node_tests += 2 * visits;
 }
 
 // NONE: main.cpp:376-386, spheres staged through shared memory by the whole block (all threads must call).
@@ -540,7 +636,8 @@ __global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
         } else if (MODE == 3) {
             if (active) hit_obj = kd_any_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, cnt) ? 1 : -1;
         } else if (active) {
-            traverse_bvh<MODE == 0>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+            if (MODE == 0) traverse_bvh<true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+            else traverse_fast<true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
             if (best_leaf >= 0) {
                 hit_obj = __ldg(A.bvh.prim_order + best_leaf);
                 float4 s = __ldg(A.bvh.leaf_sph + best_leaf);
@@ -633,7 +730,7 @@ __device__ __forceinline__ void closest_hit(const RenderArgs& A, float ox, float
         int best_key = 0, best_leaf = -1;
         float len2 = dx * dx + dy * dy + dz * dz;
         if (MODE == 0 || !(fabsf(len2 - 1.0f) < 1e-3f)) traverse_bvh<true>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
-        else traverse_bvh<false>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+        else traverse_fast<false>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
         if (best_leaf >= 0) {
             hit_obj = __ldg(A.bvh.prim_order + best_leaf);
             float4 s = __ldg(A.bvh.leaf_sph + best_leaf);
@@ -794,7 +891,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A)
         float len2 = dx * dx + dy * dy + dz * dz;
         bool unit = fabsf(len2 - 1.0f) < 1e-3f;
         if (A.exact || !unit) traverse_bvh<true>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
-        else traverse_bvh<false>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+        else traverse_fast<false>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
         if (best_leaf >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf);
     }
     if (active) { A.hit[i] = hit_obj; A.t[i] = tnear; cnt.rays = 1; }
@@ -810,7 +907,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A)
 BvhView make_view(const DeviceBvh& b)
 {
     BvhView v;
-    v.nodes = b.nodes; v.leaf_sph = b.leaf_sph; v.prim_order = b.prim_order;
+    v.nodes = b.nodes; v.leaf_sph = b.leaf_sph; v.prim_order = b.prim_order; v.leaf_parent = b.leaf_parent;
     v.root_ref = b.root_ref; v.tie_by_objid = b.tie_by_objid;
     for (int i = 0; i < 6; ++i) v.root_box[i] = b.root_box[i];
     return v;
