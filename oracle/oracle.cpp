@@ -66,6 +66,27 @@ Box prim_box(const float* s)  // main.cpp:686-688: centre -/+ radius in float
     return Box{{s[0] - s[3], s[1] - s[3], s[2] - s[3]}, {s[0] + s[3], s[1] + s[3], s[2] + s[3]}};
 }
 
+// Primitive table seen by the builders: type 0 = spheres (n x {cx,cy,cz,r}), type 1 = triangles (n x 9, extension:
+// box = min/max of the vertices, centre = (min + max) * 0.5f).
+struct Prims {
+    const float* data; int type;
+    Box box(int i) const
+    {
+        if (type == 0) return prim_box(data + 4 * (size_t)i);
+        const float* t = data + 9 * (size_t)i;
+        Box b;
+        b.mn = V3{std::min(std::min(t[0], t[3]), t[6]), std::min(std::min(t[1], t[4]), t[7]), std::min(std::min(t[2], t[5]), t[8])};
+        b.mx = V3{std::max(std::max(t[0], t[3]), t[6]), std::max(std::max(t[1], t[4]), t[7]), std::max(std::max(t[2], t[5]), t[8])};
+        return b;
+    }
+    V3 centre(int i) const
+    {
+        if (type == 0) { const float* q = data + 4 * (size_t)i; return V3{q[0], q[1], q[2]}; }
+        Box b = box(i);
+        return V3{(b.mn.x + b.mx.x) * 0.5f, (b.mn.y + b.mx.y) * 0.5f, (b.mn.z + b.mx.z) * 0.5f};
+    }
+};
+
 // ----------------------------------------------------------------------------------------------
 // constructBVHNew, accelerators.h:246-337, emitting the pre-order LinearBVHNode array directly.
 // Returns 0, or -6 when std::partition returns endIndex (the reference then recurses forever).
@@ -203,8 +224,8 @@ struct LbvhBuilder {
 // raytracer-data-structures_b200/csrc/sah.cu. PARITY UNPINNED by the reference; this is the oracle for K7.
 // ----------------------------------------------------------------------------------------------
 struct SahBuilder {
-    const float* sph; std::vector<int>& order; std::vector<LinearNode>& out; int B; int max_depth = 0;
-    SahBuilder(const float* s, std::vector<int>& o, std::vector<LinearNode>& n, int b) : sph(s), order(o), out(n), B(b) {}
+    Prims sph; std::vector<int>& order; std::vector<LinearNode>& out; int B; int max_depth = 0;
+    SahBuilder(Prims s, std::vector<int>& o, std::vector<LinearNode>& n, int b) : sph(s), order(o), out(n), B(b) {}
     static float area(const Box& b)   // accelerators.h:122-125
     {
         float dx = b.mx.x - b.mn.x, dy = b.mx.y - b.mn.y, dz = b.mx.z - b.mn.z;
@@ -217,13 +238,13 @@ struct SahBuilder {
         max_depth = std::max(max_depth, depth);
         Box box;
         if (e - s == 1) {
-            box = prim_box(sph + 4 * order[s]);
+            box = sph.box(order[s]);
             out[my].offset = s; out[my].nPrimitives = 1; out[my].axis = 0; out[my].pad = 0;
         } else {
             const float INF = INFINITY;
             float cmn[3] = {INF, INF, INF}, cmx[3] = {-INF, -INF, -INF};
             for (int p = s; p < e; ++p)
-                for (int a = 0; a < 3; ++a) { float c = sph[4 * order[p] + a]; cmn[a] = std::min(cmn[a], c); cmx[a] = std::max(cmx[a], c); }
+                { V3 cc = sph.centre(order[p]); for (int a = 0; a < 3; ++a) { float c = comp(cc, a); cmn[a] = std::min(cmn[a], c); cmx[a] = std::max(cmx[a], c); } }
             float ex = cmx[0] - cmn[0], ey = cmx[1] - cmn[1], ez = cmx[2] - cmn[2];
             int axis = (ex > ey && ex > ez) ? 0 : (ey > ez ? 1 : 2);
             float lo = cmn[axis], hi = cmx[axis];
@@ -232,10 +253,10 @@ struct SahBuilder {
             std::vector<Box> bb(B, Box{{INF, INF, INF}, {-INF, -INF, -INF}});
             for (int p = s; p < e; ++p) {
                 int b = 0;
-                if (hi > lo) { b = (int)((float)B * ((sph[4 * order[p] + axis] - lo) / (hi - lo))); if (b > B - 1) b = B - 1; }
+                if (hi > lo) { b = (int)((float)B * ((comp(sph.centre(order[p]), axis) - lo) / (hi - lo))); if (b > B - 1) b = B - 1; }
                 bin[p - s] = b;
                 cnt[b]++;
-                bb[b] = join(bb[b], prim_box(sph + 4 * order[p]));
+                bb[b] = join(bb[b], sph.box(order[p]));
             }
             std::vector<Box> rb(B); std::vector<unsigned> rc(B, 0);
             Box acc{{INF, INF, INF}, {-INF, -INF, -INF}}; unsigned n_acc = 0;
@@ -308,10 +329,39 @@ inline bool ray_sphere(const float o[3], const float d[3], const float* s /*cx,c
     return true;
 }
 
+// Moller-Trumbore as in the reference's never-compiled MOLLER_TRUMBORE branch (main.cpp:138-162, `v_0` read as v0,
+// no culling, EPS 1e-6) + the t < 0 rejection of the geometric branch (main.cpp:184). Extension: PARITY UNPINNED.
+inline bool ray_triangle(const float o[3], const float d[3], const float* v /*9 floats*/, float& t)
+{
+    const float e1x = v[3] - v[0], e1y = v[4] - v[1], e1z = v[5] - v[2];
+    const float e2x = v[6] - v[0], e2y = v[7] - v[1], e2z = v[8] - v[2];
+    const float px = d[1] * e2z - d[2] * e2y, py = d[2] * e2x - d[0] * e2z, pz = d[0] * e2y - d[1] * e2x;
+    const float det = e1x * px + e1y * py + e1z * pz;
+    if (std::fabs(det) < 1e-6f) return false;
+    const float inv = 1 / det;
+    const float tx = o[0] - v[0], ty = o[1] - v[1], tz = o[2] - v[2];
+    const float u = (tx * px + ty * py + tz * pz) * inv;
+    if (u < 0 || u > 1) return false;
+    const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+    const float w = (d[0] * qx + d[1] * qy + d[2] * qz) * inv;
+    if (w < 0 || u + w > 1) return false;
+    t = (e2x * qx + e2y * qy + e2z * qz) * inv;
+    return !(t < 0);
+}
+
 struct Scene {
     const float* sph; const float* mat; int n;
     const LinearNode* nodes; const int* prim_order; int n_nodes;
     int tie_by_objid;
+    int prim_type = 0;   // 0: sph = n x 4 spheres; 1: sph = n x 9 triangles
+    bool test(const float o[3], const float d[3], int obj, float& t0, float& t1) const
+    {
+        if (prim_type == 0) return ray_sphere(o, d, sph + 4 * (size_t)obj, t0, t1);
+        float t;
+        if (!ray_triangle(o, d, sph + 9 * (size_t)obj, t)) return false;
+        t0 = t1 = t;
+        return true;
+    }
 };
 
 // boxIntersect accelerators.h:668-690 + candidate loop main.cpp:343-358 over a flattened tree.
@@ -330,7 +380,7 @@ void closest_bvh(const Scene& S, const float o[3], const float d[3], int& hit, f
             int leafpos = nd.offset, obj = S.prim_order[leafpos];
             if (cand) ++*cand;
             float t0 = INFINITY, t1 = INFINITY;
-            if (ray_sphere(o, d, S.sph + 4 * obj, t0, t1)) {
+            if (S.test(o, d, obj, t0, t1)) {
                 if (t0 < 0) t0 = t1;
                 int key = S.tie_by_objid ? obj : leafpos;
                 if (t0 < tnear || (t0 == tnear && hit >= 0 && key < best_key)) { tnear = t0; hit = obj; best_key = key; }
@@ -348,7 +398,7 @@ void closest_none(const Scene& S, const float o[3], const float d[3], int& hit, 
     hit = -1; tnear = INFINITY;
     for (int i = 0; i < S.n; ++i) {
         float t0 = INFINITY, t1 = INFINITY;
-        if (ray_sphere(o, d, S.sph + 4 * i, t0, t1)) {
+        if (S.test(o, d, i, t0, t1)) {
             if (t0 < 0) t0 = t1;
             if (t0 < tnear) { tnear = t0; hit = i; }
         }
@@ -430,10 +480,17 @@ void cast_ray(CastCtx& C, const float o[3], const float d[3], int depth, float r
     C.rays++;
     if (hit_out) *hit_out = hit;
     if (hit < 0) { rgb[0] = 0.6f; rgb[1] = 0.8f; rgb[2] = 1.0f; return; }                     // :318,394
-    const float* sph = S.sph + 4 * hit;
     const float* mat = S.mat + 4 * hit;
     float hp[3] = {o[0] + d[0] * tnear, o[1] + d[1] * tnear, o[2] + d[2] * tnear};
-    float N[3] = {hp[0] - sph[0], hp[1] - sph[1], hp[2] - sph[2]};
+    float N[3];
+    if (S.prim_type == 0) {
+        const float* sph = S.sph + 4 * (size_t)hit;
+        N[0] = hp[0] - sph[0]; N[1] = hp[1] - sph[1]; N[2] = hp[2] - sph[2];
+    } else {   // main.cpp:165-168: N = v0v1 x v0v2
+        const float* v = S.sph + 9 * (size_t)hit;
+        float e1x = v[3] - v[0], e1y = v[4] - v[1], e1z = v[5] - v[2], e2x = v[6] - v[0], e2y = v[7] - v[1], e2z = v[8] - v[2];
+        N[0] = e1y * e2z - e1z * e2y; N[1] = e1z * e2x - e1x * e2z; N[2] = e1x * e2y - e1y * e2x;
+    }
     normalize(N);
     if (d[0] * N[0] + d[1] * N[1] + d[2] * N[2] > 0) { N[0] = -N[0]; N[1] = -N[1]; N[2] = -N[2]; }
     const float bias = 1e-4;                                                                  // :404
@@ -553,13 +610,16 @@ int orc_scene_from_vertices(const float* v, int nv, int clones, float* cxyz_r, f
 }
 
 // Median-split BVH over the first n_use of n spheres. nodes: capacity 2*n_use-1; prim_order: n_use.
+int orc_build_bvh_p(const float* prims, int prim_type, int n_use, LinearNode* nodes, int* prim_order, int* n_nodes, int* max_depth);
 int orc_build_bvh(const float* cxyz_r, int n_use, LinearNode* nodes, int* prim_order, int* n_nodes, int* max_depth)
 {
+    return orc_build_bvh_p(cxyz_r, 0, n_use, nodes, prim_order, n_nodes, max_depth);
+}
+int orc_build_bvh_p(const float* prims, int prim_type, int n_use, LinearNode* nodes, int* prim_order, int* n_nodes, int* max_depth)
+{
+    Prims PV{prims, prim_type};
     std::vector<Prim> P(n_use);
-    for (int i = 0; i < n_use; ++i) {
-        P[i].c = V3{cxyz_r[4 * i], cxyz_r[4 * i + 1], cxyz_r[4 * i + 2]};
-        P[i].r = cxyz_r[4 * i + 3]; P[i].id = i; P[i].box = prim_box(cxyz_r + 4 * i);
-    }
+    for (int i = 0; i < n_use; ++i) { P[i].c = PV.centre(i); P[i].r = 0; P[i].id = i; P[i].box = PV.box(i); }
     std::vector<LinearNode> out;
     out.reserve(2 * (size_t)n_use);
     MedianBuilder B(P, out);
@@ -572,13 +632,18 @@ int orc_build_bvh(const float* cxyz_r, int n_use, LinearNode* nodes, int* prim_o
     return 0;
 }
 
+int orc_build_sah_p(const float* prims, int prim_type, int n, int bins, LinearNode* nodes, int* prim_order, int* n_nodes, int* max_depth);
 int orc_build_sah(const float* cxyz_r, int n, int bins, LinearNode* nodes, int* prim_order, int* n_nodes, int* max_depth)
+{
+    return orc_build_sah_p(cxyz_r, 0, n, bins, nodes, prim_order, n_nodes, max_depth);
+}
+int orc_build_sah_p(const float* prims, int prim_type, int n, int bins, LinearNode* nodes, int* prim_order, int* n_nodes, int* max_depth)
 {
     std::vector<int> order(n);
     for (int i = 0; i < n; ++i) order[i] = i;
     std::vector<LinearNode> out;
     out.reserve(2 * (size_t)n);
-    SahBuilder B(cxyz_r, order, out, bins);
+    SahBuilder B(Prims{prims, prim_type}, order, out, bins);
     B.build(0, n, 0);
     *n_nodes = (int)out.size();
     if (max_depth) *max_depth = B.max_depth;
@@ -593,17 +658,28 @@ void orc_morton30(const float* xyz, int n, uint32_t* codes)
 }
 
 // LBVH as the reference intends it. bits 30|63; ref_norm: (c+30)/1000 (accelerators.h:577) else scene-normalised.
+int orc_build_lbvh_p(const float* prims, int prim_type, int n, int bits, int ref_norm, LinearNode* nodes, int* prim_order,
+                     uint64_t* keys_sorted, int* n_nodes, int* max_depth);
 int orc_build_lbvh(const float* cxyz_r, int n, int bits, int ref_norm, LinearNode* nodes, int* prim_order, uint64_t* keys_sorted,
                    int* n_nodes, int* max_depth)
 {
+    return orc_build_lbvh_p(cxyz_r, 0, n, bits, ref_norm, nodes, prim_order, keys_sorted, n_nodes, max_depth);
+}
+int orc_build_lbvh_p(const float* prims, int prim_type, int n, int bits, int ref_norm, LinearNode* nodes, int* prim_order,
+                     uint64_t* keys_sorted, int* n_nodes, int* max_depth)
+{
+    Prims PV{prims, prim_type};
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int i = 0; i < n; ++i)
-        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], cxyz_r[4 * i + a]); hi[a] = std::max(hi[a], cxyz_r[4 * i + a]); }
+    for (int i = 0; i < n; ++i) {
+        V3 cc = PV.centre(i);
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], comp(cc, a)); hi[a] = std::max(hi[a], comp(cc, a)); }
+    }
     std::vector<std::pair<uint64_t, int>> kv(n);
     for (int i = 0; i < n; ++i) {
         float q[3];
+        V3 cc = PV.centre(i);
         for (int a = 0; a < 3; ++a) {
-            float c = cxyz_r[4 * i + a];
+            float c = comp(cc, a);
             if (ref_norm) q[a] = (c + 30.0f) / 1000.0f;
             else { float e = hi[a] - lo[a]; q[a] = e > 0.0f ? (c - lo[a]) / e : 0.0f; }
         }
@@ -613,7 +689,7 @@ int orc_build_lbvh(const float* cxyz_r, int n, int bits, int ref_norm, LinearNod
     std::stable_sort(kv.begin(), kv.end(), [](const std::pair<uint64_t, int>& a, const std::pair<uint64_t, int>& b) { return a.first < b.first; });
     std::vector<uint64_t> K(n);
     std::vector<Box> LB(n);
-    for (int i = 0; i < n; ++i) { K[i] = kv[i].first; prim_order[i] = kv[i].second; LB[i] = prim_box(cxyz_r + 4 * kv[i].second); if (keys_sorted) keys_sorted[i] = K[i]; }
+    for (int i = 0; i < n; ++i) { K[i] = kv[i].first; prim_order[i] = kv[i].second; LB[i] = PV.box(kv[i].second); if (keys_sorted) keys_sorted[i] = K[i]; }
     std::vector<LinearNode> out;
     out.reserve(2 * (size_t)n);
     LbvhBuilder B(K, LB, out, bits);
@@ -625,10 +701,18 @@ int orc_build_lbvh(const float* cxyz_r, int n, int bits, int ref_norm, LinearNod
 }
 
 // Closest hits of arbitrary rays. nodes == NULL -> NONE brute force.
+void orc_trace_p(const float* prims, int prim_type, int n, const LinearNode* nodes, const int* prim_order, int n_nodes, int tie_by_objid,
+                 const float* o, const float* d, int nrays, int* hit, float* t, long long* candidates);
 void orc_trace(const float* cxyz_r, int n, const LinearNode* nodes, const int* prim_order, int n_nodes, int tie_by_objid,
                const float* o, const float* d, int nrays, int* hit, float* t, long long* candidates)
 {
-    Scene S{cxyz_r, nullptr, n, nodes, prim_order, n_nodes, tie_by_objid};
+    orc_trace_p(cxyz_r, 0, n, nodes, prim_order, n_nodes, tie_by_objid, o, d, nrays, hit, t, candidates);
+}
+void orc_trace_p(const float* prims, int prim_type, int n, const LinearNode* nodes, const int* prim_order, int n_nodes, int tie_by_objid,
+                 const float* o, const float* d, int nrays, int* hit, float* t, long long* candidates)
+{
+    Scene S{prims, nullptr, n, nodes, prim_order, n_nodes, tie_by_objid};
+    S.prim_type = prim_type;
     long long cand = 0;
     for (int r = 0; r < nrays; ++r) {
         if (nodes) closest_bvh(S, o + 3 * r, d + 3 * r, hit[r], t[r], &cand);
@@ -650,7 +734,8 @@ void orc_render_rows_ex(const float* cxyz_r, const float* rgb_mat, int n, const 
                         int tie_by_objid, const float* lights7, int m, int width, int height, int spp, int y0, int y1,
                         int shadows, uint8_t* rgb8, int* hit_out, float* accum, float* dirs, long long* ray_counts3)
 {
-    Scene S{cxyz_r, rgb_mat, n, nodes, prim_order, n_nodes, tie_by_objid};
+    Scene S{cxyz_r, rgb_mat, n, nodes, prim_order, n_nodes, tie_by_objid & 1};
+    S.prim_type = (tie_by_objid >> 8) & 1;   // bit 8 of the flag word: the primitive table holds triangles (n x 9)
     std::vector<Light> L(m);
     for (int i = 0; i < m; ++i) {
         const float* l = lights7 + 7 * i;

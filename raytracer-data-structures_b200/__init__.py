@@ -165,6 +165,15 @@ class Rtds:
         self._check(self.lib.rtds_set_spheres(self.ctx, _ptr(cxyz_r), _ptr(rgb_mat), cxyz_r.shape[0]))
         self.n = cxyz_r.shape[0]
 
+    def set_triangles(self, v0v1v2, rgb_mat=None):
+        """Triangle scene (extension; the reference never instantiates class Triangle): (n, 9) float32."""
+        tris = np.ascontiguousarray(v0v1v2, np.float32).reshape(-1, 9)
+        if rgb_mat is not None:
+            rgb_mat = np.ascontiguousarray(rgb_mat, np.float32).reshape(-1, 4)
+            assert rgb_mat.shape[0] == tris.shape[0]
+        self._check(self.lib.rtds_set_triangles(self.ctx, _ptr(tris), _ptr(rgb_mat), tris.shape[0]))
+        self.n = tris.shape[0]
+
     def set_lights(self, lights7):
         lights7 = np.ascontiguousarray(lights7, np.float32).reshape(-1, 7)
         self._check(self.lib.rtds_set_lights(self.ctx, _ptr(lights7), lights7.shape[0]))

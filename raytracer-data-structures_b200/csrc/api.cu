@@ -43,7 +43,21 @@ void rtds_free_bvh(DeviceBvh& b)
     if (b.leaf_sph) cudaFree(b.leaf_sph);
     if (b.prim_order) cudaFree(b.prim_order);
     if (b.leaf_parent) cudaFree(b.leaf_parent);
+    if (b.leaf_tri) cudaFree(b.leaf_tri);
     b = DeviceBvh();
+}
+
+int rtds_alloc_bvh_for(rtds_ctx* ctx, DeviceBvh& b, int n_prims)
+{
+    RTDS_TRY(rtds_alloc_bvh(b, n_prims));
+    b.prim_type = ctx->prim_type;
+    if (ctx->prim_type == 1 && b.tri_capacity < n_prims) {
+        if (b.leaf_tri) cudaFree(b.leaf_tri);
+        b.leaf_tri = nullptr; b.tri_capacity = 0;
+        RTDS_CUDA(cudaMalloc(&b.leaf_tri, sizeof(float4) * 3 * (size_t)n_prims));
+        b.tri_capacity = n_prims;
+    }
+    return RTDS_OK;
 }
 
 // (Re)uses the arrays when they are large enough: cudaMalloc/cudaFree are device-wide synchronisation points and
@@ -139,6 +153,7 @@ int rtds_set_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int
     RTDS_CUDA(cudaSetDevice(c->device));
     RTDS_CUDA(cudaStreamSynchronize(c->stream));
     c->n = 0;
+    c->prim_type = 0;
     c->bvh.valid = false; c->kd.valid = false; c->bvh_acc = -1;
     if (c->sph_capacity < n) {
         if (c->d_sph) cudaFree(c->d_sph);
@@ -170,11 +185,47 @@ int rtds_set_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int
     return RTDS_OK;
 }
 
-int rtds_set_triangles(rtds_ctx* c, const float*, const float*, int)
+int rtds_set_triangles(rtds_ctx* c, const float* v0v1v2, const float* rgb_mat, int n)
 {
-    (void)c;
-    rtds_set_error("set_triangles: not implemented in this round");
-    return RTDS_ERR_UNSUPPORTED;
+    if (!c || !v0v1v2 || n <= 0) { rtds_set_error("set_triangles: bad arguments"); return RTDS_ERR_INVALID; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    c->n = 0;
+    c->bvh.valid = false; c->kd.valid = false; c->bvh_acc = -1;
+    if (c->tri_capacity < n) {
+        if (c->d_tris) cudaFree(c->d_tris);
+        c->d_tris = nullptr; c->tri_capacity = 0;
+        RTDS_CUDA(cudaMalloc(&c->d_tris, sizeof(float4) * 3 * (size_t)n));
+        c->tri_capacity = n;
+    }
+    if (c->sph_capacity < n) {   // the material table (and an unused sphere table of the same length) ride along
+        if (c->d_sph) cudaFree(c->d_sph);
+        if (c->d_mat) cudaFree(c->d_mat);
+        c->d_sph = nullptr; c->d_mat = nullptr; c->sph_capacity = 0;
+        RTDS_CUDA(cudaMalloc(&c->d_sph, sizeof(float4) * (size_t)n));
+        RTDS_CUDA(cudaMalloc(&c->d_mat, sizeof(float4) * (size_t)n));
+        c->sph_capacity = n;
+    }
+    std::vector<float> padded((size_t)n * 12);     // 9 floats -> 3 x float4 (16-byte vertex loads on the device)
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            padded[12 * (size_t)i + 4 * k] = v0v1v2[9 * (size_t)i + 3 * k];
+            padded[12 * (size_t)i + 4 * k + 1] = v0v1v2[9 * (size_t)i + 3 * k + 1];
+            padded[12 * (size_t)i + 4 * k + 2] = v0v1v2[9 * (size_t)i + 3 * k + 2];
+            padded[12 * (size_t)i + 4 * k + 3] = 0.f;
+        }
+    RTDS_CUDA(cudaMemcpyAsync(c->d_tris, padded.data(), sizeof(float4) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    std::vector<float> m((size_t)n * 4);
+    c->has_materials = false;
+    for (int i = 0; i < n; ++i) {
+        if (rgb_mat) { for (int k = 0; k < 4; ++k) m[4 * (size_t)i + k] = rgb_mat[4 * (size_t)i + k]; if (rgb_mat[4 * (size_t)i + 3] != 0.f) c->has_materials = true; }
+        else { m[4 * (size_t)i] = 0.8f; m[4 * (size_t)i + 1] = 0.7f; m[4 * (size_t)i + 2] = 0.f; m[4 * (size_t)i + 3] = 0.f; }
+    }
+    RTDS_CUDA(cudaMemcpyAsync(c->d_mat, m.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    c->prim_type = 1;
+    c->n = n;
+    return RTDS_OK;
 }
 
 int rtds_set_lights(rtds_ctx* c, const float* l, int m)
@@ -208,6 +259,7 @@ int rtds_build(rtds_ctx* c, int acc, const rtds_build_params* p, rtds_build_stat
         else {
             // accelerators.h:583: constructLBVHNew(objects, codes, 0, size()-1): the last object is dropped
             if (c->n < 2) { rtds_set_error("build: compat LBVH needs >= 2 objects (the reference drops the last one)"); return RTDS_ERR_INVALID; }
+            if (c->prim_type != 0) { rtds_set_error("build: compat LBVH (drop the last object) is defined for the reference's sphere scenes only"); return RTDS_ERR_UNSUPPORTED; }
             rc = rtds_build_median(c, c->n - 1, st);
         }
         break;

@@ -161,16 +161,16 @@ __global__ void kd_assign_slots(KdNode* nodes, int lvl_begin, int lvl_n, const i
 
 // :865-870 — one thread per list entry of the level
 __global__ void kd_gen_edges(const KdNode* __restrict__ nodes, const int* __restrict__ idx, const int* __restrict__ owner, int n_entries,
-                             const float4* __restrict__ sph, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals)
+                             const PrimView pv, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_entries) return;
     const KdNode& nd = nodes[owner[j]];
     if (nd.state != 0) return;
     int prim = idx[j];
-    float4 s = __ldg(sph + prim);
-    float c = nd.axis == 0 ? s.x : (nd.axis == 1 ? s.y : s.z);
-    float lo = c - s.w, hi = c + s.w;
+    float cc[3], mn[3], mx[3];
+    prim_fetch(pv, prim, cc, mn, mx);
+    float lo = mn[nd.axis], hi = mx[nd.axis];
     int e = nd.edge_start + 2 * (j - nd.prim_off);
     unsigned long long slot = (unsigned long long)nd.slot << 33;
     keys[e] = slot | ((unsigned long long)f2ord(lo) << 1) | 0ull;      // Start
@@ -417,7 +417,7 @@ template <typename T> T* carve(char*& p, size_t count)
 
 }  // namespace
 
-int rtds_build_kd(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats* st)
+static int build_kd_attempt(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats* st, size_t entries_per_prim)
 {
     const int n = ctx->n;
     KdParams P;
@@ -435,9 +435,9 @@ int rtds_build_kd(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats* 
     int launches = 0;
 
     // capacities: list entries per level are bounded in practice by a small multiple of n (PBRT reserves (depth+1)*n)
-    const size_t cap_entries = std::max<size_t>((size_t)n * 12, 1 << 16);
+    const size_t cap_entries = std::max<size_t>((size_t)n * entries_per_prim, 1 << 16);
     const size_t cap_edges = 2 * cap_entries;
-    const size_t cap_nodes = std::max<size_t>((size_t)n * 8, 1 << 12);
+    const size_t cap_nodes = std::max<size_t>((size_t)n * std::min<size_t>(entries_per_prim, 48), 1 << 12);
     const int scan_tiles = (int)((cap_edges + SC_TILE - 1) / SC_TILE) + 1;
     size_t bytes = 0;
     auto add = [&](size_t b) { bytes += (b + 255) & ~(size_t)255; };
@@ -509,7 +509,7 @@ int rtds_build_kd(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats* 
             ++launches;
             int slot_bits = 1; while ((1 << slot_bits) < n_slots) ++slot_bits;
             for (int round = 0; round < 3; ++round) {
-                kd_gen_edges<<<G(n_entries), T, 0, s>>>(nodes, idx[cur], owner[cur], n_entries, ctx->d_sph, keys, vals);
+                kd_gen_edges<<<G(n_entries), T, 0, s>>>(nodes, idx[cur], owner[cur], n_entries, rtds_prim_view(ctx), keys, vals);
                 ++launches;
                 RTDS_TRY(rtds_onesweep_sort_u64(ctx, (uint64_t*)keys, vals, (uint64_t*)keys_tmp, vals_tmp, n_edges, 33 + slot_bits, &launches));
                 if (((33 + slot_bits + 7) / 8) & 1) { /* odd pass count: rtds_onesweep_sort copies back */ }
@@ -607,4 +607,16 @@ int rtds_build_kd(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats* 
         st->ms = ms;
     }
     return RTDS_OK;
+}
+
+// List entries per level are bounded by (maxDepth+1)*n in PBRT's own allocation (accelerators.h:976); in practice
+// a few n for the reference's small spheres, more when primitives straddle many planes: grow and retry.
+int rtds_build_kd(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats* st)
+{
+    int rc = RTDS_ERR_CAPACITY;
+    for (size_t mult : {(size_t)12, (size_t)40, (size_t)128}) {
+        rc = build_kd_attempt(ctx, bp, st, mult);
+        if (rc != RTDS_ERR_CAPACITY) break;
+    }
+    return rc;
 }

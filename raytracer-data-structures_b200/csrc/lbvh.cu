@@ -20,19 +20,19 @@ __global__ void bounds_init_kernel(unsigned* out)
     if (i < 12) out[i] = ((i % 6) < 3) ? 0xffffffffu : 0u;
 }
 
-__global__ void __launch_bounds__(256) bounds_kernel(const float4* __restrict__ sph, int n, unsigned* __restrict__ out)
+__global__ void __launch_bounds__(256) bounds_kernel(const PrimView pv, int n, unsigned* __restrict__ out)
 {
     float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
     float bmin[3] = {INFINITY, INFINITY, INFINITY}, bmax[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 s = ldg4(sph + i);
-        float c[3] = {s.x, s.y, s.z};
+        float c[3], mn[3], mx[3];
+        prim_fetch(pv, i, c, mn, mx);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             cmin[a] = fminf(cmin[a], c[a]);
             cmax[a] = fmaxf(cmax[a], c[a]);
-            bmin[a] = fminf(bmin[a], c[a] - s.w);
-            bmax[a] = fmaxf(bmax[a], c[a] + s.w);
+            bmin[a] = fminf(bmin[a], mn[a]);
+            bmax[a] = fmaxf(bmax[a], mx[a]);
         }
     }
 #pragma unroll
@@ -101,12 +101,14 @@ __device__ __forceinline__ unsigned long long morton63(float x, float y, float z
 // ref_norm: (centre + 30) / 1000 (accelerators.h:577); else (centre - cmin) / (cmax - cmin) per axis.
 template <typename K>
 __global__ void __launch_bounds__(256)
-morton_kernel(const float4* __restrict__ sph, int n, const unsigned* __restrict__ bounds_ord, int ref_norm,
+morton_kernel(const PrimView pv, int n, const unsigned* __restrict__ bounds_ord, int ref_norm,
               K* __restrict__ keys, uint32_t* __restrict__ vals)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 s = ldg4(sph + i);
+    float c_[3], mn_[3], mx_[3];
+    prim_fetch(pv, i, c_, mn_, mx_);
+    const float3 s = make_float3(c_[0], c_[1], c_[2]);
     float x, y, z;
     if (ref_norm) {
         x = (s.x + 30.0f) / 1000.0f; y = (s.y + 30.0f) / 1000.0f; z = (s.z + 30.0f) / 1000.0f;
@@ -194,18 +196,17 @@ __device__ __forceinline__ void store_child_box(Node64* nd, int side, const floa
 }
 
 __global__ void __launch_bounds__(256)
-refit_kernel(const float4* __restrict__ sph, const uint32_t* __restrict__ sorted_ids, int n, Node64* nodes,
-             const int* __restrict__ leaf_parent, float4* __restrict__ leaf_sph, int* __restrict__ prim_order,
+refit_kernel(const PrimView pv, const uint32_t* __restrict__ sorted_ids, int n, Node64* nodes,
+             const int* __restrict__ leaf_parent, float4* __restrict__ leaf_sph, float4* __restrict__ leaf_tri, int* __restrict__ prim_order,
              unsigned* __restrict__ counters, float* __restrict__ root_box)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     int prim = (int)sorted_ids[j];
-    float4 s = ldg4(sph + prim);
-    leaf_sph[j] = make_float4(s.x, s.y, s.z, s.w * s.w);
+    prim_store_leaf(pv, prim, j, leaf_sph, leaf_tri);
     prim_order[j] = prim;
-    float mn[3] = {s.x - s.w, s.y - s.w, s.z - s.w};
-    float mx[3] = {s.x + s.w, s.y + s.w, s.z + s.w};
+    float cc[3], mn[3], mx[3];
+    prim_fetch(pv, prim, cc, mn, mx);
     if (n == 1) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) { root_box[a] = mn[a]; root_box[3 + a] = mx[a]; }
@@ -349,7 +350,7 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
     uint32_t* d_vals = (uint32_t*)(base + off_vals);
     uint32_t* d_vals_tmp = (uint32_t*)(base + off_vals_tmp);
 
-    RTDS_TRY(rtds_alloc_bvh(b, n));
+    RTDS_TRY(rtds_alloc_bvh_for(ctx, b, n));
     if (ctx->keys_capacity < n) {
         if (ctx->d_keys_sorted) cudaFree(ctx->d_keys_sorted);
         ctx->d_keys_sorted = nullptr;
@@ -363,8 +364,9 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
     const int T = 256;
     const int G = (n + T - 1) / T;
     bounds_init_kernel<<<1, 32, 0, s>>>(d_bounds);
-    bounds_kernel<<<min(G, ctx->sm_count * 8), T, 0, s>>>(ctx->d_sph, n, d_bounds);
-    morton_kernel<K><<<G, T, 0, s>>>(ctx->d_sph, n, d_bounds, p ? p->morton_ref_norm : 0, d_keys, d_vals);
+    const PrimView pv = rtds_prim_view(ctx);
+    bounds_kernel<<<min(G, ctx->sm_count * 8), T, 0, s>>>(pv, n, d_bounds);
+    morton_kernel<K><<<G, T, 0, s>>>(pv, n, d_bounds, p ? p->morton_ref_norm : 0, d_keys, d_vals);
     launches += 3;
     RTDS_TRY((sizeof(K) == 4)
                  ? rtds_onesweep_sort_u32(ctx, (uint32_t*)d_keys, d_vals, (uint32_t*)d_keys_tmp, d_vals_tmp, n, key_bits, &launches)
@@ -376,7 +378,7 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
         karras_kernel<K><<<(n - 1 + T - 1) / T, T, 0, s>>>(d_keys, n, b.nodes, b.leaf_parent);
         launches += 1;
     }
-    refit_kernel<<<G, T, 0, s>>>(ctx->d_sph, d_vals, n, b.nodes, b.leaf_parent, b.leaf_sph, b.prim_order, d_counters, d_root_box);
+    refit_kernel<<<G, T, 0, s>>>(pv, d_vals, n, b.nodes, b.leaf_parent, b.leaf_sph, b.leaf_tri, b.prim_order, d_counters, d_root_box);
     depth_kernel<<<G, T, 0, s>>>(b.nodes, b.leaf_parent, n, d_depth);
     widen_keys_kernel<K><<<G, T, 0, s>>>(d_keys, n, ctx->d_keys_sorted);
     launches += 3;
@@ -413,7 +415,7 @@ int rtds_scene_bounds(rtds_ctx* ctx, float out12[12])
     RTDS_TRY(rtds_ensure_scratch(ctx, 4096));
     unsigned* d_bounds = (unsigned*)((char*)ctx->d_scratch + ctx->scratch_bytes - 256);   // tail of the scratch area
     bounds_init_kernel<<<1, 32, 0, ctx->stream>>>(d_bounds);
-    bounds_kernel<<<min((ctx->n + 255) / 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->d_sph, ctx->n, d_bounds);
+    bounds_kernel<<<min((ctx->n + 255) / 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(rtds_prim_view(ctx), ctx->n, d_bounds);
     RTDS_CUDA(cudaGetLastError());
     unsigned h[12];
     RTDS_CUDA(cudaMemcpyAsync(h, d_bounds, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
@@ -431,8 +433,8 @@ int rtds_scene_bounds(rtds_ctx* ctx, float out12[12])
 int rtds_bvh_refit(rtds_ctx* ctx, DeviceBvh& b, const uint32_t* d_ids, int n, unsigned* d_counters, float* d_root_box)
 {
     RTDS_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned) * (size_t)n, ctx->stream));
-    refit_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_sph, d_ids, n, b.nodes, b.leaf_parent, b.leaf_sph, b.prim_order,
-                                                           d_counters, d_root_box);
+    refit_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(rtds_prim_view(ctx), d_ids, n, b.nodes, b.leaf_parent, b.leaf_sph, b.leaf_tri,
+                                                           b.prim_order, d_counters, d_root_box);
     RTDS_CUDA(cudaGetLastError());
     return RTDS_OK;
 }

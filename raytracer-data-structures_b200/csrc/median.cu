@@ -31,7 +31,8 @@ namespace {
 struct Task { int s, e, parent_enc; };   // parent_enc = parent*2+side, -1 for the root
 
 struct MedianArgs {
-    const float4* cen;       // objId -> {cx,cy,cz,r}
+    PrimView pv;             // objId -> centre / AABB
+    float4* leaf_tri_unused;
     int*   perm;             // scene position -> objId
     float* key;              // scene position -> centre[dim] of the task that owns the position
     int*   la;               // scratch lists, indexed by scene position
@@ -228,8 +229,8 @@ __device__ __forceinline__ void push_task(Task* next, int* next_count, int s, in
 // a size-1 child of interior node `node`: its box and its leaf record
 __device__ __forceinline__ void emit_single_leaf(const MedianArgs& A, int pos, int node, int side)
 {
-    float4 c = A.cen[A.perm[pos]];
-    float mn[3] = {c.x - c.w, c.y - c.w, c.z - c.w}, mx[3] = {c.x + c.w, c.y + c.w, c.z + c.w};
+    float cc[3], mn[3], mx[3];
+    prim_fetch(A.pv, A.perm[pos], cc, mn, mx);
     for (int i = 0; i < 6; ++i) write_box(A, node * 2 + side, mn, mx, i);
     A.leaf_info[pos] = node * 2 + side + 2;
 }
@@ -247,9 +248,9 @@ __device__ void subtree_sequential(const MedianArgs& A, Task root)
         const int s = t.s, e = t.e, m = e - s;
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (int p = s; p < e; ++p) {
-            float4 c = A.cen[A.perm[p]];
-            mn[0] = fminf(mn[0], c.x - c.w); mn[1] = fminf(mn[1], c.y - c.w); mn[2] = fminf(mn[2], c.z - c.w);
-            mx[0] = fmaxf(mx[0], c.x + c.w); mx[1] = fmaxf(mx[1], c.y + c.w); mx[2] = fmaxf(mx[2], c.z + c.w);
+            float cc[3], pmn[3], pmx[3];
+            prim_fetch(A.pv, A.perm[p], cc, pmn, pmx);
+            for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], pmn[a]); mx[a] = fmaxf(mx[a], pmx[a]); }
         }
         for (int i = 0; i < 6; ++i) write_box(A, t.parent_enc, mn, mx, i);
         if (m <= 1) { A.leaf_info[s] = t.parent_enc + 2; continue; }
@@ -258,8 +259,9 @@ __device__ void subtree_sequential(const MedianArgs& A, Task root)
         if (hi == lo) { atomicCAS(&A.counters[C_ERR], 0, RTDS_ERR_UNSUPPORTED); return; }
         const float pmid = (lo + hi) / 2;
         for (int p = s; p < e; ++p) {
-            float4 c = A.cen[A.perm[p]];
-            A.key[p] = dim == 0 ? c.x : (dim == 1 ? c.y : c.z);
+            float cc[3], pmn[3], pmx[3];
+            prim_fetch(A.pv, A.perm[p], cc, pmn, pmx);
+            A.key[p] = cc[dim];
         }
         int mid = seq_partition(A.key, A.perm, s, e, pmid);
         if (mid != s && mid != e) {
@@ -349,9 +351,10 @@ __global__ void __launch_bounds__(BLOCK) median_block_kernel(const MedianArgs A,
     {
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (int p = s + tid; p < e; p += BLOCK) {
-            float4 c = A.cen[perm[p]];
-            mn[0] = fminf(mn[0], c.x - c.w); mn[1] = fminf(mn[1], c.y - c.w); mn[2] = fminf(mn[2], c.z - c.w);
-            mx[0] = fmaxf(mx[0], c.x + c.w); mx[1] = fmaxf(mx[1], c.y + c.w); mx[2] = fmaxf(mx[2], c.z + c.w);
+            float cc[3], pmn[3], pmx[3];
+            prim_fetch(A.pv, perm[p], cc, pmn, pmx);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], pmn[a]); mx[a] = fmaxf(mx[a], pmx[a]); }
         }
 #pragma unroll
         for (int a = 0; a < 3; ++a)
@@ -382,8 +385,9 @@ __global__ void __launch_bounds__(BLOCK) median_block_kernel(const MedianArgs A,
     // 2. keys + std::partition(centre[dim] < pmid)
     int cT = 0;
     for (int p = s + tid; p < e; p += BLOCK) {
-        float4 c = A.cen[perm[p]];
-        float k = dim == 0 ? c.x : (dim == 1 ? c.y : c.z);
+        float cc[3], pmn[3], pmx[3];
+        prim_fetch(A.pv, perm[p], cc, pmn, pmx);
+        float k = cc[dim];
         key[p] = k;
         cT += (k < pmid) ? 1 : 0;
     }
@@ -475,9 +479,9 @@ __global__ void tile_scan_kernel(int* tile_counts, int tiles, int* total)
 }
 
 __global__ void __launch_bounds__(FIN_BLOCK)
-leaf_emit_kernel(const int* __restrict__ leaf_info, const int* __restrict__ perm, const float4* __restrict__ cen, int n,
-                 const int* __restrict__ tile_offsets, Node64* nodes, float4* __restrict__ leaf_sph, int* __restrict__ prim_order,
-                 int* __restrict__ leaf_parent, int* __restrict__ counters)
+leaf_emit_kernel(const int* __restrict__ leaf_info, const int* __restrict__ perm, const PrimView pv, int n,
+                 const int* __restrict__ tile_offsets, Node64* nodes, float4* __restrict__ leaf_sph, float4* __restrict__ leaf_tri,
+                 int* __restrict__ prim_order, int* __restrict__ leaf_parent, int* __restrict__ counters)
 {
     __shared__ int ws[FIN_BLOCK / 32];
     __shared__ int running;
@@ -498,8 +502,7 @@ leaf_emit_kernel(const int* __restrict__ leaf_info, const int* __restrict__ perm
         if (f) {
             const int r = start + woff + __popc(b & ((1u << lane) - 1u));
             const int obj = perm[p];
-            float4 c = cen[obj];
-            leaf_sph[r] = make_float4(c.x, c.y, c.z, c.w * c.w);
+            prim_store_leaf(pv, obj, r, leaf_sph, leaf_tri);
             prim_order[r] = obj;
             const int pe = info - 2;
             if (pe < 0) { leaf_parent[r] = 0; counters[C_ROOT] = ~r; }
@@ -531,7 +534,7 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
     b.valid = false;
     int small = 64;
     if (const char* e = getenv("RTDS_MEDIAN_SMALL")) small = atoi(e) > 0 ? atoi(e) : small;   // test hook: huge -> all sequential
-    RTDS_TRY(rtds_alloc_bvh(b, n));
+    RTDS_TRY(rtds_alloc_bvh_for(ctx, b, n));
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const int fin_tiles = (n + FIN_TILE - 1) / FIN_TILE;
     size_t o_perm = 0, o_key = o_perm + al(4 * (size_t)n), o_la = o_key + al(4 * (size_t)n), o_lb = o_la + al(4 * (size_t)n),
@@ -541,7 +544,7 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
     RTDS_TRY(rtds_ensure_scratch(ctx, total));
     char* base = (char*)ctx->d_scratch;
     MedianArgs A;
-    A.cen = ctx->d_sph;
+    A.pv = rtds_prim_view(ctx); A.leaf_tri_unused = nullptr;
     A.perm = (int*)(base + o_perm); A.key = (float*)(base + o_key); A.la = (int*)(base + o_la); A.lb = (int*)(base + o_lb);
     A.leaf_info = (int*)(base + o_info); A.nodes = b.nodes; A.root_box = (float*)(base + o_root); A.counters = (int*)(base + o_cnt);
     A.tasks_a = (Task*)(base + o_ta); A.tasks_b = (Task*)(base + o_tb);
@@ -582,7 +585,7 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
     }
     leaf_count_kernel<<<fin_tiles, FIN_BLOCK, 0, s>>>(A.leaf_info, n, d_tiles);
     tile_scan_kernel<<<1, 32, 0, s>>>(d_tiles, fin_tiles, A.counters + 5);
-    leaf_emit_kernel<<<fin_tiles, FIN_BLOCK, 0, s>>>(A.leaf_info, A.perm, A.cen, n, d_tiles, b.nodes, b.leaf_sph, b.prim_order,
+    leaf_emit_kernel<<<fin_tiles, FIN_BLOCK, 0, s>>>(A.leaf_info, A.perm, A.pv, n, d_tiles, b.nodes, b.leaf_sph, b.leaf_tri, b.prim_order,
                                                       b.leaf_parent, A.counters);
     launches += 3;
     RTDS_CUDA(cudaGetLastError());

@@ -179,6 +179,54 @@ __device__ __forceinline__ bool sphere_test(float ox, float oy, float oz, float 
     return true;
 }
 
+// Möller–Trumbore as written in the reference's (never compiled) MOLLER_TRUMBORE branch of
+// Triangle::rayTriangleIntersect (main.cpp:138-162, `v_0` read as v0, no culling, EPS = 1e-6 main.cpp:59), plus the
+// t < 0 rejection of its geometric branch (main.cpp:184). Extension: the reference never instantiates triangles.
+__device__ __forceinline__ bool tri_test(float ox, float oy, float oz, float dx, float dy, float dz, float4 v0, float4 v1, float4 v2,
+                                         float& t)
+{
+    const float e1x = v1.x - v0.x, e1y = v1.y - v0.y, e1z = v1.z - v0.z;
+    const float e2x = v2.x - v0.x, e2y = v2.y - v0.y, e2z = v2.z - v0.z;
+    const float px = dy * e2z - dz * e2y, py = dz * e2x - dx * e2z, pz = dx * e2y - dy * e2x;   // dir x v0v2
+    const float det = e1x * px + e1y * py + e1z * pz;
+    if (fabsf(det) < 1e-6f) return false;
+    const float inv = 1 / det;
+    const float tx = ox - v0.x, ty = oy - v0.y, tz = oz - v0.z;
+    const float u = (tx * px + ty * py + tz * pz) * inv;
+    if (u < 0 || u > 1) return false;
+    const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;   // tvec x v0v1
+    const float v = (dx * qx + dy * qy + dz * qz) * inv;
+    if (v < 0 || u + v > 1) return false;
+    t = (e2x * qx + e2y * qy + e2z * qz) * inv;
+    return !(t < 0);
+}
+
+// primitive test on an objId-indexed table (NONE loop, KD leaves)
+__device__ __forceinline__ bool obj_test(int type, const float4* __restrict__ sph, const float4* __restrict__ tri, int i, float ox, float oy,
+                                         float oz, float dx, float dy, float dz, float& t0, float& t1)
+{
+    if (type == 0) {
+        float4 s = __ldg(sph + i);
+        return sphere_test(ox, oy, oz, dx, dy, dz, make_float4(s.x, s.y, s.z, s.w * s.w), t0, t1);
+    }
+    float t;
+    if (!tri_test(ox, oy, oz, dx, dy, dz, __ldg(tri + 3 * (size_t)i), __ldg(tri + 3 * (size_t)i + 1), __ldg(tri + 3 * (size_t)i + 2), t)) return false;
+    t0 = t1 = t;
+    return true;
+}
+
+// un-normalised surface normal at the hit: spheres P - centre (main.cpp:398), triangles v0v1 x v0v2 (main.cpp:165-168)
+__device__ __forceinline__ void raw_normal(int type, const float4* __restrict__ sph_c /*centre in .xyz*/, const float4* __restrict__ tri,
+                                           size_t idx, float hx, float hy, float hz, float& nx, float& ny, float& nz)
+{
+    if (type == 0) { float4 s = __ldg(sph_c + idx); nx = hx - s.x; ny = hy - s.y; nz = hz - s.z; }
+    else {
+        float4 a = __ldg(tri + 3 * idx), b = __ldg(tri + 3 * idx + 1), c = __ldg(tri + 3 * idx + 2);
+        float e1x = b.x - a.x, e1y = b.y - a.y, e1z = b.z - a.z, e2x = c.x - a.x, e2y = c.y - a.y, e2z = c.z - a.z;
+        nx = e1y * e2z - e1z * e2y; ny = e1z * e2x - e1x * e2z; nz = e1x * e2y - e1y * e2x;
+    }
+}
+
 // candidate update of main.cpp:350-355 / :379-384 with the reference's "first candidate wins" made
 // order-independent: `key` is the candidate's position in the reference's candidate order.
 __device__ __forceinline__ void candidate(float t0, float t1, int key, int leaf, float& tnear, int& best_key, int& best_leaf)
@@ -192,6 +240,8 @@ __device__ __forceinline__ void candidate(float t0, float t1, int key, int leaf,
 struct BvhView {
     const Node64* nodes;
     const float4* leaf_sph;
+    const float4* leaf_tri;
+    int           prim_type;
     const int*    prim_order;
     const int*    leaf_parent;
     int           root_ref;
@@ -200,6 +250,18 @@ struct BvhView {
 };
 
 constexpr int STACK_MAX = 64;
+
+__device__ __forceinline__ bool leaf_test(const BvhView& B, int leaf, float ox, float oy, float oz, float dx, float dy, float dz, float& t0,
+                                          float& t1)
+{
+    if (B.prim_type == 0) return sphere_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_sph + leaf), t0, t1);
+    float t;
+    if (!tri_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_tri + 3 * (size_t)leaf), __ldg(B.leaf_tri + 3 * (size_t)leaf + 1),
+                  __ldg(B.leaf_tri + 3 * (size_t)leaf + 2), t))
+        return false;
+    t0 = t1 = t;
+    return true;
+}
 
 // pruning margin for the ordered traversal: bounds the float error of raySphereIntersect's t0 against the
 // true entry distance for any sphere inside the root box (DESIGN.md "Ordered traversal is exact").
@@ -246,7 +308,7 @@ __device__ __forceinline__ void traverse_bvh(const BvhView& B, float ox, float o
     if (B.root_ref < 0) {
         float t0, t1;
         cnt.prim_tests++;
-        if (sphere_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_sph), t0, t1))
+        if (leaf_test(B, 0, ox, oy, oz, dx, dy, dz, t0, t1))
             candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order) : 0, 0, tnear, best_key, best_leaf);
         return;
     }
@@ -288,7 +350,7 @@ __device__ __forceinline__ void traverse_bvh(const BvhView& B, float ox, float o
             int leaf = ~left;
             float t0, t1;
             cnt.prim_tests++;
-            if (sphere_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_sph + leaf), t0, t1))
+            if (leaf_test(B, leaf, ox, oy, oz, dx, dy, dz, t0, t1))
                 candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
             hitL = false;
         }
@@ -296,7 +358,7 @@ __device__ __forceinline__ void traverse_bvh(const BvhView& B, float ox, float o
             int leaf = ~right;
             float t0, t1;
             cnt.prim_tests++;
-            if (sphere_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_sph + leaf), t0, t1))
+            if (leaf_test(B, leaf, ox, oy, oz, dx, dy, dz, t0, t1))
                 candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
             hitR = false;
         }
@@ -401,7 +463,7 @@ __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float 
             if (slab_test(ox, oy, oz, dx, dy, dz, bx0, by0, bz0, bx1, by1, bz1, a, b2)) {
                 float t0, t1;
                 cnt.prim_tests++;
-                if (sphere_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_sph + leaf), t0, t1)) {
+                if (leaf_test(B, leaf, ox, oy, oz, dx, dy, dz, t0, t1)) {
                     candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
                     tlim = tnear + margin;
                 }
@@ -424,22 +486,31 @@ __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float 
 
 // NONE: main.cpp:376-386, spheres staged through shared memory by the whole block (all threads must call).
 constexpr int NONE_CHUNK = 1024;
-__device__ __forceinline__ void brute_force_block(const float4* __restrict__ sph /*objId order {c,r}*/, int n, bool active,
+__device__ __forceinline__ void brute_force_block(int type, const float4* __restrict__ sph /*objId order {c,r}*/,
+                                                  const float4* __restrict__ tri, int n, bool active,
                                                   float ox, float oy, float oz, float dx, float dy, float dz, float& tnear,
                                                   int& best, Counters& cnt, float4* sh)
 {
-    for (int base = 0; base < n; base += NONE_CHUNK) {
-        int m = min(NONE_CHUNK, n - base);
+    const int chunk = type == 0 ? NONE_CHUNK : NONE_CHUNK / 3;
+    for (int base = 0; base < n; base += chunk) {
+        int m = min(chunk, n - base);
         __syncthreads();
-        for (int i = threadIdx.x; i < m; i += blockDim.x) {
-            float4 s = __ldg(sph + base + i);
-            sh[i] = make_float4(s.x, s.y, s.z, s.w * s.w);
+        if (type == 0) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                float4 s = __ldg(sph + base + i);
+                sh[i] = make_float4(s.x, s.y, s.z, s.w * s.w);
+            }
+        } else {
+            for (int i = threadIdx.x; i < 3 * m; i += blockDim.x) sh[i] = __ldg(tri + 3 * (size_t)base + i);
         }
         __syncthreads();
         if (active) {
             for (int i = 0; i < m; ++i) {
                 float t0, t1;
-                if (sphere_test(ox, oy, oz, dx, dy, dz, sh[i], t0, t1)) {
+                bool h;
+                if (type == 0) h = sphere_test(ox, oy, oz, dx, dy, dz, sh[i], t0, t1);
+                else { float t; h = tri_test(ox, oy, oz, dx, dy, dz, sh[3 * i], sh[3 * i + 1], sh[3 * i + 2], t); t0 = t1 = t; }
+                if (h) {
                     if (t0 < 0) t0 = t1;
                     if (t0 < tnear) { tnear = t0; best = base + i; }
                 }
@@ -456,6 +527,8 @@ struct KdView {
     const rtds_kd_node* nodes;
     const int*          prim_idx;
     const float4*       sph;       // objId-indexed {c, r} (kdtreeAllSceneObjects)
+    const float4*       tri;       // objId-indexed v0,v1,v2 (extension)
+    int                 prim_type;
     float               bounds[6];
 };
 
@@ -477,17 +550,15 @@ __device__ __forceinline__ bool kd_any_hit(const KdView& K, float ox, float oy, 
         if ((nd.w1 & 3u) == 3u) {
             const int np = (int)nd.w2;
             if (np == 1) {
-                float4 sp = __ldg(K.sph + (int)nd.w0);
                 float t0, t1;
                 cnt.prim_tests++;
-                if (sphere_test(ox, oy, oz, dx, dy, dz, make_float4(sp.x, sp.y, sp.z, sp.w * sp.w), t0, t1)) return true;
+                if (obj_test(K.prim_type, K.sph, K.tri, (int)nd.w0, ox, oy, oz, dx, dy, dz, t0, t1)) return true;
             } else {
                 for (int i = 0; i < np; ++i) {
                     int prim = __ldg(K.prim_idx + (int)nd.w0 + i);
-                    float4 sp = __ldg(K.sph + prim);
                     float t0, t1;
                     cnt.prim_tests++;
-                    if (sphere_test(ox, oy, oz, dx, dy, dz, make_float4(sp.x, sp.y, sp.z, sp.w * sp.w), t0, t1)) return true;
+                    if (obj_test(K.prim_type, K.sph, K.tri, prim, ox, oy, oz, dx, dy, dz, t0, t1)) return true;
                 }
             }
             if (todoPos > 0) { --todoPos; node = todo_node[todoPos]; tMin = todo_tmin[todoPos]; tMax = todo_tmax[todoPos]; }
@@ -542,13 +613,10 @@ __device__ __forceinline__ float pow25f(float xf)
     return (float)(x16 * x8 * x);
 }
 
-__device__ __forceinline__ void shade_diffuse(const ShadeParams& P, float ox, float oy, float oz, float dx, float dy,
-                                              float dz, float tnear, float cx, float cy, float cz, float sr, float sg,
-                                              float sb, float& r, float& g, float& b)
+__device__ __forceinline__ void shade_diffuse(const ShadeParams& P, float dx, float dy, float dz, float hx, float hy, float hz,
+                                              float nx, float ny, float nz, float sr, float sg, float sb, float& r, float& g, float& b)
 {
-    // hitPoint = rayorig + raydir * tnear; nhit = normalize(hitPoint - centre); flip towards the ray
-    float hx = ox + dx * tnear, hy = oy + dy * tnear, hz = oz + dz * tnear;
-    float nx = hx - cx, ny = hy - cy, nz = hz - cz;
+    // (hx,hy,hz) = rayorig + raydir * tnear; (nx,ny,nz) = hitPoint - centre (un-normalised): normalise, flip towards the ray
     normalize3(nx, ny, nz);
     if (dx * nx + dy * ny + dz * nz > 0) { nx = -nx; ny = -ny; nz = -nz; }
     float hr = 0, hg = 0, hb = 0;
@@ -587,6 +655,8 @@ struct RenderArgs {
     BvhView bvh;
     KdView  kd;
     const float4* sph;           // objId-indexed {c, r}
+    const float4* tri;           // objId-indexed v0,v1,v2 (triangle scenes)
+    int           prim_type;
     const float4* mat;           // objId-indexed {rgb, material}
     int           n;             // primitive count for NONE
     ShadeParams   shade;
@@ -629,20 +699,14 @@ __global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
         }
         float tnear = INFINITY;
         int best_key = 0, best_leaf = -1, hit_obj = -1;
-        float cx = 0, cy = 0, cz = 0;
         if (MODE == 2) {
-            brute_force_block(A.sph, A.n, active, 0.f, 0.f, 0.f, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
-            if (hit_obj >= 0) { float4 s = __ldg(A.sph + hit_obj); cx = s.x; cy = s.y; cz = s.z; }
+            brute_force_block(A.prim_type, A.sph, A.tri, A.n, active, 0.f, 0.f, 0.f, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
         } else if (MODE == 3) {
             if (active) hit_obj = kd_any_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, cnt) ? 1 : -1;
         } else if (active) {
             if (MODE == 0) traverse_bvh<true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
             else traverse_fast<true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
-            if (best_leaf >= 0) {
-                hit_obj = __ldg(A.bvh.prim_order + best_leaf);
-                float4 s = __ldg(A.bvh.leaf_sph + best_leaf);
-                cx = s.x; cy = s.y; cz = s.z;
-            }
+            if (best_leaf >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf);
         }
         if (active) {
             float r, g, b;
@@ -650,7 +714,11 @@ __global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
             else if (MODE == 3) { r = 0.f; g = 0.f; b = 0.f; }       // main.cpp:369: a KD hit is black
             else {
                 float4 m = __ldg(A.mat + hit_obj);
-                shade_diffuse(A.shade, 0.f, 0.f, 0.f, dx, dy, dz, tnear, cx, cy, cz, m.x, m.y, m.z, r, g, b);
+                const float hx = 0.f + dx * tnear, hy = 0.f + dy * tnear, hz = 0.f + dz * tnear;     // main.cpp:396
+                float nx, ny, nz;
+                if (MODE == 2) raw_normal(A.prim_type, A.sph, A.tri, (size_t)hit_obj, hx, hy, hz, nx, ny, nz);
+                else raw_normal(A.bvh.prim_type, A.bvh.leaf_sph, A.bvh.leaf_tri, (size_t)best_leaf, hx, hy, hz, nx, ny, nz);
+                shade_diffuse(A.shade, dx, dy, dz, hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b);
             }
             acc_r += r; acc_g += g; acc_b += b;
             last_hit = hit_obj;
@@ -713,16 +781,15 @@ __device__ __forceinline__ void refract_dir(float ix, float iy, float iz, float 
 
 template <int MODE>
 __device__ __forceinline__ void closest_hit(const RenderArgs& A, float ox, float oy, float oz, float dx, float dy, float dz, float& tnear,
-                                            int& hit_obj, float& cx, float& cy, float& cz, Counters& cnt)
+                                            int& hit_obj, int& hit_leaf, Counters& cnt)
 {
-    tnear = INFINITY; hit_obj = -1;
+    tnear = INFINITY; hit_obj = -1; hit_leaf = -1;
     if (MODE == 2) {   // main.cpp:376-386, straight from global memory (all lanes read the same address)
         for (int i = 0; i < A.n; ++i) {
-            float4 s = __ldg(A.sph + i);
             float t0, t1;
-            if (sphere_test(ox, oy, oz, dx, dy, dz, make_float4(s.x, s.y, s.z, s.w * s.w), t0, t1)) {
+            if (obj_test(A.prim_type, A.sph, A.tri, i, ox, oy, oz, dx, dy, dz, t0, t1)) {
                 if (t0 < 0) t0 = t1;
-                if (t0 < tnear) { tnear = t0; hit_obj = i; cx = s.x; cy = s.y; cz = s.z; }
+                if (t0 < tnear) { tnear = t0; hit_obj = i; }
             }
         }
         cnt.prim_tests += A.n;
@@ -731,11 +798,7 @@ __device__ __forceinline__ void closest_hit(const RenderArgs& A, float ox, float
         float len2 = dx * dx + dy * dy + dz * dz;
         if (MODE == 0 || !(fabsf(len2 - 1.0f) < 1e-3f)) traverse_bvh<true>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
         else traverse_fast<false>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
-        if (best_leaf >= 0) {
-            hit_obj = __ldg(A.bvh.prim_order + best_leaf);
-            float4 s = __ldg(A.bvh.leaf_sph + best_leaf);
-            cx = s.x; cy = s.y; cz = s.z;
-        }
+        if (best_leaf >= 0) { hit_obj = __ldg(A.bvh.prim_order + best_leaf); hit_leaf = best_leaf; }
     }
 }
 
@@ -769,16 +832,18 @@ __global__ void __launch_bounds__(128) render_full_kernel(const RenderArgs A)
             int nmult = 0;
             for (int depth = 1;; ++depth) {
                 if (depth > A.shade.max_depth) break;                        // main.cpp:311-313: sky
-                float tnear, cx = 0, cy = 0, cz = 0;
-                int hit_obj;
-                closest_hit<MODE>(A, ox, oy, oz, dx, dy, dz, tnear, hit_obj, cx, cy, cz, cnt);
+                float tnear;
+                int hit_obj, hit_leaf;
+                closest_hit<MODE>(A, ox, oy, oz, dx, dy, dz, tnear, hit_obj, hit_leaf, cnt);
                 cnt.rays++;
                 if (depth == 1) last_hit = hit_obj;
                 if (hit_obj < 0) break;                                      // sky
                 const float4 m = __ldg(A.mat + hit_obj);
                 const int material = (int)m.w;
                 float hx = ox + dx * tnear, hy = oy + dy * tnear, hz = oz + dz * tnear;
-                float nx = hx - cx, ny = hy - cy, nz = hz - cz;
+                float nx, ny, nz;
+                if (MODE == 2) raw_normal(A.prim_type, A.sph, A.tri, (size_t)hit_obj, hx, hy, hz, nx, ny, nz);
+                else raw_normal(A.bvh.prim_type, A.bvh.leaf_sph, A.bvh.leaf_tri, (size_t)hit_leaf, hx, hy, hz, nx, ny, nz);
                 normalize3(nx, ny, nz);
                 if (dx * nx + dy * ny + dz * nz > 0) { nx = -nx; ny = -ny; nz = -nz; }
                 if (material == RTDS_REFLECTION_AND_REFRACTION) {            // main.cpp:418-434
@@ -814,9 +879,9 @@ __global__ void __launch_bounds__(128) render_full_kernel(const RenderArgs A)
                         float sx = front ? hx + nx * bias : hx - nx * bias;
                         float sy = front ? hy + ny * bias : hy - ny * bias;
                         float sz = front ? hz + nz * bias : hz - nz * bias;
-                        float ts, ux, uy, uz;
-                        int sh;
-                        closest_hit<MODE>(A, sx, sy, sz, lx, ly, lz, ts, sh, ux, uy, uz, cnt);
+                        float ts;
+                        int sh, shl;
+                        closest_hit<MODE>(A, sx, sy, sz, lx, ly, lz, ts, sh, shl, cnt);
                         cnt.rays++;
                         shadow_rays++;
                         if (sh >= 0 && ts * ts < dist2) lit = 0.0f;           // main.cpp:471-472
@@ -861,7 +926,7 @@ struct TraceArgs {
     const float* o; const float* d; int nrays;
     BvhView bvh;
     KdView kd;
-    const float4* sph; int n;
+    const float4* sph; const float4* tri; int prim_type; int n;
     int* hit; float* t;
     unsigned long long* counters;
     int exact;
@@ -883,7 +948,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A)
     float tnear = INFINITY;
     int best_key = 0, best_leaf = -1, hit_obj = -1;
     if (MODE == 2) {
-        brute_force_block(A.sph, A.n, active, ox, oy, oz, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
+        brute_force_block(A.prim_type, A.sph, A.tri, A.n, active, ox, oy, oz, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
     } else if (MODE == 3) {
         if (active) { hit_obj = kd_any_hit(A.kd, ox, oy, oz, dx, dy, dz, cnt) ? 1 : -1; tnear = 0.f; }
     } else if (active) {
@@ -907,7 +972,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A)
 BvhView make_view(const DeviceBvh& b)
 {
     BvhView v;
-    v.nodes = b.nodes; v.leaf_sph = b.leaf_sph; v.prim_order = b.prim_order; v.leaf_parent = b.leaf_parent;
+    v.nodes = b.nodes; v.leaf_sph = b.leaf_sph; v.prim_order = b.prim_order; v.leaf_parent = b.leaf_parent; v.leaf_tri = b.leaf_tri; v.prim_type = b.prim_type;
     v.root_ref = b.root_ref; v.tie_by_objid = b.tie_by_objid;
     for (int i = 0; i < 6; ++i) v.root_box[i] = b.root_box[i];
     return v;
@@ -916,7 +981,7 @@ BvhView make_view(const DeviceBvh& b)
 KdView make_kd_view(const rtds_ctx* ctx)
 {
     KdView v;
-    v.nodes = ctx->kd.nodes; v.prim_idx = ctx->kd.prim_idx; v.sph = ctx->d_sph;
+    v.nodes = ctx->kd.nodes; v.prim_idx = ctx->kd.prim_idx; v.sph = ctx->d_sph; v.tri = ctx->d_tris; v.prim_type = ctx->prim_type;
     for (int i = 0; i < 6; ++i) v.bounds[i] = ctx->kd.bounds[i];
     return v;
 }
@@ -1022,7 +1087,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.inv_w = 1 / float(W); A.inv_h = 1 / float(H);
     A.aspect = W / float(H);
     A.angle = (float)tan(3.141592653589793 * 0.5 * fov / 180.);
-    A.n = ctx->n; A.sph = ctx->d_sph; A.mat = ctx->d_mat;
+    A.n = ctx->n; A.sph = ctx->d_sph; A.tri = ctx->d_tris; A.prim_type = ctx->prim_type; A.mat = ctx->d_mat;
     if (!brute && !kdt) A.bvh = make_view(ctx->bvh); else A.bvh = BvhView();
     if (kdt) A.kd = make_kd_view(ctx); else A.kd = KdView();
     A.shade.n_lights = ctx->n_lights;
@@ -1110,7 +1175,7 @@ int rtds_trace_impl(rtds_ctx* ctx, int acc, int exact, const float* h_o, const f
     A.o = d_o; A.d = d_d; A.nrays = nrays;
     if (!brute && !kdt) A.bvh = make_view(ctx->bvh); else A.bvh = BvhView();
     if (kdt) A.kd = make_kd_view(ctx); else A.kd = KdView();
-    A.sph = ctx->d_sph; A.n = ctx->n; A.hit = d_hit; A.t = d_t; A.counters = ctx->d_counters; A.exact = exact;
+    A.sph = ctx->d_sph; A.tri = ctx->d_tris; A.prim_type = ctx->prim_type; A.n = ctx->n; A.hit = d_hit; A.t = d_t; A.counters = ctx->d_counters; A.exact = exact;
     RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
     if (kdt) trace_kernel<3><<<(nrays + 127) / 128, 128, 0, s>>>(A);
     else if (brute) trace_kernel<2><<<(nrays + 127) / 128, 128, 0, s>>>(A);

@@ -55,6 +55,9 @@ struct DeviceBvh {
     int      root_ref = 0;         // 0 (interior node 0) or ~0 when the tree is a single leaf
     Node64*  nodes = nullptr;      // [n_internal]
     float4*  leaf_sph = nullptr;   // [n_prims] {cx,cy,cz,r^2} in leaf order (radius2 = r*r, accelerators.h:71)
+    float4*  leaf_tri = nullptr;   // [3*n_prims] v0,v1,v2 in leaf order when the scene holds triangles (extension)
+    int      tri_capacity = 0;
+    int      prim_type = 0;        // 0 spheres, 1 triangles
     int*     prim_order = nullptr; // [n_prims] leafpos -> objId
     int*     leaf_parent = nullptr;// [n_prims] interior parent of each leaf (bit 31 set: right child)
     float    root_box[6] = {0, 0, 0, 0, 0, 0};
@@ -93,9 +96,10 @@ struct rtds_ctx {
     int     n_lights = 0;
     RtdsLight lights[RTDS_MAX_LIGHTS];
 
-    // triangles (extension)
-    int     n_tris = 0;
-    float*  d_tris = nullptr;
+    // triangles (extension): objId-indexed v0,v1,v2 as 3 float4 per triangle; prim_type selects the primitive table
+    int     prim_type = 0;           // 0 spheres (d_sph), 1 triangles (d_tris)
+    int     tri_capacity = 0;
+    float4* d_tris = nullptr;
 
     DeviceBvh bvh;               // last BVH/LBVH build
     int       bvh_acc = -1;      // acc type that produced `bvh`
@@ -128,6 +132,13 @@ struct rtds_ctx {
     uint8_t* h_pinned = nullptr;     // pinned host staging for D2H of frames
     size_t   pinned_bytes = 0;
 };
+
+// The builders see primitives through this view: a centre (split / Morton key) and an AABB.
+//   spheres   : centre = c, box = c -/+ r in float (main.cpp:686-688)
+//   triangles : box = min/max of the vertices, centre = (min + max) * 0.5f          (extension)
+struct PrimView { int type; const float4* sph; const float4* tri; };
+inline PrimView rtds_prim_view(const rtds_ctx* c) { return PrimView{c->prim_type, c->d_sph, c->d_tris}; }
+int rtds_alloc_bvh_for(rtds_ctx* ctx, DeviceBvh& b, int n_prims);
 
 int rtds_ensure_scratch(rtds_ctx* ctx, size_t bytes);
 template <typename T> int rtds_realloc(T** p, size_t* cap_bytes, size_t need_bytes);
@@ -182,4 +193,29 @@ __device__ __forceinline__ float ord2f(unsigned u)
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+__device__ __forceinline__ void prim_fetch(const PrimView& pv, int i, float c[3], float mn[3], float mx[3])
+{
+    if (pv.type == 0) {
+        float4 s = __ldg(pv.sph + i);
+        c[0] = s.x; c[1] = s.y; c[2] = s.z;
+        mn[0] = s.x - s.w; mn[1] = s.y - s.w; mn[2] = s.z - s.w;
+        mx[0] = s.x + s.w; mx[1] = s.y + s.w; mx[2] = s.z + s.w;
+    } else {
+        float4 a = __ldg(pv.tri + 3 * (size_t)i), b = __ldg(pv.tri + 3 * (size_t)i + 1), d = __ldg(pv.tri + 3 * (size_t)i + 2);
+        mn[0] = fminf(fminf(a.x, b.x), d.x); mn[1] = fminf(fminf(a.y, b.y), d.y); mn[2] = fminf(fminf(a.z, b.z), d.z);
+        mx[0] = fmaxf(fmaxf(a.x, b.x), d.x); mx[1] = fmaxf(fmaxf(a.y, b.y), d.y); mx[2] = fmaxf(fmaxf(a.z, b.z), d.z);
+        c[0] = (mn[0] + mx[0]) * 0.5f; c[1] = (mn[1] + mx[1]) * 0.5f; c[2] = (mn[2] + mx[2]) * 0.5f;
+    }
+}
+// leaf payload in leaf order: spheres {c, r^2}; triangles v0,v1,v2
+__device__ __forceinline__ void prim_store_leaf(const PrimView& pv, int prim, int leafpos, float4* leaf_sph, float4* leaf_tri)
+{
+    if (pv.type == 0) {
+        float4 s = __ldg(pv.sph + prim);
+        leaf_sph[leafpos] = make_float4(s.x, s.y, s.z, s.w * s.w);
+    } else {
+        for (int k = 0; k < 3; ++k) leaf_tri[3 * (size_t)leafpos + k] = __ldg(pv.tri + 3 * (size_t)prim + k);
+    }
+}
 #endif

@@ -46,16 +46,17 @@ __global__ void sah_reset(SahTask* tasks, SahBins* bins, int n_tasks, int B)
     }
 }
 
-__global__ void sah_centre_bounds(const int* __restrict__ perm, const int* __restrict__ owner, int n, const float4* __restrict__ sph, SahTask* tasks)
+__global__ void sah_centre_bounds(const int* __restrict__ perm, const int* __restrict__ owner, int n, const PrimView pv, SahTask* tasks)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     int t = owner[p];
     if (t < 0) return;
-    float4 c = __ldg(sph + perm[p]);
+    float c[3], mn[3], mx[3];
+    prim_fetch(pv, perm[p], c, mn, mx);
     unsigned* cb = tasks[t].cb;
-    atomicMin(&cb[0], f2ord(c.x)); atomicMin(&cb[1], f2ord(c.y)); atomicMin(&cb[2], f2ord(c.z));
-    atomicMax(&cb[3], f2ord(c.x)); atomicMax(&cb[4], f2ord(c.y)); atomicMax(&cb[5], f2ord(c.z));
+    atomicMin(&cb[0], f2ord(c[0])); atomicMin(&cb[1], f2ord(c[1])); atomicMin(&cb[2], f2ord(c[2]));
+    atomicMax(&cb[3], f2ord(c[0])); atomicMax(&cb[4], f2ord(c[1])); atomicMax(&cb[5], f2ord(c[2]));
 }
 
 __device__ __forceinline__ int sah_axis(const unsigned cb[6], float& lo, float& hi)
@@ -67,27 +68,28 @@ __device__ __forceinline__ int sah_axis(const unsigned cb[6], float& lo, float& 
     return axis;
 }
 
-__global__ void sah_binning(const int* __restrict__ perm, const int* __restrict__ owner, int n, const float4* __restrict__ sph,
+__global__ void sah_binning(const int* __restrict__ perm, const int* __restrict__ owner, int n, const PrimView pv,
                             const SahTask* __restrict__ tasks, SahBins* bins, int* __restrict__ bin_of, int B)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     int t = owner[p];
     if (t < 0) return;
-    float4 c = __ldg(sph + perm[p]);
+    float c[3], mn[3], mx[3];
+    prim_fetch(pv, perm[p], c, mn, mx);
     float lo, hi;
     int axis = sah_axis(tasks[t].cb, lo, hi);
     int b = 0;
     if (hi > lo) {
-        float k = (axis == 0 ? c.x : (axis == 1 ? c.y : c.z));
+        float k = c[axis];
         b = (int)((float)B * ((k - lo) / (hi - lo)));
         if (b > B - 1) b = B - 1;
     }
     bin_of[p] = b;
     atomicAdd(&bins[t].cnt[b], 1u);
     unsigned* bx = bins[t].box[b];
-    atomicMin(&bx[0], f2ord(c.x - c.w)); atomicMin(&bx[1], f2ord(c.y - c.w)); atomicMin(&bx[2], f2ord(c.z - c.w));
-    atomicMax(&bx[3], f2ord(c.x + c.w)); atomicMax(&bx[4], f2ord(c.y + c.w)); atomicMax(&bx[5], f2ord(c.z + c.w));
+    atomicMin(&bx[0], f2ord(mn[0])); atomicMin(&bx[1], f2ord(mn[1])); atomicMin(&bx[2], f2ord(mn[2]));
+    atomicMax(&bx[3], f2ord(mx[0])); atomicMax(&bx[4], f2ord(mx[1])); atomicMax(&bx[5], f2ord(mx[2]));
 }
 
 __device__ __forceinline__ float box_area(const float mn[3], const float mx[3])   // BoxBoundries::SurfaceArea, accelerators.h:122-125
@@ -262,7 +264,8 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats*
     const int n = ctx->n;
     const int B = (bp && bp->sah_bins > 1) ? std::min(bp->sah_bins, MAXB) : 16;
     DeviceBvh& b = ctx->bvh;
-    RTDS_TRY(rtds_alloc_bvh(b, n));
+    RTDS_TRY(rtds_alloc_bvh_for(ctx, b, n));
+    const PrimView pv = rtds_prim_view(ctx);
     const size_t max_tasks = (size_t)n / 2 + 2;
     const int tiles = (int)(((size_t)std::max<size_t>(n, 2 * max_tasks) + SC_TILE - 1) / SC_TILE) + 1;
     size_t bytes = 6 * (((size_t)n * 4 + 255) & ~(size_t)255) + 2 * ((sizeof(SahTask) * max_tasks + 255) & ~(size_t)255) +
@@ -311,8 +314,8 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats*
     while (n_tasks > 0) {
         SahTask* tk = tasks[cur];
         sah_reset<<<G(n_tasks), T, 0, s>>>(tk, bins, n_tasks, B);
-        sah_centre_bounds<<<G(n), T, 0, s>>>(perm[cur], owner[cur], n, ctx->d_sph, tk);
-        sah_binning<<<G(n), T, 0, s>>>(perm[cur], owner[cur], n, ctx->d_sph, tk, bins, bin_of, B);
+        sah_centre_bounds<<<G(n), T, 0, s>>>(perm[cur], owner[cur], n, pv, tk);
+        sah_binning<<<G(n), T, 0, s>>>(perm[cur], owner[cur], n, pv, tk, bins, bin_of, B);
         sah_decide<<<G(n_tasks), T, 0, s>>>(tk, bins, n_tasks, B, node_base, child_flags);
         launches += 4;
         RTDS_TRY(xscan(child_flags, child_scan, 2 * n_tasks));

@@ -71,13 +71,13 @@ class Oracle:
         assert got == n
         return sph, mat
 
-    def build_bvh(self, sph, n_use=None):
+    def build_bvh(self, sph, n_use=None, prim_type=0):
         sph = np.ascontiguousarray(sph, np.float32)
         n_use = sph.shape[0] if n_use is None else n_use
         nodes = np.zeros(2 * n_use - 1, LINEAR)
         order = np.zeros(n_use, np.int32)
         nn, md = C.c_int(), C.c_int()
-        rc = self.lib.orc_build_bvh(self._p(sph), n_use, self._p(nodes), self._p(order), C.byref(nn), C.byref(md))
+        rc = self.lib.orc_build_bvh_p(self._p(sph), prim_type, n_use, self._p(nodes), self._p(order), C.byref(nn), C.byref(md))
         if rc != 0:
             return rc, None, None, 0
         nodes = nodes[:nn.value]
@@ -89,25 +89,25 @@ class Oracle:
         nodes["offset"][leaf] = np.arange(order.shape[0], dtype=np.int32)
         return 0, nodes, order, md.value
 
-    def build_lbvh(self, sph, bits=30, ref_norm=0):
+    def build_lbvh(self, sph, bits=30, ref_norm=0, prim_type=0):
         sph = np.ascontiguousarray(sph, np.float32)
         n = sph.shape[0]
         nodes = np.zeros(2 * n - 1, LINEAR)
         order = np.zeros(n, np.int32)
         keys = np.zeros(n, np.uint64)
         nn, md = C.c_int(), C.c_int()
-        rc = self.lib.orc_build_lbvh(self._p(sph), n, bits, ref_norm, self._p(nodes), self._p(order), self._p(keys),
-                                     C.byref(nn), C.byref(md))
+        rc = self.lib.orc_build_lbvh_p(self._p(sph), prim_type, n, bits, ref_norm, self._p(nodes), self._p(order), self._p(keys),
+                                       C.byref(nn), C.byref(md))
         assert rc == 0
         return nodes[:nn.value], order, keys, md.value
 
-    def build_sah(self, sph, bins=16):
+    def build_sah(self, sph, bins=16, prim_type=0):
         sph = np.ascontiguousarray(sph, np.float32)
         n = sph.shape[0]
         nodes = np.zeros(2 * n - 1, LINEAR)
         order = np.zeros(n, np.int32)
         nn, md = C.c_int(), C.c_int()
-        self.lib.orc_build_sah(self._p(sph), n, bins, self._p(nodes), self._p(order), C.byref(nn), C.byref(md))
+        self.lib.orc_build_sah_p(self._p(sph), prim_type, n, bins, self._p(nodes), self._p(order), C.byref(nn), C.byref(md))
         return nodes[:nn.value], order, md.value
 
     def morton30(self, xyz):
@@ -116,7 +116,7 @@ class Oracle:
         self.lib.orc_morton30(self._p(xyz), xyz.shape[0], self._p(codes))
         return codes
 
-    def trace(self, sph, nodes, order, o, d, tie_by_objid=0):
+    def trace(self, sph, nodes, order, o, d, tie_by_objid=0, prim_type=0):
         sph = np.ascontiguousarray(sph, np.float32)
         o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
         d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
@@ -126,8 +126,8 @@ class Oracle:
         hit = np.zeros(n, np.int32)
         t = np.zeros(n, np.float32)
         cand = C.c_longlong()
-        self.lib.orc_trace(self._p(sph), sph.shape[0], self._p(nodes), self._p(order), 0 if nodes is None else nodes.shape[0],
-                           tie_by_objid, self._p(o), self._p(d), n, self._p(hit), self._p(t), C.byref(cand))
+        self.lib.orc_trace_p(self._p(sph), prim_type, sph.shape[0], self._p(nodes), self._p(order), 0 if nodes is None else nodes.shape[0],
+                             tie_by_objid, self._p(o), self._p(d), n, self._p(hit), self._p(t), C.byref(cand))
         return hit, t, cand.value
 
     def jitter(self, n, first=0):
@@ -136,7 +136,7 @@ class Oracle:
         return out
 
     def render_rows(self, sph, mat, nodes, order, width, height, spp, y0=0, y1=None, tie_by_objid=0, lights=None,
-                    want_hit=True, want_accum=False, want_dirs=False, shadows=0):
+                    want_hit=True, want_accum=False, want_dirs=False, shadows=0, prim_type=0):
         y1 = height if y1 is None else y1
         sph = np.ascontiguousarray(sph, np.float32)
         mat = np.ascontiguousarray(mat, np.float32)
@@ -148,7 +148,7 @@ class Oracle:
         dirs = np.zeros((rows, width, spp, 3), np.float32) if want_dirs else None
         counts = np.zeros(3, np.int64)
         self.lib.orc_render_rows_ex(self._p(sph), self._p(mat), sph.shape[0], self._p(nodes), self._p(order),
-                                    0 if nodes is None else nodes.shape[0], tie_by_objid, self._p(lights), lights.shape[0],
+                                    0 if nodes is None else nodes.shape[0], tie_by_objid | (prim_type << 8), self._p(lights), lights.shape[0],
                                     width, height, spp, y0, y1, int(shadows), self._p(rgb), self._p(hit), self._p(accum),
                                     self._p(dirs), self._p(counts))
         self.last_ray_counts = counts
@@ -299,6 +299,20 @@ def synthetic_scene(n, seed=1, ground=True, radius=0.05):
     mat = np.zeros_like(sph)
     mat[:n, 0], mat[:n, 1] = 0.8, 0.7
     return sph, mat
+
+
+def triangle_scene(n, seed, ground=True):
+    """Seeded soup of small triangles in front of the camera (+ two large ground triangles): (m, 9) and (m, 4)."""
+    rng = np.random.default_rng(seed)
+    c = rng.normal(size=(n, 1, 3)).astype(np.float32) * np.float32(4.0) + np.asarray([0, 0, -60], np.float32)
+    v = c + rng.normal(size=(n, 3, 3)).astype(np.float32) * np.float32(0.6)
+    tris = v.reshape(n, 9)
+    if ground:
+        g = np.asarray([[-60, -8, -20, 60, -8, -20, 60, -8, -140], [-60, -8, -20, 60, -8, -140, -60, -8, -140]], np.float32)
+        tris = np.concatenate([tris, g], 0)
+    mat = np.zeros((tris.shape[0], 4), np.float32)
+    mat[:, :3] = rng.uniform(0.1, 0.9, size=(tris.shape[0], 3)).astype(np.float32)
+    return np.ascontiguousarray(tris, np.float32), mat
 
 
 def material_scene(n, seed, frac_rr=0.1, frac_refl=0.1, big=True):
