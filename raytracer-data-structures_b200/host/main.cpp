@@ -8,6 +8,8 @@
 //   RTDS_GPUS             1,2,4,8: interleaved scanline tiles, one context + one host thread per GPU
 //   RTDS_EXACT=1          reference traversal (visit every node whose slab test passes) instead of the ordered one
 //   RTDS_LBVH_MODE        compat (default: what the reference's LBVH code does) | true (Morton/Karras LBVH)
+//   RTDS_PRIMS=triangles  extension: read `f` lines too and render the mesh's triangles (Moller-Trumbore) instead of one
+//                         sphere per vertex; vertices get the same transform as the sphere centres (main.cpp:680-682)
 //   RTDS_OUT              output file (default ./output.ppm)
 #include <chrono>
 #include <cstdlib>
@@ -81,6 +83,27 @@ int main(int, char**)
 
 	HostScene scene;
 	if (!create_scene(settings, models_dir, clones, scene)) return 1;
+	const bool triangles = getenv("RTDS_PRIMS") && !strcmp(getenv("RTDS_PRIMS"), "triangles");
+	std::vector<float> tri_mat;
+	if (triangles) {
+		std::vector<float> v;
+		std::vector<int> f;
+		std::string path = std::string(models_dir) + "/" + model_file_name(settings.sceneModel);
+		if (!load_obj(path, true, v, f) || f.empty()) {
+			std::cerr << "RTDS_PRIMS=triangles: " << path << " has no `f` lines (the reference's models are vertex-only)" << endl;
+			return 1;
+		}
+		for (size_t k = 0; k + 2 < f.size(); k += 3)
+			for (int c = 0; c < 3; ++c) {
+				const float* p = &v[3 * (size_t)f[k + c]];
+				scene.tris.push_back(p[0] * 100);
+				scene.tris.push_back(p[1] * 100 + -10);
+				scene.tris.push_back(p[2] * 100 + -60);
+			}
+		tri_mat.assign(scene.tris.size() / 9 * 4, 0.f);
+		for (size_t i = 0; i < tri_mat.size() / 4; ++i) { tri_mat[4 * i] = 0.8f; tri_mat[4 * i + 1] = 0.7f; }
+		cout << "Number of triangles: " << scene.tris.size() / 9 << endl;
+	}
 
 	cout << "Wraping BV for each object .... \n";
 	cout << "Done .... \n Time: ";
@@ -90,7 +113,8 @@ int main(int, char**)
 	std::vector<rtds_ctx*> ctx(n_gpus, nullptr);
 	for (int g = 0; g < n_gpus; ++g) {
 		CHECK(rtds_create(&ctx[g], g));
-		CHECK(rtds_set_spheres(ctx[g], scene.cxyz_r.data(), scene.rgb_mat.data(), scene.n()));
+		if (triangles) CHECK(rtds_set_triangles(ctx[g], scene.tris.data(), tri_mat.data(), (int)(scene.tris.size() / 9)));
+		else CHECK(rtds_set_spheres(ctx[g], scene.cxyz_r.data(), scene.rgb_mat.data(), scene.n()));
 	}
 
 	rtds_build_params bp;

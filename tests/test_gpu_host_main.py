@@ -1,0 +1,65 @@
+"""GPU: the C++ drop-in driver (host/main.cpp -> rtds_main) end to end: same log lines as the reference's main(),
+and with settings.h's defaults an output.ppm byte-identical to the reference's shipped one."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import conftest as T
+
+rt = T.rtds_b200
+G = T.load_golden_json()
+pytestmark = pytest.mark.gpu
+MAIN = os.path.join(T.PKG_DIR, "rtds_main")
+
+
+def _models(tmp_path):
+    d = tmp_path / "models"
+    d.mkdir()
+    with open(d / "bunny.obj", "w") as f:
+        for x, y, z in T.bunny_vertices():
+            f.write("v %.9g %.9g %.9g\n" % (x, y, z))
+    return d
+
+
+def _run(tmp_path, **env):
+    e = dict(os.environ, RTDS_MODELS_DIR=str(tmp_path / "models"), RTDS_OUT=str(tmp_path / "out.ppm"))
+    e.update({k: str(v) for k, v in env.items()})
+    r = subprocess.run([MAIN], env=e, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout, open(tmp_path / "out.ppm", "rb").read()
+
+
+def test_default_settings_reproduce_output_ppm(tmp_path):
+    if not os.path.exists(MAIN):
+        pytest.skip("rtds_main not built")
+    _models(tmp_path)
+    out, ppm = _run(tmp_path)
+    assert hashlib.md5(ppm).hexdigest() == "c69c66375f2c6bda433f9f457a4b2b2e"      # = /root/reference/project/raytracer/output.ppm
+    for line in ("Start rendering ....", "Height: 480", "Width: 640", "DataStructure: 0", "Anti-aliasing samples: 1",
+                 "Number of spheres: 35947", "<<<<<<< This is BVH >>>>>>", "Total number of nodes: 71895",
+                 "--------- Rendering Completed ---------"):
+        assert line in out, line
+    out, ppm = _run(tmp_path, RTDS_EXACT=1)
+    assert hashlib.md5(ppm).hexdigest() == "c69c66375f2c6bda433f9f457a4b2b2e"
+    assert "Number of Sphere intersection tests: 323685 test" in out               # the reference's own statistic
+
+
+@pytest.mark.parametrize("ds,md5key", [(3, "LBVH"), (1, "KDTREE"), (4, "NONE")])
+def test_other_data_structures_match_reference_frames(tmp_path, ds, md5key):
+    if not os.path.exists(MAIN):
+        pytest.skip("rtds_main not built")
+    _models(tmp_path)
+    out, ppm = _run(tmp_path, RTDS_DS=ds)
+    assert hashlib.md5(ppm).hexdigest() == G["default_config"][md5key]["ppm_md5"]
+
+
+def test_multi_gpu_in_one_process(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2 or not os.path.exists(MAIN):
+        pytest.skip("needs 2 GPUs")
+    _models(tmp_path)
+    out, ppm = _run(tmp_path, RTDS_GPUS=2)
+    assert hashlib.md5(ppm).hexdigest() == "c69c66375f2c6bda433f9f457a4b2b2e"
