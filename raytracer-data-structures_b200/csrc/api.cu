@@ -20,7 +20,7 @@ int rtds_ensure_scratch(rtds_ctx* ctx, size_t bytes)
     if (ctx->scratch_bytes >= bytes) return RTDS_OK;
     if (ctx->d_scratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_scratch); }
     ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
-    size_t want = bytes + bytes / 8 + 4096;
+    size_t want = (bytes + bytes / 8 + 8192) & ~(size_t)4095;
     RTDS_CUDA(cudaMalloc(&ctx->d_scratch, want));
     ctx->scratch_bytes = want;
     return RTDS_OK;

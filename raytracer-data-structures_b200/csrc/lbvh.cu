@@ -413,7 +413,7 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
 int rtds_scene_bounds(rtds_ctx* ctx, float out12[12])
 {
     RTDS_TRY(rtds_ensure_scratch(ctx, 4096));
-    unsigned* d_bounds = (unsigned*)((char*)ctx->d_scratch + ctx->scratch_bytes - 256);   // tail of the scratch area
+    unsigned* d_bounds = (unsigned*)((char*)ctx->d_scratch + ((ctx->scratch_bytes - 512) & ~(size_t)255));   // aligned tail of the scratch area
     bounds_init_kernel<<<1, 32, 0, ctx->stream>>>(d_bounds);
     bounds_kernel<<<min((ctx->n + 255) / 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(rtds_prim_view(ctx), ctx->n, d_bounds);
     RTDS_CUDA(cudaGetLastError());

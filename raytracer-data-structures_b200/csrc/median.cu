@@ -410,6 +410,7 @@ __global__ void __launch_bounds__(BLOCK) median_block_kernel(const MedianArgs A,
         int first = s, last = e, depth_limit = lg2(m) * 2;
         while (last - first > 3) {
             if (depth_limit == 0) {
+                if (tid == 0) { atomicAdd(&A.counters[7], 1); atomicAdd(&A.counters[8], last - first); }
                 if (tid == 0) { seq_heap_select(key, perm, first, nth + 1, last); swp(key, perm, first, nth); }
                 first = last = nth;   // done (skip the insertion sort below, as the reference returns here)
                 break;
@@ -589,7 +590,7 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
                                                       b.leaf_parent, A.counters);
     launches += 3;
     RTDS_CUDA(cudaGetLastError());
-    int h_cnt[8];
+    int h_cnt[12];
     RTDS_CUDA(cudaMemcpyAsync(h_cnt, A.counters, sizeof h_cnt, cudaMemcpyDeviceToHost, s));
     RTDS_CUDA(cudaMemcpyAsync(b.root_box, A.root_box, sizeof(float) * 6, cudaMemcpyDeviceToHost, s));
     RTDS_CUDA(cudaStreamSynchronize(s));
@@ -601,6 +602,7 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
         rtds_set_error("median-split build: a range has zero extent on its longest axis (accelerators.h:286-293 pushes unrelated ids); unsupported");
         return RTDS_ERR_UNSUPPORTED;
     }
+    if (getenv("RTDS_MEDIAN_DEBUG")) fprintf(stderr, "[median] heap-select fallbacks: %d (elements %d)\n", h_cnt[7], h_cnt[8]);
     const int n_leaves = h_cnt[5], n_internal = h_cnt[C_NODES];
     if (n_leaves != n_internal + 1) { rtds_set_error("median-split build: internal error (%d leaves, %d interior)", n_leaves, n_internal); return RTDS_ERR_CUDA; }
     b.n_prims = n_leaves;

@@ -46,17 +46,37 @@ __global__ void sah_reset(SahTask* tasks, SahBins* bins, int n_tasks, int B)
     }
 }
 
-__global__ void sah_centre_bounds(const int* __restrict__ perm, const int* __restrict__ owner, int n, const PrimView pv, SahTask* tasks)
+// Blocks whose 256 positions all belong to ONE task (every block of the upper levels) reduce in registers / shared
+// memory first and touch the task's global words once per block; mixed blocks use the global atomics directly.
+// Both paths are exact (min/max and integer adds are order-independent).
+__global__ void __launch_bounds__(256) sah_centre_bounds(const int* __restrict__ perm, const int* __restrict__ owner, int n, const PrimView pv,
+                                                         SahTask* tasks)
 {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    int t = owner[p];
-    if (t < 0) return;
-    float c[3], mn[3], mx[3];
-    prim_fetch(pv, perm[p], c, mn, mx);
-    unsigned* cb = tasks[t].cb;
-    atomicMin(&cb[0], f2ord(c[0])); atomicMin(&cb[1], f2ord(c[1])); atomicMin(&cb[2], f2ord(c[2]));
-    atomicMax(&cb[3], f2ord(c[0])); atomicMax(&cb[4], f2ord(c[1])); atomicMax(&cb[5], f2ord(c[2]));
+    __shared__ int s_first, s_uniform;
+    __shared__ unsigned s_cb[6];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = p < n ? owner[p] : -2;
+    if (threadIdx.x == 0) { s_first = t; s_uniform = 1; for (int a = 0; a < 3; ++a) { s_cb[a] = 0xffffffffu; s_cb[3 + a] = 0u; } }
+    __syncthreads();
+    if (t != s_first && t != -2) s_uniform = 0;
+    __syncthreads();
+    float c[3] = {0, 0, 0}, mn[3], mx[3];
+    const bool act = t >= 0;
+    if (act) prim_fetch(pv, perm[p], c, mn, mx);
+    if (s_uniform && s_first >= 0) {
+        unsigned lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) { lo[a] = act ? f2ord(c[a]) : 0xffffffffu; hi[a] = act ? f2ord(c[a]) : 0u; }
+        for (int o = 16; o; o >>= 1)
+            for (int a = 0; a < 3; ++a) { lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o)); hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o)); }
+        if ((threadIdx.x & 31) == 0) for (int a = 0; a < 3; ++a) { atomicMin(&s_cb[a], lo[a]); atomicMax(&s_cb[3 + a], hi[a]); }
+        __syncthreads();
+        if (threadIdx.x < 3) atomicMin(&tasks[s_first].cb[threadIdx.x], s_cb[threadIdx.x]);
+        else if (threadIdx.x < 6) atomicMax(&tasks[s_first].cb[threadIdx.x], s_cb[threadIdx.x]);
+    } else if (act) {
+        unsigned* cb = tasks[t].cb;
+        atomicMin(&cb[0], f2ord(c[0])); atomicMin(&cb[1], f2ord(c[1])); atomicMin(&cb[2], f2ord(c[2]));
+        atomicMax(&cb[3], f2ord(c[0])); atomicMax(&cb[4], f2ord(c[1])); atomicMax(&cb[5], f2ord(c[2]));
+    }
 }
 
 __device__ __forceinline__ int sah_axis(const unsigned cb[6], float& lo, float& hi)
@@ -68,28 +88,52 @@ __device__ __forceinline__ int sah_axis(const unsigned cb[6], float& lo, float& 
     return axis;
 }
 
-__global__ void sah_binning(const int* __restrict__ perm, const int* __restrict__ owner, int n, const PrimView pv,
-                            const SahTask* __restrict__ tasks, SahBins* bins, int* __restrict__ bin_of, int B)
+__global__ void __launch_bounds__(256) sah_binning(const int* __restrict__ perm, const int* __restrict__ owner, int n, const PrimView pv,
+                                                   const SahTask* __restrict__ tasks, SahBins* bins, int* __restrict__ bin_of, int B)
 {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    int t = owner[p];
-    if (t < 0) return;
-    float c[3], mn[3], mx[3];
-    prim_fetch(pv, perm[p], c, mn, mx);
-    float lo, hi;
-    int axis = sah_axis(tasks[t].cb, lo, hi);
+    __shared__ int s_first, s_uniform;
+    __shared__ unsigned s_cnt[MAXB];
+    __shared__ unsigned s_box[MAXB][6];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = p < n ? owner[p] : -2;
+    if (threadIdx.x == 0) { s_first = t; s_uniform = 1; }
+    if (threadIdx.x < MAXB) { s_cnt[threadIdx.x] = 0; for (int a = 0; a < 3; ++a) { s_box[threadIdx.x][a] = 0xffffffffu; s_box[threadIdx.x][3 + a] = 0u; } }
+    __syncthreads();
+    if (t != s_first && t != -2) s_uniform = 0;
+    __syncthreads();
+    const bool act = t >= 0;
     int b = 0;
-    if (hi > lo) {
-        float k = c[axis];
-        b = (int)((float)B * ((k - lo) / (hi - lo)));
-        if (b > B - 1) b = B - 1;
+    float c[3], mn[3], mx[3];
+    if (act) {
+        prim_fetch(pv, perm[p], c, mn, mx);
+        float lo, hi;
+        int axis = sah_axis(tasks[t].cb, lo, hi);
+        if (hi > lo) {
+            float k = c[axis];
+            b = (int)((float)B * ((k - lo) / (hi - lo)));
+            if (b > B - 1) b = B - 1;
+        }
+        bin_of[p] = b;
     }
-    bin_of[p] = b;
-    atomicAdd(&bins[t].cnt[b], 1u);
-    unsigned* bx = bins[t].box[b];
-    atomicMin(&bx[0], f2ord(mn[0])); atomicMin(&bx[1], f2ord(mn[1])); atomicMin(&bx[2], f2ord(mn[2]));
-    atomicMax(&bx[3], f2ord(mx[0])); atomicMax(&bx[4], f2ord(mx[1])); atomicMax(&bx[5], f2ord(mx[2]));
+    if (s_uniform && s_first >= 0) {
+        if (act) {
+            atomicAdd(&s_cnt[b], 1u);
+            atomicMin(&s_box[b][0], f2ord(mn[0])); atomicMin(&s_box[b][1], f2ord(mn[1])); atomicMin(&s_box[b][2], f2ord(mn[2]));
+            atomicMax(&s_box[b][3], f2ord(mx[0])); atomicMax(&s_box[b][4], f2ord(mx[1])); atomicMax(&s_box[b][5], f2ord(mx[2]));
+        }
+        __syncthreads();
+        if (threadIdx.x < B && s_cnt[threadIdx.x]) {
+            SahBins& g = bins[s_first];
+            const int bb = threadIdx.x;
+            atomicAdd(&g.cnt[bb], s_cnt[bb]);
+            for (int a = 0; a < 3; ++a) { atomicMin(&g.box[bb][a], s_box[bb][a]); atomicMax(&g.box[bb][3 + a], s_box[bb][3 + a]); }
+        }
+    } else if (act) {
+        atomicAdd(&bins[t].cnt[b], 1u);
+        unsigned* bx = bins[t].box[b];
+        atomicMin(&bx[0], f2ord(mn[0])); atomicMin(&bx[1], f2ord(mn[1])); atomicMin(&bx[2], f2ord(mn[2]));
+        atomicMax(&bx[3], f2ord(mx[0])); atomicMax(&bx[4], f2ord(mx[1])); atomicMax(&bx[5], f2ord(mx[2]));
+    }
 }
 
 __device__ __forceinline__ float box_area(const float mn[3], const float mx[3])   // BoxBoundries::SurfaceArea, accelerators.h:122-125
