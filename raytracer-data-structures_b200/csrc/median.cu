@@ -25,6 +25,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -334,6 +335,46 @@ __device__ int block_sum(BlockShared<BLOCK>& S, int v)
     return t;
 }
 
+// __introselect (stl_algo.h:1957-1980) on [first,last) by one thread block; `s` is the owning task's start (the
+// scratch lists live at la+s / lb+s). Also the tail of the cooperative kernel's rounds once a range is small.
+template <int BLOCK>
+__device__ void block_introselect(BlockShared<BLOCK>& S, const MedianArgs& A, int s, int first, int last, int nth, int depth_limit)
+{
+    const int tid = threadIdx.x;
+    float* key = A.key;
+    int* perm = A.perm;
+    while (last - first > 3) {
+        if (depth_limit == 0) {
+            if (tid == 0) { atomicAdd(&A.counters[7], 1); atomicAdd(&A.counters[8], last - first); }
+            if (tid == 0) { seq_heap_select(key, perm, first, nth + 1, last); swp(key, perm, first, nth); }
+            first = last = nth;   // done (skip the insertion sort below, as the reference returns here)
+            break;
+        }
+        --depth_limit;
+        if (tid == 0) seq_move_median_to_first(key, perm, first, first + 1, first + (last - first) / 2, last - 1);
+        __syncthreads();
+        const float v = key[first];
+        const int lo_p = first + 1;
+        int* L = A.la + s;
+        int* R = A.lb + s;   // ascending; R_desc[i] = R[nR-1-i]
+        const int nL = block_compact(S, lo_p, last, [&](int p) { return !(key[p] < v); }, L);
+        const int nR = block_compact(S, lo_p, last, [&](int p) { return !(v < key[p]); }, R);
+        const int nmin = min(nL, nR);
+        int kc = 0;
+        for (int i = tid; i < nmin; i += BLOCK) kc += (L[i] < R[nR - 1 - i]) ? 1 : 0;
+        const int k = block_sum(S, kc);
+        int cut;
+        if (k == 0) cut = L[0];
+        else cut = min(k < nL ? L[k] : INT_MAX, R[nR - k]);
+        __syncthreads();   // everyone has read L/R heads before the swaps move keys (lists are position lists: safe)
+        for (int i = tid; i < k; i += BLOCK) swp(key, perm, L[i], R[nR - 1 - i]);
+        __syncthreads();
+        if (cut <= nth) first = cut; else last = cut;
+    }
+    if (tid == 0 && last - first > 0) seq_insertion_sort(key, perm, first, last);
+    __syncthreads();
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) median_block_kernel(const MedianArgs A, const Task* __restrict__ tasks,
                                                              const int* __restrict__ count, Task* __restrict__ next,
@@ -406,39 +447,7 @@ __global__ void __launch_bounds__(BLOCK) median_block_kernel(const MedianArgs A,
 
     // 3. std::nth_element(first, first + m/2, last): __introselect
     const int nth = (s + e) / 2;
-    {
-        int first = s, last = e, depth_limit = lg2(m) * 2;
-        while (last - first > 3) {
-            if (depth_limit == 0) {
-                if (tid == 0) { atomicAdd(&A.counters[7], 1); atomicAdd(&A.counters[8], last - first); }
-                if (tid == 0) { seq_heap_select(key, perm, first, nth + 1, last); swp(key, perm, first, nth); }
-                first = last = nth;   // done (skip the insertion sort below, as the reference returns here)
-                break;
-            }
-            --depth_limit;
-            if (tid == 0) seq_move_median_to_first(key, perm, first, first + 1, first + (last - first) / 2, last - 1);
-            __syncthreads();
-            const float v = key[first];
-            const int lo_p = first + 1;
-            int* L = A.la + s;
-            int* R = A.lb + s;   // ascending; R_desc[i] = R[nR-1-i]
-            const int nL = block_compact(S, lo_p, last, [&](int p) { return !(key[p] < v); }, L);
-            const int nR = block_compact(S, lo_p, last, [&](int p) { return !(v < key[p]); }, R);
-            const int nmin = min(nL, nR);
-            int kc = 0;
-            for (int i = tid; i < nmin; i += BLOCK) kc += (L[i] < R[nR - 1 - i]) ? 1 : 0;
-            const int k = block_sum(S, kc);
-            int cut;
-            if (k == 0) cut = L[0];
-            else cut = min(k < nL ? L[k] : INT_MAX, R[nR - k]);
-            __syncthreads();   // everyone has read L/R heads before the swaps move keys (lists are position lists: safe)
-            for (int i = tid; i < k; i += BLOCK) swp(key, perm, L[i], R[nR - 1 - i]);
-            __syncthreads();
-            if (cut <= nth) first = cut; else last = cut;
-        }
-        if (tid == 0 && last - first > 0) seq_insertion_sort(key, perm, first, last);
-        __syncthreads();
-    }
+    block_introselect<BLOCK>(S, A, s, s, e, nth, lg2(m) * 2);
 
     // 4. node + children
     if (tid == 0) {
@@ -449,6 +458,182 @@ __global__ void __launch_bounds__(BLOCK) median_block_kernel(const MedianArgs A,
         const int mid = nth;
         if (mid - s == 1) emit_single_leaf(A, s, node, 0); else push_task(next, next_count, s, mid, node * 2);
         if (e - mid == 1) emit_single_leaf(A, mid, node, 1); else push_task(next, next_count, mid, e, node * 2 + 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cooperative kernel for the few huge ranges at the top of the tree: the WHOLE grid works on one task at a time.
+// Same algorithm as median_block_kernel; every streaming pass is split over the blocks (contiguous slices, so lists
+// stay in ascending position order), with grid-wide barriers between the dependent steps. Ranges that have shrunk
+// below COOP_TAIL are finished by block 0 with the block-level code.
+// ---------------------------------------------------------------------------------------------------
+constexpr int COOP_BLOCK = 1024;
+constexpr int COOP_TAIL = 16384;
+
+struct CoopScratch {          // global, zeroed per launch
+    unsigned box[6];          // ordered uints
+    int      cnt[4];          // general counters
+    int      blk[2][1024];    // per-block counts of the two lists
+};
+
+__device__ __forceinline__ void slice_of(int lo, int hi, int& a, int& b)
+{
+    const long long len = hi - lo;
+    const long long chunk = (len + gridDim.x - 1) / gridDim.x;
+    a = (int)min((long long)hi, lo + chunk * blockIdx.x);
+    b = (int)min((long long)hi, lo + chunk * (blockIdx.x + 1));
+}
+
+// two simultaneous ascending compactions over [lo,hi): list 0 -> out0, list 1 -> out1; returns counts
+template <typename F0, typename F1>
+__device__ void grid_compact2(cooperative_groups::grid_group& grid, BlockShared<COOP_BLOCK>& S, CoopScratch* G, int lo, int hi, F0 f0, F1 f1,
+                              int* __restrict__ out0, int* __restrict__ out1, int& n0, int& n1)
+{
+    int a, b;
+    slice_of(lo, hi, a, b);
+    int c0 = 0, c1 = 0;
+    for (int p = a + threadIdx.x; p < b; p += COOP_BLOCK) { c0 += f0(p) ? 1 : 0; c1 += f1(p) ? 1 : 0; }
+    c0 = block_sum(S, c0);
+    c1 = block_sum(S, c1);
+    if (threadIdx.x == 0) { G->blk[0][blockIdx.x] = c0; G->blk[1][blockIdx.x] = c1; }
+    grid.sync();
+    int o0 = 0, o1 = 0, t0 = 0, t1 = 0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += COOP_BLOCK) {
+        int x0 = G->blk[0][i], x1 = G->blk[1][i];
+        t0 += x0; t1 += x1;
+        if (i < (int)blockIdx.x) { o0 += x0; o1 += x1; }
+    }
+    o0 = block_sum(S, o0); o1 = block_sum(S, o1); t0 = block_sum(S, t0); t1 = block_sum(S, t1);
+    block_compact(S, a, b, f0, out0 + o0);
+    block_compact(S, a, b, f1, out1 + o1);
+    n0 = t0; n1 = t1;
+    grid.sync();
+}
+
+__global__ void __launch_bounds__(COOP_BLOCK) median_coop_kernel(const MedianArgs A, const Task* __restrict__ tasks, const int* __restrict__ count,
+                                                                 Task* __restrict__ next, int* __restrict__ next_count, CoopScratch* G)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ BlockShared<COOP_BLOCK> S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool lead = blockIdx.x == 0 && tid == 0;
+    float* key = A.key;
+    int* perm = A.perm;
+    const int n_tasks = *count;
+    for (int ti = 0; ti < n_tasks; ++ti) {
+        if (A.counters[C_ERR]) return;          // uniform: set before a grid barrier, read after it
+        const Task t = tasks[ti];
+        const int s = t.s, e = t.e, m = e - s;
+        if (lead) { for (int a = 0; a < 3; ++a) { G->box[a] = 0xffffffffu; G->box[3 + a] = 0u; } G->cnt[0] = 0; G->cnt[1] = 0; }
+        grid.sync();
+        // 1. bounds
+        {
+            int a, b;
+            slice_of(s, e, a, b);
+            float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int p = a + tid; p < b; p += COOP_BLOCK) {
+                float cc[3], pmn[3], pmx[3];
+                prim_fetch(A.pv, perm[p], cc, pmn, pmx);
+#pragma unroll
+                for (int x = 0; x < 3; ++x) { mn[x] = fminf(mn[x], pmn[x]); mx[x] = fmaxf(mx[x], pmx[x]); }
+            }
+#pragma unroll
+            for (int x = 0; x < 3; ++x)
+                for (int o = 16; o; o >>= 1) {
+                    mn[x] = fminf(mn[x], __shfl_xor_sync(0xffffffffu, mn[x], o));
+                    mx[x] = fmaxf(mx[x], __shfl_xor_sync(0xffffffffu, mx[x], o));
+                }
+            if (lane == 0 && a < b) {
+#pragma unroll
+                for (int x = 0; x < 3; ++x) { atomicMin(&G->box[x], f2ord(mn[x])); atomicMax(&G->box[3 + x], f2ord(mx[x])); }
+            }
+            (void)warp;
+        }
+        grid.sync();
+        float mn[3] = {ord2f(G->box[0]), ord2f(G->box[1]), ord2f(G->box[2])}, mx[3] = {ord2f(G->box[3]), ord2f(G->box[4]), ord2f(G->box[5])};
+        if (blockIdx.x == 0 && tid < 6) write_box(A, t.parent_enc, mn, mx, tid);
+        const int dim = max_axis(mn, mx);
+        const float lo = mn[dim], hi = mx[dim];
+        if (hi == lo) { if (lead) atomicCAS(&A.counters[C_ERR], 0, RTDS_ERR_UNSUPPORTED); grid.sync(); continue; }
+        const float pmid = (lo + hi) / 2;
+        // 2. keys + count of pred
+        {
+            int a, b;
+            slice_of(s, e, a, b);
+            int c = 0;
+            for (int p = a + tid; p < b; p += COOP_BLOCK) {
+                float cc[3], pmn[3], pmx[3];
+                prim_fetch(A.pv, perm[p], cc, pmn, pmx);
+                const float k = cc[dim];
+                key[p] = k;
+                c += (k < pmid) ? 1 : 0;
+            }
+            c = block_sum(S, c);
+            if (tid == 0 && c) atomicAdd(&G->cnt[0], c);
+        }
+        grid.sync();
+        const int cT = G->cnt[0];
+        if (cT == 0) { if (lead) A.leaf_info[s] = t.parent_enc + 2; grid.sync(); continue; }              // drop (:321-327)
+        if (cT == m) { if (lead) atomicCAS(&A.counters[C_ERR], 0, RTDS_ERR_DEGENERATE); grid.sync(); continue; }
+        // std::partition
+        {
+            const int cut = s + cT;
+            int* F = A.la + s;
+            int* T = A.lb + s;
+            int nF, nT;
+            // one pass over [s,e): positions left of the cut that fail pred -> F, positions right of it that pass -> T
+            grid_compact2(grid, S, G, s, e, [&](int p) { return p < cut && !(key[p] < pmid); }, [&](int p) { return p >= cut && key[p] < pmid; },
+                          F, T, nF, nT);
+            const int k = nF;
+            for (int i = blockIdx.x * COOP_BLOCK + tid; i < k; i += gridDim.x * COOP_BLOCK) swp(key, perm, F[i], T[k - 1 - i]);
+            grid.sync();
+        }
+        // std::nth_element
+        const int nth = (s + e) / 2;
+        int first = s, last = e, depth_limit = lg2(m) * 2;
+        bool done = false;
+        while (last - first > COOP_TAIL) {
+            if (depth_limit == 0) {
+                if (lead) { atomicAdd(&A.counters[7], 1); atomicAdd(&A.counters[8], last - first); }
+                if (lead) { seq_heap_select(key, perm, first, nth + 1, last); swp(key, perm, first, nth); }
+                done = true;
+                break;
+            }
+            --depth_limit;
+            if (lead) { seq_move_median_to_first(key, perm, first, first + 1, first + (last - first) / 2, last - 1); G->cnt[1] = 0; }
+            grid.sync();
+            const float v = key[first];
+            int* L = A.la + s;
+            int* R = A.lb + s;
+            int nL, nR;
+            grid_compact2(grid, S, G, first + 1, last, [&](int p) { return !(key[p] < v); }, [&](int p) { return !(v < key[p]); }, L, R, nL, nR);
+            const int nmin = min(nL, nR);
+            int kc = 0;
+            for (int i = blockIdx.x * COOP_BLOCK + tid; i < nmin; i += gridDim.x * COOP_BLOCK) kc += (L[i] < R[nR - 1 - i]) ? 1 : 0;
+            kc = block_sum(S, kc);
+            if (tid == 0 && kc) atomicAdd(&G->cnt[1], kc);
+            grid.sync();
+            const int k = G->cnt[1];
+            int cut;
+            if (k == 0) cut = L[0];
+            else cut = min(k < nL ? L[k] : INT_MAX, R[nR - k]);
+            for (int i = blockIdx.x * COOP_BLOCK + tid; i < k; i += gridDim.x * COOP_BLOCK) swp(key, perm, L[i], R[nR - 1 - i]);
+            grid.sync();
+            if (cut <= nth) first = cut; else last = cut;
+        }
+        if (!done && blockIdx.x == 0) block_introselect<COOP_BLOCK>(S, A, s, first, last, nth, depth_limit);
+        // node + children
+        if (lead) {
+            const int node = atomicAdd(&A.counters[C_NODES], 1);
+            A.nodes[node].axis = dim;
+            A.nodes[node].parent = t.parent_enc;
+            link_child(A, t.parent_enc, node);
+            const int mid = nth;
+            if (mid - s == 1) emit_single_leaf(A, s, node, 0); else push_task(next, next_count, s, mid, node * 2);
+            if (e - mid == 1) emit_single_leaf(A, mid, node, 1); else push_task(next, next_count, mid, e, node * 2 + 1);
+        }
+        grid.sync();
     }
 }
 
@@ -541,7 +726,7 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
     size_t o_perm = 0, o_key = o_perm + al(4 * (size_t)n), o_la = o_key + al(4 * (size_t)n), o_lb = o_la + al(4 * (size_t)n),
            o_info = o_lb + al(4 * (size_t)n), o_ta = o_info + al(4 * (size_t)n), o_tb = o_ta + al(sizeof(Task) * ((size_t)n / 2 + 2)),
            o_cnt = o_tb + al(sizeof(Task) * ((size_t)n / 2 + 2)), o_root = o_cnt + 256, o_tiles = o_root + 256,
-           total = o_tiles + al(4 * (size_t)fin_tiles + 4);
+           o_coop = o_tiles + al(4 * (size_t)fin_tiles + 4), total = o_coop + al(sizeof(CoopScratch));
     RTDS_TRY(rtds_ensure_scratch(ctx, total));
     char* base = (char*)ctx->d_scratch;
     MedianArgs A;
@@ -567,10 +752,28 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
     Task* cur = A.tasks_a; Task* nxt = A.tasks_b;
     int ccur = C_TA, cnxt = C_TB;
     long long max_size = n, max_tasks = 1;
+    int coop_threshold = 65536;     // ranges larger than this get the whole grid, one after another
+    if (const char* e = getenv("RTDS_MEDIAN_COOP")) coop_threshold = atoi(e) > 0 ? atoi(e) : (1 << 30);
+    int coop_blocks = 0;
+    {
+        int per_sm = 0;
+        RTDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, median_coop_kernel, COOP_BLOCK, 0));
+        coop_blocks = std::min(ctx->sm_count * std::max(per_sm, 0), 1024);
+        int can = 0;
+        RTDS_CUDA(cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, ctx->device));
+        if (!can) coop_blocks = 0;
+    }
+    CoopScratch* d_coop = (CoopScratch*)(base + o_coop);
     while (max_size > small) {
         RTDS_CUDA(cudaMemsetAsync(A.counters + cnxt, 0, sizeof(int), s));
         const int grid = (int)std::min<long long>(max_tasks, (long long)n / 2 + 1);
-        if (max_size > 4096) median_block_kernel<1024><<<grid, 1024, 0, s>>>(A, cur, A.counters + ccur, nxt, A.counters + cnxt);
+        if (max_size > coop_threshold && coop_blocks > 0 && small < coop_threshold) {
+            RTDS_CUDA(cudaMemsetAsync(d_coop, 0, sizeof(CoopScratch), s));
+            const Task* a_tasks = cur; const int* a_count = A.counters + ccur; Task* a_next = nxt; int* a_ncount = A.counters + cnxt;
+            void* args[] = {(void*)&A, (void*)&a_tasks, (void*)&a_count, (void*)&a_next, (void*)&a_ncount, (void*)&d_coop};
+            RTDS_CUDA(cudaLaunchCooperativeKernel((void*)median_coop_kernel, dim3(coop_blocks), dim3(COOP_BLOCK), args, 0, s));
+        }
+        else if (max_size > 4096) median_block_kernel<1024><<<grid, 1024, 0, s>>>(A, cur, A.counters + ccur, nxt, A.counters + cnxt);
         else if (max_size > 512) median_block_kernel<256><<<grid, 256, 0, s>>>(A, cur, A.counters + ccur, nxt, A.counters + cnxt);
         else median_block_kernel<64><<<grid, 64, 0, s>>>(A, cur, A.counters + ccur, nxt, A.counters + cnxt);
         ++launches;
