@@ -259,10 +259,18 @@ def run_ours(args):
             frame_host.copy_(my_rows[:H], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    e2e_params = ctx.render_params(W, H, SPP, exact=False)
+    e2e_stats = rt.RenderStats()
+
     def step_e2e():
         # what main.cpp does per run, through the C ABI with host buffers
         ctx.lib.rtds_set_spheres(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), n)
         ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+        if world == 1:
+            # rtds_render with a (pinned) host frame: row bands come back while later bands still render
+            rc = ctx.lib.rtds_render(ctx.ctx, rt.LBVH, C.byref(e2e_params), C.c_void_p(frame_host.data_ptr()), None, None, C.byref(e2e_stats))
+            assert rc == 0, ctx.lib.rtds_last_error()
+            return None
         st = step_resident()
         assemble_and_download()
         return st

@@ -120,6 +120,8 @@ int rtds_create(rtds_ctx** out, int device)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     RTDS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    RTDS_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_band, cudaEventDisableTiming));
     RTDS_CUDA(cudaEventCreate(&c->ev0)); RTDS_CUDA(cudaEventCreate(&c->ev1));
     RTDS_CUDA(cudaEventCreate(&c->ev2)); RTDS_CUDA(cudaEventCreate(&c->ev3));
     RTDS_CUDA(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8));
@@ -143,6 +145,8 @@ int rtds_destroy(rtds_ctx* c)
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
     cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    cudaEventDestroy(c->ev_band);
     delete c;
     return RTDS_OK;
 }
@@ -354,14 +358,26 @@ int rtds_render(rtds_ctx* c, int acc, const rtds_render_params* p, uint8_t* rgb,
     RTDS_TRY(ensure_buf(&c->d_frame, &c->frame_bytes, px * 3 + 16));
     if (hit_obj) RTDS_TRY(ensure_buf(&c->d_hit, &c->hit_bytes, px * sizeof(int) + 16));
     if (accum) RTDS_TRY(ensure_buf(&c->d_accum, &c->accum_bytes, px * 3 * sizeof(float) + 16));
-    RTDS_TRY(rtds_render_impl(c, acc, p, c->d_frame, hit_obj ? c->d_hit : nullptr, accum ? c->d_accum : nullptr, st));
-    // device -> host: local row tile j is global tile j*world + rank
     cudaStream_t s = c->stream;
     if (world == 1) {
-        RTDS_CUDA(cudaMemcpyAsync(rgb, c->d_frame, px * 3, cudaMemcpyDeviceToHost, s));
-        if (hit_obj) RTDS_CUDA(cudaMemcpyAsync(hit_obj, c->d_hit, px * sizeof(int), cudaMemcpyDeviceToHost, s));
-        if (accum) RTDS_CUDA(cudaMemcpyAsync(accum, c->d_accum, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    } else {
+        // the frame comes back band by band while later bands are still rendering
+        std::function<int(int, int)> on_band = [&](int r0, int r1) -> int {
+            const size_t off = (size_t)r0 * W, cnt = (size_t)(r1 - r0) * W;
+            RTDS_CUDA(cudaEventRecord(c->ev_band, s));
+            RTDS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_band, 0));
+            RTDS_CUDA(cudaMemcpyAsync(rgb + off * 3, c->d_frame + off * 3, cnt * 3, cudaMemcpyDeviceToHost, c->copy_stream));
+            if (hit_obj) RTDS_CUDA(cudaMemcpyAsync(hit_obj + off, c->d_hit + off, cnt * sizeof(int), cudaMemcpyDeviceToHost, c->copy_stream));
+            if (accum) RTDS_CUDA(cudaMemcpyAsync(accum + off * 3, c->d_accum + off * 3, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+            return RTDS_OK;
+        };
+        RTDS_TRY(rtds_render_impl(c, acc, p, c->d_frame, hit_obj ? c->d_hit : nullptr, accum ? c->d_accum : nullptr, st, &on_band));
+        RTDS_CUDA(cudaStreamSynchronize(s));
+        RTDS_CUDA(cudaStreamSynchronize(c->copy_stream));
+        return RTDS_OK;
+    }
+    RTDS_TRY(rtds_render_impl(c, acc, p, c->d_frame, hit_obj ? c->d_hit : nullptr, accum ? c->d_accum : nullptr, st));
+    // device -> host: local row tile j is global tile j*world + rank
+    {
         int lrow = 0;
         for (int t = p->rank; t * tile_rows < H; t += world) {
             int r0 = t * tile_rows, nr = (r0 + tile_rows <= H) ? tile_rows : H - r0;

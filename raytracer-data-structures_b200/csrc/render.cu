@@ -15,6 +15,9 @@
 // operation rounds exactly like the reference's SSE2 code.
 #include "rtds_internal.cuh"
 #include <math.h>
+#include <algorithm>
+#include <functional>
+#include <stdlib.h>
 
 namespace {
 
@@ -649,6 +652,7 @@ __device__ __forceinline__ void shade_diffuse(const ShadeParams& P, float dx, fl
 struct RenderArgs {
     int   width, height, spp;
     int   rank, world, tile_rows, local_rows;
+    int   lrow0;                 // first local row of this launch (the frame may be rendered in row bands)
     float angle, aspect, inv_w, inv_h;
     const uint32_t* jitter;      // word 0 = stream word jitter_base
     uint64_t        jitter_rel;  // (4*first_sample - jitter_base): word offset of sample 0 of pixel 0
@@ -673,7 +677,7 @@ __global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
     // block = 16 x 8 pixels; warp = 8 x 4 pixels
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int lrow = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const int lrow = A.lrow0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool active = px < A.width && lrow < A.local_rows;
     int py = 0;
     if (active) {
@@ -807,7 +811,7 @@ __global__ void __launch_bounds__(128) render_full_kernel(const RenderArgs A)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int lrow = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const int lrow = A.lrow0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool active = px < A.width && lrow < A.local_rows;
     Counters cnt = {0, 0, 0, 0};
     unsigned shadow_rays = 0, secondary_rays = 0;
@@ -1065,7 +1069,7 @@ int rtds_jitter_stream_impl(rtds_ctx* ctx, uint64_t first, int n, double* out)
 }
 
 int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_t* d_rgb_rows, int* d_hit, float* d_accum,
-                     rtds_render_stats* st)
+                     rtds_render_stats* st, const std::function<int(int, int)>* on_band)
 {
     const int W = p->width, H = p->height, spp = p->aa_samples;
     if (W <= 0 || H <= 0 || spp <= 0) { rtds_set_error("render: width/height/aa_samples must be positive"); return RTDS_ERR_INVALID; }
@@ -1080,7 +1084,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
 
     RenderArgs A;
     A.width = W; A.height = H; A.spp = spp;
-    A.rank = rank; A.world = world; A.tile_rows = tile_rows;
+    A.rank = rank; A.world = world; A.tile_rows = tile_rows; A.lrow0 = 0;
     A.local_rows = rtds_rows_for_rank(H, tile_rows, rank, world);
     // main.cpp:544-546
     const float fov = p->fov > 0 ? p->fov : 30.0f;
@@ -1117,19 +1121,32 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.jitter_rel = first_word - ctx->jitter_first_word;
     RTDS_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 8, s));
     if (A.local_rows > 0) {
-        dim3 grid((W + 15) / 16, (A.local_rows + 7) / 8), block(128);
+        // Row bands: with a band callback (host-buffer render) each band's device->host copy is queued on the copy
+        // stream as soon as its kernel is queued, so the frame download overlaps the rendering of the next bands.
+        const int total_rows = A.local_rows;
+        int n_bands = 1;
+        if (on_band && total_rows >= 512) { const char* e = getenv("RTDS_BANDS"); n_bands = e ? std::max(1, atoi(e)) : 1; }
+        const int band_rows = ((total_rows + n_bands - 1) / n_bands + 7) & ~7;
         RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
-        if (full) {
-            if (brute) render_full_kernel<2><<<grid, block, 0, s>>>(A);
-            else if (p->exact) render_full_kernel<0><<<grid, block, 0, s>>>(A);
-            else render_full_kernel<1><<<grid, block, 0, s>>>(A);
+        for (int r0 = 0; r0 < total_rows; r0 += band_rows) {
+            const int r1 = std::min(total_rows, r0 + band_rows);
+            A.lrow0 = r0;
+            A.local_rows = r1;
+            dim3 grid((W + 15) / 16, (r1 - r0 + 7) / 8), block(128);
+            if (full) {
+                if (brute) render_full_kernel<2><<<grid, block, 0, s>>>(A);
+                else if (p->exact) render_full_kernel<0><<<grid, block, 0, s>>>(A);
+                else render_full_kernel<1><<<grid, block, 0, s>>>(A);
+            }
+            else if (kdt) render_kernel<3><<<grid, block, 0, s>>>(A);
+            else if (brute) render_kernel<2><<<grid, block, 0, s>>>(A);
+            else if (p->exact) render_kernel<0><<<grid, block, 0, s>>>(A);
+            else render_kernel<1><<<grid, block, 0, s>>>(A);
+            launches += 1;
+            if (on_band) RTDS_TRY((*on_band)(r0, r1));
         }
-        else if (kdt) render_kernel<3><<<grid, block, 0, s>>>(A);
-        else if (brute) render_kernel<2><<<grid, block, 0, s>>>(A);
-        else if (p->exact) render_kernel<0><<<grid, block, 0, s>>>(A);
-        else render_kernel<1><<<grid, block, 0, s>>>(A);
+        A.local_rows = total_rows;
         RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
-        launches += 1;
         RTDS_CUDA(cudaGetLastError());
     } else {
         RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
@@ -1148,6 +1165,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
         RTDS_CUDA(cudaEventElapsedTime(&st->ms_total, ctx->ev0, ctx->ev1));
         st->kernel_launches = launches;
         st->rows = A.local_rows;
+        if (on_band) RTDS_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     }
     return RTDS_OK;
 }

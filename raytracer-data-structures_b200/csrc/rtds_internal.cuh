@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string>
 #include <vector>
+#include <functional>
 #include "../../include/rtds.h"
 
 // ---------------------------------------------------------------------------------------------------
@@ -84,6 +85,8 @@ struct RtdsLight { float c[3]; float radius; float le[3]; };
 struct rtds_ctx {
     int          device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // device->host copies of finished row bands
+    cudaEvent_t  ev_band = nullptr;
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     int          sm_count = 148;
 
@@ -173,7 +176,7 @@ void rtds_free_kd(DeviceKd& k);
 
 // render.cu — K10 render/trace, K11 MT19937 jitter stream
 int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_t* d_rgb_rows, int* d_hit,
-                     float* d_accum, rtds_render_stats* st);
+                     float* d_accum, rtds_render_stats* st, const std::function<int(int, int)>* on_band = nullptr);
 int rtds_trace_impl(rtds_ctx* ctx, int acc, int exact, const float* h_o, const float* h_d, int nrays,
                     int* h_hit, float* h_t, rtds_render_stats* st);
 int rtds_jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int* launches);
