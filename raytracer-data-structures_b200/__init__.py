@@ -310,3 +310,31 @@ def parse_obj_vertices(path):
         out.append((np.float32(toks[i + 1]), np.float32(toks[i + 2]), np.float32(toks[i + 3])))
         i += 4
     return np.asarray(out, np.float32).reshape(-1, 3)
+
+
+# ------------------------------------------------------------------------------------------------------
+# multi-GPU plumbing: the framebuffer gather (the path's only collective). torch.distributed is plumbing here —
+# NCCL over NVLink on GPUs, gloo in the CPU tests.
+# ------------------------------------------------------------------------------------------------------
+def gather_frame(local_rows, height, width, tile_rows, rank, world, dst=0, scratch=None):
+    """local_rows: uint8 tensor [>= rows_for_rank, width, 3] holding this rank's rows compactly (local tile j = global
+    tile j*world + rank). Returns the assembled [height, width, 3] frame on `dst` (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return local_rows[:height]
+    max_rows = max(len(owned_rows(height, tile_rows, r, world)) for r in range(world))
+    if local_rows.shape[0] != max_rows:
+        pad = torch.zeros((max_rows, width, 3), dtype=torch.uint8, device=local_rows.device)
+        pad[: local_rows.shape[0]] = local_rows
+        local_rows = pad
+    if rank == dst:
+        parts = scratch if scratch is not None else [torch.zeros_like(local_rows) for _ in range(world)]
+        dist.gather(local_rows, parts, dst=dst)
+        frame = torch.zeros((height, width, 3), dtype=torch.uint8, device=local_rows.device)
+        for r in range(world):
+            idx = torch.from_numpy(owned_rows(height, tile_rows, r, world)).to(local_rows.device)
+            frame[idx] = parts[r][: idx.numel()]
+        return frame
+    dist.gather(local_rows, None, dst=dst)
+    return None
