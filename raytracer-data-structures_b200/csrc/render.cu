@@ -283,7 +283,7 @@ __device__ __forceinline__ float prune_margin(const float rb[6], float ox, float
 // sphere becomes a candidate is decided by the EXACT test on its own leaf box (a leaf box inside a node box
 // passes the reference's test only if the node box does: the per-axis intervals nest monotonically).
 // Valid for finite, non-tiny direction components (checked once per ray).
-constexpr float WIDE_EPS = 4.76837158e-7f;   // 2^-21 > 2^-24 (rcp) + 2^-24 (mul) + 2^-24 (the divide's own rounding)
+constexpr float WIDE_EPS = 4.76837158e-7f;   // 2^-21 > 2^-23 (rcp.approx) + 2^-24 (mul) + 2^-24 (the divide's own rounding), x2 margin
 __device__ __forceinline__ bool slab_wide(float ox, float oy, float oz, float ix, float iy, float iz, float bminx, float bminy,
                                           float bminz, float bmaxx, float bmaxy, float bmaxz, float& tmin_o, float& tmax_o)
 {
@@ -401,17 +401,19 @@ template <bool ZERO_O>
 __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
                                               float& tnear, int& best_key, int& best_leaf, Counters& cnt)
 {
-    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+    // 1/d only feeds the conservative test (its error is inside WIDE_EPS): one MUFU.RCP each instead of an IEEE divide
+    float ix, iy, iz;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"(dx));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(dy));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(dz));
     if (B.root_ref < 0 || !(fabsf(ix) < 1e30f && fabsf(iy) < 1e30f && fabsf(iz) < 1e30f)) {
         // single-leaf tree, or a zero / tiny / non-finite direction component: the divide-based traversal
         traverse_bvh<true>(B, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
         return;
     }
-    float tmn, tmx;
-    cnt.node_tests++;
-    if (!slab_test(ox, oy, oz, dx, dy, dz, B.root_box[0], B.root_box[1], B.root_box[2], B.root_box[3], B.root_box[4],
-                   B.root_box[5], tmn, tmx))
-        return;
+    // No separate root test: a leaf box that passes the reference's slab test lies inside the root box, which then
+    // passes too (nesting), so the candidate set does not depend on it; rays that miss the scene fall out of the
+    // first interior visit.
     const float margin = prune_margin(B.root_box, ox, oy, oz);
     const float neg_margin = -margin;
     float tlim = tnear + margin;            // a subtree is opened only while its entry distance is <= tlim
