@@ -21,7 +21,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtds.so")
+LIB_PATH = os.environ.get("RTDS_LIB", os.path.join(_HERE, "librtds.so"))   # RTDS_LIB: A/B-test another build of the library
 HOST_LIB_PATH = os.path.join(_HERE, "librtds_host.so")
 
 # enum AccType { BVH, KDTREE, UNIFORM_GRID, LBVH, NONE }  (accelerators.h:21)

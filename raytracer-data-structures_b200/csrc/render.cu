@@ -657,6 +657,9 @@ struct RenderArgs {
     int   lrow0;                 // first local row of this launch (the frame may be rendered in row bands)
     float angle, aspect, inv_w, inv_h;
     const uint32_t* jitter;      // word 0 = stream word jitter_base
+    const uint32_t* mt_snap;     // MT19937 state snapshots (strip kernel regenerates its words itself)
+    unsigned long long first_sample;   // stream index of sample 0 of pixel 0 (jitter_offset)
+    int             chunk_first; // absolute snapshot chunk of block 0 of the strip kernel
     uint64_t        jitter_rel;  // (4*first_sample - jitter_base): word offset of sample 0 of pixel 0
     BvhView bvh;
     KdView  kd;
@@ -740,6 +743,120 @@ __global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
         if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
     }
     // counters: warp reduce, one atomic per warp per counter
+    unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned long long x = v[c];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(&A.counters[c], x);
+    }
+}
+
+// ===================================================================================================
+// K10 + K11 fused ("strip" kernel): one block per MT19937 snapshot chunk (8 regenerations = 4,992 words = 1,248
+// samples). The block regenerates its chunk of the reference's jitter stream into SHARED memory (plus one more
+// regeneration for a pixel whose samples straddle the chunk end) and renders the pixels whose first sample lies in
+// the chunk — consecutive pixels in scanline order, i.e. the order the reference consumes the stream in. The 531 MB
+// of jitter words a 4K x 4 spp frame needs are never written to or read from HBM. Warps hold 32 consecutive pixels
+// of a row; with sub-pixel primitives the traversal is as coherent as with 8x4 tiles (measured).
+// ===================================================================================================
+constexpr int STRIP_THREADS = 128;
+constexpr int STRIP_REGENS = MT_SNAP_EVERY + 1;
+constexpr int STRIP_SAMPLES = MT_SNAP_EVERY * MT_N / 4;   // 1,248 samples per chunk
+
+// regeneration A -> B by a block of 128 threads (two passes per 227-wide phase)
+__device__ __forceinline__ void mt_regen_128(const uint32_t* __restrict__ A, uint32_t* __restrict__ B)
+{
+    const int t = threadIdx.x;
+    for (int i = t; i < 227; i += STRIP_THREADS) B[i] = A[i + MT_M] ^ mt_twist(A[i], A[i + 1]);
+    __syncthreads();
+    for (int i = t; i < 227; i += STRIP_THREADS) B[i + 227] = B[i] ^ mt_twist(A[i + 227], A[i + 228]);
+    __syncthreads();
+    for (int i = t; i < 169; i += STRIP_THREADS) B[i + 454] = B[i + 227] ^ mt_twist(A[i + 454], A[i + 455]);
+    if (t == 0) B[623] = B[396] ^ mt_twist(A[623], B[0]);
+    __syncthreads();
+}
+
+template <int MODE /*0 = BVH exact, 1 = BVH ordered, 3 = KDTREE*/>
+__global__ void __launch_bounds__(STRIP_THREADS) render_strip_kernel(const RenderArgs A)
+{
+    __shared__ uint32_t S[2][MT_N];
+    __shared__ __align__(16) uint32_t words[STRIP_REGENS * MT_N];
+    const int lane = threadIdx.x & 31;
+    const unsigned long long chunk = (unsigned long long)A.chunk_first + blockIdx.x;
+    const unsigned long long s_lo = chunk * STRIP_SAMPLES, s_hi = s_lo + STRIP_SAMPLES;     // absolute sample range
+    const unsigned long long n_pix = (unsigned long long)A.width * A.height;
+    // pixels whose first sample (first_sample + p*spp) lies in [s_lo, s_hi)
+    unsigned long long p_lo = s_lo > A.first_sample ? (s_lo - A.first_sample + A.spp - 1) / A.spp : 0;
+    unsigned long long p_hi = s_hi > A.first_sample ? (s_hi - A.first_sample + A.spp - 1) / A.spp : 0;
+    if (p_hi > n_pix) p_hi = n_pix;
+    if (p_lo >= p_hi) return;
+    if (A.world > 1) {   // skip chunks that hold no row of this rank
+        const int y0 = (int)(p_lo / A.width), y1 = (int)((p_hi - 1) / A.width);
+        bool mine = false;
+        for (int t = y0 / A.tile_rows; t <= y1 / A.tile_rows; ++t) mine |= (t % A.world) == A.rank;
+        if (!mine) return;
+    }
+    // regenerate the chunk (+1 regeneration) from its snapshot
+    {
+        const uint32_t* src = A.mt_snap + chunk * MT_N;
+        for (int i = threadIdx.x; i < MT_N; i += STRIP_THREADS) S[0][i] = __ldg(src + i);
+        __syncthreads();
+        int cur = 0;
+        for (int r = 0; r < STRIP_REGENS; ++r) {
+            mt_regen_128(S[cur], S[cur ^ 1]);
+            cur ^= 1;
+            for (int i = threadIdx.x; i < MT_N; i += STRIP_THREADS) words[r * MT_N + i] = mt_temper(S[cur][i]);
+        }
+        __syncthreads();
+    }
+    Counters cnt = {0, 0, 0, 0};
+    for (unsigned long long p = p_lo + threadIdx.x; p < p_hi; p += STRIP_THREADS) {
+        const int py = (int)(p / A.width), px = (int)(p - (unsigned long long)py * A.width);
+        const int tile = py / A.tile_rows;
+        if (A.world > 1 && (tile % A.world) != A.rank) continue;
+        const int lrow = (tile / A.world) * A.tile_rows + (py - tile * A.tile_rows);
+        const unsigned woff = (unsigned)((A.first_sample + p * A.spp - s_lo) * 4);   // word offset of the pixel's first sample
+        float acc_r = 0, acc_g = 0, acc_b = 0;
+        int last_hit = -1;
+        for (int k = 0; k < A.spp; ++k) {
+            const uint4 jw = *reinterpret_cast<const uint4*>(&words[woff + 4 * k]);
+            double r1 = canonical53(jw.x, jw.y), r2 = canonical53(jw.z, jw.w);
+            // main.cpp:554-557
+            float dx = (float)((2 * (((double)(unsigned)px + r1) * (double)A.inv_w) - 1) * (double)A.angle * (double)A.aspect);
+            float dy = (float)((1 - 2 * (((double)(unsigned)py + r2) * (double)A.inv_h)) * (double)A.angle);
+            float dz = -1;
+            normalize3(dx, dy, dz);
+            cnt.rays++;
+            float tnear = INFINITY;
+            int best_key = 0, best_leaf = -1, hit_obj = -1;
+            if (MODE == 3) hit_obj = kd_any_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, cnt) ? 1 : -1;
+            else {
+                if (MODE == 0) traverse_bvh<true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+                else traverse_fast<true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+                if (best_leaf >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf);
+            }
+            float r, g, b;
+            if (hit_obj < 0) { r = A.shade.bg[0]; g = A.shade.bg[1]; b = A.shade.bg[2]; }
+            else if (MODE == 3) { r = 0.f; g = 0.f; b = 0.f; }
+            else {
+                float4 m = __ldg(A.mat + hit_obj);
+                const float hx = 0.f + dx * tnear, hy = 0.f + dy * tnear, hz = 0.f + dz * tnear;
+                float nx, ny, nz;
+                raw_normal(A.bvh.prim_type, A.bvh.leaf_sph, A.bvh.leaf_tri, (size_t)best_leaf, hx, hy, hz, nx, ny, nz);
+                shade_diffuse(A.shade, dx, dy, dz, hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b);
+            }
+            acc_r += r; acc_g += g; acc_b += b;
+            last_hit = hit_obj;
+        }
+        const size_t o = (size_t)lrow * A.width + px;
+        const float fs = (float)(unsigned)A.spp;
+        A.out_rgb[3 * o]     = (unsigned char)(fminf(1.0f, acc_r / fs) * 255);
+        A.out_rgb[3 * o + 1] = (unsigned char)(fminf(1.0f, acc_g / fs) * 255);
+        A.out_rgb[3 * o + 2] = (unsigned char)(fminf(1.0f, acc_b / fs) * 255);
+        if (A.out_hit) A.out_hit[o] = last_hit;
+        if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
+    }
     unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -1011,14 +1128,9 @@ int check_bvh(rtds_ctx* ctx, int acc)
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-static int jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int* launches, const JitterOwner& own)
+// MT19937 state snapshots for chunks [0, need_snaps): computed once per context by one sequential block, extended on demand
+static int ensure_snapshots(rtds_ctx* ctx, int need_snaps, int* launches)
 {
-    if (n_words == 0) return RTDS_OK;
-    const uint64_t words_per_snap = (uint64_t)MT_SNAP_EVERY * MT_N;
-    const uint64_t s0 = first_word / words_per_snap;
-    const uint64_t s1 = (first_word + n_words - 1) / words_per_snap;  // last snapshot chunk needed (inclusive)
-    if (s1 + 2 >= (1ull << 31)) { rtds_set_error("jitter stream position too large"); return RTDS_ERR_INVALID; }
-    const int need_snaps = (int)(s1 + 1);
     cudaStream_t s = ctx->stream;
     if (ctx->n_snap < need_snaps) {
         // grow geometrically; keep existing snapshots
@@ -1035,6 +1147,18 @@ static int jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, in
         ctx->d_mt_snap = nsnap;
         ctx->n_snap = cap;
     }
+    return RTDS_OK;
+}
+
+static int jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int* launches, const JitterOwner& own)
+{
+    if (n_words == 0) return RTDS_OK;
+    const uint64_t words_per_snap = (uint64_t)MT_SNAP_EVERY * MT_N;
+    const uint64_t s0 = first_word / words_per_snap;
+    const uint64_t s1 = (first_word + n_words - 1) / words_per_snap;  // last snapshot chunk needed (inclusive)
+    if (s1 + 2 >= (1ull << 31)) { rtds_set_error("jitter stream position too large"); return RTDS_ERR_INVALID; }
+    RTDS_TRY(ensure_snapshots(ctx, (int)(s1 + 1), launches));
+    cudaStream_t s = ctx->stream;
     const int blocks = (int)(s1 - s0 + 1);
     const size_t out_words = (size_t)blocks * words_per_snap;
     if (ctx->jitter_cap_words < out_words) {
@@ -1113,6 +1237,17 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     RTDS_CUDA(cudaEventRecord(ctx->ev0, s));
     const uint64_t first_word = 4ull * p->jitter_offset;
     const size_t n_words = 4ull * (size_t)W * H * spp;
+    // Optional fused strip kernel (RTDS_STRIP=1): regenerates the jitter words it needs in shared memory, so nothing is
+    // expanded into HBM. MEASURED SLOWER on B200 (3.16 ms vs 1.81 + 0.24 ms on the bench frame): a block then covers
+    // 312 consecutive pixels of one scanline instead of a 16x8 tile, and the L1 hit rate of the node stream — what
+    // this issue-bound kernel lives on — collapses. Kept as a checked (parity-tested) negative result, off by default.
+    const bool strip = !brute && !full && spp <= 150 && getenv("RTDS_STRIP") && atoi(getenv("RTDS_STRIP")) == 1;
+    const uint64_t chunk_words = (uint64_t)MT_SNAP_EVERY * MT_N;
+    const uint64_t c_first = first_word / chunk_words, c_last = (first_word + n_words - 1) / chunk_words;
+    if (strip) {
+        if (c_last + 3 >= (1ull << 31)) { rtds_set_error("jitter stream position too large"); return RTDS_ERR_INVALID; }
+        RTDS_TRY(ensure_snapshots(ctx, (int)(c_last + 1), &launches));
+    } else
     if (!(p->no_jitter_regen && ctx->d_jitter && ctx->jitter_first_word <= first_word &&
           first_word + n_words <= ctx->jitter_first_word + ctx->jitter_n_words))
     {
@@ -1120,9 +1255,22 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
         RTDS_TRY(jitter_prepare(ctx, first_word, n_words, &launches, own));
     }
     A.jitter = ctx->d_jitter;
-    A.jitter_rel = first_word - ctx->jitter_first_word;
+    A.jitter_rel = strip ? 0 : first_word - ctx->jitter_first_word;
+    A.mt_snap = ctx->d_mt_snap;
+    A.first_sample = p->jitter_offset;
+    A.chunk_first = (int)c_first;
     RTDS_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 8, s));
-    if (A.local_rows > 0) {
+    if (A.local_rows > 0 && strip) {
+        const int blocks = (int)(c_last - c_first + 1);
+        RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
+        if (kdt) render_strip_kernel<3><<<blocks, STRIP_THREADS, 0, s>>>(A);
+        else if (p->exact) render_strip_kernel<0><<<blocks, STRIP_THREADS, 0, s>>>(A);
+        else render_strip_kernel<1><<<blocks, STRIP_THREADS, 0, s>>>(A);
+        launches += 1;
+        RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
+        RTDS_CUDA(cudaGetLastError());
+        if (on_band) RTDS_TRY((*on_band)(0, A.local_rows));
+    } else if (A.local_rows > 0) {
         // Row bands: with a band callback (host-buffer render) each band's device->host copy is queued on the copy
         // stream as soon as its kernel is queued, so the frame download overlaps the rendering of the next bands.
         const int total_rows = A.local_rows;

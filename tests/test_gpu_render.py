@@ -103,3 +103,26 @@ def test_render_multisample_and_ranks(gpu_ctx, oracle):
             frame[rows] = part[rows]
             rows_seen += rows.size
         assert rows_seen == H and np.array_equal(frame, full)
+
+
+def test_fused_strip_kernel_is_exact_too(gpu_ctx, oracle, monkeypatch):
+    """RTDS_STRIP=1: the fused render + in-block MT19937 kernel (a measured negative result for speed)
+    must still produce the reference's frame: default config md5, ragged multi-sample multi-rank frames."""
+    monkeypatch.setenv("RTDS_STRIP", "1")
+    sph, mat = T.bunny_scene()
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.build(rt.BVH)
+    rgb, hit, _, _ = gpu_ctx.render(rt.BVH, 640, 480, 1, want_hit=True)
+    assert T.ppm_md5(rgb) == "c69c66375f2c6bda433f9f457a4b2b2e"
+    nodes, order = gpu_ctx.export_bvh()
+    W, H, spp = 322, 203, 5          # 5 does not divide the 1,248-sample chunk: pixels straddle chunk ends
+    full, hit, accum, _ = gpu_ctx.render(rt.BVH, W, H, spp, want_hit=True, want_accum=True)
+    rgb_o, hit_o, accum_o, _ = oracle.render_rows(sph, mat, nodes, order, W, H, spp, want_accum=True)
+    assert accum.tobytes() == accum_o.tobytes() and np.array_equal(full, rgb_o) and np.array_equal(hit, hit_o)
+    frame = np.zeros((H, W, 3), np.uint8)
+    for rank in range(3):
+        part = np.zeros((H, W, 3), np.uint8)
+        gpu_ctx.render(rt.BVH, W, H, spp, out=part, rank=rank, world=3)
+        rows = rt.owned_rows(H, 8, rank, 3)
+        frame[rows] = part[rows]
+    assert np.array_equal(frame, full)
