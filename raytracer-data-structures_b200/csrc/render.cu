@@ -1293,10 +1293,12 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             else if (p->exact) render_kernel<0><<<grid, block, 0, s>>>(A);
             else render_kernel<1><<<grid, block, 0, s>>>(A);
             launches += 1;
+            // the kernel-time event goes in BEFORE the band callback: a device->host copy into pageable memory blocks the
+            // host, and an event recorded after it would time the copy as well
+            if (r1 == total_rows) RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
             if (on_band) RTDS_TRY((*on_band)(r0, r1));
         }
         A.local_rows = total_rows;
-        RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
         RTDS_CUDA(cudaGetLastError());
     } else {
         RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
