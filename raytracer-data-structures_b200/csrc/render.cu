@@ -397,9 +397,12 @@ __device__ __forceinline__ void traverse_bvh(const BvhView& B, float ox, float o
 // case), and a leaf is only opened when it is popped with tmin still below the current hit: there the reference's
 // EXACT slab test is run on the leaf's box (re-read from its parent's record) and then the sphere test.
 // ZERO_O: the ray starts at the origin (every primary ray, main.cpp:558): t = b * (1/d), one multiply per plane.
-template <bool ZERO_O>
+// ANYHIT (shadow rays, main.cpp:468-473): stop at the first candidate with t'^2 < t2max. "The nearest hit satisfies
+// tNear^2 < lightDistance2" and "some candidate does" are the same predicate (every t' is >= 0), so the answer equals
+// the closest-hit formulation's; subtrees that start beyond sqrt(t2max) are never opened.
+template <bool ZERO_O, bool ANYHIT = false>
 __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
-                                              float& tnear, int& best_key, int& best_leaf, Counters& cnt)
+                                              float& tnear, int& best_key, int& best_leaf, Counters& cnt, float t2max = 0.f)
 {
     // 1/d only feeds the conservative test (its error is inside WIDE_EPS): one MUFU.RCP each instead of an IEEE divide
     float ix, iy, iz;
@@ -409,6 +412,7 @@ __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float 
     if (B.root_ref < 0 || !(fabsf(ix) < 1e30f && fabsf(iy) < 1e30f && fabsf(iz) < 1e30f)) {
         // single-leaf tree, or a zero / tiny / non-finite direction component: the divide-based traversal
         traverse_bvh<true>(B, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+        if (ANYHIT && !(best_leaf >= 0 && tnear * tnear < t2max)) best_leaf = -1;
         return;
     }
     // No separate root test: a leaf box that passes the reference's slab test lies inside the root box, which then
@@ -416,7 +420,7 @@ __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float 
     // first interior visit.
     const float margin = prune_margin(B.root_box, ox, oy, oz);
     const float neg_margin = -margin;
-    float tlim = tnear + margin;            // a subtree is opened only while its entry distance is <= tlim
+    float tlim = ANYHIT ? sqrtf(t2max) + margin : tnear + margin;   // a subtree is opened only while its entry distance is <= tlim
     int   stack[STACK_MAX];
     float stack_t[STACK_MAX];
     int sp = 0;
@@ -469,8 +473,13 @@ __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float 
                 float t0, t1;
                 cnt.prim_tests++;
                 if (leaf_test(B, leaf, ox, oy, oz, dx, dy, dz, t0, t1)) {
-                    candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
-                    tlim = tnear + margin;
+                    if (ANYHIT) {
+                        if (t0 < 0) t0 = t1;
+                        if (t0 * t0 < t2max) { tnear = t0; best_leaf = leaf; cnt.node_visits += visits; cnt.node_tests += 2 * visits; return; }
+                    } else {
+                        candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
+                        tlim = tnear + margin;
+                    }
                 }
             }
         }
@@ -925,6 +934,23 @@ __device__ __forceinline__ void closest_hit(const RenderArgs& A, float ox, float
     }
 }
 
+// the shadow query of main.cpp:468-473: is there a hit with tNearShadow^2 < lightDistance2?
+template <int MODE>
+__device__ __forceinline__ bool occluded(const RenderArgs& A, float ox, float oy, float oz, float dx, float dy, float dz, float dist2, Counters& cnt)
+{
+    if (MODE == 1) {
+        float len2 = dx * dx + dy * dy + dz * dz;
+        if (fabsf(len2 - 1.0f) < 1e-3f) {
+            float ts = INFINITY; int bk = 0, bl = -1;
+            traverse_fast<false, true>(A.bvh, ox, oy, oz, dx, dy, dz, ts, bk, bl, cnt, dist2);
+            return bl >= 0;
+        }
+    }
+    float ts; int sh, shl;
+    closest_hit<MODE>(A, ox, oy, oz, dx, dy, dz, ts, sh, shl, cnt);
+    return sh >= 0 && ts * ts < dist2;
+}
+
 template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE*/>
 __global__ void __launch_bounds__(128) render_full_kernel(const RenderArgs A)
 {
@@ -1002,12 +1028,9 @@ __global__ void __launch_bounds__(128) render_full_kernel(const RenderArgs A)
                         float sx = front ? hx + nx * bias : hx - nx * bias;
                         float sy = front ? hy + ny * bias : hy - ny * bias;
                         float sz = front ? hz + nz * bias : hz - nz * bias;
-                        float ts;
-                        int sh, shl;
-                        closest_hit<MODE>(A, sx, sy, sz, lx, ly, lz, ts, sh, shl, cnt);
                         cnt.rays++;
                         shadow_rays++;
-                        if (sh >= 0 && ts * ts < dist2) lit = 0.0f;           // main.cpp:471-472
+                        if (occluded<MODE>(A, sx, sy, sz, lx, ly, lz, dist2, cnt)) lit = 0.0f;   // main.cpp:471-472
                     }
                     const float ar = (L.le[0] * lit) * LdotN, ag = (L.le[1] * lit) * LdotN, ab = (L.le[2] * lit) * LdotN;
                     const float ix = -lx, iy = -ly, iz = -lz;
