@@ -304,6 +304,21 @@ def run_ours(args):
     ms_per_step = float(np.mean(per_step))
     value = total_rays / (ms_per_step * 1e-3) / 1e6
 
+    # side number (not the headline): the same frame with the shadow query on (extension: trace_more is a stub in the
+    # reference), rays = primary + shadow rays actually traced
+    sh_params = ctx.render_params(W, H, SPP, exact=False, rank=rank, world=world, tile_rows=TILE_ROWS, shadows=1)
+
+    def step_shadows():
+        st = ctx.render_device(rt.LBVH, sh_params, my_rows.data_ptr())
+        if world > 1:
+            dist.gather(my_rows, gathered, dst=0)
+        return st
+
+    sh_steps, sh_stats, _ = timed(step_shadows, 3, 1)
+    sh_rays = torch.tensor([float(sh_stats[-1]["rays"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(sh_rays)
+
     e2e_steps, _, _ = timed(step_e2e, max(2, min(args.steps, 5)), 1)
     e2e_ms = float(np.mean(e2e_steps))
     e2e_value = total_rays / (e2e_ms * 1e-3) / 1e6
@@ -347,6 +362,9 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(2 * n * 16) * world,
                         "d2h_bytes_per_step": W * H * 3,
                         "what": "per step: rtds_set_spheres (H2D from pinned) + rtds_build(LBVH) + render + gather + D2H of the RGB8 frame"},
+                "with_shadows": {"value": sh_rays.item() / (float(np.mean(sh_steps)) * 1e-3) / 1e6, "unit": "Mrays/s",
+                                 "ms_per_step": float(np.mean(sh_steps)), "rays_per_step": int(sh_rays.item()),
+                                 "note": "extension: shadow query on (the reference's trace_more is a stub); primary + shadow rays"},
                 "gpu_launches": int(launches_per_step * args.steps * world),
                 "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
