@@ -358,7 +358,10 @@ def run_ours(args):
                           "kernel_launches": build_stats[-1]["kernel_launches"]},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "kernel": "render_kernel<1> (rank 0's launch)", "kernel_ms": k_ms,
-                             "peak_source": peak_src},
+                             "peak_source": peak_src,
+                             "note": "SURVEY 8d formula (32 B x slab tests + 16 B x prim tests + 16 B per ray); that node stream is served by "
+                                     "L1/L2 (ncu: L1 hit 90 %, DRAM traffic = `traffic` bytes per launch, 2-4 % of HBM peak), so frac > 1: "
+                                     "the kernel is issue-bound (78 % of issue slots), not HBM-bound - DESIGN.md section 8"},
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(2 * n * 16) * world,
                         "d2h_bytes_per_step": W * H * 3,
                         "what": "per step: rtds_set_spheres (H2D from pinned) + rtds_build(LBVH) + render + gather + D2H of the RGB8 frame"},
