@@ -261,16 +261,19 @@ def run_ours(args):
 
     e2e_params = ctx.render_params(W, H, SPP, exact=False)
     e2e_stats = rt.RenderStats()
+    e2e_bp = rt.BuildParams()
+    e2e_bp.mode = rt.MODE_TRUE
 
     def step_e2e():
         # what main.cpp does per run, through the C ABI with host buffers
-        ctx.lib.rtds_set_spheres(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), n)
-        ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
         if world == 1:
-            # rtds_render with a (pinned) host frame: row bands come back while later bands still render
-            rc = ctx.lib.rtds_render(ctx.ctx, rt.LBVH, C.byref(e2e_params), C.c_void_p(frame_host.data_ptr()), None, None, C.byref(e2e_stats))
+            # rtds_frame = rtds_set_spheres + rtds_build + rtds_render in one synchronous call (stages overlapped inside)
+            rc = ctx.lib.rtds_frame(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), n, rt.LBVH, C.byref(e2e_bp),
+                                    C.byref(e2e_params), C.c_void_p(frame_host.data_ptr()), None, C.byref(e2e_stats))
             assert rc == 0, ctx.lib.rtds_last_error()
             return None
+        ctx.lib.rtds_set_spheres(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), n)
+        ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
         st = step_resident()
         assemble_and_download()
         return st
@@ -364,7 +367,7 @@ def run_ours(args):
                                      "the kernel is issue-bound (78 % of issue slots), not HBM-bound - DESIGN.md section 8"},
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(2 * n * 16) * world,
                         "d2h_bytes_per_step": W * H * 3,
-                        "what": "per step: rtds_set_spheres (H2D from pinned) + rtds_build(LBVH) + render + gather + D2H of the RGB8 frame"},
+                        "what": "per step: rtds_frame = rtds_set_spheres (H2D from pinned) + rtds_build(LBVH) + rtds_render into a pinned host frame (N>1: the three calls + NCCL gather + D2H on rank 0)"},
                 "with_shadows": {"value": sh_rays.item() / (float(np.mean(sh_steps)) * 1e-3) / 1e6, "unit": "Mrays/s",
                                  "ms_per_step": float(np.mean(sh_steps)), "rays_per_step": int(sh_rays.item()),
                                  "note": "extension: shadow query on (the reference's trace_more is a stub); primary + shadow rays"},

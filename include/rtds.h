@@ -175,6 +175,11 @@ int rtds_trace(rtds_ctx* ctx, int acc_type, int exact, const float* o_xyz, const
  * pixel (-1 = sky). accum (optional): width*height*3 floats, the per-pixel sums before the divide. */
 int rtds_render(rtds_ctx* ctx, int acc_type, const rtds_render_params* params, uint8_t* rgb,
                 int* hit_obj, float* accum, rtds_render_stats* stats);
+/* The whole per-run sequence of main() (main.cpp:751,800/816/832,808) in ONE synchronous call: rtds_set_spheres ->
+ * rtds_build -> rtds_render with the stages overlapped on the device (the material table is still uploading while the
+ * structure is built). Equivalent to the three calls; bst / rst may be NULL. */
+int rtds_frame(rtds_ctx* ctx, const float* cxyz_r, const float* rgb_mat, int n, int acc_type, const rtds_build_params* bp,
+               const rtds_render_params* rp, uint8_t* rgb, rtds_build_stats* bst, rtds_render_stats* rst);
 /* Same, result left on the device: d_rgb_rows is a DEVICE pointer receiving this rank's rows compactly
  * (local row-tile j = global tile j*world + rank), rtds_rows_for_rank(...)*width*3 bytes. Used by the
  * multi-GPU framebuffer gather (NCCL) and by resident-input timing. */

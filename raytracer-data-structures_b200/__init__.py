@@ -88,7 +88,7 @@ assert LINEAR_NODE_DTYPE.itemsize == 32 and KD_NODE_DTYPE.itemsize == 12
 ABI_SYMBOLS = ["rtds_last_error", "rtds_version", "rtds_create", "rtds_destroy", "rtds_set_spheres",
                "rtds_set_triangles", "rtds_set_lights", "rtds_build", "rtds_export_bvh", "rtds_export_kd",
                "rtds_export_morton", "rtds_trace", "rtds_render", "rtds_render_device", "rtds_rows_for_rank",
-               "rtds_jitter_stream", "rtds_morton30"]
+               "rtds_jitter_stream", "rtds_morton30", "rtds_frame"]
 
 _lib = None
 
@@ -117,6 +117,8 @@ def load_library(path: str = LIB_PATH):
     lib.rtds_trace.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.POINTER(RenderStats)]
     lib.rtds_render.argtypes = [vp, C.c_int, C.POINTER(RenderParams), vp, vp, vp, C.POINTER(RenderStats)]
     lib.rtds_render_device.argtypes = [vp, C.c_int, C.POINTER(RenderParams), vp, C.POINTER(RenderStats)]
+    lib.rtds_frame.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.POINTER(BuildParams), C.POINTER(RenderParams), vp, C.POINTER(BuildStats),
+                               C.POINTER(RenderStats)]
     lib.rtds_rows_for_rank.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     lib.rtds_jitter_stream.argtypes = [vp, C.c_uint64, C.c_int, vp]
     lib.rtds_morton30.argtypes = [vp, vp, C.c_int, vp]
@@ -242,6 +244,20 @@ class Rtds:
         st = RenderStats()
         self._check(self.lib.rtds_render(self.ctx, acc, C.byref(p), _ptr(rgb), _ptr(hit), _ptr(accum), C.byref(st)))
         return rgb, hit, accum, _stats_dict(st)
+
+    def frame(self, cxyz_r, rgb_mat, acc, width, height, aa_samples=1, mode=MODE_COMPAT, out=None, **kw):
+        """rtds_frame: upload + build + render + download in one call (what main() does per run)."""
+        cxyz_r = np.ascontiguousarray(cxyz_r, np.float32).reshape(-1, 4)
+        rgb_mat = None if rgb_mat is None else np.ascontiguousarray(rgb_mat, np.float32).reshape(-1, 4)
+        bp = BuildParams()
+        bp.mode = mode
+        rp = self.render_params(width, height, aa_samples, **kw)
+        rgb = out if out is not None else np.zeros((height, width, 3), np.uint8)
+        bst, rst = BuildStats(), RenderStats()
+        self._check(self.lib.rtds_frame(self.ctx, _ptr(cxyz_r), _ptr(rgb_mat), cxyz_r.shape[0], acc, C.byref(bp), C.byref(rp), _ptr(rgb),
+                                        C.byref(bst), C.byref(rst)))
+        self.n = cxyz_r.shape[0]
+        return rgb, _stats_dict(bst), _stats_dict(rst)
 
     def render_device(self, acc, params, device_ptr):
         st = RenderStats()

@@ -151,11 +151,16 @@ int rtds_destroy(rtds_ctx* c)
     return RTDS_OK;
 }
 
-int rtds_set_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n)
+}  // extern "C" (internal helpers follow)
+
+// async_mat: the material table goes up on the copy stream (with the material-flag kernel behind it) and is only
+// waited for by finish_materials(); the sphere table is complete on return either way.
+static int upload_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n, bool async_mat)
 {
     if (!c || !cxyz_r || n <= 0) { rtds_set_error("set_spheres: bad arguments"); return RTDS_ERR_INVALID; }
     RTDS_CUDA(cudaSetDevice(c->device));
     RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    RTDS_CUDA(cudaStreamSynchronize(c->copy_stream));
     c->n = 0;
     c->prim_type = 0;
     c->bvh.valid = false; c->kd.valid = false; c->bvh_acc = -1;
@@ -169,15 +174,19 @@ int rtds_set_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int
     }
     RTDS_CUDA(cudaMemcpyAsync(c->d_sph, cxyz_r, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     c->has_materials = false;
+    c->materials_pending = false;
     if (rgb_mat) {
-        RTDS_CUDA(cudaMemcpyAsync(c->d_mat, rgb_mat, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        cudaStream_t ms = async_mat ? c->copy_stream : c->stream;
+        if (async_mat) {   // the sphere table first (the build waits for it), the materials behind it on the same link
+            RTDS_CUDA(cudaEventRecord(c->ev_band, c->stream));
+            RTDS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_band, 0));
+        }
+        RTDS_CUDA(cudaMemcpyAsync(c->d_mat, rgb_mat, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, ms));
         int* d_flag = (int*)(c->d_counters + 6);
-        RTDS_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
-        material_flag_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_mat, n, d_flag);
-        int flag = 0;
-        RTDS_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        RTDS_CUDA(cudaStreamSynchronize(c->stream));
-        c->has_materials = flag != 0;
+        RTDS_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), ms));
+        material_flag_kernel<<<(n + 255) / 256, 256, 0, ms>>>(c->d_mat, n, d_flag);
+        c->materials_pending = true;
+        if (!async_mat) RTDS_TRY(rtds_finish_materials(c));
     } else {
         std::vector<float> m((size_t)n * 4);
         for (int i = 0; i < n; ++i) { m[4 * i] = 0.8f; m[4 * i + 1] = 0.7f; m[4 * i + 2] = 0.0f; m[4 * i + 3] = 0.f; }  // main.cpp:689
@@ -187,6 +196,37 @@ int rtds_set_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int
     RTDS_CUDA(cudaStreamSynchronize(c->stream));
     c->n = n;
     return RTDS_OK;
+}
+
+int rtds_finish_materials(rtds_ctx* c)
+{
+    if (!c->materials_pending) return RTDS_OK;
+    int flag = 0;
+    RTDS_CUDA(cudaStreamSynchronize(c->copy_stream));
+    RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    RTDS_CUDA(cudaMemcpy(&flag, (int*)(c->d_counters + 6), sizeof(int), cudaMemcpyDeviceToHost));
+    c->has_materials = flag != 0;
+    c->materials_pending = false;
+    return RTDS_OK;
+}
+
+extern "C" {
+
+int rtds_set_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n)
+{
+    return upload_spheres(c, cxyz_r, rgb_mat, n, false);
+}
+
+// What main() does per run, in one synchronous call with the stages overlapped: sphere table up -> build, while the
+// material table is still uploading on the copy stream -> render -> frame down.
+int rtds_frame(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n, int acc, const rtds_build_params* bp,
+               const rtds_render_params* rp, uint8_t* rgb, rtds_build_stats* bst, rtds_render_stats* rst)
+{
+    if (!c || !rp || !rgb) { rtds_set_error("frame: bad arguments"); return RTDS_ERR_INVALID; }
+    RTDS_TRY(upload_spheres(c, cxyz_r, rgb_mat, n, true));
+    RTDS_TRY(rtds_build(c, acc, bp, bst));
+    RTDS_TRY(rtds_finish_materials(c));
+    return rtds_render(c, acc, rp, rgb, nullptr, nullptr, rst);
 }
 
 int rtds_set_triangles(rtds_ctx* c, const float* v0v1v2, const float* rgb_mat, int n)

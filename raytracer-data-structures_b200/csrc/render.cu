@@ -1226,6 +1226,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     if (rank < 0 || rank >= world) { rtds_set_error("render: rank %d outside world %d", rank, world); return RTDS_ERR_INVALID; }
     const int tile_rows = p->tile_rows > 0 ? p->tile_rows : 8;
     if (ctx->n <= 0) { rtds_set_error("render: no scene"); return RTDS_ERR_NO_SCENE; }
+    RTDS_TRY(rtds_finish_materials(ctx));
     const bool kdt = acc == RTDS_KDTREE;
     if (kdt && !ctx->kd.valid) { rtds_set_error("render: KDTREE requested but no KD-tree has been built"); return RTDS_ERR_NOT_BUILT; }
     const bool brute = (acc != RTDS_BVH && acc != RTDS_LBVH && !kdt);

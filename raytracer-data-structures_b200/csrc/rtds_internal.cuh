@@ -96,6 +96,7 @@ struct rtds_ctx {
     float4* d_sph = nullptr;     // {cx,cy,cz,r}
     float4* d_mat = nullptr;     // {r,g,b,(float)material}
     bool    has_materials = false;   // any primitive with a non-DIFFUSE_AND_GLOSSY material
+    bool    materials_pending = false;   // the material upload / flag kernel is still in flight on the copy stream
     int     n_lights = 0;
     RtdsLight lights[RTDS_MAX_LIGHTS];
 
@@ -143,6 +144,7 @@ struct PrimView { int type; const float4* sph; const float4* tri; };
 inline PrimView rtds_prim_view(const rtds_ctx* c) { return PrimView{c->prim_type, c->d_sph, c->d_tris}; }
 int rtds_alloc_bvh_for(rtds_ctx* ctx, DeviceBvh& b, int n_prims);
 
+int rtds_finish_materials(rtds_ctx* ctx);
 int rtds_ensure_scratch(rtds_ctx* ctx, size_t bytes);
 template <typename T> int rtds_realloc(T** p, size_t* cap_bytes, size_t need_bytes);
 

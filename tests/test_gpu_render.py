@@ -126,3 +126,15 @@ def test_fused_strip_kernel_is_exact_too(gpu_ctx, oracle, monkeypatch):
         rows = rt.owned_rows(H, 8, rank, 3)
         frame[rows] = part[rows]
     assert np.array_equal(frame, full)
+
+
+def test_rtds_frame_equals_the_three_calls(gpu_ctx):
+    sph, mat = T.bunny_scene()
+    rgb, bst, rst = gpu_ctx.frame(sph, mat, rt.BVH, 640, 480, 1)
+    assert T.ppm_md5(rgb) == "c69c66375f2c6bda433f9f457a4b2b2e" and bst["total_nodes"] == 71895
+    sph2, mat2 = T.material_scene(1500, 11)
+    rgb_a, _, _ = gpu_ctx.frame(sph2, mat2, rt.LBVH, 240, 180, 2, mode=rt.MODE_TRUE, shadows=1)
+    gpu_ctx.set_spheres(sph2, mat2)
+    gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+    rgb_b, _, _, _ = gpu_ctx.render(rt.LBVH, 240, 180, 2, shadows=1)
+    assert np.array_equal(rgb_a, rgb_b)
