@@ -14,6 +14,7 @@
 // primitive sits at a tied split position may differ; costs, split positions and counts do not depend on it.
 // Parity for KD is therefore judged on hit results — node counts are reported next to the reference's.
 #include "rtds_internal.cuh"
+#include "scan.cuh"
 #include <math.h>
 #include <algorithm>
 
@@ -41,85 +42,8 @@ struct KdNode {                 // build-time node, breadth-first order
 
 struct KdParams { int max_prims; float isect_cost; float traversal_cost; float empty_bonus; };
 
-// ---------------------------------------------------------------------------------------------------
-// exclusive scan of 32-bit values (three kernels; n up to 2^31)
-// ---------------------------------------------------------------------------------------------------
-constexpr int SC_BLOCK = 256, SC_ITEMS = 8, SC_TILE = SC_BLOCK * SC_ITEMS;
-
-__global__ void __launch_bounds__(SC_BLOCK) scan_tile_sums(const int* __restrict__ in, int n, int* __restrict__ sums)
-{
-    __shared__ int ws[SC_BLOCK / 32];
-    long long base = (long long)blockIdx.x * SC_TILE;
-    int v = 0;
-    for (int i = threadIdx.x; i < SC_TILE; i += SC_BLOCK) { long long p = base + i; v += p < n ? in[p] : 0; }
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < SC_BLOCK / 32; ++w) t += ws[w]; sums[blockIdx.x] = t; }
-}
-__global__ void __launch_bounds__(1024) scan_sums(int* sums, int tiles, int* total)
-{
-    __shared__ int sh[1024];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < tiles; base += 1024) {
-        int i = base + threadIdx.x;
-        int v = i < tiles ? sums[i] : 0;
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-            __syncthreads();
-            sh[threadIdx.x] += t;
-            __syncthreads();
-        }
-        if (i < tiles) sums[i] = carry + sh[threadIdx.x] - v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += sh[1023];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && total) *total = carry;
-}
-__global__ void __launch_bounds__(SC_BLOCK) scan_apply(const int* __restrict__ in, int n, const int* __restrict__ sums, int* __restrict__ out)
-{
-    __shared__ int ws[SC_BLOCK / 32];
-    __shared__ int running;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) running = sums[blockIdx.x];
-    __syncthreads();
-    long long base = (long long)blockIdx.x * SC_TILE;
-    for (int it = 0; it < SC_ITEMS; ++it) {
-        long long p = base + it * SC_BLOCK + threadIdx.x;
-        int v = p < n ? in[p] : 0;
-        int x = v;
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
-        if (lane == 31) ws[warp] = x;
-        __syncthreads();
-        int woff = 0, chunk = 0;
-        for (int w = 0; w < SC_BLOCK / 32; ++w) { int c = ws[w]; woff += (w < warp) ? c : 0; chunk += c; }
-        const int start = running;
-        if (p < n) out[p] = start + woff + x - v;
-        __syncthreads();
-        if (threadIdx.x == 0) running = start + chunk;
-        __syncthreads();
-    }
-}
-
-struct Scanner {
-    rtds_ctx* ctx; int* sums; int cap_tiles; int* d_total;
-    int run(const int* in, int* out, int n, int* launches)
-    {
-        if (n <= 0) { cudaMemsetAsync(d_total, 0, sizeof(int), ctx->stream); return RTDS_OK; }
-        int tiles = (n + SC_TILE - 1) / SC_TILE;
-        if (tiles > cap_tiles) { rtds_set_error("kd scan: workspace too small"); return RTDS_ERR_CAPACITY; }
-        scan_tile_sums<<<tiles, SC_BLOCK, 0, ctx->stream>>>(in, n, sums);
-        scan_sums<<<1, 1024, 0, ctx->stream>>>(sums, tiles, d_total);
-        scan_apply<<<tiles, SC_BLOCK, 0, ctx->stream>>>(in, n, sums, out);
-        if (launches) *launches += 3;
-        return RTDS_OK;
-    }
-};
+using rtds_scan::Scanner;
+using rtds_scan::SC_TILE;
 
 // ---------------------------------------------------------------------------------------------------
 // level kernels
@@ -512,7 +436,6 @@ static int build_kd_attempt(rtds_ctx* ctx, const rtds_build_params* bp, rtds_bui
                 kd_gen_edges<<<G(n_entries), T, 0, s>>>(nodes, idx[cur], owner[cur], n_entries, rtds_prim_view(ctx), keys, vals);
                 ++launches;
                 RTDS_TRY(rtds_onesweep_sort_u64(ctx, (uint64_t*)keys, vals, (uint64_t*)keys_tmp, vals_tmp, n_edges, 33 + slot_bits, &launches));
-                if (((33 + slot_bits + 7) / 8) & 1) { /* odd pass count: rtds_onesweep_sort copies back */ }
                 kd_start_flags<<<G(n_edges), T, 0, s>>>(keys, n_edges, eflag);
                 RTDS_TRY(scan.run(eflag, start_scan, n_edges, &launches));
                 kd_reset_best<<<G(n_slots), T, 0, s>>>(best, n_slots);
@@ -524,9 +447,8 @@ static int build_kd_attempt(rtds_ctx* ctx, const rtds_build_params* bp, rtds_bui
                 RTDS_CUDA(cudaMemcpyAsync(&n_retry, d_small + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
                 RTDS_CUDA(cudaStreamSynchronize(s));
                 if (n_retry == 0) break;
-                // Nodes that found a split keep state 3/2 and ignore the re-generated edges of later rounds, but
-                // their edges are still needed for classification: later rounds regenerate ALL pending nodes' edges
-                // only, so classification below regenerates once more for everybody (see kd_regen below).
+                // Later rounds regenerate the edges of the still-pending nodes only; a decided node's segment stays
+                // sorted in place (the sort is stable and groups by slot), so its best_off keeps pointing at its edge.
             }
             // publish interior flags / child entry counts
             kd_decide<<<G(n_slots), T, 0, s>>>(nodes, slot_to_node, n_slots, best, keys, start_scan, P, 1, d_small + 1, nflag, ncnt);

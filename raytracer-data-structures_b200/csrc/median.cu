@@ -33,7 +33,6 @@ struct Task { int s, e, parent_enc; };   // parent_enc = parent*2+side, -1 for t
 
 struct MedianArgs {
     PrimView pv;             // objId -> centre / AABB
-    float4* leaf_tri_unused;
     int*   perm;             // scene position -> objId
     float* key;              // scene position -> centre[dim] of the task that owns the position
     int*   la;               // scratch lists, indexed by scene position
@@ -730,7 +729,7 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
     RTDS_TRY(rtds_ensure_scratch(ctx, total));
     char* base = (char*)ctx->d_scratch;
     MedianArgs A;
-    A.pv = rtds_prim_view(ctx); A.leaf_tri_unused = nullptr;
+    A.pv = rtds_prim_view(ctx);
     A.perm = (int*)(base + o_perm); A.key = (float*)(base + o_key); A.la = (int*)(base + o_la); A.lb = (int*)(base + o_lb);
     A.leaf_info = (int*)(base + o_info); A.nodes = b.nodes; A.root_box = (float*)(base + o_root); A.counters = (int*)(base + o_cnt);
     A.tasks_a = (Task*)(base + o_ta); A.tasks_b = (Task*)(base + o_tb);

@@ -12,6 +12,7 @@
 // Level-synchronous: bounds and bins are accumulated with exact, order-independent atomics (min/max on ordered
 // uints, integer adds), the stable partition is one global scan per level, boxes come from one atomic refit.
 #include "rtds_internal.cuh"
+#include "scan.cuh"
 #include <math.h>
 #include <algorithm>
 
@@ -253,47 +254,6 @@ __global__ void sah_init(int* perm, int* owner, int n)
     if (i < n) { perm[i] = i; owner[i] = n >= 2 ? 0 : -1; }
 }
 
-// ---- exclusive scan (same three-kernel scheme as kd.cu, kept local to this translation unit) ----
-constexpr int SC_BLOCK = 256, SC_ITEMS = 8, SC_TILE = SC_BLOCK * SC_ITEMS;
-__global__ void __launch_bounds__(SC_BLOCK) s_tile_sums(const int* __restrict__ in, int n, int* __restrict__ sums)
-{
-    __shared__ int ws[SC_BLOCK / 32];
-    long long base = (long long)blockIdx.x * SC_TILE;
-    int v = 0;
-    for (int i = threadIdx.x; i < SC_TILE; i += SC_BLOCK) { long long p = base + i; v += p < n ? in[p] : 0; }
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < SC_BLOCK / 32; ++w) t += ws[w]; sums[blockIdx.x] = t; }
-}
-__global__ void s_scan_sums(int* sums, int tiles, int* total)
-{
-    if (threadIdx.x == 0) { int run = 0; for (int i = 0; i < tiles; ++i) { int c = sums[i]; sums[i] = run; run += c; } *total = run; }
-}
-__global__ void __launch_bounds__(SC_BLOCK) s_apply(const int* __restrict__ in, int n, const int* __restrict__ sums, int* __restrict__ out)
-{
-    __shared__ int ws[SC_BLOCK / 32];
-    __shared__ int running;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) running = sums[blockIdx.x];
-    __syncthreads();
-    long long base = (long long)blockIdx.x * SC_TILE;
-    for (int it = 0; it < SC_ITEMS; ++it) {
-        long long p = base + it * SC_BLOCK + threadIdx.x;
-        int v = p < n ? in[p] : 0, x = v;
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
-        if (lane == 31) ws[warp] = x;
-        __syncthreads();
-        int woff = 0, chunk = 0;
-        for (int w = 0; w < SC_BLOCK / 32; ++w) { int c = ws[w]; woff += (w < warp) ? c : 0; chunk += c; }
-        const int start = running;
-        if (p < n) out[p] = start + woff + x - v;
-        __syncthreads();
-        if (threadIdx.x == 0) running = start + chunk;
-        __syncthreads();
-    }
-}
-
 template <typename T> T* carve(char*& p, size_t count)
 {
     T* r = (T*)p;
@@ -311,7 +271,7 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats*
     RTDS_TRY(rtds_alloc_bvh_for(ctx, b, n));
     const PrimView pv = rtds_prim_view(ctx);
     const size_t max_tasks = (size_t)n / 2 + 2;
-    const int tiles = (int)(((size_t)std::max<size_t>(n, 2 * max_tasks) + SC_TILE - 1) / SC_TILE) + 1;
+    const int tiles = (int)(((size_t)std::max<size_t>(n, 2 * max_tasks) + rtds_scan::SC_TILE - 1) / rtds_scan::SC_TILE) + 1;
     size_t bytes = 6 * (((size_t)n * 4 + 255) & ~(size_t)255) + 2 * ((sizeof(SahTask) * max_tasks + 255) & ~(size_t)255) +
                    ((sizeof(SahBins) * max_tasks + 255) & ~(size_t)255) + 4 * ((8 * max_tasks + 255) & ~(size_t)255) + ((size_t)tiles * 4 + 255) +
                    (((size_t)n * 4 + 255) & ~(size_t)255) + 4096;
@@ -332,14 +292,8 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats*
     int launches = 0;
     const int T = 256;
     auto G = [&](long long m) { return (unsigned)((m + T - 1) / T); };
-    auto xscan = [&](const int* in, int* out, int m) -> int {
-        int tl = (m + SC_TILE - 1) / SC_TILE;
-        s_tile_sums<<<tl, SC_BLOCK, 0, s>>>(in, m, sums);
-        s_scan_sums<<<1, 32, 0, s>>>(sums, tl, d_small);
-        s_apply<<<tl, SC_BLOCK, 0, s>>>(in, m, sums, out);
-        launches += 3;
-        return RTDS_OK;
-    };
+    rtds_scan::Scanner scanner{ctx, sums, tiles, d_small};
+    auto xscan = [&](const int* in, int* out, int m) -> int { return scanner.run(in, out, m, &launches); };
     int* leaf_arr = carve<int>(p, n);   // scene position -> parent*2+side+2 once the position holds a finished leaf
     RTDS_CUDA(cudaEventRecord(ctx->ev0, s));
     RTDS_CUDA(cudaMemsetAsync(leaf_arr, 0, (size_t)n * 4, s));
