@@ -711,6 +711,7 @@ __global__ void iota_kernel(int* p, int n)
 }  // namespace
 
 int rtds_bvh_compute_depth(rtds_ctx* ctx, DeviceBvh& b, int* depth_out);   // lbvh.cu
+int rtds_bvh_reorder_preorder(rtds_ctx* ctx, DeviceBvh& b, void* scratch, int* launches);
 
 int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
 {
@@ -726,6 +727,7 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
            o_info = o_lb + al(4 * (size_t)n), o_ta = o_info + al(4 * (size_t)n), o_tb = o_ta + al(sizeof(Task) * ((size_t)n / 2 + 2)),
            o_cnt = o_tb + al(sizeof(Task) * ((size_t)n / 2 + 2)), o_root = o_cnt + 256, o_tiles = o_root + 256,
            o_coop = o_tiles + al(4 * (size_t)fin_tiles + 4), total = o_coop + al(sizeof(CoopScratch));
+    total = std::max(total, al(4 * (size_t)n) + sizeof(Node64) * (size_t)n + 1024);   // the final layout pass reuses the area
     RTDS_TRY(rtds_ensure_scratch(ctx, total));
     char* base = (char*)ctx->d_scratch;
     MedianArgs A;
@@ -811,6 +813,8 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
     b.n_internal = n_internal;
     b.root_ref = h_cnt[C_ROOT];
     b.tie_by_objid = 0;
+    // layout pass; the level-loop scratch (keys, lists, task arrays: > 68 bytes per primitive from the start) is free now
+    RTDS_TRY(rtds_bvh_reorder_preorder(ctx, b, base, &launches));
     int depth = 0;
     RTDS_TRY(rtds_bvh_compute_depth(ctx, b, &depth));
     ++launches;

@@ -18,6 +18,7 @@
 
 int rtds_bvh_refit(rtds_ctx* ctx, DeviceBvh& b, const uint32_t* d_ids, int n, unsigned* d_counters, float* d_root_box);  // lbvh.cu
 int rtds_bvh_compute_depth(rtds_ctx* ctx, DeviceBvh& b, int* depth_out);
+int rtds_bvh_reorder_preorder(rtds_ctx* ctx, DeviceBvh& b, void* scratch, int* launches);
 
 namespace {
 
@@ -345,6 +346,7 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats*
     b.n_internal = n - 1;
     b.root_ref = n > 1 ? 0 : ~0;
     b.tie_by_objid = 1;
+    RTDS_TRY(rtds_bvh_reorder_preorder(ctx, b, ctx->d_scratch, &launches));   // the level-loop scratch is free now
     int depth = 0;
     RTDS_TRY(rtds_bvh_compute_depth(ctx, b, &depth));
     ++launches;
