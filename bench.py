@@ -140,6 +140,28 @@ class CpuArm:
         return rays, secs
 
 
+def unmodified_binary_baseline():
+    """SURVEY 8d baseline (A): the reference program itself (oracle/_ref/ref_output, g++ -O3 of the unmodified main.cpp)
+    on its default config (bunny, 640x480, 1 spp, BVH), stdout parsed for its own timers. One core."""
+    import re
+    import tempfile
+    binp = os.path.join(ROOT, "oracle", "_ref", "ref_output")
+    if not os.path.exists(binp):
+        return None
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "models"))
+        with open(os.path.join(d, "models", "bunny.obj"), "w") as f:
+            for x, y, z in bunny_vertices():
+                f.write("v %.9g %.9g %.9g\n" % (x, y, z))
+        t0 = time.perf_counter()
+        r = subprocess.run([binp], cwd=d, capture_output=True, text=True, timeout=300)
+        wall = time.perf_counter() - t0
+        b = re.search(r"construct BVH Tree .... \nDone .... Time: ([0-9.eE+-]+)s", r.stdout)
+        t = re.search(r"Total time spent: ([0-9.eE+-]+)s", r.stdout)
+        return {"config": "settings.h defaults: bunny 640x480 aa1 BVH, 307,200 rays, incl. load + per-pixel printf + PPM write",
+                "build_s": float(b.group(1)) if b else None, "total_s": float(t.group(1)) if t else None, "wall_s": wall, "cores": 1}
+
+
 def _child_render(arm, bands, conn):
     rays, secs = arm.render_bands(bands)
     conn.send((rays, secs))
@@ -380,7 +402,8 @@ def run_ours(args):
                 rays, secs = arm.render_bands(bands)
                 line["cpu_baseline"] = {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": 1, "kind": arm.kind,
                                         "sample": f"60 bands x 2 rows of the same frame ({rays} rays), 1 thread",
-                                        "build_s": arm.build_s, "build_ms_per_mprim": 1000 * arm.build_s / (n / 1e6)}
+                                        "build_s": arm.build_s, "build_ms_per_mprim": 1000 * arm.build_s / (n / 1e6),
+                                        "unmodified_binary": unmodified_binary_baseline()}
             except Exception as ex:   # the baseline is a reported side number; never lose the bench line over it
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 1, "kind": "unavailable", "sample": repr(ex)}
         print(json.dumps(line), flush=True)
