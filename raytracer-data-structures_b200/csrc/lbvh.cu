@@ -436,6 +436,7 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
     b.n_internal = n - 1;
     b.root_ref = n > 1 ? 0 : ~0;
     b.tie_by_objid = 1;
+    b.leaf_box_prim = ctx->prim_type == 0;
     b.max_depth = depth;
     b.valid = true;
     float ms = 0;

@@ -813,6 +813,7 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
     b.n_internal = n_internal;
     b.root_ref = h_cnt[C_ROOT];
     b.tie_by_objid = 0;
+    b.leaf_box_prim = (ctx->prim_type == 0 && n_leaves == n) ? 1 : 0;   // no dropped range: every leaf is one sphere with its own box
     // layout pass; the level-loop scratch (keys, lists, task arrays: > 68 bytes per primitive from the start) is free now
     RTDS_TRY(rtds_bvh_reorder_preorder(ctx, b, base, &launches));
     int depth = 0;

@@ -249,6 +249,7 @@ struct BvhView {
     const int*    leaf_parent;
     int           root_ref;
     int           tie_by_objid;
+    int           leaf_box_prim;   // sphere leaves whose box is exactly c -/+ r
     float         root_box[6];
 };
 
@@ -257,7 +258,7 @@ constexpr int STACK_MAX = 64;
 __device__ __forceinline__ bool leaf_test(const BvhView& B, int leaf, float ox, float oy, float oz, float dx, float dy, float dz, float& t0,
                                           float& t1)
 {
-    if (B.prim_type == 0) return sphere_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_sph + leaf), t0, t1);
+    if (B.prim_type == 0) { float4 s = __ldg(B.leaf_sph + leaf); s.w = s.w * s.w; return sphere_test(ox, oy, oz, dx, dy, dz, s, t0, t1); }   // radius2 = r*r, accelerators.h:71
     float t;
     if (!tri_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_tri + 3 * (size_t)leaf), __ldg(B.leaf_tri + 3 * (size_t)leaf + 1),
                   __ldg(B.leaf_tri + 3 * (size_t)leaf + 2), t))
@@ -394,35 +395,94 @@ __device__ __forceinline__ void traverse_bvh(const BvhView& B, float ox, float o
 
 // The ordered traversal (exact = 0), written "while-while": interior nodes and leaves are both stack items, so the
 // hot interior loop is branch-light (both children go through the conservative reciprocal test, no leaf special
-// case), and a leaf is only opened when it is popped with tmin still below the current hit: there the reference's
-// EXACT slab test is run on the leaf's box (re-read from its parent's record) and then the sphere test.
+// case), and a leaf is only opened when it is popped with tmin still below the current hit.
 // ZERO_O: the ray starts at the origin (every primary ray, main.cpp:558): t = b * (1/d), one multiply per plane.
 // ANYHIT (shadow rays, main.cpp:468-473): stop at the first candidate with t'^2 < t2max. "The nearest hit satisfies
 // tNear^2 < lightDistance2" and "some candidate does" are the same predicate (every t' is >= 0), so the answer equals
 // the closest-hit formulation's; subtrees that start beyond sqrt(t2max) are never opened.
-template <bool ZERO_O, bool ANYHIT = false>
-__device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
-                                              float& tnear, int& best_key, int& best_leaf, Counters& cnt, float t2max = 0.f)
+// OCT: direction octant (bit0: dx < 0, bit1: dy < 0, bit2: dz < 0), a compile-time constant: the near / far plane of
+// every slab is then known without min/max (t = plane * (1/d) is monotone in the plane), so a box costs six multiplies,
+// one FMNMX3 for the entry and one for the exit distance. OCT < 0: generic form with per-axis min/max.
+//
+// Conservativeness. With 1e-30 < |1/d| < 1e30 every t_a = (b - o) * rcp(d) differs from the reference's
+// t_e = (b - o) / d by at most 2^-22 relative (rcp.approx 2^-23, the multiply 2^-24, the divide's own rounding 2^-24).
+//  * interior boxes / leaf filter: exit distance widened by WIDE2 = 2^-20 relative, entry distance left as computed:
+//    tmin_e <= tmax_e implies tmin_a <= tmax_a (1 + 2^-20 sign-aware) in all three sign cases, so every box the
+//    reference's test accepts is accepted. The pruning bound tlim is widened by the same 2^-20 instead of the entry
+//    distance (accepts a superset of "tmin_a (1 - 2^-21) <= tlim").
+//  * leaves whose box is the sphere's own box (c -/+ r, main.cpp:686-688): the box is rebuilt from the leaf's sphere
+//    record (no parent-record reload) and tested with the same multiplies; if the NARROWED interval (entry pushed up,
+//    exit pushed down by 2^-21) is still non-empty the reference's divide-based test accepts for certain; only the
+//    ambiguous sliver in between (and denormal-range distances) pays for the six IEEE divides. Other trees (median
+//    split with dropped ranges, triangles) run the divide test on the box stored in the parent's record.
+// Cold paths of the ordered traversal, kept OUT OF LINE so that the octant copies of the hot loop stay small
+// (instruction-cache footprint): arguments and results by value, the view by pointer into the kernel's
+// __grid_constant__ parameter block.
+struct ColdHit { float tnear; int key, leaf; unsigned node_tests, prim_tests, node_visits; };
+static __device__ __noinline__ ColdHit traverse_exact_cold(const BvhView* B, float ox, float oy, float oz, float dx, float dy, float dz,
+                                                           float tnear, int key, int leaf)
 {
-    // 1/d only feeds the conservative test (its error is inside WIDE_EPS): one MUFU.RCP each instead of an IEEE divide
-    float ix, iy, iz;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"(dx));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(dy));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(dz));
-    if (B.root_ref < 0 || !(fabsf(ix) < 1e30f && fabsf(iy) < 1e30f && fabsf(iz) < 1e30f)) {
-        // single-leaf tree, or a zero / tiny / non-finite direction component: the divide-based traversal
-        traverse_bvh<true>(B, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
-        if (ANYHIT && !(best_leaf >= 0 && tnear * tnear < t2max)) best_leaf = -1;
-        return;
+    Counters c = {0, 0, 0, 0};
+    traverse_bvh<true>(*B, ox, oy, oz, dx, dy, dz, tnear, key, leaf, c);
+    return ColdHit{tnear, key, leaf, c.node_tests, c.prim_tests, c.node_visits};
+}
+static __device__ __noinline__ bool slab_test_cold(float ox, float oy, float oz, float dx, float dy, float dz, float bx0, float by0,
+                                                   float bz0, float bx1, float by1, float bz1)
+{
+    float a, b;
+    return slab_test(ox, oy, oz, dx, dy, dz, bx0, by0, bz0, bx1, by1, bz1, a, b);
+}
+// leaf whose box is NOT its sphere's own box (triangles; median-split trees with dropped ranges): the reference's
+// divide-based test on the box stored in the parent's record, then the primitive
+struct ColdLeaf { int pass; float t0, t1; unsigned prim_tests; };
+static __device__ __noinline__ ColdLeaf leaf_parent_box_cold(const BvhView* Bp, int leaf, float ox, float oy, float oz, float dx, float dy,
+                                                             float dz)
+{
+    const BvhView& B = *Bp;
+    const int lp = __ldg(B.leaf_parent + leaf);
+    const float4* q = reinterpret_cast<const float4*>(B.nodes + (lp & 0x7fffffff));
+    const float4 q1 = __ldg(q + 1);
+    float bx0, by0, bz0, bx1, by1, bz1;
+    if (lp < 0) { const float4 q2 = __ldg(q + 2); bx0 = q1.z; by0 = q1.w; bz0 = q2.x; bx1 = q2.y; by1 = q2.z; bz1 = q2.w; }
+    else { const float4 q0 = __ldg(q); bx0 = q0.x; by0 = q0.y; bz0 = q0.z; bx1 = q0.w; by1 = q1.x; bz1 = q1.y; }
+    ColdLeaf r = {0, 0.f, 0.f, 0u};
+    float a, b2;
+    if (slab_test(ox, oy, oz, dx, dy, dz, bx0, by0, bz0, bx1, by1, bz1, a, b2)) {
+        r.prim_tests = 1;
+        r.pass = leaf_test(B, leaf, ox, oy, oz, dx, dy, dz, r.t0, r.t1) ? 1 : 0;
     }
-    // No separate root test: a leaf box that passes the reference's slab test lies inside the root box, which then
-    // passes too (nesting), so the candidate set does not depend on it; rays that miss the scene fall out of the
-    // first interior visit.
-    const float margin = prune_margin(B.root_box, ox, oy, oz);
+    return r;
+}
+
+constexpr float WIDE2 = 9.53674316e-7f;      // 2^-20
+constexpr float NARROW_EPS = 4.76837158e-7f; // 2^-21
+
+template <int OCT>
+__device__ __forceinline__ void slab_interval(float x0, float y0, float z0, float x1, float y1, float z1, float& tmin, float& tmax)
+{
+    // (x0,y0,z0) = t of the box's min planes, (x1,y1,z1) = t of its max planes
+    if (OCT >= 0) {
+        const float xn = (OCT & 1) ? x1 : x0, xf = (OCT & 1) ? x0 : x1;
+        const float yn = (OCT & 2) ? y1 : y0, yf = (OCT & 2) ? y0 : y1;
+        const float zn = (OCT & 4) ? z1 : z0, zf = (OCT & 4) ? z0 : z1;
+        tmin = fmaxf(fmaxf(xn, yn), zn);
+        tmax = fminf(fminf(xf, yf), zf);
+    } else {
+        tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+        tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+    }
+}
+
+template <bool ZERO_O, bool ANYHIT, int OCT>
+__device__ __forceinline__ void traverse_fast_loop(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
+                                                   float ix, float iy, float iz, float margin, float& tnear, int& best_key,
+                                                   int& best_leaf, Counters& cnt, float t2max)
+{
     const float neg_margin = -margin;
-    float tlim = ANYHIT ? sqrtf(t2max) + margin : tnear + margin;   // a subtree is opened only while its entry distance is <= tlim
-    int   stack[STACK_MAX];
-    float stack_t[STACK_MAX];
+    // a subtree is opened only while its entry distance is <= tlim (kept widened by 2^-20, see above)
+    float tlim = ANYHIT ? sqrtf(t2max) + margin : tnear + margin;
+    tlim = __fmaf_rn(fabsf(tlim), WIDE2, tlim);
+    int2 stack[STACK_MAX];        // {child ref, entry distance as bits}: one 8-byte local store / load per push / pop
     int sp = 0;
     int node = 0;
     unsigned visits = 0;
@@ -442,44 +502,57 @@ __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float 
                 rx0 = (q1.z - ox) * ix; ry0 = (q1.w - oy) * iy; rz0 = (q2.x - oz) * iz;
                 rx1 = (q2.y - ox) * ix; ry1 = (q2.z - oy) * iy; rz1 = (q2.w - oz) * iz;
             }
-            float tminL = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fminf(lz0, lz1));
-            float tmaxL = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fmaxf(lz0, lz1));
-            float tminR = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fminf(rz0, rz1));
-            float tmaxR = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1));
-            tminL = __fmaf_rn(-fabsf(tminL), WIDE_EPS, tminL); tmaxL = __fmaf_rn(fabsf(tmaxL), WIDE_EPS, tmaxL);
-            tminR = __fmaf_rn(-fabsf(tminR), WIDE_EPS, tminR); tmaxR = __fmaf_rn(fabsf(tmaxR), WIDE_EPS, tmaxR);
+            float tminL, tmaxL, tminR, tmaxR;
+            slab_interval<OCT>(lx0, ly0, lz0, lx1, ly1, lz1, tminL, tmaxL);
+            slab_interval<OCT>(rx0, ry0, rz0, rx1, ry1, rz1, tminR, tmaxR);
+            tmaxL = __fmaf_rn(fabsf(tmaxL), WIDE2, tmaxL);
+            tmaxR = __fmaf_rn(fabsf(tmaxR), WIDE2, tmaxR);
             const bool hitL = tminL <= fminf(tmaxL, tlim) && tmaxL >= neg_margin;
             const bool hitR = tminR <= fminf(tmaxR, tlim) && tmaxR >= neg_margin;
             if (hitL && hitR) {
                 const bool rfirst = tminR < tminL;
-                stack[sp] = rfirst ? ch.x : ch.y;
-                stack_t[sp] = rfirst ? tminL : tminR;
+                stack[sp] = make_int2(rfirst ? ch.x : ch.y, __float_as_int(rfirst ? tminL : tminR));
                 sp = min(sp + 1, STACK_MAX - 1);
                 node = rfirst ? ch.y : ch.x;
                 continue;
             }
             if (hitL | hitR) { node = hitL ? ch.x : ch.y; continue; }
         } else {
-            // leaf: exact test on its own box (in the parent's record), then the sphere
             const int leaf = ~node;
-            const int lp = __ldg(B.leaf_parent + leaf);
-            const float4* q = reinterpret_cast<const float4*>(B.nodes + (lp & 0x7fffffff));
-            const float4 q1 = __ldg(q + 1);
-            float bx0, by0, bz0, bx1, by1, bz1;
-            if (lp < 0) { const float4 q2 = __ldg(q + 2); bx0 = q1.z; by0 = q1.w; bz0 = q2.x; bx1 = q2.y; by1 = q2.z; bz1 = q2.w; }
-            else { const float4 q0 = __ldg(q); bx0 = q0.x; by0 = q0.y; bz0 = q0.z; bx1 = q0.w; by1 = q1.x; bz1 = q1.y; }
-            float a, b2;
-            if (slab_test(ox, oy, oz, dx, dy, dz, bx0, by0, bz0, bx1, by1, bz1, a, b2)) {
-                float t0, t1;
-                cnt.prim_tests++;
-                if (leaf_test(B, leaf, ox, oy, oz, dx, dy, dz, t0, t1)) {
-                    if (ANYHIT) {
-                        if (t0 < 0) t0 = t1;
-                        if (t0 * t0 < t2max) { tnear = t0; best_leaf = leaf; cnt.node_visits += visits; cnt.node_tests += 2 * visits; return; }
-                    } else {
-                        candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
-                        tlim = tnear + margin;
-                    }
+            bool pass;
+            float t0, t1;
+            if (B.leaf_box_prim) {
+                // sphere leaf: its box is c -/+ r (bit-identical to what the builder stored in the parent's record)
+                const float4 s = __ldg(B.leaf_sph + leaf);
+                const float bx0 = s.x - s.w, by0 = s.y - s.w, bz0 = s.z - s.w, bx1 = s.x + s.w, by1 = s.y + s.w, bz1 = s.z + s.w;
+                float x0, y0, z0, x1, y1, z1;
+                if (ZERO_O) { x0 = bx0 * ix; y0 = by0 * iy; z0 = bz0 * iz; x1 = bx1 * ix; y1 = by1 * iy; z1 = bz1 * iz; }
+                else {
+                    x0 = (bx0 - ox) * ix; y0 = (by0 - oy) * iy; z0 = (bz0 - oz) * iz;
+                    x1 = (bx1 - ox) * ix; y1 = (by1 - oy) * iy; z1 = (bz1 - oz) * iz;
+                }
+                float tmn, tmx;
+                slab_interval<OCT>(x0, y0, z0, x1, y1, z1, tmn, tmx);
+                pass = __fmaf_rn(fabsf(tmn), NARROW_EPS, tmn) <= __fmaf_rn(-fabsf(tmx), NARROW_EPS, tmx) &&
+                       fminf(fabsf(tmn), fabsf(tmx)) > 1e-30f;
+                if (!pass) pass = slab_test_cold(ox, oy, oz, dx, dy, dz, bx0, by0, bz0, bx1, by1, bz1);
+                if (pass) {
+                    cnt.prim_tests++;
+                    pass = sphere_test(ox, oy, oz, dx, dy, dz, make_float4(s.x, s.y, s.z, s.w * s.w), t0, t1);
+                }
+            } else {
+                const ColdLeaf r = leaf_parent_box_cold(&B, leaf, ox, oy, oz, dx, dy, dz);
+                cnt.prim_tests += r.prim_tests;
+                pass = r.pass != 0; t0 = r.t0; t1 = r.t1;
+            }
+            if (pass) {
+                if (ANYHIT) {
+                    if (t0 < 0) t0 = t1;
+                    if (t0 * t0 < t2max) { tnear = t0; best_leaf = leaf; cnt.node_visits += visits; cnt.node_tests += 2 * visits; return; }
+                } else {
+                    candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
+                    tlim = tnear + margin;
+                    tlim = __fmaf_rn(fabsf(tlim), WIDE2, tlim);
                 }
             }
         }
@@ -487,8 +560,9 @@ __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float 
         bool found = false;
         while (sp > 0) {
             --sp;
-            if (stack_t[sp] > tlim) continue;
-            node = stack[sp];
+            const int2 e = stack[sp];
+            if (__int_as_float(e.y) > tlim) continue;
+            node = e.x;
             found = true;
             break;
         }
@@ -496,6 +570,40 @@ __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float 
     }
     cnt.node_visits += visits;
     cnt.node_tests += 2 * visits;
+}
+
+// ZNEG: the caller guarantees dz < 0 (every primary ray: dz = -1 before normalisation), four octants instead of eight.
+template <bool ZERO_O, bool ANYHIT = false, bool ZNEG = false>
+__device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
+                                              float& tnear, int& best_key, int& best_leaf, Counters& cnt, float t2max = 0.f)
+{
+    // 1/d only feeds the conservative tests (its error is inside the widening): one MUFU.RCP each instead of an IEEE divide
+    float ix, iy, iz;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"(dx));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(dy));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(dz));
+    const float amin = fminf(fminf(fabsf(ix), fabsf(iy)), fabsf(iz)), amax = fmaxf(fmaxf(fabsf(ix), fabsf(iy)), fabsf(iz));
+    if (B.root_ref < 0 || !(amin > 1e-30f && amax < 1e30f)) {
+        // single-leaf tree, or a zero / tiny / huge / non-finite direction component: the divide-based traversal
+        const ColdHit h = traverse_exact_cold(&B, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf);
+        tnear = h.tnear; best_key = h.key; best_leaf = h.leaf;
+        cnt.node_tests += h.node_tests; cnt.prim_tests += h.prim_tests; cnt.node_visits += h.node_visits;
+        if (ANYHIT && !(best_leaf >= 0 && tnear * tnear < t2max)) best_leaf = -1;
+        return;
+    }
+    // No separate root test: a leaf box that passes the reference's slab test lies inside the root box, which then
+    // passes too (nesting), so the candidate set does not depend on it; rays that miss the scene fall out of the
+    // first interior visit.
+    const float margin = prune_margin(B.root_box, ox, oy, oz);
+    const int oct = (dx < 0 ? 1 : 0) | (dy < 0 ? 2 : 0) | ((ZNEG || dz < 0) ? 4 : 0);
+#define RTDS_OCT_CASE(o) case o: traverse_fast_loop<ZERO_O, ANYHIT, o>(B, ox, oy, oz, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt, t2max); break;
+    switch (oct) {
+        RTDS_OCT_CASE(4) RTDS_OCT_CASE(5) RTDS_OCT_CASE(6) RTDS_OCT_CASE(7)
+        default:
+            if (!ZNEG) switch (oct) { RTDS_OCT_CASE(0) RTDS_OCT_CASE(1) RTDS_OCT_CASE(2) RTDS_OCT_CASE(3) default: break; }
+            break;
+    }
+#undef RTDS_OCT_CASE
 }
 
 // NONE: main.cpp:376-386, spheres staged through shared memory by the whole block (all threads must call).
@@ -678,20 +786,47 @@ struct RenderArgs {
     const float4* mat;           // objId-indexed {rgb, material}
     int           n;             // primitive count for NONE
     ShadeParams   shade;
-    uint8_t* out_rgb;            // local rows x width x 3
+    uint8_t* out_rgb;            // local rows x width x 3, or the whole frame (height x width x 3) when out_global_rows
+    int      out_global_rows;    // 1: out_rgb is a full frame indexed by the GLOBAL row (possibly another GPU's memory)
     int*     out_hit;            // optional, local rows x width
     float*   out_accum;          // optional, local rows x width x 3
     unsigned long long* counters;
 };
 
-template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE, 3 = KDTREE (any-hit, unshaded: main.cpp:362-372)*/>
-__global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
+// Block coordinates from a linear block id, image QUADRANT by quadrant (top-left, top-right, bottom-left,
+// bottom-right), row-major inside a quadrant. Primary rays of one quadrant share the direction octant, so the blocks
+// resident on an SM at any time run the same octant copy of the traversal loop (instruction-cache footprint).
+__device__ __forceinline__ void quadrant_block(int b, int nbx, int nby, int& bx, int& by)
+{
+    const int hx = nbx >> 1, hy = nby >> 1, wx = nbx - hx;
+    const int n0 = hx * hy, n1 = wx * hy, n2 = hx * (nby - hy);
+    if (b < n0) { bx = b % hx; by = b / hx; return; }
+    b -= n0;
+    if (b < n1) { bx = hx + b % wx; by = b / wx; return; }
+    b -= n1;
+    if (b < n2) { bx = b % hx; by = hy + b / hx; return; }
+    b -= n2;
+    bx = hx + b % wx; by = hy + b / wx;
+}
+
+// S = lanes per pixel. S == 1: a thread owns a pixel and loops over its samples (warp = 8 x 4 pixels, block = 16 x 8).
+// S == 4: four lanes trace four consecutive samples of one pixel at the same time (warp = 4 x 2 pixels x 4 samples,
+// block = 8 x 4 pixels): the samples of a pixel walk nearly the same nodes, so a warp-wide node load touches far
+// fewer distinct cache lines (the kernel is bound by L1 tag/data throughput of divergent 16-byte node loads), and
+// the jitter words of a warp are one contiguous 512-byte run. The per-pixel float sum is still formed in sample order
+// (main.cpp:553-560) by passing the four colours through shuffles.
+template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE, 3 = KDTREE (any-hit, unshaded: main.cpp:362-372)*/, int S>
+__global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ RenderArgs A)
 {
     __shared__ float4 sh_sph[MODE == 2 ? NONE_CHUNK : 1];
-    // block = 16 x 8 pixels; warp = 8 x 4 pixels
+    constexpr int WW = S == 1 ? 8 : 4, WH = S == 1 ? 4 : 2;     // warp footprint in pixels
+    constexpr int BW = 2 * WW, BH = 2 * WH;                       // block footprint (2 x 2 warps)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int lrow = A.lrow0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const int sub = lane % S, pl = lane / S;
+    int bx, by;
+    quadrant_block(blockIdx.x, (A.width + BW - 1) / BW, (A.local_rows - A.lrow0 + BH - 1) / BH, bx, by);
+    const int px = bx * BW + (warp & 1) * WW + (pl % WW);
+    const int lrow = A.lrow0 + by * BH + (warp >> 1) * WH + pl / WW;
     const bool active = px < A.width && lrow < A.local_rows;
     int py = 0;
     if (active) {
@@ -702,9 +837,11 @@ __global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
     float acc_r = 0, acc_g = 0, acc_b = 0;
     int last_hit = -1;
     const size_t pix = (size_t)py * A.width + px;
-    for (int k = 0; k < A.spp; ++k) {
+    for (int k0 = 0; k0 < A.spp; k0 += S) {
+        const int k = k0 + sub;
+        const bool live = active && k < A.spp;
         float dx = 0, dy = 0, dz = -1;
-        if (active) {
+        if (live) {
             size_t w = A.jitter_rel + 4 * (pix * A.spp + k);
             uint4 jw = __ldg(reinterpret_cast<const uint4*>(A.jitter + w));
             double r1 = canonical53(jw.x, jw.y), r2 = canonical53(jw.z, jw.w);
@@ -718,16 +855,16 @@ __global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
         float tnear = INFINITY;
         int best_key = 0, best_leaf = -1, hit_obj = -1;
         if (MODE == 2) {
-            brute_force_block(A.prim_type, A.sph, A.tri, A.n, active, 0.f, 0.f, 0.f, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
+            brute_force_block(A.prim_type, A.sph, A.tri, A.n, live, 0.f, 0.f, 0.f, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
         } else if (MODE == 3) {
-            if (active) hit_obj = kd_any_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, cnt) ? 1 : -1;
-        } else if (active) {
+            if (live) hit_obj = kd_any_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, cnt) ? 1 : -1;
+        } else if (live) {
             if (MODE == 0) traverse_bvh<true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
-            else traverse_fast<true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+            else traverse_fast<true, false, true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
             if (best_leaf >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf);
         }
-        if (active) {
-            float r, g, b;
+        float r = 0.f, g = 0.f, b = 0.f;
+        if (live) {
             if (hit_obj < 0) { r = A.shade.bg[0]; g = A.shade.bg[1]; b = A.shade.bg[2]; }
             else if (MODE == 3) { r = 0.f; g = 0.f; b = 0.f; }       // main.cpp:369: a KD hit is black
             else {
@@ -738,16 +875,28 @@ __global__ void __launch_bounds__(128) render_kernel(const RenderArgs A)
                 else raw_normal(A.bvh.prim_type, A.bvh.leaf_sph, A.bvh.leaf_tri, (size_t)best_leaf, hx, hy, hz, nx, ny, nz);
                 shade_diffuse(A.shade, dx, dy, dz, hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b);
             }
-            acc_r += r; acc_g += g; acc_b += b;
-            last_hit = hit_obj;
+        }
+        if (S == 1) {
+            if (live) { acc_r += r; acc_g += g; acc_b += b; last_hit = hit_obj; }
+        } else {
+            // the pixel's sum in sample order: every lane of the group adds the group's colours k0, k0+1, ...
+            const int lead = lane - sub;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const float rj = __shfl_sync(0xffffffffu, r, lead + j), gj = __shfl_sync(0xffffffffu, g, lead + j),
+                            bj = __shfl_sync(0xffffffffu, b, lead + j);
+                const int hj = __shfl_sync(0xffffffffu, hit_obj, lead + j);
+                if (k0 + j < A.spp) { acc_r += rj; acc_g += gj; acc_b += bj; last_hit = hj; }
+            }
         }
     }
-    if (active) {
-        size_t o = (size_t)lrow * A.width + px;
+    if (active && sub == 0) {
+        size_t o = (size_t)(A.out_global_rows ? py : lrow) * A.width + px;
         float fs = (float)(unsigned)A.spp;
         A.out_rgb[3 * o]     = (unsigned char)(fminf(1.0f, acc_r / fs) * 255);
         A.out_rgb[3 * o + 1] = (unsigned char)(fminf(1.0f, acc_g / fs) * 255);
         A.out_rgb[3 * o + 2] = (unsigned char)(fminf(1.0f, acc_b / fs) * 255);
+        o = (size_t)lrow * A.width + px;
         if (A.out_hit) A.out_hit[o] = last_hit;
         if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
     }
@@ -787,7 +936,7 @@ __device__ __forceinline__ void mt_regen_128(const uint32_t* __restrict__ A, uin
 }
 
 template <int MODE /*0 = BVH exact, 1 = BVH ordered, 3 = KDTREE*/>
-__global__ void __launch_bounds__(STRIP_THREADS) render_strip_kernel(const RenderArgs A)
+__global__ void __launch_bounds__(STRIP_THREADS) render_strip_kernel(const __grid_constant__ RenderArgs A)
 {
     __shared__ uint32_t S[2][MT_N];
     __shared__ __align__(16) uint32_t words[STRIP_REGENS * MT_N];
@@ -842,7 +991,7 @@ __global__ void __launch_bounds__(STRIP_THREADS) render_strip_kernel(const Rende
             if (MODE == 3) hit_obj = kd_any_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, cnt) ? 1 : -1;
             else {
                 if (MODE == 0) traverse_bvh<true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
-                else traverse_fast<true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+                else traverse_fast<true, false, true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
                 if (best_leaf >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf);
             }
             float r, g, b;
@@ -952,7 +1101,7 @@ __device__ __forceinline__ bool occluded(const RenderArgs& A, float ox, float oy
 }
 
 template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE*/>
-__global__ void __launch_bounds__(128) render_full_kernel(const RenderArgs A)
+__global__ void __launch_bounds__(128) render_full_kernel(const __grid_constant__ RenderArgs A)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
@@ -1079,7 +1228,7 @@ struct TraceArgs {
 };
 
 template <int MODE /*0 BVH, 2 NONE, 3 KDTREE*/>
-__global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A)
+__global__ void __launch_bounds__(128) trace_kernel(const __grid_constant__ TraceArgs A)
 {
     __shared__ float4 sh_sph[MODE == 2 ? NONE_CHUNK : 1];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1119,7 +1268,7 @@ BvhView make_view(const DeviceBvh& b)
 {
     BvhView v;
     v.nodes = b.nodes; v.leaf_sph = b.leaf_sph; v.prim_order = b.prim_order; v.leaf_parent = b.leaf_parent; v.leaf_tri = b.leaf_tri; v.prim_type = b.prim_type;
-    v.root_ref = b.root_ref; v.tie_by_objid = b.tie_by_objid;
+    v.root_ref = b.root_ref; v.tie_by_objid = b.tie_by_objid; v.leaf_box_prim = b.leaf_box_prim;
     for (int i = 0; i < 6; ++i) v.root_box[i] = b.root_box[i];
     return v;
 }
@@ -1253,7 +1402,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.shade.shadows = p->shadows;
     const bool full = p->shadows || ctx->has_materials;
     if (full && kdt) { rtds_set_error("render: the KDTREE path is any-hit and unshaded (main.cpp:362-372); shadows/materials need BVH, LBVH or NONE"); return RTDS_ERR_UNSUPPORTED; }
-    A.out_rgb = d_rgb_rows; A.out_hit = d_hit; A.out_accum = d_accum;
+    A.out_rgb = d_rgb_rows; A.out_hit = d_hit; A.out_accum = d_accum; A.out_global_rows = 0;
     A.counters = ctx->d_counters;
 
     cudaStream_t s = ctx->stream;
@@ -1307,15 +1456,25 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             A.lrow0 = r0;
             A.local_rows = r1;
             dim3 grid((W + 15) / 16, (r1 - r0 + 7) / 8), block(128);
+            // lanes per pixel of render_kernel: 4 when the samples fill the groups (see the kernel's header)
+            int spl = 1;
+            if (const char* e = getenv("RTDS_SPL")) { const int v = atoi(e); if (v == 1 || v == 4) spl = v; }
+            const unsigned lin1 = grid.x * grid.y, lin4 = (unsigned)((W + 7) / 8) * (unsigned)((r1 - r0 + 3) / 4);
             if (full) {
                 if (brute) render_full_kernel<2><<<grid, block, 0, s>>>(A);
                 else if (p->exact) render_full_kernel<0><<<grid, block, 0, s>>>(A);
                 else render_full_kernel<1><<<grid, block, 0, s>>>(A);
             }
-            else if (kdt) render_kernel<3><<<grid, block, 0, s>>>(A);
-            else if (brute) render_kernel<2><<<grid, block, 0, s>>>(A);
-            else if (p->exact) render_kernel<0><<<grid, block, 0, s>>>(A);
-            else render_kernel<1><<<grid, block, 0, s>>>(A);
+            else if (spl == 4) {
+                if (kdt) render_kernel<3, 4><<<lin4, block, 0, s>>>(A);
+                else if (brute) render_kernel<2, 4><<<lin4, block, 0, s>>>(A);
+                else if (p->exact) render_kernel<0, 4><<<lin4, block, 0, s>>>(A);
+                else render_kernel<1, 4><<<lin4, block, 0, s>>>(A);
+            }
+            else if (kdt) render_kernel<3, 1><<<lin1, block, 0, s>>>(A);
+            else if (brute) render_kernel<2, 1><<<lin1, block, 0, s>>>(A);
+            else if (p->exact) render_kernel<0, 1><<<lin1, block, 0, s>>>(A);
+            else render_kernel<1, 1><<<lin1, block, 0, s>>>(A);
             launches += 1;
             // the kernel-time event goes in BEFORE the band callback: a device->host copy into pageable memory blocks the
             // host, and an event recorded after it would time the copy as well

@@ -55,7 +55,7 @@ struct DeviceBvh {
     int      n_internal = 0;       // n_prims - 1 (0 when n_prims == 1)
     int      root_ref = 0;         // 0 (interior node 0) or ~0 when the tree is a single leaf
     Node64*  nodes = nullptr;      // [n_internal]
-    float4*  leaf_sph = nullptr;   // [n_prims] {cx,cy,cz,r^2} in leaf order (radius2 = r*r, accelerators.h:71)
+    float4*  leaf_sph = nullptr;   // [n_prims] {cx,cy,cz,r} in leaf order (radius2 = r*r is formed at the test, accelerators.h:71)
     float4*  leaf_tri = nullptr;   // [3*n_prims] v0,v1,v2 in leaf order when the scene holds triangles (extension)
     int      tri_capacity = 0;
     int      prim_type = 0;        // 0 spheres, 1 triangles
@@ -65,6 +65,9 @@ struct DeviceBvh {
     int      tie_by_objid = 0;     // 1: equal-t candidates resolve to the lower objId (NONE order,
                                    // main.cpp:376-386); 0: to the lower leaf position (DFS order of
                                    // boxIntersect, accelerators.h:668-690)
+    int      leaf_box_prim = 0;    // 1: sphere leaves and every leaf's box is exactly c -/+ r of its sphere (main.cpp:686-688);
+                                   // 0: triangles, or a median-split tree with dropped ranges (a leaf then carries the box of
+                                   // its whole range, accelerators.h:321-327)
     int      max_depth = 0;
     bool     valid = false;
 };
@@ -218,7 +221,7 @@ __device__ __forceinline__ void prim_store_leaf(const PrimView& pv, int prim, in
 {
     if (pv.type == 0) {
         float4 s = __ldg(pv.sph + prim);
-        leaf_sph[leafpos] = make_float4(s.x, s.y, s.z, s.w * s.w);
+        leaf_sph[leafpos] = s;
     } else {
         for (int k = 0; k < 3; ++k) leaf_tri[3 * (size_t)leafpos + k] = __ldg(pv.tri + 3 * (size_t)prim + k);
     }

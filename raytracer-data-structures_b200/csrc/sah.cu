@@ -346,6 +346,7 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats*
     b.n_internal = n - 1;
     b.root_ref = n > 1 ? 0 : ~0;
     b.tie_by_objid = 1;
+    b.leaf_box_prim = ctx->prim_type == 0;
     RTDS_TRY(rtds_bvh_reorder_preorder(ctx, b, ctx->d_scratch, &launches));   // the level-loop scratch is free now
     int depth = 0;
     RTDS_TRY(rtds_bvh_compute_depth(ctx, b, &depth));
