@@ -606,6 +606,118 @@ __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float 
 #undef RTDS_OCT_CASE
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Packet traversal: the PK = 4 consecutive samples of ONE pixel walk the tree together in one thread.
+// Why: the render kernel is bound by the L1 data pipe — every visit moves 56 bytes of node record into each lane's
+// registers (ncu: l1tex data-pipe wavefronts 65-75 % of peak, issue slots 61 %). The samples of a pixel differ by
+// sub-pixel jitter and walk nearly the same nodes, so one node load (and one stack push / pop) is shared by four
+// rays; the slab arithmetic is done per ray on the loaded record.
+// Why it returns the same hits: a sphere is a candidate of ray j iff its OWN leaf box passes the reference's slab
+// test for ray j (leaf boxes nest in every ancestor's box), a purely leaf-local criterion. The packet descends into a
+// child when ANY ray's conservative test accepts it, so each ray sees a superset of the leaves its own traversal
+// would open; at a leaf every ray runs its own narrow-accept / divide test and sphere test; pruning uses each ray's
+// own bound (a subtree is skipped only when no ray can still improve there), and equal-t candidates are resolved by
+// the order-independent key as before. Requires a common direction octant (checked by the caller) and sphere
+// leaves with their own boxes (leaf_box_prim).
+// ---------------------------------------------------------------------------------------------------
+constexpr int PK = 4;
+template <int OCT>
+__device__ __forceinline__ void traverse_packet(const BvhView& B, const float (&dx)[PK], const float (&dy)[PK], const float (&dz)[PK],
+                                                const float (&ix)[PK], const float (&iy)[PK], const float (&iz)[PK], float margin,
+                                                float (&tnear)[PK], int (&best_key)[PK], int (&best_leaf)[PK], Counters& cnt)
+{
+    const float neg_margin = -margin;
+    float tlim[PK];
+#pragma unroll
+    for (int j = 0; j < PK; ++j) { tlim[j] = tnear[j] + margin; tlim[j] = __fmaf_rn(fabsf(tlim[j]), WIDE2, tlim[j]); }
+    float tlim_max = fmaxf(fmaxf(tlim[0], tlim[1]), fmaxf(tlim[2], tlim[3]));
+    int2 stack[STACK_MAX];
+    int sp = 0;
+    int node = 0;
+    unsigned visits = 0, prim_tests = 0;
+    while (true) {
+        if (node >= 0) {
+            const float4* q = reinterpret_cast<const float4*>(B.nodes + node);
+            const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+            const int2 ch = __ldg(reinterpret_cast<const int2*>(q + 3));
+            ++visits;
+            float tL = INFINITY, tR = INFINITY;     // packet entry distances: min over the rays that accept the child
+#pragma unroll
+            for (int j = 0; j < PK; ++j) {
+                float tminL, tmaxL, tminR, tmaxR;
+                slab_interval<OCT>(q0.x * ix[j], q0.y * iy[j], q0.z * iz[j], q0.w * ix[j], q1.x * iy[j], q1.y * iz[j], tminL, tmaxL);
+                slab_interval<OCT>(q1.z * ix[j], q1.w * iy[j], q2.x * iz[j], q2.y * ix[j], q2.z * iy[j], q2.w * iz[j], tminR, tmaxR);
+                tmaxL = __fmaf_rn(fabsf(tmaxL), WIDE2, tmaxL);
+                tmaxR = __fmaf_rn(fabsf(tmaxR), WIDE2, tmaxR);
+                const bool a = tminL <= fminf(tmaxL, tlim[j]) && tmaxL >= neg_margin;
+                const bool b = tminR <= fminf(tmaxR, tlim[j]) && tmaxR >= neg_margin;
+                tL = a ? fminf(tL, tminL) : tL;
+                tR = b ? fminf(tR, tminR) : tR;
+            }
+            const bool hitL = tL < INFINITY, hitR = tR < INFINITY;
+            if (hitL && hitR) {
+                const bool rfirst = tR < tL;
+                stack[sp] = make_int2(rfirst ? ch.x : ch.y, __float_as_int(rfirst ? tL : tR));
+                sp = min(sp + 1, STACK_MAX - 1);
+                node = rfirst ? ch.y : ch.x;
+                continue;
+            }
+            if (hitL | hitR) { node = hitL ? ch.x : ch.y; continue; }
+        } else {
+            const int leaf = ~node;
+            const float4 s = __ldg(B.leaf_sph + leaf);
+            const float bx0 = s.x - s.w, by0 = s.y - s.w, bz0 = s.z - s.w, bx1 = s.x + s.w, by1 = s.y + s.w, bz1 = s.z + s.w;
+            const float4 s2 = make_float4(s.x, s.y, s.z, s.w * s.w);
+            int key = leaf;
+            if (B.tie_by_objid) key = __ldg(B.prim_order + leaf);
+#pragma unroll
+            for (int j = 0; j < PK; ++j) {
+                float tmn, tmx;
+                slab_interval<OCT>(bx0 * ix[j], by0 * iy[j], bz0 * iz[j], bx1 * ix[j], by1 * iy[j], bz1 * iz[j], tmn, tmx);
+                bool pass = __fmaf_rn(fabsf(tmn), NARROW_EPS, tmn) <= __fmaf_rn(-fabsf(tmx), NARROW_EPS, tmx) &&
+                            fminf(fabsf(tmn), fabsf(tmx)) > 1e-30f;
+                // the sliver between "certainly accepted" and "rejected even by the widened interval" takes the divides
+                if (!pass && tmn <= __fmaf_rn(fabsf(tmx), WIDE2, tmx))
+                    pass = slab_test_cold(0.f, 0.f, 0.f, dx[j], dy[j], dz[j], bx0, by0, bz0, bx1, by1, bz1);
+                if (pass) {
+                    float t0, t1;
+                    ++prim_tests;
+                    if (sphere_test(0.f, 0.f, 0.f, dx[j], dy[j], dz[j], s2, t0, t1)) {
+                        candidate(t0, t1, key, leaf, tnear[j], best_key[j], best_leaf[j]);
+                        tlim[j] = tnear[j] + margin;
+                        tlim[j] = __fmaf_rn(fabsf(tlim[j]), WIDE2, tlim[j]);
+                    }
+                }
+            }
+            tlim_max = fmaxf(fmaxf(tlim[0], tlim[1]), fmaxf(tlim[2], tlim[3]));
+        }
+        // pop
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            const int2 e = stack[sp];
+            if (__int_as_float(e.y) > tlim_max) continue;
+            node = e.x;
+            found = true;
+            break;
+        }
+        if (!found) break;
+    }
+    cnt.node_visits += visits;
+    cnt.node_tests += 2 * PK * visits;
+    cnt.prim_tests += prim_tests;
+}
+
+// single-ray fallback of the packet kernel (mixed octants / degenerate directions), out of line
+static __device__ __noinline__ ColdHit trace_primary_cold(const BvhView* B, float dx, float dy, float dz)
+{
+    Counters c = {0, 0, 0, 0};
+    float tnear = INFINITY;
+    int key = 0, leaf = -1;
+    traverse_fast<true, false, true>(*B, 0.f, 0.f, 0.f, dx, dy, dz, tnear, key, leaf, c);
+    return ColdHit{tnear, key, leaf, c.node_tests, c.prim_tests, c.node_visits};
+}
+
 // NONE: main.cpp:376-386, spheres staged through shared memory by the whole block (all threads must call).
 constexpr int NONE_CHUNK = 1024;
 __device__ __forceinline__ void brute_force_block(int type, const float4* __restrict__ sph /*objId order {c,r}*/,
@@ -901,6 +1013,103 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
     }
     // counters: warp reduce, one atomic per warp per counter
+    unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned long long x = v[c];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(&A.counters[c], x);
+    }
+}
+
+// K10, packet form: one thread per pixel, the pixel's samples traced four at a time by traverse_packet. Ordered
+// (exact = 0) BVH / LBVH traversal of sphere scenes with aa_samples % 4 == 0; everything else uses render_kernel.
+#ifndef RTDS_PK_MINB
+#define RTDS_PK_MINB 6   // measured on B200: 4 blocks (112 regs) 1.40 ms, 5 (96) 1.245, 6 (80, 188 B spilled) 1.223, 8 (64) 1.238
+#endif
+__global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const __grid_constant__ RenderArgs A)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int bx, by;
+    quadrant_block(blockIdx.x, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by);
+    const int px = bx * 16 + (warp & 1) * 8 + (lane & 7);
+    const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const bool active = px < A.width && lrow < A.local_rows;
+    Counters cnt = {0, 0, 0, 0};
+    if (active) {
+        const int tile = lrow / A.tile_rows, within = lrow - tile * A.tile_rows;
+        const int py = (tile * A.world + A.rank) * A.tile_rows + within;
+        float acc_r = 0, acc_g = 0, acc_b = 0;
+        int last_hit = -1;
+        const size_t pix = (size_t)py * A.width + px;
+        const float margin = prune_margin(A.bvh.root_box, 0.f, 0.f, 0.f);
+        for (int k0 = 0; k0 < A.spp; k0 += PK) {
+            float dx[PK], dy[PK], dz[PK], ix[PK], iy[PK], iz[PK], tnear[PK];
+            int best_key[PK], best_leaf[PK];
+            bool ok = A.bvh.root_ref >= 0;
+            int oct0 = 0;
+            const uint4* jp = reinterpret_cast<const uint4*>(A.jitter + A.jitter_rel + 4 * (pix * A.spp + k0));
+#pragma unroll
+            for (int j = 0; j < PK; ++j) {
+                const uint4 jw = __ldg(jp + j);
+                const double r1 = canonical53(jw.x, jw.y), r2 = canonical53(jw.z, jw.w);
+                // main.cpp:554-557
+                dx[j] = (float)((2 * (((double)(unsigned)px + r1) * (double)A.inv_w) - 1) * (double)A.angle * (double)A.aspect);
+                dy[j] = (float)((1 - 2 * (((double)(unsigned)py + r2) * (double)A.inv_h)) * (double)A.angle);
+                dz[j] = -1;
+                normalize3(dx[j], dy[j], dz[j]);
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix[j]) : "f"(dx[j]));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy[j]) : "f"(dy[j]));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz[j]) : "f"(dz[j]));
+                const float amin = fminf(fminf(fabsf(ix[j]), fabsf(iy[j])), fabsf(iz[j]));
+                const float amax = fmaxf(fmaxf(fabsf(ix[j]), fabsf(iy[j])), fabsf(iz[j]));
+                const int oct = (dx[j] < 0 ? 1 : 0) | (dy[j] < 0 ? 2 : 0) | 4;
+                if (j == 0) oct0 = oct;
+                ok = ok && amin > 1e-30f && amax < 1e30f && oct == oct0;
+                tnear[j] = INFINITY; best_key[j] = 0; best_leaf[j] = -1;
+            }
+            cnt.rays += PK;
+            if (ok) {
+                switch (oct0) {
+                    case 4: traverse_packet<4>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
+                    case 5: traverse_packet<5>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
+                    case 6: traverse_packet<6>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
+                    default: traverse_packet<7>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < PK; ++j) {
+                    const ColdHit h = trace_primary_cold(&A.bvh, dx[j], dy[j], dz[j]);
+                    tnear[j] = h.tnear; best_leaf[j] = h.leaf;
+                    cnt.node_tests += h.node_tests; cnt.prim_tests += h.prim_tests; cnt.node_visits += h.node_visits;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PK; ++j) {
+                float r, g, b;
+                int hit_obj = -1;
+                if (best_leaf[j] >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf[j]);
+                if (hit_obj < 0) { r = A.shade.bg[0]; g = A.shade.bg[1]; b = A.shade.bg[2]; }
+                else {
+                    const float4 m = __ldg(A.mat + hit_obj);
+                    const float hx = 0.f + dx[j] * tnear[j], hy = 0.f + dy[j] * tnear[j], hz = 0.f + dz[j] * tnear[j];     // main.cpp:396
+                    float nx, ny, nz;
+                    raw_normal(0, A.bvh.leaf_sph, nullptr, (size_t)best_leaf[j], hx, hy, hz, nx, ny, nz);
+                    shade_diffuse(A.shade, dx[j], dy[j], dz[j], hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b);
+                }
+                acc_r += r; acc_g += g; acc_b += b;     // sample order, main.cpp:553-560
+                last_hit = hit_obj;
+            }
+        }
+        size_t o = (size_t)(A.out_global_rows ? py : lrow) * A.width + px;
+        const float fs = (float)(unsigned)A.spp;
+        A.out_rgb[3 * o]     = (unsigned char)(fminf(1.0f, acc_r / fs) * 255);
+        A.out_rgb[3 * o + 1] = (unsigned char)(fminf(1.0f, acc_g / fs) * 255);
+        A.out_rgb[3 * o + 2] = (unsigned char)(fminf(1.0f, acc_b / fs) * 255);
+        o = (size_t)lrow * A.width + px;
+        if (A.out_hit) A.out_hit[o] = last_hit;
+        if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
+    }
     unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -1459,12 +1668,16 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             // lanes per pixel of render_kernel: 4 when the samples fill the groups (see the kernel's header)
             int spl = 1;
             if (const char* e = getenv("RTDS_SPL")) { const int v = atoi(e); if (v == 1 || v == 4) spl = v; }
+            // four samples of a pixel per thread as one packet (see traverse_packet); RTDS_PACKET=0 turns it off
+            bool packet = !full && !kdt && !brute && !p->exact && spp % PK == 0 && A.bvh.leaf_box_prim;
+            if (const char* e = getenv("RTDS_PACKET")) packet = packet && atoi(e) != 0;
             const unsigned lin1 = grid.x * grid.y, lin4 = (unsigned)((W + 7) / 8) * (unsigned)((r1 - r0 + 3) / 4);
             if (full) {
                 if (brute) render_full_kernel<2><<<grid, block, 0, s>>>(A);
                 else if (p->exact) render_full_kernel<0><<<grid, block, 0, s>>>(A);
                 else render_full_kernel<1><<<grid, block, 0, s>>>(A);
             }
+            else if (packet) render_packet_kernel<<<lin1, block, 0, s>>>(A);
             else if (spl == 4) {
                 if (kdt) render_kernel<3, 4><<<lin4, block, 0, s>>>(A);
                 else if (brute) render_kernel<2, 4><<<lin4, block, 0, s>>>(A);

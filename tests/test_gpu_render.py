@@ -138,3 +138,26 @@ def test_rtds_frame_equals_the_three_calls(gpu_ctx):
     gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
     rgb_b, _, _, _ = gpu_ctx.render(rt.LBVH, 240, 180, 2, shadows=1)
     assert np.array_equal(rgb_a, rgb_b)
+
+
+@pytest.mark.parametrize("acc", ["BVH", "LBVH"])
+def test_packet_traversal_equals_single_ray_and_reference_order(gpu_ctx, oracle, monkeypatch, acc):
+    """aa_samples % 4 == 0 takes the packet kernel (four samples of a pixel share every node load): hit ids, float sums
+    and bytes must equal the unpruned reference traversal (exact=1), the single-ray ordered kernel (RTDS_PACKET=0) and
+    the CPU restatement; 8 spp = two packets per pixel, image centre included (mixed-octant pixels fall back)."""
+    sph, mat = T.bunny_scene()
+    gpu_ctx.set_spheres(sph, mat)
+    a = getattr(rt, acc)
+    gpu_ctx.build(a, mode=rt.MODE_TRUE if acc == "LBVH" else rt.MODE_COMPAT)
+    nodes, order = gpu_ctx.export_bvh()
+    W, H, spp = 400, 300, 8
+    pk = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True)
+    ex = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True, exact=True)
+    monkeypatch.setenv("RTDS_PACKET", "0")
+    sr = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True)
+    for other in (ex, sr):
+        assert np.array_equal(pk[1], other[1]) and pk[2].tobytes() == other[2].tobytes() and np.array_equal(pk[0], other[0])
+    rgb_o, hit_o, accum_o, _ = oracle.render_rows(sph, mat, nodes, order, W, H, spp, tie_by_objid=1 if acc == "LBVH" else 0, want_accum=True)
+    assert np.array_equal(pk[1], hit_o) and pk[2].tobytes() == accum_o.tobytes() and np.array_equal(pk[0], rgb_o)
+    assert pk[3]["primary_rays"] == W * H * spp == sr[3]["primary_rays"]
+    assert pk[3]["node_visits"] < sr[3]["node_visits"]          # the point of the packet: fewer node loads
