@@ -122,6 +122,8 @@ int rtds_create(rtds_ctx** out, int device)
     RTDS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     RTDS_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_band, cudaEventDisableTiming));
+    RTDS_CUDA(cudaStreamCreateWithFlags(&c->jit_stream, cudaStreamNonBlocking));
+    RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_dirs, cudaEventDisableTiming));
     RTDS_CUDA(cudaEventCreate(&c->ev0)); RTDS_CUDA(cudaEventCreate(&c->ev1));
     RTDS_CUDA(cudaEventCreate(&c->ev2)); RTDS_CUDA(cudaEventCreate(&c->ev3));
     RTDS_CUDA(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8));
@@ -139,7 +141,7 @@ int rtds_destroy(rtds_ctx* c)
     cudaStreamSynchronize(c->stream);
     rtds_free_bvh(c->bvh);
     rtds_free_kd(c->kd);
-    void* bufs[] = {c->d_sph, c->d_mat, c->d_tris, c->d_keys_sorted, c->d_mt_snap, c->d_jitter, c->d_scratch,
+    void* bufs[] = {c->d_sph, c->d_mat, c->d_tris, c->d_keys_sorted, c->d_mt_snap, c->d_jitter, c->d_dirs, c->d_scratch,
                     c->d_sort_ws, c->d_frame, c->d_hit, c->d_accum, c->d_counters};
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -147,6 +149,8 @@ int rtds_destroy(rtds_ctx* c)
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     cudaEventDestroy(c->ev_band);
+    cudaStreamDestroy(c->jit_stream);
+    cudaEventDestroy(c->ev_dirs);
     delete c;
     return RTDS_OK;
 }
@@ -223,6 +227,10 @@ int rtds_frame(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n, in
                const rtds_render_params* rp, uint8_t* rgb, rtds_build_stats* bst, rtds_render_stats* rst)
 {
     if (!c || !rp || !rgb) { rtds_set_error("frame: bad arguments"); return RTDS_ERR_INVALID; }
+    // the frame's ray directions depend on the render parameters only: generate them on their own stream while the
+    // scene uploads and the structure is built
+    RTDS_CUDA(cudaSetDevice(c->device));
+    RTDS_TRY(rtds_prefetch_dirs(c, rp));
     RTDS_TRY(upload_spheres(c, cxyz_r, rgb_mat, n, true));
     RTDS_TRY(rtds_build(c, acc, bp, bst));
     RTDS_TRY(rtds_finish_materials(c));

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <functional>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -119,11 +120,17 @@ __global__ void __launch_bounds__(MT_THREADS) mt_expand_kernel(const uint32_t* _
     }
 }
 
+// exact uint32 -> double without the conversion unit: 2^52 + u is representable, the subtraction is exact
+__device__ __forceinline__ double u32_to_double(uint32_t u) { return __hiloint2double(0x43300000, (int)u) - 4503599627370496.0; }
+
 // generate_canonical<double,53>(mt19937): two draws, (lo + hi*2^32)/2^64, clamped below 1.
 __device__ __forceinline__ double canonical53(uint32_t lo, uint32_t hi)
 {
-    double sum = __uint2double_rn(lo) + __uint2double_rn(hi) * 4294967296.0;
-    double r = sum / 18446744073709551616.0;
+    // hi * 2^32 exactly: 2^84 + hi * 2^32 is representable (ulp 2^32), the subtraction is exact; the sum rounds once
+    // (to nearest even), exactly like the reference's long-double sum narrowed to double
+    const double hi32 = __hiloint2double(0x45300000, (int)hi) - 19342813113834066795298816.0;
+    const double sum = u32_to_double(lo) + hi32;
+    double r = sum * 5.42101086242752217e-20;    // / 2^64, exact
     if (r >= 1.0) r = 0.99999999999999988897769753748434595763683319091796875;  // nextafter(1,0)
     return r;
 }
@@ -134,6 +141,81 @@ __global__ void jitter_doubles_kernel(const uint32_t* __restrict__ words, size_t
     if (i < n) {
         size_t w = (first_double_rel + (size_t)i) * 2;
         out[i] = canonical53(words[w], words[w + 1]);
+    }
+}
+
+// geometry.h:125-134: n = x*x+y*y+z*z (float); factor = (float)(1 / sqrt((double)n))
+__device__ __forceinline__ void normalize3(float& x, float& y, float& z)
+{
+    float n = x * x + y * y + z * z;
+    if (n > 0) {
+        float factor = (float)(1.0 / sqrt((double)n));
+        x *= factor; y *= factor; z *= factor;
+    }
+}
+
+// Primary ray direction of sample (px, py) from its four jitter words: main.cpp:554-557 (double -> float exactly as there).
+struct RayGen { float angle, aspect, inv_w, inv_h; };
+__device__ __forceinline__ void primary_dir(const uint4 jw, int px, int py, const RayGen& G, float& dx, float& dy, float& dz)
+{
+    const double r1 = canonical53(jw.x, jw.y), r2 = canonical53(jw.z, jw.w);
+    dx = (float)((2 * ((u32_to_double((unsigned)px) + r1) * (double)G.inv_w) - 1) * (double)G.angle * (double)G.aspect);
+    dy = (float)((1 - 2 * ((u32_to_double((unsigned)py) + r2) * (double)G.inv_h)) * (double)G.angle);
+    dz = -1;
+    normalize3(dx, dy, dz);
+}
+
+// exact unsigned division by a launch-time constant (Granlund-Montgomery round-up form): magic == 0 -> power of two
+struct FastDiv { uint32_t magic, shift; };
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv d)
+{
+    if (d.magic == 0) return n >> d.shift;
+    const uint32_t q = __umulhi(n, d.magic);
+    return (((n - q) >> 1) + q) >> d.shift;
+}
+
+// K11 + ray generation fused: block b regenerates MT_SNAP_EVERY times from snapshot (s0 + b), each regeneration
+// written straight into the next 624-word slice of one shared array (the state after regeneration r IS slice r), then
+// all threads turn the chunk's 1,248 samples (4 words each) into primary directions — the double-precision part of
+// main.cpp:554-557 and Vec3::normalize — and store 3 floats per sample: 12 bytes instead of the 16 bytes of raw
+// words, and the render kernel starts from ready directions. dirs[3 * g] is frame sample g = pixel * spp + k.
+__global__ void __launch_bounds__(MT_THREADS) mt_expand_dirs_kernel(const uint32_t* __restrict__ snap, int s0, float* __restrict__ dirs,
+                                                                    unsigned long long first_sample, unsigned n_samples, int width,
+                                                                    int spp, const FastDiv div_spp, const FastDiv div_width,
+                                                                    const RayGen G, const JitterOwner own)
+{
+    __shared__ __align__(16) uint32_t words[(MT_SNAP_EVERY + 1) * MT_N];      // slice 0 = the snapshot
+    const int t = threadIdx.x;
+    const unsigned long long wlo = (unsigned long long)(s0 + blockIdx.x) * MT_SNAP_EVERY * MT_N;
+    if (own.world > 1) {
+        const unsigned long long whi = wlo + MT_SNAP_EVERY * MT_N - 1;
+        long long ylo = wlo > own.first_word ? (long long)((wlo - own.first_word) / own.row_words) : 0;
+        long long yhi = whi > own.first_word ? (long long)((whi - own.first_word) / own.row_words) : 0;
+        if (yhi >= own.height) yhi = own.height - 1;
+        bool mine = false;
+        for (long long tl = ylo / own.tile_rows; tl <= yhi / own.tile_rows; ++tl) mine |= (tl % own.world) == own.rank;
+        if (!mine) return;
+    }
+    const uint32_t* src = snap + (size_t)(s0 + blockIdx.x) * MT_N;
+    for (int i = t; i < MT_N; i += MT_THREADS) words[i] = src[i];
+    __syncthreads();
+    for (int r = 0; r < MT_SNAP_EVERY; ++r) mt_regen(words + r * MT_N, words + (r + 1) * MT_N);
+    // all threads, no barriers: temper, canonical doubles, direction, normalise, store
+    const unsigned long long as0 = wlo / 4;           // absolute stream sample of the chunk's first four words
+    const uint4* w4 = reinterpret_cast<const uint4*>(words + MT_N);
+    for (int i = t; i < MT_SNAP_EVERY * MT_N / 4; i += MT_THREADS) {
+        const unsigned long long as = as0 + i;
+        if (as >= first_sample && as - first_sample < n_samples) {
+            const unsigned g = (unsigned)(as - first_sample);
+            const unsigned pix = fast_div(g, div_spp);
+            const unsigned py = fast_div(pix, div_width), px = pix - py * (unsigned)width;
+            const uint4 w = w4[i];
+            const uint4 jw = make_uint4(mt_temper(w.x), mt_temper(w.y), mt_temper(w.z), mt_temper(w.w));
+            float dx, dy, dz;
+            primary_dir(jw, (int)px, (int)py, G, dx, dy, dz);
+            float* o = dirs + 3 * (size_t)g;
+            o[0] = dx; o[1] = dy; o[2] = dz;
+        }
     }
 }
 
@@ -828,16 +910,6 @@ struct ShadeParams {
     int       shadows;
 };
 
-// geometry.h:125-134: n = x*x+y*y+z*z (float); factor = (float)(1 / sqrt((double)n))
-__device__ __forceinline__ void normalize3(float& x, float& y, float& z)
-{
-    float n = x * x + y * y + z * z;
-    if (n > 0) {
-        float factor = (float)(1.0 / sqrt((double)n));
-        x *= factor; y *= factor; z *= factor;
-    }
-}
-
 // powf(x, 25) for x in [0, ~1]: exact-product chain in double, one rounding to float. glibc's powf is
 // correctly rounded except in astronomically rare cases, and so is this.
 __device__ __forceinline__ float pow25f(float xf)
@@ -885,7 +957,8 @@ struct RenderArgs {
     int   rank, world, tile_rows, local_rows;
     int   lrow0;                 // first local row of this launch (the frame may be rendered in row bands)
     float angle, aspect, inv_w, inv_h;
-    const uint32_t* jitter;      // word 0 = stream word jitter_base
+    const uint32_t* jitter;      // word 0 = stream word jitter_base (strip kernel / tests only)
+    const float*    dirs;        // primary directions, 3 floats per frame sample (pixel * spp + k), from mt_expand_dirs_kernel
     const uint32_t* mt_snap;     // MT19937 state snapshots (strip kernel regenerates its words itself)
     unsigned long long first_sample;   // stream index of sample 0 of pixel 0 (jitter_offset)
     int             chunk_first; // absolute snapshot chunk of block 0 of the strip kernel
@@ -954,14 +1027,8 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         const bool live = active && k < A.spp;
         float dx = 0, dy = 0, dz = -1;
         if (live) {
-            size_t w = A.jitter_rel + 4 * (pix * A.spp + k);
-            uint4 jw = __ldg(reinterpret_cast<const uint4*>(A.jitter + w));
-            double r1 = canonical53(jw.x, jw.y), r2 = canonical53(jw.z, jw.w);
-            // main.cpp:554-557
-            float xx = (float)((2 * (((double)(unsigned)px + r1) * (double)A.inv_w) - 1) * (double)A.angle * (double)A.aspect);
-            float yy = (float)((1 - 2 * (((double)(unsigned)py + r2) * (double)A.inv_h)) * (double)A.angle);
-            dx = xx; dy = yy; dz = -1;
-            normalize3(dx, dy, dz);
+            const float* dp = A.dirs + 3 * (pix * A.spp + k);      // main.cpp:554-557, computed by mt_expand_dirs_kernel
+            dx = __ldg(dp); dy = __ldg(dp + 1); dz = __ldg(dp + 2);
             cnt.rays++;
         }
         float tnear = INFINITY;
@@ -1048,16 +1115,13 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
             int best_key[PK], best_leaf[PK];
             bool ok = A.bvh.root_ref >= 0;
             int oct0 = 0;
-            const uint4* jp = reinterpret_cast<const uint4*>(A.jitter + A.jitter_rel + 4 * (pix * A.spp + k0));
+            // the packet's 4 directions are 48 contiguous, 16-byte aligned bytes (main.cpp:554-557, from mt_expand_dirs_kernel)
+            const float4* dp = reinterpret_cast<const float4*>(A.dirs + 3 * (pix * A.spp + k0));
+            const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+            dx[0] = d0.x; dy[0] = d0.y; dz[0] = d0.z; dx[1] = d0.w; dy[1] = d1.x; dz[1] = d1.y;
+            dx[2] = d1.z; dy[2] = d1.w; dz[2] = d2.x; dx[3] = d2.y; dy[3] = d2.z; dz[3] = d2.w;
 #pragma unroll
             for (int j = 0; j < PK; ++j) {
-                const uint4 jw = __ldg(jp + j);
-                const double r1 = canonical53(jw.x, jw.y), r2 = canonical53(jw.z, jw.w);
-                // main.cpp:554-557
-                dx[j] = (float)((2 * (((double)(unsigned)px + r1) * (double)A.inv_w) - 1) * (double)A.angle * (double)A.aspect);
-                dy[j] = (float)((1 - 2 * (((double)(unsigned)py + r2) * (double)A.inv_h)) * (double)A.angle);
-                dz[j] = -1;
-                normalize3(dx[j], dy[j], dz[j]);
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix[j]) : "f"(dx[j]));
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy[j]) : "f"(dy[j]));
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz[j]) : "f"(dz[j]));
@@ -1188,12 +1252,8 @@ __global__ void __launch_bounds__(STRIP_THREADS) render_strip_kernel(const __gri
         int last_hit = -1;
         for (int k = 0; k < A.spp; ++k) {
             const uint4 jw = *reinterpret_cast<const uint4*>(&words[woff + 4 * k]);
-            double r1 = canonical53(jw.x, jw.y), r2 = canonical53(jw.z, jw.w);
-            // main.cpp:554-557
-            float dx = (float)((2 * (((double)(unsigned)px + r1) * (double)A.inv_w) - 1) * (double)A.angle * (double)A.aspect);
-            float dy = (float)((1 - 2 * (((double)(unsigned)py + r2) * (double)A.inv_h)) * (double)A.angle);
-            float dz = -1;
-            normalize3(dx, dy, dz);
+            float dx, dy, dz;
+            primary_dir(jw, px, py, RayGen{A.angle, A.aspect, A.inv_w, A.inv_h}, dx, dy, dz);
             cnt.rays++;
             float tnear = INFINITY;
             int best_key = 0, best_leaf = -1, hit_obj = -1;
@@ -1326,13 +1386,8 @@ __global__ void __launch_bounds__(128) render_full_kernel(const __grid_constant_
         const size_t pix = (size_t)py * A.width + px;
         const float bias = A.shade.bias;
         for (int k = 0; k < A.spp; ++k) {
-            size_t w = A.jitter_rel + 4 * (pix * A.spp + k);
-            uint4 jw = __ldg(reinterpret_cast<const uint4*>(A.jitter + w));
-            double r1 = canonical53(jw.x, jw.y), r2 = canonical53(jw.z, jw.w);
-            float dx = (float)((2 * (((double)(unsigned)px + r1) * (double)A.inv_w) - 1) * (double)A.angle * (double)A.aspect);
-            float dy = (float)((1 - 2 * (((double)(unsigned)py + r2) * (double)A.inv_h)) * (double)A.angle);
-            float dz = -1;
-            normalize3(dx, dy, dz);
+            const float* dp = A.dirs + 3 * (pix * A.spp + k);      // main.cpp:554-557, computed by mt_expand_dirs_kernel
+            float dx = __ldg(dp), dy = __ldg(dp + 1), dz = __ldg(dp + 2);
             float ox = 0, oy = 0, oz = 0;
             float r = A.shade.bg[0], g = A.shade.bg[1], b = A.shade.bg[2];
             float mult[2] = {1.f, 1.f};   // (1 - kr) of the REFLECTION_AND_REFRACTION hits on the way, outermost first
@@ -1531,6 +1586,8 @@ static int ensure_snapshots(rtds_ctx* ctx, int need_snaps, int* launches)
     return RTDS_OK;
 }
 
+static inline unsigned __float_as_uint_host(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+
 static int jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int* launches, const JitterOwner& own)
 {
     if (n_words == 0) return RTDS_OK;
@@ -1556,6 +1613,50 @@ static int jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, in
     return RTDS_OK;
 }
 
+// Primary directions of the frame's samples (pixel * spp + k), generated from the jitter stream starting at sample
+// `first_sample`; only the chunks that hold rows of `own` are filled.
+static int dirs_prepare(rtds_ctx* ctx, uint64_t first_sample, int W, int H, int spp, const RayGen& G, const JitterOwner& own, int* launches,
+                        cudaStream_t stream)
+{
+    const uint64_t n_samples = (uint64_t)W * H * spp;
+    if (n_samples >= (1ull << 32)) { rtds_set_error("render: width*height*aa_samples must be below 2^32"); return RTDS_ERR_INVALID; }
+    const uint64_t words_per_snap = (uint64_t)MT_SNAP_EVERY * MT_N;
+    const uint64_t first_word = 4 * first_sample, n_words = 4 * n_samples;
+    const uint64_t s0 = first_word / words_per_snap, s1 = (first_word + n_words - 1) / words_per_snap;
+    if (s1 + 2 >= (1ull << 31)) { rtds_set_error("jitter stream position too large"); return RTDS_ERR_INVALID; }
+    RTDS_TRY(ensure_snapshots(ctx, (int)(s1 + 1), launches));
+    if (ctx->dirs_cap_floats < 3 * n_samples) {
+        if (ctx->d_dirs) cudaFree(ctx->d_dirs);
+        ctx->d_dirs = nullptr; ctx->dirs_cap_floats = 0;
+        RTDS_CUDA(cudaMalloc(&ctx->d_dirs, sizeof(float) * 3 * n_samples));
+        ctx->dirs_cap_floats = 3 * n_samples;
+    }
+    auto make_div = [](uint32_t d) {
+        FastDiv f{0u, 0u};
+        uint32_t fl = 0;
+        while ((2ull << fl) <= d) ++fl;                         // floor(log2 d)
+        if ((d & (d - 1)) == 0) { f.shift = fl; return f; }
+        const uint64_t num = 1ull << (32 + fl);
+        uint64_t pm = num / d;
+        const uint64_t rem = num % d;
+        pm += pm;
+        if (rem + rem >= d) pm += 1;
+        f.magic = (uint32_t)(1 + pm);
+        f.shift = fl;
+        return f;
+    };
+    mt_expand_dirs_kernel<<<(unsigned)(s1 - s0 + 1), MT_THREADS, 0, stream>>>(ctx->d_mt_snap, (int)s0, ctx->d_dirs, first_sample,
+                                                                                 (unsigned)n_samples, W, spp, make_div((uint32_t)spp),
+                                                                                 make_div((uint32_t)W), G, own);
+    if (launches) *launches += 1;
+    RTDS_CUDA(cudaGetLastError());
+    ctx->dirs_key[0] = first_sample; ctx->dirs_key[1] = (uint64_t)W; ctx->dirs_key[2] = (uint64_t)H; ctx->dirs_key[3] = (uint64_t)spp;
+    ctx->dirs_key[4] = ((uint64_t)__float_as_uint_host(G.angle) << 32) | __float_as_uint_host(G.aspect);
+    ctx->dirs_key[5] = ((uint64_t)(unsigned)own.rank << 40) | ((uint64_t)(unsigned)own.world << 20) | (uint64_t)(unsigned)own.tile_rows;
+    ctx->dirs_valid = true;
+    return RTDS_OK;
+}
+
 int rtds_jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int* launches)
 {
     JitterOwner all{0, 1, 1, 0, 1, 1};
@@ -1572,6 +1673,36 @@ int rtds_jitter_stream_impl(rtds_ctx* ctx, uint64_t first, int n, double* out)
     RTDS_CUDA(cudaGetLastError());
     RTDS_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     RTDS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RTDS_OK;
+}
+
+static RayGen make_raygen(const rtds_render_params* p)
+{
+    // main.cpp:544-546
+    const float fov = p->fov > 0 ? p->fov : 30.0f;
+    RayGen G;
+    G.inv_w = 1 / float(p->width); G.inv_h = 1 / float(p->height);
+    G.aspect = p->width / float(p->height);
+    G.angle = (float)tan(3.141592653589793 * 0.5 * fov / 180.);
+    return G;
+}
+
+int rtds_prefetch_dirs(rtds_ctx* ctx, const rtds_render_params* p)
+{
+    const int W = p->width, H = p->height, spp = p->aa_samples;
+    if (W <= 0 || H <= 0 || spp <= 0) return RTDS_OK;        // the render call reports the error
+    const int world = p->world > 0 ? p->world : 1, rank = p->rank, tile_rows = p->tile_rows > 0 ? p->tile_rows : 8;
+    if (rank < 0 || rank >= world) return RTDS_OK;
+    if (getenv("RTDS_STRIP") && atoi(getenv("RTDS_STRIP")) == 1) return RTDS_OK;
+    if (ctx->dirs_pending) RTDS_CUDA(cudaStreamSynchronize(ctx->jit_stream));
+    RTDS_CUDA(cudaStreamSynchronize(ctx->stream));            // a render still reading d_dirs
+    const RayGen G = make_raygen(p);
+    JitterOwner own{4ull * p->jitter_offset, 4ull * (unsigned long long)W * spp, tile_rows, rank, world, H};
+    int launches = 0;
+    RTDS_TRY(dirs_prepare(ctx, p->jitter_offset, W, H, spp, G, own, &launches, ctx->jit_stream));
+    RTDS_CUDA(cudaEventRecord(ctx->ev_dirs, ctx->jit_stream));
+    ctx->dirs_pending = true;
+    ctx->dirs_pending_launches = launches;
     return RTDS_OK;
 }
 
@@ -1594,11 +1725,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.width = W; A.height = H; A.spp = spp;
     A.rank = rank; A.world = world; A.tile_rows = tile_rows; A.lrow0 = 0;
     A.local_rows = rtds_rows_for_rank(H, tile_rows, rank, world);
-    // main.cpp:544-546
-    const float fov = p->fov > 0 ? p->fov : 30.0f;
-    A.inv_w = 1 / float(W); A.inv_h = 1 / float(H);
-    A.aspect = W / float(H);
-    A.angle = (float)tan(3.141592653589793 * 0.5 * fov / 180.);
+    { const RayGen G0 = make_raygen(p); A.inv_w = G0.inv_w; A.inv_h = G0.inv_h; A.aspect = G0.aspect; A.angle = G0.angle; }
     A.n = ctx->n; A.sph = ctx->d_sph; A.tri = ctx->d_tris; A.prim_type = ctx->prim_type; A.mat = ctx->d_mat;
     if (!brute && !kdt) A.bvh = make_view(ctx->bvh); else A.bvh = BvhView();
     if (kdt) A.kd = make_kd_view(ctx); else A.kd = KdView();
@@ -1629,13 +1756,25 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     if (strip) {
         if (c_last + 3 >= (1ull << 31)) { rtds_set_error("jitter stream position too large"); return RTDS_ERR_INVALID; }
         RTDS_TRY(ensure_snapshots(ctx, (int)(c_last + 1), &launches));
-    } else
-    if (!(p->no_jitter_regen && ctx->d_jitter && ctx->jitter_first_word <= first_word &&
-          first_word + n_words <= ctx->jitter_first_word + ctx->jitter_n_words))
-    {
-        JitterOwner own{first_word, 4ull * (unsigned long long)W * spp, tile_rows, rank, world, H};
-        RTDS_TRY(jitter_prepare(ctx, first_word, n_words, &launches, own));
+    } else {
+        const RayGen G{A.angle, A.aspect, A.inv_w, A.inv_h};
+        const uint64_t key[6] = {p->jitter_offset, (uint64_t)W, (uint64_t)H, (uint64_t)spp,
+                                 ((uint64_t)__float_as_uint_host(G.angle) << 32) | __float_as_uint_host(G.aspect),
+                                 ((uint64_t)(unsigned)rank << 40) | ((uint64_t)(unsigned)world << 20) | (uint64_t)(unsigned)tile_rows};
+        if (ctx->dirs_pending && ctx->dirs_valid && memcmp(key, ctx->dirs_key, sizeof key) == 0) {
+            // generated ahead of time by rtds_prefetch_dirs for exactly this frame
+            RTDS_CUDA(cudaStreamWaitEvent(s, ctx->ev_dirs, 0));
+            launches += ctx->dirs_pending_launches;
+        } else {
+            if (ctx->dirs_pending) RTDS_CUDA(cudaStreamWaitEvent(s, ctx->ev_dirs, 0));      // never overwrite d_dirs under a running prefetch
+            if (!(p->no_jitter_regen && ctx->dirs_valid && memcmp(key, ctx->dirs_key, sizeof key) == 0)) {
+                JitterOwner own{first_word, 4ull * (unsigned long long)W * spp, tile_rows, rank, world, H};
+                RTDS_TRY(dirs_prepare(ctx, p->jitter_offset, W, H, spp, G, own, &launches, s));
+            }
+        }
+        ctx->dirs_pending = false;
     }
+    A.dirs = ctx->d_dirs;
     A.jitter = ctx->d_jitter;
     A.jitter_rel = strip ? 0 : first_word - ctx->jitter_first_word;
     A.mt_snap = ctx->d_mt_snap;

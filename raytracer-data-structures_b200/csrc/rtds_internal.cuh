@@ -125,6 +125,14 @@ struct rtds_ctx {
     size_t    jitter_cap_words = 0;
     uint64_t  jitter_first_word = 0; // stream index of d_jitter[0]
     size_t    jitter_n_words = 0;
+    float*    d_dirs = nullptr;      // primary ray directions of the last frame, 3 floats per sample
+    size_t    dirs_cap_floats = 0;
+    uint64_t  dirs_key[6] = {0, 0, 0, 0, 0, 0};   // what d_dirs was generated for (no_jitter_regen reuse)
+    bool      dirs_valid = false;
+    bool      dirs_pending = false;  // generated ahead of the render on jit_stream (rtds_frame); ev_dirs marks completion
+    int       dirs_pending_launches = 0;
+    cudaStream_t jit_stream = nullptr;
+    cudaEvent_t  ev_dirs = nullptr;
 
     // scratch
     void*   d_scratch = nullptr;
@@ -185,6 +193,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
 int rtds_trace_impl(rtds_ctx* ctx, int acc, int exact, const float* h_o, const float* h_d, int nrays,
                     int* h_hit, float* h_t, rtds_render_stats* st);
 int rtds_jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int* launches);
+int rtds_prefetch_dirs(rtds_ctx* ctx, const rtds_render_params* p);
 
 // ---------------------------------------------------------------------------------------------------
 // small device helpers
