@@ -8,8 +8,10 @@ Workload (config.workload): BASELINE config 3's stand-in — the reference's own
 Stanford bunny: 30 clones = 1,078,411 spheres (the report's "Happy Buddha" count is 30 x 35,947), 3840x2160,
 4 spp, dataStructure = LBVH, one light, shadows off (= the reference's behaviour: trace_more is a stub).
 A step is one frame: jitter stream regeneration + ray generation + traversal + intersection + shading +
-quantisation of all 33,177,600 primary rays (+ the NCCL framebuffer gather when N>1).  The frame is FIXED and
-its scanline tiles are interleaved over the ranks, so scaling is strong.
+quantisation of all 33,177,600 primary rays. N>1: the frame is FIXED and its scanline tiles are interleaved over the
+ranks (strong scaling); every rank's render kernel stores its tiles straight into rank 0's frame buffer over NVLink
+(CUDA IPC peer memory, rtds_render_shared) and raises a flag rank 0 waits on: no collective (--gather nccl = the
+older per-rank buffers + NCCL gather, kept for comparison).
 
 value  = rays/s with the scene and tree resident in HBM (device-side time, CUDA events, max over ranks).
 e2e    = the same frame through the C-ABI a reference user would call, per step: H2D of the sphere table,
@@ -235,7 +237,17 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator comes up; the bench's stdout is ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     rt = entry.load_rtds()
     ctx = rt.Rtds(local_rank)              # raises if the CUDA library / GPU is missing: no fallback
@@ -264,7 +276,21 @@ def run_ours(args):
     row_index = [torch.from_numpy(rt.owned_rows(H, TILE_ROWS, r, world)).to(dev) for r in range(world)] if rank == 0 else None
     frame_dev = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev) if rank == 0 else None
 
+    # N > 1: the frame is assembled by the render kernels themselves. Rank 0 owns one frame buffer; every rank maps it
+    # (CUDA IPC) and stores its tiles straight into it over NVLink, then raises its flag; rank 0 waits for all flags on
+    # its stream. `--gather nccl` keeps the older path (per-rank buffers + NCCL gather) for comparison.
+    p2p = world > 1 and args.gather == "p2p"
+    seq = [0]
+    if p2p:
+        box = [ctx.shared_frame_create(W, H, world) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            ctx.shared_frame_open(box[0], W, H, world, rank)
+
     def step_resident():
+        if p2p:
+            seq[0] += 1
+            return ctx.render_shared(rt.LBVH, params, seq[0])
         st = ctx.render_device(rt.LBVH, params, my_rows.data_ptr())
         if world > 1:
             dist.gather(my_rows, gathered, dst=0)
@@ -272,6 +298,10 @@ def run_ours(args):
 
     def assemble_and_download():
         if rank != 0:
+            return
+        if p2p:
+            rc = ctx.lib.rtds_shared_frame_read(ctx.ctx, C.c_void_p(frame_host.data_ptr()))
+            assert rc == 0, ctx.lib.rtds_last_error()
             return
         if world > 1:
             for r in range(world):
@@ -334,6 +364,9 @@ def run_ours(args):
     sh_params = ctx.render_params(W, H, SPP, exact=False, rank=rank, world=world, tile_rows=TILE_ROWS, shadows=1)
 
     def step_shadows():
+        if p2p:
+            seq[0] += 1
+            return ctx.render_shared(rt.LBVH, sh_params, seq[0])
         st = ctx.render_device(rt.LBVH, sh_params, my_rows.data_ptr())
         if world > 1:
             dist.gather(my_rows, gathered, dst=0)
@@ -373,7 +406,9 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "width": W, "height": H, "aa_samples": SPP, "n_prims": int(n),
                            "accel": "LBVH true mode (30-bit Morton, onesweep, Karras, atomic refit)", "traversal": "ordered, pruned (exact=0)",
-                           "partition": f"interleaved {TILE_ROWS}-row scanline tiles over {world} rank(s); NCCL gather of RGB8 rows" if world > 1 else "single GPU",
+                           "partition": (f"interleaved {TILE_ROWS}-row scanline tiles over {world} rank(s); " +
+                                         ("render kernels store RGB8 tiles straight into rank 0's frame over NVLink (CUDA IPC peer memory) + per-rank flags, no collective"
+                                          if p2p else "NCCL gather of RGB8 rows")) if world > 1 else "single GPU",
                            "l2": "flushed between timed steps (256 MiB fill); per-frame inputs (531 MB jitter words + 90 MB tree) exceed L2"},
                 "rays_per_step": total_rays,
                 "per_ray": {"slab_tests": cnt[0].item() / total_rays, "sphere_tests": cnt[1].item() / total_rays,
@@ -409,6 +444,8 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if p2p:
+            ctx.shared_frame_close()
         dist.destroy_process_group()
     ctx.close()
     return 0
@@ -421,6 +458,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1 frame assembly: peer stores (default) or NCCL gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

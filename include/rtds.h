@@ -187,6 +187,28 @@ int rtds_render_device(rtds_ctx* ctx, int acc_type, const rtds_render_params* pa
                        rtds_render_stats* stats);
 int rtds_rows_for_rank(int height, int tile_rows, int rank, int world);
 
+/* ---- Multi-GPU frame assembly without a collective -------------------------------------------------------------
+ * The scene and structure are replicated, the image is split into interleaved scanline tiles (rank / world of
+ * rtds_render_params). Instead of rendering into per-rank buffers and gathering them (rtds_render_device + NCCL),
+ * every rank's render kernel stores its tiles STRAIGHT into one frame that lives in rank 0's memory: peer stores
+ * over NVLink / NVSwitch, 16 bytes at a time, overlapped with the tracing; a per-rank completion flag follows the
+ * tiles and rank 0 waits for all flags on its own stream. Replaces render()'s single `image` buffer (main.cpp:543).
+ *   rank 0            : rtds_shared_frame_create (ipc_handle_out: 64 bytes to pass to the other processes)
+ *   rank r, other proc: rtds_shared_frame_open(handle, ..., r)        (cudaIpcOpenMemHandle)
+ *   rank r, same proc : rtds_shared_frame_attach(ctx_r, ctx_0, r)     (peer access; one context per GPU)
+ *   every rank, frame : rtds_render_shared(ctx, acc, params, seq)     seq != 0 and different from the previous frame's;
+ *                       synchronous; on rank 0 it returns when EVERY rank's tiles of frame `seq` have landed
+ *   rank 0            : rtds_shared_frame_read (device -> host) or rtds_shared_frame_ptr (device pointer, H*W*3 bytes)
+ * The caller keeps frames apart: no rank may start frame k+1 before rank 0 has consumed frame k (a frame-loop barrier). */
+#define RTDS_IPC_HANDLE_BYTES 64
+int rtds_shared_frame_create(rtds_ctx* owner, int width, int height, int world, void* ipc_handle_out);
+int rtds_shared_frame_open(rtds_ctx* ctx, const void* ipc_handle, int width, int height, int world, int rank);
+int rtds_shared_frame_attach(rtds_ctx* ctx, rtds_ctx* owner, int rank);
+int rtds_render_shared(rtds_ctx* ctx, int acc_type, const rtds_render_params* params, uint32_t frame_seq, rtds_render_stats* stats);
+int rtds_shared_frame_ptr(rtds_ctx* ctx, void** d_frame);
+int rtds_shared_frame_read(rtds_ctx* owner, uint8_t* rgb);
+int rtds_shared_frame_close(rtds_ctx* ctx);
+
 /* First n doubles of random_double()'s stream starting at double index `first` (main.cpp:503-508), generated
  * by the device MT19937 kernels. Host pointer. */
 int rtds_jitter_stream(rtds_ctx* ctx, uint64_t first, int n, double* out);

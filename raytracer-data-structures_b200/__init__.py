@@ -88,7 +88,9 @@ assert LINEAR_NODE_DTYPE.itemsize == 32 and KD_NODE_DTYPE.itemsize == 12
 ABI_SYMBOLS = ["rtds_last_error", "rtds_version", "rtds_create", "rtds_destroy", "rtds_set_spheres",
                "rtds_set_triangles", "rtds_set_lights", "rtds_build", "rtds_export_bvh", "rtds_export_kd",
                "rtds_export_morton", "rtds_trace", "rtds_render", "rtds_render_device", "rtds_rows_for_rank",
-               "rtds_jitter_stream", "rtds_morton30", "rtds_frame"]
+               "rtds_jitter_stream", "rtds_morton30", "rtds_frame", "rtds_shared_frame_create", "rtds_shared_frame_open",
+               "rtds_shared_frame_attach", "rtds_render_shared", "rtds_shared_frame_ptr", "rtds_shared_frame_read",
+               "rtds_shared_frame_close"]
 
 _lib = None
 
@@ -122,6 +124,13 @@ def load_library(path: str = LIB_PATH):
     lib.rtds_rows_for_rank.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     lib.rtds_jitter_stream.argtypes = [vp, C.c_uint64, C.c_int, vp]
     lib.rtds_morton30.argtypes = [vp, vp, C.c_int, vp]
+    lib.rtds_shared_frame_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    lib.rtds_shared_frame_open.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.rtds_shared_frame_attach.argtypes = [vp, vp, C.c_int]
+    lib.rtds_render_shared.argtypes = [vp, C.c_int, C.POINTER(RenderParams), C.c_uint32, C.POINTER(RenderStats)]
+    lib.rtds_shared_frame_ptr.argtypes = [vp, C.POINTER(vp)]
+    lib.rtds_shared_frame_read.argtypes = [vp, vp]
+    lib.rtds_shared_frame_close.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -263,6 +272,38 @@ class Rtds:
         st = RenderStats()
         self._check(self.lib.rtds_render_device(self.ctx, acc, C.byref(params), C.c_void_p(device_ptr), C.byref(st)))
         return _stats_dict(st)
+
+    # -- multi-GPU frame assembled by peer stores (no collective) ----------------------------------
+    def shared_frame_create(self, width, height, world):
+        """Rank 0: allocate the frame every rank renders into; returns the 64-byte CUDA IPC handle for other processes."""
+        h = (C.c_ubyte * 64)()
+        self._check(self.lib.rtds_shared_frame_create(self.ctx, width, height, world, C.cast(h, C.c_void_p)))
+        return bytes(h)
+
+    def shared_frame_open(self, handle, width, height, world, rank):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self.lib.rtds_shared_frame_open(self.ctx, C.cast(buf, C.c_void_p), width, height, world, rank))
+
+    def shared_frame_attach(self, owner, rank):
+        self._check(self.lib.rtds_shared_frame_attach(self.ctx, owner.ctx, rank))
+
+    def render_shared(self, acc, params, frame_seq):
+        st = RenderStats()
+        self._check(self.lib.rtds_render_shared(self.ctx, acc, C.byref(params), frame_seq, C.byref(st)))
+        return _stats_dict(st)
+
+    def shared_frame_ptr(self):
+        p = C.c_void_p()
+        self._check(self.lib.rtds_shared_frame_ptr(self.ctx, C.byref(p)))
+        return p.value
+
+    def shared_frame_read(self, width, height, out=None):
+        rgb = out if out is not None else np.zeros((height, width, 3), np.uint8)
+        self._check(self.lib.rtds_shared_frame_read(self.ctx, _ptr(rgb)))
+        return rgb
+
+    def shared_frame_close(self):
+        self._check(self.lib.rtds_shared_frame_close(self.ctx))
 
     def jitter_stream(self, first, n):
         out = np.zeros(n, np.float64)

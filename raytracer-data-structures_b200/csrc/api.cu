@@ -84,6 +84,23 @@ void rtds_free_kd(DeviceKd& k)
 }
 
 int rtds_jitter_stream_impl(rtds_ctx* ctx, uint64_t first, int n, double* out);
+static size_t shared_frame_bytes(int W, int H, int world, size_t* flags_off)
+{
+    const size_t fo = ((size_t)W * H * 3 + 255) & ~(size_t)255;
+    if (flags_off) *flags_off = fo;
+    return fo + 128 * (size_t)world;
+}
+
+static void shared_frame_drop(rtds_ctx* c)
+{
+    SharedFrame& f = c->shared;
+    if (f.frame) {
+        if (f.owner) cudaFree(f.frame);
+        else if (f.ipc_mapped) cudaIpcCloseMemHandle(f.frame);
+    }
+    f = SharedFrame();
+}
+
 
 // does any primitive carry a material other than DIFFUSE_AND_GLOSSY? (selects the full castRay kernel)
 __global__ void material_flag_kernel(const float4* __restrict__ mat, int n, int* flag)
@@ -147,6 +164,7 @@ int rtds_destroy(rtds_ctx* c)
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
     cudaStreamDestroy(c->stream);
+    shared_frame_drop(c);
     cudaStreamDestroy(c->copy_stream);
     cudaEventDestroy(c->ev_band);
     cudaStreamDestroy(c->jit_stream);
@@ -437,6 +455,123 @@ int rtds_render(rtds_ctx* c, int acc, const rtds_render_params* p, uint8_t* rgb,
         }
     }
     RTDS_CUDA(cudaStreamSynchronize(s));
+    return RTDS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-GPU frame assembly by direct peer stores (no collective): see include/rtds.h
+// ---------------------------------------------------------------------------------------------------
+int rtds_shared_frame_create(rtds_ctx* c, int width, int height, int world, void* ipc_handle_out)
+{
+    if (!c || width <= 0 || height <= 0 || world <= 0 || world > 32) { rtds_set_error("shared_frame_create: bad arguments"); return RTDS_ERR_INVALID; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    shared_frame_drop(c);
+    SharedFrame& f = c->shared;
+    size_t fo = 0;
+    f.bytes = shared_frame_bytes(width, height, world, &fo);
+    RTDS_CUDA(cudaMalloc(&f.frame, f.bytes));
+    RTDS_CUDA(cudaMemset(f.frame, 0, f.bytes));
+    f.flags = reinterpret_cast<volatile uint32_t*>(f.frame + fo);
+    f.width = width; f.height = height; f.world = world; f.rank = 0; f.owner = true;
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t h;
+        RTDS_CUDA(cudaIpcGetMemHandle(&h, f.frame));
+        static_assert(sizeof(h) == RTDS_IPC_HANDLE_BYTES, "IPC handle size");
+        memcpy(ipc_handle_out, &h, sizeof h);
+    }
+    return RTDS_OK;
+}
+
+int rtds_shared_frame_open(rtds_ctx* c, const void* ipc_handle, int width, int height, int world, int rank)
+{
+    if (!c || !ipc_handle || width <= 0 || height <= 0 || rank <= 0 || rank >= world || world > 32) {
+        rtds_set_error("shared_frame_open: bad arguments (rank 0 is the owner and calls rtds_shared_frame_create)");
+        return RTDS_ERR_INVALID;
+    }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    shared_frame_drop(c);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof h);
+    void* p = nullptr;
+    RTDS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    SharedFrame& f = c->shared;
+    size_t fo = 0;
+    f.bytes = shared_frame_bytes(width, height, world, &fo);
+    f.frame = (uint8_t*)p;
+    f.flags = reinterpret_cast<volatile uint32_t*>(f.frame + fo);
+    f.width = width; f.height = height; f.world = world; f.rank = rank; f.owner = false; f.ipc_mapped = true;
+    return RTDS_OK;
+}
+
+int rtds_shared_frame_attach(rtds_ctx* c, rtds_ctx* owner, int rank)
+{
+    if (!c || !owner || c == owner || !owner->shared.frame || !owner->shared.owner || rank <= 0 || rank >= owner->shared.world) {
+        rtds_set_error("shared_frame_attach: bad arguments");
+        return RTDS_ERR_INVALID;
+    }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    shared_frame_drop(c);
+    if (c->device != owner->device) {
+        int can = 0;
+        RTDS_CUDA(cudaDeviceCanAccessPeer(&can, c->device, owner->device));
+        if (!can) { rtds_set_error("shared_frame_attach: device %d cannot access device %d", c->device, owner->device); return RTDS_ERR_UNSUPPORTED; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(owner->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) RTDS_CUDA(e);
+        (void)cudaGetLastError();
+    }
+    c->shared = owner->shared;
+    c->shared.owner = false; c->shared.ipc_mapped = false; c->shared.rank = rank;
+    return RTDS_OK;
+}
+
+int rtds_render_shared(rtds_ctx* c, int acc, const rtds_render_params* p, uint32_t frame_seq, rtds_render_stats* st)
+{
+    if (!c || !p || frame_seq == 0) { rtds_set_error("render_shared: bad arguments (frame_seq must be non-zero)"); return RTDS_ERR_INVALID; }
+    SharedFrame& f = c->shared;
+    if (!f.frame) { rtds_set_error("render_shared: no shared frame (rtds_shared_frame_create / _open / _attach first)"); return RTDS_ERR_INVALID; }
+    const int world = p->world > 0 ? p->world : 1;
+    if (p->width != f.width || p->height != f.height || world != f.world || p->rank != f.rank) {
+        rtds_set_error("render_shared: params (%dx%d rank %d/%d) do not match the shared frame (%dx%d rank %d/%d)", p->width, p->height,
+                       p->rank, world, f.width, f.height, f.rank, f.world);
+        return RTDS_ERR_INVALID;
+    }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    f.seq = frame_seq;
+    rtds_render_stats local;
+    RTDS_TRY(rtds_render_impl(c, acc, p, f.frame, nullptr, nullptr, st ? st : &local, nullptr, true));   // synchronous (reads the counters)
+    const int status = (st ? st : &local)->reserved[0];      // frame_wait_kernel's verdict, read back with the counters
+    if (f.owner && status != 0) {
+        rtds_set_error("render_shared: timed out waiting for rank %d's tiles of frame %u", status - 1, frame_seq);
+        return RTDS_ERR_CUDA;
+    }
+    return RTDS_OK;
+}
+
+int rtds_shared_frame_ptr(rtds_ctx* c, void** d_frame)
+{
+    if (!c || !d_frame || !c->shared.frame) { rtds_set_error("shared_frame_ptr: no shared frame"); return RTDS_ERR_INVALID; }
+    *d_frame = c->shared.frame;
+    return RTDS_OK;
+}
+
+int rtds_shared_frame_read(rtds_ctx* c, uint8_t* rgb)
+{
+    if (!c || !rgb || !c->shared.frame) { rtds_set_error("shared_frame_read: no shared frame"); return RTDS_ERR_INVALID; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    RTDS_CUDA(cudaMemcpyAsync(rgb, c->shared.frame, (size_t)c->shared.width * c->shared.height * 3, cudaMemcpyDeviceToHost, c->stream));
+    RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    return RTDS_OK;
+}
+
+int rtds_shared_frame_close(rtds_ctx* c)
+{
+    if (!c) return RTDS_ERR_INVALID;
+    RTDS_CUDA(cudaSetDevice(c->device));
+    RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    shared_frame_drop(c);
     return RTDS_OK;
 }
 

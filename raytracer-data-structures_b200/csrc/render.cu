@@ -973,10 +973,43 @@ struct RenderArgs {
     ShadeParams   shade;
     uint8_t* out_rgb;            // local rows x width x 3, or the whole frame (height x width x 3) when out_global_rows
     int      out_global_rows;    // 1: out_rgb is a full frame indexed by the GLOBAL row (possibly another GPU's memory)
+    int      out_vec16;          // out_rgb is 16-byte aligned and width % 16 == 0: blocks store whole 16-byte words
     int*     out_hit;            // optional, local rows x width
     float*   out_accum;          // optional, local rows x width x 3
     unsigned long long* counters;
 };
+
+// Frame-buffer write of one 16 x 8 pixel block (128 threads, one pixel each). The block's RGB8 values are staged in
+// shared memory and leave as 24 aligned 16-byte stores (8 rows x 48 bytes) instead of 384 single-byte stores: when the
+// frame lives in ANOTHER GPU's memory (out_global_rows: every rank stores its tiles straight into rank 0's frame over
+// NVLink, there is no gather afterwards) the transfer is made of full 16-byte writes. Falls back to byte stores for
+// ragged widths / edge blocks / unaligned buffers. All 128 threads of the block must call.
+__device__ __forceinline__ int global_row_of(const RenderArgs& A, int lrow)
+{
+    const int tile = lrow / A.tile_rows, within = lrow - tile * A.tile_rows;
+    return (tile * A.world + A.rank) * A.tile_rows + within;
+}
+__device__ __forceinline__ void store_block_rgb(const RenderArgs& A, int bx, int by, int px, int lrow, bool active, unsigned char r8,
+                                                unsigned char g8, unsigned char b8)
+{
+    __shared__ __align__(16) unsigned char tile[8][48];
+    const int row0 = A.lrow0 + by * 8;
+    const bool fast = A.out_vec16 && bx * 16 + 16 <= A.width && row0 + 8 <= A.local_rows;     // block-uniform
+    if (fast) {
+        const int lx = px - bx * 16, ly = lrow - row0;
+        tile[ly][3 * lx] = r8; tile[ly][3 * lx + 1] = g8; tile[ly][3 * lx + 2] = b8;
+        __syncthreads();
+        if (threadIdx.x < 24) {
+            const int row = threadIdx.x / 3, seg = threadIdx.x - 3 * row;
+            const int orow = A.out_global_rows ? global_row_of(A, row0 + row) : row0 + row;
+            const uint4 v = *reinterpret_cast<const uint4*>(&tile[row][16 * seg]);
+            *reinterpret_cast<uint4*>(A.out_rgb + ((size_t)orow * A.width + bx * 16) * 3 + 16 * seg) = v;
+        }
+    } else if (active) {
+        const size_t o = (size_t)(A.out_global_rows ? global_row_of(A, lrow) : lrow) * A.width + px;
+        A.out_rgb[3 * o] = r8; A.out_rgb[3 * o + 1] = g8; A.out_rgb[3 * o + 2] = b8;
+    }
+}
 
 // Block coordinates from a linear block id, image QUADRANT by quadrant (top-left, top-right, bottom-left,
 // bottom-right), row-major inside a quadrant. Primary rays of one quadrant share the direction octant, so the blocks
@@ -994,39 +1027,26 @@ __device__ __forceinline__ void quadrant_block(int b, int nbx, int nby, int& bx,
     bx = hx + b % wx; by = hy + b / wx;
 }
 
-// S = lanes per pixel. S == 1: a thread owns a pixel and loops over its samples (warp = 8 x 4 pixels, block = 16 x 8).
-// S == 4: four lanes trace four consecutive samples of one pixel at the same time (warp = 4 x 2 pixels x 4 samples,
-// block = 8 x 4 pixels): the samples of a pixel walk nearly the same nodes, so a warp-wide node load touches far
-// fewer distinct cache lines (the kernel is bound by L1 tag/data throughput of divergent 16-byte node loads), and
-// the jitter words of a warp are one contiguous 512-byte run. The per-pixel float sum is still formed in sample order
-// (main.cpp:553-560) by passing the four colours through shuffles.
-template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE, 3 = KDTREE (any-hit, unshaded: main.cpp:362-372)*/, int S>
+// K10: one thread per pixel (warp = 8 x 4 pixels, block = 16 x 8), samples looped in order so the per-pixel float
+// accumulation matches main.cpp:553-560.
+template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE, 3 = KDTREE (any-hit, unshaded: main.cpp:362-372)*/>
 __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ RenderArgs A)
 {
     __shared__ float4 sh_sph[MODE == 2 ? NONE_CHUNK : 1];
-    constexpr int WW = S == 1 ? 8 : 4, WH = S == 1 ? 4 : 2;     // warp footprint in pixels
-    constexpr int BW = 2 * WW, BH = 2 * WH;                       // block footprint (2 x 2 warps)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sub = lane % S, pl = lane / S;
     int bx, by;
-    quadrant_block(blockIdx.x, (A.width + BW - 1) / BW, (A.local_rows - A.lrow0 + BH - 1) / BH, bx, by);
-    const int px = bx * BW + (warp & 1) * WW + (pl % WW);
-    const int lrow = A.lrow0 + by * BH + (warp >> 1) * WH + pl / WW;
+    quadrant_block(blockIdx.x, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by);
+    const int px = bx * 16 + (warp & 1) * 8 + (lane & 7);
+    const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool active = px < A.width && lrow < A.local_rows;
-    int py = 0;
-    if (active) {
-        int tile = lrow / A.tile_rows, within = lrow - tile * A.tile_rows;
-        py = (tile * A.world + A.rank) * A.tile_rows + within;
-    }
+    const int py = active ? global_row_of(A, lrow) : 0;
     Counters cnt = {0, 0, 0, 0};
     float acc_r = 0, acc_g = 0, acc_b = 0;
     int last_hit = -1;
     const size_t pix = (size_t)py * A.width + px;
-    for (int k0 = 0; k0 < A.spp; k0 += S) {
-        const int k = k0 + sub;
-        const bool live = active && k < A.spp;
+    for (int k = 0; k < A.spp; ++k) {
         float dx = 0, dy = 0, dz = -1;
-        if (live) {
+        if (active) {
             const float* dp = A.dirs + 3 * (pix * A.spp + k);      // main.cpp:554-557, computed by mt_expand_dirs_kernel
             dx = __ldg(dp); dy = __ldg(dp + 1); dz = __ldg(dp + 2);
             cnt.rays++;
@@ -1034,16 +1054,16 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         float tnear = INFINITY;
         int best_key = 0, best_leaf = -1, hit_obj = -1;
         if (MODE == 2) {
-            brute_force_block(A.prim_type, A.sph, A.tri, A.n, live, 0.f, 0.f, 0.f, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
+            brute_force_block(A.prim_type, A.sph, A.tri, A.n, active, 0.f, 0.f, 0.f, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
         } else if (MODE == 3) {
-            if (live) hit_obj = kd_any_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, cnt) ? 1 : -1;
-        } else if (live) {
+            if (active) hit_obj = kd_any_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, cnt) ? 1 : -1;
+        } else if (active) {
             if (MODE == 0) traverse_bvh<true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
             else traverse_fast<true, false, true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
             if (best_leaf >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf);
         }
-        float r = 0.f, g = 0.f, b = 0.f;
-        if (live) {
+        if (active) {
+            float r, g, b;
             if (hit_obj < 0) { r = A.shade.bg[0]; g = A.shade.bg[1]; b = A.shade.bg[2]; }
             else if (MODE == 3) { r = 0.f; g = 0.f; b = 0.f; }       // main.cpp:369: a KD hit is black
             else {
@@ -1054,28 +1074,15 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                 else raw_normal(A.bvh.prim_type, A.bvh.leaf_sph, A.bvh.leaf_tri, (size_t)best_leaf, hx, hy, hz, nx, ny, nz);
                 shade_diffuse(A.shade, dx, dy, dz, hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b);
             }
-        }
-        if (S == 1) {
-            if (live) { acc_r += r; acc_g += g; acc_b += b; last_hit = hit_obj; }
-        } else {
-            // the pixel's sum in sample order: every lane of the group adds the group's colours k0, k0+1, ...
-            const int lead = lane - sub;
-#pragma unroll
-            for (int j = 0; j < S; ++j) {
-                const float rj = __shfl_sync(0xffffffffu, r, lead + j), gj = __shfl_sync(0xffffffffu, g, lead + j),
-                            bj = __shfl_sync(0xffffffffu, b, lead + j);
-                const int hj = __shfl_sync(0xffffffffu, hit_obj, lead + j);
-                if (k0 + j < A.spp) { acc_r += rj; acc_g += gj; acc_b += bj; last_hit = hj; }
-            }
+            acc_r += r; acc_g += g; acc_b += b;
+            last_hit = hit_obj;
         }
     }
-    if (active && sub == 0) {
-        size_t o = (size_t)(A.out_global_rows ? py : lrow) * A.width + px;
-        float fs = (float)(unsigned)A.spp;
-        A.out_rgb[3 * o]     = (unsigned char)(fminf(1.0f, acc_r / fs) * 255);
-        A.out_rgb[3 * o + 1] = (unsigned char)(fminf(1.0f, acc_g / fs) * 255);
-        A.out_rgb[3 * o + 2] = (unsigned char)(fminf(1.0f, acc_b / fs) * 255);
-        o = (size_t)lrow * A.width + px;
+    const float fs = (float)(unsigned)A.spp;
+    store_block_rgb(A, bx, by, px, lrow, active, (unsigned char)(fminf(1.0f, acc_r / fs) * 255),
+                    (unsigned char)(fminf(1.0f, acc_g / fs) * 255), (unsigned char)(fminf(1.0f, acc_b / fs) * 255));
+    if (active) {
+        const size_t o = (size_t)lrow * A.width + px;
         if (A.out_hit) A.out_hit[o] = last_hit;
         if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
     }
@@ -1103,9 +1110,9 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
     const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool active = px < A.width && lrow < A.local_rows;
     Counters cnt = {0, 0, 0, 0};
+    unsigned char r8 = 0, g8 = 0, b8 = 0;
     if (active) {
-        const int tile = lrow / A.tile_rows, within = lrow - tile * A.tile_rows;
-        const int py = (tile * A.world + A.rank) * A.tile_rows + within;
+        const int py = global_row_of(A, lrow);
         float acc_r = 0, acc_g = 0, acc_b = 0;
         int last_hit = -1;
         const size_t pix = (size_t)py * A.width + px;
@@ -1165,15 +1172,15 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
                 last_hit = hit_obj;
             }
         }
-        size_t o = (size_t)(A.out_global_rows ? py : lrow) * A.width + px;
         const float fs = (float)(unsigned)A.spp;
-        A.out_rgb[3 * o]     = (unsigned char)(fminf(1.0f, acc_r / fs) * 255);
-        A.out_rgb[3 * o + 1] = (unsigned char)(fminf(1.0f, acc_g / fs) * 255);
-        A.out_rgb[3 * o + 2] = (unsigned char)(fminf(1.0f, acc_b / fs) * 255);
-        o = (size_t)lrow * A.width + px;
+        r8 = (unsigned char)(fminf(1.0f, acc_r / fs) * 255);
+        g8 = (unsigned char)(fminf(1.0f, acc_g / fs) * 255);
+        b8 = (unsigned char)(fminf(1.0f, acc_b / fs) * 255);
+        const size_t o = (size_t)lrow * A.width + px;
         if (A.out_hit) A.out_hit[o] = last_hit;
         if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
     }
+    store_block_rgb(A, bx, by, px, lrow, active, r8, g8, b8);
     unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -1373,14 +1380,16 @@ template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE*/>
 __global__ void __launch_bounds__(128) render_full_kernel(const __grid_constant__ RenderArgs A)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int lrow = A.lrow0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    int bx, by;
+    quadrant_block(blockIdx.x, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by);
+    const int px = bx * 16 + (warp & 1) * 8 + (lane & 7);
+    const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool active = px < A.width && lrow < A.local_rows;
     Counters cnt = {0, 0, 0, 0};
     unsigned shadow_rays = 0, secondary_rays = 0;
+    unsigned char r8 = 0, g8 = 0, b8 = 0;
     if (active) {
-        const int tile = lrow / A.tile_rows, within = lrow - tile * A.tile_rows;
-        const int py = (tile * A.world + A.rank) * A.tile_rows + within;
+        const int py = global_row_of(A, lrow);
         float acc_r = 0, acc_g = 0, acc_b = 0;
         int last_hit = -1;
         const size_t pix = (size_t)py * A.width + px;
@@ -1463,12 +1472,13 @@ __global__ void __launch_bounds__(128) render_full_kernel(const __grid_constant_
         }
         size_t o = (size_t)lrow * A.width + px;
         float fs = (float)(unsigned)A.spp;
-        A.out_rgb[3 * o]     = (unsigned char)(fminf(1.0f, acc_r / fs) * 255);
-        A.out_rgb[3 * o + 1] = (unsigned char)(fminf(1.0f, acc_g / fs) * 255);
-        A.out_rgb[3 * o + 2] = (unsigned char)(fminf(1.0f, acc_b / fs) * 255);
+        r8 = (unsigned char)(fminf(1.0f, acc_r / fs) * 255);
+        g8 = (unsigned char)(fminf(1.0f, acc_g / fs) * 255);
+        b8 = (unsigned char)(fminf(1.0f, acc_b / fs) * 255);
         if (A.out_hit) A.out_hit[o] = last_hit;
         if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
     }
+    store_block_rgb(A, bx, by, px, lrow, active, r8, g8, b8);
     unsigned v[6] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays, shadow_rays, secondary_rays};
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
@@ -1707,7 +1717,7 @@ int rtds_prefetch_dirs(rtds_ctx* ctx, const rtds_render_params* p)
 }
 
 int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_t* d_rgb_rows, int* d_hit, float* d_accum,
-                     rtds_render_stats* st, const std::function<int(int, int)>* on_band)
+                     rtds_render_stats* st, const std::function<int(int, int)>* on_band, bool global_rows)
 {
     const int W = p->width, H = p->height, spp = p->aa_samples;
     if (W <= 0 || H <= 0 || spp <= 0) { rtds_set_error("render: width/height/aa_samples must be positive"); return RTDS_ERR_INVALID; }
@@ -1738,7 +1748,8 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.shade.shadows = p->shadows;
     const bool full = p->shadows || ctx->has_materials;
     if (full && kdt) { rtds_set_error("render: the KDTREE path is any-hit and unshaded (main.cpp:362-372); shadows/materials need BVH, LBVH or NONE"); return RTDS_ERR_UNSUPPORTED; }
-    A.out_rgb = d_rgb_rows; A.out_hit = d_hit; A.out_accum = d_accum; A.out_global_rows = 0;
+    A.out_rgb = d_rgb_rows; A.out_hit = d_hit; A.out_accum = d_accum; A.out_global_rows = global_rows ? 1 : 0;
+    A.out_vec16 = (((uintptr_t)d_rgb_rows & 15) == 0 && W % 16 == 0) ? 1 : 0;
     A.counters = ctx->d_counters;
 
     cudaStream_t s = ctx->stream;
@@ -1750,7 +1761,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     // expanded into HBM. MEASURED SLOWER on B200 (3.16 ms vs 1.81 + 0.24 ms on the bench frame): a block then covers
     // 312 consecutive pixels of one scanline instead of a 16x8 tile, and the L1 hit rate of the node stream — what
     // this issue-bound kernel lives on — collapses. Kept as a checked (parity-tested) negative result, off by default.
-    const bool strip = !brute && !full && spp <= 150 && getenv("RTDS_STRIP") && atoi(getenv("RTDS_STRIP")) == 1;
+    const bool strip = !brute && !full && !global_rows && spp <= 150 && getenv("RTDS_STRIP") && atoi(getenv("RTDS_STRIP")) == 1;
     const uint64_t chunk_words = (uint64_t)MT_SNAP_EVERY * MT_N;
     const uint64_t c_first = first_word / chunk_words, c_last = (first_word + n_words - 1) / chunk_words;
     if (strip) {
@@ -1803,30 +1814,21 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             const int r1 = std::min(total_rows, r0 + band_rows);
             A.lrow0 = r0;
             A.local_rows = r1;
-            dim3 grid((W + 15) / 16, (r1 - r0 + 7) / 8), block(128);
-            // lanes per pixel of render_kernel: 4 when the samples fill the groups (see the kernel's header)
-            int spl = 1;
-            if (const char* e = getenv("RTDS_SPL")) { const int v = atoi(e); if (v == 1 || v == 4) spl = v; }
+            const dim3 block(128);
+            const unsigned lin = (unsigned)((W + 15) / 16) * (unsigned)((r1 - r0 + 7) / 8);     // quadrant-major linear grid
             // four samples of a pixel per thread as one packet (see traverse_packet); RTDS_PACKET=0 turns it off
             bool packet = !full && !kdt && !brute && !p->exact && spp % PK == 0 && A.bvh.leaf_box_prim;
             if (const char* e = getenv("RTDS_PACKET")) packet = packet && atoi(e) != 0;
-            const unsigned lin1 = grid.x * grid.y, lin4 = (unsigned)((W + 7) / 8) * (unsigned)((r1 - r0 + 3) / 4);
             if (full) {
-                if (brute) render_full_kernel<2><<<grid, block, 0, s>>>(A);
-                else if (p->exact) render_full_kernel<0><<<grid, block, 0, s>>>(A);
-                else render_full_kernel<1><<<grid, block, 0, s>>>(A);
+                if (brute) render_full_kernel<2><<<lin, block, 0, s>>>(A);
+                else if (p->exact) render_full_kernel<0><<<lin, block, 0, s>>>(A);
+                else render_full_kernel<1><<<lin, block, 0, s>>>(A);
             }
-            else if (packet) render_packet_kernel<<<lin1, block, 0, s>>>(A);
-            else if (spl == 4) {
-                if (kdt) render_kernel<3, 4><<<lin4, block, 0, s>>>(A);
-                else if (brute) render_kernel<2, 4><<<lin4, block, 0, s>>>(A);
-                else if (p->exact) render_kernel<0, 4><<<lin4, block, 0, s>>>(A);
-                else render_kernel<1, 4><<<lin4, block, 0, s>>>(A);
-            }
-            else if (kdt) render_kernel<3, 1><<<lin1, block, 0, s>>>(A);
-            else if (brute) render_kernel<2, 1><<<lin1, block, 0, s>>>(A);
-            else if (p->exact) render_kernel<0, 1><<<lin1, block, 0, s>>>(A);
-            else render_kernel<1, 1><<<lin1, block, 0, s>>>(A);
+            else if (packet) render_packet_kernel<<<lin, block, 0, s>>>(A);
+            else if (kdt) render_kernel<3><<<lin, block, 0, s>>>(A);
+            else if (brute) render_kernel<2><<<lin, block, 0, s>>>(A);
+            else if (p->exact) render_kernel<0><<<lin, block, 0, s>>>(A);
+            else render_kernel<1><<<lin, block, 0, s>>>(A);
             launches += 1;
             // the kernel-time event goes in BEFORE the band callback: a device->host copy into pageable memory blocks the
             // host, and an event recorded after it would time the copy as well
@@ -1839,6 +1841,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
         RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
         RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
     }
+    if (global_rows && ctx->shared.frame) RTDS_TRY(rtds_shared_frame_signal_wait(ctx, ctx->shared.seq, &launches));
     RTDS_CUDA(cudaEventRecord(ctx->ev1, s));
     if (st) {
         unsigned long long c[8];
@@ -1852,8 +1855,45 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
         RTDS_CUDA(cudaEventElapsedTime(&st->ms_total, ctx->ev0, ctx->ev1));
         st->kernel_launches = launches;
         st->rows = A.local_rows;
+        st->reserved[0] = (int)(unsigned)c[7];      // shared frame: 1 + the rank the owner timed out on (0 = complete)
         if (on_band) RTDS_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     }
+    return RTDS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Shared frame: completion flags of the multi-GPU frame assembly (one 128-byte line per rank behind the frame)
+// ---------------------------------------------------------------------------------------------------
+__global__ void frame_signal_kernel(volatile uint32_t* flag, uint32_t seq)
+{
+    __threadfence_system();        // this rank's tile stores (previous kernel on the stream) before the flag
+    *flag = seq;
+}
+__global__ void frame_wait_kernel(const volatile uint32_t* flags, int world, uint32_t seq, long long timeout_cycles, int* status)
+{
+    const int r = threadIdx.x;
+    if (r < world) {
+        const long long t0 = clock64();
+        while ((int)(flags[32 * r] - seq) < 0) {     // a rank may already have signalled a later frame
+            if (clock64() - t0 > timeout_cycles) { atomicExch(status, 1 + r); break; }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+
+int rtds_shared_frame_signal_wait(rtds_ctx* ctx, uint32_t seq, int* launches)
+{
+    cudaStream_t s = ctx->stream;
+    SharedFrame& f = ctx->shared;
+    frame_signal_kernel<<<1, 1, 0, s>>>(f.flags + 32 * f.rank, seq);
+    *launches += 1;
+    if (f.owner) {
+        RTDS_CUDA(cudaMemsetAsync(ctx->d_counters + 7, 0, sizeof(unsigned long long), s));
+        frame_wait_kernel<<<1, 32, 0, s>>>(f.flags, f.world, seq, 20000000000ll /* ~10 s */, (int*)(ctx->d_counters + 7));
+        *launches += 1;
+    }
+    RTDS_CUDA(cudaGetLastError());
     return RTDS_OK;
 }
 

@@ -85,6 +85,18 @@ struct DeviceKd {
 struct RtdsLight { float c[3]; float radius; float le[3]; };
 #define RTDS_MAX_LIGHTS 8
 
+// Frame shared by the ranks of a multi-GPU render: lives in the owner's (rank 0's) memory; peers map it (CUDA IPC
+// across processes, peer access inside one process) and their render kernels store into it directly.
+struct SharedFrame {
+    uint8_t*  frame = nullptr;      // height x width x 3, then one 128-byte flag line per rank
+    volatile uint32_t* flags = nullptr;
+    size_t    bytes = 0;
+    int       width = 0, height = 0, world = 0, rank = 0;
+    bool      owner = false;
+    bool      ipc_mapped = false;   // opened with cudaIpcOpenMemHandle (close with cudaIpcCloseMemHandle)
+    uint32_t  seq = 0;
+};
+
 struct rtds_ctx {
     int          device = 0;
     cudaStream_t stream = nullptr;
@@ -145,6 +157,7 @@ struct rtds_ctx {
     float*   d_accum = nullptr; size_t accum_bytes = 0;
     unsigned long long* d_counters = nullptr;  // render counters [8]
     uint8_t* h_pinned = nullptr;     // pinned host staging for D2H of frames
+    SharedFrame shared;
     size_t   pinned_bytes = 0;
 };
 
@@ -189,7 +202,9 @@ void rtds_free_kd(DeviceKd& k);
 
 // render.cu — K10 render/trace, K11 MT19937 jitter stream
 int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_t* d_rgb_rows, int* d_hit,
-                     float* d_accum, rtds_render_stats* st, const std::function<int(int, int)>* on_band = nullptr);
+                     float* d_accum, rtds_render_stats* st, const std::function<int(int, int)>* on_band = nullptr,
+                     bool global_rows = false);
+int rtds_shared_frame_signal_wait(rtds_ctx* ctx, uint32_t seq, int* launches);
 int rtds_trace_impl(rtds_ctx* ctx, int acc, int exact, const float* h_o, const float* h_d, int nrays,
                     int* h_hit, float* h_t, rtds_render_stats* st);
 int rtds_jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int* launches);
