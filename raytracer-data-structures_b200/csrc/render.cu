@@ -708,7 +708,7 @@ __device__ __forceinline__ void traverse_packet(const BvhView& B, const float (&
                                                 const float (&ix)[PK], const float (&iy)[PK], const float (&iz)[PK], float margin,
                                                 float (&tnear)[PK], int (&best_key)[PK], int (&best_leaf)[PK], Counters& cnt)
 {
-    const float neg_margin = -margin;
+    const float zthr = margin * (9.5367431640625e-7f / 0.00278f);      // prune_margin = 0.00278 * corner distance
     float tlim[PK];
 #pragma unroll
     for (int j = 0; j < PK; ++j) { tlim[j] = tnear[j] + margin; tlim[j] = __fmaf_rn(fabsf(tlim[j]), WIDE2, tlim[j]); }
@@ -723,7 +723,15 @@ __device__ __forceinline__ void traverse_packet(const BvhView& B, const float (&
             const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
             const int2 ch = __ldg(reinterpret_cast<const int2*>(q + 3));
             ++visits;
-            float tL = INFINITY, tR = INFINITY;     // packet entry distances: min over the rays that accept the child
+            // Boxes behind the camera. Every ray of the packet has dz < 0 (OCT bit 2). A sphere the reference's test can
+            // hit has float tca >= 0, so its true tca >= -delta (delta = the rounding error of the three-term dot product,
+            // <= 2^-21 * |c|), and the sphere contains the ray point at parameter tca, whose z = tca * dz <= delta: every
+            // box on its root path has zmin <= delta. zthr = 2^-20 * (distance to the root box's far corner) > delta.
+            // ONE compare per child for the whole packet replaces "exit distance >= -margin" per ray.
+            // The same holds on x and y with the exit plane the octant selects.
+            const bool frontL = q0.z <= zthr && ((OCT & 2) ? q0.y <= zthr : q1.x >= -zthr) && ((OCT & 1) ? q0.x <= zthr : q0.w >= -zthr);
+            const bool frontR = q2.x <= zthr && ((OCT & 2) ? q1.w <= zthr : q2.z >= -zthr) && ((OCT & 1) ? q1.z <= zthr : q2.y >= -zthr);
+            float kL[PK], kR[PK];                   // entry distance of the rays that accept the child, +inf otherwise
 #pragma unroll
             for (int j = 0; j < PK; ++j) {
                 float tminL, tmaxL, tminR, tmaxR;
@@ -731,11 +739,12 @@ __device__ __forceinline__ void traverse_packet(const BvhView& B, const float (&
                 slab_interval<OCT>(q1.z * ix[j], q1.w * iy[j], q2.x * iz[j], q2.y * ix[j], q2.z * iy[j], q2.w * iz[j], tminR, tmaxR);
                 tmaxL = __fmaf_rn(fabsf(tmaxL), WIDE2, tmaxL);
                 tmaxR = __fmaf_rn(fabsf(tmaxR), WIDE2, tmaxR);
-                const bool a = tminL <= fminf(tmaxL, tlim[j]) && tmaxL >= neg_margin;
-                const bool b = tminR <= fminf(tmaxR, tlim[j]) && tmaxR >= neg_margin;
-                tL = a ? fminf(tL, tminL) : tL;
-                tR = b ? fminf(tR, tminR) : tR;
+                kL[j] = tminL <= fminf(tmaxL, tlim[j]) ? tminL : INFINITY;
+                kR[j] = tminR <= fminf(tmaxR, tlim[j]) ? tminR : INFINITY;
             }
+            // packet entry distances: min over the rays that accept the child
+            const float tL = frontL ? fminf(fminf(fminf(kL[0], kL[1]), kL[2]), kL[3]) : INFINITY;
+            const float tR = frontR ? fminf(fminf(fminf(kR[0], kR[1]), kR[2]), kR[3]) : INFINITY;
             const bool hitL = tL < INFINITY, hitR = tR < INFINITY;
             if (hitL && hitR) {
                 const bool rfirst = tR < tL;
@@ -973,37 +982,39 @@ struct RenderArgs {
     ShadeParams   shade;
     uint8_t* out_rgb;            // local rows x width x 3, or the whole frame (height x width x 3) when out_global_rows
     int      out_global_rows;    // 1: out_rgb is a full frame indexed by the GLOBAL row (possibly another GPU's memory)
-    int      out_vec16;          // out_rgb is 16-byte aligned and width % 16 == 0: blocks store whole 16-byte words
+    int      out_vec8;           // out_rgb is 8-byte aligned and width % 8 == 0: warps store whole 8-byte words
     int*     out_hit;            // optional, local rows x width
     float*   out_accum;          // optional, local rows x width x 3
     unsigned long long* counters;
 };
 
-// Frame-buffer write of one 16 x 8 pixel block (128 threads, one pixel each). The block's RGB8 values are staged in
-// shared memory and leave as 24 aligned 16-byte stores (8 rows x 48 bytes) instead of 384 single-byte stores: when the
-// frame lives in ANOTHER GPU's memory (out_global_rows: every rank stores its tiles straight into rank 0's frame over
-// NVLink, there is no gather afterwards) the transfer is made of full 16-byte writes. Falls back to byte stores for
-// ragged widths / edge blocks / unaligned buffers. All 128 threads of the block must call.
+// Frame-buffer write of a warp's 8 x 4 pixels. The warp's RGB8 values are staged in shared memory and leave as 12
+// aligned 8-byte stores (4 rows x 24 bytes) instead of 96 single-byte stores: when the frame lives in ANOTHER GPU's
+// memory (out_global_rows: every rank stores its tiles straight into rank 0's frame over NVLink, there is no gather
+// afterwards) the transfer is made of full 8-byte writes. Warp-level only (__syncwarp): a block barrier here made
+// finished warps wait for the slowest one (10 % of the kernel's stall samples). Falls back to byte stores for ragged
+// widths / edge warps / unaligned buffers. All 32 lanes of the warp must call.
 __device__ __forceinline__ int global_row_of(const RenderArgs& A, int lrow)
 {
     const int tile = lrow / A.tile_rows, within = lrow - tile * A.tile_rows;
     return (tile * A.world + A.rank) * A.tile_rows + within;
 }
-__device__ __forceinline__ void store_block_rgb(const RenderArgs& A, int bx, int by, int px, int lrow, bool active, unsigned char r8,
-                                                unsigned char g8, unsigned char b8)
+__device__ __forceinline__ void store_warp_rgb(const RenderArgs& A, int px, int lrow, bool active, unsigned char r8, unsigned char g8,
+                                               unsigned char b8)
 {
-    __shared__ __align__(16) unsigned char tile[8][48];
-    const int row0 = A.lrow0 + by * 8;
-    const bool fast = A.out_vec16 && bx * 16 + 16 <= A.width && row0 + 8 <= A.local_rows;     // block-uniform
+    __shared__ __align__(16) unsigned char tile[4][4][24];       // [warp][row][8 pixels x 3]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px0 = px - (lane & 7), row0 = lrow - (lane >> 3);   // the warp's top-left pixel
+    const bool fast = A.out_vec8 && px0 + 8 <= A.width && row0 + 4 <= A.local_rows;     // warp-uniform
     if (fast) {
-        const int lx = px - bx * 16, ly = lrow - row0;
-        tile[ly][3 * lx] = r8; tile[ly][3 * lx + 1] = g8; tile[ly][3 * lx + 2] = b8;
-        __syncthreads();
-        if (threadIdx.x < 24) {
-            const int row = threadIdx.x / 3, seg = threadIdx.x - 3 * row;
+        unsigned char* t = &tile[warp][lane >> 3][3 * (lane & 7)];
+        t[0] = r8; t[1] = g8; t[2] = b8;
+        __syncwarp();
+        if (lane < 12) {
+            const int row = lane / 3, seg = lane - 3 * row;
             const int orow = A.out_global_rows ? global_row_of(A, row0 + row) : row0 + row;
-            const uint4 v = *reinterpret_cast<const uint4*>(&tile[row][16 * seg]);
-            *reinterpret_cast<uint4*>(A.out_rgb + ((size_t)orow * A.width + bx * 16) * 3 + 16 * seg) = v;
+            const uint2 v = *reinterpret_cast<const uint2*>(&tile[warp][row][8 * seg]);
+            *reinterpret_cast<uint2*>(A.out_rgb + ((size_t)orow * A.width + px0) * 3 + 8 * seg) = v;
         }
     } else if (active) {
         const size_t o = (size_t)(A.out_global_rows ? global_row_of(A, lrow) : lrow) * A.width + px;
@@ -1079,8 +1090,8 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         }
     }
     const float fs = (float)(unsigned)A.spp;
-    store_block_rgb(A, bx, by, px, lrow, active, (unsigned char)(fminf(1.0f, acc_r / fs) * 255),
-                    (unsigned char)(fminf(1.0f, acc_g / fs) * 255), (unsigned char)(fminf(1.0f, acc_b / fs) * 255));
+    store_warp_rgb(A, px, lrow, active, (unsigned char)(fminf(1.0f, acc_r / fs) * 255),
+                   (unsigned char)(fminf(1.0f, acc_g / fs) * 255), (unsigned char)(fminf(1.0f, acc_b / fs) * 255));
     if (active) {
         const size_t o = (size_t)lrow * A.width + px;
         if (A.out_hit) A.out_hit[o] = last_hit;
@@ -1180,7 +1191,7 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
         if (A.out_hit) A.out_hit[o] = last_hit;
         if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
     }
-    store_block_rgb(A, bx, by, px, lrow, active, r8, g8, b8);
+    store_warp_rgb(A, px, lrow, active, r8, g8, b8);
     unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -1478,7 +1489,7 @@ __global__ void __launch_bounds__(128) render_full_kernel(const __grid_constant_
         if (A.out_hit) A.out_hit[o] = last_hit;
         if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
     }
-    store_block_rgb(A, bx, by, px, lrow, active, r8, g8, b8);
+    store_warp_rgb(A, px, lrow, active, r8, g8, b8);
     unsigned v[6] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays, shadow_rays, secondary_rays};
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
@@ -1749,7 +1760,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     const bool full = p->shadows || ctx->has_materials;
     if (full && kdt) { rtds_set_error("render: the KDTREE path is any-hit and unshaded (main.cpp:362-372); shadows/materials need BVH, LBVH or NONE"); return RTDS_ERR_UNSUPPORTED; }
     A.out_rgb = d_rgb_rows; A.out_hit = d_hit; A.out_accum = d_accum; A.out_global_rows = global_rows ? 1 : 0;
-    A.out_vec16 = (((uintptr_t)d_rgb_rows & 15) == 0 && W % 16 == 0) ? 1 : 0;
+    A.out_vec8 = (((uintptr_t)d_rgb_rows & 7) == 0 && W % 8 == 0) ? 1 : 0;
     A.counters = ctx->d_counters;
 
     cudaStream_t s = ctx->stream;
