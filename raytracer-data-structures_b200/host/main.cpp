@@ -167,6 +167,10 @@ int main(int, char**)
 	// render (main.cpp:541-566): every GPU renders its interleaved scanline tiles into the shared host frame
 	std::vector<uint8_t> rgb((size_t)settings.width * settings.height * 3);
 	std::vector<rtds_render_stats> rs(n_gpus);
+	// N > 1: GPU 0 owns the frame and the other GPUs' render kernels store their tiles straight into it (peer access over
+	// NVLink, rtds_shared_frame_*); without peer access every GPU renders into its own buffer and copies its rows to the host.
+	bool shared = n_gpus > 1 && rtds_shared_frame_create(ctx[0], settings.width, settings.height, n_gpus, nullptr) == RTDS_OK;
+	for (int g = 1; shared && g < n_gpus; ++g) shared = rtds_shared_frame_attach(ctx[g], ctx[0], g) == RTDS_OK;
 	{
 		std::vector<std::thread> th;
 		for (int g = 0; g < n_gpus; ++g)
@@ -175,10 +179,12 @@ int main(int, char**)
 				memset(&rp, 0, sizeof rp);
 				rp.width = settings.width; rp.height = settings.height; rp.aa_samples = settings.aa_samples;
 				rp.exact = exact; rp.rank = g; rp.world = n_gpus; rp.tile_rows = 8;
-				CHECK(rtds_render(ctx[g], settings.dataStructure, &rp, rgb.data(), nullptr, nullptr, &rs[g]));
+				if (shared) CHECK(rtds_render_shared(ctx[g], settings.dataStructure, &rp, 1u, &rs[g]));
+				else CHECK(rtds_render(ctx[g], settings.dataStructure, &rp, rgb.data(), nullptr, nullptr, &rs[g]));
 			});
 		for (auto& t : th) t.join();
 	}
+	if (shared) CHECK(rtds_shared_frame_read(ctx[0], rgb.data()));
 	write_ppm(out_path, settings, rgb);
 
 	unsigned long long tests = 0, rays = 0;
