@@ -1107,13 +1107,72 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
     }
 }
 
+// the shadow query of main.cpp:468-473 for the packet kernel (one ray, any-hit), out of line; same answers as occluded<1>
+struct ShadowHit { int occluded; unsigned node_tests, prim_tests, node_visits; };
+static __device__ __noinline__ ShadowHit shadow_query_cold(const BvhView* B, float ox, float oy, float oz, float dx, float dy, float dz,
+                                                          float dist2)
+{
+    Counters c = {0, 0, 0, 0};
+    float ts = INFINITY;
+    int bk = 0, bl = -1;
+    const float len2 = dx * dx + dy * dy + dz * dz;
+    int occ;
+    if (fabsf(len2 - 1.0f) < 1e-3f) {
+        traverse_fast<false, true>(*B, ox, oy, oz, dx, dy, dz, ts, bk, bl, c, dist2);
+        occ = bl >= 0;
+    } else {
+        traverse_bvh<true>(*B, ox, oy, oz, dx, dy, dz, ts, bk, bl, c);
+        occ = bl >= 0 && ts * ts < dist2;
+    }
+    return ShadowHit{occ, c.node_tests, c.prim_tests, c.node_visits};
+}
+
+// castRay's DIFFUSE_AND_GLOSSY branch with the shadow query evaluated (main.cpp:447-494), as in render_full_kernel
+__device__ __forceinline__ void shade_diffuse_shadowed(const RenderArgs& A, float dx, float dy, float dz, float hx, float hy, float hz,
+                                                       float nx, float ny, float nz, float sr, float sg, float sb, float& r, float& g,
+                                                       float& b, Counters& cnt, unsigned& shadow_rays)
+{
+    normalize3(nx, ny, nz);
+    if (dx * nx + dy * ny + dz * nz > 0) { nx = -nx; ny = -ny; nz = -nz; }
+    const float bias = A.shade.bias;
+    float hr = 0, hg = 0, hb = 0;
+    for (int i = 0; i < A.shade.n_lights; ++i) {
+        const RtdsLight& L = A.shade.lights[i];
+        float lx = L.c[0] - hx, ly = L.c[1] - hy, lz = L.c[2] - hz;
+        const float dist2 = lx * lx + ly * ly + lz * lz;
+        normalize3(lx, ly, lz);
+        const float LdotN = fmaxf(0.f, lx * nx + ly * ny + lz * nz);
+        const bool front = dx * nx + dy * ny + dz * nz < 0;
+        const float sx = front ? hx + nx * bias : hx - nx * bias;
+        const float sy = front ? hy + ny * bias : hy - ny * bias;
+        const float sz = front ? hz + nz * bias : hz - nz * bias;
+        cnt.rays++;
+        shadow_rays++;
+        const ShadowHit sh = shadow_query_cold(&A.bvh, sx, sy, sz, lx, ly, lz, dist2);
+        cnt.node_tests += sh.node_tests; cnt.prim_tests += sh.prim_tests; cnt.node_visits += sh.node_visits;
+        const float lit = sh.occluded ? 0.0f : 1.0f;                                   // main.cpp:471-472
+        const float ar = (L.le[0] * lit) * LdotN, ag = (L.le[1] * lit) * LdotN, ab = (L.le[2] * lit) * LdotN;
+        const float ix = -lx, iy = -ly, iz = -lz;
+        const float s2 = 2 * (ix * nx + iy * ny + iz * nz);
+        const float qx = ix - nx * s2, qy = iy - ny * s2, qz = iz - nz * s2;
+        const float sp = pow25f(fmaxf(0.f, -(qx * dx + qy * dy + qz * dz)));
+        hr += (ar * (0.815f * 0.8f)) / 2.0f + (L.le[0] * sp) * 0.5f;
+        hg += (ag * (0.235f * 0.8f)) / 2.0f + (L.le[1] * sp) * 0.5f;
+        hb += (ab * (0.031f * 0.8f)) / 2.0f + (L.le[2] * sp) * 0.5f;
+        hr += sr; hg += sg; hb += sb;
+    }
+    r = hr; g = hg; b = hb;
+}
+
 // K10, packet form: one thread per pixel, the pixel's samples traced four at a time by traverse_packet. Ordered
 // (exact = 0) BVH / LBVH traversal of sphere scenes with aa_samples % 4 == 0; everything else uses render_kernel.
 #ifndef RTDS_PK_MINB
 #define RTDS_PK_MINB 6   // measured on B200: 4 blocks (112 regs) 1.40 ms, 5 (96) 1.245, 6 (80, 188 B spilled) 1.223, 8 (64) 1.238
 #endif
+template <bool SHADOWS /*evaluate the shadow query (extension; the reference's trace_more is a stub)*/>
 __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const __grid_constant__ RenderArgs A)
 {
+    unsigned shadow_rays = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int bx, by;
     quadrant_block(blockIdx.x, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by);
@@ -1177,7 +1236,8 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
                     const float hx = 0.f + dx[j] * tnear[j], hy = 0.f + dy[j] * tnear[j], hz = 0.f + dz[j] * tnear[j];     // main.cpp:396
                     float nx, ny, nz;
                     raw_normal(0, A.bvh.leaf_sph, nullptr, (size_t)best_leaf[j], hx, hy, hz, nx, ny, nz);
-                    shade_diffuse(A.shade, dx[j], dy[j], dz[j], hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b);
+                    if (SHADOWS) shade_diffuse_shadowed(A, dx[j], dy[j], dz[j], hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b, cnt, shadow_rays);
+                    else shade_diffuse(A.shade, dx[j], dy[j], dz[j], hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b);
                 }
                 acc_r += r; acc_g += g; acc_b += b;     // sample order, main.cpp:553-560
                 last_hit = hit_obj;
@@ -1192,9 +1252,9 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
         if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
     }
     store_warp_rgb(A, px, lrow, active, r8, g8, b8);
-    unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
+    unsigned v[5] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays, shadow_rays};
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < (SHADOWS ? 5 : 4); ++c) {
         unsigned long long x = v[c];
         for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0 && x) atomicAdd(&A.counters[c], x);
@@ -1828,14 +1888,17 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             const dim3 block(128);
             const unsigned lin = (unsigned)((W + 15) / 16) * (unsigned)((r1 - r0 + 7) / 8);     // quadrant-major linear grid
             // four samples of a pixel per thread as one packet (see traverse_packet); RTDS_PACKET=0 turns it off
-            bool packet = !full && !kdt && !brute && !p->exact && spp % PK == 0 && A.bvh.leaf_box_prim;
+            // (shadows without reflective / refractive materials stay on the packet kernel; the shadow rays are single)
+            bool packet = (!full || !ctx->has_materials) && !kdt && !brute && !p->exact && spp % PK == 0 && A.bvh.leaf_box_prim &&
+                          A.shade.max_depth >= 1;
             if (const char* e = getenv("RTDS_PACKET")) packet = packet && atoi(e) != 0;
-            if (full) {
+            if (packet && full) render_packet_kernel<true><<<lin, block, 0, s>>>(A);
+            else if (full) {
                 if (brute) render_full_kernel<2><<<lin, block, 0, s>>>(A);
                 else if (p->exact) render_full_kernel<0><<<lin, block, 0, s>>>(A);
                 else render_full_kernel<1><<<lin, block, 0, s>>>(A);
             }
-            else if (packet) render_packet_kernel<<<lin, block, 0, s>>>(A);
+            else if (packet) render_packet_kernel<false><<<lin, block, 0, s>>>(A);
             else if (kdt) render_kernel<3><<<lin, block, 0, s>>>(A);
             else if (brute) render_kernel<2><<<lin, block, 0, s>>>(A);
             else if (p->exact) render_kernel<0><<<lin, block, 0, s>>>(A);

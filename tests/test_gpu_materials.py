@@ -78,3 +78,29 @@ def test_shadows_darken_only(gpu_ctx):
     assert np.count_nonzero((acc_b < acc_a).any(-1)) > 1000
     assert st_b["shadow_rays"] == np.count_nonzero(hit >= 0) and st_b["rays"] == 1920 * 1080 + st_b["shadow_rays"]
     print("1920x1080 LBVH: %.3f ms primary only, %.3f ms with shadows (%d shadow rays)" % (st_a["ms_kernel"], st_b["ms_kernel"], st_b["shadow_rays"]))
+
+
+@pytest.mark.parametrize("acc", [rt.BVH, rt.LBVH])
+def test_shadowed_packet_kernel_matches_restatement_and_full_kernel(gpu_ctx, oracle, monkeypatch, acc):
+    """Shadows on, diffuse materials only, aa_samples % 4 == 0: the packet kernel traces the primary rays (four samples of a
+    pixel together) and single shadow rays; float sums, bytes and ray counts must equal the CPU restatement and the full
+    castRay kernel (RTDS_PACKET=0)."""
+    sph, mat = T.synthetic_scene(4000, 77)
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.set_lights(LIGHTS3)
+    try:
+        gpu_ctx.build(acc, mode=rt.MODE_TRUE if acc == rt.LBVH else rt.MODE_COMPAT)
+        nodes, order = gpu_ctx.export_bvh()
+        W, H, spp = 322, 203, 4
+        rgb, hit, accum, st = gpu_ctx.render(acc, W, H, spp, want_hit=True, want_accum=True, shadows=1)
+        rgb_o, hit_o, accum_o, _ = oracle.render_rows(sph, mat, nodes, order, W, H, spp, tie_by_objid=1 if acc == rt.LBVH else 0,
+                                                       lights=LIGHTS3, want_accum=True, shadows=1)
+        rays, sh, sec = oracle.last_ray_counts
+        assert (st["rays"], st["shadow_rays"], st["secondary_rays"]) == (rays, sh, sec) and sh > 1000 and sec == 0
+        assert np.array_equal(hit, hit_o) and accum.tobytes() == accum_o.tobytes() and np.array_equal(rgb, rgb_o)
+        monkeypatch.setenv("RTDS_PACKET", "0")
+        rgb_f, hit_f, accum_f, st_f = gpu_ctx.render(acc, W, H, spp, want_hit=True, want_accum=True, shadows=1)
+        assert accum.tobytes() == accum_f.tobytes() and np.array_equal(rgb, rgb_f) and np.array_equal(hit, hit_f)
+        assert st_f["shadow_rays"] == st["shadow_rays"]
+    finally:
+        gpu_ctx.set_lights(np.asarray([[0, 3, 30, 10, 1, 1, 1]], np.float32))
