@@ -47,14 +47,22 @@ __global__ void __launch_bounds__(256) bounds_kernel(const PrimView pv, int n, u
             bmax[a] = fmaxf(bmax[a], __shfl_xor_sync(0xffffffffu, bmax[a], o));
         }
     }
+    // one set of 12 atomics per BLOCK: all warps hammering the same 12 words made this kernel atomic-bound (77 us for 17 MB)
+    __shared__ unsigned sh[8][12];
+    const int warp = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            atomicMin(&out[a], f2ord(cmin[a]));
-            atomicMax(&out[3 + a], f2ord(cmax[a]));
-            atomicMin(&out[6 + a], f2ord(bmin[a]));
-            atomicMax(&out[9 + a], f2ord(bmax[a]));
+            sh[warp][a] = f2ord(cmin[a]); sh[warp][3 + a] = f2ord(cmax[a]);
+            sh[warp][6 + a] = f2ord(bmin[a]); sh[warp][9 + a] = f2ord(bmax[a]);
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const bool is_min = (threadIdx.x % 6) < 3;
+        unsigned v = sh[0][threadIdx.x];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = is_min ? min(v, sh[w][threadIdx.x]) : max(v, sh[w][threadIdx.x]);
+        if (is_min) atomicMin(&out[threadIdx.x], v); else atomicMax(&out[threadIdx.x], v);
     }
 }
 
@@ -201,10 +209,11 @@ __device__ __forceinline__ void store_child_box(Node64* nd, int side, const floa
 __global__ void __launch_bounds__(256)
 refit_kernel(const PrimView pv, const uint32_t* __restrict__ sorted_ids, int n, Node64* nodes,
              const int* __restrict__ leaf_parent, float4* __restrict__ leaf_sph, float4* __restrict__ leaf_tri, int* __restrict__ prim_order,
-             unsigned* __restrict__ counters, float* __restrict__ root_box)
+             unsigned* __restrict__ counters, float* __restrict__ root_box, int* __restrict__ max_depth)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
+    unsigned height = 0;     // of the subtree this thread has finished; travels through the arrival counter (bits 8..)
     int prim = (int)sorted_ids[j];
     prim_store_leaf(pv, prim, j, leaf_sph, leaf_tri);
     prim_order[j] = prim;
@@ -221,8 +230,9 @@ refit_kernel(const PrimView pv, const uint32_t* __restrict__ sorted_ids, int n, 
         Node64* nd = nodes + parent;
         store_child_box(nd, side, mn, mx);
         __threadfence();
-        unsigned old = atomicAdd(&counters[parent], 1u);
+        unsigned old = atomicAdd(&counters[parent], 1u + (height << 8));
         if (old == 0) return;  // the sibling subtree is not finished: its last thread continues
+        height = 1u + max(height, old >> 8);
         __threadfence();
         const float* omin = side ? nd->lmin : nd->rmin;
         const float* omax = side ? nd->lmax : nd->rmax;
@@ -235,6 +245,7 @@ refit_kernel(const PrimView pv, const uint32_t* __restrict__ sorted_ids, int n, 
         if (pe < 0) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) { root_box[a] = mn[a]; root_box[3 + a] = mx[a]; }
+            if (max_depth) *max_depth = (int)height;      // depth of the deepest leaf (root = 0): bounds the traversal stack
             return;
         }
         parent = pe >> 1;
@@ -420,12 +431,11 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
         karras_kernel<K><<<(n - 1 + T - 1) / T, T, 0, s>>>(d_keys, n, b.nodes, b.leaf_parent);
         launches += 1;
     }
-    refit_kernel<<<G, T, 0, s>>>(pv, d_vals, n, b.nodes, b.leaf_parent, b.leaf_sph, b.leaf_tri, b.prim_order, d_counters, d_root_box);
+    refit_kernel<<<G, T, 0, s>>>(pv, d_vals, n, b.nodes, b.leaf_parent, b.leaf_sph, b.leaf_tri, b.prim_order, d_counters, d_root_box, d_depth);
     b.n_prims = n;
     RTDS_TRY(rtds_bvh_reorder_preorder(ctx, b, base + off_reorder, &launches));
-    depth_kernel<<<G, T, 0, s>>>(b.nodes, b.leaf_parent, n, d_depth);
     widen_keys_kernel<K><<<G, T, 0, s>>>(d_keys, n, ctx->d_keys_sorted);
-    launches += 3;
+    launches += 2;
     RTDS_CUDA(cudaEventRecord(ctx->ev1, s));
     RTDS_CUDA(cudaGetLastError());
     RTDS_CUDA(cudaMemcpyAsync(b.root_box, d_root_box, sizeof(float) * 6, cudaMemcpyDeviceToHost, s));
@@ -475,11 +485,11 @@ int rtds_scene_bounds(rtds_ctx* ctx, float out12[12])
 
 // Bottom-up refit of a finished topology (nodes[].left/right/parent, leaf_parent[]) whose leaves hold the primitives
 // d_ids[leafpos]: fills every child-box slot, leaf_sph, prim_order and root_box. d_counters: n zeroed unsigneds.
-int rtds_bvh_refit(rtds_ctx* ctx, DeviceBvh& b, const uint32_t* d_ids, int n, unsigned* d_counters, float* d_root_box)
+int rtds_bvh_refit(rtds_ctx* ctx, DeviceBvh& b, const uint32_t* d_ids, int n, unsigned* d_counters, float* d_root_box, int* d_depth)
 {
     RTDS_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned) * (size_t)n, ctx->stream));
     refit_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(rtds_prim_view(ctx), d_ids, n, b.nodes, b.leaf_parent, b.leaf_sph, b.leaf_tri,
-                                                           b.prim_order, d_counters, d_root_box);
+                                                           b.prim_order, d_counters, d_root_box, d_depth);
     RTDS_CUDA(cudaGetLastError());
     return RTDS_OK;
 }

@@ -16,7 +16,7 @@
 #include <math.h>
 #include <algorithm>
 
-int rtds_bvh_refit(rtds_ctx* ctx, DeviceBvh& b, const uint32_t* d_ids, int n, unsigned* d_counters, float* d_root_box);  // lbvh.cu
+int rtds_bvh_refit(rtds_ctx* ctx, DeviceBvh& b, const uint32_t* d_ids, int n, unsigned* d_counters, float* d_root_box, int* d_depth);  // lbvh.cu
 int rtds_bvh_compute_depth(rtds_ctx* ctx, DeviceBvh& b, int* depth_out);
 int rtds_bvh_reorder_preorder(rtds_ctx* ctx, DeviceBvh& b, void* scratch, int* launches);
 
@@ -337,10 +337,14 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats*
     ++launches;
     unsigned* d_counters = (unsigned*)scan;
     float* d_root = (float*)(d_small + 16);
-    RTDS_TRY(rtds_bvh_refit(ctx, b, (const uint32_t*)perm[cur], n, d_counters, d_root));
+    int* d_depth = (int*)(d_root + 8);      // the refit carries subtree heights up: the root's height is the deepest leaf's depth
+    RTDS_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(int), s));
+    RTDS_TRY(rtds_bvh_refit(ctx, b, (const uint32_t*)perm[cur], n, d_counters, d_root, d_depth));
     ++launches;
     RTDS_CUDA(cudaGetLastError());
+    int depth = 0;
     RTDS_CUDA(cudaMemcpyAsync(b.root_box, d_root, sizeof(float) * 6, cudaMemcpyDeviceToHost, s));
+    RTDS_CUDA(cudaMemcpyAsync(&depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, s));
     RTDS_CUDA(cudaStreamSynchronize(s));
     b.n_prims = n;
     b.n_internal = n - 1;
@@ -348,9 +352,6 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats*
     b.tie_by_objid = 1;
     b.leaf_box_prim = ctx->prim_type == 0;
     RTDS_TRY(rtds_bvh_reorder_preorder(ctx, b, ctx->d_scratch, &launches));   // the level-loop scratch is free now
-    int depth = 0;
-    RTDS_TRY(rtds_bvh_compute_depth(ctx, b, &depth));
-    ++launches;
     RTDS_CUDA(cudaEventRecord(ctx->ev1, s));
     RTDS_CUDA(cudaStreamSynchronize(s));
     b.max_depth = depth;

@@ -33,7 +33,7 @@ def main():
         for r in range(world):
             p = ctx.render_params(W, H, SPP, rank=r, world=world, tile_rows=tr)
             ks, ts = [], []
-            for it in range(6):
+            for it in range(int(os.environ.get("ITERS", "6"))):
                 if flush_on:
                     flush.fill_(1)
                 torch.cuda.synchronize()
@@ -41,6 +41,8 @@ def main():
                 if it >= 2:
                     ks.append(st["ms_kernel"]); ts.append(st["ms_total"])
             per_rank.append((float(np.mean(ks)), float(np.mean(ts))))
+        if os.environ.get("PER_RANK"):
+            print(json.dumps({"tile_rows": tr, "kernel_ms_per_rank": [round(a, 4) for a, _ in per_rank]}), flush=True)
         k = [a for a, _ in per_rank]
         t = [b for _, b in per_rank]
         print(json.dumps({"world": world, "tile_rows": tr, "flush": flush_on, "kernel_ms_max": round(max(k), 4), "kernel_ms_min": round(min(k), 4),
