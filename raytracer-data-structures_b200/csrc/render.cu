@@ -1,15 +1,9 @@
-// render.cu — K10 (ray generation + traversal + ray/sphere test + shading + accumulate + 8-bit quantise)
-// and K11 (MT19937 jitter stream).
+// render.cu — K10: the render kernels (shading + accumulate + 8-bit quantise around the traversals of traverse.cuh,
+// primary directions from mt19937.cuh), the parity-probe trace kernel, the multi-GPU frame flags, and their host side.
 //
 // Reference semantics reproduced here (all citations relative to /root/reference/project/raytracer/):
-//   render()            main.cpp:541-566   ray generation, per-pixel sample loop, accumulation order
-//   random_double()     main.cpp:503-508   std::mt19937 (seed 5489) + uniform_real_distribution<double>:
-//                                          generate_canonical<double,53> = (lo + hi*2^32) / 2^64
-//   castRay()           main.cpp:291-500   candidate loop (strict <, first candidate wins), Phong shading
-//   boxIntersect()      accelerators.h:668-690  collect every leaf whose ancestor chain passes the slab test
-//   boundingBoxIntersection() accelerators.h:588-626  slab test: 6 IEEE divides, no t-range test
-//   raySphereIntersect() accelerators.h:79-92  geometric solution
-//   Vec3::normalize()   geometry.h:125-134 factor = (float)(1.0 / sqrt((double)n))
+//   render()            main.cpp:541-566   per-pixel sample loop, accumulation order
+//   castRay()           main.cpp:291-500   Phong shading, material branches, depth limit, shadow query
 //   write_into_file()   main.cpp:516-528   (unsigned char)(min(1, c/aa) * 255)
 // The translation unit is compiled with -fmad=false -prec-div=true -prec-sqrt=true so that every float
 // operation rounds exactly like the reference's SSE2 code.
@@ -20,892 +14,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "mt19937.cuh"
+#include "traverse.cuh"
+
 namespace {
-
-// ===================================================================================================
-// K11: MT19937
-// ===================================================================================================
-constexpr int MT_N = 624, MT_M = 397;
-constexpr int MT_SNAP_EVERY = 8;  // regenerations between stored state snapshots
-constexpr int MT_THREADS = 256;
-
-__device__ __forceinline__ uint32_t mt_twist(uint32_t u, uint32_t v)
-{
-    return (((u & 0x80000000u) | (v & 0x7fffffffu)) >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
-}
-__device__ __forceinline__ uint32_t mt_temper(uint32_t y)
-{
-    y ^= (y >> 11);
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= (y >> 18);
-    return y;
-}
-
-// One regeneration A -> B (624 words) by a block of >= 227 threads, three dependent phases.
-__device__ __forceinline__ void mt_regen(const uint32_t* __restrict__ A, uint32_t* __restrict__ B)
-{
-    const int t = threadIdx.x;
-    if (t < 227) B[t] = A[t + MT_M] ^ mt_twist(A[t], A[t + 1]);
-    __syncthreads();
-    if (t < 227) B[t + 227] = B[t] ^ mt_twist(A[t + 227], A[t + 228]);
-    __syncthreads();
-    if (t < 169) B[t + 454] = B[t + 227] ^ mt_twist(A[t + 454], A[t + 455]);
-    if (t == 169) B[623] = B[396] ^ mt_twist(A[623], B[0]);
-    __syncthreads();
-}
-
-// Sequential walk of the generator by ONE block: stores the state after every MT_SNAP_EVERY regenerations.
-// snap[k] = state after k*MT_SNAP_EVERY regenerations; k in [k0, k1). snap[0] is the seeded state.
-__global__ void __launch_bounds__(MT_THREADS) mt_snapshot_kernel(uint32_t* __restrict__ snap, int k0, int k1, uint32_t seed)
-{
-    __shared__ uint32_t S[2][MT_N];
-    const int t = threadIdx.x;
-    int cur = 0;
-    if (k0 == 0) {
-        if (t == 0) {
-            uint32_t x = seed;
-            S[0][0] = x;
-            for (int i = 1; i < MT_N; ++i) { x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i; S[0][i] = x; }
-        }
-        __syncthreads();
-        for (int i = t; i < MT_N; i += MT_THREADS) snap[i] = S[0][i];
-        k0 = 1;
-    } else {
-        for (int i = t; i < MT_N; i += MT_THREADS) S[0][i] = snap[(size_t)(k0 - 1) * MT_N + i];
-        __syncthreads();
-    }
-    for (int k = k0; k < k1; ++k) {
-        for (int r = 0; r < MT_SNAP_EVERY; ++r) { mt_regen(S[cur], S[cur ^ 1]); cur ^= 1; }
-        for (int i = t; i < MT_N; i += MT_THREADS) snap[(size_t)k * MT_N + i] = S[cur][i];
-    }
-}
-
-// Which part of the stream a rank needs: the samples of the scanline tiles it owns (all of it when world == 1).
-struct JitterOwner {
-    unsigned long long first_word;   // stream word of sample 0 of pixel 0
-    unsigned long long row_words;    // 4 * width * spp
-    int tile_rows, rank, world, height;
-};
-
-// Block b regenerates MT_SNAP_EVERY times from snapshot (s0 + b) and writes the tempered words.
-// out[0] is stream word (s0 * MT_SNAP_EVERY * 624). Chunks that hold no sample of an owned row are skipped.
-__global__ void __launch_bounds__(MT_THREADS) mt_expand_kernel(const uint32_t* __restrict__ snap, int s0,
-                                                               uint32_t* __restrict__ out, size_t n_words, const JitterOwner own)
-{
-    __shared__ uint32_t S[2][MT_N];
-    const int t = threadIdx.x;
-    const size_t base = (size_t)blockIdx.x * MT_SNAP_EVERY * MT_N;
-    if (own.world > 1) {
-        const unsigned long long wlo = (unsigned long long)(s0 + blockIdx.x) * MT_SNAP_EVERY * MT_N;
-        const unsigned long long whi = wlo + MT_SNAP_EVERY * MT_N - 1;
-        long long ylo = wlo > own.first_word ? (long long)((wlo - own.first_word) / own.row_words) : 0;
-        long long yhi = whi > own.first_word ? (long long)((whi - own.first_word) / own.row_words) : 0;
-        if (yhi >= own.height) yhi = own.height - 1;
-        bool mine = false;
-        for (long long tl = ylo / own.tile_rows; tl <= yhi / own.tile_rows; ++tl) mine |= (tl % own.world) == own.rank;
-        if (!mine) return;
-    }
-    const uint32_t* src = snap + (size_t)(s0 + blockIdx.x) * MT_N;
-    for (int i = t; i < MT_N; i += MT_THREADS) S[0][i] = src[i];
-    __syncthreads();
-    int cur = 0;
-    for (int r = 0; r < MT_SNAP_EVERY; ++r) {
-        mt_regen(S[cur], S[cur ^ 1]);
-        cur ^= 1;
-        for (int i = t; i < MT_N; i += MT_THREADS) {
-            size_t w = base + (size_t)r * MT_N + i;
-            if (w < n_words) out[w] = mt_temper(S[cur][i]);
-        }
-    }
-}
-
-// exact uint32 -> double without the conversion unit: 2^52 + u is representable, the subtraction is exact
-__device__ __forceinline__ double u32_to_double(uint32_t u) { return __hiloint2double(0x43300000, (int)u) - 4503599627370496.0; }
-
-// generate_canonical<double,53>(mt19937): two draws, (lo + hi*2^32)/2^64, clamped below 1.
-__device__ __forceinline__ double canonical53(uint32_t lo, uint32_t hi)
-{
-    // hi * 2^32 exactly: 2^84 + hi * 2^32 is representable (ulp 2^32), the subtraction is exact; the sum rounds once
-    // (to nearest even), exactly like the reference's long-double sum narrowed to double
-    const double hi32 = __hiloint2double(0x45300000, (int)hi) - 19342813113834066795298816.0;
-    const double sum = u32_to_double(lo) + hi32;
-    double r = sum * 5.42101086242752217e-20;    // / 2^64, exact
-    if (r >= 1.0) r = 0.99999999999999988897769753748434595763683319091796875;  // nextafter(1,0)
-    return r;
-}
-
-__global__ void jitter_doubles_kernel(const uint32_t* __restrict__ words, size_t first_double_rel, int n, double* __restrict__ out)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        size_t w = (first_double_rel + (size_t)i) * 2;
-        out[i] = canonical53(words[w], words[w + 1]);
-    }
-}
-
-// geometry.h:125-134: n = x*x+y*y+z*z (float); factor = (float)(1 / sqrt((double)n))
-__device__ __forceinline__ void normalize3(float& x, float& y, float& z)
-{
-    float n = x * x + y * y + z * z;
-    if (n > 0) {
-        float factor = (float)(1.0 / sqrt((double)n));
-        x *= factor; y *= factor; z *= factor;
-    }
-}
-
-// Primary ray direction of sample (px, py) from its four jitter words: main.cpp:554-557 (double -> float exactly as there).
-struct RayGen { float angle, aspect, inv_w, inv_h; };
-__device__ __forceinline__ void primary_dir(const uint4 jw, int px, int py, const RayGen& G, float& dx, float& dy, float& dz)
-{
-    const double r1 = canonical53(jw.x, jw.y), r2 = canonical53(jw.z, jw.w);
-    dx = (float)((2 * ((u32_to_double((unsigned)px) + r1) * (double)G.inv_w) - 1) * (double)G.angle * (double)G.aspect);
-    dy = (float)((1 - 2 * ((u32_to_double((unsigned)py) + r2) * (double)G.inv_h)) * (double)G.angle);
-    dz = -1;
-    normalize3(dx, dy, dz);
-}
-
-// exact unsigned division by a launch-time constant (Granlund-Montgomery round-up form): magic == 0 -> power of two
-struct FastDiv { uint32_t magic, shift; };
-__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv d)
-{
-    if (d.magic == 0) return n >> d.shift;
-    const uint32_t q = __umulhi(n, d.magic);
-    return (((n - q) >> 1) + q) >> d.shift;
-}
-
-// K11 + ray generation fused: block b regenerates MT_SNAP_EVERY times from snapshot (s0 + b), each regeneration
-// written straight into the next 624-word slice of one shared array (the state after regeneration r IS slice r), then
-// all threads turn the chunk's 1,248 samples (4 words each) into primary directions — the double-precision part of
-// main.cpp:554-557 and Vec3::normalize — and store 3 floats per sample: 12 bytes instead of the 16 bytes of raw
-// words, and the render kernel starts from ready directions. dirs[3 * g] is frame sample g = pixel * spp + k.
-__global__ void __launch_bounds__(MT_THREADS) mt_expand_dirs_kernel(const uint32_t* __restrict__ snap, int s0, float* __restrict__ dirs,
-                                                                    unsigned long long first_sample, unsigned n_samples, int width,
-                                                                    int spp, const FastDiv div_spp, const FastDiv div_width,
-                                                                    const RayGen G, const JitterOwner own)
-{
-    __shared__ __align__(16) uint32_t words[(MT_SNAP_EVERY + 1) * MT_N];      // slice 0 = the snapshot
-    const int t = threadIdx.x;
-    const unsigned long long wlo = (unsigned long long)(s0 + blockIdx.x) * MT_SNAP_EVERY * MT_N;
-    if (own.world > 1) {
-        const unsigned long long whi = wlo + MT_SNAP_EVERY * MT_N - 1;
-        long long ylo = wlo > own.first_word ? (long long)((wlo - own.first_word) / own.row_words) : 0;
-        long long yhi = whi > own.first_word ? (long long)((whi - own.first_word) / own.row_words) : 0;
-        if (yhi >= own.height) yhi = own.height - 1;
-        bool mine = false;
-        for (long long tl = ylo / own.tile_rows; tl <= yhi / own.tile_rows; ++tl) mine |= (tl % own.world) == own.rank;
-        if (!mine) return;
-    }
-    const uint32_t* src = snap + (size_t)(s0 + blockIdx.x) * MT_N;
-    for (int i = t; i < MT_N; i += MT_THREADS) words[i] = src[i];
-    __syncthreads();
-    for (int r = 0; r < MT_SNAP_EVERY; ++r) mt_regen(words + r * MT_N, words + (r + 1) * MT_N);
-    // all threads, no barriers: temper, canonical doubles, direction, normalise, store
-    const unsigned long long as0 = wlo / 4;           // absolute stream sample of the chunk's first four words
-    const uint4* w4 = reinterpret_cast<const uint4*>(words + MT_N);
-    for (int i = t; i < MT_SNAP_EVERY * MT_N / 4; i += MT_THREADS) {
-        const unsigned long long as = as0 + i;
-        if (as >= first_sample && as - first_sample < n_samples) {
-            const unsigned g = (unsigned)(as - first_sample);
-            const unsigned pix = fast_div(g, div_spp);
-            const unsigned py = fast_div(pix, div_width), px = pix - py * (unsigned)width;
-            const uint4 w = w4[i];
-            const uint4 jw = make_uint4(mt_temper(w.x), mt_temper(w.y), mt_temper(w.z), mt_temper(w.w));
-            float dx, dy, dz;
-            primary_dir(jw, (int)px, (int)py, G, dx, dy, dz);
-            float* o = dirs + 3 * (size_t)g;
-            o[0] = dx; o[1] = dy; o[2] = dz;
-        }
-    }
-}
-
-// ===================================================================================================
-// ray / box / sphere primitives with the reference's exact operation order
-// ===================================================================================================
-struct Counters { unsigned node_tests, prim_tests, node_visits, rays; };
-
-// accelerators.h:588-626 (and :628-666 for the variant returning tMin/tMax)
-__device__ __forceinline__ bool slab_test(float ox, float oy, float oz, float dx, float dy, float dz, float bminx,
-                                          float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, float& tmin_o,
-                                          float& tmax_o)
-{
-    float tmin = (bminx - ox) / dx;
-    float tmax = (bmaxx - ox) / dx;
-    if (tmin > tmax) { float t = tmin; tmin = tmax; tmax = t; }
-    float tymin = (bminy - oy) / dy;
-    float tymax = (bmaxy - oy) / dy;
-    if (tymin > tymax) { float t = tymin; tymin = tymax; tymax = t; }
-    if ((tmin > tymax) || (tymin > tmax)) return false;
-    if (tymin > tmin) tmin = tymin;
-    if (tymax < tmax) tmax = tymax;
-    float tzmin = (bminz - oz) / dz;
-    float tzmax = (bmaxz - oz) / dz;
-    if (tzmin > tzmax) { float t = tzmin; tzmin = tzmax; tzmax = t; }
-    if ((tmin > tzmax) || (tzmin > tmax)) return false;
-    if (tzmin > tmin) tmin = tzmin;
-    if (tzmax < tmax) tmax = tzmax;
-    tmin_o = tmin;
-    tmax_o = tmax;
-    return true;
-}
-
-// accelerators.h:79-92; s = {cx,cy,cz,r^2}
-__device__ __forceinline__ bool sphere_test(float ox, float oy, float oz, float dx, float dy, float dz, float4 s, float& t0,
-                                            float& t1)
-{
-    float lx = s.x - ox, ly = s.y - oy, lz = s.z - oz;
-    float tca = lx * dx + ly * dy + lz * dz;
-    if (tca < 0) return false;
-    float d2 = (lx * lx + ly * ly + lz * lz) - tca * tca;
-    if (d2 > s.w) return false;
-    float thc = sqrtf(s.w - d2);
-    t0 = tca - thc;
-    t1 = tca + thc;
-    return true;
-}
-
-// Möller–Trumbore as written in the reference's (never compiled) MOLLER_TRUMBORE branch of
-// Triangle::rayTriangleIntersect (main.cpp:138-162, `v_0` read as v0, no culling, EPS = 1e-6 main.cpp:59), plus the
-// t < 0 rejection of its geometric branch (main.cpp:184). Extension: the reference never instantiates triangles.
-__device__ __forceinline__ bool tri_test(float ox, float oy, float oz, float dx, float dy, float dz, float4 v0, float4 v1, float4 v2,
-                                         float& t)
-{
-    const float e1x = v1.x - v0.x, e1y = v1.y - v0.y, e1z = v1.z - v0.z;
-    const float e2x = v2.x - v0.x, e2y = v2.y - v0.y, e2z = v2.z - v0.z;
-    const float px = dy * e2z - dz * e2y, py = dz * e2x - dx * e2z, pz = dx * e2y - dy * e2x;   // dir x v0v2
-    const float det = e1x * px + e1y * py + e1z * pz;
-    if (fabsf(det) < 1e-6f) return false;
-    const float inv = 1 / det;
-    const float tx = ox - v0.x, ty = oy - v0.y, tz = oz - v0.z;
-    const float u = (tx * px + ty * py + tz * pz) * inv;
-    if (u < 0 || u > 1) return false;
-    const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;   // tvec x v0v1
-    const float v = (dx * qx + dy * qy + dz * qz) * inv;
-    if (v < 0 || u + v > 1) return false;
-    t = (e2x * qx + e2y * qy + e2z * qz) * inv;
-    return !(t < 0);
-}
-
-// primitive test on an objId-indexed table (NONE loop, KD leaves)
-__device__ __forceinline__ bool obj_test(int type, const float4* __restrict__ sph, const float4* __restrict__ tri, int i, float ox, float oy,
-                                         float oz, float dx, float dy, float dz, float& t0, float& t1)
-{
-    if (type == 0) {
-        float4 s = __ldg(sph + i);
-        return sphere_test(ox, oy, oz, dx, dy, dz, make_float4(s.x, s.y, s.z, s.w * s.w), t0, t1);
-    }
-    float t;
-    if (!tri_test(ox, oy, oz, dx, dy, dz, __ldg(tri + 3 * (size_t)i), __ldg(tri + 3 * (size_t)i + 1), __ldg(tri + 3 * (size_t)i + 2), t)) return false;
-    t0 = t1 = t;
-    return true;
-}
-
-// un-normalised surface normal at the hit: spheres P - centre (main.cpp:398), triangles v0v1 x v0v2 (main.cpp:165-168)
-__device__ __forceinline__ void raw_normal(int type, const float4* __restrict__ sph_c /*centre in .xyz*/, const float4* __restrict__ tri,
-                                           size_t idx, float hx, float hy, float hz, float& nx, float& ny, float& nz)
-{
-    if (type == 0) { float4 s = __ldg(sph_c + idx); nx = hx - s.x; ny = hy - s.y; nz = hz - s.z; }
-    else {
-        float4 a = __ldg(tri + 3 * idx), b = __ldg(tri + 3 * idx + 1), c = __ldg(tri + 3 * idx + 2);
-        float e1x = b.x - a.x, e1y = b.y - a.y, e1z = b.z - a.z, e2x = c.x - a.x, e2y = c.y - a.y, e2z = c.z - a.z;
-        nx = e1y * e2z - e1z * e2y; ny = e1z * e2x - e1x * e2z; nz = e1x * e2y - e1y * e2x;
-    }
-}
-
-// candidate update of main.cpp:350-355 / :379-384 with the reference's "first candidate wins" made
-// order-independent: `key` is the candidate's position in the reference's candidate order.
-__device__ __forceinline__ void candidate(float t0, float t1, int key, int leaf, float& tnear, int& best_key, int& best_leaf)
-{
-    if (t0 < 0) t0 = t1;
-    if (t0 < tnear || (t0 == tnear && best_leaf >= 0 && key < best_key)) {
-        tnear = t0; best_key = key; best_leaf = leaf;
-    }
-}
-
-struct BvhView {
-    const Node64* nodes;
-    const float4* leaf_sph;
-    const float4* leaf_tri;
-    int           prim_type;
-    const int*    prim_order;
-    const int*    leaf_parent;
-    int           root_ref;
-    int           tie_by_objid;
-    int           leaf_box_prim;   // sphere leaves whose box is exactly c -/+ r
-    float         root_box[6];
-};
-
-constexpr int STACK_MAX = 64;
-
-__device__ __forceinline__ bool leaf_test(const BvhView& B, int leaf, float ox, float oy, float oz, float dx, float dy, float dz, float& t0,
-                                          float& t1)
-{
-    if (B.prim_type == 0) { float4 s = __ldg(B.leaf_sph + leaf); s.w = s.w * s.w; return sphere_test(ox, oy, oz, dx, dy, dz, s, t0, t1); }   // radius2 = r*r, accelerators.h:71
-    float t;
-    if (!tri_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_tri + 3 * (size_t)leaf), __ldg(B.leaf_tri + 3 * (size_t)leaf + 1),
-                  __ldg(B.leaf_tri + 3 * (size_t)leaf + 2), t))
-        return false;
-    t0 = t1 = t;
-    return true;
-}
-
-// pruning margin for the ordered traversal: bounds the float error of raySphereIntersect's t0 against the
-// true entry distance for any sphere inside the root box (DESIGN.md "Ordered traversal is exact").
-__device__ __forceinline__ float prune_margin(const float rb[6], float ox, float oy, float oz)
-{
-    float ex = fmaxf(fabsf(rb[0] - ox), fabsf(rb[3] - ox));
-    float ey = fmaxf(fabsf(rb[1] - oy), fabsf(rb[4] - oy));
-    float ez = fmaxf(fabsf(rb[2] - oz), fabsf(rb[5] - oz));
-    float D = sqrtf(ex * ex + ey * ey + ez * ez);
-    return D * 0.00278f;
-}
-
-// Conservative slab test for INTERIOR boxes of the ordered traversal: t = (b - o) * (1/d) instead of six IEEE
-// divides, with the interval widened by more than the rounding difference between the two forms, so it accepts
-// every box the reference's test accepts (and a few more). Interior tests only steer the descent — whether a
-// sphere becomes a candidate is decided by the EXACT test on its own leaf box (a leaf box inside a node box
-// passes the reference's test only if the node box does: the per-axis intervals nest monotonically).
-// Valid for finite, non-tiny direction components (checked once per ray).
-constexpr float WIDE_EPS = 4.76837158e-7f;   // 2^-21 > 2^-23 (rcp.approx) + 2^-24 (mul) + 2^-24 (the divide's own rounding), x2 margin
-__device__ __forceinline__ bool slab_wide(float ox, float oy, float oz, float ix, float iy, float iz, float bminx, float bminy,
-                                          float bminz, float bmaxx, float bmaxy, float bmaxz, float& tmin_o, float& tmax_o)
-{
-    float x0 = (bminx - ox) * ix, x1 = (bmaxx - ox) * ix;
-    float y0 = (bminy - oy) * iy, y1 = (bmaxy - oy) * iy;
-    float z0 = (bminz - oz) * iz, z1 = (bmaxz - oz) * iz;
-    float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
-    float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
-    tmin = tmin - fabsf(tmin) * WIDE_EPS;
-    tmax = tmax + fabsf(tmax) * WIDE_EPS;
-    tmin_o = tmin;
-    tmax_o = tmax;
-    return tmin <= tmax;
-}
-
-template <bool EXACT>
-__device__ __forceinline__ void traverse_bvh(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
-                                             float& tnear, int& best_key, int& best_leaf, Counters& cnt)
-{
-    float tmn, tmx;
-    cnt.node_tests++;
-    if (!slab_test(ox, oy, oz, dx, dy, dz, B.root_box[0], B.root_box[1], B.root_box[2], B.root_box[3], B.root_box[4],
-                   B.root_box[5], tmn, tmx))
-        return;
-    if (B.root_ref < 0) {
-        float t0, t1;
-        cnt.prim_tests++;
-        if (leaf_test(B, 0, ox, oy, oz, dx, dy, dz, t0, t1))
-            candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order) : 0, 0, tnear, best_key, best_leaf);
-        return;
-    }
-    const float margin = EXACT ? 0.0f : prune_margin(B.root_box, ox, oy, oz);
-    // reciprocal direction for the conservative interior test; rays with a zero / tiny / non-finite component
-    // take the exact divide-based test everywhere
-    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
-    const bool wide_ok = !EXACT && fabsf(ix) < 1e30f && fabsf(iy) < 1e30f && fabsf(iz) < 1e30f;
-    int   stack[STACK_MAX];
-    float stack_t[EXACT ? 1 : STACK_MAX];
-    int sp = 0;
-    int node = 0;
-    while (true) {
-        const float4* q = reinterpret_cast<const float4*>(B.nodes + node);
-        float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-        int4 q3 = __ldg(reinterpret_cast<const int4*>(q + 3));
-        cnt.node_visits++;
-        cnt.node_tests += 2;
-        const int left = q3.x, right = q3.y;
-        float tminL, tmaxL, tminR, tmaxR;
-        bool hitL, hitR;
-        if (!EXACT && wide_ok) {
-            // interior child: the conservative test is the answer; leaf child: it is a filter — a box the wide
-            // test rejects is rejected by the reference's test too, only survivors pay for the six divides
-            hitL = slab_wide(ox, oy, oz, ix, iy, iz, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tminL, tmaxL);
-            hitR = slab_wide(ox, oy, oz, ix, iy, iz, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tminR, tmaxR);
-            if (hitL && left < 0) hitL = slab_test(ox, oy, oz, dx, dy, dz, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tminL, tmaxL);
-            if (hitR && right < 0) hitR = slab_test(ox, oy, oz, dx, dy, dz, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tminR, tmaxR);
-        } else {
-            hitL = slab_test(ox, oy, oz, dx, dy, dz, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tminL, tmaxL);
-            hitR = slab_test(ox, oy, oz, dx, dy, dz, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tminR, tmaxR);
-        }
-        if (!EXACT) {
-            // NaN-safe: a comparison with NaN is false and keeps the child
-            if (hitL && (tminL > tnear + margin || tmaxL < -margin)) hitL = false;
-            if (hitR && (tminR > tnear + margin || tmaxR < -margin)) hitR = false;
-        }
-        if (hitL && left < 0) {
-            int leaf = ~left;
-            float t0, t1;
-            cnt.prim_tests++;
-            if (leaf_test(B, leaf, ox, oy, oz, dx, dy, dz, t0, t1))
-                candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
-            hitL = false;
-        }
-        if (hitR && right < 0) {
-            int leaf = ~right;
-            float t0, t1;
-            cnt.prim_tests++;
-            if (leaf_test(B, leaf, ox, oy, oz, dx, dy, dz, t0, t1))
-                candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
-            hitR = false;
-        }
-        if (hitL && hitR) {
-            int nearc = left, farc = right;
-            float tfar = tminR;
-            if (!EXACT && tminR < tminL) { nearc = right; farc = left; tfar = tminL; }
-            if (sp < STACK_MAX) {
-                stack[sp] = farc;
-                if (!EXACT) stack_t[sp] = tfar;
-                ++sp;
-            }
-            node = nearc;
-            continue;
-        }
-        if (hitL) { node = left; continue; }
-        if (hitR) { node = right; continue; }
-        // pop
-        bool found = false;
-        while (sp > 0) {
-            --sp;
-            if (!EXACT && stack_t[sp] > tnear + margin) continue;
-            node = stack[sp];
-            found = true;
-            break;
-        }
-        if (!found) break;
-    }
-}
-
-// The ordered traversal (exact = 0), written "while-while": interior nodes and leaves are both stack items, so the
-// hot interior loop is branch-light (both children go through the conservative reciprocal test, no leaf special
-// case), and a leaf is only opened when it is popped with tmin still below the current hit.
-// ZERO_O: the ray starts at the origin (every primary ray, main.cpp:558): t = b * (1/d), one multiply per plane.
-// ANYHIT (shadow rays, main.cpp:468-473): stop at the first candidate with t'^2 < t2max. "The nearest hit satisfies
-// tNear^2 < lightDistance2" and "some candidate does" are the same predicate (every t' is >= 0), so the answer equals
-// the closest-hit formulation's; subtrees that start beyond sqrt(t2max) are never opened.
-// OCT: direction octant (bit0: dx < 0, bit1: dy < 0, bit2: dz < 0), a compile-time constant: the near / far plane of
-// every slab is then known without min/max (t = plane * (1/d) is monotone in the plane), so a box costs six multiplies,
-// one FMNMX3 for the entry and one for the exit distance. OCT < 0: generic form with per-axis min/max.
-//
-// Conservativeness. With 1e-30 < |1/d| < 1e30 every t_a = (b - o) * rcp(d) differs from the reference's
-// t_e = (b - o) / d by at most 2^-22 relative (rcp.approx 2^-23, the multiply 2^-24, the divide's own rounding 2^-24).
-//  * interior boxes / leaf filter: exit distance widened by WIDE2 = 2^-20 relative, entry distance left as computed:
-//    tmin_e <= tmax_e implies tmin_a <= tmax_a (1 + 2^-20 sign-aware) in all three sign cases, so every box the
-//    reference's test accepts is accepted. The pruning bound tlim is widened by the same 2^-20 instead of the entry
-//    distance (accepts a superset of "tmin_a (1 - 2^-21) <= tlim").
-//  * leaves whose box is the sphere's own box (c -/+ r, main.cpp:686-688): the box is rebuilt from the leaf's sphere
-//    record (no parent-record reload) and tested with the same multiplies; if the NARROWED interval (entry pushed up,
-//    exit pushed down by 2^-21) is still non-empty the reference's divide-based test accepts for certain; only the
-//    ambiguous sliver in between (and denormal-range distances) pays for the six IEEE divides. Other trees (median
-//    split with dropped ranges, triangles) run the divide test on the box stored in the parent's record.
-// Cold paths of the ordered traversal, kept OUT OF LINE so that the octant copies of the hot loop stay small
-// (instruction-cache footprint): arguments and results by value, the view by pointer into the kernel's
-// __grid_constant__ parameter block.
-struct ColdHit { float tnear; int key, leaf; unsigned node_tests, prim_tests, node_visits; };
-static __device__ __noinline__ ColdHit traverse_exact_cold(const BvhView* B, float ox, float oy, float oz, float dx, float dy, float dz,
-                                                           float tnear, int key, int leaf)
-{
-    Counters c = {0, 0, 0, 0};
-    traverse_bvh<true>(*B, ox, oy, oz, dx, dy, dz, tnear, key, leaf, c);
-    return ColdHit{tnear, key, leaf, c.node_tests, c.prim_tests, c.node_visits};
-}
-static __device__ __noinline__ bool slab_test_cold(float ox, float oy, float oz, float dx, float dy, float dz, float bx0, float by0,
-                                                   float bz0, float bx1, float by1, float bz1)
-{
-    float a, b;
-    return slab_test(ox, oy, oz, dx, dy, dz, bx0, by0, bz0, bx1, by1, bz1, a, b);
-}
-// leaf whose box is NOT its sphere's own box (triangles; median-split trees with dropped ranges): the reference's
-// divide-based test on the box stored in the parent's record, then the primitive
-struct ColdLeaf { int pass; float t0, t1; unsigned prim_tests; };
-static __device__ __noinline__ ColdLeaf leaf_parent_box_cold(const BvhView* Bp, int leaf, float ox, float oy, float oz, float dx, float dy,
-                                                             float dz)
-{
-    const BvhView& B = *Bp;
-    const int lp = __ldg(B.leaf_parent + leaf);
-    const float4* q = reinterpret_cast<const float4*>(B.nodes + (lp & 0x7fffffff));
-    const float4 q1 = __ldg(q + 1);
-    float bx0, by0, bz0, bx1, by1, bz1;
-    if (lp < 0) { const float4 q2 = __ldg(q + 2); bx0 = q1.z; by0 = q1.w; bz0 = q2.x; bx1 = q2.y; by1 = q2.z; bz1 = q2.w; }
-    else { const float4 q0 = __ldg(q); bx0 = q0.x; by0 = q0.y; bz0 = q0.z; bx1 = q0.w; by1 = q1.x; bz1 = q1.y; }
-    ColdLeaf r = {0, 0.f, 0.f, 0u};
-    float a, b2;
-    if (slab_test(ox, oy, oz, dx, dy, dz, bx0, by0, bz0, bx1, by1, bz1, a, b2)) {
-        r.prim_tests = 1;
-        r.pass = leaf_test(B, leaf, ox, oy, oz, dx, dy, dz, r.t0, r.t1) ? 1 : 0;
-    }
-    return r;
-}
-
-constexpr float WIDE2 = 9.53674316e-7f;      // 2^-20
-constexpr float NARROW_EPS = 4.76837158e-7f; // 2^-21
-
-template <int OCT>
-__device__ __forceinline__ void slab_interval(float x0, float y0, float z0, float x1, float y1, float z1, float& tmin, float& tmax)
-{
-    // (x0,y0,z0) = t of the box's min planes, (x1,y1,z1) = t of its max planes
-    if (OCT >= 0) {
-        const float xn = (OCT & 1) ? x1 : x0, xf = (OCT & 1) ? x0 : x1;
-        const float yn = (OCT & 2) ? y1 : y0, yf = (OCT & 2) ? y0 : y1;
-        const float zn = (OCT & 4) ? z1 : z0, zf = (OCT & 4) ? z0 : z1;
-        tmin = fmaxf(fmaxf(xn, yn), zn);
-        tmax = fminf(fminf(xf, yf), zf);
-    } else {
-        tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
-        tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
-    }
-}
-
-template <bool ZERO_O, bool ANYHIT, int OCT>
-__device__ __forceinline__ void traverse_fast_loop(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
-                                                   float ix, float iy, float iz, float margin, float& tnear, int& best_key,
-                                                   int& best_leaf, Counters& cnt, float t2max)
-{
-    const float neg_margin = -margin;
-    // a subtree is opened only while its entry distance is <= tlim (kept widened by 2^-20, see above)
-    float tlim = ANYHIT ? sqrtf(t2max) + margin : tnear + margin;
-    tlim = __fmaf_rn(fabsf(tlim), WIDE2, tlim);
-    int2 stack[STACK_MAX];        // {child ref, entry distance as bits}: one 8-byte local store / load per push / pop
-    int sp = 0;
-    int node = 0;
-    unsigned visits = 0;
-    while (true) {
-        if (node >= 0) {
-            const float4* q = reinterpret_cast<const float4*>(B.nodes + node);
-            const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-            const int2 ch = __ldg(reinterpret_cast<const int2*>(q + 3));
-            ++visits;
-            float lx0, lx1, ly0, ly1, lz0, lz1, rx0, rx1, ry0, ry1, rz0, rz1;
-            if (ZERO_O) {
-                lx0 = q0.x * ix; ly0 = q0.y * iy; lz0 = q0.z * iz; lx1 = q0.w * ix; ly1 = q1.x * iy; lz1 = q1.y * iz;
-                rx0 = q1.z * ix; ry0 = q1.w * iy; rz0 = q2.x * iz; rx1 = q2.y * ix; ry1 = q2.z * iy; rz1 = q2.w * iz;
-            } else {
-                lx0 = (q0.x - ox) * ix; ly0 = (q0.y - oy) * iy; lz0 = (q0.z - oz) * iz;
-                lx1 = (q0.w - ox) * ix; ly1 = (q1.x - oy) * iy; lz1 = (q1.y - oz) * iz;
-                rx0 = (q1.z - ox) * ix; ry0 = (q1.w - oy) * iy; rz0 = (q2.x - oz) * iz;
-                rx1 = (q2.y - ox) * ix; ry1 = (q2.z - oy) * iy; rz1 = (q2.w - oz) * iz;
-            }
-            float tminL, tmaxL, tminR, tmaxR;
-            slab_interval<OCT>(lx0, ly0, lz0, lx1, ly1, lz1, tminL, tmaxL);
-            slab_interval<OCT>(rx0, ry0, rz0, rx1, ry1, rz1, tminR, tmaxR);
-            tmaxL = __fmaf_rn(fabsf(tmaxL), WIDE2, tmaxL);
-            tmaxR = __fmaf_rn(fabsf(tmaxR), WIDE2, tmaxR);
-            const bool hitL = tminL <= fminf(tmaxL, tlim) && tmaxL >= neg_margin;
-            const bool hitR = tminR <= fminf(tmaxR, tlim) && tmaxR >= neg_margin;
-            if (hitL && hitR) {
-                const bool rfirst = tminR < tminL;
-                stack[sp] = make_int2(rfirst ? ch.x : ch.y, __float_as_int(rfirst ? tminL : tminR));
-                sp = min(sp + 1, STACK_MAX - 1);
-                node = rfirst ? ch.y : ch.x;
-                continue;
-            }
-            if (hitL | hitR) { node = hitL ? ch.x : ch.y; continue; }
-        } else {
-            const int leaf = ~node;
-            bool pass;
-            float t0, t1;
-            if (B.leaf_box_prim) {
-                // sphere leaf: its box is c -/+ r (bit-identical to what the builder stored in the parent's record)
-                const float4 s = __ldg(B.leaf_sph + leaf);
-                const float bx0 = s.x - s.w, by0 = s.y - s.w, bz0 = s.z - s.w, bx1 = s.x + s.w, by1 = s.y + s.w, bz1 = s.z + s.w;
-                float x0, y0, z0, x1, y1, z1;
-                if (ZERO_O) { x0 = bx0 * ix; y0 = by0 * iy; z0 = bz0 * iz; x1 = bx1 * ix; y1 = by1 * iy; z1 = bz1 * iz; }
-                else {
-                    x0 = (bx0 - ox) * ix; y0 = (by0 - oy) * iy; z0 = (bz0 - oz) * iz;
-                    x1 = (bx1 - ox) * ix; y1 = (by1 - oy) * iy; z1 = (bz1 - oz) * iz;
-                }
-                float tmn, tmx;
-                slab_interval<OCT>(x0, y0, z0, x1, y1, z1, tmn, tmx);
-                pass = __fmaf_rn(fabsf(tmn), NARROW_EPS, tmn) <= __fmaf_rn(-fabsf(tmx), NARROW_EPS, tmx) &&
-                       fminf(fabsf(tmn), fabsf(tmx)) > 1e-30f;
-                if (!pass) pass = slab_test_cold(ox, oy, oz, dx, dy, dz, bx0, by0, bz0, bx1, by1, bz1);
-                if (pass) {
-                    cnt.prim_tests++;
-                    pass = sphere_test(ox, oy, oz, dx, dy, dz, make_float4(s.x, s.y, s.z, s.w * s.w), t0, t1);
-                }
-            } else {
-                const ColdLeaf r = leaf_parent_box_cold(&B, leaf, ox, oy, oz, dx, dy, dz);
-                cnt.prim_tests += r.prim_tests;
-                pass = r.pass != 0; t0 = r.t0; t1 = r.t1;
-            }
-            if (pass) {
-                if (ANYHIT) {
-                    if (t0 < 0) t0 = t1;
-                    if (t0 * t0 < t2max) { tnear = t0; best_leaf = leaf; cnt.node_visits += visits; cnt.node_tests += 2 * visits; return; }
-                } else {
-                    candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
-                    tlim = tnear + margin;
-                    tlim = __fmaf_rn(fabsf(tlim), WIDE2, tlim);
-                }
-            }
-        }
-        // pop
-        bool found = false;
-        while (sp > 0) {
-            --sp;
-            const int2 e = stack[sp];
-            if (__int_as_float(e.y) > tlim) continue;
-            node = e.x;
-            found = true;
-            break;
-        }
-        if (!found) break;
-    }
-    cnt.node_visits += visits;
-    cnt.node_tests += 2 * visits;
-}
-
-// ZNEG: the caller guarantees dz < 0 (every primary ray: dz = -1 before normalisation), four octants instead of eight.
-template <bool ZERO_O, bool ANYHIT = false, bool ZNEG = false>
-__device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
-                                              float& tnear, int& best_key, int& best_leaf, Counters& cnt, float t2max = 0.f)
-{
-    // 1/d only feeds the conservative tests (its error is inside the widening): one MUFU.RCP each instead of an IEEE divide
-    float ix, iy, iz;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"(dx));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(dy));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(dz));
-    const float amin = fminf(fminf(fabsf(ix), fabsf(iy)), fabsf(iz)), amax = fmaxf(fmaxf(fabsf(ix), fabsf(iy)), fabsf(iz));
-    if (B.root_ref < 0 || !(amin > 1e-30f && amax < 1e30f)) {
-        // single-leaf tree, or a zero / tiny / huge / non-finite direction component: the divide-based traversal
-        const ColdHit h = traverse_exact_cold(&B, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf);
-        tnear = h.tnear; best_key = h.key; best_leaf = h.leaf;
-        cnt.node_tests += h.node_tests; cnt.prim_tests += h.prim_tests; cnt.node_visits += h.node_visits;
-        if (ANYHIT && !(best_leaf >= 0 && tnear * tnear < t2max)) best_leaf = -1;
-        return;
-    }
-    // No separate root test: a leaf box that passes the reference's slab test lies inside the root box, which then
-    // passes too (nesting), so the candidate set does not depend on it; rays that miss the scene fall out of the
-    // first interior visit.
-    const float margin = prune_margin(B.root_box, ox, oy, oz);
-    const int oct = (dx < 0 ? 1 : 0) | (dy < 0 ? 2 : 0) | ((ZNEG || dz < 0) ? 4 : 0);
-#define RTDS_OCT_CASE(o) case o: traverse_fast_loop<ZERO_O, ANYHIT, o>(B, ox, oy, oz, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt, t2max); break;
-    switch (oct) {
-        RTDS_OCT_CASE(4) RTDS_OCT_CASE(5) RTDS_OCT_CASE(6) RTDS_OCT_CASE(7)
-        default:
-            if (!ZNEG) switch (oct) { RTDS_OCT_CASE(0) RTDS_OCT_CASE(1) RTDS_OCT_CASE(2) RTDS_OCT_CASE(3) default: break; }
-            break;
-    }
-#undef RTDS_OCT_CASE
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Packet traversal: the PK = 4 consecutive samples of ONE pixel walk the tree together in one thread.
-// Why: the render kernel is bound by the L1 data pipe — every visit moves 56 bytes of node record into each lane's
-// registers (ncu: l1tex data-pipe wavefronts 65-75 % of peak, issue slots 61 %). The samples of a pixel differ by
-// sub-pixel jitter and walk nearly the same nodes, so one node load (and one stack push / pop) is shared by four
-// rays; the slab arithmetic is done per ray on the loaded record.
-// Why it returns the same hits: a sphere is a candidate of ray j iff its OWN leaf box passes the reference's slab
-// test for ray j (leaf boxes nest in every ancestor's box), a purely leaf-local criterion. The packet descends into a
-// child when ANY ray's conservative test accepts it, so each ray sees a superset of the leaves its own traversal
-// would open; at a leaf every ray runs its own narrow-accept / divide test and sphere test; pruning uses each ray's
-// own bound (a subtree is skipped only when no ray can still improve there), and equal-t candidates are resolved by
-// the order-independent key as before. Requires a common direction octant (checked by the caller) and sphere
-// leaves with their own boxes (leaf_box_prim).
-// ---------------------------------------------------------------------------------------------------
-constexpr int PK = 4;
-template <int OCT>
-__device__ __forceinline__ void traverse_packet(const BvhView& B, const float (&dx)[PK], const float (&dy)[PK], const float (&dz)[PK],
-                                                const float (&ix)[PK], const float (&iy)[PK], const float (&iz)[PK], float margin,
-                                                float (&tnear)[PK], int (&best_key)[PK], int (&best_leaf)[PK], Counters& cnt)
-{
-    const float zthr = margin * (9.5367431640625e-7f / 0.00278f);      // prune_margin = 0.00278 * corner distance
-    float tlim[PK];
-#pragma unroll
-    for (int j = 0; j < PK; ++j) { tlim[j] = tnear[j] + margin; tlim[j] = __fmaf_rn(fabsf(tlim[j]), WIDE2, tlim[j]); }
-    float tlim_max = fmaxf(fmaxf(tlim[0], tlim[1]), fmaxf(tlim[2], tlim[3]));
-    int2 stack[STACK_MAX];
-    int sp = 0;
-    int node = 0;
-    unsigned visits = 0, prim_tests = 0;
-    while (true) {
-        if (node >= 0) {
-            const float4* q = reinterpret_cast<const float4*>(B.nodes + node);
-            const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-            const int2 ch = __ldg(reinterpret_cast<const int2*>(q + 3));
-            ++visits;
-            // Boxes behind the camera. Every ray of the packet has dz < 0 (OCT bit 2). A sphere the reference's test can
-            // hit has float tca >= 0, so its true tca >= -delta (delta = the rounding error of the three-term dot product,
-            // <= 2^-21 * |c|), and the sphere contains the ray point at parameter tca, whose z = tca * dz <= delta: every
-            // box on its root path has zmin <= delta. zthr = 2^-20 * (distance to the root box's far corner) > delta.
-            // ONE compare per child for the whole packet replaces "exit distance >= -margin" per ray.
-            // The same holds on x and y with the exit plane the octant selects.
-            const bool frontL = q0.z <= zthr && ((OCT & 2) ? q0.y <= zthr : q1.x >= -zthr) && ((OCT & 1) ? q0.x <= zthr : q0.w >= -zthr);
-            const bool frontR = q2.x <= zthr && ((OCT & 2) ? q1.w <= zthr : q2.z >= -zthr) && ((OCT & 1) ? q1.z <= zthr : q2.y >= -zthr);
-            float kL[PK], kR[PK];                   // entry distance of the rays that accept the child, +inf otherwise
-#pragma unroll
-            for (int j = 0; j < PK; ++j) {
-                float tminL, tmaxL, tminR, tmaxR;
-                slab_interval<OCT>(q0.x * ix[j], q0.y * iy[j], q0.z * iz[j], q0.w * ix[j], q1.x * iy[j], q1.y * iz[j], tminL, tmaxL);
-                slab_interval<OCT>(q1.z * ix[j], q1.w * iy[j], q2.x * iz[j], q2.y * ix[j], q2.z * iy[j], q2.w * iz[j], tminR, tmaxR);
-                tmaxL = __fmaf_rn(fabsf(tmaxL), WIDE2, tmaxL);
-                tmaxR = __fmaf_rn(fabsf(tmaxR), WIDE2, tmaxR);
-                kL[j] = tminL <= fminf(tmaxL, tlim[j]) ? tminL : INFINITY;
-                kR[j] = tminR <= fminf(tmaxR, tlim[j]) ? tminR : INFINITY;
-            }
-            // packet entry distances: min over the rays that accept the child
-            const float tL = frontL ? fminf(fminf(fminf(kL[0], kL[1]), kL[2]), kL[3]) : INFINITY;
-            const float tR = frontR ? fminf(fminf(fminf(kR[0], kR[1]), kR[2]), kR[3]) : INFINITY;
-            const bool hitL = tL < INFINITY, hitR = tR < INFINITY;
-            if (hitL && hitR) {
-                const bool rfirst = tR < tL;
-                stack[sp] = make_int2(rfirst ? ch.x : ch.y, __float_as_int(rfirst ? tL : tR));
-                sp = min(sp + 1, STACK_MAX - 1);
-                node = rfirst ? ch.y : ch.x;
-                continue;
-            }
-            if (hitL | hitR) { node = hitL ? ch.x : ch.y; continue; }
-        } else {
-            const int leaf = ~node;
-            const float4 s = __ldg(B.leaf_sph + leaf);
-            const float bx0 = s.x - s.w, by0 = s.y - s.w, bz0 = s.z - s.w, bx1 = s.x + s.w, by1 = s.y + s.w, bz1 = s.z + s.w;
-            const float4 s2 = make_float4(s.x, s.y, s.z, s.w * s.w);
-            int key = leaf;
-            if (B.tie_by_objid) key = __ldg(B.prim_order + leaf);
-#pragma unroll
-            for (int j = 0; j < PK; ++j) {
-                float tmn, tmx;
-                slab_interval<OCT>(bx0 * ix[j], by0 * iy[j], bz0 * iz[j], bx1 * ix[j], by1 * iy[j], bz1 * iz[j], tmn, tmx);
-                bool pass = __fmaf_rn(fabsf(tmn), NARROW_EPS, tmn) <= __fmaf_rn(-fabsf(tmx), NARROW_EPS, tmx) &&
-                            fminf(fabsf(tmn), fabsf(tmx)) > 1e-30f;
-                // the sliver between "certainly accepted" and "rejected even by the widened interval" takes the divides
-                if (!pass && tmn <= __fmaf_rn(fabsf(tmx), WIDE2, tmx))
-                    pass = slab_test_cold(0.f, 0.f, 0.f, dx[j], dy[j], dz[j], bx0, by0, bz0, bx1, by1, bz1);
-                if (pass) {
-                    float t0, t1;
-                    ++prim_tests;
-                    if (sphere_test(0.f, 0.f, 0.f, dx[j], dy[j], dz[j], s2, t0, t1)) {
-                        candidate(t0, t1, key, leaf, tnear[j], best_key[j], best_leaf[j]);
-                        tlim[j] = tnear[j] + margin;
-                        tlim[j] = __fmaf_rn(fabsf(tlim[j]), WIDE2, tlim[j]);
-                    }
-                }
-            }
-            tlim_max = fmaxf(fmaxf(tlim[0], tlim[1]), fmaxf(tlim[2], tlim[3]));
-        }
-        // pop
-        bool found = false;
-        while (sp > 0) {
-            --sp;
-            const int2 e = stack[sp];
-            if (__int_as_float(e.y) > tlim_max) continue;
-            node = e.x;
-            found = true;
-            break;
-        }
-        if (!found) break;
-    }
-    cnt.node_visits += visits;
-    cnt.node_tests += 2 * PK * visits;
-    cnt.prim_tests += prim_tests;
-}
-
-// single-ray fallback of the packet kernel (mixed octants / degenerate directions), out of line
-static __device__ __noinline__ ColdHit trace_primary_cold(const BvhView* B, float dx, float dy, float dz)
-{
-    Counters c = {0, 0, 0, 0};
-    float tnear = INFINITY;
-    int key = 0, leaf = -1;
-    traverse_fast<true, false, true>(*B, 0.f, 0.f, 0.f, dx, dy, dz, tnear, key, leaf, c);
-    return ColdHit{tnear, key, leaf, c.node_tests, c.prim_tests, c.node_visits};
-}
-
-// NONE: main.cpp:376-386, spheres staged through shared memory by the whole block (all threads must call).
-constexpr int NONE_CHUNK = 1024;
-__device__ __forceinline__ void brute_force_block(int type, const float4* __restrict__ sph /*objId order {c,r}*/,
-                                                  const float4* __restrict__ tri, int n, bool active,
-                                                  float ox, float oy, float oz, float dx, float dy, float dz, float& tnear,
-                                                  int& best, Counters& cnt, float4* sh)
-{
-    const int chunk = type == 0 ? NONE_CHUNK : NONE_CHUNK / 3;
-    for (int base = 0; base < n; base += chunk) {
-        int m = min(chunk, n - base);
-        __syncthreads();
-        if (type == 0) {
-            for (int i = threadIdx.x; i < m; i += blockDim.x) {
-                float4 s = __ldg(sph + base + i);
-                sh[i] = make_float4(s.x, s.y, s.z, s.w * s.w);
-            }
-        } else {
-            for (int i = threadIdx.x; i < 3 * m; i += blockDim.x) sh[i] = __ldg(tri + 3 * (size_t)base + i);
-        }
-        __syncthreads();
-        if (active) {
-            for (int i = 0; i < m; ++i) {
-                float t0, t1;
-                bool h;
-                if (type == 0) h = sphere_test(ox, oy, oz, dx, dy, dz, sh[i], t0, t1);
-                else { float t; h = tri_test(ox, oy, oz, dx, dy, dz, sh[3 * i], sh[3 * i + 1], sh[3 * i + 2], t); t0 = t1 = t; }
-                if (h) {
-                    if (t0 < 0) t0 = t1;
-                    if (t0 < tnear) { tnear = t0; best = base + i; }
-                }
-            }
-            cnt.prim_tests += m;
-        }
-    }
-}
-
-// ===================================================================================================
-// kdtreeIntersect (accelerators.h:997-1086): any-hit, front-to-back, 64-entry todo stack
-// ===================================================================================================
-struct KdView {
-    const rtds_kd_node* nodes;
-    const int*          prim_idx;
-    const float4*       sph;       // objId-indexed {c, r} (kdtreeAllSceneObjects)
-    const float4*       tri;       // objId-indexed v0,v1,v2 (extension)
-    int                 prim_type;
-    float               bounds[6];
-};
-
-__device__ __forceinline__ bool kd_any_hit(const KdView& K, float ox, float oy, float oz, float dx, float dy, float dz, Counters& cnt)
-{
-    float tMin, tMax;
-    cnt.node_tests++;
-    if (!slab_test(ox, oy, oz, dx, dy, dz, K.bounds[0], K.bounds[1], K.bounds[2], K.bounds[3], K.bounds[4], K.bounds[5], tMin, tMax))
-        return false;
-    const float o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
-    const float inv[3] = {1 / dx, 1 / dy, 1 / dz};
-    int   todo_node[64];
-    float todo_tmin[64], todo_tmax[64];
-    int todoPos = 0;
-    int node = 0;
-    while (true) {
-        const rtds_kd_node nd = K.nodes[node];
-        cnt.node_visits++;
-        if ((nd.w1 & 3u) == 3u) {
-            const int np = (int)nd.w2;
-            if (np == 1) {
-                float t0, t1;
-                cnt.prim_tests++;
-                if (obj_test(K.prim_type, K.sph, K.tri, (int)nd.w0, ox, oy, oz, dx, dy, dz, t0, t1)) return true;
-            } else {
-                for (int i = 0; i < np; ++i) {
-                    int prim = __ldg(K.prim_idx + (int)nd.w0 + i);
-                    float t0, t1;
-                    cnt.prim_tests++;
-                    if (obj_test(K.prim_type, K.sph, K.tri, prim, ox, oy, oz, dx, dy, dz, t0, t1)) return true;
-                }
-            }
-            if (todoPos > 0) { --todoPos; node = todo_node[todoPos]; tMin = todo_tmin[todoPos]; tMax = todo_tmax[todoPos]; }
-            else break;
-        } else {
-            const int axis = (int)(nd.w1 & 3u);
-            const float split = __uint_as_float(nd.w0);
-            const float tPlane = (split - o[axis]) * inv[axis];
-            const bool belowFirst = (o[axis] < split) || (o[axis] == split && d[axis] <= 0);
-            const int below = node + 1, above = (int)(nd.w1 >> 2);
-            const int first = belowFirst ? below : above, second = belowFirst ? above : below;
-            if (tPlane > tMax || tPlane <= 0) node = first;
-            else if (tPlane < tMin) node = second;
-            else {
-                if (todoPos < 64) { todo_node[todoPos] = second; todo_tmin[todoPos] = tPlane; todo_tmax[todoPos] = tMax; ++todoPos; }
-                node = first;
-                tMax = tPlane;
-            }
-        }
-    }
-    return false;
-}
 
 // ===================================================================================================
 // shading: castRay's DIFFUSE_AND_GLOSSY branch (main.cpp:394-497)
@@ -1069,7 +181,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         } else if (MODE == 3) {
             if (active) hit_obj = kd_any_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, cnt) ? 1 : -1;
         } else if (active) {
-            if (MODE == 0) traverse_bvh<true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+            if (MODE == 0) traverse_bvh_exact(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
             else traverse_fast<true, false, true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
             if (best_leaf >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf);
         }
@@ -1121,7 +233,7 @@ static __device__ __noinline__ ShadowHit shadow_query_cold(const BvhView* B, flo
         traverse_fast<false, true>(*B, ox, oy, oz, dx, dy, dz, ts, bk, bl, c, dist2);
         occ = bl >= 0;
     } else {
-        traverse_bvh<true>(*B, ox, oy, oz, dx, dy, dz, ts, bk, bl, c);
+        traverse_bvh_exact(*B, ox, oy, oz, dx, dy, dz, ts, bk, bl, c);
         occ = bl >= 0 && ts * ts < dist2;
     }
     return ShadowHit{occ, c.node_tests, c.prim_tests, c.node_visits};
@@ -1337,7 +449,7 @@ __global__ void __launch_bounds__(STRIP_THREADS) render_strip_kernel(const __gri
             int best_key = 0, best_leaf = -1, hit_obj = -1;
             if (MODE == 3) hit_obj = kd_any_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, cnt) ? 1 : -1;
             else {
-                if (MODE == 0) traverse_bvh<true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+                if (MODE == 0) traverse_bvh_exact(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
                 else traverse_fast<true, false, true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
                 if (best_leaf >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf);
             }
@@ -1424,7 +536,7 @@ __device__ __forceinline__ void closest_hit(const RenderArgs& A, float ox, float
     } else {
         int best_key = 0, best_leaf = -1;
         float len2 = dx * dx + dy * dy + dz * dz;
-        if (MODE == 0 || !(fabsf(len2 - 1.0f) < 1e-3f)) traverse_bvh<true>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+        if (MODE == 0 || !(fabsf(len2 - 1.0f) < 1e-3f)) traverse_bvh_exact(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
         else traverse_fast<false>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
         if (best_leaf >= 0) { hit_obj = __ldg(A.bvh.prim_order + best_leaf); hit_leaf = best_leaf; }
     }
@@ -1595,7 +707,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const __grid_constant__ Trac
         // the ordered traversal's pruning bound assumes a unit direction (as every ray castRay makes has)
         float len2 = dx * dx + dy * dy + dz * dz;
         bool unit = fabsf(len2 - 1.0f) < 1e-3f;
-        if (A.exact || !unit) traverse_bvh<true>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+        if (A.exact || !unit) traverse_bvh_exact(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
         else traverse_fast<false>(A.bvh, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf, cnt);
         if (best_leaf >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf);
     }
