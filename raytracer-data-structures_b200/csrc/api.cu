@@ -144,6 +144,7 @@ int rtds_create(rtds_ctx** out, int device)
     RTDS_CUDA(cudaEventCreate(&c->ev0)); RTDS_CUDA(cudaEventCreate(&c->ev1));
     RTDS_CUDA(cudaEventCreate(&c->ev2)); RTDS_CUDA(cudaEventCreate(&c->ev3));
     RTDS_CUDA(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8));
+    RTDS_CUDA(cudaMallocHost(&c->h_counters, sizeof(unsigned long long) * 8));
     // main.cpp:775: Sphere light2(0, (0,3,30), 10, (1,1,1), 0, 0, emission (1,1,1))
     c->n_lights = 1;
     c->lights[0] = RtdsLight{{0.f, 3.f, 30.f}, 10.f, {1.f, 1.f, 1.f}};
@@ -165,6 +166,7 @@ int rtds_destroy(rtds_ctx* c)
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
     cudaStreamDestroy(c->stream);
     shared_frame_drop(c);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->copy_stream);
     cudaEventDestroy(c->ev_band);
     cudaStreamDestroy(c->jit_stream);

@@ -169,21 +169,25 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv d)
 __global__ void __launch_bounds__(MT_THREADS) mt_expand_dirs_kernel(const uint32_t* __restrict__ snap, int s0, float* __restrict__ dirs,
                                                                     unsigned long long first_sample, unsigned n_samples, int width,
                                                                     int spp, const FastDiv div_spp, const FastDiv div_width,
-                                                                    const RayGen G, const JitterOwner own)
+                                                                    const RayGen G, const JitterOwner own, int chunks_per_tile)
 {
     __shared__ __align__(16) uint32_t words[(MT_SNAP_EVERY + 1) * MT_N];      // slice 0 = the snapshot
     const int t = threadIdx.x;
-    const unsigned long long wlo = (unsigned long long)(s0 + blockIdx.x) * MT_SNAP_EVERY * MT_N;
+    // world == 1: block b = chunk s0 + b. world > 1: the grid covers only the rank's OWN scanline tiles
+    // (chunks_per_tile blocks per owned tile; owned tiles are never adjacent, so no chunk is generated twice)
+    unsigned long long chunk = (unsigned long long)s0 + blockIdx.x;
     if (own.world > 1) {
-        const unsigned long long whi = wlo + MT_SNAP_EVERY * MT_N - 1;
-        long long ylo = wlo > own.first_word ? (long long)((wlo - own.first_word) / own.row_words) : 0;
-        long long yhi = whi > own.first_word ? (long long)((whi - own.first_word) / own.row_words) : 0;
-        if (yhi >= own.height) yhi = own.height - 1;
-        bool mine = false;
-        for (long long tl = ylo / own.tile_rows; tl <= yhi / own.tile_rows; ++tl) mine |= (tl % own.world) == own.rank;
-        if (!mine) return;
+        const unsigned k = blockIdx.x / (unsigned)chunks_per_tile, c = blockIdx.x - k * (unsigned)chunks_per_tile;
+        const unsigned long long tile = (unsigned long long)own.rank + (unsigned long long)k * own.world;
+        const unsigned long long row0 = tile * own.tile_rows;
+        if (row0 >= (unsigned long long)own.height) return;
+        const unsigned long long row1 = min(row0 + own.tile_rows, (unsigned long long)own.height);
+        const unsigned long long w0 = own.first_word + row0 * own.row_words, w1 = own.first_word + row1 * own.row_words - 1;
+        chunk = w0 / (MT_SNAP_EVERY * MT_N) + c;
+        if (chunk > w1 / (MT_SNAP_EVERY * MT_N)) return;
     }
-    const uint32_t* src = snap + (size_t)(s0 + blockIdx.x) * MT_N;
+    const unsigned long long wlo = chunk * MT_SNAP_EVERY * MT_N;
+    const uint32_t* src = snap + (size_t)chunk * MT_N;
     for (int i = t; i < MT_N; i += MT_THREADS) words[i] = src[i];
     __syncthreads();
     for (int r = 0; r < MT_SNAP_EVERY; ++r) mt_regen(words + r * MT_N, words + (r + 1) * MT_N);

@@ -94,6 +94,7 @@ struct RenderArgs {
     ShadeParams   shade;
     uint8_t* out_rgb;            // local rows x width x 3, or the whole frame (height x width x 3) when out_global_rows
     int      out_global_rows;    // 1: out_rgb is a full frame indexed by the GLOBAL row (possibly another GPU's memory)
+    int      block_order;        // 0 quadrant-major, 1 row-major, 2 quadrant-major from the centre rows outwards (default)
     int      out_vec8;           // out_rgb is 8-byte aligned and width % 8 == 0: warps store whole 8-byte words
     int*     out_hit;            // optional, local rows x width
     float*   out_accum;          // optional, local rows x width x 3
@@ -137,13 +138,16 @@ __device__ __forceinline__ void store_warp_rgb(const RenderArgs& A, int px, int 
 // Block coordinates from a linear block id, image QUADRANT by quadrant (top-left, top-right, bottom-left,
 // bottom-right), row-major inside a quadrant. Primary rays of one quadrant share the direction octant, so the blocks
 // resident on an SM at any time run the same octant copy of the traversal loop (instruction-cache footprint).
-__device__ __forceinline__ void quadrant_block(int b, int nbx, int nby, int& bx, int& by)
+__device__ __forceinline__ void quadrant_block(int b, int nbx, int nby, int& bx, int& by, int order)
 {
+    if (order == 1) { bx = b % nbx; by = b / nbx; return; }       // plain row-major (experiment)
     const int hx = nbx >> 1, hy = nby >> 1, wx = nbx - hx;
     const int n0 = hx * hy, n1 = wx * hy, n2 = hx * (nby - hy);
-    if (b < n0) { bx = b % hx; by = b / hx; return; }
+    // order 2: inside the two upper quadrants the block rows run from the image centre UP, so every quadrant starts at
+    // the centre rows (experiment: heavy rows first)
+    if (b < n0) { bx = b % hx; by = b / hx; if (order == 2) by = hy - 1 - by; return; }
     b -= n0;
-    if (b < n1) { bx = hx + b % wx; by = b / wx; return; }
+    if (b < n1) { bx = hx + b % wx; by = b / wx; if (order == 2) by = hy - 1 - by; return; }
     b -= n1;
     if (b < n2) { bx = b % hx; by = hy + b / hx; return; }
     b -= n2;
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
     __shared__ float4 sh_sph[MODE == 2 ? NONE_CHUNK : 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int bx, by;
-    quadrant_block(blockIdx.x, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by);
+    quadrant_block(blockIdx.x, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by, A.block_order);
     const int px = bx * 16 + (warp & 1) * 8 + (lane & 7);
     const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool active = px < A.width && lrow < A.local_rows;
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
     unsigned shadow_rays = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int bx, by;
-    quadrant_block(blockIdx.x, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by);
+    quadrant_block(blockIdx.x, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by, A.block_order);
     const int px = bx * 16 + (warp & 1) * 8 + (lane & 7);
     const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool active = px < A.width && lrow < A.local_rows;
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(128) render_full_kernel(const __grid_constant_
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int bx, by;
-    quadrant_block(blockIdx.x, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by);
+    quadrant_block(blockIdx.x, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by, A.block_order);
     const int px = bx * 16 + (warp & 1) * 8 + (lane & 7);
     const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool active = px < A.width && lrow < A.local_rows;
@@ -838,9 +842,19 @@ static int dirs_prepare(rtds_ctx* ctx, uint64_t first_sample, int W, int H, int 
         f.shift = fl;
         return f;
     };
-    mt_expand_dirs_kernel<<<(unsigned)(s1 - s0 + 1), MT_THREADS, 0, stream>>>(ctx->d_mt_snap, (int)s0, ctx->d_dirs, first_sample,
-                                                                                 (unsigned)n_samples, W, spp, make_div((uint32_t)spp),
-                                                                                 make_div((uint32_t)W), G, own);
+    unsigned grid = (unsigned)(s1 - s0 + 1);
+    int chunks_per_tile = 0;
+    if (own.world > 1) {
+        // only the chunks that hold rows of this rank's tiles: (#owned tiles) x (max chunks a tile can span)
+        const uint64_t tile_words = (uint64_t)own.tile_rows * own.row_words;
+        chunks_per_tile = (int)((tile_words + words_per_snap - 1) / words_per_snap + 1);
+        const int n_tiles = (H + own.tile_rows - 1) / own.tile_rows;
+        const int owned = own.rank < n_tiles ? (n_tiles - own.rank + own.world - 1) / own.world : 0;
+        grid = (unsigned)owned * (unsigned)chunks_per_tile;
+    }
+    if (grid > 0)
+        mt_expand_dirs_kernel<<<grid, MT_THREADS, 0, stream>>>(ctx->d_mt_snap, (int)s0, ctx->d_dirs, first_sample, (unsigned)n_samples, W, spp,
+                                                                make_div((uint32_t)spp), make_div((uint32_t)W), G, own, chunks_per_tile);
     if (launches) *launches += 1;
     RTDS_CUDA(cudaGetLastError());
     ctx->dirs_key[0] = first_sample; ctx->dirs_key[1] = (uint64_t)W; ctx->dirs_key[2] = (uint64_t)H; ctx->dirs_key[3] = (uint64_t)spp;
@@ -933,6 +947,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     if (full && kdt) { rtds_set_error("render: the KDTREE path is any-hit and unshaded (main.cpp:362-372); shadows/materials need BVH, LBVH or NONE"); return RTDS_ERR_UNSUPPORTED; }
     A.out_rgb = d_rgb_rows; A.out_hit = d_hit; A.out_accum = d_accum; A.out_global_rows = global_rows ? 1 : 0;
     A.out_vec8 = (((uintptr_t)d_rgb_rows & 7) == 0 && W % 8 == 0) ? 1 : 0;
+    A.block_order = getenv("RTDS_BLOCK_ORDER") ? atoi(getenv("RTDS_BLOCK_ORDER")) : 2;
     A.counters = ctx->d_counters;
 
     cudaStream_t s = ctx->stream;
@@ -1030,8 +1045,8 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     if (global_rows && ctx->shared.frame) RTDS_TRY(rtds_shared_frame_signal_wait(ctx, ctx->shared.seq, &launches));
     RTDS_CUDA(cudaEventRecord(ctx->ev1, s));
     if (st) {
-        unsigned long long c[8];
-        RTDS_CUDA(cudaMemcpyAsync(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, s));
+        unsigned long long* c = ctx->h_counters;      // pinned: the read-back is on every frame's critical path
+        RTDS_CUDA(cudaMemcpyAsync(c, ctx->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
         RTDS_CUDA(cudaStreamSynchronize(s));
         memset(st, 0, sizeof *st);
         st->node_tests = c[0]; st->prim_tests = c[1]; st->node_visits = c[2];

@@ -156,6 +156,7 @@ struct rtds_ctx {
     int*     d_hit = nullptr;  size_t hit_bytes = 0;
     float*   d_accum = nullptr; size_t accum_bytes = 0;
     unsigned long long* d_counters = nullptr;  // render counters [8]
+    unsigned long long* h_counters = nullptr;  // pinned host copy [8]
     uint8_t* h_pinned = nullptr;     // pinned host staging for D2H of frames
     SharedFrame shared;
     size_t   pinned_bytes = 0;
