@@ -285,6 +285,63 @@ __device__ __forceinline__ void shade_diffuse_shadowed(const RenderArgs& A, floa
 #ifndef RTDS_PK_MINB
 #define RTDS_PK_MINB 6   // measured on B200: 4 blocks (112 regs) 1.40 ms, 5 (96) 1.245, 6 (80, 188 B spilled) 1.223, 8 (64) 1.238
 #endif
+// closest hits of four primary rays (origin 0, dz < 0): one packet when they share a direction octant and the ordered
+// traversal's preconditions hold, four single-ray traversals (out of line) otherwise
+__device__ __forceinline__ void trace_packet4(const RenderArgs& A, const float (&dx)[PK], const float (&dy)[PK], const float (&dz)[PK],
+                                              float margin, float (&tnear)[PK], int (&best_leaf)[PK], Counters& cnt)
+{
+    float ix[PK], iy[PK], iz[PK];
+    int best_key[PK];
+    bool ok = A.bvh.root_ref >= 0;
+    int oct0 = 0;
+#pragma unroll
+    for (int j = 0; j < PK; ++j) {
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix[j]) : "f"(dx[j]));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy[j]) : "f"(dy[j]));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz[j]) : "f"(dz[j]));
+        const float amin = fminf(fminf(fabsf(ix[j]), fabsf(iy[j])), fabsf(iz[j]));
+        const float amax = fmaxf(fmaxf(fabsf(ix[j]), fabsf(iy[j])), fabsf(iz[j]));
+        const int oct = (dx[j] < 0 ? 1 : 0) | (dy[j] < 0 ? 2 : 0) | 4;
+        if (j == 0) oct0 = oct;
+        ok = ok && amin > 1e-30f && amax < 1e30f && oct == oct0;
+        tnear[j] = INFINITY; best_key[j] = 0; best_leaf[j] = -1;
+    }
+    if (ok) {
+        switch (oct0) {
+            case 4: traverse_packet<4>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
+            case 5: traverse_packet<5>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
+            case 6: traverse_packet<6>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
+            default: traverse_packet<7>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < PK; ++j) {
+            const ColdHit h = trace_primary_cold(&A.bvh, dx[j], dy[j], dz[j]);
+            tnear[j] = h.tnear; best_leaf[j] = h.leaf;
+            cnt.node_tests += h.node_tests; cnt.prim_tests += h.prim_tests; cnt.node_visits += h.node_visits;
+        }
+    }
+}
+
+// colour of one primary ray of a packet (sphere leaves), main.cpp:394-497
+template <bool SHADOWS>
+__device__ __forceinline__ int shade_packet_ray(const RenderArgs& A, float dx, float dy, float dz, float tnear, int best_leaf, float& r,
+                                                float& g, float& b, Counters& cnt, unsigned& shadow_rays)
+{
+    int hit_obj = -1;
+    if (best_leaf >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf);
+    if (hit_obj < 0) { r = A.shade.bg[0]; g = A.shade.bg[1]; b = A.shade.bg[2]; }
+    else {
+        const float4 m = __ldg(A.mat + hit_obj);
+        const float hx = 0.f + dx * tnear, hy = 0.f + dy * tnear, hz = 0.f + dz * tnear;     // main.cpp:396
+        float nx, ny, nz;
+        raw_normal(0, A.bvh.leaf_sph, nullptr, (size_t)best_leaf, hx, hy, hz, nx, ny, nz);
+        if (SHADOWS) shade_diffuse_shadowed(A, dx, dy, dz, hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b, cnt, shadow_rays);
+        else shade_diffuse(A.shade, dx, dy, dz, hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b);
+    }
+    return hit_obj;
+}
+
 template <bool SHADOWS /*evaluate the shadow query (extension; the reference's trace_more is a stub)*/>
 __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const __grid_constant__ RenderArgs A)
 {
@@ -304,59 +361,20 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
         const size_t pix = (size_t)py * A.width + px;
         const float margin = prune_margin(A.bvh.root_box, 0.f, 0.f, 0.f);
         for (int k0 = 0; k0 < A.spp; k0 += PK) {
-            float dx[PK], dy[PK], dz[PK], ix[PK], iy[PK], iz[PK], tnear[PK];
-            int best_key[PK], best_leaf[PK];
-            bool ok = A.bvh.root_ref >= 0;
-            int oct0 = 0;
+            float dx[PK], dy[PK], dz[PK], tnear[PK];
+            int best_leaf[PK];
             // the packet's 4 directions are 48 contiguous, 16-byte aligned bytes (main.cpp:554-557, from mt_expand_dirs_kernel)
             const float4* dp = reinterpret_cast<const float4*>(A.dirs + 3 * (pix * A.spp + k0));
             const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
             dx[0] = d0.x; dy[0] = d0.y; dz[0] = d0.z; dx[1] = d0.w; dy[1] = d1.x; dz[1] = d1.y;
             dx[2] = d1.z; dy[2] = d1.w; dz[2] = d2.x; dx[3] = d2.y; dy[3] = d2.z; dz[3] = d2.w;
-#pragma unroll
-            for (int j = 0; j < PK; ++j) {
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix[j]) : "f"(dx[j]));
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy[j]) : "f"(dy[j]));
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz[j]) : "f"(dz[j]));
-                const float amin = fminf(fminf(fabsf(ix[j]), fabsf(iy[j])), fabsf(iz[j]));
-                const float amax = fmaxf(fmaxf(fabsf(ix[j]), fabsf(iy[j])), fabsf(iz[j]));
-                const int oct = (dx[j] < 0 ? 1 : 0) | (dy[j] < 0 ? 2 : 0) | 4;
-                if (j == 0) oct0 = oct;
-                ok = ok && amin > 1e-30f && amax < 1e30f && oct == oct0;
-                tnear[j] = INFINITY; best_key[j] = 0; best_leaf[j] = -1;
-            }
             cnt.rays += PK;
-            if (ok) {
-                switch (oct0) {
-                    case 4: traverse_packet<4>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
-                    case 5: traverse_packet<5>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
-                    case 6: traverse_packet<6>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
-                    default: traverse_packet<7>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < PK; ++j) {
-                    const ColdHit h = trace_primary_cold(&A.bvh, dx[j], dy[j], dz[j]);
-                    tnear[j] = h.tnear; best_leaf[j] = h.leaf;
-                    cnt.node_tests += h.node_tests; cnt.prim_tests += h.prim_tests; cnt.node_visits += h.node_visits;
-                }
-            }
+            trace_packet4(A, dx, dy, dz, margin, tnear, best_leaf, cnt);
 #pragma unroll
             for (int j = 0; j < PK; ++j) {
                 float r, g, b;
-                int hit_obj = -1;
-                if (best_leaf[j] >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf[j]);
-                if (hit_obj < 0) { r = A.shade.bg[0]; g = A.shade.bg[1]; b = A.shade.bg[2]; }
-                else {
-                    const float4 m = __ldg(A.mat + hit_obj);
-                    const float hx = 0.f + dx[j] * tnear[j], hy = 0.f + dy[j] * tnear[j], hz = 0.f + dz[j] * tnear[j];     // main.cpp:396
-                    float nx, ny, nz;
-                    raw_normal(0, A.bvh.leaf_sph, nullptr, (size_t)best_leaf[j], hx, hy, hz, nx, ny, nz);
-                    if (SHADOWS) shade_diffuse_shadowed(A, dx[j], dy[j], dz[j], hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b, cnt, shadow_rays);
-                    else shade_diffuse(A.shade, dx[j], dy[j], dz[j], hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b);
-                }
+                last_hit = shade_packet_ray<SHADOWS>(A, dx[j], dy[j], dz[j], tnear[j], best_leaf[j], r, g, b, cnt, shadow_rays);
                 acc_r += r; acc_g += g; acc_b += b;     // sample order, main.cpp:553-560
-                last_hit = hit_obj;
             }
         }
         const float fs = (float)(unsigned)A.spp;
@@ -1016,6 +1034,9 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             const unsigned lin = (unsigned)((W + 15) / 16) * (unsigned)((r1 - r0 + 7) / 8);     // quadrant-major linear grid
             // four samples of a pixel per thread as one packet (see traverse_packet); RTDS_PACKET=0 turns it off
             // (shadows without reflective / refractive materials stay on the packet kernel; the shadow rays are single)
+            // Only the samples of ONE pixel are packed: packets of neighbouring pixels (2 x 2 pixels x 1 sample, 2 pixels x 2
+            // samples) were measured slower than single rays - 0.208 vs 0.187 ms on the bunny at 1080p, 4.57 vs 2.19 ms on
+            // the 7 M-sphere scene - pixel-sized primitives make neighbouring pixels' paths diverge right below the top levels.
             bool packet = (!full || !ctx->has_materials) && !kdt && !brute && !p->exact && spp % PK == 0 && A.bvh.leaf_box_prim &&
                           A.shade.max_depth >= 1;
             if (const char* e = getenv("RTDS_PACKET")) packet = packet && atoi(e) != 0;

@@ -161,3 +161,30 @@ def test_packet_traversal_equals_single_ray_and_reference_order(gpu_ctx, oracle,
     assert np.array_equal(pk[1], hit_o) and pk[2].tobytes() == accum_o.tobytes() and np.array_equal(pk[0], rgb_o)
     assert pk[3]["primary_rays"] == W * H * spp == sr[3]["primary_rays"]
     assert pk[3]["node_visits"] < sr[3]["node_visits"]          # the point of the packet: fewer node loads
+
+
+def test_bench_frame_full_size_packet_equals_reference_traversal(gpu_ctx):
+    """BASELINE config 3 at FULL size (bunny x 30 clones = 1,078,411 spheres, 3840x2160, 4 spp, LBVH): the frame the bench
+    times (packet kernel, ordered + pruned) is byte-identical to the unpruned reference traversal (exact=1) and has the
+    same hit ids; ray count and rank partition properties hold."""
+    v = np.fromfile(T.GOLDEN + "/bunny_vertices.f32", np.float32).reshape(-1, 3)
+    sph, mat = rt.scene_from_vertices(v, 30)
+    assert sph.shape[0] == 1078411
+    gpu_ctx.set_spheres(sph, mat)
+    st = gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+    assert st["total_nodes"] == 2 * 1078411 - 1
+    W, H, spp = 3840, 2160, 4
+    fast, hit_f, _, st_f = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True)
+    exact, hit_e, _, st_e = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, exact=True)
+    assert st_f["primary_rays"] == st_e["primary_rays"] == W * H * spp
+    assert np.array_equal(hit_f, hit_e) and np.array_equal(fast, exact)
+    assert hashlib.sha256(fast.tobytes()).hexdigest() == hashlib.sha256(exact.tobytes()).hexdigest()
+    assert (hit_f >= 0).mean() > 0.3                      # bunny + ground cover a good part of the frame
+    # two ranks' tiles assemble to the same frame
+    frame = np.zeros_like(fast)
+    for rank in range(2):
+        part = np.zeros_like(fast)
+        gpu_ctx.render(rt.LBVH, W, H, spp, out=part, rank=rank, world=2)
+        rows = rt.owned_rows(H, 8, rank, 2)
+        frame[rows] = part[rows]
+    assert np.array_equal(frame, fast)
