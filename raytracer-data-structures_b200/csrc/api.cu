@@ -169,6 +169,9 @@ int rtds_destroy(rtds_ctx* c)
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->copy_stream);
     cudaEventDestroy(c->ev_band);
+    for (int k = 0; k < RTDS_MAX_BANDS; ++k) if (c->band_streams[k]) cudaStreamDestroy(c->band_streams[k]);
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    for (int k = 0; k < RTDS_MAX_BANDS; ++k) if (c->ev_bands[k]) cudaEventDestroy(c->ev_bands[k]);
     cudaStreamDestroy(c->jit_stream);
     cudaEventDestroy(c->ev_dirs);
     delete c;
@@ -429,10 +432,9 @@ int rtds_render(rtds_ctx* c, int acc, const rtds_render_params* p, uint8_t* rgb,
     cudaStream_t s = c->stream;
     if (world == 1) {
         // the frame comes back band by band while later bands are still rendering
-        std::function<int(int, int)> on_band = [&](int r0, int r1) -> int {
+        std::function<int(int, int, cudaEvent_t)> on_band = [&](int r0, int r1, cudaEvent_t done) -> int {
             const size_t off = (size_t)r0 * W, cnt = (size_t)(r1 - r0) * W;
-            RTDS_CUDA(cudaEventRecord(c->ev_band, s));
-            RTDS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_band, 0));
+            RTDS_CUDA(cudaStreamWaitEvent(c->copy_stream, done, 0));
             RTDS_CUDA(cudaMemcpyAsync(rgb + off * 3, c->d_frame + off * 3, cnt * 3, cudaMemcpyDeviceToHost, c->copy_stream));
             if (hit_obj) RTDS_CUDA(cudaMemcpyAsync(hit_obj + off, c->d_hit + off, cnt * sizeof(int), cudaMemcpyDeviceToHost, c->copy_stream));
             if (accum) RTDS_CUDA(cudaMemcpyAsync(accum + off * 3, c->d_accum + off * 3, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));

@@ -912,6 +912,18 @@ static RayGen make_raygen(const rtds_render_params* p)
     return G;
 }
 
+int rtds_ensure_band_streams(rtds_ctx* ctx)
+{
+    if (ctx->band_streams[0]) return RTDS_OK;
+    int least = 0, greatest = 0;
+    RTDS_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));     // numerically: greatest <= least
+    for (int k = 0; k < RTDS_MAX_BANDS; ++k)
+        RTDS_CUDA(cudaStreamCreateWithPriority(&ctx->band_streams[k], cudaStreamNonBlocking, std::min(least, greatest + k)));
+    RTDS_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+    for (int k = 0; k < RTDS_MAX_BANDS; ++k) RTDS_CUDA(cudaEventCreateWithFlags(&ctx->ev_bands[k], cudaEventDisableTiming));
+    return RTDS_OK;
+}
+
 int rtds_prefetch_dirs(rtds_ctx* ctx, const rtds_render_params* p)
 {
     const int W = p->width, H = p->height, spp = p->aa_samples;
@@ -932,7 +944,7 @@ int rtds_prefetch_dirs(rtds_ctx* ctx, const rtds_render_params* p)
 }
 
 int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_t* d_rgb_rows, int* d_hit, float* d_accum,
-                     rtds_render_stats* st, const std::function<int(int, int)>* on_band, bool global_rows)
+                     rtds_render_stats* st, const std::function<int(int, int, cudaEvent_t)>* on_band, bool global_rows)
 {
     const int W = p->width, H = p->height, spp = p->aa_samples;
     if (W <= 0 || H <= 0 || spp <= 0) { rtds_set_error("render: width/height/aa_samples must be positive"); return RTDS_ERR_INVALID; }
@@ -1017,19 +1029,32 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
         launches += 1;
         RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
         RTDS_CUDA(cudaGetLastError());
-        if (on_band) RTDS_TRY((*on_band)(0, A.local_rows));
+        if (on_band) { RTDS_CUDA(cudaEventRecord(ctx->ev_band, s)); RTDS_TRY((*on_band)(0, A.local_rows, ctx->ev_band)); }
     } else if (A.local_rows > 0) {
-        // Row bands: with a band callback (host-buffer render) each band's device->host copy is queued on the copy
-        // stream as soon as its kernel is queued, so the frame download overlaps the rendering of the next bands.
+        // Row bands (host-buffer renders only): the frame is rendered as n_bands kernels on streams of DESCENDING priority,
+        // all released at once. The block scheduler drains the higher-priority band first and fills its tail with the next
+        // band's blocks, so the bands finish one after the other without idle SMs, and each band's device->host copy
+        // (copy stream, behind the band's event) overlaps the rendering of the remaining bands: only the last band's
+        // copy is exposed. (Bands as consecutive kernels on ONE stream were measured slower: every band pays its tail.)
         const int total_rows = A.local_rows;
         int n_bands = 1;
-        if (on_band && total_rows >= 512) { const char* e = getenv("RTDS_BANDS"); n_bands = e ? std::max(1, atoi(e)) : 1; }
+        if (on_band && total_rows >= 512) {
+            const char* e = getenv("RTDS_BANDS");
+            n_bands = e ? std::max(1, std::min(RTDS_MAX_BANDS, atoi(e))) : 4;
+            RTDS_TRY(rtds_ensure_band_streams(ctx));
+        }
         const int band_rows = ((total_rows + n_bands - 1) / n_bands + 7) & ~7;
         RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
+        if (n_bands > 1) RTDS_CUDA(cudaEventRecord(ctx->ev_ready, s));       // directions + counters are ready behind this
         for (int r0 = 0; r0 < total_rows; r0 += band_rows) {
             const int r1 = std::min(total_rows, r0 + band_rows);
             A.lrow0 = r0;
             A.local_rows = r1;
+            cudaStream_t s = ctx->stream;                       // shadows the main stream inside the band loop
+            if (n_bands > 1) {
+                s = ctx->band_streams[std::min(r0 / band_rows, RTDS_MAX_BANDS - 1)];
+                RTDS_CUDA(cudaStreamWaitEvent(s, ctx->ev_ready, 0));
+            }
             const dim3 block(128);
             const unsigned lin = (unsigned)((W + 15) / 16) * (unsigned)((r1 - r0 + 7) / 8);     // quadrant-major linear grid
             // four samples of a pixel per thread as one packet (see traverse_packet); RTDS_PACKET=0 turns it off
@@ -1054,8 +1079,21 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             launches += 1;
             // the kernel-time event goes in BEFORE the band callback: a device->host copy into pageable memory blocks the
             // host, and an event recorded after it would time the copy as well
-            if (r1 == total_rows) RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
-            if (on_band) RTDS_TRY((*on_band)(r0, r1));
+            if (n_bands == 1) {
+                RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
+                if (on_band) { RTDS_CUDA(cudaEventRecord(ctx->ev_band, s)); RTDS_TRY((*on_band)(r0, r1, ctx->ev_band)); }
+            } else {
+                cudaEvent_t done = ctx->ev_bands[std::min(r0 / band_rows, RTDS_MAX_BANDS - 1)];
+                RTDS_CUDA(cudaEventRecord(done, s));
+                RTDS_CUDA(cudaStreamWaitEvent(ctx->stream, done, 0));       // the main stream joins every band
+            }
+        }
+        if (n_bands > 1) {
+            RTDS_CUDA(cudaEventRecord(ctx->ev3, ctx->stream));
+            // every band is queued: now the copies (a copy into pageable host memory blocks the host until it is done, so it
+            // must not sit between two launches)
+            for (int r0 = 0; r0 < total_rows; r0 += band_rows)
+                RTDS_TRY((*on_band)(r0, std::min(total_rows, r0 + band_rows), ctx->ev_bands[std::min(r0 / band_rows, RTDS_MAX_BANDS - 1)]));
         }
         A.local_rows = total_rows;
         RTDS_CUDA(cudaGetLastError());

@@ -97,11 +97,15 @@ struct SharedFrame {
     uint32_t  seq = 0;
 };
 
+#define RTDS_MAX_BANDS 8
+
 struct rtds_ctx {
     int          device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // device->host copies of finished row bands
     cudaEvent_t  ev_band = nullptr;
+    cudaStream_t band_streams[RTDS_MAX_BANDS] = {};   // descending priority, created on first use (host-buffer renders)
+    cudaEvent_t  ev_ready = nullptr, ev_bands[RTDS_MAX_BANDS] = {};
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     int          sm_count = 148;
 
@@ -203,13 +207,14 @@ void rtds_free_kd(DeviceKd& k);
 
 // render.cu — K10 render/trace, K11 MT19937 jitter stream
 int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_t* d_rgb_rows, int* d_hit,
-                     float* d_accum, rtds_render_stats* st, const std::function<int(int, int)>* on_band = nullptr,
+                     float* d_accum, rtds_render_stats* st, const std::function<int(int, int, cudaEvent_t)>* on_band = nullptr,
                      bool global_rows = false);
 int rtds_shared_frame_signal_wait(rtds_ctx* ctx, uint32_t seq, int* launches);
 int rtds_trace_impl(rtds_ctx* ctx, int acc, int exact, const float* h_o, const float* h_d, int nrays,
                     int* h_hit, float* h_t, rtds_render_stats* st);
 int rtds_jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, int* launches);
 int rtds_prefetch_dirs(rtds_ctx* ctx, const rtds_render_params* p);
+int rtds_ensure_band_streams(rtds_ctx* ctx);
 
 // ---------------------------------------------------------------------------------------------------
 // small device helpers
