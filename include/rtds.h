@@ -122,7 +122,11 @@ typedef struct {
     int      tile_rows;                     /* <=0 -> 8 */
     uint64_t jitter_offset;                 /* first sample's index in random_double()'s stream (main.cpp:503-508) */
     int      no_jitter_regen;               /* 1: reuse the jitter words generated by the previous call */
-    int      reserved[7];
+    int      kd_closest;                    /* KDTREE only. 0 = reference behaviour: any-hit, hit pixels black
+                                               (main.cpp:362-372). 1 = closest-hit KD traversal + castRay's shading
+                                               (extension: PBRT's KdTreeAccel::Intersect, whose any-hit sibling
+                                               accelerators.h:997-1086 is a port of) */
+    int      reserved[6];
 } rtds_render_params;
 
 typedef struct {
@@ -165,8 +169,10 @@ int rtds_export_kd(rtds_ctx* ctx, rtds_kd_node* nodes, int cap_nodes, int* n_nod
 int rtds_export_morton(rtds_ctx* ctx, uint64_t* keys, int* prim_ids, int cap, int* n);
 
 /* Parity probe: closest hit of arbitrary rays through the built structure (acc_type NONE: brute force).
- * hit_obj: objId or -1; t: tnear (INFINITY on miss). KDTREE is any-hit like the reference: hit_obj = 1/-1, t = 0.
+ * hit_obj: objId or -1; t: tnear (INFINITY on miss). KDTREE is any-hit like the reference: hit_obj = 1/-1, t = 0;
+ * with RTDS_TRACE_KD_CLOSEST or-ed into `exact` it is the closest-hit KD traversal (objId, tnear) of kd_closest.
  * exact as in rtds_render_params. Host pointers, o/d are nrays x 3. */
+#define RTDS_TRACE_KD_CLOSEST 2
 int rtds_trace(rtds_ctx* ctx, int acc_type, int exact, const float* o_xyz, const float* d_xyz, int nrays,
                int* hit_obj, float* t, rtds_render_stats* stats);
 

@@ -721,6 +721,77 @@ void orc_trace_p(const float* prims, int prim_type, int n, const LinearNode* nod
     if (candidates) *candidates = cand;
 }
 
+// Closest-hit KD traversal over an exported KdAccelNode[] (12-byte nodes, accelerators.h:715-742; leaf primitive lists
+// as kdtreePrimitiveIndices). EXTENSION, PARITY UNPINNED by the reference (its KD path is any-hit, accelerators.h:997-1086):
+// the walk is that function's (root slab test returning tMin/tMax accelerators.h:628-666, tPlane / belowFirst rule and
+// 64-entry todo stack :1033-1075) with the two differences PBRT's KdTreeAccel::Intersect has from its IntersectP:
+// a hit shortens the ray instead of returning, and the walk stops when `tnear < tMin` of the current cell. Candidates as
+// main.cpp:379-384, ties towards the smaller objId (= the NONE loop's first-candidate-wins).
+struct KdNode { uint32_t w0, w1, w2; };
+void orc_kd_closest(const float* prims, int prim_type, int n, const KdNode* nodes, const int* prim_idx, const float* bounds6,
+                    const float* o_all, const float* d_all, int nrays, int* hit, float* t, long long* prim_tests)
+{
+    Scene S{prims, nullptr, n, nullptr, nullptr, 0, 1};
+    S.prim_type = prim_type;
+    long long tests = 0;
+    for (int r = 0; r < nrays; ++r) {
+        const float* o = o_all + 3 * r; const float* d = d_all + 3 * r;
+        hit[r] = -1; t[r] = INFINITY;
+        // boundingBoxIntersection (tMin/tMax variant), accelerators.h:628-666
+        float tmin = (bounds6[0] - o[0]) / d[0], tmax = (bounds6[3] - o[0]) / d[0];
+        if (tmin > tmax) std::swap(tmin, tmax);
+        float tymin = (bounds6[1] - o[1]) / d[1], tymax = (bounds6[4] - o[1]) / d[1];
+        if (tymin > tymax) std::swap(tymin, tymax);
+        if ((tmin > tymax) || (tymin > tmax)) continue;
+        if (tymin > tmin) tmin = tymin;
+        if (tymax < tmax) tmax = tymax;
+        float tzmin = (bounds6[2] - o[2]) / d[2], tzmax = (bounds6[5] - o[2]) / d[2];
+        if (tzmin > tzmax) std::swap(tzmin, tzmax);
+        if ((tmin > tzmax) || (tzmin > tmax)) continue;
+        if (tzmin > tmin) tmin = tzmin;
+        if (tzmax < tmax) tmax = tzmax;
+        float tMin = tmin, tMax = tmax;
+        const float inv[3] = {1 / d[0], 1 / d[1], 1 / d[2]};
+        struct Todo { int node; float tMin, tMax; } todo[64];
+        int todoPos = 0, node = 0, best = -1;
+        float tnear = INFINITY;
+        while (true) {
+            if (tnear < tMin) break;
+            const KdNode& nd = nodes[node];
+            if ((nd.w1 & 3u) == 3u) {
+                const int np = (int)nd.w2;
+                for (int i = 0; i < np; ++i) {
+                    const int prim = np == 1 ? (int)nd.w0 : prim_idx[(int)nd.w0 + i];
+                    float t0 = INFINITY, t1 = INFINITY;
+                    ++tests;
+                    if (S.test(o, d, prim, t0, t1)) {
+                        if (t0 < 0) t0 = t1;
+                        if (t0 < tnear || (t0 == tnear && best >= 0 && prim < best)) { tnear = t0; best = prim; }
+                    }
+                }
+                if (todoPos > 0) { --todoPos; node = todo[todoPos].node; tMin = todo[todoPos].tMin; tMax = todo[todoPos].tMax; }
+                else break;
+            } else {
+                const int axis = (int)(nd.w1 & 3u);
+                float split; memcpy(&split, &nd.w0, 4);
+                const float tPlane = (split - o[axis]) * inv[axis];
+                const bool belowFirst = (o[axis] < split) || (o[axis] == split && d[axis] <= 0);
+                const int below = node + 1, above = (int)(nd.w1 >> 2);
+                const int first = belowFirst ? below : above, second = belowFirst ? above : below;
+                if (tPlane > tMax || tPlane <= 0) node = first;
+                else if (tPlane < tMin) node = second;
+                else {
+                    if (todoPos < 64) { todo[todoPos].node = second; todo[todoPos].tMin = tPlane; todo[todoPos].tMax = tMax; ++todoPos; }
+                    node = first;
+                    tMax = tPlane;
+                }
+            }
+        }
+        hit[r] = best; t[r] = tnear;
+    }
+    if (prim_tests) *prim_tests = tests;
+}
+
 void orc_jitter(double* out, int n, unsigned long long first)
 {
     MT g;

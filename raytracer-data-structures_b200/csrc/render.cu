@@ -156,7 +156,8 @@ __device__ __forceinline__ void quadrant_block(int b, int nbx, int nby, int& bx,
 
 // K10: one thread per pixel (warp = 8 x 4 pixels, block = 16 x 8), samples looped in order so the per-pixel float
 // accumulation matches main.cpp:553-560.
-template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE, 3 = KDTREE (any-hit, unshaded: main.cpp:362-372)*/>
+template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE, 3 = KDTREE (any-hit, unshaded: main.cpp:362-372),
+                     4 = KDTREE closest hit, shaded (extension: rtds_render_params.kd_closest)*/>
 __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ RenderArgs A)
 {
     __shared__ float4 sh_sph[MODE == 2 ? NONE_CHUNK : 1];
@@ -184,6 +185,8 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
             brute_force_block(A.prim_type, A.sph, A.tri, A.n, active, 0.f, 0.f, 0.f, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
         } else if (MODE == 3) {
             if (active) hit_obj = kd_any_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, cnt) ? 1 : -1;
+        } else if (MODE == 4) {
+            if (active) kd_closest_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, tnear, hit_obj, cnt);
         } else if (active) {
             if (MODE == 0) traverse_bvh_exact(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
             else traverse_fast<true, false, true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                 float4 m = __ldg(A.mat + hit_obj);
                 const float hx = 0.f + dx * tnear, hy = 0.f + dy * tnear, hz = 0.f + dz * tnear;     // main.cpp:396
                 float nx, ny, nz;
-                if (MODE == 2) raw_normal(A.prim_type, A.sph, A.tri, (size_t)hit_obj, hx, hy, hz, nx, ny, nz);
+                if (MODE == 2 || MODE == 4) raw_normal(A.prim_type, A.sph, A.tri, (size_t)hit_obj, hx, hy, hz, nx, ny, nz);
                 else raw_normal(A.bvh.prim_type, A.bvh.leaf_sph, A.bvh.leaf_tri, (size_t)best_leaf, hx, hy, hz, nx, ny, nz);
                 shade_diffuse(A.shade, dx, dy, dz, hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b);
             }
@@ -706,7 +709,7 @@ struct TraceArgs {
     int exact;
 };
 
-template <int MODE /*0 BVH, 2 NONE, 3 KDTREE*/>
+template <int MODE /*0 BVH, 2 NONE, 3 KDTREE any-hit, 4 KDTREE closest hit*/>
 __global__ void __launch_bounds__(128) trace_kernel(const __grid_constant__ TraceArgs A)
 {
     __shared__ float4 sh_sph[MODE == 2 ? NONE_CHUNK : 1];
@@ -725,6 +728,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const __grid_constant__ Trac
         brute_force_block(A.prim_type, A.sph, A.tri, A.n, active, ox, oy, oz, dx, dy, dz, tnear, hit_obj, cnt, sh_sph);
     } else if (MODE == 3) {
         if (active) { hit_obj = kd_any_hit(A.kd, ox, oy, oz, dx, dy, dz, cnt) ? 1 : -1; tnear = 0.f; }
+    } else if (MODE == 4) {
+        if (active) kd_closest_hit(A.kd, ox, oy, oz, dx, dy, dz, tnear, hit_obj, cnt);
     } else if (active) {
         // the ordered traversal's pruning bound assumes a unit direction (as every ray castRay makes has)
         float len2 = dx * dx + dy * dy + dz * dz;
@@ -974,7 +979,8 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.shade.max_depth = p->max_depth > 0 ? p->max_depth : 2;
     A.shade.shadows = p->shadows;
     const bool full = p->shadows || ctx->has_materials;
-    if (full && kdt) { rtds_set_error("render: the KDTREE path is any-hit and unshaded (main.cpp:362-372); shadows/materials need BVH, LBVH or NONE"); return RTDS_ERR_UNSUPPORTED; }
+    if (full && kdt) { rtds_set_error("render: the KDTREE path traces primary rays only (any-hit and unshaded as main.cpp:362-372, or kd_closest); shadows/materials need BVH, LBVH or NONE"); return RTDS_ERR_UNSUPPORTED; }
+    const bool kd_closest = kdt && p->kd_closest;
     A.out_rgb = d_rgb_rows; A.out_hit = d_hit; A.out_accum = d_accum; A.out_global_rows = global_rows ? 1 : 0;
     A.out_vec8 = (((uintptr_t)d_rgb_rows & 7) == 0 && W % 8 == 0) ? 1 : 0;
     A.block_order = getenv("RTDS_BLOCK_ORDER") ? atoi(getenv("RTDS_BLOCK_ORDER")) : 2;
@@ -989,7 +995,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     // expanded into HBM. MEASURED SLOWER on B200 (3.16 ms vs 1.81 + 0.24 ms on the bench frame): a block then covers
     // 312 consecutive pixels of one scanline instead of a 16x8 tile, and the L1 hit rate of the node stream — what
     // this issue-bound kernel lives on — collapses. Kept as a checked (parity-tested) negative result, off by default.
-    const bool strip = !brute && !full && !global_rows && spp <= 150 && getenv("RTDS_STRIP") && atoi(getenv("RTDS_STRIP")) == 1;
+    const bool strip = !brute && !full && !kd_closest && !global_rows && spp <= 150 && getenv("RTDS_STRIP") && atoi(getenv("RTDS_STRIP")) == 1;
     const uint64_t chunk_words = (uint64_t)MT_SNAP_EVERY * MT_N;
     const uint64_t c_first = first_word / chunk_words, c_last = (first_word + n_words - 1) / chunk_words;
     if (strip) {
@@ -1072,6 +1078,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
                 else render_full_kernel<1><<<lin, block, 0, s>>>(A);
             }
             else if (packet) render_packet_kernel<false><<<lin, block, 0, s>>>(A);
+            else if (kd_closest) render_kernel<4><<<lin, block, 0, s>>>(A);
             else if (kdt) render_kernel<3><<<lin, block, 0, s>>>(A);
             else if (brute) render_kernel<2><<<lin, block, 0, s>>>(A);
             else if (p->exact) render_kernel<0><<<lin, block, 0, s>>>(A);
@@ -1180,9 +1187,10 @@ int rtds_trace_impl(rtds_ctx* ctx, int acc, int exact, const float* h_o, const f
     A.o = d_o; A.d = d_d; A.nrays = nrays;
     if (!brute && !kdt) A.bvh = make_view(ctx->bvh); else A.bvh = BvhView();
     if (kdt) A.kd = make_kd_view(ctx); else A.kd = KdView();
-    A.sph = ctx->d_sph; A.tri = ctx->d_tris; A.prim_type = ctx->prim_type; A.n = ctx->n; A.hit = d_hit; A.t = d_t; A.counters = ctx->d_counters; A.exact = exact;
+    A.sph = ctx->d_sph; A.tri = ctx->d_tris; A.prim_type = ctx->prim_type; A.n = ctx->n; A.hit = d_hit; A.t = d_t; A.counters = ctx->d_counters; A.exact = exact & 1;
     RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
-    if (kdt) trace_kernel<3><<<(nrays + 127) / 128, 128, 0, s>>>(A);
+    if (kdt && (exact & RTDS_TRACE_KD_CLOSEST)) trace_kernel<4><<<(nrays + 127) / 128, 128, 0, s>>>(A);
+    else if (kdt) trace_kernel<3><<<(nrays + 127) / 128, 128, 0, s>>>(A);
     else if (brute) trace_kernel<2><<<(nrays + 127) / 128, 128, 0, s>>>(A);
     else trace_kernel<0><<<(nrays + 127) / 128, 128, 0, s>>>(A);
     RTDS_CUDA(cudaEventRecord(ctx->ev3, s));

@@ -621,4 +621,57 @@ __device__ __forceinline__ bool kd_any_hit(const KdView& K, float ox, float oy, 
     return false;
 }
 
+// Closest-hit KD traversal (extension, PARITY UNPINNED by the reference: its KD path is any-hit and unshaded,
+// main.cpp:362-372). Same walk as kdtreeIntersect above (accelerators.h:1012-1083: plane distance, belowFirst rule,
+// 64-entry todo stack) with the two changes PBRT's KdTreeAccel::Intersect makes to its IntersectP, which the reference
+// ported: a hit shortens the ray instead of ending the walk, and the walk ends when the current cell starts beyond the
+// nearest hit (`tnear < tMin`). Candidates are reduced like main.cpp:379-384 (t0 < 0 -> t1, strict <) with ties broken
+// towards the smaller objId = the NONE loop's "first candidate wins", so hit ids equal the brute-force path's except for
+// rays whose nearest hit lies (in float) outside every cell the primitive overlaps.
+__device__ __forceinline__ void kd_closest_hit(const KdView& K, float ox, float oy, float oz, float dx, float dy, float dz, float& tnear,
+                                               int& hit_obj, Counters& cnt)
+{
+    float tMin, tMax;
+    cnt.node_tests++;
+    if (!slab_test(ox, oy, oz, dx, dy, dz, K.bounds[0], K.bounds[1], K.bounds[2], K.bounds[3], K.bounds[4], K.bounds[5], tMin, tMax))
+        return;
+    const float o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
+    const float inv[3] = {1 / dx, 1 / dy, 1 / dz};
+    int   todo_node[64];
+    float todo_tmin[64], todo_tmax[64];
+    int todoPos = 0;
+    int node = 0;
+    int best_key = 0;
+    while (true) {
+        if (tnear < tMin) break;
+        const rtds_kd_node nd = K.nodes[node];
+        cnt.node_visits++;
+        if ((nd.w1 & 3u) == 3u) {
+            const int np = (int)nd.w2;
+            for (int i = 0; i < np; ++i) {
+                const int prim = np == 1 ? (int)nd.w0 : __ldg(K.prim_idx + (int)nd.w0 + i);
+                float t0, t1;
+                cnt.prim_tests++;
+                if (obj_test(K.prim_type, K.sph, K.tri, prim, ox, oy, oz, dx, dy, dz, t0, t1)) candidate(t0, t1, prim, prim, tnear, best_key, hit_obj);
+            }
+            if (todoPos > 0) { --todoPos; node = todo_node[todoPos]; tMin = todo_tmin[todoPos]; tMax = todo_tmax[todoPos]; }
+            else break;
+        } else {
+            const int axis = (int)(nd.w1 & 3u);
+            const float split = __uint_as_float(nd.w0);
+            const float tPlane = (split - o[axis]) * inv[axis];
+            const bool belowFirst = (o[axis] < split) || (o[axis] == split && d[axis] <= 0);
+            const int below = node + 1, above = (int)(nd.w1 >> 2);
+            const int first = belowFirst ? below : above, second = belowFirst ? above : below;
+            if (tPlane > tMax || tPlane <= 0) node = first;
+            else if (tPlane < tMin) node = second;
+            else {
+                if (todoPos < 64) { todo_node[todoPos] = second; todo_tmin[todoPos] = tPlane; todo_tmax[todoPos] = tMax; ++todoPos; }
+                node = first;
+                tMax = tPlane;
+            }
+        }
+    }
+}
+
 }  // namespace

@@ -10,6 +10,8 @@
 //   RTDS_LBVH_MODE        compat (default: what the reference's LBVH code does) | true (Morton/Karras LBVH)
 //   RTDS_PRIMS=triangles  extension: read `f` lines too and render the mesh's triangles (Moller-Trumbore) instead of one
 //                         sphere per vertex; vertices get the same transform as the sphere centres (main.cpp:680-682)
+//   RTDS_KD_CLOSEST=1     extension: KDTREE frames by closest-hit traversal + shading instead of the reference's any-hit
+//                         black/sky frame (main.cpp:362-372)
 //   RTDS_OUT              output file (default ./output.ppm)
 #include <chrono>
 #include <cstdlib>
@@ -179,6 +181,7 @@ int main(int, char**)
 				memset(&rp, 0, sizeof rp);
 				rp.width = settings.width; rp.height = settings.height; rp.aa_samples = settings.aa_samples;
 				rp.exact = exact; rp.rank = g; rp.world = n_gpus; rp.tile_rows = 8;
+				rp.kd_closest = env_int("RTDS_KD_CLOSEST", 0);   // 0 = the reference's any-hit, unshaded KD frame
 				if (shared) CHECK(rtds_render_shared(ctx[g], settings.dataStructure, &rp, 1u, &rs[g]));
 				else CHECK(rtds_render(ctx[g], settings.dataStructure, &rp, rgb.data(), nullptr, nullptr, &rs[g]));
 			});

@@ -130,6 +130,24 @@ class Oracle:
                              tie_by_objid, self._p(o), self._p(d), n, self._p(hit), self._p(t), C.byref(cand))
         return hit, t, cand.value
 
+    def kd_closest(self, prims, kd_nodes, kd_idx, bounds, o, d, prim_type=0):
+        """Closest-hit KD traversal (extension) over an exported KdAccelNode[]: (hit objId | -1, tnear, prim tests)."""
+        prims = np.ascontiguousarray(prims, np.float32)
+        kd_nodes = np.ascontiguousarray(kd_nodes)
+        kd_idx = np.ascontiguousarray(kd_idx, np.int32)
+        bounds = np.ascontiguousarray(bounds, np.float32)
+        o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+        n = d.shape[0]
+        if o.shape[0] == 1 and n > 1:
+            o = np.ascontiguousarray(np.broadcast_to(o, (n, 3)))
+        hit = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float32)
+        tests = C.c_longlong()
+        self.lib.orc_kd_closest(self._p(prims), prim_type, prims.shape[0], self._p(kd_nodes), self._p(kd_idx), self._p(bounds),
+                                self._p(o), self._p(d), n, self._p(hit), self._p(t), C.byref(tests))
+        return hit, t, tests.value
+
     def jitter(self, n, first=0):
         out = np.zeros(n, np.float64)
         self.lib.orc_jitter(self._p(out), n, C.c_ulonglong(first))
@@ -237,6 +255,19 @@ class Ref:
         out = np.zeros(n, np.float64)
         self.lib.ref_jitter(self._p(out), n)
         return out
+
+    def kd_dump(self):
+        """The reference's own KdAccelNode[] (nextFreeNode entries), kdtreePrimitiveIndices and tree bounds."""
+        n = self.lib.ref_kd_dump(None, 0, None, 0, None, None)
+        assert n > 0, "no KD-tree built in the reference harness"
+        nodes = np.zeros(n, rtds_b200.KD_NODE_DTYPE)
+        nidx = C.c_int()
+        self.lib.ref_kd_dump(None, 0, None, 0, C.byref(nidx), None)
+        idx = np.zeros(max(nidx.value, 1), np.int32)
+        bounds = np.zeros(6, np.float32)
+        self.lib.ref_kd_dump(self._p(nodes), n, self._p(idx), idx.size, C.byref(nidx), self._p(bounds))
+        return nodes, idx[:nidx.value], bounds
+
 
 
 def ref_dump_to_linear(recs):

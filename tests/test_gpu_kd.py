@@ -91,3 +91,90 @@ def test_kd_vs_compiled_reference_random_scenes(gpu_ctx):
         print("n=%d: reference %d counted nodes, GPU %d; any-hit differs on %d of %d rays" % (n, total_ref, st["total_nodes"], diff, m))
         assert diff <= m // 2000
         assert abs(st["total_nodes"] - total_ref) <= max(4, 0.02 * total_ref)
+
+
+# ---- closest-hit KD traversal + shading (extension, rtds_render_params.kd_closest / RTDS_TRACE_KD_CLOSEST) ---------------
+def test_kd_closest_hit_default_config(gpu_ctx, oracle):
+    """The default config through the KD-tree with closest-hit traversal: hit ids and tnear bit-exact against the CPU
+    restatement walking the SAME exported node array; against the reference's NONE hits (golden) only float-phantom
+    rays differ; where the hit is the BVH path's the shaded pixel is the BVH frame's (= the reference's output.ppm)."""
+    from test_oracle_vs_reference import phantom_none_hits
+    sph, mat = T.bunny_scene()
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.build(rt.KDTREE)
+    nodes, idx, bounds = gpu_ctx.export_kd()
+    W, H = 640, 480
+    rgb, hit, accum, rs = gpu_ctx.render(rt.KDTREE, W, H, 1, want_hit=True, want_accum=True, kd_closest=1)
+    rc, bn, bo, _ = oracle.build_bvh(sph)
+    rgb_b, hit_b, acc_b, dirs = oracle.render_rows(sph, mat, bn, bo, W, H, 1, want_dirs=True, want_accum=True)
+    d = dirs.reshape(-1, 3)
+    hit_o, t_o, tests_o = oracle.kd_closest(sph, nodes, idx, bounds, np.zeros((1, 3), np.float32), d)
+    assert np.array_equal(hit.reshape(-1), hit_o)
+    assert rs["prim_tests"] == tests_o                       # the same walk: identical number of primitive tests
+    h_t, t_t, _ = gpu_ctx.trace(rt.KDTREE, np.zeros((1, 3), np.float32), d, kd_closest=True)
+    assert np.array_equal(h_t, hit_o) and t_t.tobytes() == t_o.tobytes()
+    gold = np.load(T.GOLDEN + "/bunny_hits_640x480.npz")
+    where = np.nonzero(hit_o != gold["hit_none"].reshape(-1))[0]
+    print("KD closest hit: %d of %d pixels differ from the reference's NONE hits (all float-phantom hits of NONE); "
+          "%.2f prim tests/ray, kernel %.3f ms" % (len(where), W * H, tests_o / (W * H), rs["ms_kernel"]))
+    assert len(where) <= 31 and phantom_none_hits(sph, d, gold["hit_none"], where).all()
+    same = hit == hit_b
+    assert same.mean() > 0.999
+    assert np.array_equal(rgb[same], rgb_b[same]) and accum[same].tobytes() == acc_b[same].tobytes()
+    # any-hit mode is unchanged by the flag's existence
+    rgb_a, _, _, _ = gpu_ctx.render(rt.KDTREE, W, H, 1)
+    assert T.ppm_md5(rgb_a) == G["kd"]["ppm_md5"]
+
+
+def test_kd_closest_hit_random_rays_and_multisample(gpu_ctx, oracle):
+    rng = np.random.default_rng(77)
+    for n, seed in ((300, 5), (20000, 6)):
+        sph, mat = T.synthetic_scene(n, seed)
+        gpu_ctx.set_spheres(sph, mat)
+        gpu_ctx.build(rt.KDTREE)
+        nodes, idx, bounds = gpu_ctx.export_kd()
+        m = 30000
+        tgt = sph[rng.integers(0, n, m), :3] + rng.normal(size=(m, 3)).astype(np.float32) * np.float32(0.06)
+        o = np.zeros((m, 3), np.float32)
+        o[m // 2:] = rng.normal(size=(m - m // 2, 3)).astype(np.float32) * np.float32(15)     # origins inside and outside the tree bounds
+        d = tgt - o
+        d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        h, t, st = gpu_ctx.trace(rt.KDTREE, o, d, kd_closest=True)
+        h_o, t_o, tests_o = oracle.kd_closest(sph, nodes, idx, bounds, o, d)
+        assert np.array_equal(h, h_o) and t.tobytes() == t_o.tobytes() and st["prim_tests"] == tests_o
+        h_n, t_n, _ = gpu_ctx.trace(rt.NONE, o, d)
+        diff = int(np.count_nonzero(h != h_n))
+        print("n=%d: closest-hit KD differs from brute force on %d of %d rays" % (n, diff, m))
+        assert diff <= m // 1000
+        agree = h == h_n
+        assert t[agree].tobytes() == t_n[agree].tobytes()
+    # 4 spp frame: float sums equal the LBVH path's wherever all samples hit the same primitives (checked through the frames)
+    W, H = 320, 240
+    rgb_k, hit_k, acc_k, _ = gpu_ctx.render(rt.KDTREE, W, H, 4, want_hit=True, want_accum=True, kd_closest=1)
+    gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+    rgb_l, hit_l, acc_l, _ = gpu_ctx.render(rt.LBVH, W, H, 4, want_hit=True, want_accum=True)
+    differ = np.count_nonzero(np.any(acc_k != acc_l, axis=-1))
+    print("4 spp: %d of %d pixels differ between the closest-hit KD frame and the LBVH frame" % (differ, W * H))
+    assert differ <= W * H // 500
+    assert np.abs(rgb_k.astype(int) - rgb_l.astype(int)).max(axis=-1).reshape(-1)[np.all(acc_k == acc_l, axis=-1).reshape(-1)].max() == 0
+
+
+def test_kd_closest_hit_triangles(gpu_ctx, oracle):
+    tris, mat = T.triangle_scene(20000, 55, ground=False)
+    c = tris.reshape(-1, 3, 3).mean(1, keepdims=True)
+    tris = np.ascontiguousarray((c + (tris.reshape(-1, 3, 3) - c) * np.float32(0.25)).reshape(-1, 9), np.float32)
+    gpu_ctx.set_triangles(tris, mat)
+    gpu_ctx.build(rt.KDTREE)
+    nodes, idx, bounds = gpu_ctx.export_kd()
+    rng = np.random.default_rng(56)
+    m = 20000
+    tgt = tris.reshape(-1, 3, 3).mean(1)[rng.integers(0, tris.shape[0], m)] + rng.normal(size=(m, 3)).astype(np.float32) * np.float32(0.1)
+    d = (tgt / np.linalg.norm(tgt, axis=1, keepdims=True)).astype(np.float32)
+    o = np.zeros((1, 3), np.float32)
+    h, t, _ = gpu_ctx.trace(rt.KDTREE, o, d, kd_closest=True)
+    h_o, t_o, _ = oracle.kd_closest(tris, nodes, idx, bounds, o, d, prim_type=1)
+    assert np.array_equal(h, h_o) and t.tobytes() == t_o.tobytes()
+    h_n, t_n, _ = gpu_ctx.trace(rt.NONE, o, d)
+    assert np.count_nonzero(h != h_n) <= m // 1000 and (h >= 0).mean() > 0.2
+    with pytest.raises(rt.RtdsError):                      # primary rays only on the KD path
+        gpu_ctx.render(rt.KDTREE, 64, 48, 1, kd_closest=1, shadows=1)

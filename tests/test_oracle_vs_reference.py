@@ -65,3 +65,43 @@ def test_port_castray_materials_equal_reference(ref, oracle):
     assert np.count_nonzero(acc_r != acc_o) < 0.001 * acc_r.size
     assert np.abs(rgb_r.astype(int) - rgb_o.astype(int)).max() <= 1
     ref.lib.ref_set_lights(np.asarray([[0, 3, 30, 10, 1, 1, 1]], np.float32).ctypes.data_as(T.C.c_void_p), 1)
+
+
+def phantom_none_hits(sph, d, hit_none, where):
+    """For the rays `where` (flat indices): True where the NONE loop's hit is a float phantom — in float64 the ray
+    passes OUTSIDE the sphere (raySphereIntersect's d2 = l.l - tca*tca cancels catastrophically at |l| ~ 60:
+    accelerators.h:85-87), so no spatial subdivision can hold the 'hit point' in a cell the sphere overlaps."""
+    out = np.zeros(len(where), bool)
+    for k, r in enumerate(where):
+        s = sph[hit_none.reshape(-1)[r]].astype(np.float64)
+        dv = d[r].astype(np.float64)
+        dv /= np.linalg.norm(dv)
+        tca = s[:3] @ dv
+        out[k] = np.sqrt(max(0.0, s[:3] @ s[:3] - tca * tca)) > s[3]
+    return out
+
+
+def test_port_kd_closest_hit_on_the_reference_kd_tree(ref, oracle):
+    """Closest-hit KD traversal (extension; the reference's KD path is any-hit): the restatement walks the reference's
+    OWN KdAccelNode[] for the default config's 307,200 primary rays and must find the NONE loop's hits (golden, from
+    the unmodified reference) — except where NONE's hit is a float phantom — and agree with kdtreeIntersect's any-hit mask."""
+    sph, mat = T.bunny_scene()
+    ref.scene_from_spheres(sph, mat)
+    ref.build(rt.KDTREE)
+    nodes, idx, bounds = ref.kd_dump()
+    W, H = 640, 480
+    rc, bn, bo, _ = oracle.build_bvh(sph)
+    _, _, _, dirs = oracle.render_rows(sph, mat, bn, bo, W, H, 1, want_dirs=True)      # main.cpp:554-557's directions
+    d = dirs.reshape(-1, 3)
+    gold = np.load(T.GOLDEN + "/bunny_hits_640x480.npz")
+    hit, t, tests = oracle.kd_closest(sph, nodes, idx, bounds, np.zeros((1, 3), np.float32), d)
+    where = np.nonzero(hit != gold["hit_none"].reshape(-1))[0]
+    print("KD closest hit on the reference's tree: %d of %d pixels differ from the NONE golden hits, %.2f prim tests/ray" %
+          (len(where), W * H, tests / (W * H)))
+    assert len(where) <= 31                                           # 0.01 %
+    assert phantom_none_hits(sph, d, gold["hit_none"], where).all()    # every one of them: the true ray misses NONE's sphere
+    mask = np.unpackbits(np.load(T.GOLDEN + "/bunny_kd_mask_640x480.npy")).astype(bool).reshape(-1)
+    assert np.array_equal(hit >= 0, mask)                             # same hit/miss as the reference's kdtreeIntersect
+    same = hit == gold["hit_none"].reshape(-1)
+    t_none = oracle.trace(sph, None, None, np.zeros((1, 3), np.float32), d[same][::97])[1]
+    assert t[same][::97].tobytes() == t_none.tobytes()                # and the same tnear bits
