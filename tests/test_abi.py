@@ -47,3 +47,28 @@ def test_rows_for_rank_partition():
             assert sorted(sum((r.tolist() for r in rows), [])) == list(range(h))
             for r in range(world):
                 assert rt.rows_for_rank(h, 8, r, world) == rows[r].size
+
+
+def test_ctypes_layouts_equal_the_headers(tmp_path):
+    """sizeof / offsetof of every struct field as the C compiler lays include/rtds.h out == the ctypes mirror."""
+    import subprocess
+    structs = {"rtds_build_params": rt.BuildParams, "rtds_build_stats": rt.BuildStats, "rtds_render_params": rt.RenderParams,
+               "rtds_render_stats": rt.RenderStats}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "rtds.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for f, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ['printf("rtds_linear_bvh_node %zu\\n", sizeof(rtds_linear_bvh_node));', 'printf("rtds_kd_node %zu\\n", sizeof(rtds_kd_node));',
+              'printf("RTDS_TRACE_KD_CLOSEST %d\\n", RTDS_TRACE_KD_CLOSEST);', "return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(T.ROOT, "include"), "-o", str(exe), str(src)])   # the header is plain C
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for f, _ in cls._fields_:
+            assert int(got[f"{cname}.{f}"]) == getattr(cls, f).offset, f"{cname}.{f}"
+    assert int(got["rtds_linear_bvh_node"]) == 32 and int(got["rtds_kd_node"]) == 12
+    assert int(got["RTDS_TRACE_KD_CLOSEST"]) == rt.TRACE_KD_CLOSEST
