@@ -2,6 +2,7 @@
 // There is no CPU path in this library: every entry point that computes anything launches CUDA kernels,
 // and rtds_create fails when no sm_100 device is usable.
 #include "rtds_internal.cuh"
+#include <chrono>
 #include <stdarg.h>
 #include <string.h>
 
@@ -253,11 +254,23 @@ int rtds_frame(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n, in
     // the frame's ray directions depend on the render parameters only: generate them on their own stream while the
     // scene uploads and the structure is built
     RTDS_CUDA(cudaSetDevice(c->device));
+    // RTDS_TRACE_FRAME=1: host-clock timeline of the call's stages on stderr (profiling aid)
+    static const bool trace = getenv("RTDS_TRACE_FRAME") && atoi(getenv("RTDS_TRACE_FRAME")) != 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
     RTDS_TRY(rtds_prefetch_dirs(c, rp));
+    const double t_dirs = us();
     RTDS_TRY(upload_spheres(c, cxyz_r, rgb_mat, n, true));
+    const double t_up = us();
     RTDS_TRY(rtds_build(c, acc, bp, bst));
+    const double t_build = us();
     RTDS_TRY(rtds_finish_materials(c));
-    return rtds_render(c, acc, rp, rgb, nullptr, nullptr, rst);
+    const double t_mat = us();
+    const int rc = rtds_render(c, acc, rp, rgb, nullptr, nullptr, rst);
+    if (trace)
+        fprintf(stderr, "[rtds_frame] dirs enqueued %.0f us | spheres up %.0f | build done %.0f | materials done %.0f | render+download done %.0f\n",
+                t_dirs, t_up, t_build, t_mat, us());
+    return rc;
 }
 
 int rtds_set_triangles(rtds_ctx* c, const float* v0v1v2, const float* rgb_mat, int n)

@@ -49,6 +49,8 @@ def main():
             print("skipped", acc, kw, e)
             continue
         ctx.export_bvh()
+        if kw.get("mode") == rt.MODE_TRUE:
+            ctx.export_morton()
         for exact in (True, False):
             ctx.render(acc, W, H, 1, exact=exact, want_hit=True, want_accum=True)
             ctx.trace(acc, rays_o, rays_d, exact=exact)
@@ -57,7 +59,6 @@ def main():
         ctx.render(acc, W + 5, H + 3, 3, shadows=1)   # ragged frame, single-ray kernels
         ctx.render(acc, W, H, 2, rank=1, world=3)     # a rank's interleaved tiles
         done.append((acc, kw))
-    ctx.export_morton()
     os.environ["RTDS_STRIP"] = "1"
     ctx.render(rt.LBVH, W, H, 2)                      # fused strip kernel (opt-in)
     del os.environ["RTDS_STRIP"]
