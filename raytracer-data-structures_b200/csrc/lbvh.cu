@@ -6,6 +6,7 @@
 //   K5 atomic bottom-up AABB refit       (node bounds = union of leaf boxBoundries, accelerators.h:257-260)
 // plus the pre-order flattening into the reference's LinearBVHNode layout (accelerators.h:231-240).
 #include "rtds_internal.cuh"
+#include <chrono>
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
@@ -382,6 +383,9 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
     const int n = ctx->n;
     DeviceBvh& b = ctx->bvh;
     int launches = 0;
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto tr_us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tr0).count(); };
+    double tr[4] = {0, 0, 0, 0};
     // scratch: bounds[12] | counters[n] | max_depth | keys, keys_tmp | vals, vals_tmp
     size_t off_bounds = 0;
     size_t off_counters = 256;
@@ -413,7 +417,9 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
     ctx->n_keys = n;
 
     cudaStream_t s = ctx->stream;
+    tr[0] = tr_us();
     RTDS_CUDA(cudaEventRecord(ctx->ev0, s));
+    if (g_rtds_trace_ev[0]) RTDS_CUDA(cudaEventRecord(g_rtds_trace_ev[4], s));
     const int T = 256;
     const int G = (n + T - 1) / T;
     bounds_init_kernel<<<1, 32, 0, s>>>(d_bounds);
@@ -421,11 +427,12 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
     bounds_kernel<<<min(G, ctx->sm_count * 8), T, 0, s>>>(pv, n, d_bounds);
     morton_kernel<K><<<G, T, 0, s>>>(pv, n, d_bounds, p ? p->morton_ref_norm : 0, d_keys, d_vals);
     launches += 3;
+    tr[1] = tr_us();
     RTDS_TRY((sizeof(K) == 4)
                  ? rtds_onesweep_sort_u32(ctx, (uint32_t*)d_keys, d_vals, (uint32_t*)d_keys_tmp, d_vals_tmp, n, key_bits, &launches)
                  : rtds_onesweep_sort_u64(ctx, (uint64_t*)d_keys, d_vals, (uint64_t*)d_keys_tmp, d_vals_tmp, n, key_bits, &launches));
-    RTDS_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned) * (size_t)n + 0, s));
-    RTDS_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(int), s));
+    RTDS_TRY(rtds_zero_async(d_counters, sizeof(unsigned) * (size_t)n, s, &launches));     // kernels, not cudaMemsetAsync: see rtds_zero_async
+    RTDS_TRY(rtds_zero_async(d_depth, sizeof(int), s, &launches));
     float* d_root_box = (float*)(d_bounds + 16);
     if (n > 1) {
         karras_kernel<K><<<(n - 1 + T - 1) / T, T, 0, s>>>(d_keys, n, b.nodes, b.leaf_parent);
@@ -437,11 +444,20 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
     widen_keys_kernel<K><<<G, T, 0, s>>>(d_keys, n, ctx->d_keys_sorted);
     launches += 2;
     RTDS_CUDA(cudaEventRecord(ctx->ev1, s));
+    if (g_rtds_trace_ev[0]) RTDS_CUDA(cudaEventRecord(g_rtds_trace_ev[5], s));
     RTDS_CUDA(cudaGetLastError());
-    RTDS_CUDA(cudaMemcpyAsync(b.root_box, d_root_box, sizeof(float) * 6, cudaMemcpyDeviceToHost, s));
-    int depth = 0;
-    RTDS_CUDA(cudaMemcpyAsync(&depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, s));
+    // root box + depth come back into PINNED memory: a copy into pageable memory is staged by the driver, ~15 us each
+    // on the rtds_frame critical path
+    float* h_box = reinterpret_cast<float*>(ctx->h_counters + 9);
+    int* h_depth = reinterpret_cast<int*>(ctx->h_counters + 12);
+    RTDS_CUDA(cudaMemcpyAsync(h_box, d_root_box, sizeof(float) * 6, cudaMemcpyDeviceToHost, s));
+    tr[2] = tr_us();
+    RTDS_CUDA(cudaMemcpyAsync(h_depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, s));
     RTDS_CUDA(cudaStreamSynchronize(s));
+    tr[3] = tr_us();
+    for (int i = 0; i < 6; ++i) b.root_box[i] = h_box[i];
+    const int depth = *h_depth;
+    if (g_rtds_trace_ev[0]) fprintf(stderr, "[lbvh build host] allocs done %.0f us | 3 launches in %.0f | all enqueued %.0f | synced %.0f\n", tr[0], tr[1], tr[2], tr[3]);
     b.n_prims = n;
     b.n_internal = n - 1;
     b.root_ref = n > 1 ? 0 : ~0;

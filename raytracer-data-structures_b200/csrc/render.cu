@@ -925,7 +925,9 @@ int rtds_ensure_band_streams(rtds_ctx* ctx)
     for (int k = 0; k < RTDS_MAX_BANDS; ++k)
         RTDS_CUDA(cudaStreamCreateWithPriority(&ctx->band_streams[k], cudaStreamNonBlocking, std::min(least, greatest + k)));
     RTDS_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
-    for (int k = 0; k < RTDS_MAX_BANDS; ++k) RTDS_CUDA(cudaEventCreateWithFlags(&ctx->ev_bands[k], cudaEventDisableTiming));
+    // timing only when RTDS_TRACE_FRAME reads them (measured: timing-enabled band events cost the frame ~0.1 ms)
+    const bool tr = getenv("RTDS_TRACE_FRAME") && atoi(getenv("RTDS_TRACE_FRAME")) > 1;
+    for (int k = 0; k < RTDS_MAX_BANDS; ++k) RTDS_CUDA(cudaEventCreateWithFlags(&ctx->ev_bands[k], tr ? cudaEventDefault : cudaEventDisableTiming));
     return RTDS_OK;
 }
 
@@ -941,7 +943,9 @@ int rtds_prefetch_dirs(rtds_ctx* ctx, const rtds_render_params* p)
     const RayGen G = make_raygen(p);
     JitterOwner own{4ull * p->jitter_offset, 4ull * (unsigned long long)W * spp, tile_rows, rank, world, H};
     int launches = 0;
+    if (g_rtds_trace_ev[0]) RTDS_CUDA(cudaEventRecord(g_rtds_trace_ev[1], ctx->jit_stream));
     RTDS_TRY(dirs_prepare(ctx, p->jitter_offset, W, H, spp, G, own, &launches, ctx->jit_stream));
+    if (g_rtds_trace_ev[0]) RTDS_CUDA(cudaEventRecord(g_rtds_trace_ev[2], ctx->jit_stream));
     RTDS_CUDA(cudaEventRecord(ctx->ev_dirs, ctx->jit_stream));
     ctx->dirs_pending = true;
     ctx->dirs_pending_launches = launches;
@@ -1049,16 +1053,35 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             n_bands = e ? std::max(1, std::min(RTDS_MAX_BANDS, atoi(e))) : 4;
             RTDS_TRY(rtds_ensure_band_streams(ctx));
         }
-        const int band_rows = ((total_rows + n_bands - 1) / n_bands + 7) & ~7;
+        // Band boundaries (multiples of 8 rows): equal shares by default. RTDS_BAND_RATIO = r (percent) makes every band r %
+        // of the one before it. MEASURED (RTDS_TRACE_FRAME=2, bench frame): shrinking bands do not shorten the ~140 us of
+        // copies that trail the last kernel (4 equal bands 2.16 ms, 5 bands at 60 % 2.20-2.25, 6 at 70 % 2.16): a band only
+        // completes when its longest-running blocks (image centre) are done, the lower-priority bands fill in meanwhile, and
+        // the last two or three bands all end within ~50 us of each other whatever their size.
+        int band_start[RTDS_MAX_BANDS + 1];
+        {
+            const int pct = getenv("RTDS_BAND_RATIO") ? std::max(10, std::min(100, atoi(getenv("RTDS_BAND_RATIO")))) : 100;
+            double w[RTDS_MAX_BANDS], sum = 0;
+            for (int k = 0; k < n_bands; ++k) { w[k] = k ? w[k - 1] * pct / 100.0 : 1.0; sum += w[k]; }
+            band_start[0] = 0;
+            double acc = 0;
+            for (int k = 1; k < n_bands; ++k) {
+                acc += w[k - 1];
+                const int r = ((int)(total_rows * (acc / sum)) + 7) & ~7;
+                band_start[k] = std::min(total_rows, std::max(band_start[k - 1], r));
+            }
+            band_start[n_bands] = total_rows;
+        }
         RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
         if (n_bands > 1) RTDS_CUDA(cudaEventRecord(ctx->ev_ready, s));       // directions + counters are ready behind this
-        for (int r0 = 0; r0 < total_rows; r0 += band_rows) {
-            const int r1 = std::min(total_rows, r0 + band_rows);
+        for (int bi = 0; bi < n_bands; ++bi) {
+            const int r0 = band_start[bi], r1 = band_start[bi + 1];
+            if (r1 <= r0) continue;
             A.lrow0 = r0;
             A.local_rows = r1;
             cudaStream_t s = ctx->stream;                       // shadows the main stream inside the band loop
             if (n_bands > 1) {
-                s = ctx->band_streams[std::min(r0 / band_rows, RTDS_MAX_BANDS - 1)];
+                s = ctx->band_streams[bi];
                 RTDS_CUDA(cudaStreamWaitEvent(s, ctx->ev_ready, 0));
             }
             const dim3 block(128);
@@ -1090,7 +1113,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
                 RTDS_CUDA(cudaEventRecord(ctx->ev3, s));
                 if (on_band) { RTDS_CUDA(cudaEventRecord(ctx->ev_band, s)); RTDS_TRY((*on_band)(r0, r1, ctx->ev_band)); }
             } else {
-                cudaEvent_t done = ctx->ev_bands[std::min(r0 / band_rows, RTDS_MAX_BANDS - 1)];
+                cudaEvent_t done = ctx->ev_bands[bi];
                 RTDS_CUDA(cudaEventRecord(done, s));
                 RTDS_CUDA(cudaStreamWaitEvent(ctx->stream, done, 0));       // the main stream joins every band
             }
@@ -1099,8 +1122,8 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             RTDS_CUDA(cudaEventRecord(ctx->ev3, ctx->stream));
             // every band is queued: now the copies (a copy into pageable host memory blocks the host until it is done, so it
             // must not sit between two launches)
-            for (int r0 = 0; r0 < total_rows; r0 += band_rows)
-                RTDS_TRY((*on_band)(r0, std::min(total_rows, r0 + band_rows), ctx->ev_bands[std::min(r0 / band_rows, RTDS_MAX_BANDS - 1)]));
+            for (int bi = 0; bi < n_bands; ++bi)
+                if (band_start[bi + 1] > band_start[bi]) RTDS_TRY((*on_band)(band_start[bi], band_start[bi + 1], ctx->ev_bands[bi]));
         }
         A.local_rows = total_rows;
         RTDS_CUDA(cudaGetLastError());

@@ -160,7 +160,7 @@ struct rtds_ctx {
     int*     d_hit = nullptr;  size_t hit_bytes = 0;
     float*   d_accum = nullptr; size_t accum_bytes = 0;
     unsigned long long* d_counters = nullptr;  // render counters [8]
-    unsigned long long* h_counters = nullptr;  // pinned host copy [8]
+    unsigned long long* h_counters = nullptr;  // pinned [16]: [0..7] render counters, [8] material flag, [9..11] LBVH root box, [12] depth
     uint8_t* h_pinned = nullptr;     // pinned host staging for D2H of frames
     SharedFrame shared;
     size_t   pinned_bytes = 0;
@@ -200,6 +200,14 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st);
 
 // sah.cu — K7 binned SAH BVH
 int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st);
+
+// Zero fill by a KERNEL (api.cu). cudaMemsetAsync may be executed by a copy engine; on the rtds_frame path that queues
+// the build's clears behind the 17 MB material upload still running on the copy stream (measured: the build stalled until
+// the upload had finished). p 4-byte aligned, bytes a multiple of 4.
+int rtds_zero_async(void* p, size_t bytes, cudaStream_t s, int* launches = nullptr);
+
+// RTDS_TRACE_FRAME=1 (profiling aid, api.cu): timing events of rtds_frame's device timeline; [0] == nullptr when off
+extern cudaEvent_t g_rtds_trace_ev[8];
 
 // kd.cu — K8 KD-tree SAH build
 int rtds_build_kd(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st);

@@ -160,7 +160,7 @@ int onesweep_sort(rtds_ctx* ctx, K* d_keys, uint32_t* d_vals, K* d_keys_tmp, uin
     uint32_t* ghist = (uint32_t*)ctx->d_sort_ws;
     uint32_t* ticket = ghist + (size_t)passes * RADIX;
     uint32_t* status = ticket + RADIX;
-    RTDS_CUDA(cudaMemsetAsync(ctx->d_sort_ws, 0, bytes, ctx->stream));
+    RTDS_TRY(rtds_zero_async(ctx->d_sort_ws, bytes, ctx->stream, launches));
 
     int hist_blocks = min(tiles, ctx->sm_count * 8);
     histogram_kernel<K><<<hist_blocks, SORT_THREADS, passes * RADIX * sizeof(uint32_t), ctx->stream>>>(d_keys, n, passes, ghist);

@@ -8,7 +8,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["RTDS_TRACE_FRAME"] = "1"
+os.environ.setdefault("RTDS_TRACE_FRAME", "1")
 import __graft_entry__ as entry  # noqa: E402
 
 rt = entry.load_rtds()
