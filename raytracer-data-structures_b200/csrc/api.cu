@@ -327,6 +327,7 @@ int rtds_frame(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n, in
             fprintf(stderr, " us\n");
             cudaGetLastError();
         }
+        cudaGetLastError();      // an event of a stage that did not run on this path leaves an error behind
         fprintf(stderr, "[rtds_frame device] dirs %.0f..%.0f us | build %.0f..%.0f | materials up %.0f | render %.0f..%.0f | frame down %.0f\n",
                 1e3 * d0, 1e3 * d1, 1e3 * b0, 1e3 * b1, 1e3 * m1, 1e3 * r0, 1e3 * r1, 1e3 * c1);
     }
@@ -506,6 +507,19 @@ int rtds_render(rtds_ctx* c, int acc, const rtds_render_params* p, uint8_t* rgb,
     if (hit_obj) RTDS_TRY(ensure_buf(&c->d_hit, &c->hit_bytes, px * sizeof(int) + 16));
     if (accum) RTDS_TRY(ensure_buf(&c->d_accum, &c->accum_bytes, px * 3 * sizeof(float) + 16));
     cudaStream_t s = c->stream;
+    // RTDS_ZEROCOPY=1 (experiment, MEASURED SLOWER, off by default): when the caller's frame is pinned host memory, the render
+    // kernel stores its RGB8 tiles straight into it over PCIe (mapped memory) - no bands, no device->host copy afterwards.
+    // Frame identical, but the 8-byte posted writes reach only ~17 GB/s and throttle the kernel: 1.09 -> 1.48 ms, e2e 2.34 vs
+    // 2.12 ms with the banded copies.
+    if (world == 1 && !hit_obj && !accum && getenv("RTDS_ZEROCOPY") && atoi(getenv("RTDS_ZEROCOPY")) == 1) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, rgb) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            RTDS_TRY(rtds_render_impl(c, acc, p, (uint8_t*)at.devicePointer, nullptr, nullptr, st, nullptr, false));
+            RTDS_CUDA(cudaStreamSynchronize(s));
+            return RTDS_OK;
+        }
+        cudaGetLastError();
+    }
     if (world == 1) {
         // the frame comes back band by band while later bands are still rendering
         std::function<int(int, int, cudaEvent_t)> on_band = [&](int r0, int r1, cudaEvent_t done) -> int {

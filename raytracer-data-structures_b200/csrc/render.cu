@@ -290,6 +290,7 @@ __device__ __forceinline__ void shade_diffuse_shadowed(const RenderArgs& A, floa
 #endif
 // closest hits of four primary rays (origin 0, dz < 0): one packet when they share a direction octant and the ordered
 // traversal's preconditions hold, four single-ray traversals (out of line) otherwise
+template <bool HULL>
 __device__ __forceinline__ void trace_packet4(const RenderArgs& A, const float (&dx)[PK], const float (&dy)[PK], const float (&dz)[PK],
                                               float margin, float (&tnear)[PK], int (&best_leaf)[PK], Counters& cnt)
 {
@@ -311,10 +312,10 @@ __device__ __forceinline__ void trace_packet4(const RenderArgs& A, const float (
     }
     if (ok) {
         switch (oct0) {
-            case 4: traverse_packet<4>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
-            case 5: traverse_packet<5>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
-            case 6: traverse_packet<6>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
-            default: traverse_packet<7>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
+            case 4: traverse_packet<4, HULL>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
+            case 5: traverse_packet<5, HULL>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
+            case 6: traverse_packet<6, HULL>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
+            default: traverse_packet<7, HULL>(A.bvh, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt); break;
         }
     } else {
 #pragma unroll
@@ -345,7 +346,8 @@ __device__ __forceinline__ int shade_packet_ray(const RenderArgs& A, float dx, f
     return hit_obj;
 }
 
-template <bool SHADOWS /*evaluate the shadow query (extension; the reference's trace_more is a stub)*/>
+template <bool SHADOWS /*evaluate the shadow query (extension; the reference's trace_more is a stub)*/,
+          bool HULL /*interior boxes tested once per packet against the hull of the four reciprocal directions*/>
 __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const __grid_constant__ RenderArgs A)
 {
     unsigned shadow_rays = 0;
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
             dx[0] = d0.x; dy[0] = d0.y; dz[0] = d0.z; dx[1] = d0.w; dy[1] = d1.x; dz[1] = d1.y;
             dx[2] = d1.z; dy[2] = d1.w; dz[2] = d2.x; dx[3] = d2.y; dy[3] = d2.z; dz[3] = d2.w;
             cnt.rays += PK;
-            trace_packet4(A, dx, dy, dz, margin, tnear, best_leaf, cnt);
+            trace_packet4<HULL>(A, dx, dy, dz, margin, tnear, best_leaf, cnt);
 #pragma unroll
             for (int j = 0; j < PK; ++j) {
                 float r, g, b;
@@ -1094,13 +1096,16 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             bool packet = (!full || !ctx->has_materials) && !kdt && !brute && !p->exact && spp % PK == 0 && A.bvh.leaf_box_prim &&
                           A.shade.max_depth >= 1;
             if (const char* e = getenv("RTDS_PACKET")) packet = packet && atoi(e) != 0;
-            if (packet && full) render_packet_kernel<true><<<lin, block, 0, s>>>(A);
+            // interior boxes tested once per packet against the hull of the four reciprocal directions (default; RTDS_HULL=0:
+            // once per ray). Bench frame: same frame, node visits 3.17 -> 3.18 per ray, kernel 1.16 -> 0.99 ms.
+            const bool hull = getenv("RTDS_HULL") ? atoi(getenv("RTDS_HULL")) != 0 : true;
+            if (packet && full) { if (hull) render_packet_kernel<true, true><<<lin, block, 0, s>>>(A); else render_packet_kernel<true, false><<<lin, block, 0, s>>>(A); }
             else if (full) {
                 if (brute) render_full_kernel<2><<<lin, block, 0, s>>>(A);
                 else if (p->exact) render_full_kernel<0><<<lin, block, 0, s>>>(A);
                 else render_full_kernel<1><<<lin, block, 0, s>>>(A);
             }
-            else if (packet) render_packet_kernel<false><<<lin, block, 0, s>>>(A);
+            else if (packet) { if (hull) render_packet_kernel<false, true><<<lin, block, 0, s>>>(A); else render_packet_kernel<false, false><<<lin, block, 0, s>>>(A); }
             else if (kd_closest) render_kernel<4><<<lin, block, 0, s>>>(A);
             else if (kdt) render_kernel<3><<<lin, block, 0, s>>>(A);
             else if (brute) render_kernel<2><<<lin, block, 0, s>>>(A);

@@ -151,11 +151,15 @@ def test_packet_traversal_equals_single_ray_and_reference_order(gpu_ctx, oracle,
     gpu_ctx.build(a, mode=rt.MODE_TRUE if acc == "LBVH" else rt.MODE_COMPAT)
     nodes, order = gpu_ctx.export_bvh()
     W, H, spp = 400, 300, 8
-    pk = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True)
+    pk = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True)     # default: interior boxes tested once per packet (hull)
     ex = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True, exact=True)
+    monkeypatch.setenv("RTDS_HULL", "0")                                   # interior boxes tested per ray
+    pr = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True)
+    monkeypatch.delenv("RTDS_HULL")
     monkeypatch.setenv("RTDS_PACKET", "0")
     sr = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True)
-    for other in (ex, sr):
+    assert pk[3]["node_tests"] < pr[3]["node_tests"] and pk[3]["node_visits"] <= 1.05 * pr[3]["node_visits"]
+    for other in (ex, sr, pr):
         assert np.array_equal(pk[1], other[1]) and pk[2].tobytes() == other[2].tobytes() and np.array_equal(pk[0], other[0])
     rgb_o, hit_o, accum_o, _ = oracle.render_rows(sph, mat, nodes, order, W, H, spp, tie_by_objid=1 if acc == "LBVH" else 0, want_accum=True)
     assert np.array_equal(pk[1], hit_o) and pk[2].tobytes() == accum_o.tobytes() and np.array_equal(pk[0], rgb_o)

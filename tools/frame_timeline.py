@@ -29,6 +29,9 @@ for i in range(8):
     rc = ctx.lib.rtds_frame(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), sph.shape[0], rt.LBVH, C.byref(bp),
                             C.byref(rp), C.c_void_p(frame.data_ptr()), C.byref(bst), C.byref(rst))
     dt = (time.perf_counter() - t0) * 1e3
-    assert rc == 0
+    assert rc == 0, ctx.lib.rtds_last_error()
     print("frame %d: %.3f ms wall; build %.3f ms device, render kernel %.3f ms, render total %.3f ms device" %
           (i, dt, bst.ms, rst.ms_kernel, rst.ms_total), file=sys.stderr)
+if os.environ.get("RTDS_CHECK_FRAME"):          # compare the last frame with a plain render of the same scene
+    ref_rgb, _, _, _ = ctx.render(rt.LBVH, W, H, SPP)
+    print("frame equals rtds_render's:", bool((frame.numpy() == ref_rgb).all()), file=sys.stderr)
