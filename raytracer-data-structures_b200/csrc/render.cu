@@ -346,6 +346,17 @@ __device__ __forceinline__ int shade_packet_ray(const RenderArgs& A, float dx, f
     return hit_obj;
 }
 
+// the same, out of line (RTDS_SHADE_OOL experiment): one copy of the shading code per kernel instead of four
+struct ShadedRay { float r, g, b; int hit; };
+static __device__ __noinline__ ShadedRay shade_packet_ray_ool(const RenderArgs* A, float dx, float dy, float dz, float tnear, int best_leaf)
+{
+    ShadedRay o;
+    Counters c = {0, 0, 0, 0};
+    unsigned sr = 0;
+    o.hit = shade_packet_ray<false>(*A, dx, dy, dz, tnear, best_leaf, o.r, o.g, o.b, c, sr);
+    return o;
+}
+
 template <bool SHADOWS /*evaluate the shadow query (extension; the reference's trace_more is a stub)*/,
           bool HULL /*interior boxes tested once per packet against the hull of the four reciprocal directions*/>
 __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const __grid_constant__ RenderArgs A)
@@ -378,6 +389,10 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
 #pragma unroll
             for (int j = 0; j < PK; ++j) {
                 float r, g, b;
+#ifndef RTDS_SHADE_INLINE
+                if (!SHADOWS) { const ShadedRay sh = shade_packet_ray_ool(&A, dx[j], dy[j], dz[j], tnear[j], best_leaf[j]); r = sh.r; g = sh.g; b = sh.b; last_hit = sh.hit; }
+                else
+#endif
                 last_hit = shade_packet_ray<SHADOWS>(A, dx[j], dy[j], dz[j], tnear[j], best_leaf[j], r, g, b, cnt, shadow_rays);
                 acc_r += r; acc_g += g; acc_b += b;     // sample order, main.cpp:553-560
             }
