@@ -29,16 +29,21 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
     return y;
 }
 
-// One regeneration A -> B (624 words) by a block of >= 227 threads, three dependent phases.
+// One regeneration A -> B (624 words) by a block of >= 227 threads, ONE phase and one barrier: x[k+624] =
+// x[k+397] ^ twist(x[k], x[k+1]) makes B[t+227] depend on B[t] and B[t+454] on B[t+227], so thread t carries its own
+// chain of three words in registers; B[623] needs B[396] (thread 169's second word) and B[0], which that thread recomputes.
+// (Three 227-wide phases with a barrier each cost the jitter kernel 24 barriers per block and left a third of the warps idle.)
 __device__ __forceinline__ void mt_regen(const uint32_t* __restrict__ A, uint32_t* __restrict__ B)
 {
     const int t = threadIdx.x;
-    if (t < 227) B[t] = A[t + MT_M] ^ mt_twist(A[t], A[t + 1]);
-    __syncthreads();
-    if (t < 227) B[t + 227] = B[t] ^ mt_twist(A[t + 227], A[t + 228]);
-    __syncthreads();
-    if (t < 169) B[t + 454] = B[t + 227] ^ mt_twist(A[t + 454], A[t + 455]);
-    if (t == 169) B[623] = B[396] ^ mt_twist(A[623], B[0]);
+    if (t < 227) {
+        const uint32_t b0 = A[t + MT_M] ^ mt_twist(A[t], A[t + 1]);
+        B[t] = b0;
+        const uint32_t b1 = b0 ^ mt_twist(A[t + 227], A[t + 228]);
+        B[t + 227] = b1;
+        if (t < 169) B[t + 454] = b1 ^ mt_twist(A[t + 454], A[t + 455]);
+        else if (t == 169) B[623] = b1 ^ mt_twist(A[623], A[MT_M] ^ mt_twist(A[0], A[1]));
+    }
     __syncthreads();
 }
 
@@ -194,18 +199,34 @@ __global__ void __launch_bounds__(MT_THREADS) mt_expand_dirs_kernel(const uint32
     // all threads, no barriers: temper, canonical doubles, direction, normalise, store
     const unsigned long long as0 = wlo / 4;           // absolute stream sample of the chunk's first four words
     const uint4* w4 = reinterpret_cast<const uint4*>(words + MT_N);
-    for (int i = t; i < MT_SNAP_EVERY * MT_N / 4; i += MT_THREADS) {
-        const unsigned long long as = as0 + i;
-        if (as >= first_sample && as - first_sample < n_samples) {
-            const unsigned g = (unsigned)(as - first_sample);
-            const unsigned pix = fast_div(g, div_spp);
-            const unsigned py = fast_div(pix, div_width), px = pix - py * (unsigned)width;
+    constexpr int CHUNK_SAMPLES = MT_SNAP_EVERY * MT_N / 4;
+    // frame sample of the chunk's first stream sample; chunks that lie wholly inside the frame (all but the first and the
+    // last) need no 64-bit range check per sample, and when aa_samples divides the thread stride the pixel coordinates
+    // advance by additions instead of two divisions per sample
+    const long long rel = (long long)as0 - (long long)first_sample;
+    const bool inside = rel >= 0 && rel + CHUNK_SAMPLES <= (long long)n_samples;
+    const bool stepping = inside && (MT_THREADS % spp) == 0;
+    const unsigned step_px = stepping ? (unsigned)(MT_THREADS / spp) : 0u;
+    unsigned px = 0, py = 0;
+    if (stepping) {
+        const unsigned pix = fast_div((unsigned)rel + (unsigned)t, div_spp);
+        py = fast_div(pix, div_width); px = pix - py * (unsigned)width;
+    }
+    for (int i = t; i < CHUNK_SAMPLES; i += MT_THREADS) {
+        const long long gl = rel + i;
+        if (inside || (gl >= 0 && gl < (long long)n_samples)) {
+            const unsigned g = (unsigned)gl;
+            if (!stepping) {
+                const unsigned pix = fast_div(g, div_spp);
+                py = fast_div(pix, div_width); px = pix - py * (unsigned)width;
+            }
             const uint4 w = w4[i];
             const uint4 jw = make_uint4(mt_temper(w.x), mt_temper(w.y), mt_temper(w.z), mt_temper(w.w));
             float dx, dy, dz;
             primary_dir(jw, (int)px, (int)py, G, dx, dy, dz);
             float* o = dirs + 3 * (size_t)g;
             o[0] = dx; o[1] = dy; o[2] = dz;
+            if (stepping) { px += step_px; while (px >= (unsigned)width) { px -= (unsigned)width; ++py; } }
         }
     }
 }
