@@ -470,12 +470,12 @@ def run_ours(args):
                                             "what": "bytes that must cross HBM per launch: 12 B/ray directions in + 3 B/pixel out + the tree once"},
                              "ncu": {k: ncu.get(k) for k in ("issue_active_pct", "warps_active_pct", "l1tex_hit_pct", "lts_hit_pct", "pipe_alu_pct",
                                                              "pipe_fma_pct", "l1tex_throughput_pct", "dram_throughput_pct")} if ncu else None,
-                             "note": "`achieved` follows SURVEY 8d (32 B x slab tests + 16 B x prim tests + 16 B per ray, from the kernel's own "
-                                     "counters): with 1,078,411 sub-pixel spheres that is ~840 B/ray, a stream the packet kernel serves from "
-                                     "registers (one node load feeds the 4 samples of a pixel), L1 (86 % hit) and L2, so frac > 1 and HBM is "
-                                     "not the bound: measured DRAM traffic is `traffic` bytes per launch (~5 % of peak, = `compulsory`); ncu "
-                                     "shows the kernel issue/latency-bound (68 % of issue slots, ALU pipe 57 %, 37 % occupancy at 80 regs) - "
-                                     "DESIGN.md section 8, profiles/"},
+                             "note": ("`achieved` follows SURVEY 8d (32 B x slab tests + 16 B x prim tests + 16 B per ray, from the kernel's own "
+                                      "counters; the packet kernel tests an interior box once per 4-ray packet, so slab tests/ray is a quarter "
+                                      "of the node boxes a ray meets). That stream is served from registers (one node load feeds the 4 samples "
+                                      "of a pixel), L1 and L2, so frac can exceed 1 and HBM is not the bound: measured DRAM traffic is `traffic` "
+                                      "bytes per launch (~`compulsory`); ncu (`ncu` block, profiles/) shows the kernel issue/latency-bound - "
+                                      "DESIGN.md section 8")},
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(2 * n * 16) * world,
                         "d2h_bytes_per_step": W * H * 3,
                         "what": "per step: rtds_frame = rtds_set_spheres (H2D from pinned) + rtds_build(LBVH) + rtds_render into a pinned host frame, ray directions generated on a side stream meanwhile (N>1: set_spheres + build + rtds_render_shared on every rank, D2H of the assembled frame on rank 0)"},
