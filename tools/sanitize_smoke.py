@@ -59,6 +59,7 @@ def main():
         ctx.render(acc, W + 5, H + 3, 3, shadows=1)   # ragged frame, single-ray kernels
         ctx.render(acc, W, H, 2, rank=1, world=3)     # a rank's interleaved tiles
         done.append((acc, kw))
+    ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
     os.environ["RTDS_STRIP"] = "1"
     ctx.render(rt.LBVH, W, H, 2)                      # fused strip kernel (opt-in)
     del os.environ["RTDS_STRIP"]
