@@ -22,13 +22,21 @@ ctx = rt.Rtds(0)
 ctx.set_spheres(sph, mat)
 ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
 out = np.zeros((H, W, 3), np.uint8)
+dev = None
+if os.environ.get("AB_DEVICE"):            # resident path: rtds_render_device into a device buffer (no download, no bands)
+    import torch
+    dev = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda")
 ref = None
 for rep in range(2):
     for val in vals:
         os.environ[var] = val
         ms = []
         for i in range(6):
-            rgb, _, _, st = ctx.render(rt.LBVH, W, H, SPP, out=out, shadows=shadows)
+            if dev is not None:
+                st = ctx.render_device(rt.LBVH, ctx.render_params(W, H, SPP, shadows=shadows), dev.data_ptr())
+                rgb = dev.cpu().numpy()
+            else:
+                rgb, _, _, st = ctx.render(rt.LBVH, W, H, SPP, out=out, shadows=shadows)
             ms.append(st["ms_kernel"])
         md5 = hashlib.md5(rgb.tobytes()).hexdigest()
         if ref is None:
