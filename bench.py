@@ -365,6 +365,14 @@ def run_ours(args):
                                     C.byref(e2e_params), C.c_void_p(frame_host.data_ptr()), None, C.byref(e2e_stats))
             assert rc == 0, ctx.lib.rtds_last_error()
             return None
+        if p2p:
+            # rtds_frame_shared = the same per rank with rtds_render_shared at the end; rank 0 then downloads the assembled frame
+            seq[0] += 1
+            rc = ctx.lib.rtds_frame_shared(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), n, rt.LBVH, C.byref(e2e_bp),
+                                           C.byref(params), seq[0], None, C.byref(e2e_stats))
+            assert rc == 0, ctx.lib.rtds_last_error()
+            assemble_and_download()
+            return None
         ctx.lib.rtds_set_spheres(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), n)
         ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
         st = step_resident()
@@ -478,7 +486,7 @@ def run_ours(args):
                                       "DESIGN.md section 8")},
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(2 * n * 16) * world,
                         "d2h_bytes_per_step": W * H * 3,
-                        "what": "per step: rtds_frame = rtds_set_spheres (H2D from pinned) + rtds_build(LBVH) + rtds_render into a pinned host frame, ray directions generated on a side stream meanwhile (N>1: set_spheres + build + rtds_render_shared on every rank, D2H of the assembled frame on rank 0)"},
+                        "what": "per step: rtds_frame = rtds_set_spheres (H2D from pinned) + rtds_build(LBVH) + rtds_render into a pinned host frame, ray directions generated on a side stream meanwhile (N>1: rtds_frame_shared = the same with rtds_render_shared on every rank, then D2H of the assembled frame on rank 0)"},
                 "with_shadows": {"value": sh_rays.item() / (float(np.mean(sh_steps)) * 1e-3) / 1e6, "unit": "Mrays/s",
                                  "ms_per_step": float(np.mean(sh_steps)), "rays_per_step": int(sh_rays.item()),
                                  "note": "extension: shadow query on (the reference's trace_more is a stub); primary + shadow rays"},

@@ -203,6 +203,7 @@ int rtds_rows_for_rank(int height, int tile_rows, int rank, int world);
  *   rank r, other proc: rtds_shared_frame_open(handle, ..., r)        (cudaIpcOpenMemHandle)
  *   rank r, same proc : rtds_shared_frame_attach(ctx_r, ctx_0, r)     (peer access; one context per GPU)
  *   every rank, frame : rtds_render_shared(ctx, acc, params, seq)     seq != 0 and different from the previous frame's;
+ *                       (or rtds_frame_shared: upload + build + rtds_render_shared in one call)
  *                       synchronous; on rank 0 it returns when EVERY rank's tiles of frame `seq` have landed
  *   rank 0            : rtds_shared_frame_read (device -> host) or rtds_shared_frame_ptr (device pointer, H*W*3 bytes)
  * The caller keeps frames apart: no rank may start frame k+1 before rank 0 has consumed frame k (a frame-loop barrier). */
@@ -211,6 +212,10 @@ int rtds_shared_frame_create(rtds_ctx* owner, int width, int height, int world, 
 int rtds_shared_frame_open(rtds_ctx* ctx, const void* ipc_handle, int width, int height, int world, int rank);
 int rtds_shared_frame_attach(rtds_ctx* ctx, rtds_ctx* owner, int rank);
 int rtds_render_shared(rtds_ctx* ctx, int acc_type, const rtds_render_params* params, uint32_t frame_seq, rtds_render_stats* stats);
+/* rtds_frame for one rank of a multi-GPU run: rtds_set_spheres -> rtds_build -> rtds_render_shared in one synchronous call,
+ * stages overlapped as in rtds_frame (what main() does per run, main.cpp:751,800/816/832,808, on every GPU). */
+int rtds_frame_shared(rtds_ctx* ctx, const float* cxyz_r, const float* rgb_mat, int n, int acc_type, const rtds_build_params* bp,
+                      const rtds_render_params* rp, uint32_t frame_seq, rtds_build_stats* bst, rtds_render_stats* rst);
 int rtds_shared_frame_ptr(rtds_ctx* ctx, void** d_frame);
 int rtds_shared_frame_read(rtds_ctx* owner, uint8_t* rgb);
 int rtds_shared_frame_close(rtds_ctx* ctx);

@@ -90,7 +90,7 @@ ABI_SYMBOLS = ["rtds_last_error", "rtds_version", "rtds_create", "rtds_destroy",
                "rtds_set_triangles", "rtds_set_lights", "rtds_build", "rtds_export_bvh", "rtds_export_kd",
                "rtds_export_morton", "rtds_trace", "rtds_render", "rtds_render_device", "rtds_rows_for_rank",
                "rtds_jitter_stream", "rtds_morton30", "rtds_frame", "rtds_shared_frame_create", "rtds_shared_frame_open",
-               "rtds_shared_frame_attach", "rtds_render_shared", "rtds_shared_frame_ptr", "rtds_shared_frame_read",
+               "rtds_shared_frame_attach", "rtds_render_shared", "rtds_frame_shared", "rtds_shared_frame_ptr", "rtds_shared_frame_read",
                "rtds_shared_frame_close"]
 
 _lib = None
@@ -129,6 +129,8 @@ def load_library(path: str = LIB_PATH):
     lib.rtds_shared_frame_open.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.rtds_shared_frame_attach.argtypes = [vp, vp, C.c_int]
     lib.rtds_render_shared.argtypes = [vp, C.c_int, C.POINTER(RenderParams), C.c_uint32, C.POINTER(RenderStats)]
+    lib.rtds_frame_shared.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.POINTER(BuildParams), C.POINTER(RenderParams), C.c_uint32,
+                                      C.POINTER(BuildStats), C.POINTER(RenderStats)]
     lib.rtds_shared_frame_ptr.argtypes = [vp, C.POINTER(vp)]
     lib.rtds_shared_frame_read.argtypes = [vp, vp]
     lib.rtds_shared_frame_close.argtypes = [vp]
@@ -293,6 +295,18 @@ class Rtds:
         st = RenderStats()
         self._check(self.lib.rtds_render_shared(self.ctx, acc, C.byref(params), frame_seq, C.byref(st)))
         return _stats_dict(st)
+
+    def frame_shared(self, cxyz_r, rgb_mat, acc, params, frame_seq, mode=MODE_COMPAT):
+        """rtds_frame_shared: upload + build + render_shared in one call (one rank of a multi-GPU run)."""
+        cxyz_r = np.ascontiguousarray(cxyz_r, np.float32).reshape(-1, 4)
+        rgb_mat = None if rgb_mat is None else np.ascontiguousarray(rgb_mat, np.float32).reshape(-1, 4)
+        bp = BuildParams()
+        bp.mode = mode
+        bst, rst = BuildStats(), RenderStats()
+        self._check(self.lib.rtds_frame_shared(self.ctx, _ptr(cxyz_r), _ptr(rgb_mat), cxyz_r.shape[0], acc, C.byref(bp), C.byref(params),
+                                               frame_seq, C.byref(bst), C.byref(rst)))
+        self.n = cxyz_r.shape[0]
+        return _stats_dict(bst), _stats_dict(rst)
 
     def shared_frame_ptr(self):
         p = C.c_void_p()

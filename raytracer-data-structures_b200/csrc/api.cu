@@ -645,6 +645,21 @@ int rtds_render_shared(rtds_ctx* c, int acc, const rtds_render_params* p, uint32
     return RTDS_OK;
 }
 
+// rtds_frame for one rank of a multi-GPU run: upload + build + rtds_render_shared with the stages overlapped exactly as in
+// rtds_frame (ray directions on a side stream and the material table on the copy stream while the sphere table uploads and
+// the structure is built).
+int rtds_frame_shared(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n, int acc, const rtds_build_params* bp,
+                      const rtds_render_params* rp, uint32_t frame_seq, rtds_build_stats* bst, rtds_render_stats* rst)
+{
+    if (!c || !rp) { rtds_set_error("frame_shared: bad arguments"); return RTDS_ERR_INVALID; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    RTDS_TRY(rtds_prefetch_dirs(c, rp));
+    RTDS_TRY(upload_spheres(c, cxyz_r, rgb_mat, n, true));
+    RTDS_TRY(rtds_build(c, acc, bp, bst));
+    RTDS_TRY(rtds_finish_materials(c));
+    return rtds_render_shared(c, acc, rp, frame_seq, rst);
+}
+
 int rtds_shared_frame_ptr(rtds_ctx* c, void** d_frame)
 {
     if (!c || !d_frame || !c->shared.frame) { rtds_set_error("shared_frame_ptr: no shared frame"); return RTDS_ERR_INVALID; }

@@ -37,6 +37,12 @@ def test_shared_frame_in_process_equals_single_rank(gpu_ctx, world, W, H, spp, s
                 rays += st["primary_rays"]
             assert rays == W * H * spp
             assert np.array_equal(gpu_ctx.shared_frame_read(W, H), full)
+        # rtds_frame_shared: upload + build + render_shared in one call per rank gives the same frame
+        for r in range(world - 1, -1, -1):
+            p = ranks[r].render_params(W, H, spp, rank=r, world=world, shadows=shadows)
+            bst, rst = ranks[r].frame_shared(sph, mat, rt.LBVH, p, 7, mode=rt.MODE_TRUE)
+            assert bst["n_prims"] == sph.shape[0] and rst["rows"] == rt.rows_for_rank(H, 8, r, world)
+        assert np.array_equal(gpu_ctx.shared_frame_read(W, H), full)
         # mismatching parameters are refused
         with pytest.raises(rt.RtdsError):
             ranks[1].render_shared(rt.LBVH, ranks[1].render_params(W, H, spp, rank=0, world=world), 3)
