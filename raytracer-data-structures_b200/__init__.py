@@ -352,12 +352,14 @@ def owned_rows(height, tile_rows, rank, world):
 GROUND = (0.93591022, -105.47120094, -43.2363205, 100.0)   # main.cpp:703
 
 
-def scene_from_vertices(v, clones=1):
-    """(n*clones+1, 4) float32 {cx,cy,cz,r} and matching {r,g,b,material}, float arithmetic as main.cpp:679-682."""
+def scene_from_vertices(v, clones=1, clone_shift=20):
+    """(n*clones+1, 4) float32 {cx,cy,cz,r} and matching {r,g,b,material}, float arithmetic as main.cpp:679-682.
+    clone_shift: the reference shifts clone k by 20*k on every axis (mostly off-screen); 2 is the report's experiment with
+    the clones in view (Report/Performance.xlsx rows 10-12) - measurement variant only."""
     v = np.ascontiguousarray(v, np.float32).reshape(-1, 3)
     parts = []
     for clone in range(clones):
-        shift = np.float32(clone * 20)
+        shift = np.float32(clone * clone_shift)
         c = v * np.float32(100) + shift
         c[:, 1] += np.float32(-10)
         c[:, 2] += np.float32(-60)

@@ -192,3 +192,24 @@ def test_bench_frame_full_size_packet_equals_reference_traversal(gpu_ctx):
         rows = rt.owned_rows(H, 8, rank, 2)
         frame[rows] = part[rows]
     assert np.array_equal(frame, fast)
+
+
+def test_visible_clones_variant_packet_equals_reference_traversal(gpu_ctx, oracle):
+    """SURVEY 8d's visible variant of config 3 (clone shift 2: the bunnies overlap in view, far more candidates per ray), reduced
+    to 8 clones at 960x540x4spp: packet + hull traversal == unpruned reference traversal == CPU restatement (hit ids, sums, bytes)."""
+    v = np.fromfile(T.GOLDEN + "/bunny_vertices.f32", np.float32).reshape(-1, 3)
+    sph, mat = rt.scene_from_vertices(v, 8, clone_shift=2)
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+    nodes, order = gpu_ctx.export_bvh()
+    W, H, spp = 960, 540, 4
+    fast, hit_f, acc_f, st_f = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True)
+    exact, hit_e, acc_e, st_e = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True, exact=True)
+    assert np.array_equal(hit_f, hit_e) and acc_f.tobytes() == acc_e.tobytes() and np.array_equal(fast, exact)
+    y0, y1 = 200, 330                                   # the CPU restatement on the densest rows
+    rgb_o, hit_o, acc_o, _ = oracle.render_rows(sph, mat, nodes, order, W, H, spp, y0, y1, tie_by_objid=1, want_accum=True)
+    assert np.array_equal(hit_f[y0:y1], hit_o) and acc_f[y0:y1].tobytes() == acc_o.tobytes() and np.array_equal(fast[y0:y1], rgb_o)
+    assert (hit_f >= 0).mean() > 0.4
+    sh, _, _, st_s = gpu_ctx.render(rt.LBVH, W, H, spp, shadows=1)
+    sh_e, _, _, _ = gpu_ctx.render(rt.LBVH, W, H, spp, shadows=1, exact=True)
+    assert np.array_equal(sh, sh_e) and st_s["shadow_rays"] > 0

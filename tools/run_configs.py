@@ -108,6 +108,13 @@ def main():
         for sh in (0, 1):
             out.append(run(ctx, "config3: bunny x30 clones 3840x2160 aa4 LBVH(true)", rt.LBVH, rt.MODE_TRUE, 3840, 2160, 4, shadows=sh))
         out.append(run(ctx, "config3: same, BVH(median, bit-exact)", rt.BVH, rt.MODE_COMPAT, 3840, 2160, 4))
+    if "3v" in which or "3" in which:
+        # the VISIBLE variant of config 3 - clone shift 2 instead of 20, every clone inside the view
+        sph, mat = rt.scene_from_vertices(V, 30, clone_shift=2)
+        ctx.set_spheres(sph, mat)
+        for sh in (0, 1):
+            out.append(run(ctx, "config3-visible: bunny x30 clones, clone shift 2 (all in view), 3840x2160 aa4 LBVH(true)", rt.LBVH, rt.MODE_TRUE,
+                           3840, 2160, 4, shadows=sh))
     if "4" in which:
         sph, mat = torus_knot_scene(7_000_000)
         ctx.set_spheres(sph, mat)
