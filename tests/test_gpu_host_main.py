@@ -63,3 +63,22 @@ def test_multi_gpu_in_one_process(tmp_path):
     _models(tmp_path)
     out, ppm = _run(tmp_path, RTDS_GPUS=2)
     assert hashlib.md5(ppm).hexdigest() == "c69c66375f2c6bda433f9f457a4b2b2e"
+
+
+def test_kd_closest_hit_through_the_driver(tmp_path, gpu_ctx):
+    """RTDS_KD_CLOSEST=1: the driver's KDTREE frame is the closest-hit, shaded one (extension) = the library call's frame; without
+    the variable it stays the reference's any-hit black/sky frame (previous test)."""
+    if not os.path.exists(MAIN):
+        pytest.skip("rtds_main not built")
+    _models(tmp_path)
+    out, ppm = _run(tmp_path, RTDS_DS=1, RTDS_KD_CLOSEST=1)
+    assert "<<<<<<< This is KDTREE >>>>>>" in out and "Depth is: 28" in out
+    sph, mat = T.bunny_scene()
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.build(rt.KDTREE)
+    rgb, _, _, _ = gpu_ctx.render(rt.KDTREE, 640, 480, 1, kd_closest=1)
+    assert hashlib.md5(ppm).hexdigest() == T.ppm_md5(rgb) != G["default_config"]["KDTREE"]["ppm_md5"]
+    bvh = np.frombuffer(ppm[-640 * 480 * 3:], np.uint8).reshape(480, 640, 3)
+    gpu_ctx.build(rt.BVH)
+    ref_rgb, _, _, _ = gpu_ctx.render(rt.BVH, 640, 480, 1)                     # byte-identical to the reference's output.ppm
+    assert np.count_nonzero(np.any(bvh != ref_rgb, axis=-1)) <= 640 * 480 // 1000   # same picture but for grazing rays
