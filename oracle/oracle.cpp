@@ -20,11 +20,13 @@
 // Build: oracle/Makefile -> oracle/liboracle.so   (g++ -O2 -ffp-contract=off: no FMA contraction, like the
 // reference's x86-64 baseline build).
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -790,6 +792,116 @@ void orc_kd_closest(const float* prims, int prim_type, int n, const KdNode* node
         hit[r] = best; t[r] = tnear;
     }
     if (prim_tests) *prim_tests = tests;
+}
+
+// ----------------------------------------------------------------------------------------------
+// 4-wide collapse of a flattened binary BVH (definition for the planned wide-node traversal, DESIGN.md section 10.1;
+// no reference counterpart: the reference's trees are binary, accelerators.h:131-156). Deterministic:
+//   wide(b) for a binary interior node b starts from the list [left(b), right(b)] and, while the list has fewer than four
+//   entries and holds an interior node, replaces IN PLACE the interior entry with the largest box surface area (first one
+//   on ties; SurfaceArea as accelerators.h:122-125) by its two children - 2..4 children, DFS order preserved;
+//   every interior entry c left in the list becomes wide(c); wide nodes are numbered in pre-order, root = 0.
+// Child boxes are the binary nodes' own boxes (bit-identical), so the candidate criterion - "the LEAF's box passes the
+// reference's slab test" - is untouched and the collect-all trace below returns closest_bvh()'s hits.
+// ----------------------------------------------------------------------------------------------
+struct Wide4Node {
+    float bmin[4][3], bmax[4][3];
+    int32_t child[4];        // >= 0: wide node index; < 0: ~leafpos (index into prim_order); unused slots: INT32_MAX
+    int32_t n_children, binary_node, pad[2];
+};
+static_assert(sizeof(Wide4Node) == 128, "Wide4Node is 128 bytes");
+
+int orc_collapse4(const LinearNode* nodes, int n_nodes, Wide4Node* out, int cap)
+{
+    if (n_nodes <= 0 || nodes[0].nPrimitives) return 0;      // a single leaf has no interior node to widen
+    std::vector<std::pair<int, int>> todo;                   // (binary node, wide index), LIFO with children pushed in reverse = pre-order
+    int n_wide = 1;
+    todo.push_back({0, 0});
+    std::vector<Wide4Node> W(1);
+    while (!todo.empty()) {
+        const auto [b, w] = todo.back();
+        todo.pop_back();
+        int listed[4] = {b + 1, nodes[b].offset, 0, 0}, m = 2;
+        auto area = [&](int c) {
+            const float dx = nodes[c].bmax[0] - nodes[c].bmin[0], dy = nodes[c].bmax[1] - nodes[c].bmin[1], dz = nodes[c].bmax[2] - nodes[c].bmin[2];
+            return 2 * (dx * dy + dx * dz + dy * dz);
+        };
+        while (m < 4) {
+            int pick = -1;
+            float best = -1.f;
+            for (int k = 0; k < m; ++k)
+                if (!nodes[listed[k]].nPrimitives) { const float a = area(listed[k]); if (a > best) { best = a; pick = k; } }
+            if (pick < 0) break;
+            const int c = listed[pick];
+            for (int k = m; k > pick + 1; --k) listed[k] = listed[k - 1];
+            listed[pick] = c + 1; listed[pick + 1] = nodes[c].offset;
+            ++m;
+        }
+        Wide4Node nd;
+        memset(&nd, 0, sizeof nd);
+        nd.n_children = m; nd.binary_node = b;
+        for (int k = 0; k < 4; ++k) {
+            if (k >= m) { nd.child[k] = INT32_MAX; continue; }
+            const LinearNode& c = nodes[listed[k]];
+            for (int a = 0; a < 3; ++a) { nd.bmin[k][a] = c.bmin[a]; nd.bmax[k][a] = c.bmax[a]; }
+            if (c.nPrimitives) nd.child[k] = ~c.offset;
+            else { nd.child[k] = n_wide++; W.push_back(Wide4Node()); }
+        }
+        W[w] = nd;
+        // provisional indices are handed out in listing order; the pre-order numbering follows below
+        for (int k = m - 1; k >= 0; --k) if (nd.child[k] >= 0 && nd.child[k] != INT32_MAX) todo.push_back({listed[k], nd.child[k]});
+    }
+    // renumber to pre-order (DFS, children in listing order)
+    std::vector<int> order, new_index(n_wide, -1);
+    std::vector<int> st{0};
+    while (!st.empty()) {
+        const int w = st.back(); st.pop_back();
+        new_index[w] = (int)order.size(); order.push_back(w);
+        for (int k = W[w].n_children - 1; k >= 0; --k) if (W[w].child[k] >= 0 && W[w].child[k] != INT32_MAX) st.push_back(W[w].child[k]);
+    }
+    if (out) {
+        if (cap < n_wide) return -n_wide;
+        for (int i = 0; i < n_wide; ++i) {
+            Wide4Node nd = W[order[i]];
+            for (int k = 0; k < nd.n_children; ++k) if (nd.child[k] >= 0) nd.child[k] = new_index[nd.child[k]];
+            out[i] = nd;
+        }
+    }
+    return n_wide;
+}
+
+// boxIntersect's collect-all walk (accelerators.h:668-690) + the candidate loop (main.cpp:343-358) over the 4-wide tree:
+// every child box that passes the reference's slab test is opened; candidates are reduced with the same order-independent
+// key as closest_bvh (leaf position, or objId with tie_by_objid).
+void orc_trace_wide4(const float* prims, int prim_type, int n, const Wide4Node* wide, int n_wide, const int* prim_order, int tie_by_objid,
+                     const float* o_all, const float* d_all, int nrays, int* hit, float* t, long long* box_tests)
+{
+    Scene S{prims, nullptr, n, nullptr, prim_order, 0, tie_by_objid};
+    S.prim_type = prim_type;
+    long long tests = 0;
+    for (int r = 0; r < nrays; ++r) {
+        const float* o = o_all + 3 * r; const float* d = d_all + 3 * r;
+        int best = -1, best_key = 0; float tnear = INFINITY;
+        int stack[256]; int sp = 0;
+        if (n_wide > 0) stack[sp++] = 0;
+        while (sp) {
+            const Wide4Node& nd = wide[stack[--sp]];
+            for (int k = 0; k < nd.n_children; ++k) {
+                ++tests;
+                if (!slab(o, d, nd.bmin[k], nd.bmax[k])) continue;
+                if (nd.child[k] >= 0) { if (sp < 256) stack[sp++] = nd.child[k]; continue; }
+                const int leafpos = ~nd.child[k], obj = prim_order[leafpos];
+                float t0 = INFINITY, t1 = INFINITY;
+                if (S.test(o, d, obj, t0, t1)) {
+                    if (t0 < 0) t0 = t1;
+                    const int key = tie_by_objid ? obj : leafpos;
+                    if (t0 < tnear || (t0 == tnear && best >= 0 && key < best_key)) { tnear = t0; best = obj; best_key = key; }
+                }
+            }
+        }
+        hit[r] = best; t[r] = tnear;
+    }
+    if (box_tests) *box_tests = tests;
 }
 
 void orc_jitter(double* out, int n, unsigned long long first)

@@ -38,6 +38,9 @@ def load_rtds():
 
 rtds_b200 = load_rtds()
 LINEAR = rtds_b200.LINEAR_NODE_DTYPE
+WIDE4 = np.dtype([("bmin", np.float32, (4, 3)), ("bmax", np.float32, (4, 3)), ("child", np.int32, 4), ("n_children", np.int32),
+                  ("binary_node", np.int32), ("pad", np.int32, 2)])
+assert WIDE4.itemsize == 128
 
 
 def has_gpu():
@@ -146,6 +149,28 @@ class Oracle:
         tests = C.c_longlong()
         self.lib.orc_kd_closest(self._p(prims), prim_type, prims.shape[0], self._p(kd_nodes), self._p(kd_idx), self._p(bounds),
                                 self._p(o), self._p(d), n, self._p(hit), self._p(t), C.byref(tests))
+        return hit, t, tests.value
+
+    def collapse4(self, nodes):
+        """4-wide collapse of a LinearBVHNode[] (oracle.cpp: Wide4Node, 128 bytes)."""
+        nodes = np.ascontiguousarray(nodes)
+        n = self.lib.orc_collapse4(self._p(nodes), nodes.shape[0], None, 0)
+        wide = np.zeros(n, WIDE4)
+        assert self.lib.orc_collapse4(self._p(nodes), nodes.shape[0], self._p(wide), n) == n
+        return wide
+
+    def trace_wide4(self, prims, wide, order, o, d, tie_by_objid=0, prim_type=0):
+        prims = np.ascontiguousarray(prims, np.float32)
+        o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+        n = d.shape[0]
+        if o.shape[0] == 1 and n > 1:
+            o = np.ascontiguousarray(np.broadcast_to(o, (n, 3)))
+        hit = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float32)
+        tests = C.c_longlong()
+        self.lib.orc_trace_wide4(self._p(prims), prim_type, prims.shape[0], self._p(wide), wide.shape[0], self._p(np.ascontiguousarray(order, np.int32)),
+                                 tie_by_objid, self._p(o), self._p(d), n, self._p(hit), self._p(t), C.byref(tests))
         return hit, t, tests.value
 
     def jitter(self, n, first=0):

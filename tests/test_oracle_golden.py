@@ -126,3 +126,45 @@ def test_oracle_none_rows_match_golden_hits(oracle):
     rgb, hit, _, _ = oracle.render_rows(sph, mat, None, None, 640, 480, 1, y0, y1)
     gold = np.load(T.GOLDEN + "/bunny_hits_640x480.npz")
     assert np.array_equal(hit, gold["hit_none"][y0:y1])
+
+
+def test_wide4_collapse_keeps_boxes_leaves_and_hits(oracle):
+    """Definition of the 4-wide collapse (oracle.cpp, groundwork for the wide-node traversal of DESIGN.md 10.1): every leaf once,
+    child boxes = the binary nodes' boxes, 2..4 children (largest-area entry expanded first), pre-order numbering; the collect-all trace over the wide tree returns
+    the binary tree's hits and tnear bits (the candidate criterion is leaf-local) with fewer box tests per ray."""
+    sph, mat = T.bunny_scene()
+    for build in ("median", "lbvh"):
+        if build == "median":
+            rc, nodes, order, _ = oracle.build_bvh(sph)
+            tie = 0
+        else:
+            nodes, order, _, _ = oracle.build_lbvh(sph, 30)
+            tie = 1
+        wide = oracle.collapse4(nodes)
+        nc = wide["n_children"]
+        assert nc.min() >= 2 and nc.max() <= 4 and nc.mean() > 3.0 and wide.shape[0] < 0.5 * ((nodes.shape[0] - 1) // 2)
+        used = np.arange(4)[None, :] < nc[:, None]
+        ch = wide["child"]
+        leaves = ~ch[used & (ch < 0)]
+        assert np.array_equal(np.sort(leaves), np.arange(order.shape[0]))                 # every leaf position exactly once
+        inner = ch[used & (ch >= 0)]
+        assert np.array_equal(np.sort(inner), np.arange(1, wide.shape[0]))                # every wide node but the root has one parent
+        assert np.all(inner > np.repeat(np.arange(wide.shape[0]), (used & (ch >= 0)).sum(1)))   # pre-order: children after parents
+        assert np.all(ch[~used] == np.iinfo(np.int32).max)
+        # child boxes are the binary nodes' boxes: a leaf child's box is the leaf node's
+        leaf_nodes = nodes[nodes["nPrimitives"] > 0]
+        lb = {int(o): (a.tobytes(), b.tobytes()) for o, a, b in zip(leaf_nodes["offset"], leaf_nodes["bmin"], leaf_nodes["bmax"])}
+        wi, ki = np.nonzero(used & (ch < 0))
+        for w, k in list(zip(wi, ki))[::97]:
+            assert (wide["bmin"][w, k].tobytes(), wide["bmax"][w, k].tobytes()) == lb[int(~ch[w, k])]
+        rng = np.random.default_rng(5)
+        m = 20000
+        tgt = sph[rng.integers(0, sph.shape[0] - 1, m), :3] + rng.normal(size=(m, 3)).astype(np.float32) * np.float32(0.07)
+        d = (tgt / np.linalg.norm(tgt, axis=1, keepdims=True)).astype(np.float32)
+        o = np.zeros((1, 3), np.float32)
+        h2, t2, cand = oracle.trace(sph, nodes, order, o, d, tie_by_objid=tie)
+        h4, t4, tests4 = oracle.trace_wide4(sph, wide, order, o, d, tie_by_objid=tie)
+        assert np.array_equal(h2, h4) and t2.tobytes() == t4.tobytes()
+        assert (h2 >= 0).mean() > 0.5
+        print("%s: %d binary nodes -> %d wide nodes (%.2f children each), %.1f box tests per ray on the wide tree" %
+              (build, nodes.shape[0], wide.shape[0], nc.mean(), tests4 / m))
