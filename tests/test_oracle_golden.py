@@ -185,4 +185,4 @@ def test_packet_model_hits_and_wide_tree_saves_visits(oracle):
     assert np.array_equal(hb.reshape(-1), h_exact) and np.array_equal(hw.reshape(-1), h_exact)
     assert sb["packets"] == sw["packets"] > 0.9 * d.shape[0] and abs(sb["prim_tests"] - sw["prim_tests"]) < 0.01 * sb["prim_tests"]   # pruning order differs
     assert sw["interior_visits"] < 0.66 * sb["interior_visits"] and sw["box_tests"] < 1.1 * sb["box_tests"]
-    assert (h_exact >= 0).mean() > 0.3
+    assert (h_exact >= 0).mean() > 0.2
