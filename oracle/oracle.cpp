@@ -811,7 +811,12 @@ struct Wide4Node {
 };
 static_assert(sizeof(Wide4Node) == 128, "Wide4Node is 128 bytes");
 
-int orc_collapse4(const LinearNode* nodes, int n_nodes, Wide4Node* out, int cap)
+int orc_collapse4_rule(const LinearNode* nodes, int n_nodes, Wide4Node* out, int cap, int rule);
+int orc_collapse4(const LinearNode* nodes, int n_nodes, Wide4Node* out, int cap) { return orc_collapse4_rule(nodes, n_nodes, out, cap, 0); }
+// rule 0: expand the interior entry with the largest surface area (the definition); rule 1 (model experiments only): the first
+// interior entry in list order; rule 2: the interior entry with the most leaves below it (subtree size from the pre-order layout);
+// rule 3: plain two-level collapse (grandchildren), no choice at all
+int orc_collapse4_rule(const LinearNode* nodes, int n_nodes, Wide4Node* out, int cap, int rule)
 {
     if (n_nodes <= 0 || nodes[0].nPrimitives) return 0;      // a single leaf has no interior node to widen
     std::vector<std::pair<int, int>> todo;                   // (binary node, wide index), LIFO with children pushed in reverse = pre-order
@@ -826,11 +831,29 @@ int orc_collapse4(const LinearNode* nodes, int n_nodes, Wide4Node* out, int cap)
             const float dx = nodes[c].bmax[0] - nodes[c].bmin[0], dy = nodes[c].bmax[1] - nodes[c].bmin[1], dz = nodes[c].bmax[2] - nodes[c].bmin[2];
             return 2 * (dx * dy + dx * dz + dy * dz);
         };
-        while (m < 4) {
+        if (rule == 3) {      // model experiment: plain two-level collapse (each child replaced by its own children once)
+            int two[4], k2 = 0;
+            for (int k = 0; k < 2; ++k) {
+                const int c = listed[k];
+                if (nodes[c].nPrimitives) two[k2++] = c; else { two[k2++] = c + 1; two[k2++] = nodes[c].offset; }
+            }
+            for (int k = 0; k < k2; ++k) listed[k] = two[k];
+            m = k2;
+        }
+        while (m < 4 && rule != 3) {
             int pick = -1;
             float best = -1.f;
             for (int k = 0; k < m; ++k)
-                if (!nodes[listed[k]].nPrimitives) { const float a = area(listed[k]); if (a > best) { best = a; pick = k; } }
+                if (!nodes[listed[k]].nPrimitives) {
+                    const int c = listed[k];
+                    // pre-order layout: the subtree of c ends where its right sibling-or-ancestor's right child begins; its size
+                    // is recovered by walking right children down to a leaf
+                    float a;
+                    if (rule == 0) a = area(c);
+                    else if (rule == 1) a = (float)(m - k);
+                    else { int e = c; while (!nodes[e].nPrimitives) e = nodes[e].offset; a = (float)(e - c); }
+                    if (a > best) { best = a; pick = k; }
+                }
             if (pick < 0) break;
             const int c = listed[pick];
             for (int k = m; k > pick + 1; --k) listed[k] = listed[k - 1];
@@ -962,6 +985,8 @@ void orc_packet_model(const float* cxyz_r, int n, const LinearNode* nodes, int n
                       int tie_by_objid, const float* dirs /*packets x 4 x 3*/, int n_packets, int use_wide, int* hit /*packets x 4*/,
                       PacketStats* out)
 {
+    const int order_mode = use_wide >> 4;      // 0: accepted children fully sorted by entry bound; 1: nearest first, the rest in list order
+    use_wide &= 15;
     Scene S{cxyz_r, nullptr, n, nodes, prim_order, n_nodes, tie_by_objid};
     PacketStats st = {0, 0, 0, 0, 0, 0};
     float ex = 0, ey = 0, ez = 0;
@@ -1012,7 +1037,8 @@ void orc_packet_model(const float* cxyz_r, int n, const LinearNode* nodes, int n
                     const int kids[2] = {cur + 1, nodes[cur].offset};
                     for (int k = 0; k < 2; ++k) { float t; ++st.box_tests; if (P.hull(nodes[kids[k]].bmin, nodes[kids[k]].bmax, t)) acc[m++] = Item{kids[k], t}; }
                 }
-                std::stable_sort(acc, acc + m, [](const Item& a, const Item& b) { return a.t < b.t; });
+                if (order_mode == 0) std::stable_sort(acc, acc + m, [](const Item& a, const Item& b) { return a.t < b.t; });
+                else if (m > 1) { int kmin = 0; for (int k = 1; k < m; ++k) if (acc[k].t < acc[kmin].t) kmin = k; std::swap(acc[0], acc[kmin]); }
                 for (int k = m - 1; k >= 1; --k) stack.push_back(acc[k]);          // nearest of the deferred ones on top
                 st.max_stack = std::max<long long>(st.max_stack, (long long)stack.size());
                 if (m) { cur = acc[0].ref; continue; }

@@ -20,8 +20,10 @@ oracle = T.Oracle()
 sph, mat = rt.scene_from_vertices(T.bunny_vertices(), clones, clone_shift=shift)
 t0 = time.time()
 nodes, order, _, _ = oracle.build_lbvh(sph, 30)
-wide = oracle.collapse4(nodes)
-print("LBVH %d nodes -> %d wide nodes (%.2f children each) in %.1f s" % (nodes.shape[0], wide.shape[0], wide["n_children"].mean(), time.time() - t0))
+RULE, ORDER = int(os.environ.get("COLLAPSE_RULE", "0")), int(os.environ.get("ORDER_MODE", "0"))
+wide = oracle.collapse4(nodes, RULE)
+print("LBVH %d nodes -> %d wide nodes (%.2f children each) in %.1f s; collapse rule %d, child order mode %d" %
+      (nodes.shape[0], wide.shape[0], wide["n_children"].mean(), time.time() - t0, RULE, ORDER))
 tot = {False: None, True: None}
 hits_ok = True
 for y in range(step // 2, H, step):
@@ -30,7 +32,7 @@ for y in range(step // 2, H, step):
     # the exact per-ray hits of all four samples (render_rows reports the last sample's hit only)
     h_exact, _, _ = oracle.trace(sph, nodes, order, np.zeros((1, 3), np.float32), d.reshape(-1, 3), tie_by_objid=1)
     for use_wide in (False, True):
-        hit, st = oracle.packet_model(sph, nodes, wide, order, d, use_wide=use_wide)
+        hit, st = oracle.packet_model(sph, nodes, wide, order, d, use_wide=use_wide, order_mode=ORDER)
         hits_ok &= bool(np.array_equal(hit.reshape(-1), h_exact))
         tot[use_wide] = st if tot[use_wide] is None else {k: (max(tot[use_wide][k], v) if k == "max_stack" else tot[use_wide][k] + v) for k, v in st.items()}
 print("model hits == unpruned reference traversal on every sampled ray:", hits_ok)
