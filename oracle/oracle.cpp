@@ -985,7 +985,9 @@ void orc_packet_model(const float* cxyz_r, int n, const LinearNode* nodes, int n
                       int tie_by_objid, const float* dirs /*packets x 4 x 3*/, int n_packets, int use_wide, int* hit /*packets x 4*/,
                       PacketStats* out)
 {
-    const int order_mode = use_wide >> 4;      // 0: accepted children fully sorted by entry bound; 1: nearest first, the rest in list order
+    const int order_mode = (use_wide >> 4) & 15;   // 0: accepted children fully sorted by entry bound; 1: nearest first, the rest in list order
+    const int quant_bits = (use_wide >> 8) & 255;  // > 0 (wide tree only): child boxes quantised OUTWARD to this many bits per plane relative to
+                                                   // the union of the node's child boxes - what a compressed node would hold (conservative)
     use_wide &= 15;
     Scene S{cxyz_r, nullptr, n, nodes, prim_order, n_nodes, tie_by_objid};
     PacketStats st = {0, 0, 0, 0, 0, 0};
@@ -1032,7 +1034,32 @@ void orc_packet_model(const float* cxyz_r, int n, const LinearNode* nodes, int n
                 Item acc[4]; int m = 0;
                 if (use_wide) {
                     const Wide4Node& nd = wide[cur];
-                    for (int k = 0; k < nd.n_children; ++k) { float t; ++st.box_tests; if (P.hull(nd.bmin[k], nd.bmax[k], t)) acc[m++] = Item{nd.child[k], t}; }
+                    float pmin[3], pext[3];
+                    if (quant_bits) {
+                        for (int a = 0; a < 3; ++a) {
+                            float lo = INFINITY, hi = -INFINITY;
+                            for (int k = 0; k < nd.n_children; ++k) { lo = std::min(lo, nd.bmin[k][a]); hi = std::max(hi, nd.bmax[k][a]); }
+                            pmin[a] = lo; pext[a] = hi - lo;
+                        }
+                    }
+                    for (int k = 0; k < nd.n_children; ++k) {
+                        float t, qmin[3], qmax[3];
+                        const float* bmn = nd.bmin[k]; const float* bmx = nd.bmax[k];
+                        if (quant_bits) {
+                            const double levels = (double)((1u << quant_bits) - 1);
+                            for (int a = 0; a < 3; ++a) {
+                                if (pext[a] > 0) {
+                                    const double step = (double)pext[a] / levels;
+                                    qmin[a] = (float)(pmin[a] + std::floor(((double)nd.bmin[k][a] - pmin[a]) / step) * step);
+                                    qmax[a] = (float)(pmin[a] + std::ceil(((double)nd.bmax[k][a] - pmin[a]) / step) * step);
+                                    qmin[a] = std::min(qmin[a], nd.bmin[k][a]); qmax[a] = std::max(qmax[a], nd.bmax[k][a]);   // float rounding: stay outside
+                                } else { qmin[a] = nd.bmin[k][a]; qmax[a] = nd.bmax[k][a]; }
+                            }
+                            bmn = qmin; bmx = qmax;
+                        }
+                        ++st.box_tests;
+                        if (P.hull(bmn, bmx, t)) acc[m++] = Item{nd.child[k], t};
+                    }
                 } else {
                     const int kids[2] = {cur + 1, nodes[cur].offset};
                     for (int k = 0; k < 2; ++k) { float t; ++st.box_tests; if (P.hull(nodes[kids[k]].bmin, nodes[kids[k]].bmax, t)) acc[m++] = Item{kids[k], t}; }
