@@ -939,13 +939,14 @@ struct PacketStats { long long packets, interior_visits, leaf_visits, box_tests,
 namespace {
 struct PacketState {
     const Scene* S;
-    float d[4][3], inv[4][3], ilo[3], ihi[3];
-    float tnear[4]; int best[4], best_key[4];
+    int NR = 4;                     // rays per packet (<= 16)
+    float d[16][3], inv[16][3], ilo[3], ihi[3];
+    float tnear[16]; int best[16], best_key[16];
     float margin, tlim_max;
     void update_tlim()
     {
         tlim_max = -INFINITY;
-        for (int j = 0; j < 4; ++j) { float t = tnear[j] + margin; t = std::fabs(t) * 9.53674316e-7f + t; tlim_max = std::max(tlim_max, t); }
+        for (int j = 0; j < NR; ++j) { float t = tnear[j] + margin; t = std::fabs(t) * 9.53674316e-7f + t; tlim_max = std::max(tlim_max, t); }
     }
     // hull test of one box: lower bound of the entry distances (returned), accept flag
     bool hull(const float* bmin, const float* bmax, float& tmin_lo) const
@@ -966,7 +967,7 @@ struct PacketState {
         const float* s = S->sph + 4 * (size_t)obj;
         const float bmin[3] = {s[0] - s[3], s[1] - s[3], s[2] - s[3]}, bmax[3] = {s[0] + s[3], s[1] + s[3], s[2] + s[3]};
         const float o[3] = {0, 0, 0};
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NR; ++j) {
             if (!slab(o, d[j], bmin, bmax)) continue;              // the reference's own test decides candidacy (leaf-local)
             ++st.prim_tests;
             float t0 = INFINITY, t1 = INFINITY;
@@ -982,12 +983,13 @@ struct PacketState {
 }  // namespace
 
 void orc_packet_model(const float* cxyz_r, int n, const LinearNode* nodes, int n_nodes, const Wide4Node* wide, int n_wide, const int* prim_order,
-                      int tie_by_objid, const float* dirs /*packets x 4 x 3*/, int n_packets, int use_wide, int* hit /*packets x 4*/,
+                      int tie_by_objid, const float* dirs /*packets x NR x 3*/, int n_packets, int use_wide, int* hit /*packets x NR*/,
                       PacketStats* out)
 {
     const int order_mode = (use_wide >> 4) & 15;   // 0: accepted children fully sorted by entry bound; 1: nearest first, the rest in list order
     const int quant_bits = (use_wide >> 8) & 255;  // > 0 (wide tree only): child boxes quantised OUTWARD to this many bits per plane relative to
                                                    // the union of the node's child boxes - what a compressed node would hold (conservative)
+    const int NR = ((use_wide >> 16) & 31) ? ((use_wide >> 16) & 31) : 4;      // rays per packet, default 4, <= 16
     use_wide &= 15;
     Scene S{cxyz_r, nullptr, n, nodes, prim_order, n_nodes, tie_by_objid};
     PacketStats st = {0, 0, 0, 0, 0, 0};
@@ -1001,23 +1003,23 @@ void orc_packet_model(const float* cxyz_r, int n, const LinearNode* nodes, int n
     std::vector<Item> stack;
     for (int p = 0; p < n_packets; ++p) {
         PacketState P;
-        P.S = &S; P.margin = margin;
+        P.S = &S; P.margin = margin; P.NR = NR;
         bool same_oct = true;
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NR; ++j)
             for (int a = 0; a < 3; ++a) {
-                P.d[j][a] = dirs[(size_t)p * 12 + 3 * j + a];
+                P.d[j][a] = dirs[((size_t)p * NR + j) * 3 + a];
                 P.inv[j][a] = 1.0f / P.d[j][a];
                 if ((P.d[j][a] < 0) != (P.d[0][a] < 0)) same_oct = false;
             }
-        for (int j = 0; j < 4; ++j) { P.tnear[j] = INFINITY; P.best[j] = -1; P.best_key[j] = 0; }
+        for (int j = 0; j < NR; ++j) { P.tnear[j] = INFINITY; P.best[j] = -1; P.best_key[j] = 0; }
         if (!same_oct) {      // the kernel traces such pixels ray by ray; leave them out of the counts
-            for (int j = 0; j < 4; ++j) { float t; const float o[3] = {0, 0, 0}; closest_bvh(S, o, P.d[j], hit[4 * p + j], t, nullptr); }
+            for (int j = 0; j < NR; ++j) { float t; const float o[3] = {0, 0, 0}; closest_bvh(S, o, P.d[j], hit[NR * p + j], t, nullptr); }
             continue;
         }
         ++st.packets;
         for (int a = 0; a < 3; ++a) {
-            P.ilo[a] = std::min(std::min(P.inv[0][a], P.inv[1][a]), std::min(P.inv[2][a], P.inv[3][a]));
-            P.ihi[a] = std::max(std::max(P.inv[0][a], P.inv[1][a]), std::max(P.inv[2][a], P.inv[3][a]));
+            P.ilo[a] = P.ihi[a] = P.inv[0][a];
+            for (int j = 1; j < NR; ++j) { P.ilo[a] = std::min(P.ilo[a], P.inv[j][a]); P.ihi[a] = std::max(P.ihi[a], P.inv[j][a]); }
         }
         P.update_tlim();
         stack.clear();
@@ -1078,7 +1080,7 @@ void orc_packet_model(const float* cxyz_r, int n, const LinearNode* nodes, int n
                 break;
             }
         }
-        for (int j = 0; j < 4; ++j) hit[4 * p + j] = P.best[j];
+        for (int j = 0; j < NR; ++j) hit[NR * p + j] = P.best[j];
     }
     if (out) *out = st;
 }

@@ -176,11 +176,13 @@ class Oracle:
     def packet_model(self, sph, nodes, wide, order, dirs, tie_by_objid=1, use_wide=False, order_mode=0, quant_bits=0):
         """CPU model of the ordered packet traversal (counts only; oracle.cpp orc_packet_model). dirs: (packets, 4, 3)."""
         sph = np.ascontiguousarray(sph, np.float32)
-        dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 4, 3)
-        hit = np.zeros((dirs.shape[0], 4), np.int32)
+        dirs = np.ascontiguousarray(dirs, np.float32)
+        nr = dirs.shape[-2] if dirs.ndim == 3 else 4        # rays per packet (<= 16)
+        dirs = dirs.reshape(-1, nr, 3)
+        hit = np.zeros((dirs.shape[0], nr), np.int32)
         st = np.zeros(6, np.int64)
         self.lib.orc_packet_model(self._p(sph), sph.shape[0], self._p(nodes), nodes.shape[0], self._p(wide), wide.shape[0],
-                                  self._p(np.ascontiguousarray(order, np.int32)), tie_by_objid, self._p(dirs), dirs.shape[0], int(use_wide) | (order_mode << 4) | (quant_bits << 8),
+                                  self._p(np.ascontiguousarray(order, np.int32)), tie_by_objid, self._p(dirs), dirs.shape[0], int(use_wide) | (order_mode << 4) | (quant_bits << 8) | (nr << 16),
                                   self._p(hit), self._p(st))
         keys = ("packets", "interior_visits", "leaf_visits", "box_tests", "prim_tests", "max_stack")
         return hit, dict(zip(keys, (int(x) for x in st)))
