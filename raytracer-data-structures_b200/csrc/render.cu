@@ -416,6 +416,81 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
 }
 
 // ===================================================================================================
+// K10, pixel-quad form (OPT-IN, RTDS_QUAD=1; written after the GPU budget of round 1 was spent - compiled, built from the
+// tested packet pieces, NOT yet run on hardware): one thread per 2 x 2 pixels, the k-th samples of the four pixels traced as
+// one packet by traverse_packet<OCT, HULL>. Why: with the hull test an interior visit costs the same for any packet, and the
+// CPU model (tools/packet_size_model.py) shows the union of four neighbouring pixels' paths is ~1.03x
+// one pixel's: 1.64 instead of 5.54 interior visits per ray on the bunny at 1080p, 1 spp. Serves aa_samples that are not a
+// multiple of 4 (those take the sample packets of render_packet_kernel). Per-pixel accumulation stays in sample order.
+// ===================================================================================================
+template <bool HULL>
+__global__ void __launch_bounds__(128, RTDS_PK_MINB) render_quad_kernel(const __grid_constant__ RenderArgs A)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // block = 16 x 8 quads = 32 x 16 pixels, warp = 8 x 4 quads; row-major blocks over the quad grid of this launch's rows
+    const int nqx = (A.width + 1) / 2, nbx = (nqx + 15) / 16;
+    const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
+    const int qx = bx * 16 + (warp & 1) * 8 + (lane & 7);
+    const int qrow = by * 8 + (warp >> 1) * 4 + (lane >> 3);           // quad row inside [lrow0, local_rows)
+    const int lrow_top = A.lrow0 + 2 * qrow;
+    Counters cnt = {0, 0, 0, 0};
+    if (qx < nqx && lrow_top < A.local_rows) {
+        const float margin = prune_margin(A.bvh.root_box, 0.f, 0.f, 0.f);
+        // the quad's pixels: j = 0..3 -> (2 qx + (j & 1), lrow_top + (j >> 1)); pixels outside the frame are traced as copies
+        // of pixel 0 and dropped
+        bool valid[PK];
+        size_t pix[PK];
+        int px[PK], lrow[PK];
+#pragma unroll
+        for (int j = 0; j < PK; ++j) {
+            px[j] = 2 * qx + (j & 1);
+            lrow[j] = lrow_top + (j >> 1);
+            valid[j] = px[j] < A.width && lrow[j] < A.local_rows;
+            const int pj = valid[j] ? j : 0;
+            pix[j] = (size_t)global_row_of(A, lrow_top + (pj >> 1)) * A.width + (2 * qx + (pj & 1));
+        }
+        float acc_r[PK] = {0, 0, 0, 0}, acc_g[PK] = {0, 0, 0, 0}, acc_b[PK] = {0, 0, 0, 0};
+        int last_hit[PK] = {-1, -1, -1, -1};
+        for (int k = 0; k < A.spp; ++k) {
+            float dx[PK], dy[PK], dz[PK], tnear[PK];
+            int best_leaf[PK];
+#pragma unroll
+            for (int j = 0; j < PK; ++j) {
+                const float* dp = A.dirs + 3 * (pix[j] * A.spp + k);      // main.cpp:554-557, from mt_expand_dirs_kernel
+                dx[j] = __ldg(dp); dy[j] = __ldg(dp + 1); dz[j] = __ldg(dp + 2);
+                cnt.rays += valid[j] ? 1u : 0u;
+            }
+            trace_packet4<HULL>(A, dx, dy, dz, margin, tnear, best_leaf, cnt);
+#pragma unroll
+            for (int j = 0; j < PK; ++j) {
+                const ShadedRay sh = shade_packet_ray_ool(&A, dx[j], dy[j], dz[j], tnear[j], best_leaf[j]);
+                acc_r[j] += sh.r; acc_g[j] += sh.g; acc_b[j] += sh.b;       // sample order per pixel, main.cpp:553-560
+                last_hit[j] = sh.hit;
+            }
+        }
+        const float fs = (float)(unsigned)A.spp;
+#pragma unroll
+        for (int j = 0; j < PK; ++j) {
+            if (!valid[j]) continue;
+            const size_t o_loc = (size_t)lrow[j] * A.width + px[j];
+            const size_t o = (size_t)(A.out_global_rows ? global_row_of(A, lrow[j]) : lrow[j]) * A.width + px[j];
+            A.out_rgb[3 * o] = (unsigned char)(fminf(1.0f, acc_r[j] / fs) * 255);
+            A.out_rgb[3 * o + 1] = (unsigned char)(fminf(1.0f, acc_g[j] / fs) * 255);
+            A.out_rgb[3 * o + 2] = (unsigned char)(fminf(1.0f, acc_b[j] / fs) * 255);
+            if (A.out_hit) A.out_hit[o_loc] = last_hit[j];
+            if (A.out_accum) { A.out_accum[3 * o_loc] = acc_r[j]; A.out_accum[3 * o_loc + 1] = acc_g[j]; A.out_accum[3 * o_loc + 2] = acc_b[j]; }
+        }
+    }
+    unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned long long x = v[c];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(&A.counters[c], x);
+    }
+}
+
+// ===================================================================================================
 // K10 + K11 fused ("strip" kernel): one block per MT19937 snapshot chunk (8 regenerations = 4,992 words = 1,248
 // samples). The block regenerates its chunk of the reference's jitter stream into SHARED memory (plus one more
 // regeneration for a pixel whose samples straddle the chunk end) and renders the pixels whose first sample lies in
@@ -1114,6 +1189,10 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             // interior boxes tested once per packet against the hull of the four reciprocal directions (default; RTDS_HULL=0:
             // once per ray). Bench frame: same frame, node visits 3.17 -> 3.18 per ray, kernel 1.16 -> 0.99 ms.
             const bool hull = getenv("RTDS_HULL") ? atoi(getenv("RTDS_HULL")) != 0 : true;
+            // opt-in (RTDS_QUAD=1): packets of 2 x 2 neighbouring pixels for aa_samples that are not a multiple of 4; band rows are
+            // multiples of 8 and tile_rows even, so a quad's two rows lie in the same band and the same scanline tile
+            const bool quad = !full && !packet && !kdt && !brute && !p->exact && A.bvh.leaf_box_prim && (tile_rows % 2) == 0 && (r0 % 2) == 0 &&
+                              getenv("RTDS_QUAD") && atoi(getenv("RTDS_QUAD")) == 1;
             if (packet && full) { if (hull) render_packet_kernel<true, true><<<lin, block, 0, s>>>(A); else render_packet_kernel<true, false><<<lin, block, 0, s>>>(A); }
             else if (full) {
                 if (brute) render_full_kernel<2><<<lin, block, 0, s>>>(A);
@@ -1121,6 +1200,10 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
                 else render_full_kernel<1><<<lin, block, 0, s>>>(A);
             }
             else if (packet) { if (hull) render_packet_kernel<false, true><<<lin, block, 0, s>>>(A); else render_packet_kernel<false, false><<<lin, block, 0, s>>>(A); }
+            else if (quad) {
+                const unsigned qlin = (unsigned)(((W + 1) / 2 + 15) / 16) * (unsigned)((((r1 - r0) + 1) / 2 + 7) / 8);
+                if (hull) render_quad_kernel<true><<<qlin, block, 0, s>>>(A); else render_quad_kernel<false><<<qlin, block, 0, s>>>(A);
+            }
             else if (kd_closest) render_kernel<4><<<lin, block, 0, s>>>(A);
             else if (kdt) render_kernel<3><<<lin, block, 0, s>>>(A);
             else if (brute) render_kernel<2><<<lin, block, 0, s>>>(A);

@@ -1,6 +1,7 @@
 """GPU parity: jitter stream, traversal + ray/sphere test (rtds_trace), and the whole render path — against the
 oracle port, the golden vectors of the unmodified reference, and (size-independent) cross-mode properties."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -213,3 +214,23 @@ def test_visible_clones_variant_packet_equals_reference_traversal(gpu_ctx, oracl
     sh, _, _, st_s = gpu_ctx.render(rt.LBVH, W, H, spp, shadows=1)
     sh_e, _, _, _ = gpu_ctx.render(rt.LBVH, W, H, spp, shadows=1, exact=True)
     assert np.array_equal(sh, sh_e) and st_s["shadow_rays"] > 0
+
+
+@pytest.mark.skipif(not os.environ.get("RTDS_TEST_EXPERIMENTAL"), reason="opt-in kernel written after round 1's GPU budget was spent: "
+                    "set RTDS_TEST_EXPERIMENTAL=1 to run it (first thing to do in the next round)")
+@pytest.mark.parametrize("W,H,spp", [(640, 480, 1), (401, 299, 1), (322, 203, 3), (400, 300, 2)])
+def test_quad_packets_equal_single_ray(gpu_ctx, oracle, monkeypatch, W, H, spp):
+    """RTDS_QUAD=1: packets of 2x2 neighbouring pixels (render_quad_kernel) must give the single-ray kernel's hit ids, sums and
+    bytes, ragged frames and a rank's interleaved tiles included."""
+    sph, mat = T.bunny_scene()
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+    ref = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True)
+    ref_r1 = gpu_ctx.render(rt.LBVH, W, H, spp, rank=1, world=3)
+    monkeypatch.setenv("RTDS_QUAD", "1")
+    quad = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True)
+    quad_r1 = gpu_ctx.render(rt.LBVH, W, H, spp, rank=1, world=3)
+    assert np.array_equal(quad[1], ref[1]) and quad[2].tobytes() == ref[2].tobytes() and np.array_equal(quad[0], ref[0])
+    rows = rt.owned_rows(H, 8, 1, 3)
+    assert np.array_equal(quad_r1[0][rows], ref_r1[0][rows])
+    assert quad[3]["primary_rays"] == W * H * spp and quad[3]["node_visits"] < 0.6 * ref[3]["node_visits"]
