@@ -416,8 +416,7 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
 }
 
 // ===================================================================================================
-// K10, pixel-quad form (OPT-IN, RTDS_QUAD=1; written after the GPU budget of round 1 was spent - compiled, built from the
-// tested packet pieces, NOT yet run on hardware): one thread per 2 x 2 pixels, the k-th samples of the four pixels traced as
+// K10, pixel-quad form (OPT-IN, RTDS_QUAD=1: parity-tested on the B200, speed not measured yet): one thread per 2 x 2 pixels, the k-th samples of the four pixels traced as
 // one packet by traverse_packet<OCT, HULL>. Why: with the hull test an interior visit costs the same for any packet, and the
 // CPU model (tools/packet_size_model.py) shows the union of four neighbouring pixels' paths is ~1.03x
 // one pixel's: 1.64 instead of 5.54 interior visits per ray on the bunny at 1080p, 1 spp. Serves aa_samples that are not a

@@ -216,8 +216,6 @@ def test_visible_clones_variant_packet_equals_reference_traversal(gpu_ctx, oracl
     assert np.array_equal(sh, sh_e) and st_s["shadow_rays"] > 0
 
 
-@pytest.mark.skipif(not os.environ.get("RTDS_TEST_EXPERIMENTAL"), reason="opt-in kernel written after round 1's GPU budget was spent: "
-                    "set RTDS_TEST_EXPERIMENTAL=1 to run it (first thing to do in the next round)")
 @pytest.mark.parametrize("W,H,spp", [(640, 480, 1), (401, 299, 1), (322, 203, 3), (400, 300, 2)])
 def test_quad_packets_equal_single_ray(gpu_ctx, oracle, monkeypatch, W, H, spp):
     """RTDS_QUAD=1: packets of 2x2 neighbouring pixels (render_quad_kernel) must give the single-ray kernel's hit ids, sums and
