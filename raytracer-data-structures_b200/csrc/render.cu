@@ -416,6 +416,118 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
 }
 
 // ===================================================================================================
+// K10, two-pixel packet form (OPT-IN, RTDS_PACKET2=1; finished after round 1's GPU budget was spent: compiles, NOT yet run on
+// hardware, its parity test is skipped unless RTDS_TEST_EXPERIMENTAL=1): one thread per TWO horizontally adjacent pixels, the
+// samples k0..k0+3 of both pixels traced as one 8-ray packet by traverse_packet_n<OCT, 8>. The CPU model
+// (tools/packet_size_model.py) gives 1.58 instead of 3.11 interior visits per ray on the bench frame.
+// ===================================================================================================
+constexpr int PK2 = 2 * PK;
+#ifndef RTDS_PK2_MINB
+#define RTDS_PK2_MINB 4
+#endif
+__device__ __forceinline__ void trace_packet8(const RenderArgs& A, const float (&dx)[PK2], const float (&dy)[PK2], const float (&dz)[PK2],
+                                              float margin, float (&tnear)[PK2], int (&best_leaf)[PK2], Counters& cnt)
+{
+    int best_key[PK2];
+    bool ok = A.bvh.root_ref >= 0;
+    int oct0 = 0;
+    float ixlo = INFINITY, ixhi = -INFINITY, iylo = INFINITY, iyhi = -INFINITY, izlo = INFINITY, izhi = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < PK2; ++j) {
+        float ix, iy, iz;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"(dx[j]));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(dy[j]));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(dz[j]));
+        const float amin = fminf(fminf(fabsf(ix), fabsf(iy)), fabsf(iz));
+        const float amax = fmaxf(fmaxf(fabsf(ix), fabsf(iy)), fabsf(iz));
+        const int oct = (dx[j] < 0 ? 1 : 0) | (dy[j] < 0 ? 2 : 0) | 4;
+        if (j == 0) oct0 = oct;
+        ok = ok && amin > 1e-30f && amax < 1e30f && oct == oct0;
+        ixlo = fminf(ixlo, ix); ixhi = fmaxf(ixhi, ix);
+        iylo = fminf(iylo, iy); iyhi = fmaxf(iyhi, iy);
+        izlo = fminf(izlo, iz); izhi = fmaxf(izhi, iz);
+        tnear[j] = INFINITY; best_key[j] = 0; best_leaf[j] = -1;
+    }
+    if (ok) {
+        switch (oct0) {
+            case 4: traverse_packet_n<4, PK2>(A.bvh, dx, dy, dz, ixlo, ixhi, iylo, iyhi, izlo, izhi, margin, tnear, best_key, best_leaf, cnt); break;
+            case 5: traverse_packet_n<5, PK2>(A.bvh, dx, dy, dz, ixlo, ixhi, iylo, iyhi, izlo, izhi, margin, tnear, best_key, best_leaf, cnt); break;
+            case 6: traverse_packet_n<6, PK2>(A.bvh, dx, dy, dz, ixlo, ixhi, iylo, iyhi, izlo, izhi, margin, tnear, best_key, best_leaf, cnt); break;
+            default: traverse_packet_n<7, PK2>(A.bvh, dx, dy, dz, ixlo, ixhi, iylo, iyhi, izlo, izhi, margin, tnear, best_key, best_leaf, cnt); break;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < PK2; ++j) {
+            const ColdHit h = trace_primary_cold(&A.bvh, dx[j], dy[j], dz[j]);
+            tnear[j] = h.tnear; best_leaf[j] = h.leaf;
+            cnt.node_tests += h.node_tests; cnt.prim_tests += h.prim_tests; cnt.node_visits += h.node_visits;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128, RTDS_PK2_MINB) render_packet2_kernel(const __grid_constant__ RenderArgs A)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // thread = 2 x 1 pixels; block = 16 x 8 threads = 32 x 8 pixels, warp = 8 x 4 threads; row-major blocks over this launch's rows
+    const int ntx = (A.width + 1) / 2, nbx = (ntx + 15) / 16;
+    const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
+    const int tx = bx * 16 + (warp & 1) * 8 + (lane & 7);
+    const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
+    Counters cnt = {0, 0, 0, 0};
+    if (tx < ntx && lrow < A.local_rows) {
+        const float margin = prune_margin(A.bvh.root_box, 0.f, 0.f, 0.f);
+        const int px0 = 2 * tx;
+        const bool two = px0 + 1 < A.width;                       // odd widths: the last thread of a row has one pixel (traced twice)
+        const int py = global_row_of(A, lrow);
+        const size_t pixA = (size_t)py * A.width + px0, pixB = pixA + (two ? 1 : 0);
+        float accA[3] = {0, 0, 0}, accB[3] = {0, 0, 0};
+        int lastA = -1, lastB = -1;
+        for (int k0 = 0; k0 < A.spp; k0 += PK) {
+            float dx[PK2], dy[PK2], dz[PK2], tnear[PK2];
+            int best_leaf[PK2];
+            // each pixel's 4 directions are 48 contiguous, 16-byte aligned bytes (aa_samples % 4 == 0)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float4* dp = reinterpret_cast<const float4*>(A.dirs + 3 * ((h ? pixB : pixA) * A.spp + k0));
+                const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+                const int o = 4 * h;
+                dx[o] = d0.x; dy[o] = d0.y; dz[o] = d0.z; dx[o + 1] = d0.w; dy[o + 1] = d1.x; dz[o + 1] = d1.y;
+                dx[o + 2] = d1.z; dy[o + 2] = d1.w; dz[o + 2] = d2.x; dx[o + 3] = d2.y; dy[o + 3] = d2.z; dz[o + 3] = d2.w;
+            }
+            cnt.rays += two ? PK2 : PK;
+            trace_packet8(A, dx, dy, dz, margin, tnear, best_leaf, cnt);
+#pragma unroll
+            for (int j = 0; j < PK2; ++j) {
+                const ShadedRay sh = shade_packet_ray_ool(&A, dx[j], dy[j], dz[j], tnear[j], best_leaf[j]);
+                if (j < PK) { accA[0] += sh.r; accA[1] += sh.g; accA[2] += sh.b; lastA = sh.hit; }      // sample order per pixel
+                else { accB[0] += sh.r; accB[1] += sh.g; accB[2] += sh.b; lastB = sh.hit; }
+            }
+        }
+        const float fs = (float)(unsigned)A.spp;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const float* acc = h ? accB : accA;
+            const int px = px0 + h;
+            const size_t o_loc = (size_t)lrow * A.width + px;
+            const size_t o = (size_t)(A.out_global_rows ? py : lrow) * A.width + px;
+            A.out_rgb[3 * o] = (unsigned char)(fminf(1.0f, acc[0] / fs) * 255);
+            A.out_rgb[3 * o + 1] = (unsigned char)(fminf(1.0f, acc[1] / fs) * 255);
+            A.out_rgb[3 * o + 2] = (unsigned char)(fminf(1.0f, acc[2] / fs) * 255);
+            if (A.out_hit) A.out_hit[o_loc] = h ? lastB : lastA;
+            if (A.out_accum) { A.out_accum[3 * o_loc] = acc[0]; A.out_accum[3 * o_loc + 1] = acc[1]; A.out_accum[3 * o_loc + 2] = acc[2]; }
+        }
+    }
+    unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned long long x = v[c];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(&A.counters[c], x);
+    }
+}
+
+// ===================================================================================================
 // K10, pixel-quad form (OPT-IN, RTDS_QUAD=1: parity-tested on the B200, speed not measured yet): one thread per 2 x 2 pixels, the k-th samples of the four pixels traced as
 // one packet by traverse_packet<OCT, HULL>. Why: with the hull test an interior visit costs the same for any packet, and the
 // CPU model (tools/packet_size_model.py) shows the union of four neighbouring pixels' paths is ~1.03x
@@ -1197,6 +1309,10 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
                 if (brute) render_full_kernel<2><<<lin, block, 0, s>>>(A);
                 else if (p->exact) render_full_kernel<0><<<lin, block, 0, s>>>(A);
                 else render_full_kernel<1><<<lin, block, 0, s>>>(A);
+            }
+            else if (packet && hull && getenv("RTDS_PACKET2") && atoi(getenv("RTDS_PACKET2")) == 1) {      // opt-in: 2 pixels x 4 samples per thread
+                const unsigned plin = (unsigned)(((W + 1) / 2 + 15) / 16) * (unsigned)((r1 - r0 + 7) / 8);
+                render_packet2_kernel<<<plin, block, 0, s>>>(A);
             }
             else if (packet) { if (hull) render_packet_kernel<false, true><<<lin, block, 0, s>>>(A); else render_packet_kernel<false, false><<<lin, block, 0, s>>>(A); }
             else if (quad) {

@@ -232,3 +232,23 @@ def test_quad_packets_equal_single_ray(gpu_ctx, oracle, monkeypatch, W, H, spp):
     rows = rt.owned_rows(H, 8, 1, 3)
     assert np.array_equal(quad_r1[0][rows], ref_r1[0][rows])
     assert quad[3]["primary_rays"] == W * H * spp and quad[3]["node_visits"] < 0.6 * ref[3]["node_visits"]
+
+
+@pytest.mark.skipif(not os.environ.get("RTDS_TEST_EXPERIMENTAL"), reason="opt-in kernel finished after round 1's GPU budget was spent (compiled, "
+                    "never run on hardware): RTDS_TEST_EXPERIMENTAL=1 runs it - the first thing to do in the next round")
+@pytest.mark.parametrize("W,H,spp", [(640, 480, 4), (401, 299, 4), (322, 203, 8)])
+def test_two_pixel_packets_equal_sample_packets(gpu_ctx, monkeypatch, W, H, spp):
+    """RTDS_PACKET2=1: 8-ray packets (2 adjacent pixels x 4 samples, render_packet2_kernel / traverse_packet_n) must give the
+    4-ray sample-packet kernel's hit ids, sums and bytes; odd widths and a rank's interleaved tiles included."""
+    sph, mat = T.bunny_scene()
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+    ref = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True)
+    ref_r1 = gpu_ctx.render(rt.LBVH, W, H, spp, rank=1, world=3)
+    monkeypatch.setenv("RTDS_PACKET2", "1")
+    two = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True)
+    two_r1 = gpu_ctx.render(rt.LBVH, W, H, spp, rank=1, world=3)
+    assert np.array_equal(two[1], ref[1]) and two[2].tobytes() == ref[2].tobytes() and np.array_equal(two[0], ref[0])
+    rows = rt.owned_rows(H, 8, 1, 3)
+    assert np.array_equal(two_r1[0][rows], ref_r1[0][rows])
+    assert two[3]["primary_rays"] == W * H * spp and two[3]["node_visits"] < 0.7 * ref[3]["node_visits"]
