@@ -91,7 +91,7 @@ ABI_SYMBOLS = ["rtds_last_error", "rtds_version", "rtds_create", "rtds_destroy",
                "rtds_export_morton", "rtds_trace", "rtds_render", "rtds_render_device", "rtds_rows_for_rank",
                "rtds_jitter_stream", "rtds_morton30", "rtds_frame", "rtds_shared_frame_create", "rtds_shared_frame_open",
                "rtds_shared_frame_attach", "rtds_render_shared", "rtds_frame_shared", "rtds_shared_frame_ptr", "rtds_shared_frame_read",
-               "rtds_shared_frame_close"]
+               "rtds_shared_frame_close", "rtds_set_option", "rtds_get_option"]
 
 _lib = None
 
@@ -134,6 +134,8 @@ def load_library(path: str = LIB_PATH):
     lib.rtds_shared_frame_ptr.argtypes = [vp, C.POINTER(vp)]
     lib.rtds_shared_frame_read.argtypes = [vp, vp]
     lib.rtds_shared_frame_close.argtypes = [vp]
+    lib.rtds_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.rtds_get_option.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int)]
     _lib = lib
     return lib
 
@@ -169,6 +171,15 @@ class Rtds:
             self.close()
         except Exception:
             pass
+
+    def set_option(self, name, value):
+        """Tuning / test switch of this context (rtds_set_option); defaults come from RTDS_<NAME>, read once at creation."""
+        self._check(self.lib.rtds_set_option(self.ctx, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = C.c_int()
+        self._check(self.lib.rtds_get_option(self.ctx, name.encode(), C.byref(v)))
+        return v.value
 
     # -- scene ---------------------------------------------------------------------------------
     def set_spheres(self, cxyz_r, rgb_mat=None):

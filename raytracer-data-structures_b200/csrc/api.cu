@@ -8,7 +8,18 @@
 #include <string.h>
 
 static thread_local char g_err[1024] = "";
-cudaEvent_t g_rtds_trace_ev[8] = {};
+
+// name <-> environment variable <-> field of RtdsOptions (rtds_set_option / rtds_get_option; defaults read once in rtds_create)
+const RtdsOptionName g_rtds_option_names[] = {
+    {"block_order", "RTDS_BLOCK_ORDER", &RtdsOptions::block_order}, {"strip", "RTDS_STRIP", &RtdsOptions::strip},
+    {"bands", "RTDS_BANDS", &RtdsOptions::bands}, {"band_ratio", "RTDS_BAND_RATIO", &RtdsOptions::band_ratio},
+    {"packet", "RTDS_PACKET", &RtdsOptions::packet}, {"hull", "RTDS_HULL", &RtdsOptions::hull},
+    {"zerocopy", "RTDS_ZEROCOPY", &RtdsOptions::zerocopy}, {"trace_frame", "RTDS_TRACE_FRAME", &RtdsOptions::trace_frame},
+    {"median_small", "RTDS_MEDIAN_SMALL", &RtdsOptions::median_small}, {"median_coop", "RTDS_MEDIAN_COOP", &RtdsOptions::median_coop},
+    {"median_debug", "RTDS_MEDIAN_DEBUG", &RtdsOptions::median_debug}, {"node_preorder", "RTDS_NODE_PREORDER", &RtdsOptions::node_preorder},
+    {"l2_prefetch", "RTDS_L2_PREFETCH", &RtdsOptions::l2_prefetch}, {"frame_graph", "RTDS_FRAME_GRAPH", &RtdsOptions::frame_graph},
+};
+const int g_rtds_n_option_names = (int)(sizeof g_rtds_option_names / sizeof g_rtds_option_names[0]);
 
 static __global__ void zero_words_kernel(uint32_t* __restrict__ p, size_t n_words)
 {
@@ -144,6 +155,24 @@ __global__ void material_flag_kernel(const float4* __restrict__ mat, int n, int*
     if (__any_sync(0xffffffffu, f) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
+extern "C" int rtds_destroy(rtds_ctx* c);
+static int create_resources(rtds_ctx* c)
+{
+    RTDS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    RTDS_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_band, cudaEventDisableTiming));
+    RTDS_CUDA(cudaStreamCreateWithFlags(&c->jit_stream, cudaStreamNonBlocking));
+    RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_dirs, cudaEventDisableTiming));
+    RTDS_CUDA(cudaEventCreate(&c->ev0)); RTDS_CUDA(cudaEventCreate(&c->ev1));
+    RTDS_CUDA(cudaEventCreate(&c->ev2)); RTDS_CUDA(cudaEventCreate(&c->ev3));
+    RTDS_CUDA(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8));
+    RTDS_CUDA(cudaMallocHost(&c->h_counters, sizeof(unsigned long long) * 16));    // [8..15]: material flag read-back
+    // main.cpp:775: Sphere light2(0, (0,3,30), 10, (1,1,1), 0, 0, emission (1,1,1))
+    c->n_lights = 1;
+    c->lights[0] = RtdsLight{{0.f, 3.f, 30.f}, 10.f, {1.f, 1.f, 1.f}};
+    return RTDS_OK;
+}
+
 extern "C" {
 
 const char* rtds_last_error(void) { return g_err; }
@@ -169,19 +198,13 @@ int rtds_create(rtds_ctx** out, int device)
     }
     rtds_ctx* c = new rtds_ctx();
     c->device = device;
+    // the RTDS_* switches are read here, once per context, never on a frame's path
+    for (int i = 0; i < g_rtds_n_option_names; ++i)
+        if (const char* e = getenv(g_rtds_option_names[i].env)) c->opt.*(g_rtds_option_names[i].field) = atoi(e);
+    if (const char* e = getenv("RTDS_NODE_ORDER")) c->opt.node_preorder = !strcmp(e, "preorder");
     c->sm_count = prop.multiProcessorCount;
-    RTDS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    RTDS_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_band, cudaEventDisableTiming));
-    RTDS_CUDA(cudaStreamCreateWithFlags(&c->jit_stream, cudaStreamNonBlocking));
-    RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_dirs, cudaEventDisableTiming));
-    RTDS_CUDA(cudaEventCreate(&c->ev0)); RTDS_CUDA(cudaEventCreate(&c->ev1));
-    RTDS_CUDA(cudaEventCreate(&c->ev2)); RTDS_CUDA(cudaEventCreate(&c->ev3));
-    RTDS_CUDA(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8));
-    RTDS_CUDA(cudaMallocHost(&c->h_counters, sizeof(unsigned long long) * 16));    // [8..15]: material flag read-back
-    // main.cpp:775: Sphere light2(0, (0,3,30), 10, (1,1,1), 0, 0, emission (1,1,1))
-    c->n_lights = 1;
-    c->lights[0] = RtdsLight{{0.f, 3.f, 30.f}, 10.f, {1.f, 1.f, 1.f}};
+    const int rc = create_resources(c);
+    if (rc != RTDS_OK) { rtds_destroy(c); return rc; }      // rtds_destroy copes with a partially built context
     *out = c;
     return RTDS_OK;
 }
@@ -190,24 +213,23 @@ int rtds_destroy(rtds_ctx* c)
 {
     if (!c) return RTDS_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     rtds_free_bvh(c->bvh);
     rtds_free_kd(c->kd);
     void* bufs[] = {c->d_sph, c->d_mat, c->d_tris, c->d_keys_sorted, c->d_mt_snap, c->d_jitter, c->d_dirs, c->d_scratch,
                     c->d_sort_ws, c->d_frame, c->d_hit, c->d_accum, c->d_counters};
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
-    cudaStreamDestroy(c->stream);
+    for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->ev3, c->ev_band, c->ev_dirs}) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
     shared_frame_drop(c);
     if (c->h_counters) cudaFreeHost(c->h_counters);
-    cudaStreamDestroy(c->copy_stream);
-    cudaEventDestroy(c->ev_band);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int k = 0; k < RTDS_MAX_BANDS; ++k) if (c->band_streams[k]) cudaStreamDestroy(c->band_streams[k]);
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
     for (int k = 0; k < RTDS_MAX_BANDS; ++k) if (c->ev_bands[k]) cudaEventDestroy(c->ev_bands[k]);
-    cudaStreamDestroy(c->jit_stream);
-    cudaEventDestroy(c->ev_dirs);
+    if (c->jit_stream) cudaStreamDestroy(c->jit_stream);
+    for (auto& e : c->trace_ev) if (e) cudaEventDestroy(e);
     delete c;
     return RTDS_OK;
 }
@@ -254,7 +276,7 @@ static int upload_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat
         material_flag_kernel<<<(n + 255) / 256, 256, 0, ms>>>(c->d_mat, n, d_flag);
         // the flag comes back into pinned memory behind the kernel: finish_materials() only has to wait for the stream
         RTDS_CUDA(cudaMemcpyAsync(c->h_counters + 8, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ms));
-        if (g_rtds_trace_ev[0]) RTDS_CUDA(cudaEventRecord(g_rtds_trace_ev[3], ms));
+        RTDS_TRACE_RECORD(c, 3, ms);
         c->materials_pending = true;
         if (!async_mat) RTDS_TRY(rtds_finish_materials(c));
     } else {
@@ -298,9 +320,12 @@ int rtds_frame(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n, in
     // scene uploads and the structure is built
     RTDS_CUDA(cudaSetDevice(c->device));
     // RTDS_TRACE_FRAME=1: host-clock timeline of the call's stages on stderr (profiling aid)
-    static const bool trace = getenv("RTDS_TRACE_FRAME") && atoi(getenv("RTDS_TRACE_FRAME")) != 0;
-    if (trace && !g_rtds_trace_ev[0]) for (auto& e : g_rtds_trace_ev) RTDS_CUDA(cudaEventCreate(&e));
-    if (trace) RTDS_CUDA(cudaEventRecord(g_rtds_trace_ev[0], c->stream));
+    const bool trace = c->opt.trace_frame != 0;
+    if (trace && !c->trace_ev[0]) {
+        for (auto& e : c->trace_ev) if (cudaEventCreate(&e) != cudaSuccess) e = nullptr;
+        if (!c->trace_ev[7]) { for (auto& e : c->trace_ev) { if (e) cudaEventDestroy(e); e = nullptr; } (void)cudaGetLastError(); }
+    }
+    RTDS_TRACE_RECORD(c, 0, c->stream);
     const auto t0 = std::chrono::steady_clock::now();
     auto us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
     RTDS_TRY(rtds_prefetch_dirs(c, rp));
@@ -312,18 +337,18 @@ int rtds_frame(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n, in
     RTDS_TRY(rtds_finish_materials(c));
     const double t_mat = us();
     const int rc = rtds_render(c, acc, rp, rgb, nullptr, nullptr, rst);
-    if (trace && rc == RTDS_OK) {
+    if (trace && rc == RTDS_OK && c->trace_ev[0]) {
         cudaDeviceSynchronize();
         float d0 = 0, d1 = 0, b0 = 0, b1 = 0, m1 = 0, r0 = 0, r1 = 0;
-        cudaEventElapsedTime(&d0, g_rtds_trace_ev[0], g_rtds_trace_ev[1]); cudaEventElapsedTime(&d1, g_rtds_trace_ev[0], g_rtds_trace_ev[2]);
-        cudaEventElapsedTime(&b0, g_rtds_trace_ev[0], g_rtds_trace_ev[4]); cudaEventElapsedTime(&b1, g_rtds_trace_ev[0], g_rtds_trace_ev[5]);
-        cudaEventElapsedTime(&m1, g_rtds_trace_ev[0], g_rtds_trace_ev[3]);
-        cudaEventElapsedTime(&r0, g_rtds_trace_ev[0], c->ev2); cudaEventElapsedTime(&r1, g_rtds_trace_ev[0], c->ev3);
+        cudaEventElapsedTime(&d0, c->trace_ev[0], c->trace_ev[1]); cudaEventElapsedTime(&d1, c->trace_ev[0], c->trace_ev[2]);
+        cudaEventElapsedTime(&b0, c->trace_ev[0], c->trace_ev[4]); cudaEventElapsedTime(&b1, c->trace_ev[0], c->trace_ev[5]);
+        cudaEventElapsedTime(&m1, c->trace_ev[0], c->trace_ev[3]);
+        cudaEventElapsedTime(&r0, c->trace_ev[0], c->ev2); cudaEventElapsedTime(&r1, c->trace_ev[0], c->ev3);
         float c1 = 0;
-        cudaEventElapsedTime(&c1, g_rtds_trace_ev[0], g_rtds_trace_ev[6]);
-        if (c->ev_bands[0] && atoi(getenv("RTDS_TRACE_FRAME")) > 1) {
+        cudaEventElapsedTime(&c1, c->trace_ev[0], c->trace_ev[6]);
+        if (c->ev_bands[0] && c->opt.trace_frame > 1) {
             fprintf(stderr, "[rtds_frame device] bands end at");
-            for (int k = 0; k < RTDS_MAX_BANDS; ++k) { float e = 0; if (cudaEventElapsedTime(&e, g_rtds_trace_ev[0], c->ev_bands[k]) == cudaSuccess && e > 0) fprintf(stderr, " %.0f", 1e3 * e); }
+            for (int k = 0; k < RTDS_MAX_BANDS; ++k) { float e = 0; if (cudaEventElapsedTime(&e, c->trace_ev[0], c->ev_bands[k]) == cudaSuccess && e > 0) fprintf(stderr, " %.0f", 1e3 * e); }
             fprintf(stderr, " us\n");
             cudaGetLastError();
         }
@@ -511,7 +536,7 @@ int rtds_render(rtds_ctx* c, int acc, const rtds_render_params* p, uint8_t* rgb,
     // kernel stores its RGB8 tiles straight into it over PCIe (mapped memory) - no bands, no device->host copy afterwards.
     // Frame identical, but the 8-byte posted writes reach only ~17 GB/s and throttle the kernel: 1.09 -> 1.48 ms, e2e 2.34 vs
     // 2.12 ms with the banded copies.
-    if (world == 1 && !hit_obj && !accum && getenv("RTDS_ZEROCOPY") && atoi(getenv("RTDS_ZEROCOPY")) == 1) {
+    if (world == 1 && !hit_obj && !accum && c->opt.zerocopy == 1) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, rgb) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
             RTDS_TRY(rtds_render_impl(c, acc, p, (uint8_t*)at.devicePointer, nullptr, nullptr, st, nullptr, false));
@@ -531,7 +556,7 @@ int rtds_render(rtds_ctx* c, int acc, const rtds_render_params* p, uint8_t* rgb,
             return RTDS_OK;
         };
         RTDS_TRY(rtds_render_impl(c, acc, p, c->d_frame, hit_obj ? c->d_hit : nullptr, accum ? c->d_accum : nullptr, st, &on_band));
-        if (g_rtds_trace_ev[0]) RTDS_CUDA(cudaEventRecord(g_rtds_trace_ev[6], c->copy_stream));
+        RTDS_TRACE_RECORD(c, 6, c->copy_stream);
         RTDS_CUDA(cudaStreamSynchronize(s));
         RTDS_CUDA(cudaStreamSynchronize(c->copy_stream));
         return RTDS_OK;
@@ -690,6 +715,24 @@ int rtds_jitter_stream(rtds_ctx* c, uint64_t first, int n, double* out)
     if (!c || !out || n < 0) { rtds_set_error("jitter_stream: bad arguments"); return RTDS_ERR_INVALID; }
     RTDS_CUDA(cudaSetDevice(c->device));
     return rtds_jitter_stream_impl(c, first, n, out);
+}
+
+int rtds_set_option(rtds_ctx* c, const char* name, int value)
+{
+    if (!c || !name) { rtds_set_error("set_option: bad arguments"); return RTDS_ERR_INVALID; }
+    for (int i = 0; i < g_rtds_n_option_names; ++i)
+        if (!strcmp(name, g_rtds_option_names[i].name)) { c->opt.*(g_rtds_option_names[i].field) = value; return RTDS_OK; }
+    rtds_set_error("set_option: unknown option '%s'", name);
+    return RTDS_ERR_INVALID;
+}
+
+int rtds_get_option(rtds_ctx* c, const char* name, int* value)
+{
+    if (!c || !name || !value) { rtds_set_error("get_option: bad arguments"); return RTDS_ERR_INVALID; }
+    for (int i = 0; i < g_rtds_n_option_names; ++i)
+        if (!strcmp(name, g_rtds_option_names[i].name)) { *value = c->opt.*(g_rtds_option_names[i].field); return RTDS_OK; }
+    rtds_set_error("get_option: unknown option '%s'", name);
+    return RTDS_ERR_INVALID;
 }
 
 int rtds_morton30(rtds_ctx* c, const float* xyz, int n, uint32_t* codes)

@@ -419,7 +419,7 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
     cudaStream_t s = ctx->stream;
     tr[0] = tr_us();
     RTDS_CUDA(cudaEventRecord(ctx->ev0, s));
-    if (g_rtds_trace_ev[0]) RTDS_CUDA(cudaEventRecord(g_rtds_trace_ev[4], s));
+    RTDS_TRACE_RECORD(ctx, 4, s);
     const int T = 256;
     const int G = (n + T - 1) / T;
     bounds_init_kernel<<<1, 32, 0, s>>>(d_bounds);
@@ -444,7 +444,7 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
     widen_keys_kernel<K><<<G, T, 0, s>>>(d_keys, n, ctx->d_keys_sorted);
     launches += 2;
     RTDS_CUDA(cudaEventRecord(ctx->ev1, s));
-    if (g_rtds_trace_ev[0]) RTDS_CUDA(cudaEventRecord(g_rtds_trace_ev[5], s));
+    RTDS_TRACE_RECORD(ctx, 5, s);
     RTDS_CUDA(cudaGetLastError());
     // root box + depth come back into PINNED memory: a copy into pageable memory is staged by the driver, ~15 us each
     // on the rtds_frame critical path
@@ -457,7 +457,7 @@ int build_true(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st, 
     tr[3] = tr_us();
     for (int i = 0; i < 6; ++i) b.root_box[i] = h_box[i];
     const int depth = *h_depth;
-    if (g_rtds_trace_ev[0]) fprintf(stderr, "[lbvh build host] allocs done %.0f us | 3 launches in %.0f | all enqueued %.0f | synced %.0f\n", tr[0], tr[1], tr[2], tr[3]);
+    if (ctx->trace_ev[0]) fprintf(stderr, "[lbvh build host] allocs done %.0f us | 3 launches in %.0f | all enqueued %.0f | synced %.0f\n", tr[0], tr[1], tr[2], tr[3]);
     b.n_prims = n;
     b.n_internal = n - 1;
     b.root_ref = n > 1 ? 0 : ~0;
@@ -518,8 +518,7 @@ int rtds_bvh_reorder_preorder(rtds_ctx* ctx, DeviceBvh& b, void* scratch, int* l
     if (ni <= 1) return RTDS_OK;
     // Off by default: measured +0.09 ms per million primitives of build time for <= 1 % of traversal time, on the
     // L2-resident 1 M-primitive tree and on the 7 M-primitive one alike (RTDS_NODE_ORDER=preorder turns it on).
-    const char* e = getenv("RTDS_NODE_ORDER");
-    if (!e || strcmp(e, "preorder")) return RTDS_OK;
+    if (!ctx->opt.node_preorder) return RTDS_OK;
     int* new_index = (int*)scratch;
     Node64* tmp = (Node64*)((char*)scratch + (((size_t)ni * 4 + 255) & ~(size_t)255));
     cudaStream_t s = ctx->stream;

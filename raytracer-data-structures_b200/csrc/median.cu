@@ -719,7 +719,7 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
     DeviceBvh& b = ctx->bvh;
     b.valid = false;
     int small = 64;
-    if (const char* e = getenv("RTDS_MEDIAN_SMALL")) small = atoi(e) > 0 ? atoi(e) : small;   // test hook: huge -> all sequential
+    if (ctx->opt.median_small > 0) small = ctx->opt.median_small;   // test hook (median_small option): huge -> all sequential
     RTDS_TRY(rtds_alloc_bvh_for(ctx, b, n));
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const int fin_tiles = (n + FIN_TILE - 1) / FIN_TILE;
@@ -754,7 +754,7 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
     int ccur = C_TA, cnxt = C_TB;
     long long max_size = n, max_tasks = 1;
     int coop_threshold = 65536;     // ranges larger than this get the whole grid, one after another
-    if (const char* e = getenv("RTDS_MEDIAN_COOP")) coop_threshold = atoi(e) > 0 ? atoi(e) : (1 << 30);
+    if (ctx->opt.median_coop != 0) coop_threshold = ctx->opt.median_coop > 0 ? ctx->opt.median_coop : (1 << 30);
     int coop_blocks = 0;
     {
         int per_sm = 0;
@@ -806,7 +806,7 @@ int rtds_build_median(rtds_ctx* ctx, int n_use, rtds_build_stats* st)
         rtds_set_error("median-split build: a range has zero extent on its longest axis (accelerators.h:286-293 pushes unrelated ids); unsupported");
         return RTDS_ERR_UNSUPPORTED;
     }
-    if (getenv("RTDS_MEDIAN_DEBUG")) fprintf(stderr, "[median] heap-select fallbacks: %d (elements %d)\n", h_cnt[7], h_cnt[8]);
+    if (ctx->opt.median_debug) fprintf(stderr, "[median] heap-select fallbacks: %d (elements %d)\n", h_cnt[7], h_cnt[8]);
     const int n_leaves = h_cnt[5], n_internal = h_cnt[C_NODES];
     if (n_leaves != n_internal + 1) { rtds_set_error("median-split build: internal error (%d leaves, %d interior)", n_leaves, n_internal); return RTDS_ERR_CUDA; }
     b.n_prims = n_leaves;

@@ -416,192 +416,6 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
 }
 
 // ===================================================================================================
-// K10, two-pixel packet form (OPT-IN, RTDS_PACKET2=1; finished after round 1's GPU budget was spent: compiles, NOT yet run on
-// hardware, its parity test is skipped unless RTDS_TEST_EXPERIMENTAL=1): one thread per TWO horizontally adjacent pixels, the
-// samples k0..k0+3 of both pixels traced as one 8-ray packet by traverse_packet_n<OCT, 8>. The CPU model
-// (tools/packet_size_model.py) gives 1.58 instead of 3.11 interior visits per ray on the bench frame.
-// ===================================================================================================
-constexpr int PK2 = 2 * PK;
-#ifndef RTDS_PK2_MINB
-#define RTDS_PK2_MINB 4
-#endif
-__device__ __forceinline__ void trace_packet8(const RenderArgs& A, const float (&dx)[PK2], const float (&dy)[PK2], const float (&dz)[PK2],
-                                              float margin, float (&tnear)[PK2], int (&best_leaf)[PK2], Counters& cnt)
-{
-    int best_key[PK2];
-    bool ok = A.bvh.root_ref >= 0;
-    int oct0 = 0;
-    float ixlo = INFINITY, ixhi = -INFINITY, iylo = INFINITY, iyhi = -INFINITY, izlo = INFINITY, izhi = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < PK2; ++j) {
-        float ix, iy, iz;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"(dx[j]));
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(dy[j]));
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(dz[j]));
-        const float amin = fminf(fminf(fabsf(ix), fabsf(iy)), fabsf(iz));
-        const float amax = fmaxf(fmaxf(fabsf(ix), fabsf(iy)), fabsf(iz));
-        const int oct = (dx[j] < 0 ? 1 : 0) | (dy[j] < 0 ? 2 : 0) | 4;
-        if (j == 0) oct0 = oct;
-        ok = ok && amin > 1e-30f && amax < 1e30f && oct == oct0;
-        ixlo = fminf(ixlo, ix); ixhi = fmaxf(ixhi, ix);
-        iylo = fminf(iylo, iy); iyhi = fmaxf(iyhi, iy);
-        izlo = fminf(izlo, iz); izhi = fmaxf(izhi, iz);
-        tnear[j] = INFINITY; best_key[j] = 0; best_leaf[j] = -1;
-    }
-    if (ok) {
-        switch (oct0) {
-            case 4: traverse_packet_n<4, PK2>(A.bvh, dx, dy, dz, ixlo, ixhi, iylo, iyhi, izlo, izhi, margin, tnear, best_key, best_leaf, cnt); break;
-            case 5: traverse_packet_n<5, PK2>(A.bvh, dx, dy, dz, ixlo, ixhi, iylo, iyhi, izlo, izhi, margin, tnear, best_key, best_leaf, cnt); break;
-            case 6: traverse_packet_n<6, PK2>(A.bvh, dx, dy, dz, ixlo, ixhi, iylo, iyhi, izlo, izhi, margin, tnear, best_key, best_leaf, cnt); break;
-            default: traverse_packet_n<7, PK2>(A.bvh, dx, dy, dz, ixlo, ixhi, iylo, iyhi, izlo, izhi, margin, tnear, best_key, best_leaf, cnt); break;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < PK2; ++j) {
-            const ColdHit h = trace_primary_cold(&A.bvh, dx[j], dy[j], dz[j]);
-            tnear[j] = h.tnear; best_leaf[j] = h.leaf;
-            cnt.node_tests += h.node_tests; cnt.prim_tests += h.prim_tests; cnt.node_visits += h.node_visits;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(128, RTDS_PK2_MINB) render_packet2_kernel(const __grid_constant__ RenderArgs A)
-{
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // thread = 2 x 1 pixels; block = 16 x 8 threads = 32 x 8 pixels, warp = 8 x 4 threads; row-major blocks over this launch's rows
-    const int ntx = (A.width + 1) / 2, nbx = (ntx + 15) / 16;
-    const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
-    const int tx = bx * 16 + (warp & 1) * 8 + (lane & 7);
-    const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
-    Counters cnt = {0, 0, 0, 0};
-    if (tx < ntx && lrow < A.local_rows) {
-        const float margin = prune_margin(A.bvh.root_box, 0.f, 0.f, 0.f);
-        const int px0 = 2 * tx;
-        const bool two = px0 + 1 < A.width;                       // odd widths: the last thread of a row has one pixel (traced twice)
-        const int py = global_row_of(A, lrow);
-        const size_t pixA = (size_t)py * A.width + px0, pixB = pixA + (two ? 1 : 0);
-        float accA[3] = {0, 0, 0}, accB[3] = {0, 0, 0};
-        int lastA = -1, lastB = -1;
-        for (int k0 = 0; k0 < A.spp; k0 += PK) {
-            float dx[PK2], dy[PK2], dz[PK2], tnear[PK2];
-            int best_leaf[PK2];
-            // each pixel's 4 directions are 48 contiguous, 16-byte aligned bytes (aa_samples % 4 == 0)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float4* dp = reinterpret_cast<const float4*>(A.dirs + 3 * ((h ? pixB : pixA) * A.spp + k0));
-                const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
-                const int o = 4 * h;
-                dx[o] = d0.x; dy[o] = d0.y; dz[o] = d0.z; dx[o + 1] = d0.w; dy[o + 1] = d1.x; dz[o + 1] = d1.y;
-                dx[o + 2] = d1.z; dy[o + 2] = d1.w; dz[o + 2] = d2.x; dx[o + 3] = d2.y; dy[o + 3] = d2.z; dz[o + 3] = d2.w;
-            }
-            cnt.rays += two ? PK2 : PK;
-            trace_packet8(A, dx, dy, dz, margin, tnear, best_leaf, cnt);
-#pragma unroll
-            for (int j = 0; j < PK2; ++j) {
-                const ShadedRay sh = shade_packet_ray_ool(&A, dx[j], dy[j], dz[j], tnear[j], best_leaf[j]);
-                if (j < PK) { accA[0] += sh.r; accA[1] += sh.g; accA[2] += sh.b; lastA = sh.hit; }      // sample order per pixel
-                else { accB[0] += sh.r; accB[1] += sh.g; accB[2] += sh.b; lastB = sh.hit; }
-            }
-        }
-        const float fs = (float)(unsigned)A.spp;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (h == 1 && !two) break;
-            const float* acc = h ? accB : accA;
-            const int px = px0 + h;
-            const size_t o_loc = (size_t)lrow * A.width + px;
-            const size_t o = (size_t)(A.out_global_rows ? py : lrow) * A.width + px;
-            A.out_rgb[3 * o] = (unsigned char)(fminf(1.0f, acc[0] / fs) * 255);
-            A.out_rgb[3 * o + 1] = (unsigned char)(fminf(1.0f, acc[1] / fs) * 255);
-            A.out_rgb[3 * o + 2] = (unsigned char)(fminf(1.0f, acc[2] / fs) * 255);
-            if (A.out_hit) A.out_hit[o_loc] = h ? lastB : lastA;
-            if (A.out_accum) { A.out_accum[3 * o_loc] = acc[0]; A.out_accum[3 * o_loc + 1] = acc[1]; A.out_accum[3 * o_loc + 2] = acc[2]; }
-        }
-    }
-    unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        unsigned long long x = v[c];
-        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0 && x) atomicAdd(&A.counters[c], x);
-    }
-}
-
-// ===================================================================================================
-// K10, pixel-quad form (OPT-IN, RTDS_QUAD=1: parity-tested on the B200, speed not measured yet): one thread per 2 x 2 pixels, the k-th samples of the four pixels traced as
-// one packet by traverse_packet<OCT, HULL>. Why: with the hull test an interior visit costs the same for any packet, and the
-// CPU model (tools/packet_size_model.py) shows the union of four neighbouring pixels' paths is ~1.03x
-// one pixel's: 1.64 instead of 5.54 interior visits per ray on the bunny at 1080p, 1 spp. Serves aa_samples that are not a
-// multiple of 4 (those take the sample packets of render_packet_kernel). Per-pixel accumulation stays in sample order.
-// ===================================================================================================
-template <bool HULL>
-__global__ void __launch_bounds__(128, RTDS_PK_MINB) render_quad_kernel(const __grid_constant__ RenderArgs A)
-{
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // block = 16 x 8 quads = 32 x 16 pixels, warp = 8 x 4 quads; row-major blocks over the quad grid of this launch's rows
-    const int nqx = (A.width + 1) / 2, nbx = (nqx + 15) / 16;
-    const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
-    const int qx = bx * 16 + (warp & 1) * 8 + (lane & 7);
-    const int qrow = by * 8 + (warp >> 1) * 4 + (lane >> 3);           // quad row inside [lrow0, local_rows)
-    const int lrow_top = A.lrow0 + 2 * qrow;
-    Counters cnt = {0, 0, 0, 0};
-    if (qx < nqx && lrow_top < A.local_rows) {
-        const float margin = prune_margin(A.bvh.root_box, 0.f, 0.f, 0.f);
-        // the quad's pixels: j = 0..3 -> (2 qx + (j & 1), lrow_top + (j >> 1)); pixels outside the frame are traced as copies
-        // of pixel 0 and dropped
-        bool valid[PK];
-        size_t pix[PK];
-        int px[PK], lrow[PK];
-#pragma unroll
-        for (int j = 0; j < PK; ++j) {
-            px[j] = 2 * qx + (j & 1);
-            lrow[j] = lrow_top + (j >> 1);
-            valid[j] = px[j] < A.width && lrow[j] < A.local_rows;
-            const int pj = valid[j] ? j : 0;
-            pix[j] = (size_t)global_row_of(A, lrow_top + (pj >> 1)) * A.width + (2 * qx + (pj & 1));
-        }
-        float acc_r[PK] = {0, 0, 0, 0}, acc_g[PK] = {0, 0, 0, 0}, acc_b[PK] = {0, 0, 0, 0};
-        int last_hit[PK] = {-1, -1, -1, -1};
-        for (int k = 0; k < A.spp; ++k) {
-            float dx[PK], dy[PK], dz[PK], tnear[PK];
-            int best_leaf[PK];
-#pragma unroll
-            for (int j = 0; j < PK; ++j) {
-                const float* dp = A.dirs + 3 * (pix[j] * A.spp + k);      // main.cpp:554-557, from mt_expand_dirs_kernel
-                dx[j] = __ldg(dp); dy[j] = __ldg(dp + 1); dz[j] = __ldg(dp + 2);
-                cnt.rays += valid[j] ? 1u : 0u;
-            }
-            trace_packet4<HULL>(A, dx, dy, dz, margin, tnear, best_leaf, cnt);
-#pragma unroll
-            for (int j = 0; j < PK; ++j) {
-                const ShadedRay sh = shade_packet_ray_ool(&A, dx[j], dy[j], dz[j], tnear[j], best_leaf[j]);
-                acc_r[j] += sh.r; acc_g[j] += sh.g; acc_b[j] += sh.b;       // sample order per pixel, main.cpp:553-560
-                last_hit[j] = sh.hit;
-            }
-        }
-        const float fs = (float)(unsigned)A.spp;
-#pragma unroll
-        for (int j = 0; j < PK; ++j) {
-            if (!valid[j]) continue;
-            const size_t o_loc = (size_t)lrow[j] * A.width + px[j];
-            const size_t o = (size_t)(A.out_global_rows ? global_row_of(A, lrow[j]) : lrow[j]) * A.width + px[j];
-            A.out_rgb[3 * o] = (unsigned char)(fminf(1.0f, acc_r[j] / fs) * 255);
-            A.out_rgb[3 * o + 1] = (unsigned char)(fminf(1.0f, acc_g[j] / fs) * 255);
-            A.out_rgb[3 * o + 2] = (unsigned char)(fminf(1.0f, acc_b[j] / fs) * 255);
-            if (A.out_hit) A.out_hit[o_loc] = last_hit[j];
-            if (A.out_accum) { A.out_accum[3 * o_loc] = acc_r[j]; A.out_accum[3 * o_loc + 1] = acc_g[j]; A.out_accum[3 * o_loc + 2] = acc_b[j]; }
-        }
-    }
-    unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        unsigned long long x = v[c];
-        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0 && x) atomicAdd(&A.counters[c], x);
-    }
-}
-
-// ===================================================================================================
 // K10 + K11 fused ("strip" kernel): one block per MT19937 snapshot chunk (8 regenerations = 4,992 words = 1,248
 // samples). The block regenerates its chunk of the reference's jitter stream into SHARED memory (plus one more
 // regeneration for a pixel whose samples straddle the chunk end) and renders the pixels whose first sample lies in
@@ -1129,7 +943,7 @@ int rtds_ensure_band_streams(rtds_ctx* ctx)
         RTDS_CUDA(cudaStreamCreateWithPriority(&ctx->band_streams[k], cudaStreamNonBlocking, std::min(least, greatest + k)));
     RTDS_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
     // timing only when RTDS_TRACE_FRAME reads them (measured: timing-enabled band events cost the frame ~0.1 ms)
-    const bool tr = getenv("RTDS_TRACE_FRAME") && atoi(getenv("RTDS_TRACE_FRAME")) > 1;
+    const bool tr = ctx->opt.trace_frame > 1;
     for (int k = 0; k < RTDS_MAX_BANDS; ++k) RTDS_CUDA(cudaEventCreateWithFlags(&ctx->ev_bands[k], tr ? cudaEventDefault : cudaEventDisableTiming));
     return RTDS_OK;
 }
@@ -1140,15 +954,15 @@ int rtds_prefetch_dirs(rtds_ctx* ctx, const rtds_render_params* p)
     if (W <= 0 || H <= 0 || spp <= 0) return RTDS_OK;        // the render call reports the error
     const int world = p->world > 0 ? p->world : 1, rank = p->rank, tile_rows = p->tile_rows > 0 ? p->tile_rows : 8;
     if (rank < 0 || rank >= world) return RTDS_OK;
-    if (getenv("RTDS_STRIP") && atoi(getenv("RTDS_STRIP")) == 1) return RTDS_OK;
+    if (ctx->opt.strip == 1) return RTDS_OK;
     if (ctx->dirs_pending) RTDS_CUDA(cudaStreamSynchronize(ctx->jit_stream));
     RTDS_CUDA(cudaStreamSynchronize(ctx->stream));            // a render still reading d_dirs
     const RayGen G = make_raygen(p);
     JitterOwner own{4ull * p->jitter_offset, 4ull * (unsigned long long)W * spp, tile_rows, rank, world, H};
     int launches = 0;
-    if (g_rtds_trace_ev[0]) RTDS_CUDA(cudaEventRecord(g_rtds_trace_ev[1], ctx->jit_stream));
+    RTDS_TRACE_RECORD(ctx, 1, ctx->jit_stream);
     RTDS_TRY(dirs_prepare(ctx, p->jitter_offset, W, H, spp, G, own, &launches, ctx->jit_stream));
-    if (g_rtds_trace_ev[0]) RTDS_CUDA(cudaEventRecord(g_rtds_trace_ev[2], ctx->jit_stream));
+    RTDS_TRACE_RECORD(ctx, 2, ctx->jit_stream);
     RTDS_CUDA(cudaEventRecord(ctx->ev_dirs, ctx->jit_stream));
     ctx->dirs_pending = true;
     ctx->dirs_pending_launches = launches;
@@ -1190,7 +1004,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     const bool kd_closest = kdt && p->kd_closest;
     A.out_rgb = d_rgb_rows; A.out_hit = d_hit; A.out_accum = d_accum; A.out_global_rows = global_rows ? 1 : 0;
     A.out_vec8 = (((uintptr_t)d_rgb_rows & 7) == 0 && W % 8 == 0) ? 1 : 0;
-    A.block_order = getenv("RTDS_BLOCK_ORDER") ? atoi(getenv("RTDS_BLOCK_ORDER")) : 2;
+    A.block_order = ctx->opt.block_order;
     A.counters = ctx->d_counters;
 
     cudaStream_t s = ctx->stream;
@@ -1202,7 +1016,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     // expanded into HBM. MEASURED SLOWER on B200 (3.16 ms vs 1.81 + 0.24 ms on the bench frame): a block then covers
     // 312 consecutive pixels of one scanline instead of a 16x8 tile, and the L1 hit rate of the node stream — what
     // this issue-bound kernel lives on — collapses. Kept as a checked (parity-tested) negative result, off by default.
-    const bool strip = !brute && !full && !kd_closest && !global_rows && spp <= 150 && getenv("RTDS_STRIP") && atoi(getenv("RTDS_STRIP")) == 1;
+    const bool strip = !brute && !full && !kd_closest && !global_rows && spp <= 150 && ctx->opt.strip == 1;
     const uint64_t chunk_words = (uint64_t)MT_SNAP_EVERY * MT_N;
     const uint64_t c_first = first_word / chunk_words, c_last = (first_word + n_words - 1) / chunk_words;
     if (strip) {
@@ -1252,8 +1066,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
         const int total_rows = A.local_rows;
         int n_bands = 1;
         if (on_band && total_rows >= 512) {
-            const char* e = getenv("RTDS_BANDS");
-            n_bands = e ? std::max(1, std::min(RTDS_MAX_BANDS, atoi(e))) : 4;
+            n_bands = std::max(1, std::min(RTDS_MAX_BANDS, ctx->opt.bands));
             RTDS_TRY(rtds_ensure_band_streams(ctx));
         }
         // Band boundaries (multiples of 8 rows): equal shares by default. RTDS_BAND_RATIO = r (percent) makes every band r %
@@ -1263,7 +1076,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
         // the last two or three bands all end within ~50 us of each other whatever their size.
         int band_start[RTDS_MAX_BANDS + 1];
         {
-            const int pct = getenv("RTDS_BAND_RATIO") ? std::max(10, std::min(100, atoi(getenv("RTDS_BAND_RATIO")))) : 100;
+            const int pct = std::max(10, std::min(100, ctx->opt.band_ratio));
             double w[RTDS_MAX_BANDS], sum = 0;
             for (int k = 0; k < n_bands; ++k) { w[k] = k ? w[k - 1] * pct / 100.0 : 1.0; sum += w[k]; }
             band_start[0] = 0;
@@ -1291,34 +1104,24 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             const unsigned lin = (unsigned)((W + 15) / 16) * (unsigned)((r1 - r0 + 7) / 8);     // quadrant-major linear grid
             // four samples of a pixel per thread as one packet (see traverse_packet); RTDS_PACKET=0 turns it off
             // (shadows without reflective / refractive materials stay on the packet kernel; the shadow rays are single)
-            // Only the samples of ONE pixel are packed: packets of neighbouring pixels (2 x 2 pixels x 1 sample, 2 pixels x 2
-            // samples) were measured slower than single rays - 0.208 vs 0.187 ms on the bunny at 1080p, 4.57 vs 2.19 ms on
-            // the 7 M-sphere scene - pixel-sized primitives make neighbouring pixels' paths diverge right below the top levels.
+            // Only the samples of ONE pixel are packed. Packets of neighbouring pixels were built twice and measured slower both
+            // times, also with the hull test (round 2, B200): 2 x 2 pixels x 1 sample 0.205 vs 0.087 ms (bunny 640x480), 0.25 vs
+            // 0.20 ms (1080p), 4.7 vs 2.3 ms (7 M spheres); 2 pixels x 4 samples 1.07 vs 0.97 ms on the bench frame - node visits per
+            // ray drop 2-3.4x, but a thread then carries 4-8 rays' leaf work in sequence and the grid has 2-4x fewer threads
+            // to hide latency with (negative results). Removed again.
             bool packet = (!full || !ctx->has_materials) && !kdt && !brute && !p->exact && spp % PK == 0 && A.bvh.leaf_box_prim &&
                           A.shade.max_depth >= 1;
-            if (const char* e = getenv("RTDS_PACKET")) packet = packet && atoi(e) != 0;
+            packet = packet && ctx->opt.packet != 0;
             // interior boxes tested once per packet against the hull of the four reciprocal directions (default; RTDS_HULL=0:
             // once per ray). Bench frame: same frame, node visits 3.17 -> 3.18 per ray, kernel 1.16 -> 0.99 ms.
-            const bool hull = getenv("RTDS_HULL") ? atoi(getenv("RTDS_HULL")) != 0 : true;
-            // opt-in (RTDS_QUAD=1): packets of 2 x 2 neighbouring pixels for aa_samples that are not a multiple of 4; band rows are
-            // multiples of 8 and tile_rows even, so a quad's two rows lie in the same band and the same scanline tile
-            const bool quad = !full && !packet && !kdt && !brute && !p->exact && A.bvh.leaf_box_prim && (tile_rows % 2) == 0 && (r0 % 2) == 0 &&
-                              getenv("RTDS_QUAD") && atoi(getenv("RTDS_QUAD")) == 1;
+            const bool hull = ctx->opt.hull != 0;
             if (packet && full) { if (hull) render_packet_kernel<true, true><<<lin, block, 0, s>>>(A); else render_packet_kernel<true, false><<<lin, block, 0, s>>>(A); }
             else if (full) {
                 if (brute) render_full_kernel<2><<<lin, block, 0, s>>>(A);
                 else if (p->exact) render_full_kernel<0><<<lin, block, 0, s>>>(A);
                 else render_full_kernel<1><<<lin, block, 0, s>>>(A);
             }
-            else if (packet && hull && getenv("RTDS_PACKET2") && atoi(getenv("RTDS_PACKET2")) == 1) {      // opt-in: 2 pixels x 4 samples per thread
-                const unsigned plin = (unsigned)(((W + 1) / 2 + 15) / 16) * (unsigned)((r1 - r0 + 7) / 8);
-                render_packet2_kernel<<<plin, block, 0, s>>>(A);
-            }
             else if (packet) { if (hull) render_packet_kernel<false, true><<<lin, block, 0, s>>>(A); else render_packet_kernel<false, false><<<lin, block, 0, s>>>(A); }
-            else if (quad) {
-                const unsigned qlin = (unsigned)(((W + 1) / 2 + 15) / 16) * (unsigned)((((r1 - r0) + 1) / 2 + 7) / 8);
-                if (hull) render_quad_kernel<true><<<qlin, block, 0, s>>>(A); else render_quad_kernel<false><<<qlin, block, 0, s>>>(A);
-            }
             else if (kd_closest) render_kernel<4><<<lin, block, 0, s>>>(A);
             else if (kdt) render_kernel<3><<<lin, block, 0, s>>>(A);
             else if (brute) render_kernel<2><<<lin, block, 0, s>>>(A);

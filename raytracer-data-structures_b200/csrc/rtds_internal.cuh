@@ -99,7 +99,31 @@ struct SharedFrame {
 
 #define RTDS_MAX_BANDS 8
 
+// Tuning / test switches of one context. Defaults come from the RTDS_* environment variables, read ONCE in rtds_create
+// (never on a frame's path); rtds_set_option() changes them afterwards (tests, A/B tools).
+struct RtdsOptions {
+    int block_order = 2;     // RTDS_BLOCK_ORDER  0 quadrant-major, 1 row-major, 2 quadrant-major from the centre rows outwards
+    int strip = 0;           // RTDS_STRIP        1: fused jitter + render strip kernel (measured slower; parity-tested)
+    int bands = 4;           // RTDS_BANDS        row bands of a host-buffer render (download overlapped with rendering)
+    int band_ratio = 100;    // RTDS_BAND_RATIO   each band's share of the one before it, percent
+    int packet = 1;          // RTDS_PACKET       0: never the packet kernels
+    int hull = 1;            // RTDS_HULL         0: interior boxes tested per ray instead of once per packet
+    int zerocopy = 0;        // RTDS_ZEROCOPY     1: store the frame straight into pinned host memory (measured slower)
+    int trace_frame = 0;     // RTDS_TRACE_FRAME  1: rtds_frame stage timeline on stderr, 2: + per-band events
+    int median_small = 0;    // RTDS_MEDIAN_SMALL test hook: sequential/parallel switch-over of the median split (0 = 64)
+    int median_coop = 0;     // RTDS_MEDIAN_COOP  ranges above this use the cooperative kernel (0 = 65536)
+    int median_debug = 0;    // RTDS_MEDIAN_DEBUG
+    int node_preorder = 0;   // RTDS_NODE_ORDER=preorder: renumber the nodes in DFS pre-order after the build
+    int l2_prefetch = 0;     // RTDS_L2_PREFETCH  stream the tree into L2 on a side stream while the directions are generated
+    int frame_graph = 0;     // RTDS_FRAME_GRAPH  multi-GPU shared frames: one CUDA graph launch per frame
+};
+typedef int RtdsOptions::*RtdsOptionField;
+struct RtdsOptionName { const char* name; const char* env; RtdsOptionField field; };
+extern const RtdsOptionName g_rtds_option_names[];
+extern const int g_rtds_n_option_names;
+
 struct rtds_ctx {
+    RtdsOptions  opt;
     int          device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // device->host copies of finished row bands
@@ -107,6 +131,7 @@ struct rtds_ctx {
     cudaStream_t band_streams[RTDS_MAX_BANDS] = {};   // descending priority, created on first use (host-buffer renders)
     cudaEvent_t  ev_ready = nullptr, ev_bands[RTDS_MAX_BANDS] = {};
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t  trace_ev[8] = {};        // rtds_frame's stage timeline (trace_frame option), created on this context's device
     int          sm_count = 148;
 
     // scene (objId-indexed)
@@ -206,8 +231,9 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* 
 // the upload had finished). p 4-byte aligned, bytes a multiple of 4.
 int rtds_zero_async(void* p, size_t bytes, cudaStream_t s, int* launches = nullptr);
 
-// RTDS_TRACE_FRAME=1 (profiling aid, api.cu): timing events of rtds_frame's device timeline; [0] == nullptr when off
-extern cudaEvent_t g_rtds_trace_ev[8];
+// trace_frame option (profiling aid, api.cu): timing events of rtds_frame's device timeline live in the context
+// (rtds_ctx::trace_ev, [0] == nullptr when off); a failing trace-only call never fails the frame
+#define RTDS_TRACE_RECORD(ctx, i, stream) do { if ((ctx)->trace_ev[0]) (void)cudaEventRecord((ctx)->trace_ev[i], (stream)); } while (0)
 
 // kd.cu — K8 KD-tree SAH build
 int rtds_build_kd(rtds_ctx* ctx, const rtds_build_params* p, rtds_build_stats* st);

@@ -544,102 +544,6 @@ __device__ __forceinline__ void traverse_packet(const BvhView& B, const float (&
     cnt.prim_tests += prim_tests;
 }
 
-// traverse_packet for NR rays (hull form only; OPT-IN kernels, see render_packet2_kernel): the same loop with the per-ray
-// state sized NR. The per-ray reciprocals are not kept across the walk - the interior test needs only their hull - and are
-// recomputed (rcp.approx is deterministic) at the few leaves a packet opens.
-template <int OCT, int NR>
-__device__ __forceinline__ void traverse_packet_n(const BvhView& B, const float (&dx)[NR], const float (&dy)[NR], const float (&dz)[NR],
-                                                  float ixlo, float ixhi, float iylo, float iyhi, float izlo, float izhi, float margin,
-                                                  float (&tnear)[NR], int (&best_key)[NR], int (&best_leaf)[NR], Counters& cnt)
-{
-    const float zthr = margin * (9.5367431640625e-7f / 0.00278f);
-    float tlim[NR];
-    float tlim_max = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < NR; ++j) { tlim[j] = tnear[j] + margin; tlim[j] = __fmaf_rn(fabsf(tlim[j]), WIDE2, tlim[j]); tlim_max = fmaxf(tlim_max, tlim[j]); }
-    int2 stack[STACK_MAX];
-    int sp = 0;
-    int node = 0;
-    unsigned visits = 0, prim_tests = 0;
-    while (true) {
-        if (node >= 0) {
-            const float4* q = reinterpret_cast<const float4*>(B.nodes + node);
-            const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-            const int2 ch = __ldg(reinterpret_cast<const int2*>(q + 3));
-            ++visits;
-            const bool frontL = q0.z <= zthr && ((OCT & 2) ? q0.y <= zthr : q1.x >= -zthr) && ((OCT & 1) ? q0.x <= zthr : q0.w >= -zthr);
-            const bool frontR = q2.x <= zthr && ((OCT & 2) ? q1.w <= zthr : q2.z >= -zthr) && ((OCT & 1) ? q1.z <= zthr : q2.y >= -zthr);
-            const float lnx = (OCT & 1) ? q0.w : q0.x, lfx = (OCT & 1) ? q0.x : q0.w;
-            const float lny = (OCT & 2) ? q1.x : q0.y, lfy = (OCT & 2) ? q0.y : q1.x;
-            const float lnz = q1.y, lfz = q0.z;
-            const float rnx = (OCT & 1) ? q2.y : q1.z, rfx = (OCT & 1) ? q1.z : q2.y;
-            const float rny = (OCT & 2) ? q2.z : q1.w, rfy = (OCT & 2) ? q1.w : q2.z;
-            const float rnz = q2.w, rfz = q2.x;
-            const float tminL = fmaxf(fmaxf(fminf(lnx * ixlo, lnx * ixhi), fminf(lny * iylo, lny * iyhi)), fminf(lnz * izlo, lnz * izhi));
-            float tmaxL = fminf(fminf(fmaxf(lfx * ixlo, lfx * ixhi), fmaxf(lfy * iylo, lfy * iyhi)), fmaxf(lfz * izlo, lfz * izhi));
-            const float tminR = fmaxf(fmaxf(fminf(rnx * ixlo, rnx * ixhi), fminf(rny * iylo, rny * iyhi)), fminf(rnz * izlo, rnz * izhi));
-            float tmaxR = fminf(fminf(fmaxf(rfx * ixlo, rfx * ixhi), fmaxf(rfy * iylo, rfy * iyhi)), fmaxf(rfz * izlo, rfz * izhi));
-            tmaxL = __fmaf_rn(fabsf(tmaxL), WIDE2, tmaxL);
-            tmaxR = __fmaf_rn(fabsf(tmaxR), WIDE2, tmaxR);
-            const float tL = (frontL && tminL <= fminf(tmaxL, tlim_max)) ? tminL : INFINITY;
-            const float tR = (frontR && tminR <= fminf(tmaxR, tlim_max)) ? tminR : INFINITY;
-            const bool hitL = tL < INFINITY, hitR = tR < INFINITY;
-            if (hitL && hitR) {
-                const bool rfirst = tR < tL;
-                stack[sp] = make_int2(rfirst ? ch.x : ch.y, __float_as_int(rfirst ? tL : tR));
-                sp = min(sp + 1, STACK_MAX - 1);
-                node = rfirst ? ch.y : ch.x;
-                continue;
-            }
-            if (hitL | hitR) { node = hitL ? ch.x : ch.y; continue; }
-        } else {
-            const int leaf = ~node;
-            const float4 s = __ldg(B.leaf_sph + leaf);
-            const float bx0 = s.x - s.w, by0 = s.y - s.w, bz0 = s.z - s.w, bx1 = s.x + s.w, by1 = s.y + s.w, bz1 = s.z + s.w;
-            const float4 s2 = make_float4(s.x, s.y, s.z, s.w * s.w);
-            int key = leaf;
-            if (B.tie_by_objid) key = __ldg(B.prim_order + leaf);
-            tlim_max = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < NR; ++j) {
-                float ix, iy, iz;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"(dx[j]));
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(dy[j]));
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(dz[j]));
-                float tmn, tmx;
-                slab_interval<OCT>(bx0 * ix, by0 * iy, bz0 * iz, bx1 * ix, by1 * iy, bz1 * iz, tmn, tmx);
-                bool pass = __fmaf_rn(fabsf(tmn), NARROW_EPS, tmn) <= __fmaf_rn(-fabsf(tmx), NARROW_EPS, tmx) &&
-                            fminf(fabsf(tmn), fabsf(tmx)) > 1e-30f;
-                if (!pass && tmn <= __fmaf_rn(fabsf(tmx), WIDE2, tmx))
-                    pass = slab_test_cold(0.f, 0.f, 0.f, dx[j], dy[j], dz[j], bx0, by0, bz0, bx1, by1, bz1);
-                if (pass) {
-                    float t0, t1;
-                    ++prim_tests;
-                    if (sphere_test(0.f, 0.f, 0.f, dx[j], dy[j], dz[j], s2, t0, t1)) {
-                        candidate(t0, t1, key, leaf, tnear[j], best_key[j], best_leaf[j]);
-                        tlim[j] = tnear[j] + margin;
-                        tlim[j] = __fmaf_rn(fabsf(tlim[j]), WIDE2, tlim[j]);
-                    }
-                }
-                tlim_max = fmaxf(tlim_max, tlim[j]);
-            }
-        }
-        bool found = false;
-        while (sp > 0) {
-            --sp;
-            const int2 e = stack[sp];
-            if (__int_as_float(e.y) > tlim_max) continue;
-            node = e.x;
-            found = true;
-            break;
-        }
-        if (!found) break;
-    }
-    cnt.node_visits += visits;
-    cnt.node_tests += 2 * visits;
-    cnt.prim_tests += prim_tests;
-}
-
 // single-ray fallback of the packet kernel (mixed octants / degenerate directions), out of line
 static __device__ __noinline__ ColdHit trace_primary_cold(const BvhView* B, float dx, float dy, float dz)
 {

@@ -173,20 +173,6 @@ class Oracle:
                                  tie_by_objid, self._p(o), self._p(d), n, self._p(hit), self._p(t), C.byref(tests))
         return hit, t, tests.value
 
-    def packet_model(self, sph, nodes, wide, order, dirs, tie_by_objid=1, use_wide=False, order_mode=0, quant_bits=0):
-        """CPU model of the ordered packet traversal (counts only; oracle.cpp orc_packet_model). dirs: (packets, 4, 3)."""
-        sph = np.ascontiguousarray(sph, np.float32)
-        dirs = np.ascontiguousarray(dirs, np.float32)
-        nr = dirs.shape[-2] if dirs.ndim == 3 else 4        # rays per packet (<= 16)
-        dirs = dirs.reshape(-1, nr, 3)
-        hit = np.zeros((dirs.shape[0], nr), np.int32)
-        st = np.zeros(6, np.int64)
-        self.lib.orc_packet_model(self._p(sph), sph.shape[0], self._p(nodes), nodes.shape[0], self._p(wide), wide.shape[0],
-                                  self._p(np.ascontiguousarray(order, np.int32)), tie_by_objid, self._p(dirs), dirs.shape[0], int(use_wide) | (order_mode << 4) | (quant_bits << 8) | (nr << 16),
-                                  self._p(hit), self._p(st))
-        keys = ("packets", "interior_visits", "leaf_visits", "box_tests", "prim_tests", "max_stack")
-        return hit, dict(zip(keys, (int(x) for x in st)))
-
     def jitter(self, n, first=0):
         out = np.zeros(n, np.float64)
         self.lib.orc_jitter(self._p(out), n, C.c_ulonglong(first))
@@ -397,6 +383,20 @@ def material_scene(n, seed, frac_rr=0.1, frac_refl=0.1, big=True):
     mat[:n, 3] = np.where(u < frac_rr, 1.0, np.where(u < frac_rr + frac_refl, 2.0, 0.0)).astype(np.float32)
     mat[:n, :3] = rng.uniform(0, 1, size=(n, 3)).astype(np.float32)
     return sph, mat
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def option(ctx, name, value):
+    """Set a tuning / test switch of the context (rtds_set_option) for the duration of a with-block."""
+    old = ctx.get_option(name)
+    ctx.set_option(name, value)
+    try:
+        yield
+    finally:
+        ctx.set_option(name, old)
 
 
 @pytest.fixture(scope="session")

@@ -81,7 +81,7 @@ def test_shadows_darken_only(gpu_ctx):
 
 
 @pytest.mark.parametrize("acc", [rt.BVH, rt.LBVH])
-def test_shadowed_packet_kernel_matches_restatement_and_full_kernel(gpu_ctx, oracle, monkeypatch, acc):
+def test_shadowed_packet_kernel_matches_restatement_and_full_kernel(gpu_ctx, oracle, acc):
     """Shadows on, diffuse materials only, aa_samples % 4 == 0: the packet kernel traces the primary rays (four samples of a
     pixel together) and single shadow rays; float sums, bytes and ray counts must equal the CPU restatement and the full
     castRay kernel (RTDS_PACKET=0)."""
@@ -98,8 +98,8 @@ def test_shadowed_packet_kernel_matches_restatement_and_full_kernel(gpu_ctx, ora
         rays, sh, sec = oracle.last_ray_counts
         assert (st["rays"], st["shadow_rays"], st["secondary_rays"]) == (rays, sh, sec) and sh > 1000 and sec == 0
         assert np.array_equal(hit, hit_o) and accum.tobytes() == accum_o.tobytes() and np.array_equal(rgb, rgb_o)
-        monkeypatch.setenv("RTDS_PACKET", "0")
-        rgb_f, hit_f, accum_f, st_f = gpu_ctx.render(acc, W, H, spp, want_hit=True, want_accum=True, shadows=1)
+        with T.option(gpu_ctx, "packet", 0):
+            rgb_f, hit_f, accum_f, st_f = gpu_ctx.render(acc, W, H, spp, want_hit=True, want_accum=True, shadows=1)
         assert accum.tobytes() == accum_f.tobytes() and np.array_equal(rgb, rgb_f) and np.array_equal(hit, hit_f)
         assert st_f["shadow_rays"] == st["shadow_rays"]
     finally:

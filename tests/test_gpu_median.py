@@ -79,7 +79,7 @@ def test_bvh_golden_scenes(gpu_ctx, oracle, name):
 def test_bvh_tie_fuzz_all_code_paths(gpu_ctx, oracle, small):
     """Random sizes x tie densities, with the sequential/parallel switch-over forced to every regime:
     small=1 -> every node by the block-parallel Hoare emulation; huge -> one thread runs the literal algorithms."""
-    os.environ["RTDS_MEDIAN_SMALL"] = small
+    gpu_ctx.set_option("median_small", int(small))
     try:
         rng = np.random.default_rng(int(small) % 1000 + 7)
         for trial in range(40):
@@ -93,7 +93,7 @@ def test_bvh_tie_fuzz_all_code_paths(gpu_ctx, oracle, small):
                 continue
             _check_against_oracle(gpu_ctx, oracle, sph, mat)
     finally:
-        del os.environ["RTDS_MEDIAN_SMALL"]
+        gpu_ctx.set_option("median_small", 0)
 
 
 def test_bvh_degenerate_input_is_an_error(gpu_ctx, oracle):

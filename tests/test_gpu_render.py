@@ -106,10 +106,14 @@ def test_render_multisample_and_ranks(gpu_ctx, oracle):
         assert rows_seen == H and np.array_equal(frame, full)
 
 
-def test_fused_strip_kernel_is_exact_too(gpu_ctx, oracle, monkeypatch):
+def test_fused_strip_kernel_is_exact_too(gpu_ctx, oracle):
     """RTDS_STRIP=1: the fused render + in-block MT19937 kernel (a measured negative result for speed)
     must still produce the reference's frame: default config md5, ragged multi-sample multi-rank frames."""
-    monkeypatch.setenv("RTDS_STRIP", "1")
+    with T.option(gpu_ctx, "strip", 1):
+        _strip_checks(gpu_ctx, oracle)
+
+
+def _strip_checks(gpu_ctx, oracle):
     sph, mat = T.bunny_scene()
     gpu_ctx.set_spheres(sph, mat)
     gpu_ctx.build(rt.BVH)
@@ -142,7 +146,7 @@ def test_rtds_frame_equals_the_three_calls(gpu_ctx):
 
 
 @pytest.mark.parametrize("acc", ["BVH", "LBVH"])
-def test_packet_traversal_equals_single_ray_and_reference_order(gpu_ctx, oracle, monkeypatch, acc):
+def test_packet_traversal_equals_single_ray_and_reference_order(gpu_ctx, oracle, acc):
     """aa_samples % 4 == 0 takes the packet kernel (four samples of a pixel share every node load): hit ids, float sums
     and bytes must equal the unpruned reference traversal (exact=1), the single-ray ordered kernel (RTDS_PACKET=0) and
     the CPU restatement; 8 spp = two packets per pixel, image centre included (mixed-octant pixels fall back)."""
@@ -154,11 +158,10 @@ def test_packet_traversal_equals_single_ray_and_reference_order(gpu_ctx, oracle,
     W, H, spp = 400, 300, 8
     pk = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True)     # default: interior boxes tested once per packet (hull)
     ex = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True, exact=True)
-    monkeypatch.setenv("RTDS_HULL", "0")                                   # interior boxes tested per ray
-    pr = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True)
-    monkeypatch.delenv("RTDS_HULL")
-    monkeypatch.setenv("RTDS_PACKET", "0")
-    sr = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True)
+    with T.option(gpu_ctx, "hull", 0):                                      # interior boxes tested per ray
+        pr = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True)
+    with T.option(gpu_ctx, "packet", 0):
+        sr = gpu_ctx.render(a, W, H, spp, want_hit=True, want_accum=True)
     assert pk[3]["node_tests"] < pr[3]["node_tests"] and pk[3]["node_visits"] <= 1.05 * pr[3]["node_visits"]
     for other in (ex, sr, pr):
         assert np.array_equal(pk[1], other[1]) and pk[2].tobytes() == other[2].tobytes() and np.array_equal(pk[0], other[0])
@@ -214,41 +217,3 @@ def test_visible_clones_variant_packet_equals_reference_traversal(gpu_ctx, oracl
     sh, _, _, st_s = gpu_ctx.render(rt.LBVH, W, H, spp, shadows=1)
     sh_e, _, _, _ = gpu_ctx.render(rt.LBVH, W, H, spp, shadows=1, exact=True)
     assert np.array_equal(sh, sh_e) and st_s["shadow_rays"] > 0
-
-
-@pytest.mark.parametrize("W,H,spp", [(640, 480, 1), (401, 299, 1), (322, 203, 3), (400, 300, 2)])
-def test_quad_packets_equal_single_ray(gpu_ctx, oracle, monkeypatch, W, H, spp):
-    """RTDS_QUAD=1: packets of 2x2 neighbouring pixels (render_quad_kernel) must give the single-ray kernel's hit ids, sums and
-    bytes, ragged frames and a rank's interleaved tiles included."""
-    sph, mat = T.bunny_scene()
-    gpu_ctx.set_spheres(sph, mat)
-    gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
-    ref = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True)
-    ref_r1 = gpu_ctx.render(rt.LBVH, W, H, spp, rank=1, world=3)
-    monkeypatch.setenv("RTDS_QUAD", "1")
-    quad = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True)
-    quad_r1 = gpu_ctx.render(rt.LBVH, W, H, spp, rank=1, world=3)
-    assert np.array_equal(quad[1], ref[1]) and quad[2].tobytes() == ref[2].tobytes() and np.array_equal(quad[0], ref[0])
-    rows = rt.owned_rows(H, 8, 1, 3)
-    assert np.array_equal(quad_r1[0][rows], ref_r1[0][rows])
-    assert quad[3]["primary_rays"] == W * H * spp and quad[3]["node_visits"] < 0.6 * ref[3]["node_visits"]
-
-
-@pytest.mark.skipif(not os.environ.get("RTDS_TEST_EXPERIMENTAL"), reason="opt-in kernel finished after round 1's GPU budget was spent (compiled, "
-                    "never run on hardware): RTDS_TEST_EXPERIMENTAL=1 runs it - the first thing to do in the next round")
-@pytest.mark.parametrize("W,H,spp", [(640, 480, 4), (401, 299, 4), (322, 203, 8)])
-def test_two_pixel_packets_equal_sample_packets(gpu_ctx, monkeypatch, W, H, spp):
-    """RTDS_PACKET2=1: 8-ray packets (2 adjacent pixels x 4 samples, render_packet2_kernel / traverse_packet_n) must give the
-    4-ray sample-packet kernel's hit ids, sums and bytes; odd widths and a rank's interleaved tiles included."""
-    sph, mat = T.bunny_scene()
-    gpu_ctx.set_spheres(sph, mat)
-    gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
-    ref = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True)
-    ref_r1 = gpu_ctx.render(rt.LBVH, W, H, spp, rank=1, world=3)
-    monkeypatch.setenv("RTDS_PACKET2", "1")
-    two = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True)
-    two_r1 = gpu_ctx.render(rt.LBVH, W, H, spp, rank=1, world=3)
-    assert np.array_equal(two[1], ref[1]) and two[2].tobytes() == ref[2].tobytes() and np.array_equal(two[0], ref[0])
-    rows = rt.owned_rows(H, 8, 1, 3)
-    assert np.array_equal(two_r1[0][rows], ref_r1[0][rows])
-    assert two[3]["primary_rays"] == W * H * spp and two[3]["node_visits"] < 0.7 * ref[3]["node_visits"]

@@ -1,5 +1,5 @@
 """A/B of render-kernel variants on the bench frame (resident scene + tree): kernel ms, counters, frame identity.
-usage: python tools/ab_render.py VAR=a,b[,c] [shadows]   e.g. RTDS_HULL=0,1   (GPU box)"""
+usage: python tools/ab_render.py option=a,b[,c] [shadows]   e.g. hull=0,1   (GPU box; option = an rtds_set_option name)"""
 import hashlib
 import os
 import sys
@@ -29,7 +29,7 @@ if os.environ.get("AB_DEVICE"):            # resident path: rtds_render_device i
 ref = None
 for rep in range(2):
     for val in vals:
-        os.environ[var] = val
+        ctx.set_option(var.lower().replace("rtds_", ""), int(val))
         ms = []
         for i in range(6):
             if dev is not None:

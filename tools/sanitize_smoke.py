@@ -60,9 +60,9 @@ def main():
         ctx.render(acc, W, H, 2, rank=1, world=3)     # a rank's interleaved tiles
         done.append((acc, kw))
     ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
-    os.environ["RTDS_STRIP"] = "1"
+    ctx.set_option("strip", 1)
     ctx.render(rt.LBVH, W, H, 2)                      # fused strip kernel (opt-in)
-    del os.environ["RTDS_STRIP"]
+    ctx.set_option("strip", 0)
     ctx.build(rt.KDTREE)
     ctx.export_kd()
     ctx.render(rt.KDTREE, W, H, 2)

@@ -1,4 +1,4 @@
-"""CPU model (oracle/oracle.cpp orc_packet_model): dependent node visits of the ordered packet traversal on the BENCH frame
+"""CPU model (tools/perf_model.cpp): dependent node visits of the ordered packet traversal on the BENCH frame
 (bunny x30 clones, 3840x2160, 4 spp, LBVH) over the binary tree and over its 4-wide collapse - design evidence for
 DESIGN.md section 10.1. Runs on the CPU only (rows sub-sampled). usage: python tools/wide4_model.py [row_step=48]"""
 import os
@@ -17,6 +17,9 @@ clones = int(os.environ.get("CLONES", "30"))
 shift = int(os.environ.get("CLONE_SHIFT", "20"))
 W, H, SPP = 3840, 2160, 4
 oracle = T.Oracle()
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from perf_model import PerfModel  # noqa: E402
+model = PerfModel()
 if os.environ.get("SCENE") == "config4":          # the 7 M-sphere torus-knot stand-in, 1 spp: "packets" of four identical rays
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import run_configs
@@ -39,7 +42,7 @@ for y in range(step // 2, H, step):
     # the exact per-ray hits of all four samples (render_rows reports the last sample's hit only)
     h_exact, _, _ = oracle.trace(sph, nodes, order, np.zeros((1, 3), np.float32), np.ascontiguousarray(d).reshape(-1, 3), tie_by_objid=1)
     for use_wide in (False, True):
-        hit, st = oracle.packet_model(sph, nodes, wide, order, d, use_wide=use_wide, order_mode=ORDER, quant_bits=QUANT if use_wide else 0)
+        hit, st = model.packet_model(sph, nodes, wide, order, d, use_wide=use_wide, order_mode=ORDER, quant_bits=QUANT if use_wide else 0)
         hits_ok &= bool(np.array_equal(hit.reshape(-1), h_exact))
         tot[use_wide] = st if tot[use_wide] is None else {k: (max(tot[use_wide][k], v) if k == "max_stack" else tot[use_wide][k] + v) for k, v in st.items()}
 print("model hits == unpruned reference traversal on every sampled ray:", hits_ok)
