@@ -22,6 +22,7 @@ cpu_baseline = the UNMODIFIED reference (oracle/_ref, kind "reference"; else the
          core on a bounded sample of the same frame's rows.
 """
 import argparse
+import hashlib
 import ctypes as C
 import json
 import os
@@ -36,14 +37,36 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
-W, H, SPP, CLONES = 3840, 2160, 4, 30
 TILE_ROWS = 8
-WORKLOAD = ("buddha-standin: bunny.obj x30 clones (NUMBER_OF_CLONES, main.cpp:61) = 1,078,411 spheres, "
-            "3840x2160, aa_samples 4, dataStructure LBVH, 1 light, shadows off (reference behaviour)")
 
 
 def bunny_vertices():
     return np.fromfile(os.path.join(ROOT, "tests", "golden", "bunny_vertices.f32"), np.float32).reshape(-1, 3)
+
+
+class Workload:
+    """One BASELINE.json config (or its stand-in). config3 is the one `metric` is quoted on and the default."""
+
+    def __init__(self, key, text, scene, acc, mode, accel, ref_acc, W=3840, H=2160, spp=4, shadows=0, lights=None, build_kw=None,
+                 cpu_bands=60):
+        self.key, self.text, self.scene, self.acc, self.mode, self.accel, self.ref_acc = key, text, scene, acc, mode, accel, ref_acc
+        self.W, self.H, self.spp, self.shadows, self.lights, self.build_kw, self.cpu_bands = W, H, spp, shadows, lights, build_kw or {}, cpu_bands
+
+
+def workloads(rt):
+    import rtds_b200.standins as S
+    return {
+        "config3": Workload("config3", "buddha-standin: bunny.obj x30 clones (NUMBER_OF_CLONES, main.cpp:61) = 1,078,411 spheres, "
+                            "3840x2160, aa_samples 4, dataStructure LBVH, 1 light, shadows off (reference behaviour)",
+                            lambda: rt.scene_from_vertices(bunny_vertices(), 30), rt.LBVH, rt.MODE_TRUE,
+                            "LBVH true mode (30-bit Morton, onesweep, Karras, atomic refit)", rt.LBVH),
+        "config4": Workload("config4", "dragon-standin: 7,000,000 spheres on a displaced torus knot (+ ground sphere), 3840x2160, aa_samples 1, "
+                            "binned-SAH BVH build + traversal, 1 light, shadows off",
+                            lambda: S.torus_knot_scene(7_000_000), rt.BVH, rt.MODE_SAH, "BVH, binned SAH (16 bins)", rt.BVH, spp=1, cpu_bands=120),
+        "config5": Workload("config5", "city+trees-standin: 342,989 spheres (90,811 'city' + 252,178 'trees', 10 % REFLECTION_AND_REFRACTION, "
+                            "10 % REFLECTION) + ground, 3 lights, shadow rays on, 3840x2160, aa_samples 16, LBVH",
+                            S.city_trees_scene, rt.LBVH, rt.MODE_TRUE, "LBVH true mode", rt.BVH, spp=16, shadows=1, lights=S.LIGHTS3, cpu_bands=12),
+    }
 
 
 def measured_peak():
@@ -138,8 +161,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline
 # ------------------------------------------------------------------------------------------------------
-def sample_bands(n_bands, band_rows):
-    """Evenly spaced bands of rows over the frame (the image is sky above, bunny in the middle, ground below)."""
+def sample_bands(H, n_bands, band_rows):
+    """Evenly spaced bands of rows over the frame (the image is sky above, the model in the middle, ground below)."""
     step = H // n_bands
     return [(i * step + (step - band_rows) // 2, i * step + (step - band_rows) // 2 + band_rows) for i in range(n_bands)]
 
@@ -148,39 +171,65 @@ class CpuArm:
     """The reference's own CPU implementation: oracle/_ref (unmodified reference, kind 'reference') when it was
     compiled, else the oracle port (kind 'port')."""
 
-    def __init__(self):
+    def __init__(self, wl, scene=None):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import conftest as T
-        self.T = T
+        self.T, self.wl = T, wl
         self.rt = entry.load_rtds()
-        self.sph, self.mat = self.rt.scene_from_vertices(bunny_vertices(), CLONES)
+        self.sph, self.mat = scene if scene is not None else wl.scene()
         ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_oracle.so")
         self.kind = "reference" if os.path.exists(ref_so) else "port"
         if self.kind == "reference":
             self.ref = T.Ref()
-            self.ref.scene_from_spheres(self.sph, self.mat)
-            t0 = time.perf_counter()
-            self.total_nodes, self.build_s = self.ref.build(self.rt.LBVH)     # constructLBVHTree, as main.cpp:832
-            self.build_wall = time.perf_counter() - t0
+            self.build(wl.ref_acc)
         else:
             self.oracle = T.Oracle()
             t0 = time.perf_counter()
-            rc, self.nodes, self.order, _ = self.oracle.build_bvh(self.sph, self.sph.shape[0] - 1)
+            n_use = self.sph.shape[0] - (1 if wl.ref_acc == self.rt.LBVH else 0)     # the reference's LBVH drops the last object
+            rc, self.nodes, self.order, _ = self.oracle.build_bvh(self.sph, n_use)
             self.build_s = self.build_wall = time.perf_counter() - t0
             self.total_nodes = self.nodes.shape[0]
+            self.acc = wl.ref_acc
 
-    def render_bands(self, bands):
-        rays, secs = 0, 0.0
+    def build(self, acc):
+        """(Re)build the reference's structure: constructLBVHTree (main.cpp:832) or constructBVHNew (main.cpp:800). The
+        builders reorder the scene vector, so the scene is loaded afresh first."""
+        self.ref.scene_from_spheres(self.sph, self.mat)
+        if self.wl.lights is not None:
+            self.ref.lib.ref_set_lights(self.T.Oracle._p(np.ascontiguousarray(self.wl.lights, np.float32)), int(self.wl.lights.shape[0]))
+        t0 = time.perf_counter()
+        self.total_nodes, self.build_s = self.ref.build(acc)
+        self.build_wall = time.perf_counter() - t0
+        self.acc = acc
+
+    def render_bands(self, bands, keep=False):
+        """-> rays, seconds inside the reference's ray loop, [rgb rows per band] (keep=True)."""
+        wl = self.wl
+        rays, secs, pix = 0, 0.0, []
         for (y0, y1) in bands:
             if self.kind == "reference":
-                _, _, _, s = self.ref.render_rows(self.rt.LBVH, W, H, SPP, y0, y1)
+                rgb, _, _, s = self.ref.render_rows(self.acc, wl.W, wl.H, wl.spp, y0, y1)
             else:
                 t0 = time.perf_counter()
-                self.oracle.render_rows(self.sph, self.mat, self.nodes, self.order, W, H, SPP, y0, y1, want_hit=False)
+                rgb = self.oracle.render_rows(self.sph, self.mat, self.nodes, self.order, wl.W, wl.H, wl.spp, y0, y1, want_hit=False,
+                                              lights=wl.lights)[0]
                 s = time.perf_counter() - t0
-            rays += (y1 - y0) * W * SPP
+            rays += (y1 - y0) * wl.W * wl.spp
             secs += s
-        return rays, secs
+            if keep:
+                pix.append(rgb)
+        return rays, secs, pix
+
+
+def band_diff(frame, bands, pix):
+    """max |a - b| and the number of differing pixels between a full frame and the reference's rows of `bands`."""
+    mx, bad, tot = 0, 0, 0
+    for (y0, y1), rgb in zip(bands, pix):
+        d = np.abs(frame[y0:y1].astype(np.int16) - rgb.astype(np.int16))
+        mx = max(mx, int(d.max()))
+        bad += int((d.max(axis=2) > 0).sum())
+        tot += d.shape[0] * d.shape[1]
+    return mx, bad, tot
 
 
 def unmodified_binary_baseline():
@@ -201,12 +250,30 @@ def unmodified_binary_baseline():
         wall = time.perf_counter() - t0
         b = re.search(r"construct BVH Tree .... \nDone .... Time: ([0-9.eE+-]+)s", r.stdout)
         t = re.search(r"Total time spent: ([0-9.eE+-]+)s", r.stdout)
-        return {"config": "settings.h defaults: bunny 640x480 aa1 BVH, 307,200 rays, incl. load + per-pixel printf + PPM write",
-                "build_s": float(b.group(1)) if b else None, "total_s": float(t.group(1)) if t else None, "wall_s": wall, "cores": 1}
+        out = {"config": "settings.h defaults: bunny 640x480 aa1 BVH, 307,200 rays, incl. load + per-pixel printf + PPM write",
+               "build_s": float(b.group(1)) if b else None, "total_s": float(t.group(1)) if t else None, "wall_s": wall, "cores": 1}
+        # the same run through this repo's C++ driver (host/main.cpp -> librtds.so), COLD: a fresh process pays CUDA context
+        # creation, the first cudaMallocs and the one-off MT19937 snapshot walk - nothing is warmed up
+        mainp = os.path.join(ROOT, "raytracer-data-structures_b200", "rtds_main")
+        if os.path.exists(mainp):
+            try:
+                env = dict(os.environ, RTDS_MODELS_DIR=os.path.join(d, "models"), RTDS_OUT=os.path.join(d, "out.ppm"))
+                t0 = time.perf_counter()
+                r2 = subprocess.run([mainp], cwd=d, env=env, capture_output=True, text=True, timeout=300)
+                out["rtds_main_cold_wall_s"] = time.perf_counter() - t0
+                t2 = re.search(r"Total time spent: ([0-9.eE+-]+)s", r2.stdout)
+                out["rtds_main_total_s"] = float(t2.group(1)) if t2 else None
+                ref_ppm = os.path.join(d, "output.ppm")
+                if os.path.exists(ref_ppm) and os.path.exists(os.path.join(d, "out.ppm")):
+                    out["rtds_main_ppm_identical"] = open(ref_ppm, "rb").read() == open(os.path.join(d, "out.ppm"), "rb").read()
+            except Exception as ex:
+                out["rtds_main_cold_wall_s"] = None
+                out["rtds_main_error"] = repr(ex)
+        return out
 
 
 def _child_render(arm, bands, conn):
-    rays, secs = arm.render_bands(bands)
+    rays, secs, _ = arm.render_bands(bands)
     conn.send((rays, secs))
     conn.close()
 
@@ -217,10 +284,12 @@ def run_reference(args):
         return 0
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    arm = CpuArm()
+    rt = entry.load_rtds()
+    wl = workloads(rt)[args.workload]
+    arm = CpuArm(wl)
     # bounded sample: 2 rows per band, as many bands as keep one step near ~8 s on `cores` processes
-    n_bands = max(cores, min(270, cores * 12))
-    bands = sample_bands(n_bands, 2)
+    n_bands = max(cores, min(270, cores * 12 * 4 // wl.spp))
+    bands = sample_bands(wl.H, n_bands, 2)
     chunks = [bands[i::cores] for i in range(cores)]
     ctx = mp.get_context("fork")        # children share the built scene + tree copy-on-write
 
@@ -247,12 +316,13 @@ def run_reference(args):
         rays += r
         secs += s
     value = rays / secs / 1e6
-    sample = f"{n_bands} bands x 2 rows of the 3840x2160x4spp frame per step ({rays // max(args.steps, 1)} rays), {cores} processes"
+    sample = (f"{n_bands} bands x 2 rows of the {wl.W}x{wl.H}x{wl.spp}spp frame per step ({rays // max(args.steps, 1)} rays), {cores} processes; "
+              "primary rays only (the reference's trace_more is a stub: it casts no shadow rays)")
     line = {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "width": W, "height": H, "aa_samples": SPP, "n_prims": int(arm.sph.shape[0]),
-                       "accel": "LBVH (reference: constructLBVHTree)"},
+            "config": {"workload": wl.text, "width": wl.W, "height": wl.H, "aa_samples": wl.spp, "n_prims": int(arm.sph.shape[0]),
+                       "accel": "reference: " + ("constructLBVHTree" if wl.ref_acc == rt.LBVH else "constructBVHNew")},
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": arm.kind, "sample": sample,
                              "build_s": arm.build_s, "build_ms_per_mprim": 1000 * arm.build_s / (arm.sph.shape[0] / 1e6)},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -264,6 +334,10 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -291,59 +365,61 @@ def run_ours(args):
             os.close(saved_stdout)
 
     rt = entry.load_rtds()
+    wl = workloads(rt)[args.workload]
+    W, H, SPP = wl.W, wl.H, wl.spp
     ctx = rt.Rtds(local_rank)              # raises if the CUDA library / GPU is missing: no fallback
-    sph, mat = rt.scene_from_vertices(bunny_vertices(), CLONES)
+    sph, mat = wl.scene()
     n = sph.shape[0]
     sph_pin = torch.from_numpy(sph).pin_memory()
     mat_pin = torch.from_numpy(mat).pin_memory()
+    if wl.lights is not None:
+        ctx.set_lights(wl.lights)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # resident scene + tree
+    # resident scene + structure
     ctx.set_spheres(sph, mat)
-    build_stats = [ctx.build(rt.LBVH, mode=rt.MODE_TRUE) for _ in range(4)][1:]
+    build_stats = [ctx.build(wl.acc, mode=wl.mode, **wl.build_kw) for _ in range(4)][1:]
     build_ms = float(np.median([b["ms"] for b in build_stats]))
 
-    rows = rt.rows_for_rank(H, TILE_ROWS, rank, world)
     max_rows = max(rt.rows_for_rank(H, TILE_ROWS, r, world) for r in range(world))
     my_rows = torch.zeros((max_rows, W, 3), dtype=torch.uint8, device=dev)
     gathered = [torch.zeros_like(my_rows) for _ in range(world)] if (world > 1 and rank == 0) else None
     frame_host = torch.zeros((H, W, 3), dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    params = ctx.render_params(W, H, SPP, exact=False, rank=rank, world=world, tile_rows=TILE_ROWS)
+    params = ctx.render_params(W, H, SPP, exact=False, rank=rank, world=world, tile_rows=TILE_ROWS, shadows=wl.shadows)
     row_index = [torch.from_numpy(rt.owned_rows(H, TILE_ROWS, r, world)).to(dev) for r in range(world)] if rank == 0 else None
     frame_dev = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev) if rank == 0 else None
 
     # N > 1: the frame is assembled by the render kernels themselves. Rank 0 owns one frame buffer; every rank maps it
     # (CUDA IPC) and stores its tiles straight into it over NVLink, then raises its flag; rank 0 waits for all flags on
-    # its stream. `--gather nccl` keeps the older path (per-rank buffers + NCCL gather) for comparison.
+    # its stream. `--gather nccl` times the older path (per-rank buffers + NCCL gather) instead; both are VERIFIED below.
     p2p = world > 1 and args.gather == "p2p"
     seq = [0]
-    if p2p:
+    if world > 1:
         box = [ctx.shared_frame_create(W, H, world) if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         if rank != 0:
             ctx.shared_frame_open(box[0], W, H, world, rank)
 
-    def step_resident():
-        if p2p:
-            seq[0] += 1
-            return ctx.render_shared(rt.LBVH, params, seq[0])
-        st = ctx.render_device(rt.LBVH, params, my_rows.data_ptr())
+    def render_p2p(p):
+        seq[0] += 1
+        return ctx.render_shared(wl.acc, p, seq[0])
+
+    def render_gather(p):
+        st = ctx.render_device(wl.acc, p, my_rows.data_ptr())
         if world > 1:
             dist.gather(my_rows, gathered, dst=0)
         return st
 
-    def assemble_and_download():
-        if rank != 0:
-            return
-        if p2p:
-            rc = ctx.lib.rtds_shared_frame_read(ctx.ctx, C.c_void_p(frame_host.data_ptr()))
-            assert rc == 0, ctx.lib.rtds_last_error()
-            return
+    def step_resident():
+        return render_p2p(params) if p2p else render_gather(params)
+
+    def assemble_gathered():
+        """rank 0: the gathered per-rank rows -> frame_host"""
         if world > 1:
             for r in range(world):
                 frame_dev[row_index[r]] = gathered[r][: row_index[r].numel()]
@@ -352,29 +428,40 @@ def run_ours(args):
             frame_host.copy_(my_rows[:H], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    e2e_params = ctx.render_params(W, H, SPP, exact=False)
+    def assemble_and_download():
+        if rank != 0:
+            return
+        if p2p:
+            rc = ctx.lib.rtds_shared_frame_read(ctx.ctx, C.c_void_p(frame_host.data_ptr()))
+            assert rc == 0, ctx.lib.rtds_last_error()
+            return
+        assemble_gathered()
+
+    e2e_params = ctx.render_params(W, H, SPP, exact=False, shadows=wl.shadows)
     e2e_stats = rt.RenderStats()
     e2e_bp = rt.BuildParams()
-    e2e_bp.mode = rt.MODE_TRUE
+    e2e_bp.mode = wl.mode
+    for k, v in wl.build_kw.items():
+        setattr(e2e_bp, k, v)
 
     def step_e2e():
         # what main.cpp does per run, through the C ABI with host buffers
         if world == 1:
             # rtds_frame = rtds_set_spheres + rtds_build + rtds_render in one synchronous call (stages overlapped inside)
-            rc = ctx.lib.rtds_frame(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), n, rt.LBVH, C.byref(e2e_bp),
+            rc = ctx.lib.rtds_frame(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), n, wl.acc, C.byref(e2e_bp),
                                     C.byref(e2e_params), C.c_void_p(frame_host.data_ptr()), None, C.byref(e2e_stats))
             assert rc == 0, ctx.lib.rtds_last_error()
             return None
         if p2p:
             # rtds_frame_shared = the same per rank with rtds_render_shared at the end; rank 0 then downloads the assembled frame
             seq[0] += 1
-            rc = ctx.lib.rtds_frame_shared(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), n, rt.LBVH, C.byref(e2e_bp),
+            rc = ctx.lib.rtds_frame_shared(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), n, wl.acc, C.byref(e2e_bp),
                                            C.byref(params), seq[0], None, C.byref(e2e_stats))
             assert rc == 0, ctx.lib.rtds_last_error()
             assemble_and_download()
             return None
         ctx.lib.rtds_set_spheres(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), n)
-        ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+        ctx.build(wl.acc, mode=wl.mode, **wl.build_kw)
         st = step_resident()
         assemble_and_download()
         return st
@@ -404,113 +491,207 @@ def run_ours(args):
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     per_step, stats, clocks = timed(step_resident, args.steps, args.warmup, sampler)
-    total_rays = W * H * SPP
     ms_per_step = float(np.mean(per_step))
+    rays_t = torch.tensor([float(stats[-1]["rays"])], dtype=torch.float64, device=dev)      # all rays traced: primary (+ shadow + secondary)
+    if world > 1:
+        dist.all_reduce(rays_t)
+    total_rays = int(rays_t.item())
+    primary_rays = W * H * SPP
     value = total_rays / (ms_per_step * 1e-3) / 1e6
 
-    # side number (not the headline): the same frame with the shadow query on (extension: trace_more is a stub in the
-    # reference), rays = primary + shadow rays actually traced
-    sh_params = ctx.render_params(W, H, SPP, exact=False, rank=rank, world=world, tile_rows=TILE_ROWS, shadows=1)
-
-    def step_shadows():
-        if p2p:
-            seq[0] += 1
-            return ctx.render_shared(rt.LBVH, sh_params, seq[0])
-        st = ctx.render_device(rt.LBVH, sh_params, my_rows.data_ptr())
+    # side number (not the headline) for the shadow-free workloads: the same frame with the shadow query on (extension: trace_more is
+    # a stub in the reference), rays = primary + shadow rays actually traced
+    with_shadows = None
+    if not wl.shadows:
+        sh_params = ctx.render_params(W, H, SPP, exact=False, rank=rank, world=world, tile_rows=TILE_ROWS, shadows=1)
+        sh_steps, sh_stats, _ = timed(lambda: render_p2p(sh_params) if p2p else render_gather(sh_params), 3, 1)
+        sh_rays = torch.tensor([float(sh_stats[-1]["rays"])], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.gather(my_rows, gathered, dst=0)
-        return st
-
-    sh_steps, sh_stats, _ = timed(step_shadows, 3, 1)
-    sh_rays = torch.tensor([float(sh_stats[-1]["rays"])], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(sh_rays)
+            dist.all_reduce(sh_rays)
+        with_shadows = {"value": sh_rays.item() / (float(np.mean(sh_steps)) * 1e-3) / 1e6, "unit": "Mrays/s",
+                        "ms_per_step": float(np.mean(sh_steps)), "rays_per_step": int(sh_rays.item()),
+                        "note": "extension: shadow query on (the reference's trace_more is a stub); primary + shadow rays"}
 
     e2e_steps, _, _ = timed(step_e2e, max(2, min(args.steps, 5)), 1)
     e2e_ms = float(np.mean(e2e_steps))
     e2e_value = total_rays / (e2e_ms * 1e-3) / 1e6
+    e2e_sha = sha(frame_host.numpy()) if rank == 0 else None
+
+    # ---- frame verification (outside every timed region) ------------------------------------------------------------
+    # `frame_sha256` is the hash of THE frame of this workload (jitter offset 0): every N must report the same one.
+    # N > 1: the frame assembled by peer stores AND the one assembled by the NCCL gather are compared byte for byte with
+    # the frame rank 0 renders alone (world = 1), once at jitter offset 0 and once at a fresh offset no earlier step used
+    # (a tile a rank failed to deliver would otherwise be masked by the identical tile of the previous frame).
+    verify = {}
+    ok = True
+    for tag, joff in (("", 0), ("_fresh_jitter", 977 * 1248)):
+        p_multi = ctx.render_params(W, H, SPP, exact=False, rank=rank, world=world, tile_rows=TILE_ROWS, shadows=wl.shadows, jitter_offset=joff)
+        single = None
+        if rank == 0:
+            single = np.zeros((H, W, 3), np.uint8)
+            ctx.render(wl.acc, W, H, SPP, out=single, shadows=wl.shadows, jitter_offset=joff)
+            verify["frame_sha256" + tag] = sha(single)
+        if world > 1:
+            barrier()
+            render_p2p(p_multi)
+            barrier()
+            if rank == 0:
+                got = ctx.shared_frame_read(W, H)
+                verify["p2p_matches_single_rank" + tag] = bool(np.array_equal(got, single))
+                ok &= verify["p2p_matches_single_rank" + tag]
+            barrier()
+            render_gather(p_multi)
+            if rank == 0:
+                assemble_gathered()
+                verify["nccl_gather_matches_single_rank" + tag] = bool(np.array_equal(frame_host.numpy(), single))
+                ok &= verify["nccl_gather_matches_single_rank" + tag]
+        else:
+            render_gather(p_multi)
+            torch.cuda.synchronize()
+            verify["resident_matches_host_render" + tag] = bool(np.array_equal(my_rows[:H].cpu().numpy(), single))
+            ok &= verify["resident_matches_host_render" + tag]
+    if rank == 0:
+        verify["e2e_frame_matches"] = e2e_sha == verify["frame_sha256"]
+        ok &= verify["e2e_frame_matches"]
+        verify["frame_matches_single_rank"] = bool(ok)
 
     # counters (sum over ranks) and rank 0's kernel for the roofline
     k_ms = float(np.mean([s["ms_kernel"] for s in stats]))
-    cnt = torch.tensor([stats[-1]["node_tests"], stats[-1]["prim_tests"], stats[-1]["primary_rays"], stats[-1]["node_visits"]],
+    cnt = torch.tensor([stats[-1]["node_tests"], stats[-1]["prim_tests"], stats[-1]["rays"], stats[-1]["node_visits"]],
                        dtype=torch.float64, device=dev)
     mine = cnt.clone()
     if world > 1:
         dist.all_reduce(cnt)
     launches_per_step = stats[-1]["kernel_launches"]
 
+    rc_exit = 0
     if rank == 0:
         peak, peak_src = measured_peak()
-        alg_bytes = 32.0 * mine[0].item() + 16.0 * mine[1].item() + 16.0 * mine[2].item()   # this rank's launch
-        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        traffic, ncu = None, {}
-        tpath = os.path.join(ROOT, "profiles", "render_kernel_traffic.json")
-        if world == 1 and os.path.exists(tpath):
+        alg_bytes = 32.0 * mine[0].item() + 16.0 * mine[1].item() + 16.0 * mine[2].item()   # this rank's launch, SURVEY 8d
+        alg_gbs = alg_bytes / (k_ms * 1e-3) / 1e9
+        kernel_name = {"config3": "render_packet_kernel<0,1>", "config4": "render_kernel<1>", "config5": "render_full_kernel<1>"}[wl.key]
+        ncu = {}
+        tpath = os.path.join(ROOT, "profiles", f"render_kernel_traffic_{wl.key}.json")
+        if os.path.exists(tpath):
             try:
                 ncu = json.load(open(tpath))
-                traffic = ncu.get("dram_bytes_per_launch")
             except Exception:
-                traffic, ncu = None, {}
-        # what HAS to cross HBM per launch: the ray directions in (12 B/ray), the RGB8 frame out (3 B/pixel) and every
+                ncu = {}
+        traffic = ncu.get("dram_bytes_per_launch") if world == 1 else None
+        # what HAS to cross HBM per launch: the ray directions in (12 B/primary ray), the RGB8 frame out (3 B/pixel) and every
         # distinct node / leaf record the frame touches once (bounded above by the whole tree: 64 B/node + 24 B/leaf)
-        my_rays = mine[2].item()
-        compulsory = 12.0 * my_rays + 3.0 * my_rays / SPP + 88.0 * n
+        my_primary = float(stats[-1]["primary_rays"])
+        compulsory = 12.0 * my_primary + 3.0 * my_primary / SPP + 88.0 * n
+        roof = {"kernel": kernel_name + " (rank 0's launch)", "kernel_ms": k_ms,
+                "algorithmic_gbs": alg_gbs, "algorithmic_frac_of_hbm_peak": alg_gbs / peak, "hbm_peak_gbs": peak, "peak_source": peak_src,
+                "traffic": traffic,
+                "dram_gbs": (traffic / (k_ms * 1e-3) / 1e9) if traffic else None,
+                "dram_frac_of_hbm_peak": (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "compulsory": {"bytes": compulsory, "gbs": compulsory / (k_ms * 1e-3) / 1e9,
+                               "what": "bytes that must cross HBM per launch: 12 B/ray directions in + 3 B/pixel out + the tree once"},
+                "ncu": {k: ncu.get(k) for k in ("kernel", "issue_active_pct", "warps_active_pct", "thread_inst_per_warp_inst", "l1tex_hit_pct", "lts_hit_pct",
+                                                "pipe_alu_pct", "pipe_fma_pct", "l1tex_throughput_pct", "lts_throughput_pct", "dram_throughput_pct",
+                                                "gpu_time_us_under_ncu", "source")} if ncu else None}
+        if ncu.get("issue_active_pct") is not None:
+            # The traversal kernels are NOT bound by HBM (ncu: DRAM at a few % of peak, the tree is served from L1/L2); what binds
+            # them is the issue rate / latency. bound and frac say so: issue slots busy, from the committed ncu capture of this kernel.
+            roof.update({"bound": "issue", "achieved": ncu["issue_active_pct"], "peak": 100.0, "unit": "% of issue slots busy (ncu smsp__issue_active)",
+                         "frac": ncu["issue_active_pct"] / 100.0,
+                         "note": ("bound = what ncu measures: this kernel is issue/latency-bound, not HBM-bound (dram_frac_of_hbm_peak). "
+                                  "algorithmic_gbs is SURVEY 8d's formula (32 B x slab tests + 16 B x primitive tests + 16 B per ray, from the "
+                                  "kernel's own counters, / kernel_ms measured live with CUDA events): it prices every node fetch as if it came from "
+                                  "HBM, but one node load feeds the 4 samples of a pixel and the stream is served by registers, L1 and L2, so it is "
+                                  "NOT an HBM fraction and may exceed the HBM peak. `achieved`/`frac` come from profiles/render_kernel_traffic_*.json "
+                                  "(ncu --set full of the same kernel), everything else is measured in this run.")})
+        else:
+            roof.update({"bound": "hbm", "achieved": alg_gbs, "peak": peak, "unit": "GB/s", "frac": alg_gbs / peak,
+                         "note": "no ncu capture of this kernel committed: algorithmic bytes (SURVEY 8d) / kernel time against the HBM peak"})
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "width": W, "height": H, "aa_samples": SPP, "n_prims": int(n),
-                           "accel": "LBVH true mode (30-bit Morton, onesweep, Karras, atomic refit)", "traversal": "ordered, pruned (exact=0)",
+                "config": {"workload": wl.text, "width": W, "height": H, "aa_samples": SPP, "n_prims": int(n),
+                           "accel": wl.accel, "traversal": "ordered, pruned (exact=0)",
                            "partition": (f"interleaved {TILE_ROWS}-row scanline tiles over {world} rank(s); " +
                                          ("render kernels store RGB8 tiles straight into rank 0's frame over NVLink (CUDA IPC peer memory) + per-rank flags, no collective"
                                           if p2p else "NCCL gather of RGB8 rows")) if world > 1 else "single GPU",
-                           "l2": "flushed between timed steps (256 MiB fill); per-frame inputs (398 MB ray directions + 90 MB tree) exceed L2"},
-                "rays_per_step": total_rays,
-                "per_ray": {"slab_tests": cnt[0].item() / total_rays, "sphere_tests": cnt[1].item() / total_rays,
+                           "l2": "flushed between timed steps (256 MiB fill); per-frame inputs (ray directions + tree) exceed L2"},
+                "rays_per_step": total_rays, "primary_rays_per_step": primary_rays,
+                "per_ray": {"slab_tests": cnt[0].item() / total_rays, "prim_tests": cnt[1].item() / total_rays,
                             "node_visits": cnt[3].item() / total_rays,
                             "algorithmic_bytes": (32.0 * cnt[0].item() + 16.0 * cnt[1].item()) / total_rays + 16.0},
-                "build": {"lbvh_ms": build_ms, "ms_per_mprim": build_ms / (n / 1e6), "n_prims": int(n),
+                "build": {"ms": build_ms, "ms_per_mprim": build_ms / (n / 1e6), "n_prims": int(n), "accel": wl.accel,
                           "kernel_launches": build_stats[-1]["kernel_launches"]},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": "render_packet_kernel (rank 0's launch)", "kernel_ms": k_ms,
-                             "peak_source": peak_src,
-                             "compulsory": {"bytes": compulsory, "gbs": compulsory / (k_ms * 1e-3) / 1e9,
-                                            "frac": compulsory / (k_ms * 1e-3) / 1e9 / peak,
-                                            "what": "bytes that must cross HBM per launch: 12 B/ray directions in + 3 B/pixel out + the tree once"},
-                             "ncu": {k: ncu.get(k) for k in ("issue_active_pct", "warps_active_pct", "l1tex_hit_pct", "lts_hit_pct", "pipe_alu_pct",
-                                                             "pipe_fma_pct", "l1tex_throughput_pct", "dram_throughput_pct")} if ncu else None,
-                             "note": ("`achieved` follows SURVEY 8d (32 B x slab tests + 16 B x prim tests + 16 B per ray, from the kernel's own "
-                                      "counters; the packet kernel tests an interior box once per 4-ray packet, so slab tests/ray is a quarter "
-                                      "of the node boxes a ray meets). That stream is served from registers (one node load feeds the 4 samples "
-                                      "of a pixel), L1 and L2, so frac can exceed 1 and HBM is not the bound: measured DRAM traffic is `traffic` "
-                                      "bytes per launch (~`compulsory`); ncu (`ncu` block, profiles/) shows the kernel issue/latency-bound - "
-                                      "DESIGN.md section 8")},
+                "roofline": roof,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(2 * n * 16) * world,
                         "d2h_bytes_per_step": W * H * 3,
-                        "what": "per step: rtds_frame = rtds_set_spheres (H2D from pinned) + rtds_build(LBVH) + rtds_render into a pinned host frame, ray directions generated on a side stream meanwhile (N>1: rtds_frame_shared = the same with rtds_render_shared on every rank, then D2H of the assembled frame on rank 0)"},
-                "with_shadows": {"value": sh_rays.item() / (float(np.mean(sh_steps)) * 1e-3) / 1e6, "unit": "Mrays/s",
-                                 "ms_per_step": float(np.mean(sh_steps)), "rays_per_step": int(sh_rays.item()),
-                                 "note": "extension: shadow query on (the reference's trace_more is a stub); primary + shadow rays"},
+                        "what": "per step: rtds_frame = rtds_set_spheres (H2D from pinned) + rtds_build + rtds_render into a pinned host frame, ray directions generated on a side stream meanwhile (N>1: rtds_frame_shared = the same with rtds_render_shared on every rank, then D2H of the assembled frame on rank 0)"},
+                "with_shadows": with_shadows,
                 "gpu_launches": int(launches_per_step * args.steps * world),
                 "clocks": clocks}
+        line.update(verify)
         if world == 1 and not args.no_cpu_baseline:
             try:
-                arm = CpuArm()
-                bands = sample_bands(60, 2)
-                rays, secs = arm.render_bands(bands)
-                line["cpu_baseline"] = {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": 1, "kind": arm.kind,
-                                        "sample": f"60 bands x 2 rows of the same frame ({rays} rays), 1 thread",
-                                        "build_s": arm.build_s, "build_ms_per_mprim": 1000 * arm.build_s / (n / 1e6),
-                                        "unmodified_binary": unmodified_binary_baseline()}
+                line["cpu_baseline"], line["parity"] = cpu_baseline_and_parity(rt, ctx, wl, sph, mat)
+                if line["parity"] and line["parity"].get("max_abs_diff", 0) > 1:
+                    ok = False
             except Exception as ex:   # the baseline is a reported side number; never lose the bench line over it
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 1, "kind": "unavailable", "sample": repr(ex)}
         print(json.dumps(line), flush=True)
+        rc_exit = 0 if ok else 1
     if world > 1:
         dist.barrier()
-        if p2p:
-            ctx.shared_frame_close()
+        ctx.shared_frame_close()
         dist.destroy_process_group()
     ctx.close()
-    return 0
+    return rc_exit
+
+
+def reference_parity(rt, ctx, wl, sph, mat, arm, bands, pix):
+    W, H, SPP = wl.W, wl.H, wl.spp
+    # (1) the reference's own structure, bit-exact on the GPU (COMPAT), shadows off like the reference: expect identical bytes
+    ctx.set_spheres(sph, mat)
+    ctx.build(wl.ref_acc, mode=rt.MODE_COMPAT)
+    gpu = ctx.render(wl.ref_acc, W, H, SPP)[0]
+    mx, bad, tot = band_diff(gpu, bands, pix)
+    parity = {"bands": len(bands), "rows": 2 * len(bands), "pixels": tot, "max_abs_diff": mx, "pixels_differing": bad,
+              "what": ("rows rendered by the UNMODIFIED reference (" + ("constructLBVHTree" if wl.ref_acc == rt.LBVH else "constructBVHNew") +
+                       " + render/castRay) vs rtds_build(COMPAT) + rtds_render of the same frame, per channel, 0..255")}
+    # (2) the frame this bench timed (its own accelerator: LBVH true mode / SAH) against the reference's BVH rows. Different
+    # tree, same candidate criterion (leaf-local): hits can differ only on exact-t ties between two spheres.
+    if not wl.shadows:
+        if arm.acc != rt.BVH:
+            arm.build(rt.BVH)
+            bands2 = bands[:: max(1, len(bands) // 20)]
+            _, _, pix2 = arm.render_bands(bands2, keep=True)
+        else:
+            bands2, pix2 = bands, pix
+        ctx.build(wl.acc, mode=wl.mode, **wl.build_kw)
+        timed_frame = ctx.render(wl.acc, W, H, SPP)[0]
+        mx2, bad2, tot2 = band_diff(timed_frame, bands2, pix2)
+        parity["timed_frame_vs_reference_bvh"] = {"bands": len(bands2), "pixels": tot2, "max_abs_diff": mx2, "pixels_differing": bad2}
+        parity["max_abs_diff"] = max(mx, mx2)
+    return parity
+
+
+def cpu_baseline_and_parity(rt, ctx, wl, sph, mat):
+    """The reference (oracle/_ref, 1 thread) on a bounded sample of the workload's frame - AND the pixels it renders are kept and
+    compared with this library's frame of the same structure (the reference's tree, rebuilt bit-exactly by rtds_build COMPAT), so
+    every bench run carries reference parity on its own workload. Runs after all timing."""
+    arm = CpuArm(wl, scene=(sph, mat))
+    W, H, SPP = wl.W, wl.H, wl.spp
+    bands = sample_bands(H, wl.cpu_bands, 2)
+    rays, secs, pix = arm.render_bands(bands, keep=True)
+    base = {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": 1, "kind": arm.kind,
+            "sample": f"{len(bands)} bands x 2 rows of the same frame ({rays} primary rays), 1 thread; the reference casts no shadow rays (trace_more is a stub)",
+            "build_s": arm.build_s, "build_ms_per_mprim": 1000 * arm.build_s / (sph.shape[0] / 1e6),
+            "unmodified_binary": unmodified_binary_baseline() if wl.key == "config3" else None}
+    parity = None
+    if arm.kind == "reference":
+        try:
+            parity = reference_parity(rt, ctx, wl, sph, mat, arm, bands, pix)
+        except Exception as ex:
+            parity = {"error": repr(ex)}
+    return base, parity
 
 
 def main():
@@ -519,8 +700,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3", choices=["config3", "config4", "config5"],
+                    help="BASELINE.json config (stand-in); config3 is the one the metric is quoted on (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1 frame assembly: peer stores (default) or NCCL gather")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1 frame assembly that is TIMED: peer stores (default) or NCCL gather; both are verified")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

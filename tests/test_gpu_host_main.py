@@ -82,3 +82,20 @@ def test_kd_closest_hit_through_the_driver(tmp_path, gpu_ctx):
     gpu_ctx.build(rt.BVH)
     ref_rgb, _, _, _ = gpu_ctx.render(rt.BVH, 640, 480, 1)                     # byte-identical to the reference's output.ppm
     assert np.count_nonzero(np.any(bvh != ref_rgb, axis=-1)) <= 640 * 480 // 1000   # same picture but for grazing rays
+
+
+def test_patched_reference_main_reproduces_output_ppm(tmp_path):
+    """INTEGRATION.md section B, run: the reference's OWN main.cpp with the librtds.so binding applied (integration/apply_patch.py +
+    integration/rtds_binding.inc, compiled by oracle/Makefile into oracle/_ref/ref_patched_main where the reference tree exists)
+    loads models/bunny.obj with the reference's loader, builds and renders on the GPU through the C ABI, and writes the shipped
+    output.ppm byte for byte; the log keeps the reference's lines and node count."""
+    binp = os.path.join(T.ROOT, "oracle", "_ref", "ref_patched_main")
+    if not os.path.exists(binp):
+        pytest.skip("oracle/_ref/ref_patched_main not built (needs /root/reference at build time)")
+    _models(tmp_path)
+    r = subprocess.run([binp], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ppm = open(tmp_path / "output.ppm", "rb").read()
+    assert hashlib.md5(ppm).hexdigest() == "c69c66375f2c6bda433f9f457a4b2b2e"      # = /root/reference/project/raytracer/output.ppm
+    for line in ("<<<<<<< This is BVH >>>>>>", "Total number of nodes: 71895", "--------- Rendering Completed ---------"):
+        assert line in r.stdout, line

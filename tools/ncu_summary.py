@@ -48,6 +48,8 @@ def main():
             try:
                 x = float(vals[i].replace(",", ""))
                 js[key] = x * SCALE.get(units[i], 1.0) if key.startswith("dram_bytes") else x
+                if key == "gpu_time":          # always microseconds in the JSON
+                    js[key] = x * {"second": 1e6, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3}.get(units[i], 1.0)
             except ValueError:
                 pass
         st = []
