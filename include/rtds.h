@@ -126,7 +126,11 @@ typedef struct {
                                                (main.cpp:362-372). 1 = closest-hit KD traversal + castRay's shading
                                                (extension: PBRT's KdTreeAccel::Intersect, whose any-hit sibling
                                                accelerators.h:997-1086 is a port of) */
-    int      reserved[6];
+    int      tri_geometric;                 /* triangle scenes only. 0 = Moeller-Trumbore (the reference's MOLLER_TRUMBORE branch,
+                                               main.cpp:138-162, which it never compiles); 1 = the test the reference DOES compile:
+                                               the geometric branch of Triangle::rayTriangleIntersect (main.cpp:163-215), bug for
+                                               bug (its plane distance is right for rays from the origin only) */
+    int      reserved[5];
 } rtds_render_params;
 
 typedef struct {
@@ -182,6 +186,7 @@ int rtds_export_morton(rtds_ctx* ctx, uint64_t* keys, int* prim_ids, int cap, in
  * with RTDS_TRACE_KD_CLOSEST or-ed into `exact` it is the closest-hit KD traversal (objId, tnear) of kd_closest.
  * exact as in rtds_render_params. Host pointers, o/d are nrays x 3. */
 #define RTDS_TRACE_KD_CLOSEST 2
+#define RTDS_TRACE_TRI_GEOMETRIC 4      /* or-ed into `exact`: triangles are tested like rtds_render_params.tri_geometric = 1 */
 int rtds_trace(rtds_ctx* ctx, int acc_type, int exact, const float* o_xyz, const float* d_xyz, int nrays,
                int* hit_obj, float* t, rtds_render_stats* stats);
 

@@ -351,16 +351,50 @@ inline bool ray_triangle(const float o[3], const float d[3], const float* v /*9 
     return !(t < 0);
 }
 
+// Triangle::rayTriangleIntersect as the reference COMPILES it (main.cpp:163-215, the geometric branch; MOLLER_TRUMBORE is never
+// defined): plane hit with N = v0v1 x v0v2, t = (N.orig + N.v0) / N.dir - correct for orig = 0 only, kept bug for bug -, then the
+// three inside-outside edge tests. PINNED: tests/test_oracle_vs_reference.py checks it against the reference's own class Triangle.
+inline bool ray_triangle_geometric(const float o[3], const float d[3], const float* v /*9 floats*/, float& t)
+{
+    const float ax = v[3] - v[0], ay = v[4] - v[1], az = v[5] - v[2];            // v0v1
+    const float bx = v[6] - v[0], by = v[7] - v[1], bz = v[8] - v[2];            // v0v2
+    const float Nx = ay * bz - az * by, Ny = az * bx - ax * bz, Nz = ax * by - ay * bx;
+    const float nd = Nx * d[0] + Ny * d[1] + Nz * d[2];
+    if (std::fabs(nd) < 1e-6f) return false;                                     // EPS, main.cpp:59,175
+    const float dd = Nx * v[0] + Ny * v[1] + Nz * v[2];
+    t = ((Nx * o[0] + Ny * o[1] + Nz * o[2]) + dd) / nd;                         // main.cpp:182
+    if (t < 0) return false;
+    const float Px = o[0] + d[0] * t, Py = o[1] + d[1] * t, Pz = o[2] + d[2] * t;
+    {   // edge 0
+        const float px = Px - v[0], py = Py - v[1], pz = Pz - v[2];
+        const float cx = ay * pz - az * py, cy = az * px - ax * pz, cz = ax * py - ay * px;
+        if (Nx * cx + Ny * cy + Nz * cz < 0) return false;
+    }
+    {   // edge 1
+        const float ex = v[6] - v[3], ey = v[7] - v[4], ez = v[8] - v[5];
+        const float px = Px - v[3], py = Py - v[4], pz = Pz - v[5];
+        const float cx = ey * pz - ez * py, cy = ez * px - ex * pz, cz = ex * py - ey * px;
+        if (Nx * cx + Ny * cy + Nz * cz < 0) return false;
+    }
+    {   // edge 2
+        const float ex = v[0] - v[6], ey = v[1] - v[7], ez = v[2] - v[8];
+        const float px = Px - v[6], py = Py - v[7], pz = Pz - v[8];
+        const float cx = ey * pz - ez * py, cy = ez * px - ex * pz, cz = ex * py - ey * px;
+        if (Nx * cx + Ny * cy + Nz * cz < 0) return false;
+    }
+    return true;
+}
+
 struct Scene {
     const float* sph; const float* mat; int n;
     const LinearNode* nodes; const int* prim_order; int n_nodes;
     int tie_by_objid;
-    int prim_type = 0;   // 0: sph = n x 4 spheres; 1: sph = n x 9 triangles
+    int prim_type = 0;   // 0: sph = n x 4 spheres; 1: sph = n x 9 triangles, Moller-Trumbore; 2: triangles, the reference's compiled geometric test
     bool test(const float o[3], const float d[3], int obj, float& t0, float& t1) const
     {
         if (prim_type == 0) return ray_sphere(o, d, sph + 4 * (size_t)obj, t0, t1);
         float t;
-        if (!ray_triangle(o, d, sph + 9 * (size_t)obj, t)) return false;
+        if (!(prim_type == 2 ? ray_triangle_geometric(o, d, sph + 9 * (size_t)obj, t) : ray_triangle(o, d, sph + 9 * (size_t)obj, t))) return false;
         t0 = t1 = t;
         return true;
     }
@@ -942,7 +976,7 @@ void orc_render_rows_ex(const float* cxyz_r, const float* rgb_mat, int n, const 
                         int shadows, uint8_t* rgb8, int* hit_out, float* accum, float* dirs, long long* ray_counts3)
 {
     Scene S{cxyz_r, rgb_mat, n, nodes, prim_order, n_nodes, tie_by_objid & 1};
-    S.prim_type = (tie_by_objid >> 8) & 1;   // bit 8 of the flag word: the primitive table holds triangles (n x 9)
+    S.prim_type = (tie_by_objid >> 8) & 3;   // bits 8-9 of the flag word: the primitive table holds triangles (n x 9); 2 = geometric test
     std::vector<Light> L(m);
     for (int i = 0; i < m; ++i) {
         const float* l = lights7 + 7 * i;

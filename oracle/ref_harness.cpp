@@ -276,6 +276,32 @@ void ref_trace(const float* o, const float* d, int nrays, int accType, int* hit_
     if (n_candidates) *n_candidates = cand;
 }
 
+// Brute-force closest hit over triangles with the reference's OWN class Triangle (main.cpp:107-216) and its compiled
+// rayTriangleIntersect (the geometric branch; the reference never instantiates the class itself), reduced like the NONE loop
+// (main.cpp:376-386: strict <, first candidate wins). tris9: m x {v0,v1,v2}. Also returns, per ray, how many triangles it hit.
+void ref_triangle_trace(const float* tris9, int m, const float* o, const float* d, int nrays, int* hit_id, float* t_out, int* n_hits)
+{
+    std::vector<Triangle> tris;
+    tris.reserve(m);
+    for (int i = 0; i < m; ++i) {
+        const float* v = tris9 + 9 * (size_t)i;
+        tris.push_back(Triangle(Vec3f(v[0], v[1], v[2]), Vec3f(v[3], v[4], v[5]), Vec3f(v[6], v[7], v[8]), Vec3f(0.8f, 0.7f, 0.f)));
+    }
+    for (int r = 0; r < nrays; ++r) {
+        Vec3f ro(o[3 * r], o[3 * r + 1], o[3 * r + 2]), rd(d[3 * r], d[3 * r + 1], d[3 * r + 2]);
+        float tnear = INFINITY; int hit = -1, cnt = 0;
+        for (int i = 0; i < m; ++i) {
+            float t = INFINITY;
+            if (tris[i].rayTriangleIntersect(ro, rd, t)) {
+                ++cnt;
+                if (t < tnear) { tnear = t; hit = i; }
+            }
+        }
+        hit_id[r] = hit; t_out[r] = tnear;
+        if (n_hits) n_hits[r] = cnt;
+    }
+}
+
 // castRay on caller-supplied rays (depth 1), colours out.
 void ref_cast(const float* o, const float* d, int nrays, int accType, float* rgb)
 {

@@ -30,6 +30,7 @@ BVH, KDTREE, UNIFORM_GRID, LBVH, NONE = 0, 1, 2, 3, 4
 IGEA, ARMADILLO, BUNNY, BUNNIES, TEST, GRASS, BUDDHA, CITY = range(8)
 MODE_COMPAT, MODE_TRUE, MODE_SAH = 0, 1, 2
 TRACE_KD_CLOSEST = 2      # rtds.h: or-ed into rtds_trace's `exact`
+TRACE_TRI_GEOMETRIC = 4
 
 STATUS = {0: "OK", -1: "INVALID", -2: "CUDA", -3: "NO_DEVICE", -4: "NO_SCENE", -5: "NOT_BUILT", -6: "DEGENERATE",
           -7: "CAPACITY", -8: "UNSUPPORTED"}
@@ -69,7 +70,8 @@ class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("aa_samples", C.c_int), ("fov", C.c_float),
                 ("bg", C.c_float * 3), ("bias", C.c_float), ("max_depth", C.c_int), ("shadows", C.c_int),
                 ("exact", C.c_int), ("rank", C.c_int), ("world", C.c_int), ("tile_rows", C.c_int),
-                ("jitter_offset", C.c_uint64), ("no_jitter_regen", C.c_int), ("kd_closest", C.c_int), ("reserved", C.c_int * 6)]
+                ("jitter_offset", C.c_uint64), ("no_jitter_regen", C.c_int), ("kd_closest", C.c_int), ("tri_geometric", C.c_int),
+                ("reserved", C.c_int * 5)]
 
 
 class RenderStats(C.Structure):
@@ -238,7 +240,7 @@ class Rtds:
         return keys[:n.value], ids[:n.value]
 
     # -- trace / render ------------------------------------------------------------------------
-    def trace(self, acc, o, d, exact=True, kd_closest=False):
+    def trace(self, acc, o, d, exact=True, kd_closest=False, tri_geometric=False):
         o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
         d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
         n = d.shape[0]
@@ -247,16 +249,17 @@ class Rtds:
         hit = np.full(n, -2, np.int32)
         t = np.zeros(n, np.float32)
         st = RenderStats()
-        self._check(self.lib.rtds_trace(self.ctx, acc, int(bool(exact)) | (TRACE_KD_CLOSEST if kd_closest else 0), _ptr(o), _ptr(d), n, _ptr(hit), _ptr(t), C.byref(st)))
+        self._check(self.lib.rtds_trace(self.ctx, acc, int(bool(exact)) | (TRACE_KD_CLOSEST if kd_closest else 0) | (TRACE_TRI_GEOMETRIC if tri_geometric else 0), _ptr(o), _ptr(d), n, _ptr(hit), _ptr(t), C.byref(st)))
         return hit, t, _stats_dict(st)
 
     def render_params(self, width, height, aa_samples=1, exact=False, rank=0, world=1, tile_rows=8, shadows=0,
-                      jitter_offset=0, no_jitter_regen=0, max_depth=0, kd_closest=0):
+                      jitter_offset=0, no_jitter_regen=0, max_depth=0, kd_closest=0, tri_geometric=0):
         p = RenderParams()
         p.width, p.height, p.aa_samples = width, height, aa_samples
         p.exact, p.rank, p.world, p.tile_rows, p.shadows = int(exact), rank, world, tile_rows, shadows
         p.jitter_offset, p.no_jitter_regen, p.max_depth = jitter_offset, no_jitter_regen, max_depth
         p.kd_closest = int(kd_closest)
+        p.tri_geometric = int(tri_geometric)
         return p
 
     def render(self, acc, width, height, aa_samples=1, want_hit=False, want_accum=False, out=None, **kw):

@@ -163,6 +163,9 @@ static int create_resources(rtds_ctx* c)
     RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_band, cudaEventDisableTiming));
     RTDS_CUDA(cudaStreamCreateWithFlags(&c->jit_stream, cudaStreamNonBlocking));
     RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_dirs, cudaEventDisableTiming));
+    RTDS_CUDA(cudaStreamCreateWithFlags(&c->pf_stream, cudaStreamNonBlocking));
+    RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_pf0, cudaEventDisableTiming));
+    RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_pf1, cudaEventDisableTiming));
     RTDS_CUDA(cudaEventCreate(&c->ev0)); RTDS_CUDA(cudaEventCreate(&c->ev1));
     RTDS_CUDA(cudaEventCreate(&c->ev2)); RTDS_CUDA(cudaEventCreate(&c->ev3));
     RTDS_CUDA(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8));
@@ -220,7 +223,10 @@ int rtds_destroy(rtds_ctx* c)
                     c->d_sort_ws, c->d_frame, c->d_hit, c->d_accum, c->d_counters};
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
-    for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->ev3, c->ev_band, c->ev_dirs}) if (e) cudaEventDestroy(e);
+    if (c->fg.exec) cudaGraphExecDestroy(c->fg.exec);
+    if (c->fg.graph) cudaGraphDestroy(c->fg.graph);
+    if (c->pf_stream) cudaStreamDestroy(c->pf_stream);
+    for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->ev3, c->ev_band, c->ev_dirs, c->ev_pf0, c->ev_pf1}) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     shared_frame_drop(c);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -562,13 +568,22 @@ int rtds_render(rtds_ctx* c, int acc, const rtds_render_params* p, uint8_t* rgb,
         return RTDS_OK;
     }
     RTDS_TRY(rtds_render_impl(c, acc, p, c->d_frame, hit_obj ? c->d_hit : nullptr, accum ? c->d_accum : nullptr, st));
-    // device -> host: local row tile j is global tile j*world + rank
+    // device -> host: local row tile j is global tile j*world + rank. The RGB8 rows of all whole tiles go down as ONE strided
+    // copy (source pitch = one tile, destination pitch = `world` tiles), so N ranks fill one host frame over their own PCIe
+    // links side by side - the multi-GPU end-to-end path needs no GPU-side gather when the consumer is the host.
     {
+        const size_t tile_bytes = (size_t)tile_rows * W * 3;
+        int whole = 0;
+        for (int t = p->rank; (t + 1) * tile_rows <= H; t += world) ++whole;
+        if (whole > 0)
+            RTDS_CUDA(cudaMemcpy2DAsync(rgb + (size_t)p->rank * tile_bytes, (size_t)world * tile_bytes, c->d_frame, tile_bytes, tile_bytes,
+                                        (size_t)whole, cudaMemcpyDeviceToHost, s));
         int lrow = 0;
         for (int t = p->rank; t * tile_rows < H; t += world) {
             int r0 = t * tile_rows, nr = (r0 + tile_rows <= H) ? tile_rows : H - r0;
             size_t cnt = (size_t)nr * W;
-            RTDS_CUDA(cudaMemcpyAsync(rgb + (size_t)r0 * W * 3, c->d_frame + (size_t)lrow * W * 3, cnt * 3, cudaMemcpyDeviceToHost, s));
+            if (nr < tile_rows)    // the ragged last tile
+                RTDS_CUDA(cudaMemcpyAsync(rgb + (size_t)r0 * W * 3, c->d_frame + (size_t)lrow * W * 3, cnt * 3, cudaMemcpyDeviceToHost, s));
             if (hit_obj) RTDS_CUDA(cudaMemcpyAsync(hit_obj + (size_t)r0 * W, c->d_hit + (size_t)lrow * W, cnt * sizeof(int), cudaMemcpyDeviceToHost, s));
             if (accum) RTDS_CUDA(cudaMemcpyAsync(accum + (size_t)r0 * W * 3, c->d_accum + (size_t)lrow * W * 3, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
             lrow += nr;

@@ -381,7 +381,11 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
             int best_leaf[PK];
             // the packet's 4 directions are 48 contiguous, 16-byte aligned bytes (main.cpp:554-557, from mt_expand_dirs_kernel)
             const float4* dp = reinterpret_cast<const float4*>(A.dirs + 3 * (pix * A.spp + k0));
+#ifdef RTDS_DIRS_LDCS     // experiment: read-once direction stream with the evict-first policy (keeps the tree in L2)
+            const float4 d0 = __ldcs(dp), d1 = __ldcs(dp + 1), d2 = __ldcs(dp + 2);
+#else
             const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+#endif
             dx[0] = d0.x; dy[0] = d0.y; dz[0] = d0.z; dx[1] = d0.w; dy[1] = d1.x; dz[1] = d1.y;
             dx[2] = d1.z; dy[2] = d1.w; dz[2] = d2.x; dx[3] = d2.y; dy[3] = d2.z; dz[3] = d2.w;
             cnt.rays += PK;
@@ -851,9 +855,19 @@ static int jitter_prepare(rtds_ctx* ctx, uint64_t first_word, size_t n_words, in
 }
 
 // Primary directions of the frame's samples (pixel * spp + k), generated from the jitter stream starting at sample
-// `first_sample`; only the chunks that hold rows of `own` are filled.
-static int dirs_prepare(rtds_ctx* ctx, uint64_t first_sample, int W, int H, int spp, const RayGen& G, const JitterOwner& own, int* launches,
-                        cudaStream_t stream)
+// `first_sample`; only the chunks that hold rows of `own` are filled. dirs_plan() sizes the buffers and fills the launch
+// (grid + arguments of mt_expand_dirs_kernel), dirs_prepare() also issues it on `stream`.
+struct DirsLaunch {
+    unsigned grid = 0;
+    const uint32_t* snap; int s0; float* dirs; unsigned long long first_sample; unsigned n_samples; int width, spp;
+    FastDiv div_spp, div_width; RayGen G; JitterOwner own; int chunks_per_tile;
+    void* args[12];
+    void bind() { void* a[12] = {&snap, &s0, &dirs, &first_sample, &n_samples, &width, &spp, &div_spp, &div_width, &G, &own, &chunks_per_tile};
+                  for (int i = 0; i < 12; ++i) args[i] = a[i]; }
+};
+
+static int dirs_plan(rtds_ctx* ctx, uint64_t first_sample, int W, int H, int spp, const RayGen& G, const JitterOwner& own, int* launches,
+                     DirsLaunch& L)
 {
     const uint64_t n_samples = (uint64_t)W * H * spp;
     if (n_samples >= (1ull << 32)) { rtds_set_error("render: width*height*aa_samples must be below 2^32"); return RTDS_ERR_INVALID; }
@@ -892,15 +906,25 @@ static int dirs_prepare(rtds_ctx* ctx, uint64_t first_sample, int W, int H, int 
         const int owned = own.rank < n_tiles ? (n_tiles - own.rank + own.world - 1) / own.world : 0;
         grid = (unsigned)owned * (unsigned)chunks_per_tile;
     }
-    if (grid > 0)
-        mt_expand_dirs_kernel<<<grid, MT_THREADS, 0, stream>>>(ctx->d_mt_snap, (int)s0, ctx->d_dirs, first_sample, (unsigned)n_samples, W, spp,
-                                                                make_div((uint32_t)spp), make_div((uint32_t)W), G, own, chunks_per_tile);
-    if (launches) *launches += 1;
-    RTDS_CUDA(cudaGetLastError());
+    L.grid = grid; L.snap = ctx->d_mt_snap; L.s0 = (int)s0; L.dirs = ctx->d_dirs; L.first_sample = first_sample; L.n_samples = (unsigned)n_samples;
+    L.width = W; L.spp = spp; L.div_spp = make_div((uint32_t)spp); L.div_width = make_div((uint32_t)W); L.G = G; L.own = own;
+    L.chunks_per_tile = chunks_per_tile;
+    L.bind();
     ctx->dirs_key[0] = first_sample; ctx->dirs_key[1] = (uint64_t)W; ctx->dirs_key[2] = (uint64_t)H; ctx->dirs_key[3] = (uint64_t)spp;
     ctx->dirs_key[4] = ((uint64_t)__float_as_uint_host(G.angle) << 32) | __float_as_uint_host(G.aspect);
     ctx->dirs_key[5] = ((uint64_t)(unsigned)own.rank << 40) | ((uint64_t)(unsigned)own.world << 20) | (uint64_t)(unsigned)own.tile_rows;
     ctx->dirs_valid = true;
+    return RTDS_OK;
+}
+
+static int dirs_prepare(rtds_ctx* ctx, uint64_t first_sample, int W, int H, int spp, const RayGen& G, const JitterOwner& own, int* launches,
+                        cudaStream_t stream)
+{
+    DirsLaunch L;
+    RTDS_TRY(dirs_plan(ctx, first_sample, W, H, spp, G, own, launches, L));
+    if (L.grid > 0) RTDS_CUDA(cudaLaunchKernel((const void*)mt_expand_dirs_kernel, dim3(L.grid), dim3(MT_THREADS), L.args, 0, stream));
+    if (launches) *launches += 1;
+    RTDS_CUDA(cudaGetLastError());
     return RTDS_OK;
 }
 
@@ -969,6 +993,200 @@ int rtds_prefetch_dirs(rtds_ctx* ctx, const rtds_render_params* p)
     return RTDS_OK;
 }
 
+// completion flags of the multi-GPU shared frame (one 128-byte line per rank behind the frame)
+__global__ void frame_signal_kernel(volatile uint32_t* flag, uint32_t seq)
+{
+    __threadfence_system();        // this rank's tile stores (previous kernel on the stream) before the flag
+    *flag = seq;
+}
+__global__ void frame_wait_kernel(const volatile uint32_t* flags, int world, uint32_t seq, long long timeout_cycles, int* status)
+{
+    const int r = threadIdx.x;
+    if (r < world) {
+        const long long t0 = clock64();
+        while ((int)(flags[32 * r] - seq) < 0) {     // a rank may already have signalled a later frame
+            if (clock64() - t0 > timeout_cycles) { atomicExch(status, 1 + r); break; }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+
+// Streams the tree (interior nodes + leaf spheres) into L2 with evict-last priority while the direction kernel runs: the
+// render kernel's first wave then finds the upper levels in L2 instead of every block missing on them at once, and the
+// 12 B/ray direction stream that follows does not push the tree out again. Only issued when the tree fits L2.
+__global__ void __launch_bounds__(256) l2_prefetch_kernel(const char* __restrict__ a, size_t na, const char* __restrict__ b, size_t nb)
+{
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128, stride = (size_t)gridDim.x * blockDim.x * 128;
+    for (size_t o = i0; o < na; o += stride) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a + o));
+    for (size_t o = i0; o < nb; o += stride) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(b + o));
+}
+constexpr size_t L2_PREFETCH_MAX_BYTES = 100u << 20;
+constexpr unsigned L2_PREFETCH_BLOCKS = 148 * 2;
+
+struct PrefetchArgs { const char* a; size_t na; const char* b; size_t nb; };
+static bool prefetch_plan(const rtds_ctx* ctx, bool bvh_path, PrefetchArgs& P)
+{
+    if (!ctx->opt.l2_prefetch || !bvh_path || ctx->bvh.prim_type != 0 || ctx->bvh.n_internal <= 0) return false;
+    P.a = (const char*)ctx->bvh.nodes; P.na = sizeof(Node64) * (size_t)ctx->bvh.n_internal;
+    P.b = (const char*)ctx->bvh.leaf_sph; P.nb = sizeof(float4) * (size_t)ctx->bvh.n_prims;
+    return P.na + P.nb <= L2_PREFETCH_MAX_BYTES;
+}
+
+static bool same_bytes(std::vector<unsigned char>& last, const void* now, size_t n)
+{
+    if (last.size() == n && memcmp(last.data(), now, n) == 0) return true;
+    last.assign((const unsigned char*)now, (const unsigned char*)now + n);
+    return false;
+}
+
+// frame_graph option: the whole frame as one graph launch on ctx->stream (see FrameGraph). The caller synchronises.
+static int render_frame_graph(rtds_ctx* ctx, const RenderArgs& A, const void* fn, unsigned lin, const DirsLaunch* DL, const PrefetchArgs* PF,
+                              bool shared, uint32_t seq, int* launches)
+{
+    FrameGraph& g = ctx->fg;
+    SharedFrame& f = ctx->shared;
+    const bool has_dirs = DL && DL->grid > 0, has_pf = PF != nullptr, has_signal = shared, has_wait = shared && f.owner;
+    // kernel parameter blocks
+    void* a_render[] = {(void*)&A};
+    PrefetchArgs pf = PF ? *PF : PrefetchArgs{nullptr, 0, nullptr, 0};
+    void* a_pf[] = {&pf.a, &pf.na, &pf.b, &pf.nb};
+    volatile uint32_t* sig_flag = shared ? f.flags + 32 * f.rank : nullptr;
+    void* a_signal[] = {&sig_flag, &seq};
+    const volatile uint32_t* wait_flags = f.flags;
+    int wait_world = f.world;
+    long long wait_timeout = 20000000000ll;      // ~10 s
+    int* wait_status = (int*)(ctx->d_counters + 7);
+    void* a_wait[] = {&wait_flags, &wait_world, &seq, &wait_timeout, &wait_status};
+    auto kparams = [](const void* func, unsigned grid, unsigned block, void** args) {
+        cudaKernelNodeParams kp = {};
+        kp.func = (void*)func; kp.gridDim = dim3(grid); kp.blockDim = dim3(block); kp.sharedMemBytes = 0; kp.kernelParams = args; kp.extra = nullptr;
+        return kp;
+    };
+    const bool same_shape = g.exec && g.fn_render == fn && g.has_dirs == has_dirs && g.has_pf == has_pf && g.has_signal == has_signal &&
+                            g.has_wait == has_wait;
+    if (!same_shape) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        if (g.graph) { cudaGraphDestroy(g.graph); g.graph = nullptr; }
+        RTDS_CUDA(cudaGraphCreate(&g.graph, 0));
+        cudaGraphNode_t n_ev0, n_zero, n_ev2, n_ev3, n_ev1, n_copy;
+        RTDS_CUDA(cudaGraphAddEventRecordNode(&n_ev0, g.graph, nullptr, 0, ctx->ev0));
+        cudaMemsetParams mp = {};
+        mp.dst = ctx->d_counters; mp.value = 0; mp.elementSize = 4; mp.width = 16; mp.height = 1; mp.pitch = 0;
+        RTDS_CUDA(cudaGraphAddMemsetNode(&n_zero, g.graph, &n_ev0, 1, &mp));
+        std::vector<cudaGraphNode_t> pre{n_zero};
+        if (has_dirs) {
+            cudaKernelNodeParams kp = kparams((const void*)mt_expand_dirs_kernel, DL->grid, MT_THREADS, const_cast<void**>(DL->args));
+            RTDS_CUDA(cudaGraphAddKernelNode(&g.k_dirs, g.graph, &n_ev0, 1, &kp));
+            pre.push_back(g.k_dirs);
+        }
+        if (has_pf) {
+            cudaKernelNodeParams kp = kparams((const void*)l2_prefetch_kernel, L2_PREFETCH_BLOCKS, 256, a_pf);
+            RTDS_CUDA(cudaGraphAddKernelNode(&g.k_pf, g.graph, &n_ev0, 1, &kp));
+            pre.push_back(g.k_pf);
+        }
+        RTDS_CUDA(cudaGraphAddEventRecordNode(&n_ev2, g.graph, pre.data(), pre.size(), ctx->ev2));
+        {
+            cudaKernelNodeParams kp = kparams(fn, lin, 128, a_render);
+            RTDS_CUDA(cudaGraphAddKernelNode(&g.k_render, g.graph, &n_ev2, 1, &kp));
+        }
+        RTDS_CUDA(cudaGraphAddEventRecordNode(&n_ev3, g.graph, &g.k_render, 1, ctx->ev3));
+        cudaGraphNode_t last = n_ev3;
+        if (has_signal) {
+            cudaKernelNodeParams kp = kparams((const void*)frame_signal_kernel, 1, 1, a_signal);
+            RTDS_CUDA(cudaGraphAddKernelNode(&g.k_signal, g.graph, &last, 1, &kp));
+            last = g.k_signal;
+        }
+        if (has_wait) {
+            cudaKernelNodeParams kp = kparams((const void*)frame_wait_kernel, 1, 32, a_wait);
+            RTDS_CUDA(cudaGraphAddKernelNode(&g.k_wait, g.graph, &last, 1, &kp));
+            last = g.k_wait;
+        }
+        RTDS_CUDA(cudaGraphAddEventRecordNode(&n_ev1, g.graph, &last, 1, ctx->ev1));
+        RTDS_CUDA(cudaGraphAddMemcpyNode1D(&n_copy, g.graph, &n_ev1, 1, ctx->h_counters, ctx->d_counters, sizeof(unsigned long long) * 8,
+                                           cudaMemcpyDeviceToHost));
+        RTDS_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
+        g.fn_render = fn; g.has_dirs = has_dirs; g.has_pf = has_pf; g.has_signal = has_signal; g.has_wait = has_wait;
+        g.grid_dirs = has_dirs ? DL->grid : 0; g.grid_render = lin;
+        g.last_render.assign((const unsigned char*)&A, (const unsigned char*)&A + sizeof A);
+        if (has_dirs) g.last_dirs.assign((const unsigned char*)DL, (const unsigned char*)DL + offsetof(DirsLaunch, args));
+        if (has_pf) g.last_pf.assign((const unsigned char*)&pf, (const unsigned char*)&pf + sizeof pf);
+        ++g.rebuilds;
+    } else {
+        if (!same_bytes(g.last_render, &A, sizeof A) || g.grid_render != lin) {
+            cudaKernelNodeParams kp = kparams(fn, lin, 128, a_render);
+            RTDS_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.k_render, &kp));
+            g.grid_render = lin;
+        }
+        if (has_dirs && (!same_bytes(g.last_dirs, DL, offsetof(DirsLaunch, args)) || g.grid_dirs != DL->grid)) {
+            cudaKernelNodeParams kp = kparams((const void*)mt_expand_dirs_kernel, DL->grid, MT_THREADS, const_cast<void**>(DL->args));
+            RTDS_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.k_dirs, &kp));
+            g.grid_dirs = DL->grid;
+        }
+        if (has_pf && !same_bytes(g.last_pf, &pf, sizeof pf)) {
+            cudaKernelNodeParams kp = kparams((const void*)l2_prefetch_kernel, L2_PREFETCH_BLOCKS, 256, a_pf);
+            RTDS_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.k_pf, &kp));
+        }
+        if (has_signal) {      // the frame sequence number changes every frame
+            cudaKernelNodeParams kp = kparams((const void*)frame_signal_kernel, 1, 1, a_signal);
+            RTDS_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.k_signal, &kp));
+        }
+        if (has_wait) {
+            cudaKernelNodeParams kp = kparams((const void*)frame_wait_kernel, 1, 32, a_wait);
+            RTDS_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.k_wait, &kp));
+        }
+    }
+    RTDS_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+    ++g.launches;
+    *launches += 1 + (has_dirs ? 1 : 0) + (has_pf ? 1 : 0) + (has_signal ? 1 : 0) + (has_wait ? 1 : 0);
+    return RTDS_OK;
+}
+
+// render statistics from the counters the frame left in pinned memory (the stream is already synchronised)
+static int render_stats_out(rtds_ctx* ctx, rtds_render_stats* st, int launches, int rows, bool wait_copies, bool)
+{
+    const unsigned long long* c = ctx->h_counters;
+    memset(st, 0, sizeof *st);
+    st->node_tests = c[0]; st->prim_tests = c[1]; st->node_visits = c[2];
+    st->rays = c[3]; st->shadow_rays = c[4]; st->secondary_rays = c[5];
+    st->primary_rays = c[3] - c[4] - c[5];
+    RTDS_CUDA(cudaEventElapsedTime(&st->ms_kernel, ctx->ev2, ctx->ev3));
+    RTDS_CUDA(cudaEventElapsedTime(&st->ms_total, ctx->ev0, ctx->ev1));
+    st->kernel_launches = launches;
+    st->rows = rows;
+    st->reserved[0] = (int)(unsigned)c[7];      // shared frame: 1 + the rank the owner timed out on (0 = complete)
+    if (wait_copies) RTDS_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    return RTDS_OK;
+}
+
+// Which render kernel serves this frame (all take one RenderArgs; grid = quadrant-major linear grid of 16 x 8-pixel blocks).
+static const void* select_render_kernel(const rtds_ctx* ctx, const RenderArgs& A, const rtds_render_params* p, bool full, bool kdt, bool brute,
+                                        bool kd_closest)
+{
+    // four samples of a pixel per thread as one packet (see traverse_packet); the packet option turns it off
+    // (shadows without reflective / refractive materials stay on the packet kernel; the shadow rays are single)
+    // Only the samples of ONE pixel are packed. Packets of neighbouring pixels were built twice and measured slower both
+    // times, also with the hull test (round 2, B200): 2 x 2 pixels x 1 sample 0.205 vs 0.087 ms (bunny 640x480), 0.25 vs
+    // 0.20 ms (1080p), 4.7 vs 2.3 ms (7 M spheres); 2 pixels x 4 samples 1.07 vs 0.97 ms on the bench frame - node visits per
+    // ray drop 2-3.4x, but a thread then carries 4-8 rays' leaf work in sequence and the grid has 2-4x fewer threads
+    // to hide latency with (negative results). Removed again.
+    bool packet = (!full || !ctx->has_materials) && !kdt && !brute && !p->exact && A.spp % PK == 0 && A.bvh.leaf_box_prim && A.shade.max_depth >= 1;
+    packet = packet && ctx->opt.packet != 0;
+    // interior boxes tested once per packet against the hull of the four reciprocal directions (default; hull option 0:
+    // once per ray). Bench frame: same frame, node visits 3.17 -> 3.18 per ray, kernel 1.16 -> 0.99 ms.
+    const bool hull = ctx->opt.hull != 0;
+    if (packet && full) return hull ? (const void*)render_packet_kernel<true, true> : (const void*)render_packet_kernel<true, false>;
+    if (full) {
+        if (brute) return (const void*)render_full_kernel<2>;
+        return p->exact ? (const void*)render_full_kernel<0> : (const void*)render_full_kernel<1>;
+    }
+    if (packet) return hull ? (const void*)render_packet_kernel<false, true> : (const void*)render_packet_kernel<false, false>;
+    if (kd_closest) return (const void*)render_kernel<4>;
+    if (kdt) return (const void*)render_kernel<3>;
+    if (brute) return (const void*)render_kernel<2>;
+    return p->exact ? (const void*)render_kernel<0> : (const void*)render_kernel<1>;
+}
+
 int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_t* d_rgb_rows, int* d_hit, float* d_accum,
                      rtds_render_stats* st, const std::function<int(int, int, cudaEvent_t)>* on_band, bool global_rows)
 {
@@ -992,6 +1210,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.n = ctx->n; A.sph = ctx->d_sph; A.tri = ctx->d_tris; A.prim_type = ctx->prim_type; A.mat = ctx->d_mat;
     if (!brute && !kdt) A.bvh = make_view(ctx->bvh); else A.bvh = BvhView();
     if (kdt) A.kd = make_kd_view(ctx); else A.kd = KdView();
+    if (p->tri_geometric && ctx->prim_type == 1) { A.prim_type = 2; if (A.bvh.prim_type == 1) A.bvh.prim_type = 2; if (A.kd.prim_type == 1) A.kd.prim_type = 2; }
     A.shade.n_lights = ctx->n_lights;
     for (int i = 0; i < ctx->n_lights; ++i) A.shade.lights[i] = ctx->lights[i];
     const bool bg0 = p->bg[0] == 0 && p->bg[1] == 0 && p->bg[2] == 0;
@@ -1009,16 +1228,30 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
 
     cudaStream_t s = ctx->stream;
     int launches = 0;
-    RTDS_CUDA(cudaEventRecord(ctx->ev0, s));
     const uint64_t first_word = 4ull * p->jitter_offset;
     const size_t n_words = 4ull * (size_t)W * H * spp;
-    // Optional fused strip kernel (RTDS_STRIP=1): regenerates the jitter words it needs in shared memory, so nothing is
+    // Optional fused strip kernel (strip option): regenerates the jitter words it needs in shared memory, so nothing is
     // expanded into HBM. MEASURED SLOWER on B200 (3.16 ms vs 1.81 + 0.24 ms on the bench frame): a block then covers
     // 312 consecutive pixels of one scanline instead of a 16x8 tile, and the L1 hit rate of the node stream — what
     // this issue-bound kernel lives on — collapses. Kept as a checked (parity-tested) negative result, off by default.
     const bool strip = !brute && !full && !kd_closest && !global_rows && spp <= 150 && ctx->opt.strip == 1;
+    // One graph launch per frame (frame_graph option) for renders that stay on the device: rtds_render_device and the multi-GPU
+    // shared frame. Host-buffer renders keep the banded multi-stream form below (the download overlaps the rendering there).
+    const bool graph_path = ctx->opt.frame_graph != 0 && !on_band && !strip && A.local_rows > 0 && st != nullptr && !d_hit && !d_accum;
+    PrefetchArgs PF;
+    const bool prefetch = !strip && A.local_rows > 0 && prefetch_plan(ctx, !brute && !kdt, PF);
+    if (!graph_path) RTDS_CUDA(cudaEventRecord(ctx->ev0, s));
+    if (prefetch && !graph_path) {
+        RTDS_CUDA(cudaEventRecord(ctx->ev_pf0, s));
+        RTDS_CUDA(cudaStreamWaitEvent(ctx->pf_stream, ctx->ev_pf0, 0));
+        l2_prefetch_kernel<<<L2_PREFETCH_BLOCKS, 256, 0, ctx->pf_stream>>>(PF.a, PF.na, PF.b, PF.nb);
+        RTDS_CUDA(cudaEventRecord(ctx->ev_pf1, ctx->pf_stream));
+        launches += 1;
+    }
     const uint64_t chunk_words = (uint64_t)MT_SNAP_EVERY * MT_N;
     const uint64_t c_first = first_word / chunk_words, c_last = (first_word + n_words - 1) / chunk_words;
+    DirsLaunch DL;
+    bool have_dirs_launch = false;
     if (strip) {
         if (c_last + 3 >= (1ull << 31)) { rtds_set_error("jitter stream position too large"); return RTDS_ERR_INVALID; }
         RTDS_TRY(ensure_snapshots(ctx, (int)(c_last + 1), &launches));
@@ -1035,7 +1268,13 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             if (ctx->dirs_pending) RTDS_CUDA(cudaStreamWaitEvent(s, ctx->ev_dirs, 0));      // never overwrite d_dirs under a running prefetch
             if (!(p->no_jitter_regen && ctx->dirs_valid && memcmp(key, ctx->dirs_key, sizeof key) == 0)) {
                 JitterOwner own{first_word, 4ull * (unsigned long long)W * spp, tile_rows, rank, world, H};
-                RTDS_TRY(dirs_prepare(ctx, p->jitter_offset, W, H, spp, G, own, &launches, s));
+                RTDS_TRY(dirs_plan(ctx, p->jitter_offset, W, H, spp, G, own, &launches, DL));
+                have_dirs_launch = true;
+                if (!graph_path) {
+                    if (DL.grid > 0) RTDS_CUDA(cudaLaunchKernel((const void*)mt_expand_dirs_kernel, dim3(DL.grid), dim3(MT_THREADS), DL.args, 0, s));
+                    launches += 1;
+                    RTDS_CUDA(cudaGetLastError());
+                }
             }
         }
         ctx->dirs_pending = false;
@@ -1046,7 +1285,16 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.mt_snap = ctx->d_mt_snap;
     A.first_sample = p->jitter_offset;
     A.chunk_first = (int)c_first;
+    if (graph_path) {
+        const unsigned lin = (unsigned)((W + 15) / 16) * (unsigned)((A.local_rows + 7) / 8);
+        const void* fn = select_render_kernel(ctx, A, p, full, kdt, brute, kd_closest);
+        const bool shared = global_rows && ctx->shared.frame;
+        RTDS_TRY(render_frame_graph(ctx, A, fn, lin, have_dirs_launch ? &DL : nullptr, prefetch ? &PF : nullptr, shared, ctx->shared.seq, &launches));
+        RTDS_CUDA(cudaStreamSynchronize(s));        // the graph ends with the counters' copy into pinned memory
+        return render_stats_out(ctx, st, launches, A.local_rows, false, false);
+    }
     RTDS_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 8, s));
+    if (prefetch) RTDS_CUDA(cudaStreamWaitEvent(s, ctx->ev_pf1, 0));
     if (A.local_rows > 0 && strip) {
         const int blocks = (int)(c_last - c_first + 1);
         RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
@@ -1102,31 +1350,9 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             }
             const dim3 block(128);
             const unsigned lin = (unsigned)((W + 15) / 16) * (unsigned)((r1 - r0 + 7) / 8);     // quadrant-major linear grid
-            // four samples of a pixel per thread as one packet (see traverse_packet); RTDS_PACKET=0 turns it off
-            // (shadows without reflective / refractive materials stay on the packet kernel; the shadow rays are single)
-            // Only the samples of ONE pixel are packed. Packets of neighbouring pixels were built twice and measured slower both
-            // times, also with the hull test (round 2, B200): 2 x 2 pixels x 1 sample 0.205 vs 0.087 ms (bunny 640x480), 0.25 vs
-            // 0.20 ms (1080p), 4.7 vs 2.3 ms (7 M spheres); 2 pixels x 4 samples 1.07 vs 0.97 ms on the bench frame - node visits per
-            // ray drop 2-3.4x, but a thread then carries 4-8 rays' leaf work in sequence and the grid has 2-4x fewer threads
-            // to hide latency with (negative results). Removed again.
-            bool packet = (!full || !ctx->has_materials) && !kdt && !brute && !p->exact && spp % PK == 0 && A.bvh.leaf_box_prim &&
-                          A.shade.max_depth >= 1;
-            packet = packet && ctx->opt.packet != 0;
-            // interior boxes tested once per packet against the hull of the four reciprocal directions (default; RTDS_HULL=0:
-            // once per ray). Bench frame: same frame, node visits 3.17 -> 3.18 per ray, kernel 1.16 -> 0.99 ms.
-            const bool hull = ctx->opt.hull != 0;
-            if (packet && full) { if (hull) render_packet_kernel<true, true><<<lin, block, 0, s>>>(A); else render_packet_kernel<true, false><<<lin, block, 0, s>>>(A); }
-            else if (full) {
-                if (brute) render_full_kernel<2><<<lin, block, 0, s>>>(A);
-                else if (p->exact) render_full_kernel<0><<<lin, block, 0, s>>>(A);
-                else render_full_kernel<1><<<lin, block, 0, s>>>(A);
-            }
-            else if (packet) { if (hull) render_packet_kernel<false, true><<<lin, block, 0, s>>>(A); else render_packet_kernel<false, false><<<lin, block, 0, s>>>(A); }
-            else if (kd_closest) render_kernel<4><<<lin, block, 0, s>>>(A);
-            else if (kdt) render_kernel<3><<<lin, block, 0, s>>>(A);
-            else if (brute) render_kernel<2><<<lin, block, 0, s>>>(A);
-            else if (p->exact) render_kernel<0><<<lin, block, 0, s>>>(A);
-            else render_kernel<1><<<lin, block, 0, s>>>(A);
+            const void* fn = select_render_kernel(ctx, A, p, full, kdt, brute, kd_closest);
+            void* kargs[] = {(void*)&A};
+            RTDS_CUDA(cudaLaunchKernel(fn, dim3(lin), block, kargs, 0, s));
             launches += 1;
             // the kernel-time event goes in BEFORE the band callback: a device->host copy into pageable memory blocks the
             // host, and an event recorded after it would time the copy as well
@@ -1155,19 +1381,10 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     if (global_rows && ctx->shared.frame) RTDS_TRY(rtds_shared_frame_signal_wait(ctx, ctx->shared.seq, &launches));
     RTDS_CUDA(cudaEventRecord(ctx->ev1, s));
     if (st) {
-        unsigned long long* c = ctx->h_counters;      // pinned: the read-back is on every frame's critical path
-        RTDS_CUDA(cudaMemcpyAsync(c, ctx->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
+        // pinned: the read-back is on every frame's critical path
+        RTDS_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
         RTDS_CUDA(cudaStreamSynchronize(s));
-        memset(st, 0, sizeof *st);
-        st->node_tests = c[0]; st->prim_tests = c[1]; st->node_visits = c[2];
-        st->rays = c[3]; st->shadow_rays = c[4]; st->secondary_rays = c[5];
-        st->primary_rays = c[3] - c[4] - c[5];
-        RTDS_CUDA(cudaEventElapsedTime(&st->ms_kernel, ctx->ev2, ctx->ev3));
-        RTDS_CUDA(cudaEventElapsedTime(&st->ms_total, ctx->ev0, ctx->ev1));
-        st->kernel_launches = launches;
-        st->rows = A.local_rows;
-        st->reserved[0] = (int)(unsigned)c[7];      // shared frame: 1 + the rank the owner timed out on (0 = complete)
-        if (on_band) RTDS_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        return render_stats_out(ctx, st, launches, A.local_rows, on_band != nullptr, true);
     }
     return RTDS_OK;
 }
@@ -1175,24 +1392,6 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
 // ---------------------------------------------------------------------------------------------------
 // Shared frame: completion flags of the multi-GPU frame assembly (one 128-byte line per rank behind the frame)
 // ---------------------------------------------------------------------------------------------------
-__global__ void frame_signal_kernel(volatile uint32_t* flag, uint32_t seq)
-{
-    __threadfence_system();        // this rank's tile stores (previous kernel on the stream) before the flag
-    *flag = seq;
-}
-__global__ void frame_wait_kernel(const volatile uint32_t* flags, int world, uint32_t seq, long long timeout_cycles, int* status)
-{
-    const int r = threadIdx.x;
-    if (r < world) {
-        const long long t0 = clock64();
-        while ((int)(flags[32 * r] - seq) < 0) {     // a rank may already have signalled a later frame
-            if (clock64() - t0 > timeout_cycles) { atomicExch(status, 1 + r); break; }
-            __nanosleep(100);
-        }
-    }
-    __threadfence_system();
-}
-
 int rtds_shared_frame_signal_wait(rtds_ctx* ctx, uint32_t seq, int* launches)
 {
     cudaStream_t s = ctx->stream;
@@ -1232,6 +1431,7 @@ int rtds_trace_impl(rtds_ctx* ctx, int acc, int exact, const float* h_o, const f
     if (!brute && !kdt) A.bvh = make_view(ctx->bvh); else A.bvh = BvhView();
     if (kdt) A.kd = make_kd_view(ctx); else A.kd = KdView();
     A.sph = ctx->d_sph; A.tri = ctx->d_tris; A.prim_type = ctx->prim_type; A.n = ctx->n; A.hit = d_hit; A.t = d_t; A.counters = ctx->d_counters; A.exact = exact & 1;
+    if ((exact & RTDS_TRACE_TRI_GEOMETRIC) && ctx->prim_type == 1) { A.prim_type = 2; if (A.bvh.prim_type == 1) A.bvh.prim_type = 2; if (A.kd.prim_type == 1) A.kd.prim_type = 2; }
     RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
     if (kdt && (exact & RTDS_TRACE_KD_CLOSEST)) trace_kernel<4><<<(nrays + 127) / 128, 128, 0, s>>>(A);
     else if (kdt) trace_kernel<3><<<(nrays + 127) / 128, 128, 0, s>>>(A);

@@ -99,6 +99,21 @@ struct SharedFrame {
 
 #define RTDS_MAX_BANDS 8
 
+// One frame of a device-buffer / shared-frame render as ONE cudaGraphLaunch (frame_graph option): direction kernel and tree
+// prefetch side by side -> counters cleared -> render kernel -> [flag raised -> owner waits for every rank's flag] -> counters to
+// pinned memory. Built explicitly (no stream capture); kernel arguments are refreshed with cudaGraphExecKernelNodeSetParams only
+// when they changed, the graph is rebuilt only when its shape (which nodes, which render kernel) changes.
+struct FrameGraph {
+    cudaGraph_t     graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t k_dirs = nullptr, k_pf = nullptr, k_render = nullptr, k_signal = nullptr, k_wait = nullptr;
+    const void*     fn_render = nullptr;
+    bool            has_dirs = false, has_pf = false, has_signal = false, has_wait = false;
+    unsigned        grid_dirs = 0, grid_render = 0;
+    std::vector<unsigned char> last_dirs, last_render, last_pf;     // argument bytes of the last launch (skip SetParams when equal)
+    uint64_t        launches = 0, rebuilds = 0;
+};
+
 // Tuning / test switches of one context. Defaults come from the RTDS_* environment variables, read ONCE in rtds_create
 // (never on a frame's path); rtds_set_option() changes them afterwards (tests, A/B tools).
 struct RtdsOptions {
@@ -188,6 +203,9 @@ struct rtds_ctx {
     unsigned long long* h_counters = nullptr;  // pinned [16]: [0..7] render counters, [8] material flag, [9..11] LBVH root box, [12] depth
     uint8_t* h_pinned = nullptr;     // pinned host staging for D2H of frames
     SharedFrame shared;
+    FrameGraph  fg;
+    cudaStream_t pf_stream = nullptr;   // tree prefetch into L2 beside the direction kernel (l2_prefetch option, non-graph path)
+    cudaEvent_t  ev_pf0 = nullptr, ev_pf1 = nullptr;
     size_t   pinned_bytes = 0;
 };
 

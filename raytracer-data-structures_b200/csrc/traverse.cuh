@@ -78,6 +78,48 @@ __device__ __forceinline__ bool tri_test(float ox, float oy, float oz, float dx,
     return !(t < 0);
 }
 
+// Triangle::rayTriangleIntersect as the reference COMPILES it (main.cpp:163-215: the geometric branch, MOLLER_TRUMBORE is never
+// defined): plane hit with N = v0v1 x v0v2, t = (N.orig + N.v0) / N.dir (right for orig = 0 only - kept bug for bug), three
+// inside-outside edge tests. Selected by rtds_render_params.tri_geometric / RTDS_TRACE_TRI_GEOMETRIC (prim_type 2 in the
+// views). Pinned to the reference's own class through the compiled reference (tests/test_gpu_triangles.py).
+__device__ __forceinline__ bool tri_test_geometric(float ox, float oy, float oz, float dx, float dy, float dz, float4 v0, float4 v1, float4 v2,
+                                                   float& t)
+{
+    const float ax = v1.x - v0.x, ay = v1.y - v0.y, az = v1.z - v0.z;            // v0v1
+    const float bx = v2.x - v0.x, by = v2.y - v0.y, bz = v2.z - v0.z;            // v0v2
+    const float Nx = ay * bz - az * by, Ny = az * bx - ax * bz, Nz = ax * by - ay * bx;
+    const float nd = Nx * dx + Ny * dy + Nz * dz;
+    if (fabsf(nd) < 1e-6f) return false;                                         // EPS, main.cpp:59,175
+    const float dd = Nx * v0.x + Ny * v0.y + Nz * v0.z;
+    t = ((Nx * ox + Ny * oy + Nz * oz) + dd) / nd;                               // main.cpp:182
+    if (t < 0) return false;
+    const float Px = ox + dx * t, Py = oy + dy * t, Pz = oz + dz * t;
+    {
+        const float px = Px - v0.x, py = Py - v0.y, pz = Pz - v0.z;
+        const float cx = ay * pz - az * py, cy = az * px - ax * pz, cz = ax * py - ay * px;
+        if (Nx * cx + Ny * cy + Nz * cz < 0) return false;
+    }
+    {
+        const float ex = v2.x - v1.x, ey = v2.y - v1.y, ez = v2.z - v1.z;
+        const float px = Px - v1.x, py = Py - v1.y, pz = Pz - v1.z;
+        const float cx = ey * pz - ez * py, cy = ez * px - ex * pz, cz = ex * py - ey * px;
+        if (Nx * cx + Ny * cy + Nz * cz < 0) return false;
+    }
+    {
+        const float ex = v0.x - v2.x, ey = v0.y - v2.y, ez = v0.z - v2.z;
+        const float px = Px - v2.x, py = Py - v2.y, pz = Pz - v2.z;
+        const float cx = ey * pz - ez * py, cy = ez * px - ex * pz, cz = ex * py - ey * px;
+        if (Nx * cx + Ny * cy + Nz * cz < 0) return false;
+    }
+    return true;
+}
+// type 1: Moeller-Trumbore, type 2: the reference's compiled geometric test
+__device__ __forceinline__ bool tri_test_any(int type, float ox, float oy, float oz, float dx, float dy, float dz, float4 v0, float4 v1,
+                                             float4 v2, float& t)
+{
+    return type == 2 ? tri_test_geometric(ox, oy, oz, dx, dy, dz, v0, v1, v2, t) : tri_test(ox, oy, oz, dx, dy, dz, v0, v1, v2, t);
+}
+
 // primitive test on an objId-indexed table (NONE loop, KD leaves)
 __device__ __forceinline__ bool obj_test(int type, const float4* __restrict__ sph, const float4* __restrict__ tri, int i, float ox, float oy,
                                          float oz, float dx, float dy, float dz, float& t0, float& t1)
@@ -87,7 +129,7 @@ __device__ __forceinline__ bool obj_test(int type, const float4* __restrict__ sp
         return sphere_test(ox, oy, oz, dx, dy, dz, make_float4(s.x, s.y, s.z, s.w * s.w), t0, t1);
     }
     float t;
-    if (!tri_test(ox, oy, oz, dx, dy, dz, __ldg(tri + 3 * (size_t)i), __ldg(tri + 3 * (size_t)i + 1), __ldg(tri + 3 * (size_t)i + 2), t)) return false;
+    if (!tri_test_any(type, ox, oy, oz, dx, dy, dz, __ldg(tri + 3 * (size_t)i), __ldg(tri + 3 * (size_t)i + 1), __ldg(tri + 3 * (size_t)i + 2), t)) return false;
     t0 = t1 = t;
     return true;
 }
@@ -118,7 +160,7 @@ struct BvhView {
     const Node64* nodes;
     const float4* leaf_sph;
     const float4* leaf_tri;
-    int           prim_type;
+    int           prim_type;       // 0 spheres, 1 triangles (Moeller-Trumbore), 2 triangles (the reference's compiled geometric test)
     const int*    prim_order;
     const int*    leaf_parent;
     int           root_ref;
@@ -134,8 +176,8 @@ __device__ __forceinline__ bool leaf_test(const BvhView& B, int leaf, float ox, 
 {
     if (B.prim_type == 0) { float4 s = __ldg(B.leaf_sph + leaf); s.w = s.w * s.w; return sphere_test(ox, oy, oz, dx, dy, dz, s, t0, t1); }   // radius2 = r*r, accelerators.h:71
     float t;
-    if (!tri_test(ox, oy, oz, dx, dy, dz, __ldg(B.leaf_tri + 3 * (size_t)leaf), __ldg(B.leaf_tri + 3 * (size_t)leaf + 1),
-                  __ldg(B.leaf_tri + 3 * (size_t)leaf + 2), t))
+    if (!tri_test_any(B.prim_type, ox, oy, oz, dx, dy, dz, __ldg(B.leaf_tri + 3 * (size_t)leaf), __ldg(B.leaf_tri + 3 * (size_t)leaf + 1),
+                      __ldg(B.leaf_tri + 3 * (size_t)leaf + 2), t))
         return false;
     t0 = t1 = t;
     return true;
@@ -579,7 +621,7 @@ __device__ __forceinline__ void brute_force_block(int type, const float4* __rest
                 float t0, t1;
                 bool h;
                 if (type == 0) h = sphere_test(ox, oy, oz, dx, dy, dz, sh[i], t0, t1);
-                else { float t; h = tri_test(ox, oy, oz, dx, dy, dz, sh[3 * i], sh[3 * i + 1], sh[3 * i + 2], t); t0 = t1 = t; }
+                else { float t; h = tri_test_any(type, ox, oy, oz, dx, dy, dz, sh[3 * i], sh[3 * i + 1], sh[3 * i + 2], t); t0 = t1 = t; }
                 if (h) {
                     if (t0 < 0) t0 = t1;
                     if (t0 < tnear) { tnear = t0; best = base + i; }

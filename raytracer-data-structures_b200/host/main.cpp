@@ -73,6 +73,9 @@ int main(int, char**)
 	const char* models_dir = getenv("RTDS_MODELS_DIR") ? getenv("RTDS_MODELS_DIR") : "models";
 	const char* out_path = getenv("RTDS_OUT") ? getenv("RTDS_OUT") : "./output.ppm";
 	const bool lbvh_true = getenv("RTDS_LBVH_MODE") && !strcmp(getenv("RTDS_LBVH_MODE"), "true");
+	// RTDS_TIMING=1: wall-clock stage breakdown of this (cold) run on stderr
+	const bool timing = env_int("RTDS_TIMING", 0) != 0;
+	auto stage = [&](const char* what) { if (timing) std::cerr << "[rtds_main] " << what << " done at " << seconds_since(begin_total_time) << " s" << endl; };
 
 	// Print settings (main.cpp:730-736)
 	cout << "Start rendering .... \n";
@@ -107,6 +110,7 @@ int main(int, char**)
 		cout << "Number of triangles: " << scene.tris.size() / 9 << endl;
 	}
 
+	stage("scene loaded");
 	cout << "Wraping BV for each object .... \n";
 	cout << "Done .... \n Time: ";
 	cout << float(seconds_since(begin_time)) << "s";
@@ -115,10 +119,12 @@ int main(int, char**)
 	std::vector<rtds_ctx*> ctx(n_gpus, nullptr);
 	for (int g = 0; g < n_gpus; ++g) {
 		CHECK(rtds_create(&ctx[g], g));
+		stage("rtds_create (CUDA context + module load)");
 		if (triangles) CHECK(rtds_set_triangles(ctx[g], scene.tris.data(), tri_mat.data(), (int)(scene.tris.size() / 9)));
 		else CHECK(rtds_set_spheres(ctx[g], scene.cxyz_r.data(), scene.rgb_mat.data(), scene.n()));
 	}
 
+	stage("scene uploaded");
 	rtds_build_params bp;
 	memset(&bp, 0, sizeof bp);
 	bp.mode = (settings.dataStructure == LBVH && lbvh_true) ? RTDS_MODE_TRUE : RTDS_MODE_COMPAT;
@@ -166,6 +172,7 @@ int main(int, char**)
 		break;
 	}
 
+	stage("structure built");
 	// render (main.cpp:541-566): every GPU renders its interleaved scanline tiles into the shared host frame
 	std::vector<uint8_t> rgb((size_t)settings.width * settings.height * 3);
 	std::vector<rtds_render_stats> rs(n_gpus);
@@ -182,13 +189,16 @@ int main(int, char**)
 				rp.width = settings.width; rp.height = settings.height; rp.aa_samples = settings.aa_samples;
 				rp.exact = exact; rp.rank = g; rp.world = n_gpus; rp.tile_rows = 8;
 				rp.kd_closest = env_int("RTDS_KD_CLOSEST", 0);   // 0 = the reference's any-hit, unshaded KD frame
+				rp.tri_geometric = env_int("RTDS_TRI_GEOMETRIC", 0);   // 1 = the triangle test the reference compiles (main.cpp:163-215)
 				if (shared) CHECK(rtds_render_shared(ctx[g], settings.dataStructure, &rp, 1u, &rs[g]));
 				else CHECK(rtds_render(ctx[g], settings.dataStructure, &rp, rgb.data(), nullptr, nullptr, &rs[g]));
 			});
 		for (auto& t : th) t.join();
 	}
 	if (shared) CHECK(rtds_shared_frame_read(ctx[0], rgb.data()));
+	stage("frame rendered and downloaded");
 	write_ppm(out_path, settings, rgb);
+	stage("output.ppm written");
 
 	unsigned long long tests = 0, rays = 0;
 	float traverse_ms = 0;

@@ -267,6 +267,21 @@ class Ref:
         self.lib.ref_trace(self._p(o), self._p(d), n, acc, self._p(hit), self._p(t), C.byref(cand))
         return hit, t, cand.value
 
+    def triangle_trace(self, tris, o, d):
+        """Brute-force closest hit with the reference's own class Triangle / rayTriangleIntersect (compiled geometric branch):
+        (hit index | -1, t, number of triangles hit) per ray."""
+        tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+        o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+        n = d.shape[0]
+        if o.shape[0] == 1 and n > 1:
+            o = np.ascontiguousarray(np.broadcast_to(o, (n, 3)))
+        hit = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float32)
+        cnt = np.zeros(n, np.int32)
+        self.lib.ref_triangle_trace(self._p(tris), tris.shape[0], self._p(o), self._p(d), n, self._p(hit), self._p(t), self._p(cnt))
+        return hit, t, cnt
+
     def render_rows(self, acc, width, height, spp, y0=0, y1=None, want_dirs=False, want_accum=False):
         y1 = height if y1 is None else y1
         rows = y1 - y0

@@ -217,3 +217,34 @@ def test_visible_clones_variant_packet_equals_reference_traversal(gpu_ctx, oracl
     sh, _, _, st_s = gpu_ctx.render(rt.LBVH, W, H, spp, shadows=1)
     sh_e, _, _, _ = gpu_ctx.render(rt.LBVH, W, H, spp, shadows=1, exact=True)
     assert np.array_equal(sh, sh_e) and st_s["shadow_rays"] > 0
+
+
+@pytest.mark.parametrize("spp,shadows", [(4, 0), (1, 0), (4, 1)])
+def test_frame_graph_and_l2_prefetch_do_not_change_the_frame(gpu_ctx, spp, shadows):
+    """frame_graph (the whole device-buffer frame as ONE cudaGraphLaunch) and l2_prefetch (the tree streamed into L2 beside the
+    direction kernel) are pure scheduling: bytes, counters and ray counts equal the plain stream path's, frame after frame, also
+    when the arguments change between frames (jitter offset, rank, resolution: SetParams / rebuild paths of the graph)."""
+    import torch
+    sph, mat = T.bunny_scene()
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+    cases = [(400, 300, 0, 1, 0), (400, 300, 0, 1, 0), (400, 300, 0, 1, 4321), (400, 300, 1, 3, 0), (322, 203, 0, 1, 0), (400, 300, 0, 1, 0)]
+    buf = torch.zeros((300, 400, 3), dtype=torch.uint8, device="cuda")
+
+    def run():
+        out = []
+        for (W, H, rank, world, joff) in cases:
+            buf.zero_()
+            p = gpu_ctx.render_params(W, H, spp, rank=rank, world=world, shadows=shadows, jitter_offset=joff)
+            st = gpu_ctx.render_device(rt.LBVH, p, buf.data_ptr())
+            rows = rt.rows_for_rank(H, 8, rank, world)
+            out.append((buf.cpu().numpy().reshape(-1)[: rows * W * 3].copy(), st["rays"], st["node_visits"], st["prim_tests"], st["rows"]))
+        return out
+
+    plain = run()
+    for graph, pf in ((1, 0), (0, 1), (1, 1)):
+        with T.option(gpu_ctx, "frame_graph", graph), T.option(gpu_ctx, "l2_prefetch", pf):
+            got = run()
+        for a, b in zip(plain, got):
+            assert np.array_equal(a[0], b[0]) and a[1:] == b[1:], (graph, pf)
+    assert plain[0][1] >= 400 * 300 * spp and (shadows == 0) == (plain[0][1] == 400 * 300 * spp)

@@ -14,8 +14,14 @@ rt = T.rtds_b200
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("graph", [0, 1])
 @pytest.mark.parametrize("world,W,H,spp,shadows", [(2, 320, 200, 4, 0), (3, 322, 203, 4, 0), (4, 640, 360, 1, 0), (2, 320, 200, 2, 1)])
-def test_shared_frame_in_process_equals_single_rank(gpu_ctx, world, W, H, spp, shadows):
+def test_shared_frame_in_process_equals_single_rank(gpu_ctx, world, W, H, spp, shadows, graph):
+    with T.option(gpu_ctx, "frame_graph", graph):
+        _shared_frame_in_process(gpu_ctx, world, W, H, spp, shadows, graph)
+
+
+def _shared_frame_in_process(gpu_ctx, world, W, H, spp, shadows, graph):
     sph, mat = T.synthetic_scene(3000, 31)
     gpu_ctx.set_spheres(sph, mat)
     gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
@@ -23,6 +29,7 @@ def test_shared_frame_in_process_equals_single_rank(gpu_ctx, world, W, H, spp, s
     ranks = [gpu_ctx] + [rt.Rtds(0) for _ in range(world - 1)]
     try:
         for c in ranks[1:]:
+            c.set_option("frame_graph", graph)
             c.set_spheres(sph, mat)
             c.build(rt.LBVH, mode=rt.MODE_TRUE)
         handle = gpu_ctx.shared_frame_create(W, H, world)

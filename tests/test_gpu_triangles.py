@@ -95,3 +95,41 @@ def test_triangle_kdtree_any_hit(gpu_ctx):
     h_none, _, _ = gpu_ctx.trace(rt.NONE, o, d)
     diff = np.count_nonzero((h_kd > 0) != (h_none >= 0))
     assert diff <= 0.001 * h_none.size, f"KD any-hit disagrees with brute force on {diff} rays"
+
+
+def test_geometric_triangle_test_equals_reference_class_triangle(gpu_ctx, ref, oracle):
+    """SURVEY 8a14, PINNED: with tri_geometric the GPU evaluates Triangle::rayTriangleIntersect as the reference compiles it (the
+    geometric branch, main.cpp:163-215). The compiled, unmodified reference instantiates its own class Triangle and answers the
+    same rays (oracle/ref_harness.cpp: ref_triangle_trace): hit triangle and t bits must be identical - brute force (NONE loop,
+    main.cpp:376-386) and through every BVH builder (unpruned reference traversal and the ordered one), rays from the camera origin
+    and from displaced origins (where main.cpp:182's plane distance is wrong: reproduced bug for bug)."""
+    tris, mat = T.triangle_scene(3000, 7, ground=True)
+    gpu_ctx.set_triangles(tris, mat)
+    o, d = _rays(8000, 9, tris)
+    d[:40] = np.asarray([0, 0, -1], np.float32)
+    h_r, t_r, cnt_r = ref.triangle_trace(tris, o, d)
+    h_n, t_n, _ = gpu_ctx.trace(rt.NONE, o, d, tri_geometric=True)
+    assert np.array_equal(h_n, h_r) and t_n.tobytes() == t_r.tobytes()
+    h_p, t_p, _ = oracle.trace(tris, None, None, o, d, prim_type=2)
+    assert np.array_equal(h_p, h_r) and t_p.tobytes() == t_r.tobytes()
+    assert (h_r[:4000] >= 0).mean() > 0.5 and cnt_r.max() >= 2
+    # through the trees: candidates are the leaves whose boxes the reference's slab test passes (boxIntersect), then the same test.
+    # Origin-0 rays only (what render() casts): for displaced origins the reference's t does not lie on the ray, so a box test
+    # along the ray says nothing about it.
+    o0, d0 = o[:4000], d[:4000]
+    for acc, kw, tie in ((rt.LBVH, dict(mode=rt.MODE_TRUE), 1), (rt.BVH, dict(mode=rt.MODE_SAH), 1)):
+        gpu_ctx.build(acc, **kw)
+        nodes, order = gpu_ctx.export_bvh()
+        h_o, t_o, _ = oracle.trace(tris, nodes, order, o0, d0, tie_by_objid=tie, prim_type=2)
+        for exact in (True, False):
+            h, t, _ = gpu_ctx.trace(acc, o0, d0, exact=exact, tri_geometric=True)
+            assert np.array_equal(h, h_o) and t.tobytes() == t_o.tobytes(), (acc, exact)
+        lost = np.count_nonzero(h_o != h_r[:4000])
+        assert lost <= 0.003 * 4000, lost              # only grazing hits the float slab test rejects
+    # rendered frame with the geometric test == the restatement's (shading uses the same v0v1 x v0v2 normal, main.cpp:165-168)
+    W, H, spp = 200, 150, 2
+    rgb, hit, accum, _ = gpu_ctx.render(rt.BVH, W, H, spp, want_hit=True, want_accum=True, tri_geometric=1)
+    rgb_o, hit_o, accum_o, _ = oracle.render_rows(tris, mat, nodes, order, W, H, spp, tie_by_objid=1, want_accum=True, prim_type=2)
+    assert np.array_equal(hit, hit_o) and accum.tobytes() == accum_o.tobytes() and np.array_equal(rgb, rgb_o)
+    rgb_mt = gpu_ctx.render(rt.BVH, W, H, spp)[0]
+    assert (np.abs(rgb.astype(int) - rgb_mt.astype(int)).max(axis=2) > 0).mean() < 0.01     # same picture as Moeller-Trumbore but for edges

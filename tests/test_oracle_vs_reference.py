@@ -105,3 +105,30 @@ def test_port_kd_closest_hit_on_the_reference_kd_tree(ref, oracle):
     same = hit == gold["hit_none"].reshape(-1)
     t_none = oracle.trace(sph, None, None, np.zeros((1, 3), np.float32), d[same][::97])[1]
     assert t[same][::97].tobytes() == t_none.tobytes()                # and the same tnear bits
+
+
+def test_port_geometric_triangle_test_equals_reference_class_triangle(ref, oracle):
+    """the reference's class Triangle (main.cpp:107-216) is never instantiated by its loader, but its
+    rayTriangleIntersect IS compiled (the geometric branch; MOLLER_TRUMBORE is never defined). The harness instantiates the class
+    and calls it; the port's restatement (prim_type 2) must give the same hit triangle and the same t bits - rays from the camera
+    origin (what render() casts) and from arbitrary origins (where main.cpp:182's `N.orig + d` is wrong: kept bug for bug)."""
+    tris, _ = T.triangle_scene(3000, 7, ground=True)
+    rng = np.random.default_rng(8)
+    n = 6000
+    cen = tris.reshape(-1, 3, 3).mean(1)
+    tgt = cen[rng.integers(0, cen.shape[0], n)] + rng.normal(size=(n, 3)).astype(np.float32) * np.float32(0.2)
+    o = np.zeros((n, 3), np.float32)
+    o[n // 2:] = rng.normal(size=(n - n // 2, 3)).astype(np.float32) * np.float32(5)
+    d = tgt - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    d[:50] = np.asarray([0, 0, -1], np.float32)                  # axis-parallel rays: zero components in the edge tests
+    d[50:60, 1] = 0
+    h_r, t_r, cnt_r = ref.triangle_trace(tris, o, d)
+    h_p, t_p, _ = oracle.trace(tris, None, None, o, d, prim_type=2)
+    assert np.array_equal(h_r, h_p) and t_r.tobytes() == t_p.tobytes()
+    assert (h_r[: n // 2] >= 0).mean() > 0.5 and cnt_r.max() >= 2
+    # and it is a different function from Moeller-Trumbore (prim_type 1): same triangles for origin-0 rays up to edge cases,
+    # different answers for displaced origins
+    h_m, t_m, _ = oracle.trace(tris, None, None, o, d, prim_type=1)
+    assert (h_m[: n // 2] == h_p[: n // 2]).mean() > 0.99
+    assert (h_m[n // 2:] != h_p[n // 2:]).mean() > 0.05
