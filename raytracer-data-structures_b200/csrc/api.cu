@@ -13,7 +13,7 @@ static thread_local char g_err[1024] = "";
 const RtdsOptionName g_rtds_option_names[] = {
     {"block_order", "RTDS_BLOCK_ORDER", &RtdsOptions::block_order}, {"strip", "RTDS_STRIP", &RtdsOptions::strip},
     {"bands", "RTDS_BANDS", &RtdsOptions::bands}, {"band_ratio", "RTDS_BAND_RATIO", &RtdsOptions::band_ratio},
-    {"packet", "RTDS_PACKET", &RtdsOptions::packet}, {"hull", "RTDS_HULL", &RtdsOptions::hull},
+    {"packet", "RTDS_PACKET", &RtdsOptions::packet}, {"hull", "RTDS_HULL", &RtdsOptions::hull}, {"dyn", "RTDS_DYN", &RtdsOptions::dyn},
     {"zerocopy", "RTDS_ZEROCOPY", &RtdsOptions::zerocopy}, {"trace_frame", "RTDS_TRACE_FRAME", &RtdsOptions::trace_frame},
     {"median_small", "RTDS_MEDIAN_SMALL", &RtdsOptions::median_small}, {"median_coop", "RTDS_MEDIAN_COOP", &RtdsOptions::median_coop},
     {"median_debug", "RTDS_MEDIAN_DEBUG", &RtdsOptions::median_debug}, {"node_preorder", "RTDS_NODE_PREORDER", &RtdsOptions::node_preorder},
@@ -168,7 +168,7 @@ static int create_resources(rtds_ctx* c)
     RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_pf1, cudaEventDisableTiming));
     RTDS_CUDA(cudaEventCreate(&c->ev0)); RTDS_CUDA(cudaEventCreate(&c->ev1));
     RTDS_CUDA(cudaEventCreate(&c->ev2)); RTDS_CUDA(cudaEventCreate(&c->ev3));
-    RTDS_CUDA(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8));
+    RTDS_CUDA(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 16));      // [0..7] render counters, [8..15] tile queue heads
     RTDS_CUDA(cudaMallocHost(&c->h_counters, sizeof(unsigned long long) * 16));    // [8..15]: material flag read-back
     // main.cpp:775: Sphere light2(0, (0,3,30), 10, (1,1,1), 0, 0, emission (1,1,1))
     c->n_lights = 1;
@@ -298,6 +298,18 @@ static int upload_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat
     return RTDS_OK;
 }
 
+// error exit of the overlapped one-call forms: wait for everything they queued (uploads still reading the caller's host
+// buffers on the copy stream, the direction kernel on the side stream) and drop the pending state
+static void frame_abort(rtds_ctx* c)
+{
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamSynchronize(c->jit_stream);
+    cudaStreamSynchronize(c->stream);
+    c->materials_pending = false;
+    c->dirs_pending = false;
+    (void)cudaGetLastError();
+}
+
 int rtds_finish_materials(rtds_ctx* c)
 {
     if (!c->materials_pending) return RTDS_OK;
@@ -334,15 +346,20 @@ int rtds_frame(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n, in
     RTDS_TRACE_RECORD(c, 0, c->stream);
     const auto t0 = std::chrono::steady_clock::now();
     auto us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
-    RTDS_TRY(rtds_prefetch_dirs(c, rp));
+    // every call is synchronous on return, also a failing one: nothing may still read the caller's buffers or run on the side
+    // streams after an error exit
+    auto fail = [&](int rc) { frame_abort(c); return rc; };
+    int rc = rtds_prefetch_dirs(c, rp);
+    if (rc != RTDS_OK) return fail(rc);
     const double t_dirs = us();
-    RTDS_TRY(upload_spheres(c, cxyz_r, rgb_mat, n, true));
+    if ((rc = upload_spheres(c, cxyz_r, rgb_mat, n, true)) != RTDS_OK) return fail(rc);
     const double t_up = us();
-    RTDS_TRY(rtds_build(c, acc, bp, bst));
+    if ((rc = rtds_build(c, acc, bp, bst)) != RTDS_OK) return fail(rc);
     const double t_build = us();
-    RTDS_TRY(rtds_finish_materials(c));
+    if ((rc = rtds_finish_materials(c)) != RTDS_OK) return fail(rc);
     const double t_mat = us();
-    const int rc = rtds_render(c, acc, rp, rgb, nullptr, nullptr, rst);
+    rc = rtds_render(c, acc, rp, rgb, nullptr, nullptr, rst);
+    if (rc != RTDS_OK) return fail(rc);
     if (trace && rc == RTDS_OK && c->trace_ev[0]) {
         cudaDeviceSynchronize();
         float d0 = 0, d1 = 0, b0 = 0, b1 = 0, m1 = 0, r0 = 0, r1 = 0;
@@ -373,6 +390,8 @@ int rtds_set_triangles(rtds_ctx* c, const float* v0v1v2, const float* rgb_mat, i
     if (!c || !v0v1v2 || n <= 0) { rtds_set_error("set_triangles: bad arguments"); return RTDS_ERR_INVALID; }
     RTDS_CUDA(cudaSetDevice(c->device));
     RTDS_CUDA(cudaStreamSynchronize(c->stream));
+    RTDS_CUDA(cudaStreamSynchronize(c->copy_stream));      // an asynchronous material upload of a previous rtds_frame
+    c->materials_pending = false;
     c->n = 0;
     c->bvh.valid = false; c->kd.valid = false; c->bvh_acc = -1;
     if (c->tri_capacity < n) {
@@ -693,11 +712,13 @@ int rtds_frame_shared(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, in
 {
     if (!c || !rp) { rtds_set_error("frame_shared: bad arguments"); return RTDS_ERR_INVALID; }
     RTDS_CUDA(cudaSetDevice(c->device));
-    RTDS_TRY(rtds_prefetch_dirs(c, rp));
-    RTDS_TRY(upload_spheres(c, cxyz_r, rgb_mat, n, true));
-    RTDS_TRY(rtds_build(c, acc, bp, bst));
-    RTDS_TRY(rtds_finish_materials(c));
-    return rtds_render_shared(c, acc, rp, frame_seq, rst);
+    int rc = rtds_prefetch_dirs(c, rp);
+    if (rc == RTDS_OK) rc = upload_spheres(c, cxyz_r, rgb_mat, n, true);
+    if (rc == RTDS_OK) rc = rtds_build(c, acc, bp, bst);
+    if (rc == RTDS_OK) rc = rtds_finish_materials(c);
+    if (rc == RTDS_OK) rc = rtds_render_shared(c, acc, rp, frame_seq, rst);
+    if (rc != RTDS_OK) frame_abort(c);       // synchronous on return, also when failing
+    return rc;
 }
 
 int rtds_shared_frame_ptr(rtds_ctx* c, void** d_frame)

@@ -354,6 +354,12 @@ static int build_kd_attempt(rtds_ctx* ctx, const rtds_build_params* bp, rtds_bui
         int lg = 0; { unsigned v = (unsigned)n; while (v > 1) { v >>= 1; ++lg; } }
         max_depth = (int)std::round(8 + 1.3f * lg);
     }
+    // kdtreeIntersect's todo stack holds 64 entries (accelerators.h:1008: KdToDo todo[64]) and so does the device traversal: a
+    // deeper tree could silently lose subtrees, so it is refused here instead of rendered wrongly
+    if (max_depth > 64) {
+        rtds_set_error("build: kd_max_depth %d exceeds the 64-entry traversal stack (accelerators.h:1008)", max_depth);
+        return RTDS_ERR_UNSUPPORTED;
+    }
     rtds_free_kd(ctx->kd);
     cudaStream_t s = ctx->stream;
     int launches = 0;

@@ -178,9 +178,11 @@ __global__ void __launch_bounds__(MT_THREADS) mt_expand_dirs_kernel(const uint32
 {
     __shared__ __align__(16) uint32_t words[(MT_SNAP_EVERY + 1) * MT_N];      // slice 0 = the snapshot
     const int t = threadIdx.x;
-    // world == 1: block b = chunk s0 + b. world > 1: the grid covers only the rank's OWN scanline tiles
-    // (chunks_per_tile blocks per owned tile; owned tiles are never adjacent, so no chunk is generated twice)
+    // world == 1: block b = chunk s0 + b. world > 1: the grid covers only the rank's OWN scanline tiles (chunks_per_tile blocks
+    // per owned tile). A chunk that straddles a tile boundary is regenerated by a block of each tile it touches, and every block
+    // stores only the samples of ITS tile [lo, hi) - no direction is written twice, also when a tile is shorter than a chunk.
     unsigned long long chunk = (unsigned long long)s0 + blockIdx.x;
+    long long lo = 0, hi = (long long)n_samples;      // frame samples this block may write
     if (own.world > 1) {
         const unsigned k = blockIdx.x / (unsigned)chunks_per_tile, c = blockIdx.x - k * (unsigned)chunks_per_tile;
         const unsigned long long tile = (unsigned long long)own.rank + (unsigned long long)k * own.world;
@@ -190,6 +192,8 @@ __global__ void __launch_bounds__(MT_THREADS) mt_expand_dirs_kernel(const uint32
         const unsigned long long w0 = own.first_word + row0 * own.row_words, w1 = own.first_word + row1 * own.row_words - 1;
         chunk = w0 / (MT_SNAP_EVERY * MT_N) + c;
         if (chunk > w1 / (MT_SNAP_EVERY * MT_N)) return;
+        lo = (long long)(row0 * (own.row_words / 4));
+        hi = (long long)(row1 * (own.row_words / 4));
     }
     const unsigned long long wlo = chunk * MT_SNAP_EVERY * MT_N;
     const uint32_t* src = snap + (size_t)chunk * MT_N;
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(MT_THREADS) mt_expand_dirs_kernel(const uint32
     // last) need no 64-bit range check per sample, and when aa_samples divides the thread stride the pixel coordinates
     // advance by additions instead of two divisions per sample
     const long long rel = (long long)as0 - (long long)first_sample;
-    const bool inside = rel >= 0 && rel + CHUNK_SAMPLES <= (long long)n_samples;
+    const bool inside = rel >= lo && rel + CHUNK_SAMPLES <= hi;
     const bool stepping = inside && (MT_THREADS % spp) == 0;
     const unsigned step_px = stepping ? (unsigned)(MT_THREADS / spp) : 0u;
     unsigned px = 0, py = 0;
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(MT_THREADS) mt_expand_dirs_kernel(const uint32
     }
     for (int i = t; i < CHUNK_SAMPLES; i += MT_THREADS) {
         const long long gl = rel + i;
-        if (inside || (gl >= 0 && gl < (long long)n_samples)) {
+        if (inside || (gl >= lo && gl < hi)) {
             const unsigned g = (unsigned)gl;
             if (!stepping) {
                 const unsigned pix = fast_div(g, div_spp);

@@ -95,3 +95,37 @@ def test_render_is_deterministic_and_rebuild_stable(gpu_ctx):
         trees.append(nodes.tobytes() + order.tobytes())
         frames.append(gpu_ctx.render(rt.BVH, 320, 240, 2)[0].tobytes())
     assert len(set(trees)) == 1 and len(set(frames)) == 1
+
+
+def test_failing_frame_call_is_synchronous_and_leaves_the_context_usable():
+    """rtds_frame that fails AFTER it queued its uploads (here: a KD depth beyond the 64-entry traversal stack, refused by the
+    builder) must not leave copies or the direction kernel running behind the error return, and the context must work afterwards;
+    kd_max_depth > 64 is an error, not a silently wrong frame (kdtreeIntersect's todo[64], accelerators.h:1008)."""
+    import torch
+    ctx = rt.Rtds(0)
+    try:
+        sph, mat = T.synthetic_scene(20000, 3)
+        sph_pin, mat_pin = torch.from_numpy(sph).pin_memory(), torch.from_numpy(mat).pin_memory()
+        out = np.zeros((120, 160, 3), np.uint8)
+        bp = rt.BuildParams()
+        bp.kd_max_depth = 65
+        rp = ctx.render_params(160, 120, 4)
+        for _ in range(3):
+            rc = ctx.lib.rtds_frame(ctx.ctx, C.c_void_p(sph_pin.data_ptr()), C.c_void_p(mat_pin.data_ptr()), sph.shape[0], rt.KDTREE, C.byref(bp),
+                                    C.byref(rp), out.ctypes.data_as(C.c_void_p), None, None)
+            assert rc == -8 and b"64-entry" in ctx.lib.rtds_last_error()          # UNSUPPORTED
+            sph_pin.fill_(0.0)                      # would corrupt an upload still in flight ...
+            sph_pin.copy_(torch.from_numpy(sph))    # ... and is restored for the next round
+        with pytest.raises(rt.RtdsError):
+            ctx.build(rt.KDTREE, kd_max_depth=100)
+        # the context is fine: a normal frame through the same call, equal to the three-call sequence
+        rgb, bst, rst = ctx.frame(sph, mat, rt.LBVH, 160, 120, 4, mode=rt.MODE_TRUE)
+        ctx.set_spheres(sph, mat)
+        ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+        assert np.array_equal(rgb, ctx.render(rt.LBVH, 160, 120, 4)[0])
+        tris, tmat = T.triangle_scene(500, 5)
+        ctx.set_triangles(tris, tmat)               # right after an asynchronous-material frame: no stale pending state
+        ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+        assert ctx.render(rt.LBVH, 64, 48, 1)[3]["primary_rays"] == 64 * 48
+    finally:
+        ctx.close()

@@ -104,3 +104,34 @@ def test_shadowed_packet_kernel_matches_restatement_and_full_kernel(gpu_ctx, ora
         assert st_f["shadow_rays"] == st["shadow_rays"]
     finally:
         gpu_ctx.set_lights(np.asarray([[0, 3, 30, 10, 1, 1, 1]], np.float32))
+
+
+@pytest.mark.parametrize("acc", [rt.BVH, rt.LBVH])
+@pytest.mark.parametrize("shadows,spp", [(0, 4), (1, 4), (1, 8)])
+def test_material_scenes_through_the_packet_kernel(gpu_ctx, oracle, acc, shadows, spp):
+    """Scenes with REFLECTION_AND_REFRACTION / REFLECTION primitives and aa_samples % 4 == 0: the primary rays go as packets
+    (render_packet_kernel<.., MATERIALS>), a ray that hits such a primitive continues through castRay's material branches alone.
+    Result = the single-ray castRay kernel's (packet option off) = the CPU restatement's: hit ids, float sums, bytes, ray counts."""
+    sph, mat = T.material_scene(1500, 13, frac_rr=0.15, frac_refl=0.15)
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.set_lights(LIGHTS3)
+    try:
+        gpu_ctx.build(acc, mode=rt.MODE_TRUE if acc == rt.LBVH else rt.MODE_COMPAT)
+        nodes, order = gpu_ctx.export_bvh()
+        W, H = 240, 180
+        pk = gpu_ctx.render(acc, W, H, spp, want_hit=True, want_accum=True, shadows=shadows)
+        with T.option(gpu_ctx, "packet", 0):
+            sr = gpu_ctx.render(acc, W, H, spp, want_hit=True, want_accum=True, shadows=shadows)
+        assert np.array_equal(pk[1], sr[1]) and pk[2].tobytes() == sr[2].tobytes() and np.array_equal(pk[0], sr[0])
+        for k in ("rays", "primary_rays", "shadow_rays", "secondary_rays"):
+            assert pk[3][k] == sr[3][k], k
+        assert pk[3]["secondary_rays"] > 100
+        # (the median split over spheres of mixed size drops ranges, accelerators.h:321-327: leaves then carry range boxes and the
+        # packet kernels do not apply - same kernel, same counters)
+        assert pk[3]["node_visits"] < sr[3]["node_visits"] if acc == rt.LBVH else pk[3]["node_visits"] <= sr[3]["node_visits"]
+        rgb_o, hit_o, accum_o, _ = oracle.render_rows(sph, mat, nodes, order, W, H, spp, tie_by_objid=1 if acc == rt.LBVH else 0,
+                                                       lights=LIGHTS3, want_accum=True, shadows=shadows)
+        assert np.array_equal(pk[1], hit_o) and pk[2].tobytes() == accum_o.tobytes() and np.array_equal(pk[0], rgb_o)
+        assert tuple(int(x) for x in oracle.last_ray_counts) == (pk[3]["rays"], pk[3]["shadow_rays"], pk[3]["secondary_rays"])
+    finally:
+        gpu_ctx.set_lights(np.asarray([[0, 3, 30, 10, 1, 1, 1]], np.float32))

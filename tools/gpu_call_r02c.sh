@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_render.py tests/test_gpu_shared_frame.py tests/test_gpu_host_main.py tests/test_gpu_bench_parity.py tests/test_gpu_triangles.py -q -m gpu > gpurun_out/r02c_pytest.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_render.py tests/test_gpu_shared_frame.py tests/test_gpu_host_main.py tests/test_gpu_bench_parity.py tests/test_gpu_triangles.py tests/test_gpu_materials.py tests/test_gpu_errors_edges.py -q -m gpu > gpurun_out/r02c_pytest.log 2>&1
 tail -15 gpurun_out/r02c_pytest.log
 mkdir -p /tmp/cold/models && python - <<'PY'
 import numpy as np
