@@ -13,7 +13,7 @@ static thread_local char g_err[1024] = "";
 const RtdsOptionName g_rtds_option_names[] = {
     {"block_order", "RTDS_BLOCK_ORDER", &RtdsOptions::block_order}, {"strip", "RTDS_STRIP", &RtdsOptions::strip},
     {"bands", "RTDS_BANDS", &RtdsOptions::bands}, {"band_ratio", "RTDS_BAND_RATIO", &RtdsOptions::band_ratio},
-    {"packet", "RTDS_PACKET", &RtdsOptions::packet}, {"hull", "RTDS_HULL", &RtdsOptions::hull}, {"dyn", "RTDS_DYN", &RtdsOptions::dyn},
+    {"packet", "RTDS_PACKET", &RtdsOptions::packet}, {"hull", "RTDS_HULL", &RtdsOptions::hull},
     {"zerocopy", "RTDS_ZEROCOPY", &RtdsOptions::zerocopy}, {"trace_frame", "RTDS_TRACE_FRAME", &RtdsOptions::trace_frame},
     {"median_small", "RTDS_MEDIAN_SMALL", &RtdsOptions::median_small}, {"median_coop", "RTDS_MEDIAN_COOP", &RtdsOptions::median_coop},
     {"median_debug", "RTDS_MEDIAN_DEBUG", &RtdsOptions::median_debug}, {"node_preorder", "RTDS_NODE_PREORDER", &RtdsOptions::node_preorder},
@@ -168,7 +168,7 @@ static int create_resources(rtds_ctx* c)
     RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_pf1, cudaEventDisableTiming));
     RTDS_CUDA(cudaEventCreate(&c->ev0)); RTDS_CUDA(cudaEventCreate(&c->ev1));
     RTDS_CUDA(cudaEventCreate(&c->ev2)); RTDS_CUDA(cudaEventCreate(&c->ev3));
-    RTDS_CUDA(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 16));      // [0..7] render counters, [8..15] tile queue heads
+    RTDS_CUDA(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8));
     RTDS_CUDA(cudaMallocHost(&c->h_counters, sizeof(unsigned long long) * 16));    // [8..15]: material flag read-back
     // main.cpp:775: Sphere light2(0, (0,3,30), 10, (1,1,1), 0, 0, emission (1,1,1))
     c->n_lights = 1;

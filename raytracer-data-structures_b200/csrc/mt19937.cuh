@@ -178,59 +178,62 @@ __global__ void __launch_bounds__(MT_THREADS) mt_expand_dirs_kernel(const uint32
 {
     __shared__ __align__(16) uint32_t words[(MT_SNAP_EVERY + 1) * MT_N];      // slice 0 = the snapshot
     const int t = threadIdx.x;
-    // world == 1: block b = chunk s0 + b. world > 1: the grid covers only the rank's OWN scanline tiles (chunks_per_tile blocks
-    // per owned tile). A chunk that straddles a tile boundary is regenerated by a block of each tile it touches, and every block
-    // stores only the samples of ITS tile [lo, hi) - no direction is written twice, also when a tile is shorter than a chunk.
-    unsigned long long chunk = (unsigned long long)s0 + blockIdx.x;
-    long long lo = 0, hi = (long long)n_samples;      // frame samples this block may write
-    if (own.world > 1) {
-        const unsigned k = blockIdx.x / (unsigned)chunks_per_tile, c = blockIdx.x - k * (unsigned)chunks_per_tile;
-        const unsigned long long tile = (unsigned long long)own.rank + (unsigned long long)k * own.world;
-        const unsigned long long row0 = tile * own.tile_rows;
-        if (row0 >= (unsigned long long)own.height) return;
-        const unsigned long long row1 = min(row0 + own.tile_rows, (unsigned long long)own.height);
-        const unsigned long long w0 = own.first_word + row0 * own.row_words, w1 = own.first_word + row1 * own.row_words - 1;
-        chunk = w0 / (MT_SNAP_EVERY * MT_N) + c;
-        if (chunk > w1 / (MT_SNAP_EVERY * MT_N)) return;
-        lo = (long long)(row0 * (own.row_words / 4));
-        hi = (long long)(row1 * (own.row_words / 4));
-    }
-    const unsigned long long wlo = chunk * MT_SNAP_EVERY * MT_N;
-    const uint32_t* src = snap + (size_t)chunk * MT_N;
-    for (int i = t; i < MT_N; i += MT_THREADS) words[i] = src[i];
-    __syncthreads();
-    for (int r = 0; r < MT_SNAP_EVERY; ++r) mt_regen(words + r * MT_N, words + (r + 1) * MT_N);
-    // all threads, no barriers: temper, canonical doubles, direction, normalise, store
-    const unsigned long long as0 = wlo / 4;           // absolute stream sample of the chunk's first four words
-    const uint4* w4 = reinterpret_cast<const uint4*>(words + MT_N);
-    constexpr int CHUNK_SAMPLES = MT_SNAP_EVERY * MT_N / 4;
-    // frame sample of the chunk's first stream sample; chunks that lie wholly inside the frame (all but the first and the
-    // last) need no 64-bit range check per sample, and when aa_samples divides the thread stride the pixel coordinates
-    // advance by additions instead of two divisions per sample
-    const long long rel = (long long)as0 - (long long)first_sample;
-    const bool inside = rel >= lo && rel + CHUNK_SAMPLES <= hi;
-    const bool stepping = inside && (MT_THREADS % spp) == 0;
-    const unsigned step_px = stepping ? (unsigned)(MT_THREADS / spp) : 0u;
-    unsigned px = 0, py = 0;
-    if (stepping) {
-        const unsigned pix = fast_div((unsigned)rel + (unsigned)t, div_spp);
-        py = fast_div(pix, div_width); px = pix - py * (unsigned)width;
-    }
-    for (int i = t; i < CHUNK_SAMPLES; i += MT_THREADS) {
-        const long long gl = rel + i;
-        if (inside || (gl >= lo && gl < hi)) {
-            const unsigned g = (unsigned)gl;
-            if (!stepping) {
-                const unsigned pix = fast_div(g, div_spp);
-                py = fast_div(pix, div_width); px = pix - py * (unsigned)width;
+    {
+        const unsigned vb = blockIdx.x;
+        // world == 1: block b = chunk s0 + b. world > 1: the grid covers only the rank's OWN scanline tiles (chunks_per_tile
+        // blocks per owned tile). A chunk that straddles a tile boundary is regenerated by a block of each tile it touches, and every
+        // block stores only the samples of ITS tile [lo, hi) - no direction is written twice, also when a tile is shorter than a chunk.
+        unsigned long long chunk = (unsigned long long)s0 + vb;
+        long long lo = 0, hi = (long long)n_samples;      // frame samples this block may write
+        if (own.world > 1) {
+            const unsigned k = vb / (unsigned)chunks_per_tile, c = vb - k * (unsigned)chunks_per_tile;
+            const unsigned long long tile = (unsigned long long)own.rank + (unsigned long long)k * own.world;
+            const unsigned long long row0 = tile * own.tile_rows;
+            if (row0 >= (unsigned long long)own.height) return;
+            const unsigned long long row1 = min(row0 + own.tile_rows, (unsigned long long)own.height);
+            const unsigned long long w0 = own.first_word + row0 * own.row_words, w1 = own.first_word + row1 * own.row_words - 1;
+            chunk = w0 / (MT_SNAP_EVERY * MT_N) + c;
+            if (chunk > w1 / (MT_SNAP_EVERY * MT_N)) return;
+            lo = (long long)(row0 * (own.row_words / 4));
+            hi = (long long)(row1 * (own.row_words / 4));
+        }
+        const unsigned long long wlo = chunk * MT_SNAP_EVERY * MT_N;
+        const uint32_t* src = snap + (size_t)chunk * MT_N;
+        for (int i = t; i < MT_N; i += MT_THREADS) words[i] = src[i];
+        __syncthreads();
+        for (int r = 0; r < MT_SNAP_EVERY; ++r) mt_regen(words + r * MT_N, words + (r + 1) * MT_N);
+        // all threads, no barriers: temper, canonical doubles, direction, normalise, store
+        const unsigned long long as0 = wlo / 4;           // absolute stream sample of the chunk's first four words
+        const uint4* w4 = reinterpret_cast<const uint4*>(words + MT_N);
+        constexpr int CHUNK_SAMPLES = MT_SNAP_EVERY * MT_N / 4;
+        // frame sample of the chunk's first stream sample; chunks that lie wholly inside the frame (all but the first and the
+        // last) need no 64-bit range check per sample, and when aa_samples divides the thread stride the pixel coordinates
+        // advance by additions instead of two divisions per sample
+        const long long rel = (long long)as0 - (long long)first_sample;
+        const bool inside = rel >= lo && rel + CHUNK_SAMPLES <= hi;
+        const bool stepping = inside && (MT_THREADS % spp) == 0;
+        const unsigned step_px = stepping ? (unsigned)(MT_THREADS / spp) : 0u;
+        unsigned px = 0, py = 0;
+        if (stepping) {
+            const unsigned pix = fast_div((unsigned)rel + (unsigned)t, div_spp);
+            py = fast_div(pix, div_width); px = pix - py * (unsigned)width;
+        }
+        for (int i = t; i < CHUNK_SAMPLES; i += MT_THREADS) {
+            const long long gl = rel + i;
+            if (inside || (gl >= lo && gl < hi)) {
+                const unsigned g = (unsigned)gl;
+                if (!stepping) {
+                    const unsigned pix = fast_div(g, div_spp);
+                    py = fast_div(pix, div_width); px = pix - py * (unsigned)width;
+                }
+                const uint4 w = w4[i];
+                const uint4 jw = make_uint4(mt_temper(w.x), mt_temper(w.y), mt_temper(w.z), mt_temper(w.w));
+                float dx, dy, dz;
+                primary_dir(jw, (int)px, (int)py, G, dx, dy, dz);
+                float* o = dirs + 3 * (size_t)g;
+                o[0] = dx; o[1] = dy; o[2] = dz;
+                if (stepping) { px += step_px; while (px >= (unsigned)width) { px -= (unsigned)width; ++py; } }
             }
-            const uint4 w = w4[i];
-            const uint4 jw = make_uint4(mt_temper(w.x), mt_temper(w.y), mt_temper(w.z), mt_temper(w.w));
-            float dx, dy, dz;
-            primary_dir(jw, (int)px, (int)py, G, dx, dy, dz);
-            float* o = dirs + 3 * (size_t)g;
-            o[0] = dx; o[1] = dy; o[2] = dz;
-            if (stepping) { px += step_px; while (px >= (unsigned)width) { px -= (unsigned)width; ++py; } }
         }
     }
 }

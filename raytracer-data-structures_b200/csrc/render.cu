@@ -99,7 +99,6 @@ struct RenderArgs {
     int*     out_hit;            // optional, local rows x width
     float*   out_accum;          // optional, local rows x width x 3
     unsigned long long* counters;
-    unsigned long long* queue;   // render_dyn_kernel: head of this launch's tile queue (zeroed with the counters)
 };
 
 // Frame-buffer write of a warp's 8 x 4 pixels. The warp's RGB8 values are staged in shared memory and leave as 12
@@ -142,6 +141,19 @@ __device__ __forceinline__ void store_warp_rgb(const RenderArgs& A, int px, int 
 __device__ __forceinline__ void quadrant_block(int b, int nbx, int nby, int& bx, int& by, int order)
 {
     if (order == 1) { bx = b % nbx; by = b / nbx; return; }       // plain row-major (experiment)
+    if (order == 3) {
+        // block rows from the image centre outwards, alternating below / above, full width: the rows that usually hold the
+        // model - and with it the few blocks that run 10-20x longer than the median - all start in the first wave. For the short
+        // per-rank kernels of a multi-GPU frame the kernel's length is "start of the slowest block + its duration" (measured:
+        // tools/block_timeline.py), and quadrant after quadrant starts the lower half 55 us late.
+        const int r = b / nbx, hy = nby >> 1;
+        bx = b - r * nbx;
+        int k = (r & 1) ? hy - 1 - (r >> 1) : hy + (r >> 1);      // hy, hy-1, hy+1, hy-2, ...
+        if (k < 0) k = r;                                         // the shorter side is used up: the rest in order
+        else if (k >= nby) k = nby - 1 - r;
+        by = k;
+        return;
+    }
     const int hx = nbx >> 1, hy = nby >> 1, wx = nbx - hx;
     const int n0 = hx * hy, n1 = wx * hy, n2 = hx * (nby - hy);
     // order 2: inside the two upper quadrants the block rows run from the image centre UP, so every quadrant starts at
@@ -362,12 +374,19 @@ static __device__ __noinline__ ShadedRay shade_packet_ray_ool(const RenderArgs* 
 struct MatResult { float r, g, b; unsigned node_tests, prim_tests, node_visits, rays, shadow_rays, secondary_rays; };
 static __device__ __noinline__ MatResult cast_material_cold(const RenderArgs* A, float dx, float dy, float dz, float tnear, int hit_obj, int hit_leaf);
 
+#ifdef RTDS_BLOCK_TIMING     // profiling variant (tools/block_timeline.py): start / end / SM of every block of the packet kernel
+__device__ unsigned long long g_block_times[3 * 70000];
+#endif
 template <bool SHADOWS /*evaluate the shadow query (extension; the reference's trace_more is a stub)*/,
           bool HULL /*interior boxes tested once per packet against the hull of the four reciprocal directions*/,
           bool MATERIALS = false /*the scene holds REFLECTION_AND_REFRACTION / REFLECTION primitives: rays that hit one continue
                                    through castRay's material branches (single rays, out of line); diffuse hits are shaded as always*/>
 __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const __grid_constant__ RenderArgs A)
 {
+#ifdef RTDS_BLOCK_TIMING
+    unsigned long long bt0 = 0;
+    if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(bt0));
+#endif
     unsigned shadow_rays = 0, secondary_rays = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int bx, by;
@@ -425,228 +444,18 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
         if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
     }
     store_warp_rgb(A, px, lrow, active, r8, g8, b8);
+#ifdef RTDS_BLOCK_TIMING
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x < 70000) {
+        unsigned long long bt1; unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(bt1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_block_times[3 * blockIdx.x] = bt0; g_block_times[3 * blockIdx.x + 1] = bt1; g_block_times[3 * blockIdx.x + 2] = ((unsigned long long)smid << 32) | cnt.node_visits;
+    }
+#endif
     unsigned v[6] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays, shadow_rays, secondary_rays};
 #pragma unroll
     for (int c = 0; c < (MATERIALS ? 6 : (SHADOWS ? 5 : 4)); ++c) {
-        unsigned long long x = v[c];
-        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0 && x) atomicAdd(&A.counters[c], x);
-    }
-}
-
-// ===================================================================================================
-// K10, dynamic form (the 1-spp configs and every aa_samples the sample packets do not serve): PERSISTENT warps pull 16 x 8-pixel
-// tiles from a queue (one atomic per tile), and inside a tile the 32 lanes pull PIXELS: a lane whose pixel is done takes the
-// tile's next unassigned pixel while the other lanes keep traversing. Why: with one ray per pixel the single-ray kernel ran
-// with 11 of 32 lanes active per warp instruction on the 7 M-sphere scene and 24.6 % achieved occupancy (ncu, profiles/
-// ncu_r02a_config4_render_kernel.md) - sky and ground rays end after two or three visits and their lanes then idle until the
-// warp's longest ray is through, and whole blocks retire only when their slowest warp does. Here a warp alternates between
-// (a) at most DYN_STEPS traversal steps for every lane that holds a ray and (b) a reconverged phase in which finished rays are
-// shaded together and idle lanes are refilled from the tile (ballot + popc). The per-ray algorithm is traverse_fast_loop's,
-// step for step (same conservative interior test, same leaf test, same pruning), the samples of a pixel stay on one lane in
-// sample order (main.cpp:553-560): hit ids, float sums and bytes are unchanged (parity tests run both kernels).
-// ===================================================================================================
-constexpr int DYN_TW = 16, DYN_TH = 8, DYN_PIX = DYN_TW * DYN_TH;
-#ifndef RTDS_DYN_STEPS
-#define RTDS_DYN_STEPS 8
-#endif
-#ifndef RTDS_DYN_MINB
-#define RTDS_DYN_MINB 6
-#endif
-
-template <int OCT /*4..7: every ray of the tile has this direction octant; -1: mixed*/>
-__device__ __forceinline__ void dyn_tile(const RenderArgs& A, const int px0, const int lrow0, const float margin, Counters& cnt,
-                                         unsigned char (*rgb)[DYN_TW * 3])
-{
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const BvhView& B = A.bvh;
-    const float neg_margin = -margin;
-    int next = 0;                                    // warp-uniform: the tile's next unassigned pixel
-    bool has_pixel = false, ray_on = false, ray_done = false;
-    int tpx = 0, trow = 0, k = 0, last_hit = -1;     // the lane's pixel inside the tile, its current sample
-    size_t pix = 0;
-    float acc_r = 0, acc_g = 0, acc_b = 0;
-    float dx = 0, dy = 0, dz = -1, ix = 0, iy = 0, iz = 0, tnear = INFINITY, tlim = 0;
-    int best_key = 0, best_leaf = -1, node = 0, sp = 0;
-    unsigned visits = 0;
-    int2 stack[STACK_MAX];
-    for (;;) {
-        // (a) rays that ended in the last round: shade, accumulate in sample order, next sample or pixel done
-        if (ray_done) {
-            const ShadedRay sh = shade_packet_ray_ool(&A, dx, dy, dz, tnear, best_leaf);
-            acc_r += sh.r; acc_g += sh.g; acc_b += sh.b;
-            last_hit = sh.hit;
-            ray_done = false;
-            if (++k == A.spp) {
-                const float fs = (float)(unsigned)A.spp;
-                unsigned char* t = &rgb[trow][3 * tpx];
-                t[0] = (unsigned char)(fminf(1.0f, acc_r / fs) * 255);
-                t[1] = (unsigned char)(fminf(1.0f, acc_g / fs) * 255);
-                t[2] = (unsigned char)(fminf(1.0f, acc_b / fs) * 255);
-                const size_t o = (size_t)(lrow0 + trow) * A.width + (px0 + tpx);
-                if (A.out_hit) A.out_hit[o] = last_hit;
-                if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
-                has_pixel = false;
-            }
-        }
-        // (b) idle lanes take the tile's next pixels
-        const unsigned idle = __ballot_sync(FULL, !has_pixel);
-        if (idle != 0u && next < DYN_PIX) {
-            const int mine = next + __popc(idle & ((1u << lane) - 1u));
-            if (!has_pixel && mine < DYN_PIX) {
-                tpx = mine & (DYN_TW - 1); trow = mine >> 4;
-                if (px0 + tpx < A.width && lrow0 + trow < A.local_rows) {
-                    has_pixel = true; k = 0; acc_r = acc_g = acc_b = 0.f;
-                    pix = (size_t)global_row_of(A, lrow0 + trow) * A.width + (px0 + tpx);
-                }
-            }
-            next += __popc(idle);
-        }
-        if (!__any_sync(FULL, has_pixel)) {
-            if (next >= DYN_PIX) break;
-            continue;
-        }
-        // (c) lanes without a ray start their pixel's next sample
-        if (has_pixel && !ray_on) {
-            const float* dp = A.dirs + 3 * (pix * A.spp + k);      // main.cpp:554-557, computed by mt_expand_dirs_kernel
-            dx = __ldg(dp); dy = __ldg(dp + 1); dz = __ldg(dp + 2);
-            cnt.rays++;
-            tnear = INFINITY; best_key = 0; best_leaf = -1;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"(dx));
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(dy));
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(dz));
-            const float amin = fminf(fminf(fabsf(ix), fabsf(iy)), fabsf(iz)), amax = fmaxf(fmaxf(fabsf(ix), fabsf(iy)), fabsf(iz));
-            const int oct = (dx < 0 ? 1 : 0) | (dy < 0 ? 2 : 0) | 4;
-            if (B.root_ref < 0 || !(amin > 1e-30f && amax < 1e30f) || (OCT >= 0 && oct != OCT)) {
-                // single-leaf tree, degenerate direction, or (never for a tile classified by its corners) another octant:
-                // the out-of-line single-ray traversal, finished at once
-                const ColdHit h = trace_primary_cold(&B, dx, dy, dz);
-                tnear = h.tnear; best_leaf = h.leaf;
-                cnt.node_tests += h.node_tests; cnt.prim_tests += h.prim_tests; cnt.node_visits += h.node_visits;
-                ray_done = true;
-            } else {
-                tlim = tnear + margin;               // +inf
-                node = 0; sp = 0;
-                ray_on = true;
-            }
-        }
-        // (d) at most RTDS_DYN_STEPS traversal steps per lane (traverse_fast_loop<true, false, OCT>, one iteration per step)
-        if (ray_on) {
-#pragma unroll 1
-            for (int it = 0; it < RTDS_DYN_STEPS; ++it) {
-                if (node >= 0) {
-                    const float4* q = reinterpret_cast<const float4*>(B.nodes + node);
-                    const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-                    const int2 ch = __ldg(reinterpret_cast<const int2*>(q + 3));
-                    ++visits;
-                    float tminL, tmaxL, tminR, tmaxR;
-                    slab_interval<OCT>(q0.x * ix, q0.y * iy, q0.z * iz, q0.w * ix, q1.x * iy, q1.y * iz, tminL, tmaxL);
-                    slab_interval<OCT>(q1.z * ix, q1.w * iy, q2.x * iz, q2.y * ix, q2.z * iy, q2.w * iz, tminR, tmaxR);
-                    tmaxL = __fmaf_rn(fabsf(tmaxL), WIDE2, tmaxL);
-                    tmaxR = __fmaf_rn(fabsf(tmaxR), WIDE2, tmaxR);
-                    const bool hitL = tminL <= fminf(tmaxL, tlim) && tmaxL >= neg_margin;
-                    const bool hitR = tminR <= fminf(tmaxR, tlim) && tmaxR >= neg_margin;
-                    if (hitL && hitR) {
-                        const bool rfirst = tminR < tminL;
-                        stack[sp] = make_int2(rfirst ? ch.x : ch.y, __float_as_int(rfirst ? tminL : tminR));
-                        sp = min(sp + 1, STACK_MAX - 1);
-                        node = rfirst ? ch.y : ch.x;
-                        continue;
-                    }
-                    if (hitL | hitR) { node = hitL ? ch.x : ch.y; continue; }
-                } else {
-                    const int leaf = ~node;
-                    const float4 s = __ldg(B.leaf_sph + leaf);
-                    const float bx0 = s.x - s.w, by0 = s.y - s.w, bz0 = s.z - s.w, bx1 = s.x + s.w, by1 = s.y + s.w, bz1 = s.z + s.w;
-                    float tmn, tmx;
-                    slab_interval<OCT>(bx0 * ix, by0 * iy, bz0 * iz, bx1 * ix, by1 * iy, bz1 * iz, tmn, tmx);
-                    bool pass = __fmaf_rn(fabsf(tmn), NARROW_EPS, tmn) <= __fmaf_rn(-fabsf(tmx), NARROW_EPS, tmx) &&
-                                fminf(fabsf(tmn), fabsf(tmx)) > 1e-30f;
-                    if (!pass) pass = slab_test_cold(0.f, 0.f, 0.f, dx, dy, dz, bx0, by0, bz0, bx1, by1, bz1);
-                    if (pass) {
-                        float t0, t1;
-                        cnt.prim_tests++;
-                        if (sphere_test(0.f, 0.f, 0.f, dx, dy, dz, make_float4(s.x, s.y, s.z, s.w * s.w), t0, t1)) {
-                            candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
-                            tlim = tnear + margin;
-                            tlim = __fmaf_rn(fabsf(tlim), WIDE2, tlim);
-                        }
-                    }
-                }
-                // pop
-                bool found = false;
-                while (sp > 0) {
-                    --sp;
-                    const int2 e = stack[sp];
-                    if (__int_as_float(e.y) > tlim) continue;
-                    node = e.x;
-                    found = true;
-                    break;
-                }
-                if (!found) { ray_on = false; ray_done = true; break; }
-            }
-        }
-        __syncwarp();
-    }
-    cnt.node_visits += visits;
-    cnt.node_tests += 2 * visits;
-}
-
-__global__ void __launch_bounds__(128, RTDS_DYN_MINB) render_dyn_kernel(const __grid_constant__ RenderArgs A)
-{
-    __shared__ __align__(16) unsigned char tile_rgb[4][DYN_TH][DYN_TW * 3];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nbx = (A.width + DYN_TW - 1) / DYN_TW, nby = (A.local_rows - A.lrow0 + DYN_TH - 1) / DYN_TH;
-    const unsigned n_tiles = (unsigned)nbx * (unsigned)nby;
-    const float margin = prune_margin(A.bvh.root_box, 0.f, 0.f, 0.f);
-    Counters cnt = {0, 0, 0, 0};
-    for (;;) {
-        unsigned tile = 0;
-        if (lane == 0) tile = (unsigned)atomicAdd(A.queue, 1ull);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= n_tiles) break;
-        int bx, by;
-        quadrant_block((int)tile, nbx, nby, bx, by, A.block_order);
-        const int px0 = bx * DYN_TW, lrow0 = A.lrow0 + by * DYN_TH;
-        // the tile's direction octant from its corner pixels: dx < 0 left of the image centre, dy < 0 below it (main.cpp:554-555:
-        // the jitter keeps a sample inside its pixel); a tile that touches a centre line is traversed without octant knowledge,
-        // and a ray whose octant is not the tile's takes the single-ray function
-        const int x_lo = px0, x_hi = min(px0 + DYN_TW, A.width) - 1;
-        const int y_lo = global_row_of(A, lrow0), y_hi = global_row_of(A, min(lrow0 + DYN_TH, A.local_rows) - 1);
-        const int sx = 2 * x_hi + 2 <= A.width ? 1 : (2 * x_lo >= A.width ? 0 : -1);        // 1: dx < 0 for the whole tile
-        const int sy = 2 * y_lo >= A.height ? 1 : (2 * y_hi + 2 <= A.height ? 0 : -1);      // 1: dy < 0 for the whole tile
-        unsigned char (*rgb)[DYN_TW * 3] = tile_rgb[warp];
-        if (sx < 0 || sy < 0) dyn_tile<-1>(A, px0, lrow0, margin, cnt, rgb);
-        else switch (sx | (sy << 1)) {
-            case 0: dyn_tile<4>(A, px0, lrow0, margin, cnt, rgb); break;
-            case 1: dyn_tile<5>(A, px0, lrow0, margin, cnt, rgb); break;
-            case 2: dyn_tile<6>(A, px0, lrow0, margin, cnt, rgb); break;
-            default: dyn_tile<7>(A, px0, lrow0, margin, cnt, rgb); break;
-        }
-        __syncwarp();
-        // the tile's RGB8 leaves as aligned 8-byte words (48 per full tile: 8 rows x 48 bytes), or byte by byte at ragged edges
-        const bool fast = A.out_vec8 && px0 + DYN_TW <= A.width && lrow0 + DYN_TH <= A.local_rows;
-        if (fast) {
-            for (int w = lane; w < DYN_TH * 6; w += 32) {
-                const int row = w / 6, seg = w - 6 * row;
-                const int orow = A.out_global_rows ? global_row_of(A, lrow0 + row) : lrow0 + row;
-                *reinterpret_cast<uint2*>(A.out_rgb + ((size_t)orow * A.width + px0) * 3 + 8 * seg) = *reinterpret_cast<const uint2*>(&rgb[row][8 * seg]);
-            }
-        } else {
-            for (int i = lane; i < DYN_PIX; i += 32) {
-                const int tpx = i & (DYN_TW - 1), trow = i >> 4;
-                if (px0 + tpx < A.width && lrow0 + trow < A.local_rows) {
-                    const size_t o = (size_t)(A.out_global_rows ? global_row_of(A, lrow0 + trow) : lrow0 + trow) * A.width + (px0 + tpx);
-                    A.out_rgb[3 * o] = rgb[trow][3 * tpx]; A.out_rgb[3 * o + 1] = rgb[trow][3 * tpx + 1]; A.out_rgb[3 * o + 2] = rgb[trow][3 * tpx + 2];
-                }
-            }
-        }
-        __syncwarp();
-    }
-    unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
         unsigned long long x = v[c];
         for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0 && x) atomicAdd(&A.counters[c], x);
@@ -1131,6 +940,10 @@ struct DirsLaunch {
 static int dirs_plan(rtds_ctx* ctx, uint64_t first_sample, int W, int H, int spp, const RayGen& G, const JitterOwner& own, int* launches,
                      DirsLaunch& L)
 {
+    float*& buf = ctx->d_dirs;
+    size_t& cap = ctx->dirs_cap_floats;
+    uint64_t* key = ctx->dirs_key;
+    bool& valid = ctx->dirs_valid;
     const uint64_t n_samples = (uint64_t)W * H * spp;
     if (n_samples >= (1ull << 32)) { rtds_set_error("render: width*height*aa_samples must be below 2^32"); return RTDS_ERR_INVALID; }
     const uint64_t words_per_snap = (uint64_t)MT_SNAP_EVERY * MT_N;
@@ -1138,11 +951,11 @@ static int dirs_plan(rtds_ctx* ctx, uint64_t first_sample, int W, int H, int spp
     const uint64_t s0 = first_word / words_per_snap, s1 = (first_word + n_words - 1) / words_per_snap;
     if (s1 + 2 >= (1ull << 31)) { rtds_set_error("jitter stream position too large"); return RTDS_ERR_INVALID; }
     RTDS_TRY(ensure_snapshots(ctx, (int)(s1 + 1), launches));
-    if (ctx->dirs_cap_floats < 3 * n_samples) {
-        if (ctx->d_dirs) cudaFree(ctx->d_dirs);
-        ctx->d_dirs = nullptr; ctx->dirs_cap_floats = 0;
-        RTDS_CUDA(cudaMalloc(&ctx->d_dirs, sizeof(float) * 3 * n_samples));
-        ctx->dirs_cap_floats = 3 * n_samples;
+    if (cap < 3 * n_samples) {
+        if (buf) cudaFree(buf);
+        buf = nullptr; cap = 0;
+        RTDS_CUDA(cudaMalloc(&buf, sizeof(float) * 3 * n_samples));
+        cap = 3 * n_samples;
     }
     auto make_div = [](uint32_t d) {
         FastDiv f{0u, 0u};
@@ -1168,14 +981,14 @@ static int dirs_plan(rtds_ctx* ctx, uint64_t first_sample, int W, int H, int spp
         const int owned = own.rank < n_tiles ? (n_tiles - own.rank + own.world - 1) / own.world : 0;
         grid = (unsigned)owned * (unsigned)chunks_per_tile;
     }
-    L.grid = grid; L.snap = ctx->d_mt_snap; L.s0 = (int)s0; L.dirs = ctx->d_dirs; L.first_sample = first_sample; L.n_samples = (unsigned)n_samples;
+    L.grid = grid; L.snap = ctx->d_mt_snap; L.s0 = (int)s0; L.dirs = buf; L.first_sample = first_sample; L.n_samples = (unsigned)n_samples;
     L.width = W; L.spp = spp; L.div_spp = make_div((uint32_t)spp); L.div_width = make_div((uint32_t)W); L.G = G; L.own = own;
     L.chunks_per_tile = chunks_per_tile;
     L.bind();
-    ctx->dirs_key[0] = first_sample; ctx->dirs_key[1] = (uint64_t)W; ctx->dirs_key[2] = (uint64_t)H; ctx->dirs_key[3] = (uint64_t)spp;
-    ctx->dirs_key[4] = ((uint64_t)__float_as_uint_host(G.angle) << 32) | __float_as_uint_host(G.aspect);
-    ctx->dirs_key[5] = ((uint64_t)(unsigned)own.rank << 40) | ((uint64_t)(unsigned)own.world << 20) | (uint64_t)(unsigned)own.tile_rows;
-    ctx->dirs_valid = true;
+    key[0] = first_sample; key[1] = (uint64_t)W; key[2] = (uint64_t)H; key[3] = (uint64_t)spp;
+    key[4] = ((uint64_t)__float_as_uint_host(G.angle) << 32) | __float_as_uint_host(G.aspect);
+    key[5] = ((uint64_t)(unsigned)own.rank << 40) | ((uint64_t)(unsigned)own.world << 20) | (uint64_t)(unsigned)own.tile_rows;
+    valid = true;
     return RTDS_OK;
 }
 
@@ -1334,7 +1147,7 @@ static int render_frame_graph(rtds_ctx* ctx, const RenderArgs& A, const void* fn
         cudaGraphNode_t n_ev0, n_zero, n_ev2, n_ev3, n_ev1, n_copy;
         RTDS_CUDA(cudaGraphAddEventRecordNode(&n_ev0, g.graph, nullptr, 0, ctx->ev0));
         cudaMemsetParams mp = {};
-        mp.dst = ctx->d_counters; mp.value = 0; mp.elementSize = 4; mp.width = 32; mp.height = 1; mp.pitch = 0;      // counters + tile queues
+        mp.dst = ctx->d_counters; mp.value = 0; mp.elementSize = 4; mp.width = 16; mp.height = 1; mp.pitch = 0;
         RTDS_CUDA(cudaGraphAddMemsetNode(&n_zero, g.graph, &n_ev0, 1, &mp));
         std::vector<cudaGraphNode_t> pre{n_zero};
         if (has_dirs) {
@@ -1421,17 +1234,10 @@ static int render_stats_out(rtds_ctx* ctx, rtds_render_stats* st, int launches, 
     return RTDS_OK;
 }
 
-// grid of a render kernel over `rows` local rows: one block per 16 x 8 pixels, or - render_dyn_kernel - a persistent grid
-static unsigned render_grid(rtds_ctx* ctx, const void* fn, int W, int rows)
+// grid of a render kernel over `rows` local rows: one block per 16 x 8 pixels, quadrant-major linear order
+static unsigned render_grid(rtds_ctx*, const void*, int W, int rows)
 {
-    const unsigned lin = (unsigned)((W + 15) / 16) * (unsigned)((rows + 7) / 8);     // quadrant-major linear grid of 16 x 8-pixel tiles
-    if (fn != (const void*)render_dyn_kernel) return lin;
-    if (ctx->dyn_blocks_per_sm <= 0) {
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_dyn_kernel, 128, 0) != cudaSuccess || per_sm <= 0) per_sm = RTDS_DYN_MINB;
-        ctx->dyn_blocks_per_sm = per_sm;
-    }
-    return std::max(1u, std::min((lin + 3) / 4, (unsigned)(ctx->sm_count * ctx->dyn_blocks_per_sm)));      // a warp per tile, 4 warps per block
+    return (unsigned)((W + 15) / 16) * (unsigned)((rows + 7) / 8);
 }
 
 // Which render kernel serves this frame (all take one RenderArgs; grid = quadrant-major linear grid of 16 x 8-pixel blocks).
@@ -1447,10 +1253,12 @@ static const void* select_render_kernel(const rtds_ctx* ctx, const RenderArgs& A
     // to hide latency with (negative results). Removed again.
     bool packet = !kdt && !brute && !p->exact && A.spp % PK == 0 && A.bvh.leaf_box_prim && A.shade.max_depth >= 1;
     packet = packet && ctx->opt.packet != 0;
-    // scenes with REFLECTION_AND_REFRACTION / REFLECTION primitives: the primary rays still go as packets, a ray that hits such a
-    // primitive continues through castRay's material branches on its own (config 5: 108 -> see DESIGN.md)
-    if (packet && ctx->has_materials)
-        return p->shadows ? (const void*)render_packet_kernel<true, true, true> : (const void*)render_packet_kernel<false, true, true>;
+    // scenes with REFLECTION_AND_REFRACTION / REFLECTION primitives, no shadow rays: the primary rays still go as packets, a ray
+    // that hits such a primitive continues through castRay's material branches on its own. WITH shadow rays the single-ray castRay
+    // kernel stays (measured on config 5, 3 shadowed lights, 16 spp: packets 115.9 ms vs 109.7 ms - the shadow rays are 2/3 of
+    // the rays there and stay single either way, and the out-of-line shading costs more than the shared primary visits save)
+    if (packet && ctx->has_materials && !p->shadows) return (const void*)render_packet_kernel<false, true, true>;
+    if (ctx->has_materials) packet = false;
     // interior boxes tested once per packet against the hull of the four reciprocal directions (default; hull option 0:
     // once per ray). Bench frame: same frame, node visits 3.17 -> 3.18 per ray, kernel 1.16 -> 0.99 ms.
     const bool hull = ctx->opt.hull != 0;
@@ -1459,10 +1267,6 @@ static const void* select_render_kernel(const rtds_ctx* ctx, const RenderArgs& A
         if (brute) return (const void*)render_full_kernel<2>;
         return p->exact ? (const void*)render_full_kernel<0> : (const void*)render_full_kernel<1>;
     }
-    // persistent warps with dynamic pixel fetch for everything the sample packets do not serve (dyn option: 0 off, 1 default,
-    // 2 also instead of the sample packets)
-    const bool dyn_ok = !full && !kdt && !brute && !p->exact && A.bvh.leaf_box_prim && A.bvh.prim_type == 0 && A.bvh.root_ref >= 0;
-    if (dyn_ok && (ctx->opt.dyn >= 2 || (ctx->opt.dyn == 1 && !packet))) return (const void*)render_dyn_kernel;
     if (packet) return hull ? (const void*)render_packet_kernel<false, true> : (const void*)render_packet_kernel<false, false>;
     if (kd_closest) return (const void*)render_kernel<4>;
     if (kdt) return (const void*)render_kernel<3>;
@@ -1508,7 +1312,6 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.out_vec8 = (((uintptr_t)d_rgb_rows & 7) == 0 && W % 8 == 0) ? 1 : 0;
     A.block_order = ctx->opt.block_order;
     A.counters = ctx->d_counters;
-    A.queue = ctx->d_counters + 8;
 
     cudaStream_t s = ctx->stream;
     int launches = 0;
@@ -1572,13 +1375,12 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     if (graph_path) {
         const void* fn = select_render_kernel(ctx, A, p, full, kdt, brute, kd_closest);
         const unsigned lin = render_grid(ctx, fn, W, A.local_rows);
-        A.queue = ctx->d_counters + 8;
         const bool shared = global_rows && ctx->shared.frame;
         RTDS_TRY(render_frame_graph(ctx, A, fn, lin, have_dirs_launch ? &DL : nullptr, prefetch ? &PF : nullptr, shared, ctx->shared.seq, &launches));
         RTDS_CUDA(cudaStreamSynchronize(s));        // the graph ends with the counters' copy into pinned memory
         return render_stats_out(ctx, st, launches, A.local_rows, false, false);
     }
-    RTDS_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 16, s));      // [0..7] counters, [8..15] tile queues
+    RTDS_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 8, s));
     if (prefetch) RTDS_CUDA(cudaStreamWaitEvent(s, ctx->ev_pf1, 0));
     if (A.local_rows > 0 && strip) {
         const int blocks = (int)(c_last - c_first + 1);
@@ -1636,7 +1438,6 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             const dim3 block(128);
             const void* fn = select_render_kernel(ctx, A, p, full, kdt, brute, kd_closest);
             const unsigned lin = render_grid(ctx, fn, W, r1 - r0);
-            A.queue = ctx->d_counters + 8 + bi;            // render_dyn_kernel: one tile queue per band launch
             void* kargs[] = {(void*)&A};
             RTDS_CUDA(cudaLaunchKernel(fn, dim3(lin), block, kargs, 0, s));
             launches += 1;
@@ -1739,3 +1540,10 @@ int rtds_trace_impl(rtds_ctx* ctx, int acc, int exact, const float* h_o, const f
     }
     return RTDS_OK;
 }
+
+#ifdef RTDS_BLOCK_TIMING
+extern "C" int rtds_debug_block_times(unsigned long long* out, int n_blocks)
+{
+    return cudaMemcpyFromSymbol(out, g_block_times, sizeof(unsigned long long) * 3 * (size_t)n_blocks) == cudaSuccess ? 0 : -2;
+}
+#endif

@@ -123,7 +123,6 @@ struct RtdsOptions {
     int band_ratio = 100;    // RTDS_BAND_RATIO   each band's share of the one before it, percent
     int packet = 1;          // RTDS_PACKET       0: never the packet kernels
     int hull = 1;            // RTDS_HULL         0: interior boxes tested per ray instead of once per packet
-    int dyn = 1;             // RTDS_DYN          persistent warps with dynamic pixel fetch: 0 off, 1 where the sample packets do not apply, 2 everywhere
     int zerocopy = 0;        // RTDS_ZEROCOPY     1: store the frame straight into pinned host memory (measured slower)
     int trace_frame = 0;     // RTDS_TRACE_FRAME  1: rtds_frame stage timeline on stderr, 2: + per-band events
     int median_small = 0;    // RTDS_MEDIAN_SMALL test hook: sequential/parallel switch-over of the median split (0 = 64)
@@ -131,7 +130,7 @@ struct RtdsOptions {
     int median_debug = 0;    // RTDS_MEDIAN_DEBUG
     int node_preorder = 0;   // RTDS_NODE_ORDER=preorder: renumber the nodes in DFS pre-order after the build
     int l2_prefetch = 0;     // RTDS_L2_PREFETCH  stream the tree into L2 on a side stream while the directions are generated
-    int frame_graph = 0;     // RTDS_FRAME_GRAPH  multi-GPU shared frames: one CUDA graph launch per frame
+    int frame_graph = 0;     // RTDS_FRAME_GRAPH  device-buffer / shared-frame renders: one CUDA graph launch per frame (measured: no gain)
 };
 typedef int RtdsOptions::*RtdsOptionField;
 struct RtdsOptionName { const char* name; const char* env; RtdsOptionField field; };
@@ -200,8 +199,7 @@ struct rtds_ctx {
     size_t   frame_bytes = 0;
     int*     d_hit = nullptr;  size_t hit_bytes = 0;
     float*   d_accum = nullptr; size_t accum_bytes = 0;
-    int      dyn_blocks_per_sm = 0;  // resident blocks of render_dyn_kernel per SM (occupancy query, once)
-    unsigned long long* d_counters = nullptr;  // render counters [8] + tile queue heads [8]
+    unsigned long long* d_counters = nullptr;  // render counters [8]
     unsigned long long* h_counters = nullptr;  // pinned [16]: [0..7] render counters, [8] material flag, [9..11] LBVH root box, [12] depth
     uint8_t* h_pinned = nullptr;     // pinned host staging for D2H of frames
     SharedFrame shared;

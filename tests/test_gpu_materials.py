@@ -128,7 +128,8 @@ def test_material_scenes_through_the_packet_kernel(gpu_ctx, oracle, acc, shadows
         assert pk[3]["secondary_rays"] > 100
         # (the median split over spheres of mixed size drops ranges, accelerators.h:321-327: leaves then carry range boxes and the
         # packet kernels do not apply - same kernel, same counters)
-        assert pk[3]["node_visits"] < sr[3]["node_visits"] if acc == rt.LBVH else pk[3]["node_visits"] <= sr[3]["node_visits"]
+        # and so do material scenes WITH shadow rays (measured slower through the packets: the single-ray castRay kernel stays)
+        assert pk[3]["node_visits"] < sr[3]["node_visits"] if (acc == rt.LBVH and not shadows) else pk[3]["node_visits"] <= sr[3]["node_visits"]
         rgb_o, hit_o, accum_o, _ = oracle.render_rows(sph, mat, nodes, order, W, H, spp, tie_by_objid=1 if acc == rt.LBVH else 0,
                                                        lights=LIGHTS3, want_accum=True, shadows=shadows)
         assert np.array_equal(pk[1], hit_o) and pk[2].tobytes() == accum_o.tobytes() and np.array_equal(pk[0], rgb_o)

@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_render.py tests/test_gpu_shared_frame.py tests/test_gpu_materials.py -q -m gpu 2>&1 | tail -4
+for w in 1 2 4 8; do WORLD=$w ITERS=10 timeout 600 python tools/ab_frame.py dirs_ahead=0,1 >> gpurun_out/r02h_ab_dirs_ahead.txt 2>&1; done
+cat gpurun_out/r02h_ab_dirs_ahead.txt | cut -c1-330
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02h_bench_config3.json 2> gpurun_out/r02h_bench_config3.err
+tail -c 1500 gpurun_out/r02h_bench_config3.json; tail -3 gpurun_out/r02h_bench_config3.err
