@@ -18,6 +18,7 @@ const RtdsOptionName g_rtds_option_names[] = {
     {"median_small", "RTDS_MEDIAN_SMALL", &RtdsOptions::median_small}, {"median_coop", "RTDS_MEDIAN_COOP", &RtdsOptions::median_coop},
     {"median_debug", "RTDS_MEDIAN_DEBUG", &RtdsOptions::median_debug}, {"node_preorder", "RTDS_NODE_PREORDER", &RtdsOptions::node_preorder},
     {"l2_prefetch", "RTDS_L2_PREFETCH", &RtdsOptions::l2_prefetch}, {"frame_graph", "RTDS_FRAME_GRAPH", &RtdsOptions::frame_graph},
+    {"lpt", "RTDS_LPT", &RtdsOptions::lpt},
 };
 const int g_rtds_n_option_names = (int)(sizeof g_rtds_option_names / sizeof g_rtds_option_names[0]);
 
@@ -163,6 +164,8 @@ static int create_resources(rtds_ctx* c)
     RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_band, cudaEventDisableTiming));
     RTDS_CUDA(cudaStreamCreateWithFlags(&c->jit_stream, cudaStreamNonBlocking));
     RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_dirs, cudaEventDisableTiming));
+    RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_order_go, cudaEventDisableTiming));
+    RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_order_done, cudaEventDisableTiming));
     RTDS_CUDA(cudaStreamCreateWithFlags(&c->pf_stream, cudaStreamNonBlocking));
     RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_pf0, cudaEventDisableTiming));
     RTDS_CUDA(cudaEventCreateWithFlags(&c->ev_pf1, cudaEventDisableTiming));
@@ -219,14 +222,14 @@ int rtds_destroy(rtds_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     rtds_free_bvh(c->bvh);
     rtds_free_kd(c->kd);
-    void* bufs[] = {c->d_sph, c->d_mat, c->d_tris, c->d_keys_sorted, c->d_mt_snap, c->d_jitter, c->d_dirs, c->d_scratch,
+    void* bufs[] = {c->d_sph, c->d_mat, c->d_tris, c->d_keys_sorted, c->d_mt_snap, c->d_jitter, c->d_dirs, c->d_block_cost, c->d_block_order, c->d_scratch,
                     c->d_sort_ws, c->d_frame, c->d_hit, c->d_accum, c->d_counters};
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->fg.exec) cudaGraphExecDestroy(c->fg.exec);
     if (c->fg.graph) cudaGraphDestroy(c->fg.graph);
     if (c->pf_stream) cudaStreamDestroy(c->pf_stream);
-    for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->ev3, c->ev_band, c->ev_dirs, c->ev_pf0, c->ev_pf1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->ev3, c->ev_band, c->ev_dirs, c->ev_order_go, c->ev_order_done, c->ev_pf0, c->ev_pf1}) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     shared_frame_drop(c);
     if (c->h_counters) cudaFreeHost(c->h_counters);

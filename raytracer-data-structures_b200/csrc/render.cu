@@ -99,7 +99,114 @@ struct RenderArgs {
     int*     out_hit;            // optional, local rows x width
     float*   out_accum;          // optional, local rows x width x 3
     unsigned long long* counters;
+    const int* order;            // optional: launch position -> block id (the previous frame's heaviest blocks first), see block_order_kernel
+    unsigned*  cost;             // optional: per block id, the largest per-thread node-visit count of this frame (input of the next frame's order)
 };
+
+// Heaviest blocks first. A handful of 16 x 8-pixel blocks (silhouettes, rays that graze many leaf boxes) run 15-25 times the median
+// block - measured with tools/block_timeline.py: median 7.5 us, p99 105 us, max 187 us on the bench frame - and the kernel cannot end
+// before "start of the slowest block + its duration". In launch order those blocks start late (the lower image half 55 us into
+// a 240 us per-rank kernel at 8 GPUs; 800 us into the 950 us single-GPU kernel). So every frame records each block's cost (the
+// largest node-visit count among its threads), and the NEXT frame of the same geometry launches the few hundred heaviest blocks
+// first, everything else in the usual quadrant-major order (which keeps one direction octant's loop copy per SM: +20 % per block
+// when that is given up). Pure scheduling: pixels do not depend on the order blocks run in.
+__device__ __forceinline__ int logical_block(const RenderArgs& A) { return A.order ? __ldg(A.order + blockIdx.x) : (int)blockIdx.x; }
+__device__ __forceinline__ void report_block_cost(const RenderArgs& A, int lb, unsigned cost)      // all 32 lanes
+{
+    if (A.cost) {
+        const unsigned m = __reduce_max_sync(0xffffffffu, cost);
+        if ((threadIdx.x & 31) == 0 && m) atomicMax(A.cost + lb, m);
+    }
+}
+
+// cost[0..n) of the finished frame -> order[0..n) for the next one: the heaviest blocks first, heaviest of all at the front, the
+// rest behind them in ascending id (the usual launch order). "Heaviest" = cost in the top 32nds of [0, max] from the top down
+// for as long as at most `cap` blocks (half a wave of resident blocks) qualify, and never below max/4: enough to start every
+// straggler in the first wave, few enough to leave the octant-coherent launch order of everything else alone (with 2 % of a
+// 64,800-block frame moved to the front the frame got 2 % SLOWER: an SM full of heavy blocks of all four octants). Clears cost.
+// One block of 1024 threads per band.
+constexpr int LPT_MAX_HEAVY = 512;
+constexpr int LPT_TRIAL_FRAMES = 6;      // lpt = 1: frames of a geometry spent comparing the two orders
+struct LptBands { int n_bands; int off[RTDS_MAX_BANDS + 1]; };      // a frame rendered as row bands: one launch (and one order) per band
+__global__ void __launch_bounds__(1024) block_order_kernel(unsigned* __restrict__ cost, int* __restrict__ order, const LptBands bands, int cap)
+{
+    cost += bands.off[blockIdx.x]; order += bands.off[blockIdx.x];
+    const int n = bands.off[blockIdx.x + 1] - bands.off[blockIdx.x];
+    __shared__ unsigned s_u[32];
+    __shared__ int s_i[32], s_j[32];
+    __shared__ unsigned s_hist[32];
+    __shared__ unsigned s_M;
+    __shared__ int s_tbin, s_heavy;
+    __shared__ unsigned s_hc[LPT_MAX_HEAVY];
+    __shared__ int s_hid[LPT_MAX_HEAVY];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    cap = min(cap, LPT_MAX_HEAVY);
+    unsigned mx = 0;
+    for (int i = t; i < n; i += 1024) mx = max(mx, cost[i]);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) s_u[warp] = mx;
+    if (t < 32) s_hist[t] = 0u;
+    __syncthreads();
+    if (warp == 0) { unsigned v = s_u[lane]; v = __reduce_max_sync(0xffffffffu, v); if (lane == 0) s_M = v; }
+    __syncthreads();
+    const unsigned M = s_M;
+    auto bin_of = [M](unsigned c) { return M ? (int)min(31ull, (unsigned long long)c * 32ull / M) : 0; };
+    for (int i = t; i < n; i += 1024) { const unsigned c = cost[i]; if (c) atomicAdd(&s_hist[bin_of(c)], 1u); }
+    __syncthreads();
+    if (t == 0) {
+        int tb = 32, total = 0;
+        for (int b2 = 31; b2 >= 8 && M; --b2) {          // bins >= 8: cost >= max / 4
+            if (total + (int)s_hist[b2] > cap) break;
+            total += (int)s_hist[b2];
+            tb = b2;
+        }
+        s_tbin = tb;
+    }
+    __syncthreads();
+    const int tbin = s_tbin;
+    // stable split: thread t owns ids [t*per, (t+1)*per)
+    const int per = (n + 1023) / 1024, i0 = min(n, t * per), i1 = min(n, i0 + per);
+    int mine = 0;
+    for (int i = i0; i < i1; ++i) { const unsigned c = cost[i]; mine += (c && bin_of(c) >= tbin); }
+    int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_i[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = s_i[lane], sc = v;
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += u; }
+        s_j[lane] = sc - v;                       // exclusive offset of each warp
+        if (lane == 31) s_heavy = sc;
+    }
+    __syncthreads();
+    int before = s_j[warp] + incl - mine;         // heavy ids below i0
+    const int n_heavy = s_heavy;                  // <= cap <= LPT_MAX_HEAVY
+    for (int i = i0; i < i1; ++i) {
+        const unsigned c = cost[i];
+        const bool h = c && bin_of(c) >= tbin;
+        if (h) { s_hc[before] = c; s_hid[before] = i; } else order[n_heavy + i - before] = i;
+        before += h;
+        cost[i] = 0u;
+    }
+    // the heavy ones by descending cost (ties: ascending id): bitonic sort of the padded list in shared memory
+    for (int i = n_heavy + t; i < LPT_MAX_HEAVY; i += 1024) { s_hc[i] = 0u; s_hid[i] = 0x7fffffff; }
+    __syncthreads();
+    for (int k = 2; k <= LPT_MAX_HEAVY; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (t < LPT_MAX_HEAVY) {
+                const int x = t ^ j;
+                if (x > t) {
+                    const unsigned ca = s_hc[t], cb = s_hc[x];
+                    const int ia = s_hid[t], ib = s_hid[x];
+                    const bool a_first = ca > cb || (ca == cb && ia < ib);       // a belongs before b in the final order
+                    const bool up = (t & k) == 0;
+                    if (up ? !a_first : a_first) { s_hc[t] = cb; s_hc[x] = ca; s_hid[t] = ib; s_hid[x] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    if (t < n_heavy) order[t] = s_hid[t];
+}
 
 // Frame-buffer write of a warp's 8 x 4 pixels. The warp's RGB8 values are staged in shared memory and leave as 12
 // aligned 8-byte stores (4 rows x 24 bytes) instead of 96 single-byte stores: when the frame lives in ANOTHER GPU's
@@ -176,7 +283,8 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
     __shared__ float4 sh_sph[MODE == 2 ? NONE_CHUNK : 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int bx, by;
-    quadrant_block(blockIdx.x, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by, A.block_order);
+    const int lblock = logical_block(A);
+    quadrant_block(lblock, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by, A.block_order);
     const int px = bx * 16 + (warp & 1) * 8 + (lane & 7);
     const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool active = px < A.width && lrow < A.local_rows;
@@ -229,6 +337,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         if (A.out_hit) A.out_hit[o] = last_hit;
         if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
     }
+    report_block_cost(A, lblock, cnt.node_visits + cnt.prim_tests);
     // counters: warp reduce, one atomic per warp per counter
     unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
 #pragma unroll
@@ -390,7 +499,8 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
     unsigned shadow_rays = 0, secondary_rays = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int bx, by;
-    quadrant_block(blockIdx.x, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by, A.block_order);
+    const int lblock = logical_block(A);
+    quadrant_block(lblock, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by, A.block_order);
     const int px = bx * 16 + (warp & 1) * 8 + (lane & 7);
     const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool active = px < A.width && lrow < A.local_rows;
@@ -453,6 +563,7 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
         g_block_times[3 * blockIdx.x] = bt0; g_block_times[3 * blockIdx.x + 1] = bt1; g_block_times[3 * blockIdx.x + 2] = ((unsigned long long)smid << 32) | cnt.node_visits;
     }
 #endif
+    report_block_cost(A, lblock, cnt.node_visits + cnt.prim_tests);
     unsigned v[6] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays, shadow_rays, secondary_rays};
 #pragma unroll
     for (int c = 0; c < (MATERIALS ? 6 : (SHADOWS ? 5 : 4)); ++c) {
@@ -751,7 +862,8 @@ __global__ void __launch_bounds__(128) render_full_kernel(const __grid_constant_
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int bx, by;
-    quadrant_block(blockIdx.x, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by, A.block_order);
+    const int lblock = logical_block(A);
+    quadrant_block(lblock, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by, A.block_order);
     const int px = bx * 16 + (warp & 1) * 8 + (lane & 7);
     const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool active = px < A.width && lrow < A.local_rows;
@@ -779,6 +891,7 @@ __global__ void __launch_bounds__(128) render_full_kernel(const __grid_constant_
         if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
     }
     store_warp_rgb(A, px, lrow, active, r8, g8, b8);
+    report_block_cost(A, lblock, cnt.node_visits + cnt.prim_tests);
     unsigned v[6] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays, shadow_rays, secondary_rays};
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
@@ -1217,6 +1330,8 @@ static int render_frame_graph(rtds_ctx* ctx, const RenderArgs& A, const void* fn
     return RTDS_OK;
 }
 
+static void lpt_frame_timed(rtds_ctx* ctx, float ms_kernel, bool was_lpt_frame, bool used_order);
+
 // render statistics from the counters the frame left in pinned memory (the stream is already synchronised)
 static int render_stats_out(rtds_ctx* ctx, rtds_render_stats* st, int launches, int rows, bool wait_copies, bool)
 {
@@ -1230,6 +1345,8 @@ static int render_stats_out(rtds_ctx* ctx, rtds_render_stats* st, int launches, 
     st->kernel_launches = launches;
     st->rows = rows;
     st->reserved[0] = (int)(unsigned)c[7];      // shared frame: 1 + the rank the owner timed out on (0 = complete)
+    lpt_frame_timed(ctx, st->ms_kernel, ctx->lpt_active, ctx->lpt_last_used_order);
+    ctx->lpt_active = false;
     if (wait_copies) RTDS_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     return RTDS_OK;
 }
@@ -1274,6 +1391,82 @@ static const void* select_render_kernel(const rtds_ctx* ctx, const RenderArgs& A
     return p->exact ? (const void*)render_kernel<0> : (const void*)render_kernel<1>;
 }
 
+// lpt option, before a frame's launches: size the cost / order arrays for the frame's bands (one launch each) and decide whether
+// the order learned from the previous frame applies (same kernel, geometry and banding); `s` is ordered behind the order kernel.
+static int lpt_frame_begin(rtds_ctx* ctx, const RenderArgs& A, const void* fn, const LptBands& bands, cudaStream_t s)
+{
+    ctx->lpt_active = false;
+    if (!ctx->opt.lpt) return RTDS_OK;
+    const int total = bands.off[bands.n_bands];
+    if (total <= 0) return RTDS_OK;
+    if (ctx->block_cap < total) {
+        RTDS_CUDA(cudaStreamSynchronize(ctx->jit_stream));
+        if (ctx->d_block_cost) cudaFree(ctx->d_block_cost);
+        if (ctx->d_block_order) cudaFree(ctx->d_block_order);
+        ctx->d_block_cost = nullptr; ctx->d_block_order = nullptr; ctx->block_cap = 0; ctx->block_order_valid = false;
+        RTDS_CUDA(cudaMalloc(&ctx->d_block_cost, sizeof(unsigned) * (size_t)total));
+        RTDS_CUDA(cudaMalloc(&ctx->d_block_order, sizeof(int) * (size_t)total));
+        ctx->block_cap = total;
+        memset(ctx->block_key, 0, sizeof ctx->block_key);
+    }
+    uint64_t bh = (uint64_t)bands.n_bands;
+    for (int i = 0; i <= bands.n_bands; ++i) bh = bh * 1000003ull + (uint64_t)bands.off[i];
+    const uint64_t key[5] = {(uint64_t)(uintptr_t)fn, ((uint64_t)(unsigned)A.width << 32) | (unsigned)A.local_rows,
+                             ((uint64_t)(unsigned)A.rank << 40) | ((uint64_t)(unsigned)A.world << 20) | (uint64_t)(unsigned)A.tile_rows,
+                             ((uint64_t)(unsigned)A.block_order << 32) | (unsigned)A.spp, bh};
+    RTDS_CUDA(cudaStreamWaitEvent(s, ctx->ev_order_done, 0));      // the last frame's order kernel (it also clears the costs)
+    if (memcmp(key, ctx->block_key, sizeof key) != 0) {
+        // another geometry, banding or kernel: forget the old costs and order
+        RTDS_CUDA(cudaMemsetAsync(ctx->d_block_cost, 0, sizeof(unsigned) * (size_t)total, s));
+        memcpy(ctx->block_key, key, sizeof key);
+        ctx->block_order_valid = false;
+        ctx->lpt_phase = 0; ctx->lpt_use = true; ctx->lpt_ms_base = ctx->lpt_ms_order = 0.f;
+    }
+    // lpt = 1: the library times both orders once per geometry (its own kernel events) and keeps the faster one; a geometry for
+    // which the learned order lost stops recording costs
+    ctx->lpt_active = ctx->opt.lpt >= 2 || ctx->lpt_phase < LPT_TRIAL_FRAMES || ctx->lpt_use;
+    return RTDS_OK;
+}
+
+// ... with the frame's kernel time known: baseline frame (launch order) -> trial frame (learned order) -> decision
+static void lpt_frame_timed(rtds_ctx* ctx, float ms_kernel, bool was_lpt_frame, bool used_order)
+{
+    // frames 0, 2, 4 of a geometry run in launch order, frames 1, 3, 5 in the learned order; the best time of each decides (the
+    // very first frames of a process are slow for reasons of their own)
+    if (!was_lpt_frame || ctx->opt.lpt != 1 || ctx->lpt_phase >= LPT_TRIAL_FRAMES || !(ms_kernel > 0.f)) return;
+    const bool trial = (ctx->lpt_phase & 1) != 0;
+    if (trial != used_order) return;                       // (no order yet: the frame counts as nothing)
+    float& best = trial ? ctx->lpt_ms_order : ctx->lpt_ms_base;
+    best = best > 0.f ? std::min(best, ms_kernel) : ms_kernel;
+    if (++ctx->lpt_phase == LPT_TRIAL_FRAMES) ctx->lpt_use = ctx->lpt_ms_order < 0.997f * ctx->lpt_ms_base;
+}
+
+// ... per launch: the band's slice of the two arrays
+static void lpt_band_args(rtds_ctx* ctx, RenderArgs& A, const LptBands& bands, int band)
+{
+    A.order = nullptr; A.cost = nullptr;
+    if (!ctx->lpt_active) return;
+    const bool use = ctx->opt.lpt >= 2 || (ctx->lpt_phase < LPT_TRIAL_FRAMES ? (ctx->lpt_phase & 1) != 0 : ctx->lpt_use);
+    if (ctx->block_order_valid && use) A.order = ctx->d_block_order + bands.off[band];
+    ctx->lpt_last_used_order = A.order != nullptr;
+    A.cost = ctx->d_block_cost + bands.off[band];
+}
+
+// ... and behind the frame's render kernels (`s` has joined every band): the side stream turns this frame's costs into the next
+// frame's order
+static int lpt_frame_end(rtds_ctx* ctx, const LptBands& bands, cudaStream_t s)
+{
+    if (!ctx->lpt_active) return RTDS_OK;
+    RTDS_CUDA(cudaEventRecord(ctx->ev_order_go, s));
+    RTDS_CUDA(cudaStreamWaitEvent(ctx->jit_stream, ctx->ev_order_go, 0));
+    block_order_kernel<<<bands.n_bands, 1024, 0, ctx->jit_stream>>>(ctx->d_block_cost, ctx->d_block_order, bands,
+                                                                    std::max(32, ctx->sm_count * 3 / bands.n_bands));
+    RTDS_CUDA(cudaGetLastError());
+    RTDS_CUDA(cudaEventRecord(ctx->ev_order_done, ctx->jit_stream));
+    ctx->block_order_valid = true;
+    return RTDS_OK;
+}
+
 int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_t* d_rgb_rows, int* d_hit, float* d_accum,
                      rtds_render_stats* st, const std::function<int(int, int, cudaEvent_t)>* on_band, bool global_rows)
 {
@@ -1312,6 +1505,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.out_vec8 = (((uintptr_t)d_rgb_rows & 7) == 0 && W % 8 == 0) ? 1 : 0;
     A.block_order = ctx->opt.block_order;
     A.counters = ctx->d_counters;
+    A.order = nullptr; A.cost = nullptr;
 
     cudaStream_t s = ctx->stream;
     int launches = 0;
@@ -1423,6 +1617,12 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             }
             band_start[n_bands] = total_rows;
         }
+        // lpt: every band launch starts with the blocks that were heaviest in the previous frame
+        const void* fn = select_render_kernel(ctx, A, p, full, kdt, brute, kd_closest);
+        LptBands lb;
+        lb.n_bands = n_bands; lb.off[0] = 0;
+        for (int bi = 0; bi < n_bands; ++bi) lb.off[bi + 1] = lb.off[bi] + (int)render_grid(ctx, fn, W, std::max(0, band_start[bi + 1] - band_start[bi]));
+        RTDS_TRY(lpt_frame_begin(ctx, A, fn, lb, s));
         RTDS_CUDA(cudaEventRecord(ctx->ev2, s));
         if (n_bands > 1) RTDS_CUDA(cudaEventRecord(ctx->ev_ready, s));       // directions + counters are ready behind this
         for (int bi = 0; bi < n_bands; ++bi) {
@@ -1436,8 +1636,8 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
                 RTDS_CUDA(cudaStreamWaitEvent(s, ctx->ev_ready, 0));
             }
             const dim3 block(128);
-            const void* fn = select_render_kernel(ctx, A, p, full, kdt, brute, kd_closest);
             const unsigned lin = render_grid(ctx, fn, W, r1 - r0);
+            lpt_band_args(ctx, A, lb, bi);
             void* kargs[] = {(void*)&A};
             RTDS_CUDA(cudaLaunchKernel(fn, dim3(lin), block, kargs, 0, s));
             launches += 1;
@@ -1460,6 +1660,8 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
                 if (band_start[bi + 1] > band_start[bi]) RTDS_TRY((*on_band)(band_start[bi], band_start[bi + 1], ctx->ev_bands[bi]));
         }
         A.local_rows = total_rows;
+        A.lrow0 = 0;
+        RTDS_TRY(lpt_frame_end(ctx, lb, ctx->stream));
         RTDS_CUDA(cudaGetLastError());
     } else {
         RTDS_CUDA(cudaEventRecord(ctx->ev2, s));

@@ -130,6 +130,7 @@ struct RtdsOptions {
     int median_debug = 0;    // RTDS_MEDIAN_DEBUG
     int node_preorder = 0;   // RTDS_NODE_ORDER=preorder: renumber the nodes in DFS pre-order after the build
     int l2_prefetch = 0;     // RTDS_L2_PREFETCH  stream the tree into L2 on a side stream while the directions are generated
+    int lpt = 1;             // RTDS_LPT          the previous frame's heaviest blocks are launched first: 1 = where the library measures a gain, 2 = always, 0 = never
     int frame_graph = 0;     // RTDS_FRAME_GRAPH  device-buffer / shared-frame renders: one CUDA graph launch per frame (measured: no gain)
 };
 typedef int RtdsOptions::*RtdsOptionField;
@@ -204,6 +205,18 @@ struct rtds_ctx {
     uint8_t* h_pinned = nullptr;     // pinned host staging for D2H of frames
     SharedFrame shared;
     FrameGraph  fg;
+    // lpt option: per-block costs of the last frame and the launch order derived from them, band by band (render.cu: block_order_kernel)
+    unsigned*   d_block_cost = nullptr;
+    int*        d_block_order = nullptr;
+    int         block_cap = 0;
+    uint64_t    block_key[5] = {0, 0, 0, 0, 0};   // geometry + kernel the buffers belong to
+    bool        block_order_valid = false;
+    bool        lpt_active = false;       // between lpt_frame_begin and lpt_frame_end of the current frame
+    int         lpt_phase = 0;            // frames of this geometry timed so far: even = launch order, odd = learned order; 6 = decided
+    bool        lpt_use = true;           // phase 2: the learned order was faster for this geometry
+    float       lpt_ms_base = 0.f, lpt_ms_order = 0.f;
+    bool        lpt_last_used_order = false;
+    cudaEvent_t ev_order_go = nullptr, ev_order_done = nullptr;
     cudaStream_t pf_stream = nullptr;   // tree prefetch into L2 beside the direction kernel (l2_prefetch option, non-graph path)
     cudaEvent_t  ev_pf0 = nullptr, ev_pf1 = nullptr;
     size_t   pinned_bytes = 0;

@@ -220,15 +220,16 @@ def test_visible_clones_variant_packet_equals_reference_traversal(gpu_ctx, oracl
 
 
 @pytest.mark.parametrize("spp,shadows", [(4, 0), (1, 0), (4, 1)])
-def test_frame_graph_and_l2_prefetch_do_not_change_the_frame(gpu_ctx, spp, shadows):
-    """frame_graph (the whole device-buffer frame as ONE cudaGraphLaunch) and l2_prefetch (the tree streamed into L2 beside the
-    direction kernel) are pure scheduling: bytes, counters and ray counts equal the plain stream path's, frame after frame, also
+def test_scheduling_options_do_not_change_the_frame(gpu_ctx, spp, shadows):
+    """frame_graph (the whole device-buffer frame as ONE cudaGraphLaunch), l2_prefetch (the tree streamed into L2 beside the
+    direction kernel) and lpt (the previous frame's heaviest blocks launched first) are pure scheduling: bytes, counters and ray counts equal the plain stream path's, frame after frame, also
     when the arguments change between frames (jitter offset, rank, resolution: SetParams / rebuild paths of the graph)."""
     import torch
     sph, mat = T.bunny_scene()
     gpu_ctx.set_spheres(sph, mat)
     gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
-    cases = [(400, 300, 0, 1, 0), (400, 300, 0, 1, 0), (400, 300, 0, 1, 4321), (400, 300, 1, 3, 0), (322, 203, 0, 1, 0), (400, 300, 0, 1, 0)]
+    cases = [(400, 300, 0, 1, 0), (400, 300, 0, 1, 0), (400, 300, 0, 1, 4321), (400, 300, 1, 3, 0), (400, 300, 1, 3, 0), (322, 203, 0, 1, 0),
+             (400, 300, 0, 1, 0)]
     buf = torch.zeros((300, 400, 3), dtype=torch.uint8, device="cuda")
 
     def run():
@@ -241,10 +242,13 @@ def test_frame_graph_and_l2_prefetch_do_not_change_the_frame(gpu_ctx, spp, shado
             out.append((buf.cpu().numpy().reshape(-1)[: rows * W * 3].copy(), st["rays"], st["node_visits"], st["prim_tests"], st["rows"]))
         return out
 
-    plain = run()
-    for graph, pf in ((1, 0), (0, 1), (1, 1)):
-        with T.option(gpu_ctx, "frame_graph", graph), T.option(gpu_ctx, "l2_prefetch", pf):
+    with T.option(gpu_ctx, "lpt", 0):
+        plain = run()
+    # lpt (default): a frame launches the blocks that were heaviest in the previous frame of the same geometry first (cases 0 -> 1,
+    # and again across the two runs); another geometry or kernel drops the learned order
+    for graph, pf, lpt in ((0, 0, 1), (1, 0, 0), (0, 1, 1), (1, 1, 0)):
+        with T.option(gpu_ctx, "frame_graph", graph), T.option(gpu_ctx, "l2_prefetch", pf), T.option(gpu_ctx, "lpt", lpt):
             got = run() + run()
         for a, b in zip(plain + plain, got):
-            assert np.array_equal(a[0], b[0]) and a[1:] == b[1:], (graph, pf)
+            assert np.array_equal(a[0], b[0]) and a[1:] == b[1:], (graph, pf, lpt)
     assert plain[0][1] >= 400 * 300 * spp and (shadows == 0) == (plain[0][1] == 400 * 300 * spp)

@@ -18,6 +18,8 @@ world, rank = int(os.environ.get("WORLD", "8")), int(os.environ.get("RANK", "5")
 ctx = rt.Rtds(0)
 if os.environ.get("ORDER"):
     ctx.set_option("block_order", int(os.environ["ORDER"]))
+if os.environ.get("LPT"):
+    ctx.set_option("lpt", int(os.environ["LPT"]))
 sph, mat = wl.scene()
 ctx.set_spheres(sph, mat)
 ctx.build(wl.acc, mode=wl.mode)
@@ -37,7 +39,7 @@ sm, visits = (t[:, 2] >> np.uint64(32)).astype(np.int64), (t[:, 2] & np.uint64(0
 t0 = start.min()
 start, end = (start - t0) / 1e3, (end - t0) / 1e3     # microseconds
 dur = end - start
-print("block_order %d | world %d rank %d: %d blocks, kernel %.1f us by CUDA events, %.1f us first block start -> last block end" % (ctx.get_option("block_order"), world, rank, nb, 1e3 * st["ms_kernel"], end.max()))
+print("lpt %d block_order %d | world %d rank %d: %d blocks, kernel %.1f us by CUDA events, %.1f us first block start -> last block end" % (ctx.get_option("lpt"), ctx.get_option("block_order"), world, rank, nb, 1e3 * st["ms_kernel"], end.max()))
 print("block duration us: min %.1f  median %.1f  mean %.1f  p90 %.1f  p99 %.1f  max %.1f" %
       (dur.min(), np.median(dur), dur.mean(), np.percentile(dur, 90), np.percentile(dur, 99), dur.max()))
 print("sum of block durations / (SMs x 6 slots): %.1f us (the kernel's length if every slot were always busy)" % (dur.sum() / (148 * 6)))
