@@ -581,6 +581,14 @@ def run_ours(args):
 
     # counters (sum over ranks) and rank 0's kernel for the roofline
     k_ms = float(np.mean([s["ms_kernel"] for s in stats]))
+    # per-rank stage times of the resident frame (device clocks): render kernel, and everything the call queued (directions +
+    # render + flag / wait) - the per-stage picture of the strong-scaling run
+    stage = torch.tensor([k_ms, float(np.mean([s["ms_total"] for s in stats]))], dtype=torch.float64, device=dev)
+    stages = [torch.zeros_like(stage) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(stages, stage)
+    else:
+        stages = [stage]
     cnt = torch.tensor([stats[-1]["node_tests"], stats[-1]["prim_tests"], stats[-1]["rays"], stats[-1]["node_visits"]],
                        dtype=torch.float64, device=dev)
     mine = cnt.clone()
@@ -653,6 +661,10 @@ def run_ours(args):
                                  "go down its own PCIe link into ONE page-locked host frame shared by the ranks (no GPU-side gather: the consumer is "
                                  "the host); step time = max over ranks"),
                         "via_gpu_assembled_frame": e2e_shared},
+                "per_rank": {"render_kernel_ms": [round(float(x[0].item()), 4) for x in stages],
+                             "device_total_ms": [round(float(x[1].item()), 4) for x in stages],
+                             "what": "resident frame, mean over the timed steps, CUDA events per rank: the render kernel alone / everything the "
+                                     "call queued (ray directions + render kernel + this rank's flag; on rank 0 also the wait for every rank's flag)"},
                 "with_shadows": with_shadows,
                 "gpu_launches": int(launches_per_step * args.steps * world),
                 "clocks": clocks}

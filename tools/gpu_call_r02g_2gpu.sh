@@ -8,7 +8,7 @@ timeout 600 $TR bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02g_bench_
 tail -c 1800 gpurun_out/r02g_bench_config3_2gpu.json; tail -3 gpurun_out/r02g_bench_config3_2gpu.err
 RTDS_FRAME_GRAPH=1 timeout 600 $TR bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02g_bench_config3_2gpu_graph.json 2> gpurun_out/r02g_bench_config3_2gpu_graph.err
 tail -c 600 gpurun_out/r02g_bench_config3_2gpu_graph.json
-RTDS_BLOCK_ORDER=3 timeout 600 $TR bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02g_bench_config3_2gpu_order3.json 2> gpurun_out/r02g_bench_config3_2gpu_order3.err
+RTDS_LPT=0 timeout 600 $TR bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02g_bench_config3_2gpu_lpt0.json 2> gpurun_out/r02g_bench_config3_2gpu_lpt0.err
 timeout 600 $TR bench.py --gpus 2 --steps 10 --warmup 3 --gather nccl > gpurun_out/r02g_bench_config3_2gpu_nccl.json 2> gpurun_out/r02g_bench_config3_2gpu_nccl.err
 timeout 900 $TR bench.py --gpus 2 --workload config4 --steps 5 --warmup 3 > gpurun_out/r02g_bench_config4_2gpu.json 2> gpurun_out/r02g_bench_config4_2gpu.err
 tail -c 600 gpurun_out/r02g_bench_config4_2gpu.json; tail -3 gpurun_out/r02g_bench_config4_2gpu.err
