@@ -473,6 +473,30 @@ def run_ours(args):
         assert rc == 0, ctx.lib.rtds_last_error()
         return None
 
+    # N > 1, end to end, scene exchanged over NVLink: every rank uploads only ITS 1/N of the two tables (pinned host -> device) and
+    # the ranks all-gather the parts with NCCL (the path's one real exchange step), instead of N full uploads competing for the
+    # host's memory system; then the same C-ABI calls on device-resident tables: rtds_set_spheres_device + rtds_build + rtds_render
+    # (own tiles straight into the shared host frame).
+    if world > 1:
+        per = (n + world - 1) // world
+        lo_i, hi_i = min(n, rank * per), min(n, (rank + 1) * per)
+        d_sph_full = torch.zeros((per * world, 4), dtype=torch.float32, device=dev)
+        d_mat_full = torch.zeros((per * world, 4), dtype=torch.float32, device=dev)
+        d_sph_part = torch.zeros((per, 4), dtype=torch.float32, device=dev)
+        d_mat_part = torch.zeros((per, 4), dtype=torch.float32, device=dev)
+
+    def step_e2e_sliced():
+        d_sph_part[: hi_i - lo_i].copy_(sph_pin[lo_i:hi_i], non_blocking=True)
+        d_mat_part[: hi_i - lo_i].copy_(mat_pin[lo_i:hi_i], non_blocking=True)
+        dist.all_gather_into_tensor(d_sph_full, d_sph_part)
+        dist.all_gather_into_tensor(d_mat_full, d_mat_part)
+        torch.cuda.current_stream().synchronize()
+        ctx.set_spheres_device(d_sph_full.data_ptr(), d_mat_full.data_ptr(), n)
+        ctx.build(wl.acc, mode=wl.mode, **wl.build_kw)
+        rc = ctx.lib.rtds_render(ctx.ctx, wl.acc, C.byref(e2e_params), C.c_void_p(shared_host.ctypes.data), None, None, C.byref(e2e_stats))
+        assert rc == 0, ctx.lib.rtds_last_error()
+        return None
+
     def step_e2e_shared_frame():
         # the GPU-assembled variant (N > 1): rtds_frame_shared = upload + build + rtds_render_shared on every rank (tiles go to
         # rank 0's frame over NVLink), then rank 0 downloads the whole frame. Side number.
@@ -535,6 +559,17 @@ def run_ours(args):
     e2e_ms = float(np.mean(e2e_steps))
     e2e_value = total_rays / (e2e_ms * 1e-3) / 1e6
     e2e_sha = sha(frame_host.numpy() if world == 1 else np.asarray(shared_host)) if rank == 0 else None
+    e2e_sliced = None
+    if world > 1:
+        if rank == 0:
+            shared_host[:] = 0
+        sl_steps, _, _ = timed(step_e2e_sliced, max(2, min(args.steps, 5)), 1)
+        sl_ms = float(np.mean(sl_steps))
+        sl_sha = sha(np.asarray(shared_host)) if rank == 0 else None
+        e2e_sliced = {"ms_per_step": sl_ms, "value": total_rays / (sl_ms * 1e-3) / 1e6, "unit": "Mrays/s", "frame_sha256": sl_sha,
+                      "h2d_bytes_per_step": int(2 * n * 16),
+                      "what": "every rank uploads 1/N of the scene tables, NCCL all-gather over NVLink, rtds_set_spheres_device + rtds_build + "
+                              "rtds_render (own tiles into the shared host frame)"}
     e2e_shared = None
     if p2p:
         sf_steps, _, _ = timed(step_e2e_shared_frame, 3, 1)
@@ -577,6 +612,9 @@ def run_ours(args):
     if rank == 0:
         verify["e2e_frame_matches"] = e2e_sha == verify["frame_sha256"]
         ok &= verify["e2e_frame_matches"]
+        if e2e_sliced:
+            verify["e2e_sliced_frame_matches"] = e2e_sliced["frame_sha256"] == verify["frame_sha256"]
+            ok &= verify["e2e_sliced_frame_matches"]
         verify["frame_matches_single_rank"] = bool(ok)
 
     # counters (sum over ranks) and rank 0's kernel for the roofline
@@ -660,6 +698,7 @@ def run_ours(args):
                                  "directions generated on a side stream meanwhile. N>1: every rank makes the same call with its rank/world; its tiles "
                                  "go down its own PCIe link into ONE page-locked host frame shared by the ranks (no GPU-side gather: the consumer is "
                                  "the host); step time = max over ranks"),
+                        "scene_exchanged_over_nvlink": e2e_sliced,
                         "via_gpu_assembled_frame": e2e_shared},
                 "per_rank": {"render_kernel_ms": [round(float(x[0].item()), 4) for x in stages],
                              "device_total_ms": [round(float(x[1].item()), 4) for x in stages],

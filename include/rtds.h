@@ -166,6 +166,10 @@ int rtds_get_option(rtds_ctx* ctx, const char* name, int* value);
  * rgb_mat: n x {r,g,b,(float)rtds_material}, may be NULL (-> (0.8,0.7,0), diffuse: main.cpp:689).
  * AABBs are centre -/+ radius in float, as main.cpp:686-688. Host pointers. */
 int rtds_set_spheres(rtds_ctx* ctx, const float* cxyz_r, const float* rgb_mat, int n);
+/* The same with both tables already in THIS context's device memory (DEVICE pointers; copied, not adopted; rgb_mat required).
+ * For hosts that assemble the scene on the device - e.g. a multi-GPU run in which every rank uploads 1/N of the tables and the
+ * ranks exchange the parts over NVLink (NCCL all-gather) instead of pushing N full copies through the host's memory system. */
+int rtds_set_spheres_device(rtds_ctx* ctx, const float* d_cxyz_r, const float* d_rgb_mat, int n);
 /* Triangle primitives (extension; the reference never instantiates class Triangle, main.cpp:107-216). */
 int rtds_set_triangles(rtds_ctx* ctx, const float* v0v1v2, const float* rgb_mat, int n);
 /* m x {cx,cy,cz,radius,r,g,b}; default is main.cpp:775's single light (0,3,30), emission (1,1,1). */

@@ -93,7 +93,7 @@ ABI_SYMBOLS = ["rtds_last_error", "rtds_version", "rtds_create", "rtds_destroy",
                "rtds_export_morton", "rtds_trace", "rtds_render", "rtds_render_device", "rtds_rows_for_rank",
                "rtds_jitter_stream", "rtds_morton30", "rtds_frame", "rtds_shared_frame_create", "rtds_shared_frame_open",
                "rtds_shared_frame_attach", "rtds_render_shared", "rtds_frame_shared", "rtds_shared_frame_ptr", "rtds_shared_frame_read",
-               "rtds_shared_frame_close", "rtds_set_option", "rtds_get_option"]
+               "rtds_shared_frame_close", "rtds_set_option", "rtds_get_option", "rtds_set_spheres_device"]
 
 _lib = None
 
@@ -113,6 +113,7 @@ def load_library(path: str = LIB_PATH):
     lib.rtds_create.argtypes = [C.POINTER(vp), C.c_int]
     lib.rtds_destroy.argtypes = [vp]
     lib.rtds_set_spheres.argtypes = [vp, vp, vp, C.c_int]
+    lib.rtds_set_spheres_device.argtypes = [vp, vp, vp, C.c_int]
     lib.rtds_set_triangles.argtypes = [vp, vp, vp, C.c_int]
     lib.rtds_set_lights.argtypes = [vp, vp, C.c_int]
     lib.rtds_build.argtypes = [vp, C.c_int, C.POINTER(BuildParams), C.POINTER(BuildStats)]
@@ -191,6 +192,11 @@ class Rtds:
             assert rgb_mat.shape == cxyz_r.shape
         self._check(self.lib.rtds_set_spheres(self.ctx, _ptr(cxyz_r), _ptr(rgb_mat), cxyz_r.shape[0]))
         self.n = cxyz_r.shape[0]
+
+    def set_spheres_device(self, d_cxyz_r_ptr, d_rgb_mat_ptr, n):
+        """rtds_set_spheres_device: both tables already in this GPU's memory (raw device pointers)."""
+        self._check(self.lib.rtds_set_spheres_device(self.ctx, C.c_void_p(d_cxyz_r_ptr), C.c_void_p(d_rgb_mat_ptr), n))
+        self.n = n
 
     def set_triangles(self, v0v1v2, rgb_mat=None):
         """Triangle scene (extension; the reference never instantiates class Triangle): (n, 9) float32."""

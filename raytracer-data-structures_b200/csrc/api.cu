@@ -248,7 +248,7 @@ int rtds_destroy(rtds_ctx* c)
 // async_mat: the material table goes up on the copy stream (with the material-flag kernel behind it) and is only
 // waited for by finish_materials(); the sphere table is complete on return when !async_mat, otherwise the main stream
 // is ordered behind it.
-static int upload_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n, bool async_mat)
+static int upload_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n, bool async_mat, cudaMemcpyKind kind = cudaMemcpyHostToDevice)
 {
     if (!c || !cxyz_r || n <= 0) { rtds_set_error("set_spheres: bad arguments"); return RTDS_ERR_INVALID; }
     RTDS_CUDA(cudaSetDevice(c->device));
@@ -270,7 +270,7 @@ static int upload_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat
     // build's event record and first kernels - were ordered behind the copy engine's queue and did not start before the
     // 17 MB material copy had finished as well: build start 660 us instead of 345 us into the call.)
     const bool split = async_mat && rgb_mat;
-    RTDS_CUDA(cudaMemcpyAsync(c->d_sph, cxyz_r, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, split ? c->copy_stream : c->stream));
+    RTDS_CUDA(cudaMemcpyAsync(c->d_sph, cxyz_r, sizeof(float4) * (size_t)n, kind, split ? c->copy_stream : c->stream));
     c->has_materials = false;
     c->materials_pending = false;
     if (rgb_mat) {
@@ -279,7 +279,7 @@ static int upload_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat
             RTDS_CUDA(cudaEventRecord(c->ev_band, c->copy_stream));
             RTDS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_band, 0));
         }
-        RTDS_CUDA(cudaMemcpyAsync(c->d_mat, rgb_mat, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, ms));
+        RTDS_CUDA(cudaMemcpyAsync(c->d_mat, rgb_mat, sizeof(float4) * (size_t)n, kind, ms));
         int* d_flag = (int*)(c->d_counters + 6);
         RTDS_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), ms));
         material_flag_kernel<<<(n + 255) / 256, 256, 0, ms>>>(c->d_mat, n, d_flag);
@@ -329,6 +329,12 @@ extern "C" {
 int rtds_set_spheres(rtds_ctx* c, const float* cxyz_r, const float* rgb_mat, int n)
 {
     return upload_spheres(c, cxyz_r, rgb_mat, n, false);
+}
+
+int rtds_set_spheres_device(rtds_ctx* c, const float* d_cxyz_r, const float* d_rgb_mat, int n)
+{
+    if (!d_rgb_mat) { rtds_set_error("set_spheres_device: the material table is required"); return RTDS_ERR_INVALID; }
+    return upload_spheres(c, d_cxyz_r, d_rgb_mat, n, false, cudaMemcpyDeviceToDevice);
 }
 
 // What main() does per run, in one synchronous call with the stages overlapped: sphere table up -> build, while the

@@ -129,3 +129,23 @@ def test_failing_frame_call_is_synchronous_and_leaves_the_context_usable():
         assert ctx.render(rt.LBVH, 64, 48, 1)[3]["primary_rays"] == 64 * 48
     finally:
         ctx.close()
+
+
+def test_set_spheres_device_equals_host_upload(gpu_ctx):
+    """rtds_set_spheres_device (tables already in device memory, e.g. all-gathered over NVLink from per-rank parts) gives the same
+    structure and frame as rtds_set_spheres, also for scenes with materials (the material flag is computed on the device either way)."""
+    import torch
+    for sph, mat in (T.synthetic_scene(5000, 9), T.material_scene(3000, 10)):
+        gpu_ctx.set_spheres(sph, mat)
+        gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+        nodes, order = gpu_ctx.export_bvh()
+        rgb = gpu_ctx.render(rt.LBVH, 200, 150, 4)[0]
+        d_sph, d_mat = torch.from_numpy(sph).cuda(), torch.from_numpy(mat).cuda()
+        torch.cuda.synchronize()
+        gpu_ctx.set_spheres_device(d_sph.data_ptr(), d_mat.data_ptr(), sph.shape[0])
+        gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+        nodes2, order2 = gpu_ctx.export_bvh()
+        assert nodes2.tobytes() == nodes.tobytes() and np.array_equal(order2, order)
+        assert np.array_equal(gpu_ctx.render(rt.LBVH, 200, 150, 4)[0], rgb)
+    with pytest.raises(rt.RtdsError):
+        gpu_ctx.set_spheres_device(d_sph.data_ptr(), 0, sph.shape[0])
