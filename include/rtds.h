@@ -204,6 +204,10 @@ int rtds_render(rtds_ctx* ctx, int acc_type, const rtds_render_params* params, u
  * structure is built). Equivalent to the three calls; bst / rst may be NULL. */
 int rtds_frame(rtds_ctx* ctx, const float* cxyz_r, const float* rgb_mat, int n, int acc_type, const rtds_build_params* bp,
                const rtds_render_params* rp, uint8_t* rgb, rtds_build_stats* bst, rtds_render_stats* rst);
+/* Optional head start for hosts that upload and build with separate calls: begins generating the ray directions of the frame
+ * `params` describes (render()'s jitter + ray set-up, main.cpp:554-557) on a side stream and returns at once; the next
+ * rtds_render* call with the same parameters uses them instead of generating its own. rtds_frame does this internally. */
+int rtds_prepare_frame(rtds_ctx* ctx, const rtds_render_params* params);
 /* Same, result left on the device: d_rgb_rows is a DEVICE pointer receiving this rank's rows compactly
  * (local row-tile j = global tile j*world + rank), rtds_rows_for_rank(...)*width*3 bytes. Used by the
  * multi-GPU framebuffer gather (NCCL) and by resident-input timing. */

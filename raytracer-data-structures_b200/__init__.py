@@ -93,7 +93,7 @@ ABI_SYMBOLS = ["rtds_last_error", "rtds_version", "rtds_create", "rtds_destroy",
                "rtds_export_morton", "rtds_trace", "rtds_render", "rtds_render_device", "rtds_rows_for_rank",
                "rtds_jitter_stream", "rtds_morton30", "rtds_frame", "rtds_shared_frame_create", "rtds_shared_frame_open",
                "rtds_shared_frame_attach", "rtds_render_shared", "rtds_frame_shared", "rtds_shared_frame_ptr", "rtds_shared_frame_read",
-               "rtds_shared_frame_close", "rtds_set_option", "rtds_get_option", "rtds_set_spheres_device"]
+               "rtds_shared_frame_close", "rtds_set_option", "rtds_get_option", "rtds_set_spheres_device", "rtds_prepare_frame"]
 
 _lib = None
 
@@ -114,6 +114,7 @@ def load_library(path: str = LIB_PATH):
     lib.rtds_destroy.argtypes = [vp]
     lib.rtds_set_spheres.argtypes = [vp, vp, vp, C.c_int]
     lib.rtds_set_spheres_device.argtypes = [vp, vp, vp, C.c_int]
+    lib.rtds_prepare_frame.argtypes = [vp, C.POINTER(RenderParams)]
     lib.rtds_set_triangles.argtypes = [vp, vp, vp, C.c_int]
     lib.rtds_set_lights.argtypes = [vp, vp, C.c_int]
     lib.rtds_build.argtypes = [vp, C.c_int, C.POINTER(BuildParams), C.POINTER(BuildStats)]
@@ -291,6 +292,10 @@ class Rtds:
                                         C.byref(bst), C.byref(rst)))
         self.n = cxyz_r.shape[0]
         return rgb, _stats_dict(bst), _stats_dict(rst)
+
+    def prepare_frame(self, params):
+        """rtds_prepare_frame: start generating the frame's ray directions now (side stream); returns at once."""
+        self._check(self.lib.rtds_prepare_frame(self.ctx, C.byref(params)))
 
     def render_device(self, acc, params, device_ptr):
         st = RenderStats()

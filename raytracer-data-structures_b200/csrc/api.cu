@@ -762,6 +762,13 @@ int rtds_jitter_stream(rtds_ctx* c, uint64_t first, int n, double* out)
     return rtds_jitter_stream_impl(c, first, n, out);
 }
 
+int rtds_prepare_frame(rtds_ctx* c, const rtds_render_params* p)
+{
+    if (!c || !p) { rtds_set_error("prepare_frame: bad arguments"); return RTDS_ERR_INVALID; }
+    RTDS_CUDA(cudaSetDevice(c->device));
+    return rtds_prefetch_dirs(c, p);
+}
+
 int rtds_set_option(rtds_ctx* c, const char* name, int value)
 {
     if (!c || !name) { rtds_set_error("set_option: bad arguments"); return RTDS_ERR_INVALID; }

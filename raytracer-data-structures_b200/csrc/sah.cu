@@ -23,6 +23,26 @@ int rtds_bvh_reorder_preorder(rtds_ctx* ctx, DeviceBvh& b, void* scratch, int* l
 namespace {
 
 constexpr int MAXB = 32;
+// Tasks of at most SAH_SMALL primitives - all tasks of the lower half of the levels - never touch the global bin records (896
+// bytes per task: resetting, filling and reading them was 80 % of a 7 M-primitive build): a warp (or, for tiny tasks, a thread)
+// builds the task's bins in shared (local) memory and decides the split with the same code. Same definition, same tree.
+constexpr int SAH_SMALL = 512;     // ... at most this many primitives: one WARP per task (sah_warp_tasks), bins in shared memory
+constexpr int SAH_TINY = 32;       // ... at most this many: one THREAD per task (sah_small_tasks), bins in local memory
+
+// The primitive at position p of the current order. Sphere scenes carry the sphere records ALONG with the permutation (psph:
+// position-ordered copies, scattered together with perm by sah_scatter): every per-level pass then reads them as a sequential
+// stream. Gathering sph[perm[p]] instead - 16 scattered bytes per position, two or three times per level - was what the level
+// kernels spent their time on (7 M primitives: 0.33 ms per pass). Triangle scenes (extension) keep the gather.
+__device__ __forceinline__ void pos_fetch(const PrimView& pv, const int* __restrict__ perm, const float4* __restrict__ psph, int p, float c[3],
+                                          float mn[3], float mx[3])
+{
+    if (psph) {
+        const float4 s = __ldg(psph + p);
+        c[0] = s.x; c[1] = s.y; c[2] = s.z;
+        mn[0] = s.x - s.w; mn[1] = s.y - s.w; mn[2] = s.z - s.w;       // main.cpp:686-688, as prim_fetch
+        mx[0] = s.x + s.w; mx[1] = s.y + s.w; mx[2] = s.z + s.w;
+    } else prim_fetch(pv, perm[p], c, mn, mx);
+}
 
 struct SahTask {
     int s, e, parent_enc;     // range, parent*2+side (-1 root)
@@ -41,6 +61,7 @@ __global__ void sah_reset(SahTask* tasks, SahBins* bins, int n_tasks, int B)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tasks) return;
+    if (tasks[t].e - tasks[t].s <= SAH_SMALL) return;
     for (int a = 0; a < 3; ++a) { tasks[t].cb[a] = 0xffffffffu; tasks[t].cb[3 + a] = 0u; }
     for (int b = 0; b < B; ++b) {
         bins[t].cnt[b] = 0;
@@ -48,36 +69,39 @@ __global__ void sah_reset(SahTask* tasks, SahBins* bins, int n_tasks, int B)
     }
 }
 
-// Blocks whose 256 positions all belong to ONE task (every block of the upper levels) reduce in registers / shared
-// memory first and touch the task's global words once per block; mixed blocks use the global atomics directly.
-// Both paths are exact (min/max and integer adds are order-independent).
+// Large tasks hold more than SAH_SMALL (>= 2 x 256) consecutive positions and their ids grow with the position, so the 256
+// positions of a block touch at most TWO of them: the smallest and the largest active id. Both get an accumulator in shared
+// memory and the block touches the tasks' global words once per slot - no per-position global atomics. Exact either way
+// (min / max / integer adds are order-independent).
 __global__ void __launch_bounds__(256) sah_centre_bounds(const int* __restrict__ perm, const int* __restrict__ owner, int n, const PrimView pv,
-                                                         SahTask* tasks)
+                                                         const float4* __restrict__ psph, SahTask* tasks)
 {
-    __shared__ int s_first, s_uniform;
-    __shared__ unsigned s_cb[6];
+    __shared__ int s_tmin, s_tmax;
+    __shared__ unsigned s_cb[2][6];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = p < n ? owner[p] : -2;
-    if (threadIdx.x == 0) { s_first = t; s_uniform = 1; for (int a = 0; a < 3; ++a) { s_cb[a] = 0xffffffffu; s_cb[3 + a] = 0u; } }
+    int t = p < n ? owner[p] : -2;
+    if (t >= 0 && tasks[t].e - tasks[t].s <= SAH_SMALL) t = -2;      // small tasks are handled by sah_warp_tasks / sah_small_tasks
+    if (threadIdx.x == 0) { s_tmin = 0x7fffffff; s_tmax = -1; }
+    if (threadIdx.x < 12) s_cb[threadIdx.x / 6][threadIdx.x % 6] = (threadIdx.x % 6) < 3 ? 0xffffffffu : 0u;
     __syncthreads();
-    if (t != s_first && t != -2) s_uniform = 0;
-    __syncthreads();
-    float c[3] = {0, 0, 0}, mn[3], mx[3];
     const bool act = t >= 0;
-    if (act) prim_fetch(pv, perm[p], c, mn, mx);
-    if (s_uniform && s_first >= 0) {
-        unsigned lo[3], hi[3];
-        for (int a = 0; a < 3; ++a) { lo[a] = act ? f2ord(c[a]) : 0xffffffffu; hi[a] = act ? f2ord(c[a]) : 0u; }
-        for (int o = 16; o; o >>= 1)
-            for (int a = 0; a < 3; ++a) { lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o)); hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o)); }
-        if ((threadIdx.x & 31) == 0) for (int a = 0; a < 3; ++a) { atomicMin(&s_cb[a], lo[a]); atomicMax(&s_cb[3 + a], hi[a]); }
-        __syncthreads();
-        if (threadIdx.x < 3) atomicMin(&tasks[s_first].cb[threadIdx.x], s_cb[threadIdx.x]);
-        else if (threadIdx.x < 6) atomicMax(&tasks[s_first].cb[threadIdx.x], s_cb[threadIdx.x]);
-    } else if (act) {
-        unsigned* cb = tasks[t].cb;
-        atomicMin(&cb[0], f2ord(c[0])); atomicMin(&cb[1], f2ord(c[1])); atomicMin(&cb[2], f2ord(c[2]));
-        atomicMax(&cb[3], f2ord(c[0])); atomicMax(&cb[4], f2ord(c[1])); atomicMax(&cb[5], f2ord(c[2]));
+    if (act) { atomicMin(&s_tmin, t); atomicMax(&s_tmax, t); }
+    __syncthreads();
+    if (s_tmax < 0) return;                                          // nothing but small tasks and finished leaves here
+    if (act) {
+        float c[3], mn[3], mx[3];
+        pos_fetch(pv, perm, psph, p, c, mn, mx);
+        unsigned* cb = s_cb[t == s_tmin ? 0 : 1];
+        for (int a = 0; a < 3; ++a) { const unsigned o = f2ord(c[a]); atomicMin(&cb[a], o); atomicMax(&cb[3 + a], o); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const int slot = threadIdx.x / 6, a = threadIdx.x % 6;
+        const int task = slot ? s_tmax : s_tmin;
+        if (slot == 0 || s_tmax != s_tmin) {
+            if (a < 3) { if (s_cb[slot][a] != 0xffffffffu) atomicMin(&tasks[task].cb[a], s_cb[slot][a]); }
+            else atomicMax(&tasks[task].cb[a], s_cb[slot][a]);
+        }
     }
 }
 
@@ -91,50 +115,52 @@ __device__ __forceinline__ int sah_axis(const unsigned cb[6], float& lo, float& 
 }
 
 __global__ void __launch_bounds__(256) sah_binning(const int* __restrict__ perm, const int* __restrict__ owner, int n, const PrimView pv,
-                                                   const SahTask* __restrict__ tasks, SahBins* bins, int* __restrict__ bin_of, int B)
+                                                   const float4* __restrict__ psph, const SahTask* __restrict__ tasks, SahBins* bins,
+                                                   int* __restrict__ bin_of, int B)
 {
-    __shared__ int s_first, s_uniform;
-    __shared__ unsigned s_cnt[MAXB];
-    __shared__ unsigned s_box[MAXB][6];
+    __shared__ int s_tmin, s_tmax;
+    __shared__ unsigned s_cnt[2][MAXB];
+    __shared__ unsigned s_box[2][MAXB][6];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = p < n ? owner[p] : -2;
-    if (threadIdx.x == 0) { s_first = t; s_uniform = 1; }
-    if (threadIdx.x < MAXB) { s_cnt[threadIdx.x] = 0; for (int a = 0; a < 3; ++a) { s_box[threadIdx.x][a] = 0xffffffffu; s_box[threadIdx.x][3 + a] = 0u; } }
-    __syncthreads();
-    if (t != s_first && t != -2) s_uniform = 0;
+    int t = p < n ? owner[p] : -2;
+    if (t >= 0 && tasks[t].e - tasks[t].s <= SAH_SMALL) t = -2;      // small tasks are handled by sah_warp_tasks / sah_small_tasks
+    if (threadIdx.x == 0) { s_tmin = 0x7fffffff; s_tmax = -1; }
+    if (threadIdx.x < 2 * MAXB) {
+        const int slot = threadIdx.x / MAXB, b = threadIdx.x % MAXB;
+        s_cnt[slot][b] = 0;
+        for (int a = 0; a < 3; ++a) { s_box[slot][b][a] = 0xffffffffu; s_box[slot][b][3 + a] = 0u; }
+    }
     __syncthreads();
     const bool act = t >= 0;
-    int b = 0;
-    float c[3], mn[3], mx[3];
+    if (act) { atomicMin(&s_tmin, t); atomicMax(&s_tmax, t); }
+    __syncthreads();
+    if (s_tmax < 0) return;                                          // nothing but small tasks and finished leaves here
     if (act) {
-        prim_fetch(pv, perm[p], c, mn, mx);
+        float c[3], mn[3], mx[3];
+        pos_fetch(pv, perm, psph, p, c, mn, mx);
         float lo, hi;
         int axis = sah_axis(tasks[t].cb, lo, hi);
+        int b = 0;
         if (hi > lo) {
             float k = c[axis];
             b = (int)((float)B * ((k - lo) / (hi - lo)));
             if (b > B - 1) b = B - 1;
         }
         bin_of[p] = b;
-    }
-    if (s_uniform && s_first >= 0) {
-        if (act) {
-            atomicAdd(&s_cnt[b], 1u);
-            atomicMin(&s_box[b][0], f2ord(mn[0])); atomicMin(&s_box[b][1], f2ord(mn[1])); atomicMin(&s_box[b][2], f2ord(mn[2]));
-            atomicMax(&s_box[b][3], f2ord(mx[0])); atomicMax(&s_box[b][4], f2ord(mx[1])); atomicMax(&s_box[b][5], f2ord(mx[2]));
-        }
-        __syncthreads();
-        if (threadIdx.x < B && s_cnt[threadIdx.x]) {
-            SahBins& g = bins[s_first];
-            const int bb = threadIdx.x;
-            atomicAdd(&g.cnt[bb], s_cnt[bb]);
-            for (int a = 0; a < 3; ++a) { atomicMin(&g.box[bb][a], s_box[bb][a]); atomicMax(&g.box[bb][3 + a], s_box[bb][3 + a]); }
-        }
-    } else if (act) {
-        atomicAdd(&bins[t].cnt[b], 1u);
-        unsigned* bx = bins[t].box[b];
+        const int slot = t == s_tmin ? 0 : 1;
+        atomicAdd(&s_cnt[slot][b], 1u);
+        unsigned* bx = s_box[slot][b];
         atomicMin(&bx[0], f2ord(mn[0])); atomicMin(&bx[1], f2ord(mn[1])); atomicMin(&bx[2], f2ord(mn[2]));
         atomicMax(&bx[3], f2ord(mx[0])); atomicMax(&bx[4], f2ord(mx[1])); atomicMax(&bx[5], f2ord(mx[2]));
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * MAXB) {
+        const int slot = threadIdx.x / MAXB, bb = threadIdx.x % MAXB;
+        if (bb < B && s_cnt[slot][bb] && (slot == 0 || s_tmax != s_tmin)) {
+            SahBins& g = bins[slot ? s_tmax : s_tmin];
+            atomicAdd(&g.cnt[bb], s_cnt[slot][bb]);
+            for (int a = 0; a < 3; ++a) { atomicMin(&g.box[bb][a], s_box[slot][bb][a]); atomicMax(&g.box[bb][3 + a], s_box[slot][bb][3 + a]); }
+        }
     }
 }
 
@@ -144,26 +170,19 @@ __device__ __forceinline__ float box_area(const float mn[3], const float mx[3]) 
     return 2 * (dx * dy + dx * dz + dy * dz);
 }
 
-// one thread per task: evaluate the B-1 split planes; has_child[2t], has_child[2t+1] = child is a task (size >= 2)
-__global__ void sah_decide(SahTask* tasks, const SahBins* __restrict__ bins, int n_tasks, int B, int node_base, int* __restrict__ child_flags)
+// the split decision from a task's bins (counts + boxes as ordered uints): first minimum of the binned SAH cost.
+// Backward pass: area and count of the union of bins b..B-1 (32 words of local memory instead of the suffix boxes themselves);
+// forward pass: prefix box in registers, cost(i) = nL * SA(bins 0..i) + nR * SA(bins i+1..B-1).
+__device__ __forceinline__ void sah_decide_core(const unsigned* cnt, const unsigned (*box)[6], int B, int m, int& split_bin, int& nL_out)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tasks) return;
-    SahTask& T = tasks[t];
-    const SahBins& bn = bins[t];
-    float lo, hi;
-    T.axis = sah_axis(T.cb, lo, hi);
-    T.node = node_base + t;
-    const int m = T.e - T.s;
-    // suffix unions
-    float rmn[MAXB][3], rmx[MAXB][3];
+    float rarea[MAXB];
     unsigned rcnt[MAXB];
     float amn[3] = {INFINITY, INFINITY, INFINITY}, amx[3] = {-INFINITY, -INFINITY, -INFINITY};
     unsigned acc = 0;
     for (int b = B - 1; b >= 1; --b) {
-        if (bn.cnt[b]) for (int a = 0; a < 3; ++a) { amn[a] = fminf(amn[a], ord2f(bn.box[b][a])); amx[a] = fmaxf(amx[a], ord2f(bn.box[b][3 + a])); }
-        acc += bn.cnt[b];
-        for (int a = 0; a < 3; ++a) { rmn[b][a] = amn[a]; rmx[b][a] = amx[a]; }
+        if (cnt[b]) for (int a = 0; a < 3; ++a) { amn[a] = fminf(amn[a], ord2f(box[b][a])); amx[a] = fmaxf(amx[a], ord2f(box[b][3 + a])); }
+        acc += cnt[b];
+        rarea[b] = box_area(amn, amx);
         rcnt[b] = acc;
     }
     float lmn[3] = {INFINITY, INFINITY, INFINITY}, lmx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -171,17 +190,132 @@ __global__ void sah_decide(SahTask* tasks, const SahBins* __restrict__ bins, int
     float best = INFINITY;
     int best_i = -1, best_nL = 0;
     for (int i = 0; i < B - 1; ++i) {
-        if (bn.cnt[i]) for (int a = 0; a < 3; ++a) { lmn[a] = fminf(lmn[a], ord2f(bn.box[i][a])); lmx[a] = fmaxf(lmx[a], ord2f(bn.box[i][3 + a])); }
-        nL += bn.cnt[i];
+        if (cnt[i]) for (int a = 0; a < 3; ++a) { lmn[a] = fminf(lmn[a], ord2f(box[i][a])); lmx[a] = fmaxf(lmx[a], ord2f(box[i][3 + a])); }
+        nL += cnt[i];
         unsigned nR = rcnt[i + 1];
         if (nL == 0 || nR == 0) continue;
-        float cost = (float)nL * box_area(lmn, lmx) + (float)nR * box_area(rmn[i + 1], rmx[i + 1]);
+        float cost = (float)nL * box_area(lmn, lmx) + (float)nR * rarea[i + 1];
         if (cost < best) { best = cost; best_i = i; best_nL = (int)nL; }
     }
-    if (best_i < 0) { T.split_bin = -1; T.nL = m / 2; }     // all centres in one bin: positional median of the range
-    else { T.split_bin = best_i; T.nL = best_nL; }
+    if (best_i < 0) { split_bin = -1; nL_out = m / 2; }     // all centres in one bin: positional median of the range
+    else { split_bin = best_i; nL_out = best_nL; }
+}
+
+// one thread per LARGE task: evaluate the B-1 split planes; has_child[2t], has_child[2t+1] = child is a task (size >= 2)
+__global__ void sah_decide(SahTask* tasks, const SahBins* __restrict__ bins, int n_tasks, int B, int node_base, int* __restrict__ child_flags,
+                           int* __restrict__ n_large_next)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    SahTask& T = tasks[t];
+    const int m = T.e - T.s;
+    if (m <= SAH_SMALL) return;
+    const SahBins& bn = bins[t];
+    float lo, hi;
+    T.axis = sah_axis(T.cb, lo, hi);
+    T.node = node_base + t;
+    sah_decide_core(bn.cnt, bn.box, B, m, T.split_bin, T.nL);
     child_flags[2 * t] = T.nL >= 2 ? 1 : 0;
     child_flags[2 * t + 1] = (m - T.nL) >= 2 ? 1 : 0;
+    // the next level's large and medium tasks (n_large_next[0], [1]); tiny children are not counted
+    const int nl = T.nL, nr = m - T.nL;
+    const int large = (nl > SAH_SMALL ? 1 : 0) + (nr > SAH_SMALL ? 1 : 0);
+    const int medium = ((nl > SAH_TINY && nl <= SAH_SMALL) ? 1 : 0) + ((nr > SAH_TINY && nr <= SAH_SMALL) ? 1 : 0);
+    if (large) atomicAdd(n_large_next, large);
+    if (medium) atomicAdd(n_large_next + 1, medium);
+}
+
+// one thread per TINY task (<= SAH_TINY primitives): centre bounds, bins and decision from the task's own primitives - what
+// sah_reset + sah_centre_bounds + sah_binning + sah_decide do for the large ones through global memory
+__global__ void __launch_bounds__(128) sah_small_tasks(SahTask* tasks, int n_tasks, int B, int node_base, const int* __restrict__ perm, const PrimView pv,
+                                                       const float4* __restrict__ psph, int* __restrict__ bin_of, int* __restrict__ child_flags)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    SahTask& T = tasks[t];
+    const int s0 = T.s, m = T.e - T.s;
+    if (m > SAH_TINY) return;
+    unsigned cb[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    for (int p = s0; p < s0 + m; ++p) {
+        float c[3], mn[3], mx[3];
+        pos_fetch(pv, perm, psph, p, c, mn, mx);
+        for (int a = 0; a < 3; ++a) { const unsigned o = f2ord(c[a]); cb[a] = min(cb[a], o); cb[3 + a] = max(cb[3 + a], o); }
+    }
+    for (int a = 0; a < 6; ++a) T.cb[a] = cb[a];
+    float lo, hi;
+    const int axis = sah_axis(cb, lo, hi);
+    unsigned cnt[MAXB];
+    unsigned box[MAXB][6];
+    for (int b = 0; b < B; ++b) { cnt[b] = 0u; for (int a = 0; a < 3; ++a) { box[b][a] = 0xffffffffu; box[b][3 + a] = 0u; } }
+    for (int p = s0; p < s0 + m; ++p) {
+        float c[3], mn[3], mx[3];
+        pos_fetch(pv, perm, psph, p, c, mn, mx);
+        int b = 0;
+        if (hi > lo) {
+            float k = c[axis];
+            b = (int)((float)B * ((k - lo) / (hi - lo)));
+            if (b > B - 1) b = B - 1;
+        }
+        bin_of[p] = b;
+        cnt[b] += 1u;
+        for (int a = 0; a < 3; ++a) { box[b][a] = min(box[b][a], f2ord(mn[a])); box[b][3 + a] = max(box[b][3 + a], f2ord(mx[a])); }
+    }
+    T.axis = axis;
+    T.node = node_base + t;
+    sah_decide_core(cnt, box, B, m, T.split_bin, T.nL);
+    child_flags[2 * t] = T.nL >= 2 ? 1 : 0;
+    child_flags[2 * t + 1] = (m - T.nL) >= 2 ? 1 : 0;
+}
+
+// one WARP per task of SAH_TINY < m <= SAH_SMALL primitives: the lanes stride over the task's primitives, centre bounds by warp
+// reductions, bins by shared-memory atomics (exact: min / max / integer adds), lane 0 decides with the same code
+__global__ void __launch_bounds__(128) sah_warp_tasks(SahTask* tasks, int n_tasks, int B, int node_base, const int* __restrict__ perm, const PrimView pv,
+                                                      const float4* __restrict__ psph, int* __restrict__ bin_of, int* __restrict__ child_flags,
+                                                      int* __restrict__ n_next)
+{
+    __shared__ unsigned s_cnt[4][MAXB];
+    __shared__ unsigned s_box[4][MAXB][6];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 4 + warp;
+    if (t >= n_tasks) return;
+    SahTask& T = tasks[t];
+    const int s0 = T.s, m = T.e - T.s;
+    if (m <= SAH_TINY || m > SAH_SMALL) return;
+    unsigned cb[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    for (int p = s0 + lane; p < s0 + m; p += 32) {
+        float c[3], mn[3], mx[3];
+        pos_fetch(pv, perm, psph, p, c, mn, mx);
+        for (int a = 0; a < 3; ++a) { const unsigned o = f2ord(c[a]); cb[a] = min(cb[a], o); cb[3 + a] = max(cb[3 + a], o); }
+    }
+    for (int a = 0; a < 3; ++a) { cb[a] = __reduce_min_sync(0xffffffffu, cb[a]); cb[3 + a] = __reduce_max_sync(0xffffffffu, cb[3 + a]); }
+    float lo, hi;
+    const int axis = sah_axis(cb, lo, hi);
+    for (int b = lane; b < B; b += 32) { s_cnt[warp][b] = 0u; for (int a = 0; a < 3; ++a) { s_box[warp][b][a] = 0xffffffffu; s_box[warp][b][3 + a] = 0u; } }
+    __syncwarp();
+    for (int p = s0 + lane; p < s0 + m; p += 32) {
+        float c[3], mn[3], mx[3];
+        pos_fetch(pv, perm, psph, p, c, mn, mx);
+        int b = 0;
+        if (hi > lo) {
+            float k = c[axis];
+            b = (int)((float)B * ((k - lo) / (hi - lo)));
+            if (b > B - 1) b = B - 1;
+        }
+        bin_of[p] = b;
+        atomicAdd(&s_cnt[warp][b], 1u);
+        for (int a = 0; a < 3; ++a) { atomicMin(&s_box[warp][b][a], f2ord(mn[a])); atomicMax(&s_box[warp][b][3 + a], f2ord(mx[a])); }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int a = 0; a < 6; ++a) T.cb[a] = cb[a];
+        T.axis = axis;
+        T.node = node_base + t;
+        sah_decide_core(s_cnt[warp], s_box[warp], B, m, T.split_bin, T.nL);
+        child_flags[2 * t] = T.nL >= 2 ? 1 : 0;
+        child_flags[2 * t + 1] = (m - T.nL) >= 2 ? 1 : 0;
+        const int medium = ((T.nL > SAH_TINY) ? 1 : 0) + ((m - T.nL > SAH_TINY) ? 1 : 0);      // its children are at most SAH_SMALL
+        if (medium) atomicAdd(n_next + 1, medium);
+    }
 }
 
 __global__ void sah_left_flags(const int* __restrict__ owner, const int* __restrict__ bin_of, int n, const SahTask* __restrict__ tasks, int* __restrict__ flags)
@@ -200,17 +334,18 @@ __global__ void sah_left_flags(const int* __restrict__ owner, const int* __restr
 // stable partition of every active range + creation of nodes / child tasks / leaf records
 __global__ void sah_scatter(const int* __restrict__ perm, const int* __restrict__ owner, const int* __restrict__ flags, const int* __restrict__ scan,
                             int n, const SahTask* __restrict__ tasks, const int* __restrict__ child_scan, int* __restrict__ perm_next,
-                            int* __restrict__ owner_next, int* __restrict__ leaf_info)
+                            int* __restrict__ owner_next, int* __restrict__ leaf_info, const float4* __restrict__ psph, float4* __restrict__ psph_next)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     int t = owner[p];
-    if (t < 0) { perm_next[p] = perm[p]; owner_next[p] = -1; return; }
+    if (t < 0) { perm_next[p] = perm[p]; owner_next[p] = -1; if (psph) psph_next[p] = psph[p]; return; }
     const SahTask& T = tasks[t];
     const int lefts_before = scan[p] - scan[T.s];
     const bool left = flags[p] != 0;
     const int dst = left ? T.s + lefts_before : T.s + T.nL + ((p - T.s) - lefts_before);
     perm_next[dst] = perm[p];
+    if (psph) psph_next[dst] = psph[p];
     const int m = T.e - T.s;
     const int csize = left ? T.nL : m - T.nL;
     if (csize >= 2) owner_next[dst] = child_scan[2 * t + (left ? 0 : 1)];
@@ -249,10 +384,10 @@ __global__ void sah_finalize_leaves(const int* __restrict__ leaf_info, int n, No
     if (pe & 1) nodes[pe >> 1].right = ~p; else nodes[pe >> 1].left = ~p;
 }
 
-__global__ void sah_init(int* perm, int* owner, int n)
+__global__ void sah_init(int* perm, int* owner, int n, const float4* __restrict__ sph, float4* __restrict__ psph)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { perm[i] = i; owner[i] = n >= 2 ? 0 : -1; }
+    if (i < n) { perm[i] = i; owner[i] = n >= 2 ? 0 : -1; if (psph) psph[i] = sph[i]; }
 }
 
 template <typename T> T* carve(char*& p, size_t count)
@@ -276,6 +411,8 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats*
     size_t bytes = 6 * (((size_t)n * 4 + 255) & ~(size_t)255) + 2 * ((sizeof(SahTask) * max_tasks + 255) & ~(size_t)255) +
                    ((sizeof(SahBins) * max_tasks + 255) & ~(size_t)255) + 4 * ((8 * max_tasks + 255) & ~(size_t)255) + ((size_t)tiles * 4 + 255) +
                    (((size_t)n * 4 + 255) & ~(size_t)255) + 4096;
+    const bool carry = ctx->prim_type == 0;      // sphere records travel with the permutation (pos_fetch)
+    if (carry) bytes += 2 * (((size_t)n * 16 + 255) & ~(size_t)255);
     RTDS_TRY(rtds_ensure_scratch(ctx, bytes));
     char* p = (char*)ctx->d_scratch;
     int* perm[2] = {carve<int>(p, n), carve<int>(p, n)};
@@ -296,11 +433,16 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats*
     rtds_scan::Scanner scanner{ctx, sums, tiles, d_small};
     auto xscan = [&](const int* in, int* out, int m) -> int { return scanner.run(in, out, m, &launches); };
     int* leaf_arr = carve<int>(p, n);   // scene position -> parent*2+side+2 once the position holds a finished leaf
+    float4* psph[2] = {nullptr, nullptr};
+    if (carry) { psph[0] = carve<float4>(p, n); psph[1] = carve<float4>(p, n); }
     RTDS_CUDA(cudaEventRecord(ctx->ev0, s));
     RTDS_CUDA(cudaMemsetAsync(leaf_arr, 0, (size_t)n * 4, s));
-    sah_init<<<G(n), T, 0, s>>>(perm[0], owner[0], n);
+    sah_init<<<G(n), T, 0, s>>>(perm[0], owner[0], n, ctx->d_sph, psph[0]);
     ++launches;
     int cur = 0, n_tasks = n >= 2 ? 1 : 0, node_base = 0, levels = 0;
+    int n_large = n > SAH_SMALL ? 1 : 0;        // tasks of the current level above SAH_SMALL primitives ...
+    int n_medium = (n > SAH_TINY && n <= SAH_SMALL) ? 1 : 0;      // ... and of SAH_TINY < m <= SAH_SMALL
+    int* d_large = d_small + 40;                // both counted for the next level by the deciding kernels
     if (n_tasks) {
         SahTask root;
         memset(&root, 0, sizeof root);
@@ -312,23 +454,37 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats*
     }
     while (n_tasks > 0) {
         SahTask* tk = tasks[cur];
-        sah_reset<<<G(n_tasks), T, 0, s>>>(tk, bins, n_tasks, B);
-        sah_centre_bounds<<<G(n), T, 0, s>>>(perm[cur], owner[cur], n, pv, tk);
-        sah_binning<<<G(n), T, 0, s>>>(perm[cur], owner[cur], n, pv, tk, bins, bin_of, B);
-        sah_decide<<<G(n_tasks), T, 0, s>>>(tk, bins, n_tasks, B, node_base, child_flags);
-        launches += 4;
+        RTDS_CUDA(cudaMemsetAsync(d_large, 0, 2 * sizeof(int), s));
+        if (n_large > 0) {       // tasks above SAH_SMALL primitives: bins in global memory, filled by all their positions
+            sah_reset<<<G(n_tasks), T, 0, s>>>(tk, bins, n_tasks, B);
+            sah_centre_bounds<<<G(n), T, 0, s>>>(perm[cur], owner[cur], n, pv, psph[cur], tk);
+            sah_binning<<<G(n), T, 0, s>>>(perm[cur], owner[cur], n, pv, psph[cur], tk, bins, bin_of, B);
+            sah_decide<<<G(n_tasks), T, 0, s>>>(tk, bins, n_tasks, B, node_base, child_flags, d_large);
+            launches += 4;
+        }
+        if (n_medium > 0) {      // up to SAH_SMALL primitives: one warp each, bins in shared memory
+            sah_warp_tasks<<<(n_tasks + 3) / 4, 128, 0, s>>>(tk, n_tasks, B, node_base, perm[cur], pv, psph[cur], bin_of, child_flags, d_large);
+            launches += 1;
+        }
+        if (n_tasks > n_large + n_medium) {  // up to SAH_TINY primitives: one thread each
+            sah_small_tasks<<<(n_tasks + 127) / 128, 128, 0, s>>>(tk, n_tasks, B, node_base, perm[cur], pv, psph[cur], bin_of, child_flags);
+            launches += 1;
+        }
         RTDS_TRY(xscan(child_flags, child_scan, 2 * n_tasks));
-        int next_tasks = 0;
+        int next_tasks = 0, next_large[2] = {0, 0};
         RTDS_CUDA(cudaMemcpyAsync(&next_tasks, d_small, sizeof(int), cudaMemcpyDeviceToHost, s));
+        RTDS_CUDA(cudaMemcpyAsync(next_large, d_large, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
         sah_left_flags<<<G(n), T, 0, s>>>(owner[cur], bin_of, n, tk, flags);
         ++launches;
         RTDS_TRY(xscan(flags, scan, n));
-        sah_scatter<<<G(n), T, 0, s>>>(perm[cur], owner[cur], flags, scan, n, tk, child_scan, perm[cur ^ 1], owner[cur ^ 1], leaf_arr);
+        sah_scatter<<<G(n), T, 0, s>>>(perm[cur], owner[cur], flags, scan, n, tk, child_scan, perm[cur ^ 1], owner[cur ^ 1], leaf_arr, psph[cur], psph[cur ^ 1]);
         RTDS_CUDA(cudaStreamSynchronize(s));
         sah_make_children<<<G(n_tasks), T, 0, s>>>(tk, n_tasks, child_flags, child_scan, tasks[cur ^ 1], b.nodes, node_base + n_tasks);
         launches += 2;
         node_base += n_tasks;
         n_tasks = next_tasks;
+        n_large = next_large[0];
+        n_medium = next_large[1];
         cur ^= 1;
         ++levels;
         if (levels > 4096) { rtds_set_error("sah build: runaway depth"); return RTDS_ERR_CUDA; }

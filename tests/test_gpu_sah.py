@@ -25,12 +25,16 @@ def clustered_scene(n, seed):
     return sph, mat
 
 
-@pytest.mark.parametrize("scene", ["bunny", "clustered_30000", "dups_4000", "tiny_3", "tiny_2", "tiny_1"])
+@pytest.mark.parametrize("scene", ["bunny", "clustered_30000", "clustered_250000", "dups_4000", "n_513", "n_512", "n_33", "n_32", "tiny_3", "tiny_2", "tiny_1"])
 def test_sah_tree_bit_exact(gpu_ctx, oracle, scene):
     if scene == "bunny":
         sph, mat = T.bunny_scene()
     elif scene == "clustered_30000":
         sph, mat = clustered_scene(30000, 5)
+    elif scene == "clustered_250000":
+        sph, mat = clustered_scene(250000, 8)
+    elif scene in ("n_513", "n_512", "n_33", "n_32"):   # around the warp-per-task / thread-per-task thresholds (512 / 32 primitives, ground included)
+        sph, mat = T.synthetic_scene(int(scene[2:]) - 1, 12)
     elif scene == "dups_4000":
         sph, mat = T.synthetic_scene(4000, 6)
         sph[:4000, :3] = np.round(sph[:4000, :3] / np.float32(2)) * np.float32(2)     # many identical centres: median fallback

@@ -1,0 +1,4 @@
+set -x
+mkdir -p gpurun_out
+timeout 200 python -m pytest tests/test_gpu_sah.py tests/test_gpu_triangles.py -q -m gpu --timeout 60 -x 2>&1 | tail -5
+timeout 200 python tools/build_profile.py 30 sah
