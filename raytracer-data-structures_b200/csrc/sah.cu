@@ -69,40 +69,76 @@ __global__ void sah_reset(SahTask* tasks, SahBins* bins, int n_tasks, int B)
     }
 }
 
-// Large tasks hold more than SAH_SMALL (>= 2 x 256) consecutive positions and their ids grow with the position, so the 256
-// positions of a block touch at most TWO of them: the smallest and the largest active id. Both get an accumulator in shared
-// memory and the block touches the tasks' global words once per slot - no per-position global atomics. Exact either way
-// (min / max / integer adds are order-independent).
+// The kernels of the LARGE tasks (more than SAH_SMALL >= 2 x 256 primitives). A block walks a contiguous SPAN of positions in
+// chunks of 256 and keeps ONE accumulator - for the large task it is currently inside - in shared memory; it touches that task's
+// global words only when the walk leaves the task (or the span ends). A chunk meets at most two large tasks (each covers more
+// than 512 consecutive positions): the one that continues from the chunk before (the smaller id is not required - only that the
+// two are distinct) and the one that starts in it, in this order. With one block per 256 positions the 27,000 blocks of a 7 M
+// build all sent their 112 bin words to the SAME few addresses at the top levels: 0.3 ms per pass of pure same-address atomic
+// traffic. Exact either way (min / max / integer adds are order-independent).
+constexpr int SAH_SPAN_BLOCKS_PER_SM = 8;
+__device__ __forceinline__ void sah_span(int n, int& p_begin, int& p_end)
+{
+    const int chunks = (n + 255) / 256, per = (chunks + gridDim.x - 1) / gridDim.x;
+    p_begin = min((long long)n, (long long)blockIdx.x * per * 256);
+    p_end = min(n, p_begin + per * 256);
+}
+// the large task at the chunk's first active position (it may continue from the chunk before) and the other large task of the
+// chunk, if any (-1 otherwise). All 256 threads call.
+__device__ __forceinline__ void sah_chunk_tasks(bool act, int t, int& first, int& other)
+{
+    __shared__ int s_minpos, s_first, s_other;
+    if (threadIdx.x == 0) { s_minpos = 0x7fffffff; s_first = -1; s_other = -1; }
+    __syncthreads();
+    if (act) atomicMin(&s_minpos, (int)threadIdx.x);
+    __syncthreads();
+    if ((int)threadIdx.x == s_minpos) s_first = t;
+    __syncthreads();
+    if (act && t != s_first) s_other = t;            // every writer writes the same id
+    __syncthreads();
+    first = s_first; other = s_other;
+    __syncthreads();                                 // the three words are reused by the next chunk
+}
+
 __global__ void __launch_bounds__(256) sah_centre_bounds(const int* __restrict__ perm, const int* __restrict__ owner, int n, const PrimView pv,
                                                          const float4* __restrict__ psph, SahTask* tasks)
 {
-    __shared__ int s_tmin, s_tmax;
-    __shared__ unsigned s_cb[2][6];
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    int t = p < n ? owner[p] : -2;
-    if (t >= 0 && tasks[t].e - tasks[t].s <= SAH_SMALL) t = -2;      // small tasks are handled by sah_warp_tasks / sah_small_tasks
-    if (threadIdx.x == 0) { s_tmin = 0x7fffffff; s_tmax = -1; }
-    if (threadIdx.x < 12) s_cb[threadIdx.x / 6][threadIdx.x % 6] = (threadIdx.x % 6) < 3 ? 0xffffffffu : 0u;
+    __shared__ int s_cur;
+    __shared__ unsigned s_cb[6];
+    int p0, p1;
+    sah_span(n, p0, p1);
+    if (threadIdx.x == 0) s_cur = -1;
+    if (threadIdx.x < 6) s_cb[threadIdx.x] = threadIdx.x < 3 ? 0xffffffffu : 0u;
     __syncthreads();
-    const bool act = t >= 0;
-    if (act) { atomicMin(&s_tmin, t); atomicMax(&s_tmax, t); }
-    __syncthreads();
-    if (s_tmax < 0) return;                                          // nothing but small tasks and finished leaves here
-    if (act) {
-        float c[3], mn[3], mx[3];
-        pos_fetch(pv, perm, psph, p, c, mn, mx);
-        unsigned* cb = s_cb[t == s_tmin ? 0 : 1];
-        for (int a = 0; a < 3; ++a) { const unsigned o = f2ord(c[a]); atomicMin(&cb[a], o); atomicMax(&cb[3 + a], o); }
-    }
-    __syncthreads();
-    if (threadIdx.x < 12) {
-        const int slot = threadIdx.x / 6, a = threadIdx.x % 6;
-        const int task = slot ? s_tmax : s_tmin;
-        if (slot == 0 || s_tmax != s_tmin) {
-            if (a < 3) { if (s_cb[slot][a] != 0xffffffffu) atomicMin(&tasks[task].cb[a], s_cb[slot][a]); }
-            else atomicMax(&tasks[task].cb[a], s_cb[slot][a]);
+    auto flush = [&]() {        // all threads; leaves the accumulator empty
+        if (threadIdx.x < 6 && s_cur >= 0) {
+            const unsigned v = s_cb[threadIdx.x];
+            if (threadIdx.x < 3) { if (v != 0xffffffffu) atomicMin(&tasks[s_cur].cb[threadIdx.x], v); }
+            else atomicMax(&tasks[s_cur].cb[threadIdx.x], v);
+            s_cb[threadIdx.x] = threadIdx.x < 3 ? 0xffffffffu : 0u;
+        }
+        __syncthreads();
+    };
+    for (int base = p0; base < p1; base += 256) {
+        const int p = base + threadIdx.x;
+        int t = p < p1 ? owner[p] : -2;
+        if (t >= 0 && tasks[t].e - tasks[t].s <= SAH_SMALL) t = -2;      // small tasks are handled by sah_warp_tasks / sah_small_tasks
+        const bool act = t >= 0;
+        int first, other;
+        sah_chunk_tasks(act, t, first, other);
+        for (int phase = 0; phase < 2; ++phase) {
+            const int task = phase ? other : first;
+            if (task < 0) break;
+            if (s_cur != task) { flush(); if (threadIdx.x == 0) s_cur = task; __syncthreads(); }
+            if (act && t == task) {
+                float c[3], mn[3], mx[3];
+                pos_fetch(pv, perm, psph, p, c, mn, mx);
+                for (int a = 0; a < 3; ++a) { const unsigned o = f2ord(c[a]); atomicMin(&s_cb[a], o); atomicMax(&s_cb[3 + a], o); }
+            }
+            __syncthreads();
         }
     }
+    flush();
 }
 
 __device__ __forceinline__ int sah_axis(const unsigned cb[6], float& lo, float& hi)
@@ -118,50 +154,60 @@ __global__ void __launch_bounds__(256) sah_binning(const int* __restrict__ perm,
                                                    const float4* __restrict__ psph, const SahTask* __restrict__ tasks, SahBins* bins,
                                                    int* __restrict__ bin_of, int B)
 {
-    __shared__ int s_tmin, s_tmax;
-    __shared__ unsigned s_cnt[2][MAXB];
-    __shared__ unsigned s_box[2][MAXB][6];
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    int t = p < n ? owner[p] : -2;
-    if (t >= 0 && tasks[t].e - tasks[t].s <= SAH_SMALL) t = -2;      // small tasks are handled by sah_warp_tasks / sah_small_tasks
-    if (threadIdx.x == 0) { s_tmin = 0x7fffffff; s_tmax = -1; }
-    if (threadIdx.x < 2 * MAXB) {
-        const int slot = threadIdx.x / MAXB, b = threadIdx.x % MAXB;
-        s_cnt[slot][b] = 0;
-        for (int a = 0; a < 3; ++a) { s_box[slot][b][a] = 0xffffffffu; s_box[slot][b][3 + a] = 0u; }
-    }
+    __shared__ int s_cur;
+    __shared__ unsigned s_cnt[MAXB];
+    __shared__ unsigned s_box[MAXB][6];
+    int p0, p1;
+    sah_span(n, p0, p1);
+    if (threadIdx.x == 0) s_cur = -1;
+    if (threadIdx.x < MAXB) { s_cnt[threadIdx.x] = 0; for (int a = 0; a < 3; ++a) { s_box[threadIdx.x][a] = 0xffffffffu; s_box[threadIdx.x][3 + a] = 0u; } }
     __syncthreads();
-    const bool act = t >= 0;
-    if (act) { atomicMin(&s_tmin, t); atomicMax(&s_tmax, t); }
-    __syncthreads();
-    if (s_tmax < 0) return;                                          // nothing but small tasks and finished leaves here
-    if (act) {
-        float c[3], mn[3], mx[3];
-        pos_fetch(pv, perm, psph, p, c, mn, mx);
-        float lo, hi;
-        int axis = sah_axis(tasks[t].cb, lo, hi);
+    auto flush = [&]() {        // all threads; leaves the accumulator empty
+        if (threadIdx.x < B && s_cur >= 0 && s_cnt[threadIdx.x]) {
+            SahBins& g = bins[s_cur];
+            const int bb = threadIdx.x;
+            atomicAdd(&g.cnt[bb], s_cnt[bb]);
+            for (int a = 0; a < 3; ++a) { atomicMin(&g.box[bb][a], s_box[bb][a]); atomicMax(&g.box[bb][3 + a], s_box[bb][3 + a]); }
+        }
+        __syncthreads();
+        if (threadIdx.x < MAXB) { s_cnt[threadIdx.x] = 0; for (int a = 0; a < 3; ++a) { s_box[threadIdx.x][a] = 0xffffffffu; s_box[threadIdx.x][3 + a] = 0u; } }
+        __syncthreads();
+    };
+    for (int base = p0; base < p1; base += 256) {
+        const int p = base + threadIdx.x;
+        int t = p < p1 ? owner[p] : -2;
+        if (t >= 0 && tasks[t].e - tasks[t].s <= SAH_SMALL) t = -2;      // small tasks are handled by sah_warp_tasks / sah_small_tasks
+        const bool act = t >= 0;
+        int first, other;
+        sah_chunk_tasks(act, t, first, other);
+        if (first < 0) continue;
         int b = 0;
-        if (hi > lo) {
-            float k = c[axis];
-            b = (int)((float)B * ((k - lo) / (hi - lo)));
-            if (b > B - 1) b = B - 1;
+        float c[3], mn[3], mx[3];
+        if (act) {
+            pos_fetch(pv, perm, psph, p, c, mn, mx);
+            float lo, hi;
+            int axis = sah_axis(tasks[t].cb, lo, hi);
+            if (hi > lo) {
+                float k = c[axis];
+                b = (int)((float)B * ((k - lo) / (hi - lo)));
+                if (b > B - 1) b = B - 1;
+            }
+            bin_of[p] = b;
         }
-        bin_of[p] = b;
-        const int slot = t == s_tmin ? 0 : 1;
-        atomicAdd(&s_cnt[slot][b], 1u);
-        unsigned* bx = s_box[slot][b];
-        atomicMin(&bx[0], f2ord(mn[0])); atomicMin(&bx[1], f2ord(mn[1])); atomicMin(&bx[2], f2ord(mn[2]));
-        atomicMax(&bx[3], f2ord(mx[0])); atomicMax(&bx[4], f2ord(mx[1])); atomicMax(&bx[5], f2ord(mx[2]));
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * MAXB) {
-        const int slot = threadIdx.x / MAXB, bb = threadIdx.x % MAXB;
-        if (bb < B && s_cnt[slot][bb] && (slot == 0 || s_tmax != s_tmin)) {
-            SahBins& g = bins[slot ? s_tmax : s_tmin];
-            atomicAdd(&g.cnt[bb], s_cnt[slot][bb]);
-            for (int a = 0; a < 3; ++a) { atomicMin(&g.box[bb][a], s_box[slot][bb][a]); atomicMax(&g.box[bb][3 + a], s_box[slot][bb][3 + a]); }
+        for (int phase = 0; phase < 2; ++phase) {
+            const int task = phase ? other : first;
+            if (task < 0) break;
+            if (s_cur != task) { flush(); if (threadIdx.x == 0) s_cur = task; __syncthreads(); }
+            if (act && t == task) {
+                atomicAdd(&s_cnt[b], 1u);
+                unsigned* bx = s_box[b];
+                atomicMin(&bx[0], f2ord(mn[0])); atomicMin(&bx[1], f2ord(mn[1])); atomicMin(&bx[2], f2ord(mn[2]));
+                atomicMax(&bx[3], f2ord(mx[0])); atomicMax(&bx[4], f2ord(mx[1])); atomicMax(&bx[5], f2ord(mx[2]));
+            }
+            __syncthreads();
         }
     }
+    flush();
 }
 
 __device__ __forceinline__ float box_area(const float mn[3], const float mx[3])   // BoxBoundries::SurfaceArea, accelerators.h:122-125
@@ -430,6 +476,7 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats*
     int launches = 0;
     const int T = 256;
     auto G = [&](long long m) { return (unsigned)((m + T - 1) / T); };
+    const unsigned span_grid = std::max(1u, std::min(G(n), (unsigned)(ctx->sm_count * SAH_SPAN_BLOCKS_PER_SM)));      // sah_span: contiguous spans of positions
     rtds_scan::Scanner scanner{ctx, sums, tiles, d_small};
     auto xscan = [&](const int* in, int* out, int m) -> int { return scanner.run(in, out, m, &launches); };
     int* leaf_arr = carve<int>(p, n);   // scene position -> parent*2+side+2 once the position holds a finished leaf
@@ -457,8 +504,8 @@ int rtds_build_sah(rtds_ctx* ctx, const rtds_build_params* bp, rtds_build_stats*
         RTDS_CUDA(cudaMemsetAsync(d_large, 0, 2 * sizeof(int), s));
         if (n_large > 0) {       // tasks above SAH_SMALL primitives: bins in global memory, filled by all their positions
             sah_reset<<<G(n_tasks), T, 0, s>>>(tk, bins, n_tasks, B);
-            sah_centre_bounds<<<G(n), T, 0, s>>>(perm[cur], owner[cur], n, pv, psph[cur], tk);
-            sah_binning<<<G(n), T, 0, s>>>(perm[cur], owner[cur], n, pv, psph[cur], tk, bins, bin_of, B);
+            sah_centre_bounds<<<span_grid, T, 0, s>>>(perm[cur], owner[cur], n, pv, psph[cur], tk);
+            sah_binning<<<span_grid, T, 0, s>>>(perm[cur], owner[cur], n, pv, psph[cur], tk, bins, bin_of, B);
             sah_decide<<<G(n_tasks), T, 0, s>>>(tk, bins, n_tasks, B, node_base, child_flags, d_large);
             launches += 4;
         }
