@@ -83,7 +83,48 @@ def main():
     ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
     for exact in (True, False):
         ctx.render(rt.LBVH, W, H, 2, shadows=1, exact=exact)
+    for sh in (0, 1):
+        ctx.render(rt.LBVH, W, H, 4, shadows=sh)      # materials through the packet kernel (no shadows) / castRay kernel (shadows)
     ctx.frame(sph, mat, rt.LBVH, W, H, 4, mode=rt.MODE_TRUE)      # rtds_frame: overlapped upload + build + render
+    # round 2: scheduling options on device-buffer renders - lpt (block_order_kernel: needs consecutive frames of one geometry),
+    # one CUDA graph per frame, L2 prefetch of the tree; rtds_prepare_frame; the in-process shared frame (flag + wait kernels)
+    import ctypes as C
+    dbuf = C.c_void_p()
+    cudart = C.CDLL("libcudart.so")
+    assert cudart.cudaMalloc(C.byref(dbuf), W * H * 3) == 0
+    ctx.set_option("lpt", 2)
+    for graph, pf in ((0, 0), (0, 1), (1, 0), (1, 1)):
+        ctx.set_option("frame_graph", graph); ctx.set_option("l2_prefetch", pf)
+        for rep in range(3):
+            ctx.render_device(rt.LBVH, ctx.render_params(W, H, 4), dbuf.value)
+            ctx.render_device(rt.LBVH, ctx.render_params(W, H, 1), dbuf.value)
+    ctx.set_option("frame_graph", 0); ctx.set_option("l2_prefetch", 0); ctx.set_option("lpt", 1)
+    for rep in range(8):
+        ctx.render(rt.LBVH, W, H, 4)                  # lpt = 1: baseline / trial frames, then the decision
+    ctx.prepare_frame(ctx.render_params(W, H, 4))
+    ctx.render(rt.LBVH, W, H, 4)
+    other = rt.Rtds(0)
+    other.set_spheres(sph, mat)
+    other.build(rt.LBVH, mode=rt.MODE_TRUE)
+    ctx.shared_frame_create(W, H, 2)
+    other.shared_frame_attach(ctx, 1)
+    for graph in (0, 1):
+        ctx.set_option("frame_graph", graph); other.set_option("frame_graph", graph)
+        for seq in (1 + 2 * graph, 2 + 2 * graph):
+            other.render_shared(rt.LBVH, other.render_params(W, H, 4, rank=1, world=2), seq)
+            ctx.render_shared(rt.LBVH, ctx.render_params(W, H, 4, rank=0, world=2), seq)
+    ctx.shared_frame_read(W, H)
+    other.shared_frame_close(); other.close(); ctx.shared_frame_close()
+    ctx.set_option("frame_graph", 0)
+    # rtds_set_spheres_device (D2D upload)
+    dsph, dmat = C.c_void_p(), C.c_void_p()
+    assert cudart.cudaMalloc(C.byref(dsph), sph.nbytes) == 0 and cudart.cudaMalloc(C.byref(dmat), mat.nbytes) == 0
+    assert cudart.cudaMemcpy(dsph, sph.ctypes.data_as(C.c_void_p), sph.nbytes, 1) == 0 and cudart.cudaMemcpy(dmat, mat.ctypes.data_as(C.c_void_p), mat.nbytes, 1) == 0
+    ctx.set_spheres_device(dsph.value, dmat.value, sph.shape[0])
+    ctx.build(rt.BVH, mode=rt.MODE_SAH)               # SAH: large / warp / thread task kernels all occur at this size
+    ctx.render(rt.BVH, W, H, 4)
+    for pbuf in (dbuf, dsph, dmat):
+        cudart.cudaFree(pbuf)
     # triangles
     rng = np.random.default_rng(3)
     nt = max(200, int(2000 * S))
@@ -94,6 +135,8 @@ def main():
         ctx.build(acc, **kw)
         ctx.render(acc, W, H, 2)
         ctx.trace(acc, rays_o, rays_d, exact=False)
+        ctx.render(acc, W, H, 2, tri_geometric=1)     # the triangle test the reference compiles
+        ctx.trace(acc, rays_o, rays_d, exact=False, tri_geometric=True)
     ctx.render(rt.KDTREE, W, H, 1, kd_closest=1)
     # the cooperative top-level median kernel needs a range > 65,536 objects
     if S >= 1:
