@@ -13,7 +13,7 @@ static thread_local char g_err[1024] = "";
 const RtdsOptionName g_rtds_option_names[] = {
     {"block_order", "RTDS_BLOCK_ORDER", &RtdsOptions::block_order}, {"strip", "RTDS_STRIP", &RtdsOptions::strip},
     {"bands", "RTDS_BANDS", &RtdsOptions::bands}, {"band_ratio", "RTDS_BAND_RATIO", &RtdsOptions::band_ratio},
-    {"packet", "RTDS_PACKET", &RtdsOptions::packet}, {"shadow_packets", "RTDS_SHADOW_PACKETS", &RtdsOptions::shadow_packets}, {"hull", "RTDS_HULL", &RtdsOptions::hull},
+    {"packet", "RTDS_PACKET", &RtdsOptions::packet}, {"hull", "RTDS_HULL", &RtdsOptions::hull},
     {"zerocopy", "RTDS_ZEROCOPY", &RtdsOptions::zerocopy}, {"trace_frame", "RTDS_TRACE_FRAME", &RtdsOptions::trace_frame},
     {"median_small", "RTDS_MEDIAN_SMALL", &RtdsOptions::median_small}, {"median_coop", "RTDS_MEDIAN_COOP", &RtdsOptions::median_coop},
     {"median_debug", "RTDS_MEDIAN_DEBUG", &RtdsOptions::median_debug}, {"node_preorder", "RTDS_NODE_PREORDER", &RtdsOptions::node_preorder},

@@ -29,7 +29,6 @@ struct ShadeParams {
     float     bias;
     int       max_depth;
     int       shadows;
-    int       shadow_packets;      // packet kernel: the four samples' shadow rays towards a light go as one any-hit packet
 };
 
 // powf(x, 25) for x in [0, ~1]: exact-product chain in double, one rounding to float. glibc's powf is
@@ -406,94 +405,6 @@ __device__ __forceinline__ void shade_diffuse_shadowed(const RenderArgs& A, floa
     r = hr; g = hg; b = hb;
 }
 
-// --- shadow rays of a sample packet, four at a time (occluded_packet) ---------------------------------------------------------
-struct HitGeom { float hx, hy, hz, nx, ny, nz; };      // hit point (main.cpp:396) and unit normal turned towards the ray (:398-403)
-__device__ __forceinline__ HitGeom hit_geom(const RenderArgs& A, float dx, float dy, float dz, float tnear, int best_leaf)
-{
-    HitGeom g;
-    g.hx = 0.f + dx * tnear; g.hy = 0.f + dy * tnear; g.hz = 0.f + dz * tnear;
-    raw_normal(0, A.bvh.leaf_sph, nullptr, (size_t)best_leaf, g.hx, g.hy, g.hz, g.nx, g.ny, g.nz);
-    normalize3(g.nx, g.ny, g.nz);
-    if (dx * g.nx + dy * g.ny + dz * g.nz > 0) { g.nx = -g.nx; g.ny = -g.ny; g.nz = -g.nz; }
-    return g;
-}
-// castRay's DIFFUSE_AND_GLOSSY branch (main.cpp:447-494) with the answers of the shadow queries given: bit i of `occ` = light i is
-// occluded. Same arithmetic, same order as shade_diffuse_shadowed.
-__device__ __forceinline__ void shade_diffuse_lit(const ShadeParams& P, float dx, float dy, float dz, const HitGeom& h, float sr, float sg, float sb,
-                                                  unsigned occ, float& r, float& g, float& b)
-{
-    float hr = 0, hg = 0, hb = 0;
-    for (int i = 0; i < P.n_lights; ++i) {
-        const RtdsLight& L = P.lights[i];
-        float lx = L.c[0] - h.hx, ly = L.c[1] - h.hy, lz = L.c[2] - h.hz;
-        normalize3(lx, ly, lz);
-        const float LdotN = fmaxf(0.f, lx * h.nx + ly * h.ny + lz * h.nz);
-        const float lit = (occ >> i & 1u) ? 0.0f : 1.0f;                              // main.cpp:471-472
-        const float ar = (L.le[0] * lit) * LdotN, ag = (L.le[1] * lit) * LdotN, ab = (L.le[2] * lit) * LdotN;
-        const float ix = -lx, iy = -ly, iz = -lz;
-        const float s2 = 2 * (ix * h.nx + iy * h.ny + iz * h.nz);
-        const float qx = ix - h.nx * s2, qy = iy - h.ny * s2, qz = iz - h.nz * s2;
-        const float sp = pow25f(fmaxf(0.f, -(qx * dx + qy * dy + qz * dz)));
-        hr += (ar * (0.815f * 0.8f)) / 2.0f + (L.le[0] * sp) * 0.5f;
-        hg += (ag * (0.235f * 0.8f)) / 2.0f + (L.le[1] * sp) * 0.5f;
-        hb += (ab * (0.031f * 0.8f)) / 2.0f + (L.le[2] * sp) * 0.5f;
-        hr += sr; hg += sg; hb += sb;
-    }
-    r = hr; g = hg; b = hb;
-}
-// the shadow queries of the packet's diffuse hits (bits of `live`) towards every light: occ[j] bit i = ray j is occluded from
-// light i. One any-hit packet per light when the shadow rays share a direction octant, single queries otherwise.
-static __device__ __noinline__ void shadow_packets(const RenderArgs* Ap, const float* dxp, const float* dyp, const float* dzp, const HitGeom* G,
-                                                   unsigned live, unsigned* occ, unsigned* counters /*node_tests, prim_tests, node_visits, rays*/)
-{
-    const RenderArgs& A = *Ap;
-    const float bias = A.shade.bias;
-    Counters cnt = {0, 0, 0, 0};
-    for (int i = 0; i < A.shade.n_lights; ++i) {
-        const RtdsLight& L = A.shade.lights[i];
-        float ox[PK], oy[PK], oz[PK], lx[PK], ly[PK], lz[PK], ix[PK], iy[PK], iz[PK], d2[PK];
-        bool ok = A.bvh.root_ref >= 0;
-        int sx = 0, sy = 0, sz = 0, first = 1;
-#pragma unroll
-        for (int j = 0; j < PK; ++j) {
-            ox[j] = oy[j] = oz[j] = 0.f; lx[j] = ly[j] = 0.f; lz[j] = -1.f; ix[j] = iy[j] = iz[j] = 1.f; d2[j] = 0.f;
-            if (!(live >> j & 1u)) continue;
-            const HitGeom& h = G[j];
-            float vx = L.c[0] - h.hx, vy = L.c[1] - h.hy, vz = L.c[2] - h.hz;            // main.cpp:455-466, as shade_diffuse_shadowed
-            d2[j] = vx * vx + vy * vy + vz * vz;
-            normalize3(vx, vy, vz);
-            const bool front = dxp[j] * h.nx + dyp[j] * h.ny + dzp[j] * h.nz < 0;
-            ox[j] = front ? h.hx + h.nx * bias : h.hx - h.nx * bias;
-            oy[j] = front ? h.hy + h.ny * bias : h.hy - h.ny * bias;
-            oz[j] = front ? h.hz + h.nz * bias : h.hz - h.nz * bias;
-            lx[j] = vx; ly[j] = vy; lz[j] = vz;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix[j]) : "f"(vx));
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy[j]) : "f"(vy));
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz[j]) : "f"(vz));
-            const float amin = fminf(fminf(fabsf(ix[j]), fabsf(iy[j])), fabsf(iz[j])), amax = fmaxf(fmaxf(fabsf(ix[j]), fabsf(iy[j])), fabsf(iz[j]));
-            const int ax = vx < 0, ay = vy < 0, az = vz < 0;
-            if (first) { sx = ax; sy = ay; sz = az; first = 0; }
-            const float len2 = vx * vx + vy * vy + vz * vz;
-            ok = ok && amin > 1e-30f && amax < 1e30f && ax == sx && ay == sy && az == sz && fabsf(len2 - 1.0f) < 1e-3f;
-            cnt.rays++;
-        }
-        unsigned mask = 0u;
-        if (ok) occluded_packet(A.bvh, ox, oy, oz, lx, ly, lz, ix, iy, iz, d2, live, sx, sy, sz, mask, cnt);
-        else {
-#pragma unroll
-            for (int j = 0; j < PK; ++j) {
-                if (!(live >> j & 1u)) continue;
-                const ShadowHit sh = shadow_query_cold(&A.bvh, ox[j], oy[j], oz[j], lx[j], ly[j], lz[j], d2[j]);
-                cnt.node_tests += sh.node_tests; cnt.prim_tests += sh.prim_tests; cnt.node_visits += sh.node_visits;
-                if (sh.occluded) mask |= 1u << j;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < PK; ++j) if (mask >> j & 1u) occ[j] |= 1u << i;
-    }
-    counters[0] = cnt.node_tests; counters[1] = cnt.prim_tests; counters[2] = cnt.node_visits; counters[3] = cnt.rays;
-}
-
 // K10, packet form: one thread per pixel, the pixel's samples traced four at a time by traverse_packet. Ordered
 // (exact = 0) BVH / LBVH traversal of sphere scenes with aa_samples % 4 == 0; everything else uses render_kernel.
 #ifndef RTDS_PK_MINB
@@ -612,43 +523,6 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
             dx[2] = d1.z; dy[2] = d1.w; dz[2] = d2.x; dx[3] = d2.y; dy[3] = d2.z; dz[3] = d2.w;
             cnt.rays += PK;
             trace_packet4<HULL>(A, dx, dy, dz, margin, tnear, best_leaf, cnt);
-            if (SHADOWS && A.shade.shadow_packets) {
-                // the packet's shadow rays towards each light as one any-hit packet (occluded_packet): hit geometry per ray, all
-                // queries, then the shading with the answers - same arithmetic and sample order as the one-ray-at-a-time form below
-                HitGeom G[PK];
-                int obj[PK];
-                unsigned live = 0u, special = 0u, occ[PK] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                for (int j = 0; j < PK; ++j) {
-                    obj[j] = best_leaf[j] >= 0 ? __ldg(A.bvh.prim_order + best_leaf[j]) : -1;
-                    if (obj[j] < 0) continue;
-                    if (MATERIALS && __ldg(&A.mat[obj[j]].w) != 0.0f) { special |= 1u << j; continue; }
-                    G[j] = hit_geom(A, dx[j], dy[j], dz[j], tnear[j], best_leaf[j]);
-                    live |= 1u << j;
-                }
-                if (live) {
-                    unsigned c4[4];
-                    shadow_packets(&A, dx, dy, dz, G, live, occ, c4);
-                    cnt.node_tests += c4[0]; cnt.prim_tests += c4[1]; cnt.node_visits += c4[2]; cnt.rays += c4[3]; shadow_rays += c4[3];
-                }
-#pragma unroll
-                for (int j = 0; j < PK; ++j) {
-                    float r, g, b;
-                    if (obj[j] < 0) { r = A.shade.bg[0]; g = A.shade.bg[1]; b = A.shade.bg[2]; }
-                    else if (special >> j & 1u) {
-                        const MatResult mr = cast_material_cold(&A, dx[j], dy[j], dz[j], tnear[j], obj[j], best_leaf[j]);
-                        cnt.node_tests += mr.node_tests; cnt.prim_tests += mr.prim_tests; cnt.node_visits += mr.node_visits; cnt.rays += mr.rays;
-                        shadow_rays += mr.shadow_rays; secondary_rays += mr.secondary_rays;
-                        r = mr.r; g = mr.g; b = mr.b;
-                    } else {
-                        const float4 m = __ldg(A.mat + obj[j]);
-                        shade_diffuse_lit(A.shade, dx[j], dy[j], dz[j], G[j], m.x, m.y, m.z, occ[j], r, g, b);
-                    }
-                    acc_r += r; acc_g += g; acc_b += b;     // sample order, main.cpp:553-560
-                    last_hit = obj[j];
-                }
-                continue;
-            }
 #pragma unroll
             for (int j = 0; j < PK; ++j) {
                 float r, g, b;
@@ -1501,7 +1375,6 @@ static const void* select_render_kernel(const rtds_ctx* ctx, const RenderArgs& A
     // kernel stays (measured on config 5, 3 shadowed lights, 16 spp: packets 115.9 ms vs 109.7 ms - the shadow rays are 2/3 of
     // the rays there and stay single either way, and the out-of-line shading costs more than the shared primary visits save)
     if (packet && ctx->has_materials && !p->shadows) return (const void*)render_packet_kernel<false, true, true>;
-    if (packet && ctx->has_materials && p->shadows && ctx->opt.shadow_packets) return (const void*)render_packet_kernel<true, true, true>;
     if (ctx->has_materials) packet = false;
     // interior boxes tested once per packet against the hull of the four reciprocal directions (default; hull option 0:
     // once per ray). Bench frame: same frame, node visits 3.17 -> 3.18 per ray, kernel 1.16 -> 0.99 ms.
@@ -1625,7 +1498,6 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.shade.bias = p->bias > 0 ? p->bias : 1e-4f;
     A.shade.max_depth = p->max_depth > 0 ? p->max_depth : 2;
     A.shade.shadows = p->shadows;
-    A.shade.shadow_packets = ctx->opt.shadow_packets;
     const bool full = p->shadows || ctx->has_materials;
     if (full && kdt) { rtds_set_error("render: the KDTREE path traces primary rays only (any-hit and unshaded as main.cpp:362-372, or kd_closest); shadows/materials need BVH, LBVH or NONE"); return RTDS_ERR_UNSUPPORTED; }
     const bool kd_closest = kdt && p->kd_closest;

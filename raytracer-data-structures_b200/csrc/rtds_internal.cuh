@@ -122,7 +122,6 @@ struct RtdsOptions {
     int bands = 4;           // RTDS_BANDS        row bands of a host-buffer render (download overlapped with rendering)
     int band_ratio = 100;    // RTDS_BAND_RATIO   each band's share of the one before it, percent
     int packet = 1;          // RTDS_PACKET       0: never the packet kernels
-    int shadow_packets = 1;  // RTDS_SHADOW_PACKETS  packet kernel with shadows: the four samples' shadow rays towards a light as one any-hit packet
     int hull = 1;            // RTDS_HULL         0: interior boxes tested per ray instead of once per packet
     int zerocopy = 0;        // RTDS_ZEROCOPY     1: store the frame straight into pinned host memory (measured slower)
     int trace_frame = 0;     // RTDS_TRACE_FRAME  1: rtds_frame stage timeline on stderr, 2: + per-band events

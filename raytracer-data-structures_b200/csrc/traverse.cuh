@@ -586,119 +586,6 @@ __device__ __forceinline__ void traverse_packet(const BvhView& B, const float (&
     cnt.prim_tests += prim_tests;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Shadow-ray packet: the shadow queries of the four samples of ONE pixel towards ONE light (main.cpp:468-473), any-hit, walked
-// together. The four origins are the four hit points (a pixel footprint apart), the four directions point at the same light: one
-// node load, one stack and ONE hull test per child serve all four. Arbitrary origins, so the hull is taken over origin AND
-// reciprocal-direction intervals: for an axis on which every ray moves in +direction the entry distance of ray j is
-// (bmin - o_j) * i_j >= min((bmin - o_hi) * i_lo, (bmin - o_hi) * i_hi) and its exit distance (bmax - o_j) * i_j <=
-// max((bmax - o_lo) * i_lo, (bmax - o_lo) * i_hi) (float subtraction and multiplication are monotone; for a -direction axis the
-// roles of bmin / bmax and o_lo / o_hi swap): the hull test accepts every box ANY ray's own conservative test accepts, so each ray
-// still meets every leaf its own any-hit walk could answer from, tests it with its own origin exactly as traverse_fast_loop<.., ANYHIT>
-// does, and drops out of the packet the moment it is occluded. Answer per ray = "some candidate has t0^2 < t2max" = the single
-// query's. Needs a common direction octant and sphere leaves with their own boxes (checked by the caller).
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void occluded_packet(const BvhView& B, const float (&ox)[PK], const float (&oy)[PK], const float (&oz)[PK],
-                                                const float (&dx)[PK], const float (&dy)[PK], const float (&dz)[PK],
-                                                const float (&ix)[PK], const float (&iy)[PK], const float (&iz)[PK], const float (&t2max)[PK],
-                                                unsigned live /*bit j: ray j takes part*/, const int sx, const int sy, const int sz /*1: direction < 0*/,
-                                                unsigned& occluded_mask, Counters& cnt)
-{
-    // per-ray pruning bound and margin; the packet uses the largest of each over the rays still unresolved
-    float tlim[PK], margin = 0.f;
-    float olx = INFINITY, ohx = -INFINITY, oly = INFINITY, ohy = -INFINITY, olz = INFINITY, ohz = -INFINITY;
-    float ilx = INFINITY, ihx = -INFINITY, ily = INFINITY, ihy = -INFINITY, ilz = INFINITY, ihz = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < PK; ++j) {
-        if (!(live >> j & 1u)) { tlim[j] = -INFINITY; continue; }
-        const float m = prune_margin(B.root_box, ox[j], oy[j], oz[j]);
-        margin = fmaxf(margin, m);
-        float tl = sqrtf(t2max[j]) + m;
-        tlim[j] = __fmaf_rn(fabsf(tl), WIDE2, tl);
-        olx = fminf(olx, ox[j]); ohx = fmaxf(ohx, ox[j]); oly = fminf(oly, oy[j]); ohy = fmaxf(ohy, oy[j]); olz = fminf(olz, oz[j]); ohz = fmaxf(ohz, oz[j]);
-        ilx = fminf(ilx, ix[j]); ihx = fmaxf(ihx, ix[j]); ily = fminf(ily, iy[j]); ihy = fmaxf(ihy, iy[j]); ilz = fminf(ilz, iz[j]); ihz = fmaxf(ihz, iz[j]);
-    }
-    float tlim_max = fmaxf(fmaxf(tlim[0], tlim[1]), fmaxf(tlim[2], tlim[3]));
-    const float neg_margin = -margin;
-    // origin to subtract from the near / far plane of each axis (see above)
-    const float onx = sx ? olx : ohx, ofx = sx ? ohx : olx, ony = sy ? oly : ohy, ofy = sy ? ohy : oly, onz = sz ? olz : ohz, ofz = sz ? ohz : olz;
-    int2 stack[STACK_MAX];
-    int sp = 0;
-    int node = 0;
-    unsigned visits = 0, prim_tests = 0;
-    occluded_mask = 0u;
-    while (true) {
-        if (node >= 0) {
-            const float4* q = reinterpret_cast<const float4*>(B.nodes + node);
-            const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-            const int2 ch = __ldg(reinterpret_cast<const int2*>(q + 3));
-            ++visits;
-            // left box {q0.x,q0.y,q0.z | q0.w,q1.x,q1.y}, right box {q1.z,q1.w,q2.x | q2.y,q2.z,q2.w}
-            const float lnx = (sx ? q0.w : q0.x) - onx, lfx = (sx ? q0.x : q0.w) - ofx;
-            const float lny = (sy ? q1.x : q0.y) - ony, lfy = (sy ? q0.y : q1.x) - ofy;
-            const float lnz = (sz ? q1.y : q0.z) - onz, lfz = (sz ? q0.z : q1.y) - ofz;
-            const float rnx = (sx ? q2.y : q1.z) - onx, rfx = (sx ? q1.z : q2.y) - ofx;
-            const float rny = (sy ? q2.z : q1.w) - ony, rfy = (sy ? q1.w : q2.z) - ofy;
-            const float rnz = (sz ? q2.w : q2.x) - onz, rfz = (sz ? q2.x : q2.w) - ofz;
-            const float tminL = fmaxf(fmaxf(fminf(lnx * ilx, lnx * ihx), fminf(lny * ily, lny * ihy)), fminf(lnz * ilz, lnz * ihz));
-            float tmaxL = fminf(fminf(fmaxf(lfx * ilx, lfx * ihx), fmaxf(lfy * ily, lfy * ihy)), fmaxf(lfz * ilz, lfz * ihz));
-            const float tminR = fmaxf(fmaxf(fminf(rnx * ilx, rnx * ihx), fminf(rny * ily, rny * ihy)), fminf(rnz * ilz, rnz * ihz));
-            float tmaxR = fminf(fminf(fmaxf(rfx * ilx, rfx * ihx), fmaxf(rfy * ily, rfy * ihy)), fmaxf(rfz * ilz, rfz * ihz));
-            tmaxL = __fmaf_rn(fabsf(tmaxL), WIDE2, tmaxL);
-            tmaxR = __fmaf_rn(fabsf(tmaxR), WIDE2, tmaxR);
-            const bool hitL = tminL <= fminf(tmaxL, tlim_max) && tmaxL >= neg_margin;
-            const bool hitR = tminR <= fminf(tmaxR, tlim_max) && tmaxR >= neg_margin;
-            if (hitL && hitR) {
-                const bool rfirst = tminR < tminL;
-                stack[sp] = make_int2(rfirst ? ch.x : ch.y, __float_as_int(rfirst ? tminL : tminR));
-                sp = min(sp + 1, STACK_MAX - 1);
-                node = rfirst ? ch.y : ch.x;
-                continue;
-            }
-            if (hitL | hitR) { node = hitL ? ch.x : ch.y; continue; }
-        } else {
-            const int leaf = ~node;
-            const float4 s = __ldg(B.leaf_sph + leaf);
-            const float bx0 = s.x - s.w, by0 = s.y - s.w, bz0 = s.z - s.w, bx1 = s.x + s.w, by1 = s.y + s.w, bz1 = s.z + s.w;
-            const float4 s2 = make_float4(s.x, s.y, s.z, s.w * s.w);
-#pragma unroll
-            for (int j = 0; j < PK; ++j) {
-                if (!(live >> j & 1u)) continue;
-                float tmn, tmx;
-                slab_interval<-1>((bx0 - ox[j]) * ix[j], (by0 - oy[j]) * iy[j], (bz0 - oz[j]) * iz[j], (bx1 - ox[j]) * ix[j], (by1 - oy[j]) * iy[j],
-                                  (bz1 - oz[j]) * iz[j], tmn, tmx);
-                bool pass = __fmaf_rn(fabsf(tmn), NARROW_EPS, tmn) <= __fmaf_rn(-fabsf(tmx), NARROW_EPS, tmx) &&
-                            fminf(fabsf(tmn), fabsf(tmx)) > 1e-30f;
-                if (!pass) pass = slab_test_cold(ox[j], oy[j], oz[j], dx[j], dy[j], dz[j], bx0, by0, bz0, bx1, by1, bz1);
-                if (pass) {
-                    float t0, t1;
-                    ++prim_tests;
-                    if (sphere_test(ox[j], oy[j], oz[j], dx[j], dy[j], dz[j], s2, t0, t1)) {
-                        if (t0 < 0) t0 = t1;
-                        if (t0 * t0 < t2max[j]) { occluded_mask |= 1u << j; live &= ~(1u << j); tlim[j] = -INFINITY; }
-                    }
-                }
-            }
-            if (!live) break;
-            tlim_max = fmaxf(fmaxf(tlim[0], tlim[1]), fmaxf(tlim[2], tlim[3]));
-        }
-        // pop
-        bool found = false;
-        while (sp > 0) {
-            --sp;
-            const int2 e = stack[sp];
-            if (__int_as_float(e.y) > tlim_max) continue;
-            node = e.x;
-            found = true;
-            break;
-        }
-        if (!found) break;
-    }
-    cnt.node_visits += visits;
-    cnt.node_tests += 2 * visits;
-    cnt.prim_tests += prim_tests;
-}
-
 // single-ray fallback of the packet kernel (mixed octants / degenerate directions), out of line
 static __device__ __noinline__ ColdHit trace_primary_cold(const BvhView* B, float dx, float dy, float dz)
 {
