@@ -13,7 +13,7 @@ static thread_local char g_err[1024] = "";
 const RtdsOptionName g_rtds_option_names[] = {
     {"block_order", "RTDS_BLOCK_ORDER", &RtdsOptions::block_order}, {"strip", "RTDS_STRIP", &RtdsOptions::strip},
     {"bands", "RTDS_BANDS", &RtdsOptions::bands}, {"band_ratio", "RTDS_BAND_RATIO", &RtdsOptions::band_ratio},
-    {"packet", "RTDS_PACKET", &RtdsOptions::packet}, {"hull", "RTDS_HULL", &RtdsOptions::hull},
+    {"packet", "RTDS_PACKET", &RtdsOptions::packet}, {"wavefront", "RTDS_WAVEFRONT", &RtdsOptions::wavefront}, {"hull", "RTDS_HULL", &RtdsOptions::hull},
     {"zerocopy", "RTDS_ZEROCOPY", &RtdsOptions::zerocopy}, {"trace_frame", "RTDS_TRACE_FRAME", &RtdsOptions::trace_frame},
     {"median_small", "RTDS_MEDIAN_SMALL", &RtdsOptions::median_small}, {"median_coop", "RTDS_MEDIAN_COOP", &RtdsOptions::median_coop},
     {"median_debug", "RTDS_MEDIAN_DEBUG", &RtdsOptions::median_debug}, {"node_preorder", "RTDS_NODE_PREORDER", &RtdsOptions::node_preorder},
@@ -222,7 +222,7 @@ int rtds_destroy(rtds_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     rtds_free_bvh(c->bvh);
     rtds_free_kd(c->kd);
-    void* bufs[] = {c->d_sph, c->d_mat, c->d_tris, c->d_keys_sorted, c->d_mt_snap, c->d_jitter, c->d_dirs, c->d_block_cost, c->d_block_order, c->d_scratch,
+    void* bufs[] = {c->d_sph, c->d_mat, c->d_tris, c->d_keys_sorted, c->d_mt_snap, c->d_jitter, c->d_dirs, c->d_wave, c->d_block_cost, c->d_block_order, c->d_scratch,
                     c->d_sort_ws, c->d_frame, c->d_hit, c->d_accum, c->d_counters};
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);

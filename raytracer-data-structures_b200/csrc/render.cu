@@ -99,6 +99,8 @@ struct RenderArgs {
     int*     out_hit;            // optional, local rows x width
     float*   out_accum;          // optional, local rows x width x 3
     unsigned long long* counters;
+    float*         wave_t;       // wavefront form (shadows on): per local sample (lrow * width + px) * spp + k, the primary hit's tnear ...
+    int*           wave_leaf;    // ... and leaf (-1: sky), written by wave_primary_kernel, read by wave_shade_kernel
     const int* order;            // optional: launch position -> block id (the previous frame's heaviest blocks first), see block_order_kernel
     unsigned*  cost;             // optional: per block id, the largest per-thread node-visit count of this frame (input of the next frame's order)
 };
@@ -350,8 +352,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
 
 // the shadow query of main.cpp:468-473 for the packet kernel (one ray, any-hit), out of line; same answers as occluded<1>
 struct ShadowHit { int occluded; unsigned node_tests, prim_tests, node_visits; };
-static __device__ __noinline__ ShadowHit shadow_query_cold(const BvhView* B, float ox, float oy, float oz, float dx, float dy, float dz,
-                                                          float dist2)
+__device__ __forceinline__ ShadowHit shadow_query(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz, float dist2)
 {
     Counters c = {0, 0, 0, 0};
     float ts = INFINITY;
@@ -359,16 +360,24 @@ static __device__ __noinline__ ShadowHit shadow_query_cold(const BvhView* B, flo
     const float len2 = dx * dx + dy * dy + dz * dz;
     int occ;
     if (fabsf(len2 - 1.0f) < 1e-3f) {
-        traverse_fast<false, true>(*B, ox, oy, oz, dx, dy, dz, ts, bk, bl, c, dist2);
+        traverse_fast<false, true>(B, ox, oy, oz, dx, dy, dz, ts, bk, bl, c, dist2);
         occ = bl >= 0;
     } else {
-        traverse_bvh_exact(*B, ox, oy, oz, dx, dy, dz, ts, bk, bl, c);
-        occ = bl >= 0 && ts * ts < dist2;
+        const ColdHit h = traverse_exact_cold(&B, ox, oy, oz, dx, dy, dz, ts, bk, bl);
+        c.node_tests = h.node_tests; c.prim_tests = h.prim_tests; c.node_visits = h.node_visits;
+        occ = h.leaf >= 0 && h.tnear * h.tnear < dist2;
     }
     return ShadowHit{occ, c.node_tests, c.prim_tests, c.node_visits};
 }
+static __device__ __noinline__ ShadowHit shadow_query_cold(const BvhView* B, float ox, float oy, float oz, float dx, float dy, float dz,
+                                                          float dist2)
+{
+    return shadow_query(*B, ox, oy, oz, dx, dy, dz, dist2);
+}
 
 // castRay's DIFFUSE_AND_GLOSSY branch with the shadow query evaluated (main.cpp:447-494), as in render_full_kernel
+// COLD: the any-hit traversal out of line (callers that hold a packet's state in registers) or inline (one thread = one sample)
+template <bool COLD = true>
 __device__ __forceinline__ void shade_diffuse_shadowed(const RenderArgs& A, float dx, float dy, float dz, float hx, float hy, float hz,
                                                        float nx, float ny, float nz, float sr, float sg, float sb, float& r, float& g,
                                                        float& b, Counters& cnt, unsigned& shadow_rays)
@@ -389,9 +398,14 @@ __device__ __forceinline__ void shade_diffuse_shadowed(const RenderArgs& A, floa
         const float sz = front ? hz + nz * bias : hz - nz * bias;
         cnt.rays++;
         shadow_rays++;
-        const ShadowHit sh = shadow_query_cold(&A.bvh, sx, sy, sz, lx, ly, lz, dist2);
-        cnt.node_tests += sh.node_tests; cnt.prim_tests += sh.prim_tests; cnt.node_visits += sh.node_visits;
-        const float lit = sh.occluded ? 0.0f : 1.0f;                                   // main.cpp:471-472
+        // the answer only scales the diffuse term by 0 or 1 (main.cpp:471-472), and that term is (Le * lit) * LdotN: for a light
+        // behind the surface (LdotN == 0) both answers give the same float, so the ray is counted but not traced
+        float lit = 1.0f;
+        if (LdotN > 0.f) {
+            const ShadowHit sh = COLD ? shadow_query_cold(&A.bvh, sx, sy, sz, lx, ly, lz, dist2) : shadow_query(A.bvh, sx, sy, sz, lx, ly, lz, dist2);
+            cnt.node_tests += sh.node_tests; cnt.prim_tests += sh.prim_tests; cnt.node_visits += sh.node_visits;
+            lit = sh.occluded ? 0.0f : 1.0f;
+        }
         const float ar = (L.le[0] * lit) * LdotN, ag = (L.le[1] * lit) * LdotN, ab = (L.le[2] * lit) * LdotN;
         const float ix = -lx, iy = -ly, iz = -lz;
         const float s2 = 2 * (ix * nx + iy * ny + iz * nz);
@@ -826,7 +840,9 @@ __device__ __forceinline__ void cast_ray_full(const RenderArgs& A, float dx, flo
                 float sz = front ? hz + nz * bias : hz - nz * bias;
                 cnt.rays++;
                 shadow_rays++;
-                if (occluded<MODE>(A, sx, sy, sz, lx, ly, lz, dist2, cnt)) lit = 0.0f;   // main.cpp:471-472
+                // fast form: a light behind the surface (LdotN == 0) gives the same float for either answer - counted, not traced
+                // (see shade_diffuse_shadowed); the exact and brute-force forms keep the reference's intersection-test counts
+                if ((MODE != 1 || LdotN > 0.f) && occluded<MODE>(A, sx, sy, sz, lx, ly, lz, dist2, cnt)) lit = 0.0f;   // main.cpp:471-472
             }
             const float ar = (L.le[0] * lit) * LdotN, ag = (L.le[1] * lit) * LdotN, ab = (L.le[2] * lit) * LdotN;
             const float ix = -lx, iy = -ly, iz = -lz;
@@ -892,6 +908,162 @@ __global__ void __launch_bounds__(128) render_full_kernel(const __grid_constant_
     }
     store_warp_rgb(A, px, lrow, active, r8, g8, b8);
     report_block_cost(A, lblock, cnt.node_visits + cnt.prim_tests);
+    unsigned v[6] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays, shadow_rays, secondary_rays};
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        unsigned long long x = v[c];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(&A.counters[c], x);
+    }
+}
+
+// ===================================================================================================
+// K10c: castRay with shadow rays as a WAVEFRONT (frames with shadow rays, aa_samples % 4 == 0 and <= 256, sphere leaves). The
+// single-kernel form (render_full_kernel, one thread = one pixel = 16 samples x (1 primary + n_lights shadow rays) one after the
+// other) runs with 12.6 of 32 lanes active on config 5 (ncu, profiles/ncu_r02u_kernels.md): the lanes of a warp are in different
+// phases of different rays. Here the frame is two kernels over the same sample set, each with warps full of like work:
+//   wave_primary_kernel  one thread per pixel, its samples four at a time as packets (traverse_packet): tnear + leaf per sample
+//   wave_shade_kernel    one thread per SAMPLE: the shadow rays of the hit (a warp = 32 consecutive samples - two pixels' worth -
+//                        towards one light at a time: one direction octant, origins a pixel apart), castRay's shading, material
+//                        hits through cast_material_cold; then the block adds each pixel's samples in order (main.cpp:553-560)
+// Same arithmetic per ray as the single-kernel form: identical hit ids, float sums, bytes and ray counts (tests run both).
+// ===================================================================================================
+__global__ void __launch_bounds__(128, RTDS_PK_MINB) wave_primary_kernel(const __grid_constant__ RenderArgs A)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int bx, by;
+    const int lblock = logical_block(A);
+    quadrant_block(lblock, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by, A.block_order);
+    const int px = bx * 16 + (warp & 1) * 8 + (lane & 7);
+    const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
+    Counters cnt = {0, 0, 0, 0};
+    if (px < A.width && lrow < A.local_rows) {
+        const size_t pix = (size_t)global_row_of(A, lrow) * A.width + px, lpix = (size_t)lrow * A.width + px;
+        const float margin = prune_margin(A.bvh.root_box, 0.f, 0.f, 0.f);
+        for (int k0 = 0; k0 < A.spp; k0 += PK) {
+            float dx[PK], dy[PK], dz[PK], tnear[PK];
+            int best_leaf[PK];
+            const float4* dp = reinterpret_cast<const float4*>(A.dirs + 3 * (pix * A.spp + k0));
+            const float4 d0 = __ldcs(dp), d1 = __ldcs(dp + 1), d2 = __ldcs(dp + 2);
+            dx[0] = d0.x; dy[0] = d0.y; dz[0] = d0.z; dx[1] = d0.w; dy[1] = d1.x; dz[1] = d1.y;
+            dx[2] = d1.z; dy[2] = d1.w; dz[2] = d2.x; dx[3] = d2.y; dy[3] = d2.z; dz[3] = d2.w;
+            cnt.rays += PK;
+            trace_packet4<true>(A, dx, dy, dz, margin, tnear, best_leaf, cnt);
+            *reinterpret_cast<float4*>(A.wave_t + lpix * A.spp + k0) = make_float4(tnear[0], tnear[1], tnear[2], tnear[3]);
+            *reinterpret_cast<int4*>(A.wave_leaf + lpix * A.spp + k0) = make_int4(best_leaf[0], best_leaf[1], best_leaf[2], best_leaf[3]);
+        }
+    }
+    report_block_cost(A, lblock, cnt.node_visits + cnt.prim_tests);
+    unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned long long x = v[c];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(&A.counters[c], x);
+    }
+}
+
+// one thread per local sample of the launch's rows [lrow0, local_rows): a block = WAVE_THREADS / spp consecutive pixels; a warp holds 32
+// consecutive samples (two pixels at 16 spp) - like rays, like phases. Each thread finishes its sample's castRay from the stored
+// hit (shadow rays light after light, shading; material hits through cast_material_cold), then the block adds every pixel's
+// samples in sample order (main.cpp:553-560) from shared memory.
+#define WAVE_THREADS 256
+__device__ __forceinline__ int wave_slot(int i) { return i + (i >> 5); }      // padded: a pixel's leader reads stride-spp without bank conflicts
+// the block's pixels: a tw x th tile, tw * th = the largest power of two <= WAVE_THREADS / spp (4 x 4 at 16 spp, 8 x 8 at 4 spp). A
+// square tile, not a run of one scanline: the block's rays then share the nodes they visit through L1 (the lesson of the strip kernel)
+__host__ __device__ __forceinline__ void wave_tile(int spp, int& tw, int& th)
+{
+    int lg = 0;
+    while ((2 << lg) <= WAVE_THREADS / spp) ++lg;
+    tw = 1 << ((lg + 1) / 2);
+    th = (1 << lg) / tw;
+}
+// WARP_SUM (aa_samples = 4, 8, 16 or 32: a pixel's samples sit in one warp): the per-pixel sums go through shuffles, no block barrier -
+// a barrier makes every warp wait for the block's slowest shadow ray (ncu, first version: 31 % of the stall cycles).
+#ifndef RTDS_WAVE_MINB
+#define RTDS_WAVE_MINB 4
+#endif
+template <bool WARP_SUM>
+__global__ void __launch_bounds__(WAVE_THREADS, RTDS_WAVE_MINB) wave_shade_kernel(const __grid_constant__ RenderArgs A)
+{
+    __shared__ float col[WARP_SUM ? 1 : 3][WARP_SUM ? 1 : WAVE_THREADS + WAVE_THREADS / 32];
+    __shared__ int last_obj[WARP_SUM ? 1 : WAVE_THREADS];
+    const int lane = threadIdx.x & 31;
+    int tw, th;
+    wave_tile(A.spp, tw, th);
+    const int ppb = tw * th, tiles_x = (A.width + tw - 1) / tw;
+    const int tile_y = (int)blockIdx.x / tiles_x, tile_x = (int)blockIdx.x - tile_y * tiles_x;
+    const int lp = (int)threadIdx.x / A.spp, k = (int)threadIdx.x - lp * A.spp;
+    const int px = tile_x * tw + (lp & (tw - 1)), lrow = A.lrow0 + tile_y * th + lp / tw;
+    const bool active = lp < ppb && px < A.width && lrow < A.local_rows;
+    Counters cnt = {0, 0, 0, 0};
+    unsigned shadow_rays = 0, secondary_rays = 0;
+    float r = 0.f, g = 0.f, b = 0.f;
+    int obj = -1;
+    if (active) {
+        const size_t gl = ((size_t)lrow * A.width + px) * A.spp + k;
+        const int leaf = __ldcs(A.wave_leaf + gl);
+        if (leaf >= 0) obj = __ldg(A.bvh.prim_order + leaf);
+        if (obj < 0) { r = A.shade.bg[0]; g = A.shade.bg[1]; b = A.shade.bg[2]; }
+        else {
+            const float* dp = A.dirs + 3 * (((size_t)global_row_of(A, lrow) * A.width + px) * A.spp + k);
+            const float dx = __ldcs(dp), dy = __ldcs(dp + 1), dz = __ldcs(dp + 2);
+            const float tnear = __ldcs(A.wave_t + gl);
+            const float4 m = __ldg(A.mat + obj);
+            if (m.w != 0.0f) {
+                const MatResult mr = cast_material_cold(&A, dx, dy, dz, tnear, obj, leaf);
+                cnt.node_tests += mr.node_tests; cnt.prim_tests += mr.prim_tests; cnt.node_visits += mr.node_visits; cnt.rays += mr.rays;
+                shadow_rays += mr.shadow_rays; secondary_rays += mr.secondary_rays;
+                r = mr.r; g = mr.g; b = mr.b;
+            } else {
+                const float hx = 0.f + dx * tnear, hy = 0.f + dy * tnear, hz = 0.f + dz * tnear;     // main.cpp:396
+                float nx, ny, nz;
+                raw_normal(0, A.bvh.leaf_sph, nullptr, (size_t)leaf, hx, hy, hz, nx, ny, nz);
+                shade_diffuse_shadowed<false>(A, dx, dy, dz, hx, hy, hz, nx, ny, nz, m.x, m.y, m.z, r, g, b, cnt, shadow_rays);
+            }
+        }
+    }
+    float acc_r = 0, acc_g = 0, acc_b = 0;
+    int last_hit = -1;
+    bool leader;
+    if (WARP_SUM) {
+        __syncwarp();
+        const int base = lane & ~(A.spp - 1);
+        for (int j = 0; j < A.spp; ++j) {                                       // sample order, main.cpp:553-560
+            acc_r += __shfl_sync(0xffffffffu, r, base + j); acc_g += __shfl_sync(0xffffffffu, g, base + j); acc_b += __shfl_sync(0xffffffffu, b, base + j);
+        }
+        last_hit = __shfl_sync(0xffffffffu, obj, base + A.spp - 1);
+        leader = active && k == 0;
+    } else {
+        const int sl = wave_slot(threadIdx.x);
+        col[0][sl] = r; col[1][sl] = g; col[2][sl] = b;
+        last_obj[threadIdx.x] = obj;
+        __syncthreads();
+        // thread t < ppb now speaks for the tile's pixel t
+        const int qx = tile_x * tw + ((int)threadIdx.x & (tw - 1)), qrow = A.lrow0 + tile_y * th + (int)threadIdx.x / tw;
+        leader = (int)threadIdx.x < ppb && qx < A.width && qrow < A.local_rows;
+        if (leader) {
+            const int s0 = (int)threadIdx.x * A.spp;
+            for (int j = 0; j < A.spp; ++j) {
+                const int sj = wave_slot(s0 + j);
+                acc_r += col[0][sj]; acc_g += col[1][sj]; acc_b += col[2][sj];
+            }
+            last_hit = last_obj[s0 + A.spp - 1];
+        }
+    }
+    if (leader) {
+        const int opx = WARP_SUM ? px : tile_x * tw + ((int)threadIdx.x & (tw - 1));
+        const int orow = WARP_SUM ? lrow : A.lrow0 + tile_y * th + (int)threadIdx.x / tw;
+        const float fs = (float)(unsigned)A.spp;
+        const unsigned char r8 = (unsigned char)(fminf(1.0f, acc_r / fs) * 255);
+        const unsigned char g8 = (unsigned char)(fminf(1.0f, acc_g / fs) * 255);
+        const unsigned char b8 = (unsigned char)(fminf(1.0f, acc_b / fs) * 255);
+        const size_t o = (size_t)orow * A.width + opx;
+        if (A.out_hit) A.out_hit[o] = last_hit;
+        if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
+        const size_t oo = (size_t)(A.out_global_rows ? global_row_of(A, orow) : orow) * A.width + opx;
+        A.out_rgb[3 * oo] = r8; A.out_rgb[3 * oo + 1] = g8; A.out_rgb[3 * oo + 2] = b8;
+    }
     unsigned v[6] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays, shadow_rays, secondary_rays};
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
@@ -1484,6 +1656,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
 
     RenderArgs A;
     A.width = W; A.height = H; A.spp = spp;
+    A.wave_t = nullptr; A.wave_leaf = nullptr;
     A.rank = rank; A.world = world; A.tile_rows = tile_rows; A.lrow0 = 0;
     A.local_rows = rtds_rows_for_rank(H, tile_rows, rank, world);
     { const RayGen G0 = make_raygen(p); A.inv_w = G0.inv_w; A.inv_h = G0.inv_h; A.aspect = G0.aspect; A.angle = G0.angle; }
@@ -1518,7 +1691,23 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     const bool strip = !brute && !full && !kd_closest && !global_rows && spp <= 150 && ctx->opt.strip == 1;
     // One graph launch per frame (frame_graph option) for renders that stay on the device: rtds_render_device and the multi-GPU
     // shared frame. Host-buffer renders keep the banded multi-stream form below (the download overlaps the rendering there).
-    const bool graph_path = ctx->opt.frame_graph != 0 && !on_band && !strip && A.local_rows > 0 && st != nullptr && !d_hit && !d_accum;
+    // frames with shadow rays as a wavefront of two kernels (wave_primary / wave_shade): see K10c
+    const bool wave = full && p->shadows && ctx->opt.wavefront != 0 && ctx->opt.packet != 0 && !kdt && !brute && !p->exact && !strip && spp % PK == 0 && spp <= WAVE_THREADS && A.bvh.leaf_box_prim &&
+                      A.bvh.prim_type == 0 && A.bvh.root_ref >= 0 && A.shade.max_depth >= 1 && ctx->n_lights > 0 && A.local_rows > 0;
+    if (wave) {
+        const size_t n_loc = (size_t)A.local_rows * W * spp;
+        const size_t need = n_loc * (sizeof(float) + sizeof(int)) + 1024;
+        if (ctx->wave_bytes < need) {
+            RTDS_CUDA(cudaStreamSynchronize(s));
+            if (ctx->d_wave) cudaFree(ctx->d_wave);
+            ctx->d_wave = nullptr; ctx->wave_bytes = 0;
+            RTDS_CUDA(cudaMalloc(&ctx->d_wave, need));
+            ctx->wave_bytes = need;
+        }
+        A.wave_t = (float*)ctx->d_wave;
+        A.wave_leaf = (int*)(ctx->d_wave + n_loc * sizeof(float));
+    }
+    const bool graph_path = ctx->opt.frame_graph != 0 && !wave && !on_band && !strip && A.local_rows > 0 && st != nullptr && !d_hit && !d_accum;
     PrefetchArgs PF;
     const bool prefetch = !strip && A.local_rows > 0 && prefetch_plan(ctx, !brute && !kdt, PF);
     if (!graph_path) RTDS_CUDA(cudaEventRecord(ctx->ev0, s));
@@ -1618,7 +1807,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             band_start[n_bands] = total_rows;
         }
         // lpt: every band launch starts with the blocks that were heaviest in the previous frame
-        const void* fn = select_render_kernel(ctx, A, p, full, kdt, brute, kd_closest);
+        const void* fn = wave ? (const void*)wave_primary_kernel : select_render_kernel(ctx, A, p, full, kdt, brute, kd_closest);
         LptBands lb;
         lb.n_bands = n_bands; lb.off[0] = 0;
         for (int bi = 0; bi < n_bands; ++bi) lb.off[bi + 1] = lb.off[bi] + (int)render_grid(ctx, fn, W, std::max(0, band_start[bi + 1] - band_start[bi]));
@@ -1640,6 +1829,14 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             lpt_band_args(ctx, A, lb, bi);
             void* kargs[] = {(void*)&A};
             RTDS_CUDA(cudaLaunchKernel(fn, dim3(lin), block, kargs, 0, s));
+            if (wave) {       // ... followed by the band's shadow rays and shading, one thread per sample
+                int tw, th;
+                wave_tile(spp, tw, th);
+                const unsigned tiles = (unsigned)((W + tw - 1) / tw) * (unsigned)((r1 - r0 + th - 1) / th);
+                const bool warp_sum = spp <= 32 && (spp & (spp - 1)) == 0;
+                RTDS_CUDA(cudaLaunchKernel(warp_sum ? (const void*)wave_shade_kernel<true> : (const void*)wave_shade_kernel<false>, dim3(tiles), dim3(WAVE_THREADS), kargs, 0, s));
+                launches += 1;
+            }
             launches += 1;
             // the kernel-time event goes in BEFORE the band callback: a device->host copy into pageable memory blocks the
             // host, and an event recorded after it would time the copy as well

@@ -122,6 +122,7 @@ struct RtdsOptions {
     int bands = 4;           // RTDS_BANDS        row bands of a host-buffer render (download overlapped with rendering)
     int band_ratio = 100;    // RTDS_BAND_RATIO   each band's share of the one before it, percent
     int packet = 1;          // RTDS_PACKET       0: never the packet kernels
+    int wavefront = 1;       // RTDS_WAVEFRONT    frames with shadow rays (aa_samples % 4 == 0) as three kernels: primary packets, shadow rays, shading
     int hull = 1;            // RTDS_HULL         0: interior boxes tested per ray instead of once per packet
     int zerocopy = 0;        // RTDS_ZEROCOPY     1: store the frame straight into pinned host memory (measured slower)
     int trace_frame = 0;     // RTDS_TRACE_FRAME  1: rtds_frame stage timeline on stderr, 2: + per-band events
@@ -205,6 +206,8 @@ struct rtds_ctx {
     uint8_t* h_pinned = nullptr;     // pinned host staging for D2H of frames
     SharedFrame shared;
     FrameGraph  fg;
+    char*       d_wave = nullptr;         // wavefront form: per-sample primary hits + per-(light, sample) shadow answers
+    size_t      wave_bytes = 0;
     // lpt option: per-block costs of the last frame and the launch order derived from them, band by band (render.cu: block_order_kernel)
     unsigned*   d_block_cost = nullptr;
     int*        d_block_order = nullptr;

@@ -136,3 +136,39 @@ def test_material_scenes_through_the_packet_kernel(gpu_ctx, oracle, acc, shadows
         assert tuple(int(x) for x in oracle.last_ray_counts) == (pk[3]["rays"], pk[3]["shadow_rays"], pk[3]["secondary_rays"])
     finally:
         gpu_ctx.set_lights(np.asarray([[0, 3, 30, 10, 1, 1, 1]], np.float32))
+
+
+@pytest.mark.parametrize("scene", ["materials", "diffuse"])
+@pytest.mark.parametrize("spp", [4, 8])
+def test_wavefront_shadow_frames_equal_the_single_kernel_form(gpu_ctx, oracle, scene, spp):
+    """Frames with shadow rays and aa_samples % 4 == 0 run as a wavefront of three kernels (primary packets -> one thread per
+    (light, sample) shadow ray -> shading): hit ids, float sums, bytes and ray counts must equal the single-kernel forms'
+    (wavefront off: packet kernel with single shadow rays / castRay kernel; packet off: the one-ray-at-a-time kernel) and the CPU
+    restatement's - ragged frame, a rank's interleaved tiles and row bands (a tall frame) included."""
+    sph, mat = T.material_scene(1500, 17, frac_rr=0.15, frac_refl=0.15) if scene == "materials" else T.synthetic_scene(1500, 17)
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.set_lights(LIGHTS3)
+    try:
+        gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+        nodes, order = gpu_ctx.export_bvh()
+        for (W, H) in ((241, 179), (64, 600)):
+            wv = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True, shadows=1)
+            with T.option(gpu_ctx, "wavefront", 0):
+                mk = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True, shadows=1)
+            with T.option(gpu_ctx, "packet", 0):
+                sr = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True, shadows=1)
+            for other in (mk, sr):
+                assert np.array_equal(wv[1], other[1]) and wv[2].tobytes() == other[2].tobytes() and np.array_equal(wv[0], other[0])
+                for k in ("rays", "primary_rays", "shadow_rays", "secondary_rays"):
+                    assert wv[3][k] == other[3][k], k
+            assert wv[3]["kernel_launches"] > mk[3]["kernel_launches"] and wv[3]["shadow_rays"] > 1000
+        W, H = 241, 179
+        wv = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True, shadows=1)
+        rgb_o, hit_o, accum_o, _ = oracle.render_rows(sph, mat, nodes, order, W, H, spp, tie_by_objid=1, lights=LIGHTS3, want_accum=True, shadows=1)
+        assert np.array_equal(wv[1], hit_o) and wv[2].tobytes() == accum_o.tobytes() and np.array_equal(wv[0], rgb_o)
+        assert tuple(int(x) for x in oracle.last_ray_counts) == (wv[3]["rays"], wv[3]["shadow_rays"], wv[3]["secondary_rays"])
+        part = gpu_ctx.render(rt.LBVH, W, H, spp, shadows=1, rank=1, world=3)[0]
+        rows = rt.owned_rows(H, 8, 1, 3)
+        assert np.array_equal(part[rows], wv[0][rows])
+    finally:
+        gpu_ctx.set_lights(np.asarray([[0, 3, 30, 10, 1, 1, 1]], np.float32))
