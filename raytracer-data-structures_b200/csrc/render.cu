@@ -993,8 +993,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, RTDS_WAVE_MINB) wave_shade_kerne
     wave_tile(A.spp, tw, th);
     const int ppb = tw * th, tiles_x = (A.width + tw - 1) / tw;
     const int tile_y = (int)blockIdx.x / tiles_x, tile_x = (int)blockIdx.x - tile_y * tiles_x;
-    const int lp = (int)threadIdx.x / A.spp, k = (int)threadIdx.x - lp * A.spp;
-    const int px = tile_x * tw + (lp & (tw - 1)), lrow = A.lrow0 + tile_y * th + lp / tw;
+    const int lp = WARP_SUM ? (int)threadIdx.x >> (__ffs(A.spp) - 1) : (int)threadIdx.x / A.spp, k = (int)threadIdx.x - lp * A.spp;
+    const int px = tile_x * tw + (lp & (tw - 1)), lrow = A.lrow0 + tile_y * th + (lp >> (__ffs(tw) - 1));
     const bool active = lp < ppb && px < A.width && lrow < A.local_rows;
     Counters cnt = {0, 0, 0, 0};
     unsigned shadow_rays = 0, secondary_rays = 0;
@@ -1064,12 +1064,14 @@ __global__ void __launch_bounds__(WAVE_THREADS, RTDS_WAVE_MINB) wave_shade_kerne
         const size_t oo = (size_t)(A.out_global_rows ? global_row_of(A, orow) : orow) * A.width + opx;
         A.out_rgb[3 * oo] = r8; A.out_rgb[3 * oo + 1] = g8; A.out_rgb[3 * oo + 2] = b8;
     }
+    // per-warp totals fit 32 bits here (one sample per thread): one REDUX per counter, nothing for a warp of sky samples
     unsigned v[6] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays, shadow_rays, secondary_rays};
+    if (__any_sync(0xffffffffu, (v[0] | v[3] | v[4] | v[5]) != 0)) {
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        unsigned long long x = v[c];
-        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0 && x) atomicAdd(&A.counters[c], x);
+        for (int c = 0; c < 6; ++c) {
+            const unsigned x = __reduce_add_sync(0xffffffffu, v[c]);
+            if (lane == 0 && x) atomicAdd(&A.counters[c], (unsigned long long)x);
+        }
     }
 }
 
@@ -1504,6 +1506,35 @@ static int render_frame_graph(rtds_ctx* ctx, const RenderArgs& A, const void* fn
 
 static void lpt_frame_timed(rtds_ctx* ctx, float ms_kernel, bool was_lpt_frame, bool used_order);
 
+// wavefront = 1: the two forms of a frame with shadow rays give the same bytes; which is faster depends on the scene and the frame
+// (config 5 stand-in, 16 samples x 3 lights: wavefront 53.7 ms, single kernel 104.6; bunny x 30 at 4 samples, 1 light: 2.67 vs 1.96).
+// The first WAVE_TRIAL_FRAMES timed frames of a frame geometry alternate (single kernel, wavefront, ...), the best time of each
+// decides. Frames nobody times (no statistics requested) and the time before the decision use the rule samples x lights >= 16.
+constexpr int WAVE_TRIAL_FRAMES = 4;
+static bool wave_choose(rtds_ctx* ctx, const RenderArgs& A, int n_lights, bool timed)
+{
+    ctx->wave_trial = false;
+    if (ctx->opt.wavefront >= 2) return true;
+    const uint64_t key[4] = {((uint64_t)(unsigned)A.width << 32) | (unsigned)A.height, ((uint64_t)(unsigned)A.spp << 32) | (unsigned)n_lights,
+                             ((uint64_t)(unsigned)A.rank << 40) | ((uint64_t)(unsigned)A.world << 20) | (uint64_t)(unsigned)A.tile_rows,
+                             (uint64_t)A.n};
+    if (memcmp(key, ctx->wave_key, sizeof key) != 0) {
+        memcpy(ctx->wave_key, key, sizeof key);
+        ctx->wave_phase = 0; ctx->wave_ms[0] = ctx->wave_ms[1] = 0.f;
+        ctx->wave_use = A.spp * n_lights >= 16;
+    }
+    if (timed && ctx->wave_phase < WAVE_TRIAL_FRAMES) { ctx->wave_trial = true; return (ctx->wave_phase & 1) != 0; }
+    return ctx->wave_use;
+}
+static void wave_frame_timed(rtds_ctx* ctx, float ms_kernel)
+{
+    if (!ctx->wave_trial || !(ms_kernel > 0.f)) return;
+    ctx->wave_trial = false;
+    float& best = ctx->wave_ms[ctx->wave_this_frame ? 1 : 0];
+    best = best > 0.f ? std::min(best, ms_kernel) : ms_kernel;
+    if (++ctx->wave_phase == WAVE_TRIAL_FRAMES) ctx->wave_use = ctx->wave_ms[1] < ctx->wave_ms[0];
+}
+
 // render statistics from the counters the frame left in pinned memory (the stream is already synchronised)
 static int render_stats_out(rtds_ctx* ctx, rtds_render_stats* st, int launches, int rows, bool wait_copies, bool)
 {
@@ -1517,6 +1548,7 @@ static int render_stats_out(rtds_ctx* ctx, rtds_render_stats* st, int launches, 
     st->kernel_launches = launches;
     st->rows = rows;
     st->reserved[0] = (int)(unsigned)c[7];      // shared frame: 1 + the rank the owner timed out on (0 = complete)
+    wave_frame_timed(ctx, st->ms_kernel);
     lpt_frame_timed(ctx, st->ms_kernel, ctx->lpt_active, ctx->lpt_last_used_order);
     ctx->lpt_active = false;
     if (wait_copies) RTDS_CUDA(cudaStreamSynchronize(ctx->copy_stream));
@@ -1692,8 +1724,10 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     // One graph launch per frame (frame_graph option) for renders that stay on the device: rtds_render_device and the multi-GPU
     // shared frame. Host-buffer renders keep the banded multi-stream form below (the download overlaps the rendering there).
     // frames with shadow rays as a wavefront of two kernels (wave_primary / wave_shade): see K10c
-    const bool wave = full && p->shadows && ctx->opt.wavefront != 0 && ctx->opt.packet != 0 && !kdt && !brute && !p->exact && !strip && spp % PK == 0 && spp <= WAVE_THREADS && A.bvh.leaf_box_prim &&
+    bool wave = full && p->shadows && ctx->opt.wavefront != 0 && ctx->opt.packet != 0 && !kdt && !brute && !p->exact && !strip && spp % PK == 0 && spp <= WAVE_THREADS && A.bvh.leaf_box_prim &&
                       A.bvh.prim_type == 0 && A.bvh.root_ref >= 0 && A.shade.max_depth >= 1 && ctx->n_lights > 0 && A.local_rows > 0;
+    if (wave) wave = wave_choose(ctx, A, ctx->n_lights, st != nullptr);
+    ctx->wave_this_frame = wave;
     if (wave) {
         const size_t n_loc = (size_t)A.local_rows * W * spp;
         const size_t need = n_loc * (sizeof(float) + sizeof(int)) + 1024;

@@ -122,7 +122,8 @@ struct RtdsOptions {
     int bands = 4;           // RTDS_BANDS        row bands of a host-buffer render (download overlapped with rendering)
     int band_ratio = 100;    // RTDS_BAND_RATIO   each band's share of the one before it, percent
     int packet = 1;          // RTDS_PACKET       0: never the packet kernels
-    int wavefront = 1;       // RTDS_WAVEFRONT    frames with shadow rays (aa_samples % 4 == 0) as three kernels: primary packets, shadow rays, shading
+    int wavefront = 1;       // RTDS_WAVEFRONT    frames with shadow rays (aa_samples % 4 == 0) as two kernels (primary packets; shadow rays + shading per sample):
+                             //                   0 never, 1 the library times both forms on the first frames of a geometry and keeps the faster, 2 always
     int hull = 1;            // RTDS_HULL         0: interior boxes tested per ray instead of once per packet
     int zerocopy = 0;        // RTDS_ZEROCOPY     1: store the frame straight into pinned host memory (measured slower)
     int trace_frame = 0;     // RTDS_TRACE_FRAME  1: rtds_frame stage timeline on stderr, 2: + per-band events
@@ -206,7 +207,7 @@ struct rtds_ctx {
     uint8_t* h_pinned = nullptr;     // pinned host staging for D2H of frames
     SharedFrame shared;
     FrameGraph  fg;
-    char*       d_wave = nullptr;         // wavefront form: per-sample primary hits + per-(light, sample) shadow answers
+    char*       d_wave = nullptr;         // wavefront form: per-sample primary hits (tnear, leaf)
     size_t      wave_bytes = 0;
     // lpt option: per-block costs of the last frame and the launch order derived from them, band by band (render.cu: block_order_kernel)
     unsigned*   d_block_cost = nullptr;
@@ -219,6 +220,11 @@ struct rtds_ctx {
     bool        lpt_use = true;           // phase 2: the learned order was faster for this geometry
     float       lpt_ms_base = 0.f, lpt_ms_order = 0.f;
     bool        lpt_last_used_order = false;
+    // wavefront = 1: which form of a frame with shadow rays is faster, measured once per frame geometry (render.cu, wave_choose)
+    uint64_t    wave_key[4] = {0, 0, 0, 0};
+    int         wave_phase = 0;
+    bool        wave_use = true, wave_trial = false, wave_this_frame = false;
+    float       wave_ms[2] = {0.f, 0.f};
     cudaEvent_t ev_order_go = nullptr, ev_order_done = nullptr;
     cudaStream_t pf_stream = nullptr;   // tree prefetch into L2 beside the direction kernel (l2_prefetch option, non-graph path)
     cudaEvent_t  ev_pf0 = nullptr, ev_pf1 = nullptr;

@@ -141,8 +141,9 @@ def test_material_scenes_through_the_packet_kernel(gpu_ctx, oracle, acc, shadows
 @pytest.mark.parametrize("scene", ["materials", "diffuse"])
 @pytest.mark.parametrize("spp", [4, 8])
 def test_wavefront_shadow_frames_equal_the_single_kernel_form(gpu_ctx, oracle, scene, spp):
-    """Frames with shadow rays and aa_samples % 4 == 0 run as a wavefront of three kernels (primary packets -> one thread per
-    (light, sample) shadow ray -> shading): hit ids, float sums, bytes and ray counts must equal the single-kernel forms'
+    """Frames with shadow rays and aa_samples % 4 == 0 can run as a wavefront of two kernels (primary packets -> one thread per
+    sample: its shadow rays + shading, per-pixel sums in sample order; wavefront option 2 = always): hit ids, float sums, bytes and
+    ray counts must equal the single-kernel forms'
     (wavefront off: packet kernel with single shadow rays / castRay kernel; packet off: the one-ray-at-a-time kernel) and the CPU
     restatement's - ragged frame, a rank's interleaved tiles and row bands (a tall frame) included."""
     sph, mat = T.material_scene(1500, 17, frac_rr=0.15, frac_refl=0.15) if scene == "materials" else T.synthetic_scene(1500, 17)
@@ -152,7 +153,8 @@ def test_wavefront_shadow_frames_equal_the_single_kernel_form(gpu_ctx, oracle, s
         gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
         nodes, order = gpu_ctx.export_bvh()
         for (W, H) in ((241, 179), (64, 600)):
-            wv = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True, shadows=1)
+            with T.option(gpu_ctx, "wavefront", 2):
+                wv = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True, shadows=1)
             with T.option(gpu_ctx, "wavefront", 0):
                 mk = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True, shadows=1)
             with T.option(gpu_ctx, "packet", 0):
@@ -163,12 +165,37 @@ def test_wavefront_shadow_frames_equal_the_single_kernel_form(gpu_ctx, oracle, s
                     assert wv[3][k] == other[3][k], k
             assert wv[3]["kernel_launches"] > mk[3]["kernel_launches"] and wv[3]["shadow_rays"] > 1000
         W, H = 241, 179
-        wv = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True, shadows=1)
+        with T.option(gpu_ctx, "wavefront", 2):
+            wv = gpu_ctx.render(rt.LBVH, W, H, spp, want_hit=True, want_accum=True, shadows=1)
+            part = gpu_ctx.render(rt.LBVH, W, H, spp, shadows=1, rank=1, world=3)[0]
         rgb_o, hit_o, accum_o, _ = oracle.render_rows(sph, mat, nodes, order, W, H, spp, tie_by_objid=1, lights=LIGHTS3, want_accum=True, shadows=1)
         assert np.array_equal(wv[1], hit_o) and wv[2].tobytes() == accum_o.tobytes() and np.array_equal(wv[0], rgb_o)
         assert tuple(int(x) for x in oracle.last_ray_counts) == (wv[3]["rays"], wv[3]["shadow_rays"], wv[3]["secondary_rays"])
-        part = gpu_ctx.render(rt.LBVH, W, H, spp, shadows=1, rank=1, world=3)[0]
         rows = rt.owned_rows(H, 8, 1, 3)
         assert np.array_equal(part[rows], wv[0][rows])
+    finally:
+        gpu_ctx.set_lights(np.asarray([[0, 3, 30, 10, 1, 1, 1]], np.float32))
+
+
+def test_wavefront_form_is_chosen_by_measurement(gpu_ctx):
+    """wavefront = 1 (default): the first four timed frames of a frame geometry alternate between the two forms (single kernel,
+    wavefront, ...), later frames use the faster one; every frame is the same bytes. aa_samples 12 (not a power of two) goes through
+    the block-sum variant of the per-sample kernel."""
+    sph, mat = T.synthetic_scene(3000, 5)
+    gpu_ctx.set_spheres(sph, mat)
+    gpu_ctx.set_lights(LIGHTS3)
+    try:
+        gpu_ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+        for spp in (8, 12):
+            W, H = 203 + spp, 157
+            with T.option(gpu_ctx, "wavefront", 0):
+                base = gpu_ctx.render(rt.LBVH, W, H, spp, want_accum=True, shadows=1)
+            frames = [gpu_ctx.render(rt.LBVH, W, H, spp, want_accum=True, shadows=1) for _ in range(7)]
+            launches = [f[3]["kernel_launches"] for f in frames]
+            assert launches[0] == launches[2] == base[3]["kernel_launches"] and launches[1] == launches[3] == launches[0] + 1
+            assert len(set(launches[4:])) == 1
+            for f in frames:
+                assert np.array_equal(f[0], base[0]) and f[2].tobytes() == base[2].tobytes()
+                assert f[3]["rays"] == base[3]["rays"] and f[3]["shadow_rays"] == base[3]["shadow_rays"]
     finally:
         gpu_ctx.set_lights(np.asarray([[0, 3, 30, 10, 1, 1, 1]], np.float32))
