@@ -796,7 +796,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1 frame assembly that is TIMED: peer stores (default) or NCCL gather; both are verified")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # at least 10 untimed frames: the library times alternatives on the first frames of a frame geometry and keeps the faster
+    # (block order: 6 frames, wavefront form of shadowed frames: 4) - those trial frames belong to the warm-up, the reported
+    # "warmup" is the number actually run
+    args.warmup = max(args.warmup, 10) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -311,10 +311,31 @@ __device__ __forceinline__ void slab_interval(float x0, float y0, float z0, floa
     }
 }
 
+// Interior boxes of a ray with a non-zero origin (shadow and secondary rays): t = plane * (1/d) + c, ONE FFMA per plane with
+// c = -(o * (1/d)) -/+ w folded in per axis (near planes get c - w, far planes c + w), instead of a subtract, a multiply and a
+// separate widening of the exit distance. w bounds the distance between this t and the reference's fl(fl(plane - o) / d):
+//   t = (plane * i - o * i * (1 + e4)) * (1 + e5), i = (1/d)(1 + e3), |e3| <= 2^-22 (MUFU.RCP), |e4|, |e5| <= 2^-24
+//   |t - (plane - o)/d| <= |plane - o| |i| (2^-22 + 2^-24 + ..) + |o| |i| 2^-24, and the reference's value is within 2^-23 relative
+//   of (plane - o)/d: together < (|plane| + |o|) |i| 2^-21; w = (max |plane| over the root box + |o|) |i| 2^-20 is twice that.
+// Near values only ever decrease and far values only increase, so the test accepts every box the reference's test accepts
+// (interior tests only steer: the candidate criterion is leaf-local, and the leaf test below keeps the subtract form).
+struct RayAffine { float cnx, cny, cnz, cfx, cfy, cfz; };
+__device__ __forceinline__ RayAffine ray_affine(const float rb[6], float ox, float oy, float oz, float ix, float iy, float iz, float& wmax)
+{
+    const float k = 9.53674316e-7f;     // 2^-20
+    const float wx = ((fmaxf(fabsf(rb[0]), fabsf(rb[3])) + fabsf(ox)) * fabsf(ix)) * k;
+    const float wy = ((fmaxf(fabsf(rb[1]), fabsf(rb[4])) + fabsf(oy)) * fabsf(iy)) * k;
+    const float wz = ((fmaxf(fabsf(rb[2]), fabsf(rb[5])) + fabsf(oz)) * fabsf(iz)) * k;
+    const float cx = -(ox * ix), cy = -(oy * iy), cz = -(oz * iz);
+    wmax = fmaxf(fmaxf(wx, wy), wz);
+    // (the roundings of c -/+ w are below 2^-24 of |c| + w, inside the factor of two)
+    return RayAffine{cx - wx, cy - wy, cz - wz, cx + wx, cy + wy, cz + wz};
+}
+
 template <bool ZERO_O, bool ANYHIT, int OCT>
 __device__ __forceinline__ void traverse_fast_loop(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
                                                    float ix, float iy, float iz, float margin, float& tnear, int& best_key,
-                                                   int& best_leaf, Counters& cnt, float t2max)
+                                                   int& best_leaf, Counters& cnt, float t2max, const RayAffine& R)
 {
     const float neg_margin = -margin;
     // a subtree is opened only while its entry distance is <= tlim (kept widened by 2^-20, see above)
@@ -330,21 +351,27 @@ __device__ __forceinline__ void traverse_fast_loop(const BvhView& B, float ox, f
             const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
             const int2 ch = __ldg(reinterpret_cast<const int2*>(q + 3));
             ++visits;
-            float lx0, lx1, ly0, ly1, lz0, lz1, rx0, rx1, ry0, ry1, rz0, rz1;
-            if (ZERO_O) {
-                lx0 = q0.x * ix; ly0 = q0.y * iy; lz0 = q0.z * iz; lx1 = q0.w * ix; ly1 = q1.x * iy; lz1 = q1.y * iz;
-                rx0 = q1.z * ix; ry0 = q1.w * iy; rz0 = q2.x * iz; rx1 = q2.y * ix; ry1 = q2.z * iy; rz1 = q2.w * iz;
-            } else {
-                lx0 = (q0.x - ox) * ix; ly0 = (q0.y - oy) * iy; lz0 = (q0.z - oz) * iz;
-                lx1 = (q0.w - ox) * ix; ly1 = (q1.x - oy) * iy; lz1 = (q1.y - oz) * iz;
-                rx0 = (q1.z - ox) * ix; ry0 = (q1.w - oy) * iy; rz0 = (q2.x - oz) * iz;
-                rx1 = (q2.y - ox) * ix; ry1 = (q2.z - oy) * iy; rz1 = (q2.w - oz) * iz;
-            }
             float tminL, tmaxL, tminR, tmaxR;
-            slab_interval<OCT>(lx0, ly0, lz0, lx1, ly1, lz1, tminL, tmaxL);
-            slab_interval<OCT>(rx0, ry0, rz0, rx1, ry1, rz1, tminR, tmaxR);
-            tmaxL = __fmaf_rn(fabsf(tmaxL), WIDE2, tmaxL);
-            tmaxR = __fmaf_rn(fabsf(tmaxR), WIDE2, tmaxR);
+            if (ZERO_O) {
+                const float lx0 = q0.x * ix, ly0 = q0.y * iy, lz0 = q0.z * iz, lx1 = q0.w * ix, ly1 = q1.x * iy, lz1 = q1.y * iz;
+                const float rx0 = q1.z * ix, ry0 = q1.w * iy, rz0 = q2.x * iz, rx1 = q2.y * ix, ry1 = q2.z * iy, rz1 = q2.w * iz;
+                slab_interval<OCT>(lx0, ly0, lz0, lx1, ly1, lz1, tminL, tmaxL);
+                slab_interval<OCT>(rx0, ry0, rz0, rx1, ry1, rz1, tminR, tmaxR);
+                tmaxL = __fmaf_rn(fabsf(tmaxL), WIDE2, tmaxL);
+                tmaxR = __fmaf_rn(fabsf(tmaxR), WIDE2, tmaxR);
+            } else {
+                // near / far plane of each axis by the octant; widening folded into the constants (RayAffine)
+                const float lxn = (OCT & 1) ? q0.w : q0.x, lxf = (OCT & 1) ? q0.x : q0.w;
+                const float lyn = (OCT & 2) ? q1.x : q0.y, lyf = (OCT & 2) ? q0.y : q1.x;
+                const float lzn = (OCT & 4) ? q1.y : q0.z, lzf = (OCT & 4) ? q0.z : q1.y;
+                const float rxn = (OCT & 1) ? q2.y : q1.z, rxf = (OCT & 1) ? q1.z : q2.y;
+                const float ryn = (OCT & 2) ? q2.z : q1.w, ryf = (OCT & 2) ? q1.w : q2.z;
+                const float rzn = (OCT & 4) ? q2.w : q2.x, rzf = (OCT & 4) ? q2.x : q2.w;
+                tminL = fmaxf(fmaxf(__fmaf_rn(lxn, ix, R.cnx), __fmaf_rn(lyn, iy, R.cny)), __fmaf_rn(lzn, iz, R.cnz));
+                tmaxL = fminf(fminf(__fmaf_rn(lxf, ix, R.cfx), __fmaf_rn(lyf, iy, R.cfy)), __fmaf_rn(lzf, iz, R.cfz));
+                tminR = fmaxf(fmaxf(__fmaf_rn(rxn, ix, R.cnx), __fmaf_rn(ryn, iy, R.cny)), __fmaf_rn(rzn, iz, R.cnz));
+                tmaxR = fminf(fminf(__fmaf_rn(rxf, ix, R.cfx), __fmaf_rn(ryf, iy, R.cfy)), __fmaf_rn(rzf, iz, R.cfz));
+            }
             const bool hitL = tminL <= fminf(tmaxL, tlim) && tmaxL >= neg_margin;
             const bool hitR = tminR <= fminf(tmaxR, tlim) && tmaxR >= neg_margin;
             if (hitL && hitR) {
@@ -421,8 +448,11 @@ __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float 
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(dy));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(dz));
     const float amin = fminf(fminf(fabsf(ix), fabsf(iy)), fabsf(iz)), amax = fmaxf(fmaxf(fabsf(ix), fabsf(iy)), fabsf(iz));
-    if (B.root_ref < 0 || !(amin > 1e-30f && amax < 1e30f)) {
-        // single-leaf tree, or a zero / tiny / huge / non-finite direction component: the divide-based traversal
+    RayAffine R = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float wmax = 0.f;
+    if (!ZERO_O) R = ray_affine(B.root_box, ox, oy, oz, ix, iy, iz, wmax);
+    if (B.root_ref < 0 || !(amin > 1e-30f && amax < 1e30f) || !(wmax < 1e30f)) {
+        // single-leaf tree, or a zero / tiny / huge / non-finite direction component (or products out of range): the divide-based traversal
         const ColdHit h = traverse_exact_cold(&B, ox, oy, oz, dx, dy, dz, tnear, best_key, best_leaf);
         tnear = h.tnear; best_key = h.key; best_leaf = h.leaf;
         cnt.node_tests += h.node_tests; cnt.prim_tests += h.prim_tests; cnt.node_visits += h.node_visits;
@@ -434,7 +464,7 @@ __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float 
     // first interior visit.
     const float margin = prune_margin(B.root_box, ox, oy, oz);
     const int oct = (dx < 0 ? 1 : 0) | (dy < 0 ? 2 : 0) | ((ZNEG || dz < 0) ? 4 : 0);
-#define RTDS_OCT_CASE(o) case o: traverse_fast_loop<ZERO_O, ANYHIT, o>(B, ox, oy, oz, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt, t2max); break;
+#define RTDS_OCT_CASE(o) case o: traverse_fast_loop<ZERO_O, ANYHIT, o>(B, ox, oy, oz, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt, t2max, R); break;
     switch (oct) {
         RTDS_OCT_CASE(4) RTDS_OCT_CASE(5) RTDS_OCT_CASE(6) RTDS_OCT_CASE(7)
         default:
