@@ -647,7 +647,7 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         alg_bytes = 32.0 * mine[0].item() + 16.0 * mine[1].item() + 16.0 * mine[2].item()   # this rank's launch, SURVEY 8d
         alg_gbs = alg_bytes / (k_ms * 1e-3) / 1e9
-        kernel_name = {"config3": "render_packet_kernel<0,1>", "config4": "render_kernel<1>", "config5": "render_full_kernel<1>"}[wl.key]
+        kernel_name = {"config3": "render_packet_kernel<0,1>", "config4": "render_kernel<1>", "config5": "wave_primary_kernel + wave_shade_kernel<true> (the frame's two kernels; ncu figures: wave_shade_kernel, the longer one)"}[wl.key]
         ncu = {}
         tpath = os.path.join(ROOT, "profiles", f"render_kernel_traffic_{wl.key}.json")
         if os.path.exists(tpath):
@@ -669,7 +669,7 @@ def run_ours(args):
                                "what": "bytes that must cross HBM per launch: 12 B/ray directions in + 3 B/pixel out + the tree once"},
                 "ncu": {k: ncu.get(k) for k in ("kernel", "issue_active_pct", "warps_active_pct", "thread_inst_per_warp_inst", "l1tex_hit_pct", "lts_hit_pct",
                                                 "pipe_alu_pct", "pipe_fma_pct", "l1tex_throughput_pct", "lts_throughput_pct", "dram_throughput_pct",
-                                                "gpu_time_us_under_ncu", "source")} if ncu else None}
+                                                "gpu_time_us_under_ncu", "frame_kernels", "source")} if ncu else None}
         if ncu.get("issue_active_pct") is not None:
             # The traversal kernels are NOT bound by HBM (ncu: DRAM at a few % of peak, the tree is served from L1/L2); what binds
             # them is the issue rate / latency. bound and frac say so: issue slots busy, from the committed ncu capture of this kernel.

@@ -421,6 +421,11 @@ __device__ __forceinline__ void shade_diffuse_shadowed(const RenderArgs& A, floa
 
 // K10, packet form: one thread per pixel, the pixel's samples traced four at a time by traverse_packet. Ordered
 // (exact = 0) BVH / LBVH traversal of sphere scenes with aa_samples % 4 == 0; everything else uses render_kernel.
+#ifndef RTDS_PK_THREADS
+#define RTDS_PK_THREADS 128   // block of the packet kernels: a 16 x (RTDS_PK_THREADS / 16) pixel tile, one 8 x 4 sub-tile per warp (128 or 64).
+                              // Measured (bench frame, same registers): 128 x 6 blocks 0.947 ms, 64 x 12 0.971, 64 x 10 0.994
+#endif
+constexpr int PK_TILE_H = RTDS_PK_THREADS / 16;
 #ifndef RTDS_PK_MINB
 #define RTDS_PK_MINB 6   // measured on B200: 4 blocks (112 regs) 1.40 ms, 5 (96) 1.245, 6 (80, 188 B spilled) 1.223, 8 (64) 1.238
 #endif
@@ -504,7 +509,7 @@ template <bool SHADOWS /*evaluate the shadow query (extension; the reference's t
           bool HULL /*interior boxes tested once per packet against the hull of the four reciprocal directions*/,
           bool MATERIALS = false /*the scene holds REFLECTION_AND_REFRACTION / REFLECTION primitives: rays that hit one continue
                                    through castRay's material branches (single rays, out of line); diffuse hits are shaded as always*/>
-__global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const __grid_constant__ RenderArgs A)
+__global__ void __launch_bounds__(RTDS_PK_THREADS, RTDS_PK_MINB) render_packet_kernel(const __grid_constant__ RenderArgs A)
 {
 #ifdef RTDS_BLOCK_TIMING
     unsigned long long bt0 = 0;
@@ -514,9 +519,9 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) render_packet_kernel(const 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int bx, by;
     const int lblock = logical_block(A);
-    quadrant_block(lblock, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by, A.block_order);
+    quadrant_block(lblock, (A.width + 15) / 16, (A.local_rows - A.lrow0 + PK_TILE_H - 1) / PK_TILE_H, bx, by, A.block_order);
     const int px = bx * 16 + (warp & 1) * 8 + (lane & 7);
-    const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const int lrow = A.lrow0 + by * PK_TILE_H + (warp >> 1) * 4 + (lane >> 3);
     const bool active = px < A.width && lrow < A.local_rows;
     Counters cnt = {0, 0, 0, 0};
     unsigned char r8 = 0, g8 = 0, b8 = 0;
@@ -918,7 +923,7 @@ __global__ void __launch_bounds__(128) render_full_kernel(const __grid_constant_
 }
 
 // ===================================================================================================
-// K10c: castRay with shadow rays as a WAVEFRONT (frames with shadow rays, aa_samples % 4 == 0 and <= 256, sphere leaves). The
+// K10c: castRay with shadow rays as a WAVEFRONT (frames with shadow rays, aa_samples % 4 == 0 and <= 128, sphere leaves). The
 // single-kernel form (render_full_kernel, one thread = one pixel = 16 samples x (1 primary + n_lights shadow rays) one after the
 // other) runs with 12.6 of 32 lanes active on config 5 (ncu, profiles/ncu_r02u_kernels.md): the lanes of a warp are in different
 // phases of different rays. Here the frame is two kernels over the same sample set, each with warps full of like work:
@@ -928,14 +933,14 @@ __global__ void __launch_bounds__(128) render_full_kernel(const __grid_constant_
 //                        hits through cast_material_cold; then the block adds each pixel's samples in order (main.cpp:553-560)
 // Same arithmetic per ray as the single-kernel form: identical hit ids, float sums, bytes and ray counts (tests run both).
 // ===================================================================================================
-__global__ void __launch_bounds__(128, RTDS_PK_MINB) wave_primary_kernel(const __grid_constant__ RenderArgs A)
+__global__ void __launch_bounds__(RTDS_PK_THREADS, RTDS_PK_MINB) wave_primary_kernel(const __grid_constant__ RenderArgs A)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int bx, by;
     const int lblock = logical_block(A);
-    quadrant_block(lblock, (A.width + 15) / 16, (A.local_rows - A.lrow0 + 7) / 8, bx, by, A.block_order);
+    quadrant_block(lblock, (A.width + 15) / 16, (A.local_rows - A.lrow0 + PK_TILE_H - 1) / PK_TILE_H, bx, by, A.block_order);
     const int px = bx * 16 + (warp & 1) * 8 + (lane & 7);
-    const int lrow = A.lrow0 + by * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const int lrow = A.lrow0 + by * PK_TILE_H + (warp >> 1) * 4 + (lane >> 3);
     Counters cnt = {0, 0, 0, 0};
     if (px < A.width && lrow < A.local_rows) {
         const size_t pix = (size_t)global_row_of(A, lrow) * A.width + px, lpix = (size_t)lrow * A.width + px;
@@ -963,13 +968,18 @@ __global__ void __launch_bounds__(128, RTDS_PK_MINB) wave_primary_kernel(const _
     }
 }
 
-// one thread per local sample of the launch's rows [lrow0, local_rows): a block = WAVE_THREADS / spp consecutive pixels; a warp holds 32
+// one thread per local sample of the launch's rows [lrow0, local_rows): a block = a small tile of pixels (wave_tile); a warp holds 32
 // consecutive samples (two pixels at 16 spp) - like rays, like phases. Each thread finishes its sample's castRay from the stored
-// hit (shadow rays light after light, shading; material hits through cast_material_cold), then the block adds every pixel's
-// samples in sample order (main.cpp:553-560) from shared memory.
-#define WAVE_THREADS 256
+// hit (shadow rays light after light, shading; material hits through cast_material_cold), then every pixel's samples are added in
+// sample order (main.cpp:553-560): warp shuffles, or shared memory when aa_samples is not 4, 8, 16 or 32.
+// block size x resident blocks, measured on config 5's stand-in (whole frame, ms): 256x4 50.5, 256x6 48.0, 128x8 48.8, 128x10 46.5,
+// 128x12 48.3, 128x16 64.3, 64x16 48.6, 64x20 46.7, 32x32 49.4 - small blocks (a block leaves when its slowest ray is done) and 40
+// warps per SM (48 registers, some spilled) win
+#ifndef WAVE_THREADS
+#define WAVE_THREADS 128
+#endif
 __device__ __forceinline__ int wave_slot(int i) { return i + (i >> 5); }      // padded: a pixel's leader reads stride-spp without bank conflicts
-// the block's pixels: a tw x th tile, tw * th = the largest power of two <= WAVE_THREADS / spp (4 x 4 at 16 spp, 8 x 8 at 4 spp). A
+// the block's pixels: a tw x th tile, tw * th = the largest power of two <= WAVE_THREADS / spp (4 x 2 at 16 spp, 8 x 4 at 4 spp). A
 // square tile, not a run of one scanline: the block's rays then share the nodes they visit through L1 (the lesson of the strip kernel)
 __host__ __device__ __forceinline__ void wave_tile(int spp, int& tw, int& th)
 {
@@ -981,7 +991,7 @@ __host__ __device__ __forceinline__ void wave_tile(int spp, int& tw, int& th)
 // WARP_SUM (aa_samples = 4, 8, 16 or 32: a pixel's samples sit in one warp): the per-pixel sums go through shuffles, no block barrier -
 // a barrier makes every warp wait for the block's slowest shadow ray (ncu, first version: 31 % of the stall cycles).
 #ifndef RTDS_WAVE_MINB
-#define RTDS_WAVE_MINB 4
+#define RTDS_WAVE_MINB 10
 #endif
 template <bool WARP_SUM>
 __global__ void __launch_bounds__(WAVE_THREADS, RTDS_WAVE_MINB) wave_shade_kernel(const __grid_constant__ RenderArgs A)
@@ -1403,6 +1413,7 @@ static bool same_bytes(std::vector<unsigned char>& last, const void* now, size_t
 }
 
 // frame_graph option: the whole frame as one graph launch on ctx->stream (see FrameGraph). The caller synchronises.
+static unsigned render_threads(const void* fn);
 static int render_frame_graph(rtds_ctx* ctx, const RenderArgs& A, const void* fn, unsigned lin, const DirsLaunch* DL, const PrefetchArgs* PF,
                               bool shared, uint32_t seq, int* launches)
 {
@@ -1449,7 +1460,7 @@ static int render_frame_graph(rtds_ctx* ctx, const RenderArgs& A, const void* fn
         }
         RTDS_CUDA(cudaGraphAddEventRecordNode(&n_ev2, g.graph, pre.data(), pre.size(), ctx->ev2));
         {
-            cudaKernelNodeParams kp = kparams(fn, lin, 128, a_render);
+            cudaKernelNodeParams kp = kparams(fn, lin, render_threads(fn), a_render);
             RTDS_CUDA(cudaGraphAddKernelNode(&g.k_render, g.graph, &n_ev2, 1, &kp));
         }
         RTDS_CUDA(cudaGraphAddEventRecordNode(&n_ev3, g.graph, &g.k_render, 1, ctx->ev3));
@@ -1476,7 +1487,7 @@ static int render_frame_graph(rtds_ctx* ctx, const RenderArgs& A, const void* fn
         ++g.rebuilds;
     } else {
         if (!same_bytes(g.last_render, &A, sizeof A) || g.grid_render != lin) {
-            cudaKernelNodeParams kp = kparams(fn, lin, 128, a_render);
+            cudaKernelNodeParams kp = kparams(fn, lin, render_threads(fn), a_render);
             RTDS_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.k_render, &kp));
             g.grid_render = lin;
         }
@@ -1556,9 +1567,17 @@ static int render_stats_out(rtds_ctx* ctx, rtds_render_stats* st, int launches, 
 }
 
 // grid of a render kernel over `rows` local rows: one block per 16 x 8 pixels, quadrant-major linear order
-static unsigned render_grid(rtds_ctx*, const void*, int W, int rows)
+static bool is_packet_fn(const void* fn)
 {
-    return (unsigned)((W + 15) / 16) * (unsigned)((rows + 7) / 8);
+    return fn == (const void*)render_packet_kernel<false, false> || fn == (const void*)render_packet_kernel<false, true> ||
+           fn == (const void*)render_packet_kernel<true, false> || fn == (const void*)render_packet_kernel<true, true> ||
+           fn == (const void*)render_packet_kernel<false, true, true> || fn == (const void*)wave_primary_kernel;
+}
+static unsigned render_threads(const void* fn) { return is_packet_fn(fn) ? RTDS_PK_THREADS : 128; }
+static unsigned render_grid(rtds_ctx*, const void* fn, int W, int rows)
+{
+    const int th = is_packet_fn(fn) ? PK_TILE_H : 8;
+    return (unsigned)((W + 15) / 16) * (unsigned)((rows + th - 1) / th);
 }
 
 // Which render kernel serves this frame (all take one RenderArgs; grid = quadrant-major linear grid of 16 x 8-pixel blocks).
@@ -1858,7 +1877,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
                 s = ctx->band_streams[bi];
                 RTDS_CUDA(cudaStreamWaitEvent(s, ctx->ev_ready, 0));
             }
-            const dim3 block(128);
+            const dim3 block(render_threads(fn));
             const unsigned lin = render_grid(ctx, fn, W, r1 - r0);
             lpt_band_args(ctx, A, lb, bi);
             void* kargs[] = {(void*)&A};

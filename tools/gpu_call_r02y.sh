@@ -1,4 +1,9 @@
 set -x
 mkdir -p gpurun_out
-WORKLOAD=config5 ITERS=4 timeout 900 ncu --set full --import-source on --clock-control none -k regex:wave -s 2 -c 2 -o gpurun_out/r02y_wave_c5 -f python tools/ab_frame.py wavefront=2 > gpurun_out/r02y_ncu.log 2>&1
-tail -3 gpurun_out/r02y_ncu.log
+cd raytracer-data-structures_b200/csrc
+for v in "128 6" "64 12" "64 10" "32 24"; do
+  set -- $v
+  touch render.cu
+  make -j16 EXTRA="-DRTDS_PK_THREADS=$1 -DRTDS_PK_MINB=$2" 2>&1 | grep -E "error" -A3
+  (cd ../..; echo "== PK_THREADS=$1 MINB=$2"; ITERS=12 timeout 600 python tools/ab_frame.py lpt=1 2>&1 | cut -c1-200 | head -1; WORLD=8 ITERS=10 timeout 600 python tools/ab_frame.py lpt=1 2>&1 | cut -c1-200 | head -1)
+done

@@ -36,8 +36,9 @@ def main():
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
-    js = {}
+    js, per_kernel = {}, []
     for vals in rows[2:]:
+        js = {}
         name = vals[hdr.index("Kernel Name")]
         print(f"## {name.split('(')[0]}\n\n| metric | value |\n|---|---|")
         for m, label, key in METRICS:
@@ -49,7 +50,7 @@ def main():
                 x = float(vals[i].replace(",", ""))
                 js[key] = x * SCALE.get(units[i], 1.0) if key.startswith("dram_bytes") else x
                 if key == "gpu_time":          # always microseconds in the JSON
-                    js[key] = x * {"second": 1e6, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3}.get(units[i], 1.0)
+                    js[key] = x * {"second": 1e6, "s": 1e6, "msecond": 1e3, "ms": 1e3, "usecond": 1.0, "us": 1.0, "nsecond": 1e-3, "ns": 1e-3}.get(units[i], 1.0)
             except ValueError:
                 pass
         st = []
@@ -62,8 +63,16 @@ def main():
               ", ".join(f"{s} {v:.2f}" for v, s in sorted(st, reverse=True) if v >= 0.05) + f" (sum incl. selected {tot:.2f}) |")
         print()
         js["kernel"] = name.split("(")[0]
+        per_kernel.append(js)
     if "--json" in sys.argv:
-        js["dram_bytes_per_launch"] = int(js.get("dram_bytes_read", 0) + js.get("dram_bytes_write", 0))
+        # several kernels in one capture = the kernels of ONE frame (config 5: wave_primary + wave_shade): the JSON describes the
+        # longest one and carries the frame's total DRAM bytes and every kernel's share
+        js = max(per_kernel, key=lambda k: k.get("gpu_time", 0.0))
+        js["dram_bytes_per_launch"] = int(sum(k.get("dram_bytes_read", 0) + k.get("dram_bytes_write", 0) for k in per_kernel))
+        if len(per_kernel) > 1:
+            js["frame_kernels"] = [{"kernel": k["kernel"], "gpu_time_us_under_ncu": k.get("gpu_time"),
+                                    "dram_bytes": int(k.get("dram_bytes_read", 0) + k.get("dram_bytes_write", 0)),
+                                    "issue_active_pct": k.get("issue_active_pct")} for k in per_kernel]
         if "gpu_time" in js:
             js["gpu_time_us_under_ncu"] = js.pop("gpu_time")
         if "--source" in sys.argv:

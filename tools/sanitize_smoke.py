@@ -85,6 +85,12 @@ def main():
         ctx.render(rt.LBVH, W, H, 2, shadows=1, exact=exact)
     for sh in (0, 1):
         ctx.render(rt.LBVH, W, H, 4, shadows=sh)      # materials through the packet kernel (no shadows) / castRay kernel (shadows)
+    # wavefront form of shadowed frames (wave_primary_kernel + wave_shade_kernel<warp sums / block sums>), materials in the scene
+    ctx.set_option("wavefront", 2)
+    for spp in (4, 16, 12):
+        ctx.render(rt.LBVH, W + 3, H + 1, spp, shadows=1, want_hit=True, want_accum=True)
+    ctx.render(rt.LBVH, W, H, 8, shadows=1, rank=1, world=3)
+    ctx.set_option("wavefront", 1)
     ctx.frame(sph, mat, rt.LBVH, W, H, 4, mode=rt.MODE_TRUE)      # rtds_frame: overlapped upload + build + render
     # round 2: scheduling options on device-buffer renders - lpt (block_order_kernel: needs consecutive frames of one geometry),
     # one CUDA graph per frame, L2 prefetch of the tree; rtds_prepare_frame; the in-process shared frame (flag + wait kernels)
