@@ -16,7 +16,7 @@ const RtdsOptionName g_rtds_option_names[] = {
     {"packet", "RTDS_PACKET", &RtdsOptions::packet}, {"wavefront", "RTDS_WAVEFRONT", &RtdsOptions::wavefront}, {"hull", "RTDS_HULL", &RtdsOptions::hull},
     {"zerocopy", "RTDS_ZEROCOPY", &RtdsOptions::zerocopy}, {"trace_frame", "RTDS_TRACE_FRAME", &RtdsOptions::trace_frame},
     {"median_small", "RTDS_MEDIAN_SMALL", &RtdsOptions::median_small}, {"median_coop", "RTDS_MEDIAN_COOP", &RtdsOptions::median_coop},
-    {"median_debug", "RTDS_MEDIAN_DEBUG", &RtdsOptions::median_debug}, {"node_preorder", "RTDS_NODE_PREORDER", &RtdsOptions::node_preorder},
+    {"median_debug", "RTDS_MEDIAN_DEBUG", &RtdsOptions::median_debug}, {"node_preorder", "RTDS_NODE_PREORDER", &RtdsOptions::node_preorder}, {"wide", "RTDS_WIDE", &RtdsOptions::wide},
     {"l2_prefetch", "RTDS_L2_PREFETCH", &RtdsOptions::l2_prefetch}, {"frame_graph", "RTDS_FRAME_GRAPH", &RtdsOptions::frame_graph},
     {"lpt", "RTDS_LPT", &RtdsOptions::lpt},
 };
@@ -90,6 +90,7 @@ void rtds_free_bvh(DeviceBvh& b)
     if (b.prim_order) cudaFree(b.prim_order);
     if (b.leaf_parent) cudaFree(b.leaf_parent);
     if (b.leaf_tri) cudaFree(b.leaf_tri);
+    if (b.wide) cudaFree(b.wide);
     b = DeviceBvh();
 }
 
@@ -111,6 +112,7 @@ int rtds_alloc_bvh_for(rtds_ctx* ctx, DeviceBvh& b, int n_prims)
 int rtds_alloc_bvh(DeviceBvh& b, int n_prims)
 {
     b.valid = false;
+    b.wide_valid = false;
     if (b.capacity >= n_prims && b.nodes) return RTDS_OK;
     rtds_free_bvh(b);
     size_t ni = n_prims > 1 ? (size_t)(n_prims - 1) : 1;

@@ -510,9 +510,72 @@ int rtds_bvh_refit(rtds_ctx* ctx, DeviceBvh& b, const uint32_t* d_ids, int n, un
     return RTDS_OK;
 }
 
-// Renumbers b.nodes in depth-first pre-order (see preorder_index_kernel). Needs n_internal * (4 + 64) bytes of scratch
-// at `scratch` (not overlapping anything still in use).
+// ---------------------------------------------------------------------------------------------------
+// K12: 4-wide collapse (`wide` option). One thread per interior node: its depth parity by walking the parent links (the builders
+// all write Node64::parent); a node at EVEN depth gathers its grandchildren's boxes from its two children's records - a child
+// that is a leaf contributes itself with the box its parent holds for it. Nodes at odd depth are absorbed (their slot stays unused).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wide_collapse_kernel(const Node64* __restrict__ nodes, int n_internal, Wide4* __restrict__ wide)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal) return;
+    int depth = 0;
+    for (int pe = __ldg(&nodes[i].parent); pe >= 0; pe = __ldg(&nodes[pe >> 1].parent)) ++depth;
+    if (depth & 1) return;
+    const Node64 nd = nodes[i];
+    Wide4 w;
+    int k = 0;
+    auto put = [&](int ref, const float* mn, const float* mx) {
+        w.x0[k] = mn[0]; w.y0[k] = mn[1]; w.z0[k] = mn[2]; w.x1[k] = mx[0]; w.y1[k] = mx[1]; w.z1[k] = mx[2]; w.ref[k] = ref; ++k;
+    };
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const int c = side ? nd.right : nd.left;
+        if (c >= 0) {
+            const Node64 ch = nodes[c];
+            put(ch.left, ch.lmin, ch.lmax);
+            put(ch.right, ch.rmin, ch.rmax);
+        } else {
+            put(c, side ? nd.rmin : nd.lmin, side ? nd.rmax : nd.lmax);
+        }
+    }
+    for (; k < 4; ++k) {
+        w.x0[k] = w.y0[k] = w.z0[k] = INFINITY; w.x1[k] = w.y1[k] = w.z1[k] = -INFINITY; w.ref[k] = WIDE_EMPTY;
+    }
+    w.pad[0] = w.pad[1] = w.pad[2] = w.pad[3] = 0;
+    wide[i] = w;
+}
+
+static int bvh_collapse_wide(rtds_ctx* ctx, DeviceBvh& b, int* launches)
+{
+    b.wide_valid = false;
+    const int ni = b.n_prims - 1;
+    if (!ctx->opt.wide || ni < 1) return RTDS_OK;
+    if (b.wide_capacity < ni) {
+        RTDS_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (b.wide) cudaFree(b.wide);
+        b.wide = nullptr; b.wide_capacity = 0;
+        RTDS_CUDA(cudaMalloc(&b.wide, sizeof(Wide4) * (size_t)ni));
+        b.wide_capacity = ni;
+    }
+    wide_collapse_kernel<<<(ni + 255) / 256, 256, 0, ctx->stream>>>(b.nodes, ni, b.wide);
+    RTDS_CUDA(cudaGetLastError());
+    if (launches) *launches += 1;
+    b.wide_valid = true;
+    return RTDS_OK;
+}
+
+// Layout passes behind every BVH build (all three builders end here): the optional pre-order renumbering, then the optional
+// 4-wide collapse. Renumbers b.nodes in depth-first pre-order (see preorder_index_kernel); needs n_internal * (4 + 64) bytes of
+// scratch at `scratch` (not overlapping anything still in use).
+static int bvh_reorder_preorder(rtds_ctx* ctx, DeviceBvh& b, void* scratch, int* launches);
 int rtds_bvh_reorder_preorder(rtds_ctx* ctx, DeviceBvh& b, void* scratch, int* launches)
+{
+    RTDS_TRY(bvh_reorder_preorder(ctx, b, scratch, launches));
+    return bvh_collapse_wide(ctx, b, launches);
+}
+static int bvh_reorder_preorder(rtds_ctx* ctx, DeviceBvh& b, void* scratch, int* launches)
 {
     const int ni = b.n_prims - 1;
     if (ni <= 1) return RTDS_OK;

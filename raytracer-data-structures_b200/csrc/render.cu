@@ -280,7 +280,12 @@ __device__ __forceinline__ void quadrant_block(int b, int nbx, int nby, int& bx,
 // accumulation matches main.cpp:553-560.
 template <int MODE /*0 = BVH exact, 1 = BVH ordered, 2 = NONE, 3 = KDTREE (any-hit, unshaded: main.cpp:362-372),
                      4 = KDTREE closest hit, shaded (extension: rtds_render_params.kd_closest)*/>
-__global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ RenderArgs A)
+// resident blocks of the one-ray-per-thread kernels, measured (config 4 / bunny 1080p, ms): 8 (64 registers) 1.97 / 0.179, 10 1.99 / 0.190,
+// 12 2.09 / 0.193, 16 2.27 / 0.217 - unlike the per-sample shadow kernel, spilling for occupancy loses here
+#ifndef RTDS_RK_MINB
+#define RTDS_RK_MINB 8
+#endif
+__global__ void __launch_bounds__(128, RTDS_RK_MINB) render_kernel(const __grid_constant__ RenderArgs A)
 {
     __shared__ float4 sh_sph[MODE == 2 ? NONE_CHUNK : 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -312,6 +317,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
             if (active) kd_closest_hit(A.kd, 0.f, 0.f, 0.f, dx, dy, dz, tnear, hit_obj, cnt);
         } else if (active) {
             if (MODE == 0) traverse_bvh_exact(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
+            else if (A.bvh.wide) traverse_fast<true, false, true, true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
             else traverse_fast<true, false, true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, best_key, best_leaf, cnt);
             if (best_leaf >= 0) hit_obj = __ldg(A.bvh.prim_order + best_leaf);
         }
@@ -1143,6 +1149,7 @@ BvhView make_view(const DeviceBvh& b)
     v.nodes = b.nodes; v.leaf_sph = b.leaf_sph; v.prim_order = b.prim_order; v.leaf_parent = b.leaf_parent; v.leaf_tri = b.leaf_tri; v.prim_type = b.prim_type;
     v.root_ref = b.root_ref; v.tie_by_objid = b.tie_by_objid; v.leaf_box_prim = b.leaf_box_prim;
     for (int i = 0; i < 6; ++i) v.root_box[i] = b.root_box[i];
+    v.wide = (b.wide_valid && b.root_ref >= 0) ? b.wide : nullptr;
     return v;
 }
 
@@ -1713,6 +1720,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     { const RayGen G0 = make_raygen(p); A.inv_w = G0.inv_w; A.inv_h = G0.inv_h; A.aspect = G0.aspect; A.angle = G0.angle; }
     A.n = ctx->n; A.sph = ctx->d_sph; A.tri = ctx->d_tris; A.prim_type = ctx->prim_type; A.mat = ctx->d_mat;
     if (!brute && !kdt) A.bvh = make_view(ctx->bvh); else A.bvh = BvhView();
+    if (!ctx->opt.wide) A.bvh.wide = nullptr;      // (built behind the BVH build when the option was on then)
     if (kdt) A.kd = make_kd_view(ctx); else A.kd = KdView();
     if (p->tri_geometric && ctx->prim_type == 1) { A.prim_type = 2; if (A.bvh.prim_type == 1) A.bvh.prim_type = 2; if (A.kd.prim_type == 1) A.kd.prim_type = 2; }
     A.shade.n_lights = ctx->n_lights;

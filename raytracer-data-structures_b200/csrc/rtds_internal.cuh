@@ -49,6 +49,19 @@ struct __align__(16) Node64 {
 };
 static_assert(sizeof(Node64) == 64, "Node64 must be 64 bytes");
 
+// 4-wide traversal node (`wide` option): the binary tree collapsed two levels at a time. wide[i] exists for every interior node i
+// at EVEN depth and holds the boxes of i's up to four grandchildren (a child that is a leaf stands for itself), plane by plane
+// for the four slots, and their references: >= 0 the grandchild's own index (it is at even depth again), < 0 a leaf (~leafpos),
+// WIDE_EMPTY for an unused slot (its box is inverted: min = +inf, max = -inf, no ray enters it). Interior tests only steer
+// (DESIGN.md section 7), so any conservative tree over the same leaves returns the same hits.
+struct __align__(16) Wide4 {
+    float x0[4], x1[4], y0[4], y1[4], z0[4], z1[4];
+    int   ref[4];
+    int   pad[4];
+};
+static_assert(sizeof(Wide4) == 128, "Wide4 must be 128 bytes");
+constexpr int WIDE_EMPTY = (int)0x80000000;
+
 struct DeviceBvh {
     int      capacity = 0;         // primitives the arrays below were allocated for
     int      n_prims = 0;          // leaves
@@ -69,6 +82,9 @@ struct DeviceBvh {
                                    // 0: triangles, or a median-split tree with dropped ranges (a leaf then carries the box of
                                    // its whole range, accelerators.h:321-327)
     int      max_depth = 0;
+    Wide4*   wide = nullptr;       // [wide_capacity] indexed like nodes; valid entries at even depth (wide option), else unused
+    int      wide_capacity = 0;
+    bool     wide_valid = false;
     bool     valid = false;
 };
 
@@ -130,6 +146,8 @@ struct RtdsOptions {
     int median_small = 0;    // RTDS_MEDIAN_SMALL test hook: sequential/parallel switch-over of the median split (0 = 64)
     int median_coop = 0;     // RTDS_MEDIAN_COOP  ranges above this use the cooperative kernel (0 = 65536)
     int median_debug = 0;    // RTDS_MEDIAN_DEBUG
+    int wide = 0;            // RTDS_WIDE         one-ray-per-thread primary rays walk the 4-wide collapse of the tree (built behind every BVH build).
+                             //                   Measured: node visits halve, kernels -1 ... -8 %: opt-in
     int node_preorder = 0;   // RTDS_NODE_ORDER=preorder: renumber the nodes in DFS pre-order after the build
     int l2_prefetch = 0;     // RTDS_L2_PREFETCH  stream the tree into L2 on a side stream while the directions are generated
     int lpt = 1;             // RTDS_LPT          the previous frame's heaviest blocks are launched first: 1 = where the library measures a gain, 2 = always, 0 = never

@@ -167,6 +167,7 @@ struct BvhView {
     int           tie_by_objid;
     int           leaf_box_prim;   // sphere leaves whose box is exactly c -/+ r
     float         root_box[6];
+    const Wide4*  wide;            // 4-wide collapse of `nodes` (wide option), or nullptr
 };
 
 constexpr int STACK_MAX = 64;
@@ -437,8 +438,122 @@ __device__ __forceinline__ void traverse_fast_loop(const BvhView& B, float ox, f
     cnt.node_tests += 2 * visits;
 }
 
+// The same ordered traversal over the 4-wide collapse (Wide4): one visit = seven 16-byte loads, four boxes tested; the nearest accepted
+// slot is descended, the others are pushed (unsorted: the CPU model shows no gain from sorting them). Half the dependent loads per
+// ray of the binary walk at equal arithmetic. Leaves, pruning and the candidate rule are the binary loop's, so are the hits.
+constexpr int WIDE_STACK = 96;
+template <bool ZERO_O, bool ANYHIT, int OCT>
+__device__ __forceinline__ void traverse_wide_loop(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
+                                                   float ix, float iy, float iz, float margin, float& tnear, int& best_key,
+                                                   int& best_leaf, Counters& cnt, float t2max, const RayAffine& R)
+{
+    const float neg_margin = -margin;
+    float tlim = ANYHIT ? sqrtf(t2max) + margin : tnear + margin;
+    tlim = __fmaf_rn(fabsf(tlim), WIDE2, tlim);
+    int2 stack[WIDE_STACK];
+    int sp = 0;
+    int node = 0;
+    unsigned visits = 0;
+    while (true) {
+        if (node >= 0) {
+            const float4* q = reinterpret_cast<const float4*>(B.wide + node);
+            const float4 X0 = __ldg(q), X1 = __ldg(q + 1), Y0 = __ldg(q + 2), Y1 = __ldg(q + 3), Z0 = __ldg(q + 4), Z1 = __ldg(q + 5);
+            const int4 rf = __ldg(reinterpret_cast<const int4*>(q + 6));
+            ++visits;
+            const float4 xn = (OCT & 1) ? X1 : X0, xf = (OCT & 1) ? X0 : X1;
+            const float4 yn = (OCT & 2) ? Y1 : Y0, yf = (OCT & 2) ? Y0 : Y1;
+            const float4 zn = (OCT & 4) ? Z1 : Z0, zf = (OCT & 4) ? Z0 : Z1;
+            const float xnv[4] = {xn.x, xn.y, xn.z, xn.w}, xfv[4] = {xf.x, xf.y, xf.z, xf.w};
+            const float ynv[4] = {yn.x, yn.y, yn.z, yn.w}, yfv[4] = {yf.x, yf.y, yf.z, yf.w};
+            const float znv[4] = {zn.x, zn.y, zn.z, zn.w}, zfv[4] = {zf.x, zf.y, zf.z, zf.w};
+            const int ref[4] = {rf.x, rf.y, rf.z, rf.w};
+            float tmn[4];
+            bool hit[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float tmx;
+                if (ZERO_O) {
+                    tmn[k] = fmaxf(fmaxf(xnv[k] * ix, ynv[k] * iy), znv[k] * iz);
+                    tmx = fminf(fminf(xfv[k] * ix, yfv[k] * iy), zfv[k] * iz);
+                    tmx = __fmaf_rn(fabsf(tmx), WIDE2, tmx);
+                } else {
+                    tmn[k] = fmaxf(fmaxf(__fmaf_rn(xnv[k], ix, R.cnx), __fmaf_rn(ynv[k], iy, R.cny)), __fmaf_rn(znv[k], iz, R.cnz));
+                    tmx = fminf(fminf(__fmaf_rn(xfv[k], ix, R.cfx), __fmaf_rn(yfv[k], iy, R.cfy)), __fmaf_rn(zfv[k], iz, R.cfz));
+                }
+                hit[k] = tmn[k] <= fminf(tmx, tlim) && tmx >= neg_margin;      // an unused slot has tmn = +inf
+            }
+            // nearest accepted slot first
+            int first = -1;
+            float tfirst = INFINITY;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (hit[k] && (first < 0 || tmn[k] < tfirst)) { first = k; tfirst = tmn[k]; }
+            if (first >= 0) {
+                int next = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k == first) next = ref[k];
+                    else if (hit[k]) { stack[sp] = make_int2(ref[k], __float_as_int(tmn[k])); sp = min(sp + 1, WIDE_STACK - 1); }
+                }
+                node = next;
+                continue;
+            }
+        } else {
+            const int leaf = ~node;
+            bool pass;
+            float t0, t1;
+            if (B.leaf_box_prim) {
+                const float4 s = __ldg(B.leaf_sph + leaf);
+                const float bx0 = s.x - s.w, by0 = s.y - s.w, bz0 = s.z - s.w, bx1 = s.x + s.w, by1 = s.y + s.w, bz1 = s.z + s.w;
+                float x0, y0, z0, x1, y1, z1;
+                if (ZERO_O) { x0 = bx0 * ix; y0 = by0 * iy; z0 = bz0 * iz; x1 = bx1 * ix; y1 = by1 * iy; z1 = bz1 * iz; }
+                else {
+                    x0 = (bx0 - ox) * ix; y0 = (by0 - oy) * iy; z0 = (bz0 - oz) * iz;
+                    x1 = (bx1 - ox) * ix; y1 = (by1 - oy) * iy; z1 = (bz1 - oz) * iz;
+                }
+                float tmn, tmx;
+                slab_interval<OCT>(x0, y0, z0, x1, y1, z1, tmn, tmx);
+                pass = __fmaf_rn(fabsf(tmn), NARROW_EPS, tmn) <= __fmaf_rn(-fabsf(tmx), NARROW_EPS, tmx) &&
+                       fminf(fabsf(tmn), fabsf(tmx)) > 1e-30f;
+                if (!pass) pass = slab_test_cold(ox, oy, oz, dx, dy, dz, bx0, by0, bz0, bx1, by1, bz1);
+                if (pass) {
+                    cnt.prim_tests++;
+                    pass = sphere_test(ox, oy, oz, dx, dy, dz, make_float4(s.x, s.y, s.z, s.w * s.w), t0, t1);
+                }
+            } else {
+                const ColdLeaf r = leaf_parent_box_cold(&B, leaf, ox, oy, oz, dx, dy, dz);
+                cnt.prim_tests += r.prim_tests;
+                pass = r.pass != 0; t0 = r.t0; t1 = r.t1;
+            }
+            if (pass) {
+                if (ANYHIT) {
+                    if (t0 < 0) t0 = t1;
+                    if (t0 * t0 < t2max) { tnear = t0; best_leaf = leaf; cnt.node_visits += visits; cnt.node_tests += 4 * visits; return; }
+                } else {
+                    candidate(t0, t1, B.tie_by_objid ? __ldg(B.prim_order + leaf) : leaf, leaf, tnear, best_key, best_leaf);
+                    tlim = tnear + margin;
+                    tlim = __fmaf_rn(fabsf(tlim), WIDE2, tlim);
+                }
+            }
+        }
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            const int2 e = stack[sp];
+            if (__int_as_float(e.y) > tlim) continue;
+            node = e.x;
+            found = true;
+            break;
+        }
+        if (!found) break;
+    }
+    cnt.node_visits += visits;
+    cnt.node_tests += 4 * visits;
+}
+
 // ZNEG: the caller guarantees dz < 0 (every primary ray: dz = -1 before normalisation), four octants instead of eight.
-template <bool ZERO_O, bool ANYHIT = false, bool ZNEG = false>
+// WIDE: walk the 4-wide collapse (the caller has checked B.wide).
+template <bool ZERO_O, bool ANYHIT = false, bool ZNEG = false, bool WIDE = false>
 __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float oy, float oz, float dx, float dy, float dz,
                                               float& tnear, int& best_key, int& best_leaf, Counters& cnt, float t2max = 0.f)
 {
@@ -464,7 +579,8 @@ __device__ __forceinline__ void traverse_fast(const BvhView& B, float ox, float 
     // first interior visit.
     const float margin = prune_margin(B.root_box, ox, oy, oz);
     const int oct = (dx < 0 ? 1 : 0) | (dy < 0 ? 2 : 0) | ((ZNEG || dz < 0) ? 4 : 0);
-#define RTDS_OCT_CASE(o) case o: traverse_fast_loop<ZERO_O, ANYHIT, o>(B, ox, oy, oz, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt, t2max, R); break;
+#define RTDS_OCT_CASE(o) case o: if (WIDE) traverse_wide_loop<ZERO_O, ANYHIT, o>(B, ox, oy, oz, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt, t2max, R); \
+                                else traverse_fast_loop<ZERO_O, ANYHIT, o>(B, ox, oy, oz, dx, dy, dz, ix, iy, iz, margin, tnear, best_key, best_leaf, cnt, t2max, R); break;
     switch (oct) {
         RTDS_OCT_CASE(4) RTDS_OCT_CASE(5) RTDS_OCT_CASE(6) RTDS_OCT_CASE(7)
         default:

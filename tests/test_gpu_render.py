@@ -252,3 +252,39 @@ def test_scheduling_options_do_not_change_the_frame(gpu_ctx, spp, shadows):
         for a, b in zip(plain + plain, got):
             assert np.array_equal(a[0], b[0]) and a[1:] == b[1:], (graph, pf, lpt)
     assert plain[0][1] >= 400 * 300 * spp and (shadows == 0) == (plain[0][1] == 400 * 300 * spp)
+
+
+@pytest.mark.parametrize("kind", ["lbvh", "median", "sah", "median_mixed_radii", "triangles", "tiny"])
+def test_wide_collapse_returns_the_binary_trees_hits(gpu_ctx, oracle, kind):
+    """`wide` option: every BVH build is followed by the 4-wide collapse (wide_collapse_kernel: even-depth nodes gather their
+    grandchildren), and the one-ray-per-thread primary rays walk it (traverse_wide_loop). Interior tests only steer, so hit ids, float
+    sums and bytes must equal the binary walk's - every builder, trees with dropped ranges (leaf boxes from the parent's record),
+    triangles, trees of 1..4 leaves - with fewer node visits."""
+    if kind == "triangles":
+        tris, mat = T.triangle_scene(3000, 9)
+    elif kind == "median_mixed_radii":
+        sph, mat = T.material_scene(2500, 4, frac_rr=0.0, frac_refl=0.0)      # one big sphere among small ones: dropped ranges
+    else:
+        sph, mat = T.synthetic_scene(5000, 21)
+    sizes = (2, 3, 4, 5) if kind == "tiny" else (None,)
+    for m in sizes:
+        with T.option(gpu_ctx, "wide", 1):
+            if kind == "triangles":
+                gpu_ctx.set_triangles(tris, mat)
+            elif m is not None:
+                gpu_ctx.set_spheres(sph[:m], mat[:m])
+            else:
+                gpu_ctx.set_spheres(sph, mat)
+            acc, mode = {"lbvh": (rt.LBVH, rt.MODE_TRUE), "median": (rt.BVH, rt.MODE_COMPAT), "sah": (rt.BVH, rt.MODE_SAH),
+                         "median_mixed_radii": (rt.BVH, rt.MODE_COMPAT), "triangles": (rt.LBVH, rt.MODE_TRUE), "tiny": (rt.LBVH, rt.MODE_TRUE)}[kind]
+            gpu_ctx.build(acc, mode=mode)
+            for (W, H, spp) in ((322, 203, 1), (161, 97, 3)):
+                wide = gpu_ctx.render(acc, W, H, spp, want_hit=True, want_accum=True)
+                with T.option(gpu_ctx, "wide", 0):
+                    binary = gpu_ctx.render(acc, W, H, spp, want_hit=True, want_accum=True)
+                assert np.array_equal(wide[1], binary[1]) and wide[2].tobytes() == binary[2].tobytes() and np.array_equal(wide[0], binary[0])
+                assert wide[3]["rays"] == binary[3]["rays"] and wide[3]["prim_tests"] <= binary[3]["prim_tests"] * 1.05 + 8
+                if m is None:
+                    assert wide[3]["node_visits"] < 0.75 * binary[3]["node_visits"]
+                    assert np.count_nonzero(wide[1] >= 0) > 100
+    gpu_ctx.set_spheres(*T.bunny_scene())

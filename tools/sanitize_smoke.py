@@ -85,6 +85,13 @@ def main():
         ctx.render(rt.LBVH, W, H, 2, shadows=1, exact=exact)
     for sh in (0, 1):
         ctx.render(rt.LBVH, W, H, 4, shadows=sh)      # materials through the packet kernel (no shadows) / castRay kernel (shadows)
+    # 4-wide collapse behind the build + the wide walk of the one-ray-per-thread kernel (opt-in)
+    ctx.set_option("wide", 1)
+    ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
+    ctx.render(rt.LBVH, W + 3, H + 1, 1, want_hit=True)
+    ctx.render(rt.LBVH, W, H, 3)
+    ctx.set_option("wide", 0)
+    ctx.build(rt.LBVH, mode=rt.MODE_TRUE)
     # wavefront form of shadowed frames (wave_primary_kernel + wave_shade_kernel<warp sums / block sums>), materials in the scene
     ctx.set_option("wavefront", 2)
     for spp in (4, 16, 12):
