@@ -288,3 +288,40 @@ def test_wide_collapse_returns_the_binary_trees_hits(gpu_ctx, oracle, kind):
                     assert wide[3]["node_visits"] < 0.75 * binary[3]["node_visits"]
                     assert np.count_nonzero(wide[1] >= 0) > 100
     gpu_ctx.set_spheres(*T.bunny_scene())
+
+
+def test_grazing_rays_from_arbitrary_origins_fast_equals_exact(gpu_ctx):
+    """Rays with a non-zero origin (what shadow and secondary rays are) test interior boxes with one FFMA per plane and an absolute
+    widening (traverse.cuh, ray_affine). Hard cases for it: rays aimed EXACTLY at corners / edge points of leaf boxes and at
+    tangent points of spheres, from origins on other spheres' surfaces, inside the scene and far outside it, with tiny direction
+    components. The ordered traversal must return the unpruned reference traversal's hit id and t bits on every one."""
+    sph, mat = T.synthetic_scene(20000, 31)
+    gpu_ctx.set_spheres(sph, mat)
+    rng = np.random.default_rng(32)
+    n = 60000
+    tgt_s = sph[rng.integers(0, sph.shape[0], n)]
+    sign = rng.choice(np.float32([-1, 1]), size=(n, 3))
+    tgt = tgt_s[:, :3] + sign * tgt_s[:, 3:4]                                            # a corner of the sphere's own box
+    edge = rng.random(n) < 0.4
+    ax = rng.integers(0, 3, n)
+    tgt[edge, ax[edge]] = (tgt_s[edge, ax[edge]] + rng.uniform(-1, 1, edge.sum()) * tgt_s[edge, 3]).astype(np.float32)   # edge point
+    tang = rng.random(n) < 0.3                                                           # tangent point: centre + r * unit vector
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    tgt[tang] = (tgt_s[tang, :3] + u[tang] * tgt_s[tang, 3:4]).astype(np.float32)
+    org_s = sph[rng.integers(0, sph.shape[0], n)]
+    v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    o = (org_s[:, :3] + v * org_s[:, 3:4] * 1.001).astype(np.float32)                    # just off another sphere's surface
+    far = rng.random(n) < 0.15
+    o[far] = (o[far] * rng.choice(np.float32([20, 1e3, 1e5]), size=(far.sum(), 1))).astype(np.float32)
+    d = (tgt - o).astype(np.float64)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    tiny = rng.random(n) < 0.1
+    d[tiny, ax[tiny]] = rng.choice([1e-6, 1e-9, 1e-13], tiny.sum())
+    d = d.astype(np.float32)
+    for acc, mode in ((rt.LBVH, rt.MODE_TRUE), (rt.BVH, rt.MODE_SAH)):
+        gpu_ctx.build(acc, mode=mode)
+        he, te, _ = gpu_ctx.trace(acc, o, d, exact=True)
+        hf, tf, st = gpu_ctx.trace(acc, o, d, exact=False)
+        assert np.array_equal(he, hf), np.count_nonzero(he != hf)
+        assert te.tobytes() == tf.tobytes()
+        assert 0.3 < (he >= 0).mean() < 1.0

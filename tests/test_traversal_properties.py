@@ -92,3 +92,92 @@ def test_packet_hull_test_accepts_what_any_ray_accepts():
     extra = np.count_nonzero(hull & ~any_ray) / max(1, np.count_nonzero(hull))
     print("hull accepts %.2f %% boxes no single ray accepts (random boxes, not a BVH)" % (100 * extra))
     assert 0.05 < any_ray.mean() < 0.95
+
+
+def ref_slab_origin(o, d, bmin, bmax):
+    """boundingBoxIntersection with a ray origin (accelerators.h:588-626): fl(fl(plane - o) / d), x -> y -> z, no t-range test."""
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        t0 = ((bmin - o).astype(F) / d).astype(F)
+        t1 = ((bmax - o).astype(F) / d).astype(F)
+    lo, hi = np.minimum(t0, t1), np.maximum(t0, t1)
+    tmin, tmax = lo[:, 0].copy(), hi[:, 0].copy()
+    ok = ~((tmin > hi[:, 1]) | (lo[:, 1] > tmax))
+    tmin = np.where(lo[:, 1] > tmin, lo[:, 1], tmin)
+    tmax = np.where(hi[:, 1] < tmax, hi[:, 1], tmax)
+    ok &= ~((tmin > hi[:, 2]) | (lo[:, 2] > tmax))
+    return ok
+
+
+def fma32(a, b, c):
+    """float32 fused multiply-add: the product of two float32 is exact in float64, one rounding of the sum to float64 and one to
+    float32 (double rounding can differ from a true FMA by an ulp in rare ties - far inside the widening under test)."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(F)
+
+
+def affine_interior(o, inv, bmin, bmax, rb_min, rb_max):
+    """interior test of rays with a non-zero origin (traverse.cuh, ray_affine + the !ZERO_O branch of the traversal loops):
+    t = plane * (1/d) + c, c = -(o * 1/d) -/+ w, w = (max |plane| over the root box + |o|) * |1/d| * 2^-20."""
+    k = F(2.0 ** -20)
+    R = np.maximum(np.abs(rb_min), np.abs(rb_max)).astype(F)
+    w = (((R + np.abs(o)).astype(F) * np.abs(inv)).astype(F) * k).astype(F)
+    c = (-(o * inv).astype(F)).astype(F)
+    cn, cf = (c - w).astype(F), (c + w).astype(F)
+    neg = inv < 0
+    near, far = np.where(neg, bmax, bmin), np.where(neg, bmin, bmax)
+    tmin = fma32(near, inv, cn).max(axis=1)
+    tmax = fma32(far, inv, cf).min(axis=1)
+    return tmin, tmax, w.max(axis=1)
+
+
+def test_affine_interior_test_accepts_what_the_reference_accepts():
+    """Round 2: shadow / secondary rays test interior boxes with ONE FFMA per plane. The absolute widening folded into the per-ray
+    constants must cover the cancellation in plane * i - o * i: every box the reference's fl(fl(plane - o) / d) test accepts is
+    accepted - origins on other boxes' surfaces (shadow rays), far outside the scene, direction components down to 1e-12, boxes
+    that contain the origin (t around 0), any reciprocal within 2^-22 of 1/d."""
+    rng = np.random.default_rng(3)
+    n = 400000
+    bmin, bmax = random_boxes(rng, n)
+    rb_min, rb_max = bmin.min(axis=0), bmax.max(axis=0)                      # the root box of the "scene"
+    # origins: on / near another box (shadow rays leave a surface), some inside the tested box, some far outside the scene
+    other = rng.permutation(n)
+    o = (bmin[other] + (bmax[other] - bmin[other]) * rng.uniform(-0.1, 1.1, size=(n, 3))).astype(F)
+    inside = rng.random(n) < 0.15
+    o[inside] = (bmin[inside] + (bmax[inside] - bmin[inside]) * rng.uniform(0, 1, size=(inside.sum(), 3))).astype(F)
+    far_o = rng.random(n) < 0.1
+    o[far_o] = (o[far_o] * rng.choice([30.0, 1e3, 1e5], size=(far_o.sum(), 1))).astype(F)
+    # directions aimed near the tested box from the origin (grazing cases), some with one tiny component
+    tgt = (bmin + (bmax - bmin) * rng.uniform(-0.3, 1.3, size=(n, 3))).astype(np.float64)
+    # half of the rays aim EXACTLY at a point on an edge of the box: entry and exit distance then coincide up to rounding and the
+    # reference's answer hangs on single ulps (without the widening the FFMA form rejects ~14 % of the boxes the reference accepts
+    # on such rays; checked when this test was written)
+    edge = rng.random(n) < 0.5
+    corner = np.where(rng.integers(0, 2, size=(n, 3)).astype(bool), bmin, bmax).astype(np.float64)
+    free = rng.integers(0, 3, size=n)
+    idx = np.arange(n)
+    corner[idx, free] = bmin[idx, free] + (bmax[idx, free] - bmin[idx, free]) * rng.uniform(0, 1, size=n)
+    tgt[edge] = corner[edge]
+    tgt = tgt - o
+    tgt[np.abs(tgt) < 1e-9] = 1e-9
+    d = tgt / np.linalg.norm(tgt, axis=1, keepdims=True)
+    tiny = rng.random(n) < 0.15
+    ax = rng.integers(0, 3, size=n)
+    d[tiny, ax[tiny]] = rng.choice([1e-5, 1e-8, 1e-12], size=tiny.sum()) * rng.choice([-1, 1], size=tiny.sum())
+    d = d.astype(F)
+    ref = ref_slab_origin(o, d, bmin, bmax)
+    for k in range(3):
+        rel = rng.uniform(-1, 1, size=(n, 3)) * 2.0 ** -22
+        inv = ((1.0 / d.astype(np.float64)) * (1 + rel)).astype(F)
+        tmin, tmax, wmax = affine_interior(o, inv, bmin, bmax, rb_min, rb_max)
+        fast = (np.abs(inv).min(axis=1) > 1e-30) & (np.abs(inv).max(axis=1) < 1e30) & (wmax < 1e30)      # else: the divide-based traversal
+        acc = tmin <= tmax
+        bad = ref & fast & ~acc
+        assert not np.any(bad), "the FFMA interior test rejected %d boxes the reference's divide test accepts" % bad.sum()
+    assert fast.mean() > 0.95 and 0.2 < ref.mean() < 0.98
+    # and it is not vacuous: boxes the reference rejects are still rejected most of the time, and WITHOUT the widening the same
+    # arithmetic does reject boxes the reference accepts (the sample contains the hard cases)
+    assert (~acc & ~ref).sum() > 0.5 * (~ref).sum()
+    c0 = (-(o * inv).astype(F)).astype(F)
+    neg = inv < 0
+    t0 = fma32(np.where(neg, bmax, bmin), inv, c0).max(axis=1)
+    t1 = fma32(np.where(neg, bmin, bmax), inv, c0).min(axis=1)
+    assert np.count_nonzero(ref & fast & ~(t0 <= t1)) > 1000
