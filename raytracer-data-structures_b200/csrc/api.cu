@@ -18,7 +18,7 @@ const RtdsOptionName g_rtds_option_names[] = {
     {"median_small", "RTDS_MEDIAN_SMALL", &RtdsOptions::median_small}, {"median_coop", "RTDS_MEDIAN_COOP", &RtdsOptions::median_coop},
     {"median_debug", "RTDS_MEDIAN_DEBUG", &RtdsOptions::median_debug}, {"node_preorder", "RTDS_NODE_PREORDER", &RtdsOptions::node_preorder}, {"wide", "RTDS_WIDE", &RtdsOptions::wide},
     {"l2_prefetch", "RTDS_L2_PREFETCH", &RtdsOptions::l2_prefetch}, {"frame_graph", "RTDS_FRAME_GRAPH", &RtdsOptions::frame_graph},
-    {"lpt", "RTDS_LPT", &RtdsOptions::lpt},
+    {"lpt", "RTDS_LPT", &RtdsOptions::lpt}, {"lpt_split", "RTDS_LPT_SPLIT", &RtdsOptions::lpt_split},
 };
 const int g_rtds_n_option_names = (int)(sizeof g_rtds_option_names / sizeof g_rtds_option_names[0]);
 
@@ -224,7 +224,7 @@ int rtds_destroy(rtds_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     rtds_free_bvh(c->bvh);
     rtds_free_kd(c->kd);
-    void* bufs[] = {c->d_sph, c->d_mat, c->d_tris, c->d_keys_sorted, c->d_mt_snap, c->d_jitter, c->d_dirs, c->d_wave, c->d_block_cost, c->d_block_order, c->d_scratch,
+    void* bufs[] = {c->d_sph, c->d_mat, c->d_tris, c->d_keys_sorted, c->d_mt_snap, c->d_jitter, c->d_dirs, c->d_wave, c->d_block_cost, c->d_block_order, c->d_heavy_list, c->d_block_skip, c->d_scratch,
                     c->d_sort_ws, c->d_frame, c->d_hit, c->d_accum, c->d_counters};
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);

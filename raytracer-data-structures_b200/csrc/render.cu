@@ -99,6 +99,8 @@ struct RenderArgs {
     int*     out_hit;            // optional, local rows x width
     float*   out_accum;          // optional, local rows x width x 3
     unsigned long long* counters;
+    const int*     heavy_list;   // lpt_split: tiles rendered by render_heavy_kernel this frame (-1: unused entry), or nullptr
+    const unsigned char* skip;   // ... and the per-tile flag that makes the packet kernel leave them alone
     float*         wave_t;       // wavefront form (shadows on): per local sample (lrow * width + px) * spp + k, the primary hit's tnear ...
     int*           wave_leaf;    // ... and leaf (-1: sky), written by wave_primary_kernel, read by wave_shade_kernel
     const int* order;            // optional: launch position -> block id (the previous frame's heaviest blocks first), see block_order_kernel
@@ -128,11 +130,13 @@ __device__ __forceinline__ void report_block_cost(const RenderArgs& A, int lb, u
 // 64,800-block frame moved to the front the frame got 2 % SLOWER: an SM full of heavy blocks of all four octants). Clears cost.
 // One block of 1024 threads per band.
 constexpr int LPT_MAX_HEAVY = 512;
+constexpr int LPT_SPLIT_MAX = 256;       // most tiles handed to render_heavy_kernel per frame
 constexpr int LPT_TRIAL_FRAMES = 6;      // lpt = 1: frames of a geometry spent comparing the two orders
 struct LptBands { int n_bands; int off[RTDS_MAX_BANDS + 1]; };      // a frame rendered as row bands: one launch (and one order) per band
-__global__ void __launch_bounds__(1024) block_order_kernel(unsigned* __restrict__ cost, int* __restrict__ order, const LptBands bands, int cap)
+__global__ void __launch_bounds__(1024) block_order_kernel(unsigned* __restrict__ cost, int* __restrict__ order, const LptBands bands, int cap,
+                                                           int* __restrict__ heavy_list, unsigned char* __restrict__ skip, int n_split)
 {
-    cost += bands.off[blockIdx.x]; order += bands.off[blockIdx.x];
+    cost += bands.off[blockIdx.x]; order += bands.off[blockIdx.x]; skip += bands.off[blockIdx.x];
     const int n = bands.off[blockIdx.x + 1] - bands.off[blockIdx.x];
     __shared__ unsigned s_u[32];
     __shared__ int s_i[32], s_j[32];
@@ -189,6 +193,7 @@ __global__ void __launch_bounds__(1024) block_order_kernel(unsigned* __restrict_
         if (h) { s_hc[before] = c; s_hid[before] = i; } else order[n_heavy + i - before] = i;
         before += h;
         cost[i] = 0u;
+        skip[i] = 0;
     }
     // the heavy ones by descending cost (ties: ascending id): bitonic sort of the padded list in shared memory
     for (int i = n_heavy + t; i < LPT_MAX_HEAVY; i += 1024) { s_hc[i] = 0u; s_hid[i] = 0x7fffffff; }
@@ -208,6 +213,12 @@ __global__ void __launch_bounds__(1024) block_order_kernel(unsigned* __restrict_
             __syncthreads();
         }
     if (t < n_heavy) order[t] = s_hid[t];
+    // lpt_split (single-band frames): the heaviest of them go to render_heavy_kernel next frame
+    if (heavy_list && blockIdx.x == 0) {
+        const int ns = min(n_split, n_heavy);
+        if (t < LPT_SPLIT_MAX) heavy_list[t] = t < ns ? s_hid[t] : -1;
+        if (t < ns) skip[s_hid[t]] = 1;
+    }
 }
 
 // Frame-buffer write of a warp's 8 x 4 pixels. The warp's RGB8 values are staged in shared memory and leave as 12
@@ -525,6 +536,7 @@ __global__ void __launch_bounds__(RTDS_PK_THREADS, RTDS_PK_MINB) render_packet_k
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int bx, by;
     const int lblock = logical_block(A);
+    if (A.skip && __ldg(A.skip + lblock)) return;      // lpt_split: this tile is render_heavy_kernel's (block-uniform)
     quadrant_block(lblock, (A.width + 15) / 16, (A.local_rows - A.lrow0 + PK_TILE_H - 1) / PK_TILE_H, bx, by, A.block_order);
     const int px = bx * 16 + (warp & 1) * 8 + (lane & 7);
     const int lrow = A.lrow0 + by * PK_TILE_H + (warp >> 1) * 4 + (lane >> 3);
@@ -925,6 +937,77 @@ __global__ void __launch_bounds__(128) render_full_kernel(const __grid_constant_
         unsigned long long x = v[c];
         for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0 && x) atomicAdd(&A.counters[c], x);
+    }
+}
+
+// ===================================================================================================
+// K10d: the heaviest tiles of the packet kernel, one RAY per thread (lpt_split). What bounds a rank's kernel in the strong-scaling
+// run is a handful of 16 x 8 tiles whose packets graze hundreds of leaf boxes: in the packet kernel one thread
+// walks its pixel's four samples' leaf tests one after the other. The tiles that were heaviest in the previous frame are therefore
+// rendered here instead - four blocks per tile, two pixel rows each, a thread per (pixel, sample), four neighbouring lanes per
+// pixel - on the highest-priority stream, while render_packet_kernel skips them (A.skip). Same rays, same single-ray traversal the
+// packet traversal is tested against, same shading function, sums in sample order through shuffles: same bytes.
+// ===================================================================================================
+__global__ void __launch_bounds__(128) render_heavy_kernel(const __grid_constant__ RenderArgs A)
+{
+    static_assert(PK_TILE_H == 8, "render_heavy_kernel covers a 16 x 8 tile with 4 blocks of 2 rows");
+    const int tile = __ldg(A.heavy_list + (blockIdx.x >> 2));
+    if (tile < 0) return;
+    const int lane = threadIdx.x & 31, q = blockIdx.x & 3;
+    int bx, by;
+    quadrant_block(tile, (A.width + 15) / 16, (A.local_rows - A.lrow0 + PK_TILE_H - 1) / PK_TILE_H, bx, by, A.block_order);
+    const int p = threadIdx.x >> 2, k = threadIdx.x & 3;
+    const int px = bx * 16 + (p & 15), lrow = A.lrow0 + by * PK_TILE_H + 2 * q + (p >> 4);
+    const bool active = px < A.width && lrow < A.local_rows;
+    Counters cnt = {0, 0, 0, 0};
+    float acc_r = 0, acc_g = 0, acc_b = 0;
+    int last_hit = -1;
+    unsigned est_visits = 0, est_prims = 0;
+    const size_t pix = active ? (size_t)global_row_of(A, lrow) * A.width + px : 0;
+    const int base = lane & ~3;
+    for (int k0 = 0; k0 < A.spp; k0 += PK) {
+        float r = 0.f, g = 0.f, b = 0.f;
+        int hit = -1;
+        if (active) {
+            const float* dp = A.dirs + 3 * (pix * A.spp + k0 + k);
+            const float dx = __ldcs(dp), dy = __ldcs(dp + 1), dz = __ldcs(dp + 2);
+            float tnear = INFINITY;
+            int key = 0, leaf = -1;
+            Counters c1 = {0, 0, 0, 0};
+            traverse_fast<true, false, true>(A.bvh, 0.f, 0.f, 0.f, dx, dy, dz, tnear, key, leaf, c1);
+            cnt.node_tests += c1.node_tests; cnt.prim_tests += c1.prim_tests; cnt.node_visits += c1.node_visits; cnt.rays++;
+            est_visits = max(est_visits, c1.node_visits); est_prims += c1.prim_tests;
+            const ShadedRay sh = shade_packet_ray_ool(&A, dx, dy, dz, tnear, leaf);
+            r = sh.r; g = sh.g; b = sh.b; hit = sh.hit;
+        }
+#pragma unroll
+        for (int j = 0; j < PK; ++j) {                                          // sample order, main.cpp:553-560
+            acc_r += __shfl_sync(0xffffffffu, r, base + j); acc_g += __shfl_sync(0xffffffffu, g, base + j); acc_b += __shfl_sync(0xffffffffu, b, base + j);
+        }
+        last_hit = __shfl_sync(0xffffffffu, hit, base + PK - 1);
+    }
+    if (active && k == 0) {
+        const float fs = (float)(unsigned)A.spp;
+        const unsigned char r8 = (unsigned char)(fminf(1.0f, acc_r / fs) * 255);
+        const unsigned char g8 = (unsigned char)(fminf(1.0f, acc_g / fs) * 255);
+        const unsigned char b8 = (unsigned char)(fminf(1.0f, acc_b / fs) * 255);
+        const size_t o = (size_t)lrow * A.width + px;
+        if (A.out_hit) A.out_hit[o] = last_hit;
+        if (A.out_accum) { A.out_accum[3 * o] = acc_r; A.out_accum[3 * o + 1] = acc_g; A.out_accum[3 * o + 2] = acc_b; }
+        const size_t oo = (size_t)(A.out_global_rows ? global_row_of(A, lrow) : lrow) * A.width + px;
+        A.out_rgb[3 * oo] = r8; A.out_rgb[3 * oo + 1] = g8; A.out_rgb[3 * oo + 2] = b8;
+    }
+    // the tile's cost for the next frame's order, in the packet kernel's currency (a packet's node visits ~ its longest ray's,
+    // its primitive tests = the four rays' together): the largest such pixel
+    unsigned pv = est_visits, pp = est_prims;
+    pv = max(pv, __shfl_xor_sync(0xffffffffu, pv, 1)); pv = max(pv, __shfl_xor_sync(0xffffffffu, pv, 2));
+    pp += __shfl_xor_sync(0xffffffffu, pp, 1); pp += __shfl_xor_sync(0xffffffffu, pp, 2);
+    report_block_cost(A, tile, pv + pp);
+    unsigned v[4] = {cnt.node_tests, cnt.prim_tests, cnt.node_visits, cnt.rays};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const unsigned x = __reduce_add_sync(0xffffffffu, v[c]);
+        if (lane == 0 && x) atomicAdd(&A.counters[c], (unsigned long long)x);
     }
 }
 
@@ -1636,6 +1719,10 @@ static int lpt_frame_begin(rtds_ctx* ctx, const RenderArgs& A, const void* fn, c
         ctx->d_block_cost = nullptr; ctx->d_block_order = nullptr; ctx->block_cap = 0; ctx->block_order_valid = false;
         RTDS_CUDA(cudaMalloc(&ctx->d_block_cost, sizeof(unsigned) * (size_t)total));
         RTDS_CUDA(cudaMalloc(&ctx->d_block_order, sizeof(int) * (size_t)total));
+        if (!ctx->d_heavy_list) RTDS_CUDA(cudaMalloc(&ctx->d_heavy_list, sizeof(int) * LPT_SPLIT_MAX));
+        if (ctx->d_block_skip) cudaFree(ctx->d_block_skip);
+        ctx->d_block_skip = nullptr;
+        RTDS_CUDA(cudaMalloc(&ctx->d_block_skip, (size_t)total));
         ctx->block_cap = total;
         memset(ctx->block_key, 0, sizeof ctx->block_key);
     }
@@ -1648,6 +1735,8 @@ static int lpt_frame_begin(rtds_ctx* ctx, const RenderArgs& A, const void* fn, c
     if (memcmp(key, ctx->block_key, sizeof key) != 0) {
         // another geometry, banding or kernel: forget the old costs and order
         RTDS_CUDA(cudaMemsetAsync(ctx->d_block_cost, 0, sizeof(unsigned) * (size_t)total, s));
+        RTDS_CUDA(cudaMemsetAsync(ctx->d_block_skip, 0, (size_t)total, s));
+        RTDS_CUDA(cudaMemsetAsync(ctx->d_heavy_list, 0xff, sizeof(int) * LPT_SPLIT_MAX, s));
         memcpy(ctx->block_key, key, sizeof key);
         ctx->block_order_valid = false;
         ctx->lpt_phase = 0; ctx->lpt_use = true; ctx->lpt_ms_base = ctx->lpt_ms_order = 0.f;
@@ -1674,10 +1763,12 @@ static void lpt_frame_timed(rtds_ctx* ctx, float ms_kernel, bool was_lpt_frame, 
 // ... per launch: the band's slice of the two arrays
 static void lpt_band_args(rtds_ctx* ctx, RenderArgs& A, const LptBands& bands, int band)
 {
-    A.order = nullptr; A.cost = nullptr;
+    A.order = nullptr; A.cost = nullptr; A.skip = nullptr; A.heavy_list = nullptr;
     if (!ctx->lpt_active) return;
     const bool use = ctx->opt.lpt >= 2 || (ctx->lpt_phase < LPT_TRIAL_FRAMES ? (ctx->lpt_phase & 1) != 0 : ctx->lpt_use);
     if (ctx->block_order_valid && use) A.order = ctx->d_block_order + bands.off[band];
+    // lpt_split: single-band frames of the plain packet kernel only (the caller checks the kernel and launches render_heavy_kernel)
+    if (A.order && bands.n_bands == 1 && ctx->opt.lpt_split > 0) { A.skip = ctx->d_block_skip; A.heavy_list = ctx->d_heavy_list; }
     ctx->lpt_last_used_order = A.order != nullptr;
     A.cost = ctx->d_block_cost + bands.off[band];
 }
@@ -1690,7 +1781,8 @@ static int lpt_frame_end(rtds_ctx* ctx, const LptBands& bands, cudaStream_t s)
     RTDS_CUDA(cudaEventRecord(ctx->ev_order_go, s));
     RTDS_CUDA(cudaStreamWaitEvent(ctx->jit_stream, ctx->ev_order_go, 0));
     block_order_kernel<<<bands.n_bands, 1024, 0, ctx->jit_stream>>>(ctx->d_block_cost, ctx->d_block_order, bands,
-                                                                    std::max(32, ctx->sm_count * 3 / bands.n_bands));
+                                                                    std::max(32, ctx->sm_count * 3 / bands.n_bands), ctx->d_heavy_list, ctx->d_block_skip,
+                                                                    bands.n_bands == 1 ? std::max(0, std::min(LPT_SPLIT_MAX, ctx->opt.lpt_split)) : 0);
     RTDS_CUDA(cudaGetLastError());
     RTDS_CUDA(cudaEventRecord(ctx->ev_order_done, ctx->jit_stream));
     ctx->block_order_valid = true;
@@ -1737,7 +1829,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
     A.out_vec8 = (((uintptr_t)d_rgb_rows & 7) == 0 && W % 8 == 0) ? 1 : 0;
     A.block_order = ctx->opt.block_order;
     A.counters = ctx->d_counters;
-    A.order = nullptr; A.cost = nullptr;
+    A.order = nullptr; A.cost = nullptr; A.skip = nullptr; A.heavy_list = nullptr;
 
     cudaStream_t s = ctx->stream;
     int launches = 0;
@@ -1888,8 +1980,21 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             const dim3 block(render_threads(fn));
             const unsigned lin = render_grid(ctx, fn, W, r1 - r0);
             lpt_band_args(ctx, A, lb, bi);
+            // lpt_split: only the plain packet kernel (no shadow rays, no materials) hands tiles over
+            const bool split = A.skip != nullptr && (fn == (const void*)render_packet_kernel<false, true> || fn == (const void*)render_packet_kernel<false, false>);
+            if (!split) { A.skip = nullptr; A.heavy_list = nullptr; }
             void* kargs[] = {(void*)&A};
+            if (split) {
+                RTDS_TRY(rtds_ensure_band_streams(ctx));
+                cudaStream_t hs = ctx->band_streams[0];                // highest priority: its blocks are placed first
+                RTDS_CUDA(cudaEventRecord(ctx->ev_ready, s));
+                RTDS_CUDA(cudaStreamWaitEvent(hs, ctx->ev_ready, 0));
+                RTDS_CUDA(cudaLaunchKernel((const void*)render_heavy_kernel, dim3(4 * LPT_SPLIT_MAX), dim3(128), kargs, 0, hs));
+                RTDS_CUDA(cudaEventRecord(ctx->ev_bands[0], hs));
+                launches += 1;
+            }
             RTDS_CUDA(cudaLaunchKernel(fn, dim3(lin), block, kargs, 0, s));
+            if (split) RTDS_CUDA(cudaStreamWaitEvent(s, ctx->ev_bands[0], 0));
             if (wave) {       // ... followed by the band's shadow rays and shading, one thread per sample
                 int tw, th;
                 wave_tile(spp, tw, th);

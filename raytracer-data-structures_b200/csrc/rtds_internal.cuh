@@ -150,6 +150,8 @@ struct RtdsOptions {
                              //                   Measured: node visits halve, kernels -1 ... -8 %: opt-in
     int node_preorder = 0;   // RTDS_NODE_ORDER=preorder: renumber the nodes in DFS pre-order after the build
     int l2_prefetch = 0;     // RTDS_L2_PREFETCH  stream the tree into L2 on a side stream while the directions are generated
+    int lpt_split = 128;     // RTDS_LPT_SPLIT    with a learned order in use (lpt): that many of the heaviest 16 x 8 tiles of the packet kernel are rendered by
+                             //                   render_heavy_kernel instead, one ray per thread (4 blocks per tile): a straggler's chain of leaf tests is cut in four. 0 = off
     int lpt = 1;             // RTDS_LPT          the previous frame's heaviest blocks are launched first: 1 = where the library measures a gain, 2 = always, 0 = never
     int frame_graph = 0;     // RTDS_FRAME_GRAPH  device-buffer / shared-frame renders: one CUDA graph launch per frame (measured: no gain)
 };
@@ -230,6 +232,8 @@ struct rtds_ctx {
     // lpt option: per-block costs of the last frame and the launch order derived from them, band by band (render.cu: block_order_kernel)
     unsigned*   d_block_cost = nullptr;
     int*        d_block_order = nullptr;
+    int*        d_heavy_list = nullptr;   // [LPT_SPLIT_MAX] tiles handed to render_heavy_kernel next frame (-1: unused)
+    unsigned char* d_block_skip = nullptr; // [block_cap] 1 = the packet kernel leaves this tile to render_heavy_kernel
     int         block_cap = 0;
     uint64_t    block_key[5] = {0, 0, 0, 0, 0};   // geometry + kernel the buffers belong to
     bool        block_order_valid = false;

@@ -1,2 +1,4 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_render.py -q -m gpu --timeout 120 -x -k "grazing" 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_gpu_render.py tests/test_gpu_shared_frame.py tests/test_gpu_materials.py -q -m gpu --timeout 120 -x 2>&1 | tail -6
+for w in 8 4; do echo "== world $w auto"; WORLD=$w ITERS=16 timeout 600 python tools/ab_frame.py lpt=0,1 2>&1 | cut -c1-230 | tail -2; done
+WORKLOAD=config4 WORLD=8 ITERS=14 timeout 600 python tools/ab_frame.py lpt=0,1 2>&1 | cut -c1-230 | tail -2

@@ -105,7 +105,7 @@ def main():
     dbuf = C.c_void_p()
     cudart = C.CDLL("libcudart.so")
     assert cudart.cudaMalloc(C.byref(dbuf), W * H * 3) == 0
-    ctx.set_option("lpt", 2)
+    ctx.set_option("lpt", 2)           # (lpt_split default: render_heavy_kernel takes the heaviest tiles from the second frame on)
     for graph, pf in ((0, 0), (0, 1), (1, 0), (1, 1)):
         ctx.set_option("frame_graph", graph); ctx.set_option("l2_prefetch", pf)
         for rep in range(3):
