@@ -134,7 +134,7 @@ constexpr int LPT_SPLIT_MAX = 256;       // most tiles handed to render_heavy_ke
 constexpr int LPT_TRIAL_FRAMES = 6;      // lpt = 1: frames of a geometry spent comparing the two orders
 struct LptBands { int n_bands; int off[RTDS_MAX_BANDS + 1]; };      // a frame rendered as row bands: one launch (and one order) per band
 __global__ void __launch_bounds__(1024) block_order_kernel(unsigned* __restrict__ cost, int* __restrict__ order, const LptBands bands, int cap,
-                                                           int* __restrict__ heavy_list, unsigned char* __restrict__ skip, int n_split)
+                                                           int* __restrict__ heavy_list, unsigned char* __restrict__ skip, int n_split, int min_bin)
 {
     cost += bands.off[blockIdx.x]; order += bands.off[blockIdx.x]; skip += bands.off[blockIdx.x];
     const int n = bands.off[blockIdx.x + 1] - bands.off[blockIdx.x];
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(1024) block_order_kernel(unsigned* __restrict_
     __syncthreads();
     if (t == 0) {
         int tb = 32, total = 0;
-        for (int b2 = 31; b2 >= 8 && M; --b2) {          // bins >= 8: cost >= max / 4
+        for (int b2 = 31; b2 >= min_bin && M; --b2) {    // default min_bin 8: cost >= max / 4
             if (total + (int)s_hist[b2] > cap) break;
             total += (int)s_hist[b2];
             tb = b2;
@@ -1782,7 +1782,8 @@ static int lpt_frame_end(rtds_ctx* ctx, const LptBands& bands, cudaStream_t s)
     RTDS_CUDA(cudaStreamWaitEvent(ctx->jit_stream, ctx->ev_order_go, 0));
     block_order_kernel<<<bands.n_bands, 1024, 0, ctx->jit_stream>>>(ctx->d_block_cost, ctx->d_block_order, bands,
                                                                     std::max(32, ctx->sm_count * 3 / bands.n_bands), ctx->d_heavy_list, ctx->d_block_skip,
-                                                                    bands.n_bands == 1 ? std::max(0, std::min(LPT_SPLIT_MAX, ctx->opt.lpt_split)) : 0);
+                                                                    bands.n_bands == 1 ? std::max(0, std::min(LPT_SPLIT_MAX, ctx->opt.lpt_split)) : 0,
+                                                                    std::max(1, std::min(31, ctx->opt.lpt_bin)));
     RTDS_CUDA(cudaGetLastError());
     RTDS_CUDA(cudaEventRecord(ctx->ev_order_done, ctx->jit_stream));
     ctx->block_order_valid = true;
