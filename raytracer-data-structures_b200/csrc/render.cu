@@ -131,7 +131,7 @@ __device__ __forceinline__ void report_block_cost(const RenderArgs& A, int lb, u
 // One block of 1024 threads per band.
 constexpr int LPT_MAX_HEAVY = 512;
 constexpr int LPT_SPLIT_MAX = 256;       // most tiles handed to render_heavy_kernel per frame
-constexpr int LPT_TRIAL_FRAMES = 6;      // lpt = 1: frames of a geometry spent comparing the two orders
+constexpr int LPT_TRIAL_FRAMES = 6;      // lpt = 1: timed frames of a geometry spent comparing the schedules (2 or 3 modes, round robin)
 struct LptBands { int n_bands; int off[RTDS_MAX_BANDS + 1]; };      // a frame rendered as row bands: one launch (and one order) per band
 __global__ void __launch_bounds__(1024) block_order_kernel(unsigned* __restrict__ cost, int* __restrict__ order, const LptBands bands, int cap,
                                                            int* __restrict__ heavy_list, unsigned char* __restrict__ skip, int n_split, int min_bin)
@@ -1605,7 +1605,7 @@ static int render_frame_graph(rtds_ctx* ctx, const RenderArgs& A, const void* fn
     return RTDS_OK;
 }
 
-static void lpt_frame_timed(rtds_ctx* ctx, float ms_kernel, bool was_lpt_frame, bool used_order);
+static void lpt_frame_timed(rtds_ctx* ctx, float ms_kernel, bool was_lpt_frame, int mode_run);
 
 // wavefront = 1: the two forms of a frame with shadow rays give the same bytes; which is faster depends on the scene and the frame
 // (config 5 stand-in, 16 samples x 3 lights: wavefront 53.7 ms, single kernel 104.6; bunny x 30 at 4 samples, 1 light: 2.67 vs 1.96).
@@ -1650,7 +1650,7 @@ static int render_stats_out(rtds_ctx* ctx, rtds_render_stats* st, int launches, 
     st->rows = rows;
     st->reserved[0] = (int)(unsigned)c[7];      // shared frame: 1 + the rank the owner timed out on (0 = complete)
     wave_frame_timed(ctx, st->ms_kernel);
-    lpt_frame_timed(ctx, st->ms_kernel, ctx->lpt_active, ctx->lpt_last_used_order);
+    lpt_frame_timed(ctx, st->ms_kernel, ctx->lpt_active, ctx->lpt_last_mode);
     ctx->lpt_active = false;
     if (wait_copies) RTDS_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     return RTDS_OK;
@@ -1709,6 +1709,9 @@ static const void* select_render_kernel(const rtds_ctx* ctx, const RenderArgs& A
 static int lpt_frame_begin(rtds_ctx* ctx, const RenderArgs& A, const void* fn, const LptBands& bands, cudaStream_t s)
 {
     ctx->lpt_active = false;
+    // lpt_split: single-band frames of the plain packet kernel only (no shadow rays, no materials)
+    ctx->lpt_split_ok = ctx->opt.lpt_split > 0 && bands.n_bands == 1 &&
+                        (fn == (const void*)render_packet_kernel<false, true> || fn == (const void*)render_packet_kernel<false, false>);
     if (!ctx->opt.lpt) return RTDS_OK;
     const int total = bands.off[bands.n_bands];
     if (total <= 0) return RTDS_OK;
@@ -1739,42 +1742,46 @@ static int lpt_frame_begin(rtds_ctx* ctx, const RenderArgs& A, const void* fn, c
         RTDS_CUDA(cudaMemsetAsync(ctx->d_heavy_list, 0xff, sizeof(int) * LPT_SPLIT_MAX, s));
         memcpy(ctx->block_key, key, sizeof key);
         ctx->block_order_valid = false;
-        ctx->lpt_phase = 0; ctx->lpt_use = true; ctx->lpt_ms_base = ctx->lpt_ms_order = 0.f;
+        ctx->lpt_phase = 0; ctx->lpt_choice = 1; ctx->lpt_ms[0] = ctx->lpt_ms[1] = ctx->lpt_ms[2] = 0.f;
     }
     // lpt = 1: the library times both orders once per geometry (its own kernel events) and keeps the faster one; a geometry for
     // which the learned order lost stops recording costs
-    ctx->lpt_active = ctx->opt.lpt >= 2 || ctx->lpt_phase < LPT_TRIAL_FRAMES || ctx->lpt_use;
+    ctx->lpt_active = ctx->opt.lpt >= 2 || ctx->lpt_phase < LPT_TRIAL_FRAMES || ctx->lpt_choice != 0;
     return RTDS_OK;
 }
 
 // ... with the frame's kernel time known: baseline frame (launch order) -> trial frame (learned order) -> decision
-static void lpt_frame_timed(rtds_ctx* ctx, float ms_kernel, bool was_lpt_frame, bool used_order)
+// lpt = 1: which of the three schedules is fastest depends on how many waves of blocks a launch has (one GPU: launch order; 4 GPUs:
+// the learned order; 8 GPUs: the learned order with the heaviest tiles ray-per-thread - measured on real boxes), so the library
+// times them: the first LPT_TRIAL_FRAMES timed frames of a geometry cycle through the modes, the best time of each decides.
+static int lpt_trial_mode(const rtds_ctx* ctx) { return ctx->lpt_phase % (ctx->lpt_split_ok ? 3 : 2); }
+static void lpt_frame_timed(rtds_ctx* ctx, float ms_kernel, bool was_lpt_frame, int mode_run)
 {
-    // frames 0, 2, 4 of a geometry run in launch order, frames 1, 3, 5 in the learned order; the best time of each decides (the
-    // very first frames of a process are slow for reasons of their own)
     if (!was_lpt_frame || ctx->opt.lpt != 1 || ctx->lpt_phase >= LPT_TRIAL_FRAMES || !(ms_kernel > 0.f)) return;
-    const bool trial = (ctx->lpt_phase & 1) != 0;
-    if (trial != used_order) return;                       // (no order yet: the frame counts as nothing)
-    float& best = trial ? ctx->lpt_ms_order : ctx->lpt_ms_base;
+    const int mode = lpt_trial_mode(ctx);
+    if (mode != mode_run) return;                          // (no order yet, or not a frame the split applies to: counts as nothing...
+    float& best = ctx->lpt_ms[mode];
     best = best > 0.f ? std::min(best, ms_kernel) : ms_kernel;
-    if (++ctx->lpt_phase == LPT_TRIAL_FRAMES) ctx->lpt_use = ctx->lpt_ms_order < 0.997f * ctx->lpt_ms_base;
+    if (++ctx->lpt_phase == LPT_TRIAL_FRAMES) {
+        ctx->lpt_choice = 0;
+        float t = ctx->lpt_ms[0];
+        for (int m = 1; m < 3; ++m)
+            if (ctx->lpt_ms[m] > 0.f && ctx->lpt_ms[m] < 0.997f * t) { t = ctx->lpt_ms[m]; ctx->lpt_choice = m; }
+    }
 }
 
 // ... per launch: the band's slice of the two arrays
 static void lpt_band_args(rtds_ctx* ctx, RenderArgs& A, const LptBands& bands, int band)
 {
     A.order = nullptr; A.cost = nullptr; A.skip = nullptr; A.heavy_list = nullptr;
+    ctx->lpt_last_mode = 0;
     if (!ctx->lpt_active) return;
-    const bool use = ctx->opt.lpt >= 2 || (ctx->lpt_phase < LPT_TRIAL_FRAMES ? (ctx->lpt_phase & 1) != 0 : ctx->lpt_use);
-    if (ctx->block_order_valid && use) A.order = ctx->d_block_order + bands.off[band];
-    // lpt_split: single-band frames of the plain packet kernel only (the caller checks the kernel and launches render_heavy_kernel)
-    if (A.order && bands.n_bands == 1 && ctx->opt.lpt_split > 0) { A.skip = ctx->d_block_skip; A.heavy_list = ctx->d_heavy_list; }
-    ctx->lpt_last_used_order = A.order != nullptr;
+    const int mode = ctx->opt.lpt >= 2 ? (ctx->lpt_split_ok ? 2 : 1) : (ctx->lpt_phase < LPT_TRIAL_FRAMES ? lpt_trial_mode(ctx) : ctx->lpt_choice);
+    if (ctx->block_order_valid && mode >= 1) A.order = ctx->d_block_order + bands.off[band];
+    if (A.order && mode == 2 && ctx->lpt_split_ok) { A.skip = ctx->d_block_skip; A.heavy_list = ctx->d_heavy_list; }
+    ctx->lpt_last_mode = A.order ? (A.skip ? 2 : 1) : 0;
     A.cost = ctx->d_block_cost + bands.off[band];
 }
-
-// ... and behind the frame's render kernels (`s` has joined every band): the side stream turns this frame's costs into the next
-// frame's order
 static int lpt_frame_end(rtds_ctx* ctx, const LptBands& bands, cudaStream_t s)
 {
     if (!ctx->lpt_active) return RTDS_OK;
@@ -1981,9 +1988,7 @@ int rtds_render_impl(rtds_ctx* ctx, int acc, const rtds_render_params* p, uint8_
             const dim3 block(render_threads(fn));
             const unsigned lin = render_grid(ctx, fn, W, r1 - r0);
             lpt_band_args(ctx, A, lb, bi);
-            // lpt_split: only the plain packet kernel (no shadow rays, no materials) hands tiles over
-            const bool split = A.skip != nullptr && (fn == (const void*)render_packet_kernel<false, true> || fn == (const void*)render_packet_kernel<false, false>);
-            if (!split) { A.skip = nullptr; A.heavy_list = nullptr; }
+            const bool split = A.skip != nullptr;      // lpt_split: render_heavy_kernel takes the flagged tiles
             void* kargs[] = {(void*)&A};
             if (split) {
                 RTDS_TRY(rtds_ensure_band_streams(ctx));

@@ -239,10 +239,12 @@ struct rtds_ctx {
     uint64_t    block_key[5] = {0, 0, 0, 0, 0};   // geometry + kernel the buffers belong to
     bool        block_order_valid = false;
     bool        lpt_active = false;       // between lpt_frame_begin and lpt_frame_end of the current frame
-    int         lpt_phase = 0;            // frames of this geometry timed so far: even = launch order, odd = learned order; 6 = decided
-    bool        lpt_use = true;           // phase 2: the learned order was faster for this geometry
-    float       lpt_ms_base = 0.f, lpt_ms_order = 0.f;
-    bool        lpt_last_used_order = false;
+    int         lpt_phase = 0;            // frames of this geometry timed so far, cycling through the modes (0 launch order, 1 learned order,
+                                          // 2 learned order + heaviest tiles ray-per-thread); LPT_TRIAL_FRAMES = decided
+    int         lpt_choice = 1;           // the fastest mode for this geometry once decided
+    float       lpt_ms[3] = {0.f, 0.f, 0.f};   // best kernel time seen per mode during the trial
+    bool        lpt_split_ok = false;     // this frame's kernel and banding allow the ray-per-thread hand-over (plain packet kernel, one band)
+    int         lpt_last_mode = 0;        // what the current frame actually ran (mode 1 / 2 need an order from an earlier frame)
     // wavefront = 1: which form of a frame with shadow rays is faster, measured once per frame geometry (render.cu, wave_choose)
     uint64_t    wave_key[4] = {0, 0, 0, 0};
     int         wave_phase = 0;

@@ -1,2 +1,3 @@
 set -x
-for b in 8 4 2; do for sp in 128 256; do echo "== lpt_bin=$b split=$sp"; RTDS_LPT_BIN=$b RTDS_LPT_SPLIT=$sp WORLD=8 ITERS=14 timeout 600 python tools/ab_frame.py lpt=2 2>&1 | cut -c1-230 | tail -1; done; done
+timeout 900 python -m pytest tests/test_gpu_render.py tests/test_gpu_shared_frame.py -q -m gpu --timeout 120 -x 2>&1 | tail -4
+for w in 8 4 2 1; do echo "== world $w auto"; WORLD=$w ITERS=16 timeout 600 python tools/ab_frame.py lpt=0,1 2>&1 | cut -c1-230 | tail -2; done
