@@ -153,7 +153,8 @@ struct RtdsOptions {
     int lpt_bin = 8;         // RTDS_LPT_BIN      a block counts as heavy when its cost is >= lpt_bin / 32 of the frame's largest block cost
     int lpt_split = 128;     // RTDS_LPT_SPLIT    with a learned order in use (lpt): that many of the heaviest 16 x 8 tiles of the packet kernel are rendered by
                              //                   render_heavy_kernel instead, one ray per thread (4 blocks per tile): a straggler's chain of leaf tests is cut in four. 0 = off
-    int lpt = 1;             // RTDS_LPT          the previous frame's heaviest blocks are launched first: 1 = where the library measures a gain, 2 = always, 0 = never
+    int lpt = 1;             // RTDS_LPT          the previous frame's heaviest blocks are launched first (and, lpt_split, the very heaviest rendered ray-per-thread):
+                             //                   1 = the library times the schedules per frame geometry and keeps the fastest, 2 = always, 0 = never
     int frame_graph = 0;     // RTDS_FRAME_GRAPH  device-buffer / shared-frame renders: one CUDA graph launch per frame (measured: no gain)
 };
 typedef int RtdsOptions::*RtdsOptionField;
