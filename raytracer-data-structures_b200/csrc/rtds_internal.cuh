@@ -135,7 +135,8 @@ struct FrameGraph {
 struct RtdsOptions {
     int block_order = 2;     // RTDS_BLOCK_ORDER  0 quadrant-major, 1 row-major, 2 quadrant-major from the centre rows outwards
     int strip = 0;           // RTDS_STRIP        1: fused jitter + render strip kernel (measured slower; parity-tested)
-    int bands = 4;           // RTDS_BANDS        row bands of a host-buffer render (download overlapped with rendering)
+    int bands = 6;           // RTDS_BANDS        row bands of a host-buffer render (each band's download overlaps the rendering of the next ones).
+                             //                   Measured end to end on the bench frame (round 2 final kernels): 3 1.898, 4 1.897-1.913, 5 1.888, 6 1.837-1.850, 7 1.868, 8 1.883 ms
     int band_ratio = 100;    // RTDS_BAND_RATIO   each band's share of the one before it, percent
     int packet = 1;          // RTDS_PACKET       0: never the packet kernels
     int wavefront = 1;       // RTDS_WAVEFRONT    frames with shadow rays (aa_samples % 4 == 0) as two kernels (primary packets; shadow rays + shading per sample):
