@@ -342,10 +342,7 @@ __device__ __forceinline__ void traverse_fast_loop(const BvhView& B, float ox, f
     // a subtree is opened only while its entry distance is <= tlim (kept widened by 2^-20, see above)
     float tlim = ANYHIT ? sqrtf(t2max) + margin : tnear + margin;
     tlim = __fmaf_rn(fabsf(tlim), WIDE2, tlim);
-    // {child ref, entry distance as bits}: one 8-byte local store / load per push / pop. Any-hit rays keep the bound they start
-    // with (the distance to the light), so what was accepted at push time is still wanted at pop time: 4-byte entries, no re-test
-    int2 stack[ANYHIT ? 1 : STACK_MAX];
-    int stack_ref[ANYHIT ? STACK_MAX : 1];
+    int2 stack[STACK_MAX];        // {child ref, entry distance as bits}: one 8-byte local store / load per push / pop
     int sp = 0;
     int node = 0;
     unsigned visits = 0;
@@ -380,8 +377,7 @@ __device__ __forceinline__ void traverse_fast_loop(const BvhView& B, float ox, f
             const bool hitR = tminR <= fminf(tmaxR, tlim) && tmaxR >= neg_margin;
             if (hitL && hitR) {
                 const bool rfirst = tminR < tminL;
-                if (ANYHIT) stack_ref[sp] = rfirst ? ch.x : ch.y;
-                else stack[sp] = make_int2(rfirst ? ch.x : ch.y, __float_as_int(rfirst ? tminL : tminR));
+                stack[sp] = make_int2(rfirst ? ch.x : ch.y, __float_as_int(rfirst ? tminL : tminR));
                 sp = min(sp + 1, STACK_MAX - 1);
                 node = rfirst ? ch.y : ch.x;
                 continue;
@@ -428,17 +424,13 @@ __device__ __forceinline__ void traverse_fast_loop(const BvhView& B, float ox, f
         }
         // pop
         bool found = false;
-        if (ANYHIT) {
-            if (sp > 0) { node = stack_ref[--sp]; found = true; }
-        } else {
-            while (sp > 0) {
-                --sp;
-                const int2 e = stack[sp];
-                if (__int_as_float(e.y) > tlim) continue;
-                node = e.x;
-                found = true;
-                break;
-            }
+        while (sp > 0) {
+            --sp;
+            const int2 e = stack[sp];
+            if (__int_as_float(e.y) > tlim) continue;
+            node = e.x;
+            found = true;
+            break;
         }
         if (!found) break;
     }
