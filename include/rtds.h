@@ -157,7 +157,7 @@ int rtds_destroy(rtds_ctx* ctx);
  * knobs the reference does not have). Every switch has an RTDS_<NAME> environment variable that sets its default; the
  * environment is read ONCE, in rtds_create, never while rendering. Names: block_order, strip, bands, band_ratio, packet,
  * wavefront, hull, zerocopy, trace_frame, median_small, median_coop, median_debug, node_preorder, wide, l2_prefetch,
- * frame_graph, lpt, lpt_split, lpt_bin. Unknown name -> RTDS_ERR_INVALID. No switch changes a result: they select between
+ * frame_graph, lpt, lpt_split, lpt_bin, lpt_cap. Unknown name -> RTDS_ERR_INVALID. No switch changes a result: they select between
  * kernels that are tested to produce identical frames. */
 int rtds_set_option(rtds_ctx* ctx, const char* name, int value);
 int rtds_get_option(rtds_ctx* ctx, const char* name, int* value);

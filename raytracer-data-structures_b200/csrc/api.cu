@@ -18,7 +18,7 @@ const RtdsOptionName g_rtds_option_names[] = {
     {"median_small", "RTDS_MEDIAN_SMALL", &RtdsOptions::median_small}, {"median_coop", "RTDS_MEDIAN_COOP", &RtdsOptions::median_coop},
     {"median_debug", "RTDS_MEDIAN_DEBUG", &RtdsOptions::median_debug}, {"node_preorder", "RTDS_NODE_PREORDER", &RtdsOptions::node_preorder}, {"wide", "RTDS_WIDE", &RtdsOptions::wide},
     {"l2_prefetch", "RTDS_L2_PREFETCH", &RtdsOptions::l2_prefetch}, {"frame_graph", "RTDS_FRAME_GRAPH", &RtdsOptions::frame_graph},
-    {"lpt", "RTDS_LPT", &RtdsOptions::lpt}, {"lpt_split", "RTDS_LPT_SPLIT", &RtdsOptions::lpt_split}, {"lpt_bin", "RTDS_LPT_BIN", &RtdsOptions::lpt_bin},
+    {"lpt", "RTDS_LPT", &RtdsOptions::lpt}, {"lpt_split", "RTDS_LPT_SPLIT", &RtdsOptions::lpt_split}, {"lpt_bin", "RTDS_LPT_BIN", &RtdsOptions::lpt_bin}, {"lpt_cap", "RTDS_LPT_CAP", &RtdsOptions::lpt_cap},
 };
 const int g_rtds_n_option_names = (int)(sizeof g_rtds_option_names / sizeof g_rtds_option_names[0]);
 

@@ -129,7 +129,7 @@ __device__ __forceinline__ void report_block_cost(const RenderArgs& A, int lb, u
 // straggler in the first wave, few enough to leave the octant-coherent launch order of everything else alone (with 2 % of a
 // 64,800-block frame moved to the front the frame got 2 % SLOWER: an SM full of heavy blocks of all four octants). Clears cost.
 // One block of 1024 threads per band.
-constexpr int LPT_MAX_HEAVY = 512;
+constexpr int LPT_MAX_HEAVY = 1024;
 constexpr int LPT_SPLIT_MAX = 256;       // most tiles handed to render_heavy_kernel per frame
 constexpr int LPT_TRIAL_FRAMES = 6;      // lpt = 1: timed frames of a geometry spent comparing the schedules (2 or 3 modes, round robin)
 struct LptBands { int n_bands; int off[RTDS_MAX_BANDS + 1]; };      // a frame rendered as row bands: one launch (and one order) per band
@@ -1788,7 +1788,7 @@ static int lpt_frame_end(rtds_ctx* ctx, const LptBands& bands, cudaStream_t s)
     RTDS_CUDA(cudaEventRecord(ctx->ev_order_go, s));
     RTDS_CUDA(cudaStreamWaitEvent(ctx->jit_stream, ctx->ev_order_go, 0));
     block_order_kernel<<<bands.n_bands, 1024, 0, ctx->jit_stream>>>(ctx->d_block_cost, ctx->d_block_order, bands,
-                                                                    std::max(32, ctx->sm_count * 3 / bands.n_bands), ctx->d_heavy_list, ctx->d_block_skip,
+                                                                    std::max(32, ctx->sm_count * std::max(1, ctx->opt.lpt_cap) / bands.n_bands), ctx->d_heavy_list, ctx->d_block_skip,
                                                                     bands.n_bands == 1 ? std::max(0, std::min(LPT_SPLIT_MAX, ctx->opt.lpt_split)) : 0,
                                                                     std::max(1, std::min(31, ctx->opt.lpt_bin)));
     RTDS_CUDA(cudaGetLastError());

@@ -151,6 +151,7 @@ struct RtdsOptions {
                              //                   Measured: node visits halve, kernels -1 ... -8 %: opt-in
     int node_preorder = 0;   // RTDS_NODE_ORDER=preorder: renumber the nodes in DFS pre-order after the build
     int l2_prefetch = 0;     // RTDS_L2_PREFETCH  stream the tree into L2 on a side stream while the directions are generated
+    int lpt_cap = 3;         // RTDS_LPT_CAP      at most lpt_cap x (number of SMs) blocks of a launch count as heavy (and go first, sorted by cost)
     int lpt_bin = 8;         // RTDS_LPT_BIN      a block counts as heavy when its cost is >= lpt_bin / 32 of the frame's largest block cost
     int lpt_split = 128;     // RTDS_LPT_SPLIT    with a learned order in use (lpt): that many of the heaviest 16 x 8 tiles of the packet kernel are rendered by
                              //                   render_heavy_kernel instead, one ray per thread (4 blocks per tile): a straggler's chain of leaf tests is cut in four. 0 = off
