@@ -478,8 +478,7 @@ def run_ours(args):
     # host's memory system; then the same C-ABI calls on device-resident tables: rtds_set_spheres_device + rtds_build + rtds_render
     # (own tiles straight into the shared host frame).
     if world > 1:
-        per = (n + world - 1) // world
-        lo_i, hi_i = min(n, rank * per), min(n, (rank + 1) * per)
+        per, lo_i, hi_i = rt.scene_slice(n, rank, world)
         d_sph_full = torch.zeros((per * world, 4), dtype=torch.float32, device=dev)
         d_mat_full = torch.zeros((per * world, 4), dtype=torch.float32, device=dev)
         d_sph_part = torch.zeros((per, 4), dtype=torch.float32, device=dev)
@@ -489,8 +488,8 @@ def run_ours(args):
         ctx.prepare_frame(e2e_params)            # the ray directions are generated while the scene travels
         d_sph_part[: hi_i - lo_i].copy_(sph_pin[lo_i:hi_i], non_blocking=True)
         d_mat_part[: hi_i - lo_i].copy_(mat_pin[lo_i:hi_i], non_blocking=True)
-        dist.all_gather_into_tensor(d_sph_full, d_sph_part)
-        dist.all_gather_into_tensor(d_mat_full, d_mat_part)
+        rt.exchange_scene(d_sph_part, d_sph_full)
+        rt.exchange_scene(d_mat_part, d_mat_full)
         torch.cuda.current_stream().synchronize()
         ctx.set_spheres_device(d_sph_full.data_ptr(), d_mat_full.data_ptr(), n)
         ctx.build(wl.acc, mode=wl.mode, **wl.build_kw)

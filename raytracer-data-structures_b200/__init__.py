@@ -416,6 +416,23 @@ def parse_obj_vertices(path):
 # multi-GPU plumbing: the framebuffer gather (the path's only collective). torch.distributed is plumbing here —
 # NCCL over NVLink on GPUs, gloo in the CPU tests.
 # ------------------------------------------------------------------------------------------------------
+def scene_slice(n, rank, world):
+    """The part of an n-row scene table rank uploads when the ranks exchange the scene among themselves (bench.py, N >= 2):
+    (rows per rank in the exchange buffer, first row, one past the last row). Every row belongs to exactly one rank; the last
+    ranks may own fewer rows (or none)."""
+    per = (n + world - 1) // world
+    return per, min(n, rank * per), min(n, (rank + 1) * per)
+
+
+def exchange_scene(part, full, group=None):
+    """All-gather of the per-rank parts of a scene table (one padded [per, 4] float32 tensor per rank) into `full`
+    ([per * world, 4]; its first n rows are the table). The one collective of the path - NCCL over NVLink on GPUs, gloo in the CPU
+    tests."""
+    import torch.distributed as dist
+    dist.all_gather_into_tensor(full, part, group=group)
+    return full
+
+
 def gather_frame(local_rows, height, width, tile_rows, rank, world, dst=0, scratch=None):
     """local_rows: uint8 tensor [>= rows_for_rank, width, 3] holding this rank's rows compactly (local tile j = global
     tile j*world + rank). Returns the assembled [height, width, 3] frame on `dst` (None elsewhere)."""
