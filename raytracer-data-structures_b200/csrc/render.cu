@@ -1684,9 +1684,10 @@ static const void* select_render_kernel(const rtds_ctx* ctx, const RenderArgs& A
     bool packet = !kdt && !brute && !p->exact && A.spp % PK == 0 && A.bvh.leaf_box_prim && A.shade.max_depth >= 1;
     packet = packet && ctx->opt.packet != 0;
     // scenes with REFLECTION_AND_REFRACTION / REFLECTION primitives, no shadow rays: the primary rays still go as packets, a ray
-    // that hits such a primitive continues through castRay's material branches on its own. WITH shadow rays the single-ray castRay
-    // kernel stays (measured on config 5, 3 shadowed lights, 16 spp: packets 115.9 ms vs 109.7 ms - the shadow rays are 2/3 of
-    // the rays there and stay single either way, and the out-of-line shading costs more than the shared primary visits save)
+    // that hits such a primitive continues through castRay's material branches on its own. WITH shadow rays and materials the
+    // single-kernel form is the one-ray-at-a-time castRay kernel (config 5: packets inside ONE kernel 115.9 vs 109.7 ms - the shadow
+    // rays are 2/3 of the rays and stay single either way); what such frames normally run is the wavefront form (K10c, chosen by
+    // the caller before this function is asked: 47.6 ms)
     if (packet && ctx->has_materials && !p->shadows) return (const void*)render_packet_kernel<false, true, true>;
     if (ctx->has_materials) packet = false;
     // interior boxes tested once per packet against the hull of the four reciprocal directions (default; hull option 0:
